@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py — log-posterior evals/s in (sample x datapoint) units on N B200s of one node.
+
+A "step" is one batched log-posterior evaluation (the hot call, ssi_logpost_batch) over B
+subspace points per GPU on the full synthetic dataset:
+    W = W_swa + P z  ->  Dense-chain forward over all N datapoints  ->  Gaussian log-lik -> lp[b]
+Workloads (BASELINE.json configs):
+    wide  784-1024-1024-10 relu, N=60000, M=20  (configs[2]/[4]; default, the config the metric's
+          1/2/4/8-GPU sweep is quoted on; B per GPU fixed => weak scaling)
+    uci   13-50-1 relu, N=10000, M=5, 4096 chains (configs[1])
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload wide|uci] [--batch B]
+  python bench.py --impl reference ...      # the CPU restatement of the reference's path
+
+`value` is timed with CUDA events with Z already resident in HBM; `e2e` goes through the
+reference-facing host call (host Z in pinned memory -> H2D -> kernels -> D2H of lp) every step.
+Multi-GPU: proposals are sharded across ranks (no data-path collective); lp is all-gathered
+(NCCL) inside the step, as the sampler needs it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (oracle problem name, default B per GPU, sigma_m, z scale)
+    "wide": ("wide", 4096, 1.0, 0.1),
+    "uci": ("uci", 4096, 0.1, 0.1),
+}
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self._stop, self._t = gpu_index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        pw = [float(r[3]) for r in self.rows if r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "power_w_max": max(pw) if pw else None, "samples": len(self.rows)}
+
+
+def cpu_reference(workload: str, budget_s: float, steps: int = 1, warmup: int = 0):
+    """The reference's CPU path restated (oracle/ssi_oracle.py): one z per call, Float64,
+    per-layer BLAS GEMM over the full dataset, all host cores.  Bounded sample."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import ssi_oracle as orc
+    name, _, sigma_m, zs = WORKLOADS[workload]
+    prob = orc.make_problem(name)
+    rng = np.random.default_rng(0)
+    X64, Y64 = prob.X.astype(np.float64), prob.Y.astype(np.float64)
+    prob64 = orc.Problem(prob.dims, prob.acts, X64, Y64, prob.W_swa, prob.P)
+    z = zs * rng.standard_normal(prob.M)
+    orc.density(prob64, z, sigma_m)                        # warm-up (BLAS threads, page faults)
+    t0 = time.perf_counter()
+    orc.density(prob64, z, sigma_m)
+    per_eval = time.perf_counter() - t0
+    evals_per_step = max(1, int(budget_s / max(per_eval, 1e-6) / max(1, steps + warmup)))
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        for _ in range(evals_per_step):
+            z = zs * rng.standard_normal(prob.M)
+            orc.density(prob64, z, sigma_m)
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    units = evals_per_step * len(times) * prob.N
+    try:
+        from threadpoolctl import threadpool_info
+        blas_threads = max([i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"] or [1])
+    except Exception:
+        blas_threads = os.cpu_count()
+    return {"value": units / total, "unit": "sample*datapoint/s", "cores": int(blas_threads), "kind": "port",
+            "sample": f"{evals_per_step * len(times)} sequential density(z) evaluations (one z per call, Float64 NumPy/OpenBLAS, "
+                      f"full N={prob.N}) of workload {workload}; lower bound on the reference's time (no Flux.destructure/alloc overhead)",
+            "ms_per_step": 1e3 * total / len(times), "evals_per_step": evals_per_step, "host_cpus": os.cpu_count()}
+
+
+def workload_config(workload, B, world):
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import ssi_oracle as orc
+    name = WORKLOADS[workload][0]
+    dims = {"wide": (784, 1024, 1024, 10), "uci": (13, 50, 1)}[name]
+    N = {"wide": 60000, "uci": 10000}[name]
+    M = {"wide": 20, "uci": 5}[name]
+    return {"workload": f"{workload}: MLP {'-'.join(map(str, dims))}, N={N}, M={M}, batched log-posterior over {B} subspace points per GPU",
+            "dims": list(dims), "N": N, "M": M, "batch_per_gpu": B, "global_batch": B * world,
+            "parallelism": f"proposals sharded x{world}, W_swa/P/X/Y replicated, NCCL all-gather of lp",
+            "l2": "inputs larger than L2 (X + per-sample activations stream through HBM); no explicit flush"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    res = cpu_reference(args.workload, budget_s=max(10.0, 8.0 * (args.steps + args.warmup)), steps=args.steps, warmup=args.warmup)
+    cfg = workload_config(args.workload, args.batch, world)
+    line = {"impl": "reference", "metric": "log-posterior evals/sec (samples x datapoints)", "value": res["value"],
+            "unit": "sample*datapoint/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": "sample*datapoint/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("SSI_BENCH_WORKLOAD", "wide"), choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="subspace points per GPU per step")
+    ap.add_argument("--path", default="auto", choices=["auto", "fused", "layered", "tensor"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.batch <= 0:
+        args.batch = int(os.environ.get("SSI_BENCH_BATCH", WORKLOADS[args.workload][1]))
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import ssi_oracle as orc
+    import subspaceinference_jl_b200 as ssi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    name, _, sigma_m, zs = WORKLOADS[args.workload]
+    prob = orc.make_problem(name)
+    B = args.batch
+    eng = ssi.Engine(local_rank)
+    eng.set_model(prob.dims, prob.acts)
+    eng.set_data(prob.X, prob.Y)
+    eng.set_subspace(prob.W_swa, prob.P)
+    eng.set_option("path", {"auto": 0, "fused": 1, "layered": 2, "tensor": 3}[args.path])
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+
+    # this rank's shard of the global proposal batch (global ids rank*B .. rank*B+B-1)
+    rng = np.random.default_rng(31337 + rank)
+    Z_host = torch.from_numpy((zs * rng.standard_normal((B, prob.M))).astype(np.float32)).pin_memory()   # (B, M) row-major == M x B col-major
+    lp_host = torch.empty(B, dtype=torch.float64).pin_memory()
+    dZ = Z_host.to(dev)
+    d_lp = torch.empty(B, dtype=torch.float64, device=dev)
+    d_lp_all = torch.empty(B * world, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step_device():
+        eng.logpost_dev(dZ.data_ptr(), B, d_lp.data_ptr(), sigma_m=sigma_m)
+        if world > 1:
+            dist.all_gather_into_tensor(d_lp_all, d_lp)
+
+    def step_e2e():
+        dZ.copy_(Z_host, non_blocking=True)
+        eng.logpost_dev(dZ.data_ptr(), B, d_lp.data_ptr(), sigma_m=sigma_m)
+        if world > 1:
+            dist.all_gather_into_tensor(d_lp_all, d_lp)
+        lp_host.copy_(d_lp, non_blocking=True)
+        stream.synchronize()          # the caller consumes lp every step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_device()
+    launches0 = eng.stats().kernel_launches
+    with ClockSampler(local_rank) as clk:
+        ms_dev = timed(step_device, args.steps)
+    launches = eng.stats().kernel_launches - launches0
+    path_used = ssi.PATH_NAMES[eng.stats().last_path]
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # sanity: the timed path produced the oracle's numbers (one sample, checked after timing)
+    if rank == 0:
+        ref = orc.density(prob, Z_host[0].numpy().astype(np.float64), sigma_m)
+        got = float(lp_host[0])
+        if not np.isfinite(got) or abs(got - ref) > 1e-5 * abs(ref):
+            raise SystemExit(f"bench result mismatch vs oracle: {got} vs {ref}")
+
+    if rank == 0:
+        peaks = load_peaks()
+        units_step = float(B) * world * prob.N
+        flops_unit = 2.0 * sum(a * b for a, b in zip(prob.dims[:-1], prob.dims[1:])) + 2.0 * orc.n_params(prob.dims) * prob.M / prob.N
+        value = units_step * args.steps / (ms_dev * 1e-3)
+        e2e = units_step * args.steps / (ms_e2e * 1e-3)
+        per_gpu_flops = flops_unit * B * prob.N * args.steps / (ms_dev * 1e-3)
+        peak_tf = peaks["bf16_tflops_sustained"]
+        line = {
+            "metric": "log-posterior evals/sec (samples x datapoints)", "value": value, "unit": "sample*datapoint/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, B, world),
+            "path": path_used,
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e, "unit": "sample*datapoint/s", "h2d_bytes_per_step": int(Z_host.numel() * 4),
+                    "d2h_bytes_per_step": int(lp_host.numel() * 8), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": per_gpu_flops / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": per_gpu_flops / 1e12 / peak_tf, "traffic": None,
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
+                         "flops_per_unit": flops_unit, "per": "GPU",
+                         "note": "algorithmic FP32 flops (padding and split-precision re-issue not counted)"},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cb = cpu_reference(args.workload, budget_s=15.0)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,152 @@
+/*
+ * ssi.h — C ABI of the B200-native subspace log-posterior library (libssi.so).
+ *
+ * The reference (efmanu/SubspaceInference.jl) has no FFI seam: its hot path is an
+ * inline Julia closure.  This header defines the seam at exactly the two cut points
+ * SURVEY.md 8(b) names, so that the Julia functions above it keep their signatures
+ * and reach CUDA only through `ccall` (see INTEGRATION.md for the Julia stubs):
+ *
+ *   - density(z) closure + the RWMH sampler loop   src/space_inference.jl:90-95, :108-116, :125
+ *   - SWA moments / deviation matrix / psvd / P    src/subspace_construction.jl:31, :44-52, :61-65
+ *
+ * Conventions
+ *   - every entry point is extern "C", takes plain pointers and sizes, returns
+ *     0 on success and a negative SSI_ERR_* code on failure; the message is kept per
+ *     context (ssi_last_error).  No C++ exception crosses the ABI.
+ *   - all matrices are COLUMN-MAJOR (Julia-native), so the shim passes pointer(Array):
+ *       X  in0 x N      Y  O x N      P  n x M      Z  M x B
+ *       z_trace  M x n_chains x n_steps          lp_trace / accept_trace  n_chains x n_steps
+ *   - flat parameter order is Flux.destructure's: per Dense layer vec(W_l) (out x in,
+ *     column-major) followed by b_l                 src/libs.jl:55-57, :19-22
+ *   - the caller owns every buffer for the duration of the call only; the context owns
+ *     all device memory and its stream; set_* calls copy.
+ *   - a context is bound to ONE device and is not re-entrant.  Multi-GPU runs use one
+ *     process (and one context) per GPU and shard chains by `chain_offset`; the
+ *     counter-based RNG is keyed on the GLOBAL chain id so results do not depend on
+ *     the number of GPUs.
+ *   - there is no CPU fallback: every compute entry point fails with SSI_ERR_CUDA when
+ *     no sm_100 device is usable.
+ */
+#ifndef SSI_H
+#define SSI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSI_VERSION 100            /* 0.1.0 */
+
+/* error codes */
+#define SSI_OK             0
+#define SSI_ERR_ARG       -1       /* bad argument / call order */
+#define SSI_ERR_CUDA      -2       /* CUDA runtime or driver failure, or no usable device */
+#define SSI_ERR_STATE     -3       /* model / data / subspace not set */
+#define SSI_ERR_RANK      -4       /* deviation matrix has fewer than M usable columns */
+#define SSI_ERR_UNSUPPORTED -5
+
+/* activation codes for ssi_set_model (Flux/NNlib: identity, relu, tanh, sigmoid) */
+#define SSI_ACT_IDENTITY 0
+#define SSI_ACT_RELU     1
+#define SSI_ACT_TANH     2
+#define SSI_ACT_SIGMOID  3
+
+/* terms of the log-posterior; `prior_mask` is an OR of these.
+ * The reference AS EXECUTED is SSI_TERM_LL only: its weight-prior line is dead code
+ * (src/space_inference.jl:94-95, a line-leading `+` after a complete `return`).
+ * SSI_TERM_LL|SSI_TERM_PRIOR_W is what the docs describe (docs/src/nn_example.md:61-68). */
+#define SSI_TERM_LL       1u       /* logpdf(MvNormal(vec(pred), sigma_m), vec(Y))       :94 */
+#define SSI_TERM_PRIOR_W  2u       /* logpdf(MvNormal(zeros(n), sigma_p), W_swa + P z)   :95 */
+#define SSI_TERM_PRIOR_Z  4u       /* logpdf(MvNormal(zeros(M), sigma_z), z)  (north_star) */
+
+/* execution paths for ssi_set_option("path", ...) */
+#define SSI_PATH_AUTO     0
+#define SSI_PATH_FUSED    1        /* one CTA keeps a sample's whole network in shared memory */
+#define SSI_PATH_LAYERED  2        /* per-layer FP32 SIMT GEMMs (any shape)                  */
+#define SSI_PATH_TENSOR   3        /* tcgen05/TMEM/TMA split-precision GEMMs (wide layers)   */
+
+typedef struct ssi_ctx ssi_ctx;
+
+typedef struct ssi_stats_t {
+    double last_ms;            /* device time of the last compute call (CUDA events on the ctx stream) */
+    double last_flops;         /* algorithmic flops of that call: 2*sum(in*out)*N*B + 2*n*M*B          */
+    double last_bytes;         /* algorithmic HBM bytes of that call (construction streams), else 0     */
+    double last_units;         /* (sample x datapoint) units of that call                              */
+    int64_t kernel_launches;   /* kernels launched by this context since creation                      */
+    int64_t mh_accepts;        /* accepted proposals in the last ssi_mh_run (all chains)               */
+    int64_t mh_proposals;      /* proposals in the last ssi_mh_run                                     */
+    int32_t last_path;         /* SSI_PATH_* actually used by the last log-posterior evaluation        */
+    int32_t sm_count;
+} ssi_stats_t;
+
+int  ssi_version(void);
+
+/* ---- lifecycle ------------------------------------------------------------------- */
+int  ssi_ctx_create(int device, ssi_ctx** out);
+int  ssi_ctx_destroy(ssi_ctx* ctx);
+/* message of the last failure on `ctx` (or of the last failed ssi_ctx_create when ctx==NULL) */
+const char* ssi_last_error(const ssi_ctx* ctx);
+/* run on a caller-provided cudaStream_t (e.g. torch's current stream); NULL restores the ctx stream */
+int  ssi_set_stream(ssi_ctx* ctx, void* cuda_stream);
+int  ssi_sync(ssi_ctx* ctx);
+/* keys: "path" (SSI_PATH_*), "group" (samples evaluated per wave on the layered/tensor paths) */
+int  ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value);
+int  ssi_stats(const ssi_ctx* ctx, ssi_stats_t* out);
+
+/* ---- the closure's captured state (src/space_inference.jl:86-90) ------------------- */
+/* Chain(Dense(dims[0],dims[1],act[0]), ..., Dense(dims[L-1],dims[L],act[L-1]))            */
+int  ssi_set_model(ssi_ctx* ctx, int n_layers, const int32_t* dims, const int32_t* act);
+/* full dataset, as split_data returns it (src/libs.jl:75-77); host pointers, copied      */
+int  ssi_set_data(ssi_ctx* ctx, const float* X, const float* Y, int64_t N);
+/* W_swa (n) and P (n x M column-major), host pointers, copied; n must match the model    */
+int  ssi_set_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, int64_t n, int32_t M);
+
+/* ---- density(z), batched over B subspace points (src/space_inference.jl:90-95) ----- */
+/* Z: M x B (host).  lp_out: B doubles.  terms_out: 3 x B doubles (ll, prior_w, prior_z) or NULL. */
+int  ssi_logpost_batch(ssi_ctx* ctx, const float* Z, int64_t B,
+                       double sigma_m, double sigma_p, double sigma_z, uint32_t prior_mask,
+                       double* lp_out, double* terms_out);
+/* same with DEVICE pointers; asynchronous on the ctx stream (ssi_sync to wait)            */
+int  ssi_logpost_batch_dev(ssi_ctx* ctx, const float* dZ, int64_t B,
+                           double sigma_m, double sigma_p, double sigma_z, uint32_t prior_mask,
+                           double* d_lp_out, double* d_terms_out);
+
+/* ---- sample(DensityModel(density), RWMH(MvNormal(zeros(M), sigma_z)), itr) ----------
+ * src/space_inference.jl:111-116.  n_chains independent chains, global ids
+ * chain_offset .. chain_offset+n_chains-1.  Sample 0 of each chain is a draw from the
+ * proposal (or z0 if given, M x n_chains) and counts as the first of n_steps; step t
+ * proposes z + sigma_z*eps(chain,t) and accepts iff -e(chain,t) < lp' - lp, with eps and
+ * e from the Philox stream ssi_rng_replay reproduces.  Any trace pointer may be NULL.   */
+int  ssi_mh_run(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+                double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask,
+                const float* z0_or_null,
+                float* z_trace, double* lp_trace, uint8_t* accept_trace);
+/* same, traces left on the device (pointers are device pointers or NULL); asynchronous  */
+int  ssi_mh_run_dev(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+                    double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask,
+                    const float* d_z0_or_null,
+                    float* d_z_trace, double* d_lp_trace, uint8_t* d_accept_trace);
+/* host replay of the device stream: eps_out (M floats, N(0,1)) and e_out (Exp(1)) of (chain, step) */
+int  ssi_rng_replay(uint64_t seed, int64_t chain, int64_t step, int32_t M, float* eps_out, double* e_out);
+/* map(z -> W_swa + P*z, chm) (src/space_inference.jl:125): W_out n x B column-major (host) */
+int  ssi_project(ssi_ctx* ctx, const float* Z, int64_t B, float* W_out);
+
+/* ---- subspace construction streams (src/subspace_construction.jl:31,44-52,61-65) ---- */
+/* W_swa <- zeros(n) (:31), deviation matrix with room for K_max columns (:33)             */
+int  ssi_swa_begin(ssi_ctx* ctx, int64_t n, int64_t K_max);
+/* one snapshot W (n floats, host): W_swa <- (ns*W_swa + W)/(ns+1), column <- W - W_swa     */
+/* with ns = i/c passed by the host (:46-47, :51-52)                                       */
+int  ssi_swa_push(ssi_ctx* ctx, const float* W, double n_scalar);
+int  ssi_swa_push_dev(ssi_ctx* ctx, const float* dW, double n_scalar);
+/* psvd(A) restated as Gram + symmetric eigen-solve; P = U_M S_M = A V_M (:61-65).          */
+/* W_swa_out n, P_out n x M, s_out K singular values (descending); host pointers, any NULL. */
+/* If `install` != 0 the result also becomes the context's subspace (ssi_set_subspace).     */
+int  ssi_swa_finish(ssi_ctx* ctx, int32_t M, float* W_swa_out, float* P_out, double* s_out, int32_t install);
+/* number of columns collected so far */
+int64_t ssi_swa_columns(const ssi_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSI_H */

@@ -1,0 +1,112 @@
+"""Host-side mirror of the reference's public functions for the accelerated path.
+
+Same names, argument meaning, defaults and error behaviour as
+  subspace_construction   src/subspace_construction.jl:26-67
+  subspace_inference      src/space_inference.jl:33-54
+  sub_inference           src/space_inference.jl:82-125   (alias `inference`, README.md:153-154)
+Everything numeric goes through the C ABI (include/ssi.h); there is no CPU fallback.
+Keyword arguments that do not exist in the reference (n_chains, seed, prior_mask, device,
+return_z, engine) default to the reference's behaviour: one chain, likelihood-only density
+(the weight-prior line is dead code in the reference, src/space_inference.jl:94-95).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import TERM_LL
+from .engine import Engine
+from .flux import Chain, DataLoader, extract_params, split_data, train_step
+
+_RWMH_ALIASES = ("rwmh", "mh")
+
+
+def _sym(s) -> str:
+    return str(s).lstrip(":")
+
+
+def subspace_construction(model, cost, data, opt, *, T: int = 10, c: int = 1, M: int = 3, print_freq: int = 1,
+                          engine: Engine | None = None, device: int = 0, install: bool = False):
+    """(W_swa, P) from SGD snapshots.  The per-mini-batch training step is host plumbing
+    (src/subspace_construction.jl:39-43); the moment recurrence, deviation matrix, Gram,
+    eigen-solve and P = U_M S_M run on the device (:44-52, :61-65)."""
+    if not isinstance(model, Chain):
+        raise TypeError("Error: model_re function is not available for this model")   # src/libs.jl:59
+    own = engine is None
+    eng = engine or Engine(device)
+    try:
+        n = int(extract_params(model).shape[0])
+        n_batches = len(data)
+        K_max = max(1, (T // c) * n_batches)
+        eng.swa_begin(n, K_max)
+        training_loss = 0.0
+        for i in range(1, T + 1):
+            for x, y in data:
+                training_loss = train_step(model, cost, opt, x, y)
+                if i % c == 0:
+                    eng.swa_push(extract_params(model), i / c)          # n = i/c (:46), epoch index (Q2)
+            if i % print_freq == 0 or i == T:
+                print("Traing loss: ", training_loss, " Epoch: ", i)    # (sic) :56-58
+        if install:
+            eng.set_model(model.dims, model.acts)
+        W_swa, P, _ = eng.swa_finish(M, install=install)
+        return W_swa, P
+    finally:
+        if own:
+            eng.close()
+
+
+def sub_inference(in_model, data, W_swa, P, *, σ_z: float = 1.0, σ_m: float = 1.0, σ_p: float = 1.0, itr: int = 100,
+                  M: int = 3, alg="rwmh", backend="forwarddiff",
+                  n_chains: int = 1, seed: int = 0, chain_offset: int = 0, prior_mask: int = TERM_LL,
+                  engine: Engine | None = None, device: int = 0, return_z: bool = False):
+    """RWMH in the subspace.  Returns (chn, lp): with n_chains == 1 (the reference) `chn` is a
+    list of `itr` weight vectors W_swa + P z and `lp` the `itr` log-probabilities
+    (src/space_inference.jl:125).  With n_chains > 1 `chn` is the (M, n_chains, itr) array of
+    subspace samples (materialising itr x n_chains weight vectors is what the device path
+    avoids; use Engine.project on the samples you need) and lp is (n_chains, itr)."""
+    a = _sym(alg)
+    if a not in _RWMH_ALIASES:
+        if a in ("mala", "advi", "hmc", "nuts"):
+            raise NotImplementedError(f"{a} is not available on the device path")
+        raise ValueError(f"{a} is not available")                         # src/space_inference.jl:162
+    if not isinstance(in_model, Chain):
+        raise TypeError("Error: density function is not avaliable for this model")   # :103
+    P = np.asarray(P)
+    if P.ndim != 2 or P.shape[1] != M:
+        raise ValueError(f"DimensionMismatch: P has {P.shape[-1]} columns but M = {M}")   # P*z fails in Julia (:91)
+    X, Y = split_data(data)
+    own = engine is None
+    eng = engine or Engine(device)
+    try:
+        eng.set_model(in_model.dims, in_model.acts)
+        eng.set_data(X, Y)
+        eng.set_subspace(W_swa, P)
+        zt, lt, _ = eng.mh_run(n_chains, itr, seed, sigma_z=σ_z, sigma_m=σ_m, sigma_p=σ_p, mask=prior_mask,
+                               chain_offset=chain_offset, want_accept=False)
+        if n_chains == 1 and not return_z:
+            W = eng.project(zt[:, 0, :])                                  # map(z -> W_swa + P*z, chm)
+            return [W[:, t].copy() for t in range(itr)], lt[0].copy()
+        return zt, lt
+    finally:
+        if own:
+            eng.close()
+
+
+inference = sub_inference
+
+
+def subspace_inference(model, cost, data, opt, *, σ_z: float = 1.0, σ_m: float = 1.0, σ_p: float = 1.0,
+                       itr: int = 1000, T: int = 25, c: int = 1, M: int = 20, print_freq: int = 1, alg="rwmh",
+                       backend="forwarddiff", method="subspace", **kw):
+    """construct -> sample -> (chn, lp, W_swa)   (src/space_inference.jl:33-54)."""
+    if _sym(method) == "subspace":
+        W_swa, P = subspace_construction(model, cost, data, opt, T=T, c=c, M=M, print_freq=print_freq,
+                                         device=kw.get("device", 0))
+    elif _sym(method) == "diffusion":
+        raise NotImplementedError("diffusion_subspace is not available on the device path")
+    else:
+        raise ValueError("Error: No method found")                        # :42
+    if _sym(alg) in ("turing_mh", "turing_nuts"):
+        raise NotImplementedError("turing_inference is not available on the device path")
+    chn, lp = sub_inference(model, data, W_swa, P, σ_z=σ_z, σ_m=σ_m, σ_p=σ_p, itr=itr, M=M, alg=alg, backend=backend, **kw)
+    return chn, lp, W_swa

@@ -1,0 +1,450 @@
+// ssi_api.cu — the extern "C" surface declared in include/ssi.h: context lifecycle,
+// host<->device staging and per-call timing.  All compute is in the other .cu files.
+#include "ssi_common.cuh"
+#include "ssi_rng.cuh"
+
+#include <cstdarg>
+#include <cmath>
+#include <mutex>
+
+int ssi_mh_device(ssi_ctx*, int64_t, int64_t, uint64_t, int64_t, double, double, double, uint32_t,
+                  const float*, float*, double*, uint8_t*);
+int ssi_mh_fetch_accepts(ssi_ctx*);
+int ssi_swa_push_device(ssi_ctx*, const float*, double);
+int ssi_swa_factor_device(ssi_ctx*, int, float*, double*, int*);
+
+static std::mutex g_err_mu;
+static std::string g_create_err;
+
+int ssi_fail(ssi_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) {
+        ctx->err = buf;
+    } else {
+        std::lock_guard<std::mutex> lk(g_err_mu);
+        g_create_err = buf;
+    }
+    return code;
+}
+
+int ssi_use_device(ssi_ctx* ctx) {
+    SSI_CUDA(ctx, cudaSetDevice(ctx->device));
+    return SSI_OK;
+}
+
+int ssi_reserve(ssi_ctx* ctx, ssi_buf_t& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return SSI_OK;
+    if (b.p) {
+        SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        SSI_CUDA(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    const size_t want = bytes < 256 ? 256 : bytes;
+    SSI_CUDA(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return SSI_OK;
+}
+
+static void free_buf(ssi_buf_t& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+struct call_timer {
+    ssi_ctx* ctx;
+    explicit call_timer(ssi_ctx* c) : ctx(c) { cudaEventRecord(c->ev0, c->stream); }
+    void stop(bool sync) {
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        if (sync) {
+            cudaEventSynchronize(ctx->ev1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+            ctx->stats.last_ms = ms;
+        }
+    }
+};
+
+extern "C" {
+
+int ssi_version(void) { return SSI_VERSION; }
+
+const char* ssi_last_error(const ssi_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    return g_create_err.c_str();
+}
+
+int ssi_ctx_create(int device, ssi_ctx** out) {
+    if (!out) return ssi_fail(nullptr, SSI_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return ssi_fail(nullptr, SSI_ERR_CUDA, "no CUDA device available (%s); libssi has no CPU fallback",
+                        e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return ssi_fail(nullptr, SSI_ERR_ARG, "device %d out of range [0,%d)", device, count);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return ssi_fail(nullptr, SSI_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return ssi_fail(nullptr, SSI_ERR_CUDA, "device %d is sm_%d%d; libssi is built for sm_100a only", device, prop.major, prop.minor);
+    ssi_ctx* ctx = new ssi_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->stats.sm_count = prop.multiProcessorCount;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+        ssi_fail(nullptr, SSI_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+        delete ctx;
+        return SSI_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return SSI_OK;
+}
+
+int ssi_ctx_destroy(ssi_ctx* ctx) {
+    if (!ctx) return SSI_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ssi_tc_destroy(ctx);
+    cudaFree(ctx->dX); cudaFree(ctx->dY); cudaFree(ctx->dP); cudaFree(ctx->dSubGram);
+    cudaFree(ctx->dSwaMean); cudaFree(ctx->dDev);
+    ssi_buf_t* bufs[] = {&ctx->bZ, &ctx->bLp, &ctx->bTerms, &ctx->bPartials, &ctx->bW, &ctx->bH0, &ctx->bH1, &ctx->bGram,
+                         &ctx->bEig, &ctx->bMisc, &ctx->bMhZ, &ctx->bMhZp, &ctx->bMhLp, &ctx->bMhLpP, &ctx->bMhCnt, &ctx->bSnap};
+    for (ssi_buf_t* b : bufs) free_buf(*b);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return SSI_OK;
+}
+
+int ssi_set_stream(ssi_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return SSI_ERR_ARG;
+    SSI_TRY(ssi_use_device(ctx));
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SSI_OK;
+}
+
+int ssi_sync(ssi_ctx* ctx) {
+    if (!ctx) return SSI_ERR_ARG;
+    SSI_TRY(ssi_use_device(ctx));
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    if (cudaEventQuery(ctx->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess)
+        ctx->stats.last_ms = ms;
+    (void)cudaGetLastError();
+    return SSI_OK;
+}
+
+int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) return SSI_ERR_ARG;
+    if (!strcmp(key, "path")) {
+        if (value < SSI_PATH_AUTO || value > SSI_PATH_TENSOR) return ssi_fail(ctx, SSI_ERR_ARG, "path must be one of SSI_PATH_*");
+        ctx->opt_path = (int)value;
+        return SSI_OK;
+    }
+    if (!strcmp(key, "group")) {
+        if (value < 0 || value > 4096) return ssi_fail(ctx, SSI_ERR_ARG, "group out of range");
+        ctx->opt_group = (int)value;
+        ssi_tc_invalidate(ctx);
+        return SSI_OK;
+    }
+    return ssi_fail(ctx, SSI_ERR_ARG, "unknown option '%s'", key);
+}
+
+int ssi_stats(const ssi_ctx* ctx, ssi_stats_t* out) {
+    if (!ctx || !out) return SSI_ERR_ARG;
+    *out = ctx->stats;
+    return SSI_OK;
+}
+
+int ssi_set_model(ssi_ctx* ctx, int n_layers, const int32_t* dims, const int32_t* act) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (n_layers < 1 || n_layers > SSI_MAX_LAYERS || !dims || !act)
+        return ssi_fail(ctx, SSI_ERR_ARG, "n_layers must be in [1,%d] and dims/act non-NULL", SSI_MAX_LAYERS);
+    ssi_model_t m;
+    m.L = n_layers;
+    int64_t off = 0;
+    double fl = 0;
+    for (int l = 0; l <= n_layers; ++l) {
+        if (dims[l] < 1) return ssi_fail(ctx, SSI_ERR_ARG, "dims[%d]=%d must be positive", l, dims[l]);
+        m.dims[l] = dims[l];
+        m.max_width = dims[l] > m.max_width ? dims[l] : m.max_width;
+    }
+    for (int l = 0; l < n_layers; ++l) {
+        if (act[l] < SSI_ACT_IDENTITY || act[l] > SSI_ACT_SIGMOID) return ssi_fail(ctx, SSI_ERR_ARG, "act[%d]=%d is not a supported activation", l, act[l]);
+        m.act[l] = act[l];
+        m.w_off[l] = off;
+        off += (int64_t)dims[l] * dims[l + 1];
+        m.b_off[l] = off;
+        off += dims[l + 1];
+        fl += 2.0 * (double)dims[l] * dims[l + 1];
+    }
+    m.n = off;
+    m.flops_per_point = fl;
+    const bool shape_changed = !ctx->has_model || m.n != ctx->model.n || m.dims[0] != ctx->model.dims[0] ||
+                               m.dims[n_layers] != ctx->model.dims[ctx->model.L];
+    ctx->model = m;
+    ctx->has_model = true;
+    if (shape_changed) { ctx->has_data = false; ctx->has_sub = false; }
+    ssi_tc_invalidate(ctx);
+    return SSI_OK;
+}
+
+int ssi_set_data(ssi_ctx* ctx, const float* X, const float* Y, int64_t N) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (!ctx->has_model) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_set_model must be called before ssi_set_data");
+    if (!X || !Y || N < 1) return ssi_fail(ctx, SSI_ERR_ARG, "X, Y must be non-NULL and N >= 1");
+    SSI_TRY(ssi_use_device(ctx));
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t bx = sizeof(float) * (size_t)ctx->model.dims[0] * N;
+    const size_t by = sizeof(float) * (size_t)ctx->model.dims[ctx->model.L] * N;
+    cudaFree(ctx->dX); cudaFree(ctx->dY);
+    ctx->dX = ctx->dY = nullptr;
+    ctx->has_data = false;
+    SSI_CUDA(ctx, cudaMalloc(&ctx->dX, bx));
+    SSI_CUDA(ctx, cudaMalloc(&ctx->dY, by));
+    SSI_CUDA(ctx, cudaMemcpyAsync(ctx->dX, X, bx, cudaMemcpyHostToDevice, ctx->stream));
+    SSI_CUDA(ctx, cudaMemcpyAsync(ctx->dY, Y, by, cudaMemcpyHostToDevice, ctx->stream));
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->N = N;
+    ctx->has_data = true;
+    ssi_tc_invalidate(ctx);
+    return SSI_OK;
+}
+
+static int install_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, int64_t n, int M, cudaMemcpyKind kind) {
+    if (!ctx->has_model) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_set_model must be called before the subspace is set");
+    if (n != ctx->model.n) return ssi_fail(ctx, SSI_ERR_ARG, "n=%lld does not match the model's %lld parameters", (long long)n, (long long)ctx->model.n);
+    if (M < 1 || M > SSI_MAX_M) return ssi_fail(ctx, SSI_ERR_ARG, "M=%d must be in [1,%d]", M, SSI_MAX_M);
+    SSI_TRY(ssi_use_device(ctx));
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->dP); cudaFree(ctx->dSubGram);
+    ctx->dP = nullptr; ctx->dSubGram = nullptr; ctx->dWswa = nullptr;
+    ctx->has_sub = false;
+    // [P | W_swa] as one n x (M+1) matrix so that the prior's M-space Gram is one pass
+    SSI_CUDA(ctx, cudaMalloc(&ctx->dP, sizeof(float) * (size_t)n * (M + 1)));
+    SSI_CUDA(ctx, cudaMalloc(&ctx->dSubGram, sizeof(double) * (size_t)(M + 1) * (M + 1)));
+    ctx->dWswa = ctx->dP + (size_t)n * M;
+    SSI_CUDA(ctx, cudaMemcpyAsync(ctx->dP, P, sizeof(float) * (size_t)n * M, kind, ctx->stream));
+    SSI_CUDA(ctx, cudaMemcpyAsync(ctx->dWswa, W_swa, sizeof(float) * (size_t)n, kind, ctx->stream));
+    ctx->M = M;
+    SSI_TRY(ssi_subspace_gram(ctx));
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->has_sub = true;
+    ssi_tc_invalidate(ctx);
+    return SSI_OK;
+}
+
+int ssi_set_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, int64_t n, int32_t M) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (!W_swa || !P) return ssi_fail(ctx, SSI_ERR_ARG, "W_swa and P must be non-NULL");
+    return install_subspace(ctx, W_swa, P, n, M, cudaMemcpyHostToDevice);
+}
+
+int ssi_logpost_batch_dev(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m, double sigma_p, double sigma_z,
+                          uint32_t prior_mask, double* d_lp_out, double* d_terms_out) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (B < 0 || (B > 0 && (!dZ || !d_lp_out))) return ssi_fail(ctx, SSI_ERR_ARG, "Z and lp_out must be non-NULL, B >= 0");
+    SSI_TRY(ssi_use_device(ctx));
+    call_timer t(ctx);
+    const int rc = ssi_logpost_device(ctx, dZ, B, sigma_m, sigma_p, sigma_z, prior_mask, d_lp_out, d_terms_out);
+    t.stop(false);
+    return rc;
+}
+
+int ssi_logpost_batch(ssi_ctx* ctx, const float* Z, int64_t B, double sigma_m, double sigma_p, double sigma_z,
+                      uint32_t prior_mask, double* lp_out, double* terms_out) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (B < 0 || (B > 0 && (!Z || !lp_out))) return ssi_fail(ctx, SSI_ERR_ARG, "Z and lp_out must be non-NULL, B >= 0");
+    if (!ctx->has_model || !ctx->has_data || !ctx->has_sub)
+        return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before evaluating the log-posterior");
+    if (B == 0) return SSI_OK;
+    SSI_TRY(ssi_use_device(ctx));
+    const size_t bz = sizeof(float) * (size_t)ctx->M * B;
+    SSI_TRY(ssi_reserve(ctx, ctx->bZ, bz));
+    SSI_TRY(ssi_reserve(ctx, ctx->bLp, sizeof(double) * (size_t)B));
+    if (terms_out) SSI_TRY(ssi_reserve(ctx, ctx->bTerms, sizeof(double) * 3 * (size_t)B));
+    SSI_CUDA(ctx, cudaMemcpyAsync(ctx->bZ.p, Z, bz, cudaMemcpyHostToDevice, ctx->stream));
+    call_timer t(ctx);
+    const int rc = ssi_logpost_device(ctx, (const float*)ctx->bZ.p, B, sigma_m, sigma_p, sigma_z, prior_mask,
+                                      (double*)ctx->bLp.p, terms_out ? (double*)ctx->bTerms.p : nullptr);
+    t.stop(false);
+    if (rc != SSI_OK) return rc;
+    SSI_CUDA(ctx, cudaMemcpyAsync(lp_out, ctx->bLp.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (terms_out)
+        SSI_CUDA(ctx, cudaMemcpyAsync(terms_out, ctx->bTerms.p, sizeof(double) * 3 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    return ssi_sync(ctx);
+}
+
+int ssi_mh_run_dev(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+                   double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* d_z0,
+                   float* d_z_trace, double* d_lp_trace, uint8_t* d_accept_trace) {
+    if (!ctx) return SSI_ERR_ARG;
+    SSI_TRY(ssi_use_device(ctx));
+    call_timer t(ctx);
+    const int rc = ssi_mh_device(ctx, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask,
+                                 d_z0, d_z_trace, d_lp_trace, d_accept_trace);
+    t.stop(false);
+    return rc;
+}
+
+int ssi_mh_run(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+               double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* z0,
+               float* z_trace, double* lp_trace, uint8_t* accept_trace) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (!ctx->has_model || !ctx->has_data || !ctx->has_sub)
+        return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before sampling");
+    if (n_chains <= 0 || n_steps <= 0) return ssi_fail(ctx, SSI_ERR_ARG, "n_chains and n_steps must be positive");
+    SSI_TRY(ssi_use_device(ctx));
+    const size_t cs = (size_t)n_chains * (size_t)n_steps;
+    const size_t bz = sizeof(float) * ctx->M * cs, bl = sizeof(double) * cs, ba = cs;
+    // one scratch allocation: [z_trace | lp_trace | acc | z0]
+    const size_t off_l = z_trace ? (bz + 255) / 256 * 256 : 0;
+    const size_t off_a = off_l + (lp_trace ? (bl + 255) / 256 * 256 : 0);
+    const size_t off_z0 = off_a + (accept_trace ? (ba + 255) / 256 * 256 : 0);
+    const size_t bz0 = z0 ? sizeof(float) * (size_t)ctx->M * n_chains : 0;
+    SSI_TRY(ssi_reserve(ctx, ctx->bSnap, off_z0 + bz0 + 256));
+    char* base = (char*)ctx->bSnap.p;
+    float* dzt = z_trace ? (float*)base : nullptr;
+    double* dlt = lp_trace ? (double*)(base + off_l) : nullptr;
+    uint8_t* dat = accept_trace ? (uint8_t*)(base + off_a) : nullptr;
+    float* dz0 = nullptr;
+    if (z0) {
+        dz0 = (float*)(base + off_z0);
+        SSI_CUDA(ctx, cudaMemcpyAsync(dz0, z0, bz0, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    call_timer t(ctx);
+    const int rc = ssi_mh_device(ctx, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask,
+                                 dz0, dzt, dlt, dat);
+    t.stop(false);
+    if (rc != SSI_OK) return rc;
+    if (z_trace) SSI_CUDA(ctx, cudaMemcpyAsync(z_trace, dzt, bz, cudaMemcpyDeviceToHost, ctx->stream));
+    if (lp_trace) SSI_CUDA(ctx, cudaMemcpyAsync(lp_trace, dlt, bl, cudaMemcpyDeviceToHost, ctx->stream));
+    if (accept_trace) SSI_CUDA(ctx, cudaMemcpyAsync(accept_trace, dat, ba, cudaMemcpyDeviceToHost, ctx->stream));
+    SSI_TRY(ssi_sync(ctx));
+    return ssi_mh_fetch_accepts(ctx);
+}
+
+int ssi_rng_replay(uint64_t seed, int64_t chain, int64_t step, int32_t M, float* eps_out, double* e_out) {
+    if (M < 0 || chain < 0 || step < 0 || chain > 0xffffffffll || step > 0xffffffffll) return SSI_ERR_ARG;
+    if (eps_out) {
+        for (int blk = 0; blk * 4 < M; ++blk) {
+            float e[4];
+            ssi_normal4(seed, (uint32_t)chain, (uint32_t)step, (uint32_t)blk, e);
+            for (int r = 0; r < 4 && blk * 4 + r < M; ++r) eps_out[blk * 4 + r] = e[r];
+        }
+    }
+    if (e_out) *e_out = ssi_exp1(seed, (uint32_t)chain, (uint32_t)step);
+    return SSI_OK;
+}
+
+int ssi_project(ssi_ctx* ctx, const float* Z, int64_t B, float* W_out) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (!ctx->has_model || !ctx->has_sub) return ssi_fail(ctx, SSI_ERR_STATE, "model and subspace must be set");
+    if (B < 0 || (B > 0 && (!Z || !W_out))) return ssi_fail(ctx, SSI_ERR_ARG, "Z and W_out must be non-NULL");
+    if (B == 0) return SSI_OK;
+    SSI_TRY(ssi_use_device(ctx));
+    const int64_t n = ctx->model.n;
+    // stream the samples through a bounded scratch
+    const int64_t gmax = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)(1ull << 30) / (sizeof(float) * n)));
+    SSI_TRY(ssi_reserve(ctx, ctx->bZ, sizeof(float) * (size_t)ctx->M * gmax));
+    SSI_TRY(ssi_reserve(ctx, ctx->bW, sizeof(float) * (size_t)n * gmax));
+    call_timer t(ctx);
+    for (int64_t b0 = 0; b0 < B; b0 += gmax) {
+        const int64_t g = std::min(gmax, B - b0);
+        SSI_CUDA(ctx, cudaMemcpyAsync(ctx->bZ.p, Z + b0 * ctx->M, sizeof(float) * (size_t)ctx->M * g, cudaMemcpyHostToDevice, ctx->stream));
+        SSI_TRY(ssi_project_device(ctx, (const float*)ctx->bZ.p, g, (float*)ctx->bW.p));
+        SSI_CUDA(ctx, cudaMemcpyAsync(W_out + b0 * n, ctx->bW.p, sizeof(float) * (size_t)n * g, cudaMemcpyDeviceToHost, ctx->stream));
+        SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    t.stop(true);
+    return SSI_OK;
+}
+
+int ssi_swa_begin(ssi_ctx* ctx, int64_t n, int64_t K_max) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (n < 1 || K_max < 1) return ssi_fail(ctx, SSI_ERR_ARG, "n and K_max must be positive");
+    SSI_TRY(ssi_use_device(ctx));
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->dSwaMean); cudaFree(ctx->dDev);
+    ctx->dSwaMean = ctx->dDev = nullptr;
+    ctx->swa_n = 0; ctx->swa_K = 0; ctx->swa_Kmax = 0;
+    SSI_CUDA(ctx, cudaMalloc(&ctx->dSwaMean, sizeof(float) * (size_t)n));
+    SSI_CUDA(ctx, cudaMalloc(&ctx->dDev, sizeof(float) * (size_t)n * K_max));
+    SSI_CUDA(ctx, cudaMemsetAsync(ctx->dSwaMean, 0, sizeof(float) * (size_t)n, ctx->stream));   // W_swa = zeros (:31)
+    ctx->swa_n = n;
+    ctx->swa_Kmax = K_max;
+    return SSI_OK;
+}
+
+int ssi_swa_push_dev(ssi_ctx* ctx, const float* dW, double n_scalar) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (!dW) return ssi_fail(ctx, SSI_ERR_ARG, "W must be non-NULL");
+    SSI_TRY(ssi_use_device(ctx));
+    call_timer t(ctx);
+    const int rc = ssi_swa_push_device(ctx, dW, n_scalar);
+    t.stop(false);
+    return rc;
+}
+
+int ssi_swa_push(ssi_ctx* ctx, const float* W, double n_scalar) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (!W) return ssi_fail(ctx, SSI_ERR_ARG, "W must be non-NULL");
+    if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
+    SSI_TRY(ssi_use_device(ctx));
+    SSI_TRY(ssi_reserve(ctx, ctx->bSnap, sizeof(float) * (size_t)ctx->swa_n));
+    SSI_CUDA(ctx, cudaMemcpyAsync(ctx->bSnap.p, W, sizeof(float) * (size_t)ctx->swa_n, cudaMemcpyHostToDevice, ctx->stream));
+    call_timer t(ctx);
+    const int rc = ssi_swa_push_device(ctx, (const float*)ctx->bSnap.p, n_scalar);
+    t.stop(false);
+    if (rc != SSI_OK) return rc;
+    return ssi_sync(ctx);   // the caller may reuse W immediately
+}
+
+int64_t ssi_swa_columns(const ssi_ctx* ctx) { return ctx ? ctx->swa_K : -1; }
+
+int ssi_swa_finish(ssi_ctx* ctx, int32_t M, float* W_swa_out, float* P_out, double* s_out, int32_t install) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
+    if (M < 1) return ssi_fail(ctx, SSI_ERR_ARG, "M must be positive");
+    SSI_TRY(ssi_use_device(ctx));
+    const int64_t n = ctx->swa_n;
+    const int K = (int)ctx->swa_K;
+    // scratch: P (n x M floats) | s (K doubles)
+    const size_t off_s = (sizeof(float) * (size_t)n * M + 255) / 256 * 256;
+    SSI_TRY(ssi_reserve(ctx, ctx->bW, off_s + sizeof(double) * (size_t)(K > 0 ? K : 1)));
+    float* dPout = (float*)ctx->bW.p;
+    double* ds = (double*)((char*)ctx->bW.p + off_s);
+    int sweeps = 0;
+    call_timer t(ctx);
+    const int rc = ssi_swa_factor_device(ctx, M, dPout, ds, &sweeps);
+    t.stop(false);
+    if (rc != SSI_OK) return rc;
+    if (W_swa_out) SSI_CUDA(ctx, cudaMemcpyAsync(W_swa_out, ctx->dSwaMean, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (P_out) SSI_CUDA(ctx, cudaMemcpyAsync(P_out, dPout, sizeof(float) * (size_t)n * M, cudaMemcpyDeviceToHost, ctx->stream));
+    if (s_out) SSI_CUDA(ctx, cudaMemcpyAsync(s_out, ds, sizeof(double) * (size_t)K, cudaMemcpyDeviceToHost, ctx->stream));
+    SSI_TRY(ssi_sync(ctx));
+    if (sweeps >= 60) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "Jacobi eigen-solver did not converge in %d sweeps", sweeps);
+    if (install) {
+        if (!ctx->has_model || ctx->model.n != n)
+            return ssi_fail(ctx, SSI_ERR_STATE, "install requested but the model (n=%lld) does not match the snapshots (n=%lld)",
+                            (long long)(ctx->has_model ? ctx->model.n : 0), (long long)n);
+        return install_subspace(ctx, ctx->dSwaMean, dPout, n, M, cudaMemcpyDeviceToDevice);
+    }
+    return SSI_OK;
+}
+
+}  // extern "C"

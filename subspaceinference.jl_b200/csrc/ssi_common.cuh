@@ -1,0 +1,158 @@
+// ssi_common.cuh — context, error plumbing and small device helpers shared by all
+// translation units of libssi.so.  Internal; the public surface is include/ssi.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ssi.h"
+
+#define SSI_MAX_LAYERS 16
+#define SSI_MAX_M      64
+
+struct ssi_model_t {
+    int L = 0;
+    int dims[SSI_MAX_LAYERS + 1] = {0};
+    int act[SSI_MAX_LAYERS] = {0};
+    int64_t w_off[SSI_MAX_LAYERS] = {0};   // offset of vec(W_l) in the flat vector
+    int64_t b_off[SSI_MAX_LAYERS] = {0};   // offset of b_l
+    int64_t n = 0;                         // n_params
+    int max_width = 0;                     // max over dims[0..L]
+    double flops_per_point = 0;            // 2*sum(in*out)
+};
+
+// Scratch that grows on demand and is reused between calls.
+struct ssi_buf_t {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct ssi_tc_state;   // tensor-core path private state (ssi_tc.cu)
+
+struct ssi_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t smem_optin = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+
+    // options
+    int opt_path = SSI_PATH_AUTO;
+    int opt_group = 0;
+
+    // model / data / subspace
+    ssi_model_t model;
+    bool has_model = false, has_data = false, has_sub = false;
+    float* dX = nullptr;      // in0 x N
+    float* dY = nullptr;      // O x N
+    int64_t N = 0;
+    float* dWswa = nullptr;   // n
+    float* dP = nullptr;      // n x M
+    int M = 0;
+    // M-space quantities for the weight prior: G = [P | W_swa]^T [P | W_swa]  ((M+1)x(M+1), double)
+    double* dSubGram = nullptr;
+
+    // scratch
+    ssi_buf_t bZ, bLp, bTerms, bPartials, bW, bH0, bH1, bGram, bEig, bMisc;
+
+    // MH state
+    ssi_buf_t bMhZ, bMhZp, bMhLp, bMhLpP, bMhCnt;
+
+    // SWA / construction state
+    int64_t swa_n = 0, swa_Kmax = 0, swa_K = 0;
+    float* dSwaMean = nullptr;   // n
+    float* dDev = nullptr;       // n x K_max, column-major
+    ssi_buf_t bSnap;
+
+    // tensor-core path
+    ssi_tc_state* tc = nullptr;
+
+    // stats
+    ssi_stats_t stats{};
+};
+
+// ---- error plumbing -------------------------------------------------------------------
+int ssi_fail(ssi_ctx* ctx, int code, const char* fmt, ...);
+
+#define SSI_CUDA(ctx, call)                                                              \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess)                                                          \
+            return ssi_fail((ctx), SSI_ERR_CUDA, "%s failed at %s:%d: %s", #call,        \
+                            __FILE__, __LINE__, cudaGetErrorString(e__));                \
+    } while (0)
+
+#define SSI_TRY(expr)                                                                    \
+    do {                                                                                 \
+        int rc__ = (expr);                                                               \
+        if (rc__ != SSI_OK) return rc__;                                                 \
+    } while (0)
+
+#define SSI_LAUNCH_CHECK(ctx)                                                            \
+    do {                                                                                 \
+        (ctx)->stats.kernel_launches++;                                                  \
+        SSI_CUDA((ctx), cudaGetLastError());                                             \
+    } while (0)
+
+int ssi_reserve(ssi_ctx* ctx, ssi_buf_t& b, size_t bytes);
+int ssi_use_device(ssi_ctx* ctx);
+
+// ---- entry points between translation units --------------------------------------------
+// log-posterior of B device-resident subspace points; d_lp (B) and optional d_terms (3 x B)
+int ssi_logpost_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m, double sigma_p,
+                       double sigma_z, uint32_t mask, double* d_lp, double* d_terms);
+int ssi_project_device(ssi_ctx* ctx, const float* dZ, int64_t B, float* dW /* n x B */);
+int ssi_subspace_gram(ssi_ctx* ctx);   // fills dSubGram after set_subspace
+// Gram of an n x K column-major FP32 matrix (ld = n) into a K x K double matrix on device
+int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int K, double* dG);
+
+// tensor-core path (ssi_tc.cu)
+bool ssi_tc_supported(const ssi_ctx* ctx);
+int  ssi_tc_prepare(ssi_ctx* ctx);        // after model+data(+subspace) change
+void ssi_tc_invalidate(ssi_ctx* ctx);
+void ssi_tc_destroy(ssi_ctx* ctx);
+// SSE (sum of squared errors) of B samples into d_sse (B doubles)
+int  ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse);
+
+// ---- device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ float ssi_act(float v, int act) {
+    switch (act) {
+        case SSI_ACT_RELU:    return fmaxf(v, 0.0f);
+        case SSI_ACT_TANH:    return tanhf(v);
+        case SSI_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+        default:              return v;
+    }
+}
+
+__device__ __forceinline__ double ssi_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float ssi_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum in double; result valid in thread 0.  `red` needs 32 doubles of shared memory.
+__device__ __forceinline__ double ssi_block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = ssi_warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        v = lane < nw ? red[lane] : 0.0;
+        v = ssi_warp_sum(v);
+    }
+    return v;
+}

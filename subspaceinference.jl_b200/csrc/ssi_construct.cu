@@ -1,0 +1,369 @@
+// ssi_construct.cu — subspace construction streams.
+//
+// Replaces the numeric interior of subspace_construction
+// (src/subspace_construction.jl:31,44-52,61-65):
+//   K5  W_swa <- (ns*W_swa + W)/(ns+1);  column <- W - W_swa      (:46-47, :51-52)
+//   K6  G = A'A          tall-skinny Gram of the n x K deviation matrix   (psvd, :63)
+//   K7  G = V diag(lambda) V'   cyclic Jacobi in FP64, one CTA            (psvd, :63)
+//   K8  P = A V_M  ( = U_M S_M )                                          (:65)
+// The reference SVDs A directly with LowRankApprox.psvd; U_M S_M = A V_M is an identity,
+// so the result is the same up to column sign.
+#include "ssi_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+// ======================================================================================
+// K5: SWA mean + deviation column, one float4 stream (16 n bytes per snapshot)
+// ======================================================================================
+__global__ void __launch_bounds__(256)
+k_swa_push(const float* __restrict__ W, float* __restrict__ mean, float* __restrict__ dev,
+           long long n, double ns, double inv, int vec) {
+    const long long n4 = vec ? (n >> 2) : 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const float4* W4 = reinterpret_cast<const float4*>(W);
+    float4* m4 = reinterpret_cast<float4*>(mean);
+    float4* d4 = reinterpret_cast<float4*>(dev);
+    for (long long i = t0; i < n4; i += stride) {
+        const float4 w = __ldcs(W4 + i);
+        const float4 m = m4[i];
+        const double a0 = (ns * (double)m.x + (double)w.x) * inv;
+        const double a1 = (ns * (double)m.y + (double)w.y) * inv;
+        const double a2 = (ns * (double)m.z + (double)w.z) * inv;
+        const double a3 = (ns * (double)m.w + (double)w.w) * inv;
+        m4[i] = make_float4((float)a0, (float)a1, (float)a2, (float)a3);
+        __stcs(d4 + i, make_float4((float)((double)w.x - a0), (float)((double)w.y - a1),
+                                   (float)((double)w.z - a2), (float)((double)w.w - a3)));
+    }
+    for (long long i = (n4 << 2) + t0; i < n; i += stride) {   // tail (n % 4)
+        const double a = (ns * (double)mean[i] + (double)W[i]) * inv;
+        mean[i] = (float)a;
+        dev[i] = (float)((double)W[i] - a);
+    }
+}
+
+int ssi_swa_push_device(ssi_ctx* ctx, const float* dW, double n_scalar) {
+    if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
+    if (ctx->swa_K >= ctx->swa_Kmax) return ssi_fail(ctx, SSI_ERR_ARG, "deviation matrix is full (K_max=%lld)", (long long)ctx->swa_Kmax);
+    if (!(n_scalar >= 0)) return ssi_fail(ctx, SSI_ERR_ARG, "n_scalar must be >= 0");
+    const int64_t n = ctx->swa_n;
+    float* col = ctx->dDev + ctx->swa_K * n;
+    // float4 path needs 16-byte aligned columns: n % 4 == 0 or fall back to the scalar tail for all
+    const bool aligned = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(dW) & 15) == 0);
+    const int blocks = ctx->sm_count * 8;
+    // vec = 0: everything goes through the scalar tail loop
+    k_swa_push<<<blocks, 256, 0, ctx->stream>>>(dW, ctx->dSwaMean, col, n, n_scalar, 1.0 / (n_scalar + 1.0), aligned ? 1 : 0);
+    SSI_LAUNCH_CHECK(ctx);
+    ctx->swa_K++;
+    ctx->stats.last_bytes = 16.0 * (double)n;
+    ctx->stats.last_flops = 0;
+    ctx->stats.last_units = 0;
+    return SSI_OK;
+}
+
+// ======================================================================================
+// K6: Gram G = A'A (FP32 products, FP64 across row chunks, fixed-order slab reduction)
+// ======================================================================================
+#define GT 32
+#define GR 64
+__global__ void __launch_bounds__(256)
+k_gram_partial(const float* __restrict__ A, long long n, int K, int tiles, long long rows_per_slab,
+               double* __restrict__ partial /* slabs x K x K */) {
+    __shared__ float As[GR][GT + 1];
+    __shared__ float Bs[GR][GT + 1];
+    // blockIdx.y enumerates tile pairs (ta <= tb)
+    int ta = 0, rem = blockIdx.y;
+    while (rem >= tiles - ta) { rem -= tiles - ta; ++ta; }
+    const int tb = ta + rem;
+    const int a0 = ta * GT, b0 = tb * GT;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const long long r_begin = (long long)blockIdx.x * rows_per_slab;
+    const long long r_end = min(n, r_begin + rows_per_slab);
+
+    double acc[2][2] = {{0, 0}, {0, 0}};
+    float facc[2][2] = {{0, 0}, {0, 0}};
+    int chunk = 0;
+    for (long long r0 = r_begin; r0 < r_end; r0 += GR, ++chunk) {
+#pragma unroll
+        for (int s = 0; s < (GR * GT) / 256; ++s) {
+            const int idx = tid + s * 256;
+            const int r = idx & (GR - 1), c = idx >> 6;
+            const bool rv = (r0 + r < r_end);
+            As[r][c] = (rv && a0 + c < K) ? A[(r0 + r) + (long long)(a0 + c) * n] : 0.0f;
+            Bs[r][c] = (rv && b0 + c < K) ? A[(r0 + r) + (long long)(b0 + c) * n] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < GR; ++r) {
+            const float x0 = As[r][ty * 2], x1 = As[r][ty * 2 + 1];
+            const float y0 = Bs[r][tx * 2], y1 = Bs[r][tx * 2 + 1];
+            facc[0][0] = fmaf(x0, y0, facc[0][0]);
+            facc[0][1] = fmaf(x0, y1, facc[0][1]);
+            facc[1][0] = fmaf(x1, y0, facc[1][0]);
+            facc[1][1] = fmaf(x1, y1, facc[1][1]);
+        }
+        __syncthreads();
+        if ((chunk & 3) == 3) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) { acc[i][j] += (double)facc[i][j]; facc[i][j] = 0.0f; }
+        }
+    }
+    double* out = partial + (long long)blockIdx.x * K * K;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int a = a0 + ty * 2 + i, b = b0 + tx * 2 + j;
+            if (a < K && b < K) {
+                const double v = acc[i][j] + (double)facc[i][j];
+                out[a + (long long)b * K] = v;
+                if (ta != tb) out[b + (long long)a * K] = v;
+            }
+        }
+}
+
+__global__ void k_gram_reduce(const double* __restrict__ partial, int slabs, long long KK, double* __restrict__ G) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= KK) return;
+    double s = 0.0;
+    for (int p = 0; p < slabs; ++p) s += partial[(long long)p * KK + e];
+    G[e] = s;
+}
+
+int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int K, double* dG) {
+    const int tiles = (K + GT - 1) / GT;
+    const int pairs = tiles * (tiles + 1) / 2;
+    int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(2 * ctx->sm_count, (n + 1023) / 1024));
+    int64_t rows_per = (n + slabs - 1) / slabs;
+    rows_per = (rows_per + GR - 1) / GR * GR;
+    slabs = (int)((n + rows_per - 1) / rows_per);
+    SSI_TRY(ssi_reserve(ctx, ctx->bGram, sizeof(double) * (size_t)slabs * K * K));
+    double* partial = (double*)ctx->bGram.p;
+    if (pairs > 65535) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "too many deviation columns (K=%d)", K);
+    dim3 grid(slabs, pairs);
+    k_gram_partial<<<grid, 256, 0, ctx->stream>>>(dA, n, K, tiles, rows_per, partial);
+    SSI_LAUNCH_CHECK(ctx);
+    const long long KK = (long long)K * K;
+    k_gram_reduce<<<(unsigned)((KK + 255) / 256), 256, 0, ctx->stream>>>(partial, slabs, KK, dG);
+    SSI_LAUNCH_CHECK(ctx);
+    return SSI_OK;
+}
+
+int ssi_subspace_gram(ssi_ctx* ctx) {
+    // dP holds [P | W_swa] as an n x (M+1) column-major matrix
+    return ssi_gram_device(ctx, ctx->dP, ctx->model.n, ctx->M + 1, ctx->dSubGram);
+}
+
+// ======================================================================================
+// K7: symmetric eigen-solve, parallel cyclic Jacobi (round-robin pairs), FP64, one CTA
+// ======================================================================================
+#define JAC_MAXPAIRS 1024
+__global__ void __launch_bounds__(1024)
+k_jacobi(double* __restrict__ A /* K x K, destroyed */, double* __restrict__ V /* K x K out */, int K,
+         int max_sweeps, double* __restrict__ lambda /* K, sorted desc */, int* __restrict__ order /* K */,
+         int* __restrict__ sweeps_out) {
+    __shared__ double cs[JAC_MAXPAIRS], sn[JAC_MAXPAIRS];
+    __shared__ short pp[JAC_MAXPAIRS], qq[JAC_MAXPAIRS];
+    __shared__ double red[32];
+    __shared__ double s_off, s_tot;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int m = (K + 1) & ~1;          // even number of players; index K (if any) is a bye
+    const int np = m / 2;
+    const double tol = 4.0 * ((double)K * 2.220446049250313e-16) * ((double)K * 2.220446049250313e-16);
+
+    for (long long e = tid; e < (long long)K * K; e += nt) V[e] = ((e % K) == (e / K)) ? 1.0 : 0.0;
+    __syncthreads();
+
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        // convergence: off-diagonal mass relative to the whole matrix
+        double off = 0.0, tot = 0.0;
+        for (long long e = tid; e < (long long)K * K; e += nt) {
+            const double v = A[e];
+            tot += v * v;
+            if ((e % K) != (e / K)) off += v * v;
+        }
+        off = ssi_block_sum(off, red);
+        if (tid == 0) s_off = off;
+        tot = ssi_block_sum(tot, red);
+        if (tid == 0) s_tot = tot;
+        __syncthreads();
+        if (s_off <= tol * s_tot || s_tot == 0.0) break;
+
+        for (int r = 0; r < m - 1; ++r) {
+            // pairs of this round + their rotations
+            for (int i = tid; i < np; i += nt) {
+                int p, q;
+                if (i == 0) { p = m - 1; q = r; }
+                else { p = (r + i) % (m - 1); q = (r - i + (m - 1)) % (m - 1); }
+                if (p > q) { const int t = p; p = q; q = t; }
+                double c = 1.0, s = 0.0;
+                if (q < K) {
+                    const double apq = A[p + (long long)q * K];
+                    if (apq != 0.0) {
+                        const double app = A[p + (long long)p * K], aqq = A[q + (long long)q * K];
+                        const double tau = (aqq - app) / (2.0 * apq);
+                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + t * t);
+                        s = t * c;
+                    }
+                } else {
+                    q = -1;     // bye
+                }
+                pp[i] = (short)p; qq[i] = (short)q; cs[i] = c; sn[i] = s;
+            }
+            __syncthreads();
+            // A <- J' A J, one 2x2 block per (pair_k, pair_l): no cross-block hazards
+            for (int e = tid; e < np * np; e += nt) {
+                const int ik = e / np, il = e % np;
+                const int p = pp[ik], q = qq[ik], u = pp[il], v = qq[il];
+                const double ck = cs[ik], sk = sn[ik], cl = cs[il], sl = sn[il];
+                if (q < 0 && v < 0) continue;
+                if (q < 0) {            // single row p, columns (u,v): only the column rotation
+                    const double a = A[p + (long long)u * K], b = A[p + (long long)v * K];
+                    A[p + (long long)u * K] = cl * a - sl * b;
+                    A[p + (long long)v * K] = sl * a + cl * b;
+                } else if (v < 0) {     // rows (p,q), single column u: only the row rotation
+                    const double a = A[p + (long long)u * K], b = A[q + (long long)u * K];
+                    A[p + (long long)u * K] = ck * a - sk * b;
+                    A[q + (long long)u * K] = sk * a + ck * b;
+                } else {
+                    double a_pu = A[p + (long long)u * K], a_pv = A[p + (long long)v * K];
+                    double a_qu = A[q + (long long)u * K], a_qv = A[q + (long long)v * K];
+                    // columns (A J_l)
+                    const double t_pu = cl * a_pu - sl * a_pv, t_pv = sl * a_pu + cl * a_pv;
+                    const double t_qu = cl * a_qu - sl * a_qv, t_qv = sl * a_qu + cl * a_qv;
+                    // rows (J_k' .)
+                    A[p + (long long)u * K] = ck * t_pu - sk * t_qu;
+                    A[q + (long long)u * K] = sk * t_pu + ck * t_qu;
+                    A[p + (long long)v * K] = ck * t_pv - sk * t_qv;
+                    A[q + (long long)v * K] = sk * t_pv + ck * t_qv;
+                }
+            }
+            // V <- V J
+            for (int e = tid; e < np * K; e += nt) {
+                const int il = e / K, k = e % K;
+                const int u = pp[il], v = qq[il];
+                if (v < 0) continue;
+                const double cl = cs[il], sl = sn[il];
+                const double a = V[k + (long long)u * K], b = V[k + (long long)v * K];
+                V[k + (long long)u * K] = cl * a - sl * b;
+                V[k + (long long)v * K] = sl * a + cl * b;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // rank sort of the diagonal, descending (ties by index)
+    for (int i = tid; i < K; i += nt) {
+        const double li = A[i + (long long)i * K];
+        int rank = 0;
+        for (int j = 0; j < K; ++j) {
+            const double lj = A[j + (long long)j * K];
+            rank += (lj > li) || (lj == li && j < i);
+        }
+        lambda[rank] = li;
+        order[rank] = i;
+    }
+    if (tid == 0) *sweeps_out = sweep;
+}
+
+// ======================================================================================
+// K8: P = A V_M  (second pass over A; V_M staged in shared memory, zero-padded to MP columns)
+// ======================================================================================
+template <int MP>
+__global__ void __launch_bounds__(256)
+k_form_p(const float* __restrict__ A, long long n, int K, const double* __restrict__ V, const int* __restrict__ order,
+         int M, float* __restrict__ P, int vs_in_smem) {
+    extern __shared__ float Vs[];   // K x MP
+    if (vs_in_smem) {
+        for (int e = threadIdx.x; e < K * MP; e += blockDim.x) {
+            const int k = e / MP, j = e % MP;
+            Vs[e] = j < M ? (float)V[k + (long long)order[j] * K] : 0.0f;
+        }
+        __syncthreads();
+    }
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc[MP];
+#pragma unroll
+    for (int j = 0; j < MP; ++j) acc[j] = 0.0f;
+    for (int k = 0; k < K; ++k) {
+        const float d = __ldcs(A + i + (long long)k * n);
+        if (vs_in_smem) {
+#pragma unroll
+            for (int j = 0; j < MP; j += 4) {
+                const float4 v4 = *reinterpret_cast<const float4*>(Vs + k * MP + j);
+                acc[j] = fmaf(d, v4.x, acc[j]);
+                acc[j + 1] = fmaf(d, v4.y, acc[j + 1]);
+                acc[j + 2] = fmaf(d, v4.z, acc[j + 2]);
+                acc[j + 3] = fmaf(d, v4.w, acc[j + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < MP; ++j)
+                if (j < M) acc[j] = fmaf(d, (float)V[k + (long long)order[j] * K], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < MP; ++j)
+        if (j < M) P[i + (long long)j * n] = acc[j];
+}
+
+template <int MP>
+static int launch_form_p(ssi_ctx* ctx, const float* dA, int64_t n, int K, const double* dV, const int* dOrder, int M, float* dP) {
+    const size_t smem = sizeof(float) * (size_t)K * MP;
+    const int in_smem = smem <= 160 * 1024;
+    if (in_smem && smem > 48 * 1024)
+        SSI_CUDA(ctx, cudaFuncSetAttribute(k_form_p<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_form_p<MP><<<(unsigned)((n + 255) / 256), 256, in_smem ? smem : 0, ctx->stream>>>(dA, n, K, dV, dOrder, M, dP, in_smem);
+    SSI_LAUNCH_CHECK(ctx);
+    return SSI_OK;
+}
+
+__global__ void k_singular_values(const double* __restrict__ lambda, int K, double* __restrict__ s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K) s[i] = sqrt(fmax(lambda[i], 0.0));
+}
+
+// Gram + eigen + P for the collected deviation matrix; leaves P (n x M) in dP_out (device),
+// singular values (K doubles) in d_s.
+int ssi_swa_factor_device(ssi_ctx* ctx, int M, float* dP_out, double* d_s, int* sweeps_host) {
+    const int64_t n = ctx->swa_n;
+    const int K = (int)ctx->swa_K;
+    if (K < M || n < M) return ssi_fail(ctx, SSI_ERR_RANK, "deviation matrix is %lld x %d, cannot take M=%d columns", (long long)n, K, M);
+    if (M > SSI_MAX_M) return ssi_fail(ctx, SSI_ERR_ARG, "M=%d exceeds the supported maximum %d", M, SSI_MAX_M);
+    if (K > 2 * JAC_MAXPAIRS) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "K=%d exceeds the eigen-solver limit %d", K, 2 * JAC_MAXPAIRS);
+    // layout of bEig: G (K*K) | V (K*K) | lambda (K) | order (K ints) | sweeps (int)
+    const size_t KK = (size_t)K * K;
+    SSI_TRY(ssi_reserve(ctx, ctx->bEig, sizeof(double) * (2 * KK + K) + sizeof(int) * (K + 2)));
+    double* dG = (double*)ctx->bEig.p;
+    double* dV = dG + KK;
+    double* dLam = dV + KK;
+    int* dOrder = (int*)(dLam + K);
+    int* dSweeps = dOrder + K;
+    SSI_TRY(ssi_gram_device(ctx, ctx->dDev, n, K, dG));
+    k_jacobi<<<1, 1024, 0, ctx->stream>>>(dG, dV, K, 60, dLam, dOrder, dSweeps);
+    SSI_LAUNCH_CHECK(ctx);
+    k_singular_values<<<(K + 127) / 128, 128, 0, ctx->stream>>>(dLam, K, d_s);
+    SSI_LAUNCH_CHECK(ctx);
+    int rc;
+    if (M <= 4) rc = launch_form_p<4>(ctx, ctx->dDev, n, K, dV, dOrder, M, dP_out);
+    else if (M <= 8) rc = launch_form_p<8>(ctx, ctx->dDev, n, K, dV, dOrder, M, dP_out);
+    else if (M <= 16) rc = launch_form_p<16>(ctx, ctx->dDev, n, K, dV, dOrder, M, dP_out);
+    else if (M <= 24) rc = launch_form_p<24>(ctx, ctx->dDev, n, K, dV, dOrder, M, dP_out);
+    else if (M <= 32) rc = launch_form_p<32>(ctx, ctx->dDev, n, K, dV, dOrder, M, dP_out);
+    else if (M <= 48) rc = launch_form_p<48>(ctx, ctx->dDev, n, K, dV, dOrder, M, dP_out);
+    else rc = launch_form_p<64>(ctx, ctx->dDev, n, K, dV, dOrder, M, dP_out);
+    if (rc != SSI_OK) return rc;
+    if (sweeps_host) {
+        SSI_CUDA(ctx, cudaMemcpyAsync(sweeps_host, dSweeps, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ctx->stats.last_bytes = 4.0 * (double)n * K * 2 + 4.0 * (double)n * M;
+    ctx->stats.last_flops = 2.0 * (double)n * K * K + 2.0 * (double)n * K * M;
+    ctx->stats.last_units = 0;
+    return SSI_OK;
+}

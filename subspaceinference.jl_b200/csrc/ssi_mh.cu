@@ -1,0 +1,126 @@
+// ssi_mh.cu — random-walk Metropolis-Hastings kept on the device over many chains.
+//
+// Replaces `sample(DensityModel(density), RWMH(MvNormal(zeros(M), sigma_z)), itr)`
+// (src/space_inference.jl:111-116; AdvancedMH 0.6.2 semantics):
+//   * sample 0 is a draw from the proposal and counts as the first of n_steps;
+//   * step t proposes z' = z + sigma_z * eps_t and accepts iff  -e_t < lp(z') - lp(z)
+//     with e_t ~ Exp(1)  (AdvancedMH tests `-randexp(rng) < log_alpha`);
+//   * the log-density of the current state is cached, one evaluation per step.
+// The reference runs ONE chain sequentially; here every step evaluates all chains'
+// proposals in one batched log-posterior call.  No host round-trip inside the loop.
+#include "ssi_common.cuh"
+#include "ssi_rng.cuh"
+
+#include <algorithm>
+
+// zp[m,c] = z[m,c] + sigma_z * eps(chain_off + c, step, m); with init: z = 0.
+__global__ void __launch_bounds__(256)
+k_mh_propose(const float* __restrict__ z, float* __restrict__ zp, long long n_chains, int M, unsigned long long seed,
+             long long chain_off, unsigned step, float sigma_z, int init) {
+    // one thread per (chain, block of 4 normals)
+    const int nblk = (M + 3) >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_chains * nblk) return;
+    const long long c = t / nblk;
+    const int blk = (int)(t % nblk);
+    float e[4];
+    ssi_normal4(seed, (uint32_t)(chain_off + c), step, (uint32_t)blk, e);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int m = blk * 4 + r;
+        if (m < M) {
+            const float base = init ? 0.0f : z[m + c * M];
+            zp[m + c * M] = __fmaf_rn(sigma_z, e[r], base);
+        }
+    }
+}
+
+// accept/reject + trace write for step `step`.
+__global__ void __launch_bounds__(256)
+k_mh_accept(float* __restrict__ z, const float* __restrict__ zp, double* __restrict__ lp, const double* __restrict__ lpp,
+            long long n_chains, int M, unsigned long long seed, long long chain_off, unsigned step, int force,
+            float* __restrict__ z_trace, double* __restrict__ lp_trace, unsigned char* __restrict__ acc_trace,
+            unsigned long long* __restrict__ n_acc) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned accepted = 0;
+    if (c < n_chains) {
+        bool acc;
+        if (force) {
+            acc = true;
+        } else {
+            const double e = ssi_exp1(seed, (uint32_t)(chain_off + c), step);
+            const double log_alpha = lpp[c] - lp[c];
+            acc = (-e < log_alpha);          // NaN proposal density -> reject
+        }
+        if (acc) {
+            lp[c] = lpp[c];
+            for (int m = 0; m < M; ++m) z[m + c * M] = zp[m + c * M];
+        }
+        if (z_trace) {
+            float* dst = z_trace + ((long long)step * n_chains + c) * M;
+            for (int m = 0; m < M; ++m) dst[m] = z[m + c * M];
+        }
+        if (lp_trace) lp_trace[(long long)step * n_chains + c] = lp[c];
+        if (acc_trace) acc_trace[(long long)step * n_chains + c] = acc ? 1 : 0;
+        accepted = (acc && !force) ? 1u : 0u;
+    }
+    const unsigned warp_cnt = __popc(__ballot_sync(0xffffffffu, accepted));
+    if ((threadIdx.x & 31) == 0 && warp_cnt) atomicAdd(n_acc, (unsigned long long)warp_cnt);
+}
+
+int ssi_mh_device(ssi_ctx* ctx, int64_t C, int64_t S, uint64_t seed, int64_t chain_off,
+                  double sigma_z, double sigma_m, double sigma_p, uint32_t mask,
+                  const float* d_z0, float* d_ztr, double* d_lptr, uint8_t* d_acctr) {
+    if (!ctx->has_model || !ctx->has_data || !ctx->has_sub)
+        return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before sampling");
+    if (C <= 0 || S <= 0) return ssi_fail(ctx, SSI_ERR_ARG, "n_chains and n_steps must be positive");
+    if (chain_off < 0 || chain_off + C > 0xffffffffll || S > 0xffffffffll)
+        return ssi_fail(ctx, SSI_ERR_ARG, "chain ids and steps must fit 32 bits");
+    const int M = ctx->M;
+    SSI_TRY(ssi_reserve(ctx, ctx->bMhZ, sizeof(float) * (size_t)M * C));
+    SSI_TRY(ssi_reserve(ctx, ctx->bMhZp, sizeof(float) * (size_t)M * C));
+    SSI_TRY(ssi_reserve(ctx, ctx->bMhLp, sizeof(double) * (size_t)C));
+    SSI_TRY(ssi_reserve(ctx, ctx->bMhLpP, sizeof(double) * (size_t)C));
+    SSI_TRY(ssi_reserve(ctx, ctx->bMhCnt, sizeof(unsigned long long)));
+    float* z = (float*)ctx->bMhZ.p;
+    float* zp = (float*)ctx->bMhZp.p;
+    double* lp = (double*)ctx->bMhLp.p;
+    double* lpp = (double*)ctx->bMhLpP.p;
+    unsigned long long* cnt = (unsigned long long*)ctx->bMhCnt.p;
+    SSI_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), ctx->stream));
+
+    const int nblk = (M + 3) / 4;
+    const unsigned g_prop = (unsigned)((C * nblk + 255) / 256);
+    const unsigned g_acc = (unsigned)((C + 255) / 256);
+    double units = 0, flops = 0;
+    int64_t launches0 = ctx->stats.kernel_launches;
+    (void)launches0;
+
+    for (int64_t t = 0; t < S; ++t) {
+        if (t == 0 && d_z0) {
+            SSI_CUDA(ctx, cudaMemcpyAsync(zp, d_z0, sizeof(float) * (size_t)M * C, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            k_mh_propose<<<g_prop, 256, 0, ctx->stream>>>(z, zp, C, M, seed, chain_off, (unsigned)t, (float)sigma_z, t == 0);
+            SSI_LAUNCH_CHECK(ctx);
+        }
+        SSI_TRY(ssi_logpost_device(ctx, zp, C, sigma_m, sigma_p, sigma_z, mask, lpp, nullptr));
+        units += ctx->stats.last_units;
+        flops += ctx->stats.last_flops;
+        k_mh_accept<<<g_acc, 256, 0, ctx->stream>>>(z, zp, lp, lpp, C, M, seed, chain_off, (unsigned)t, t == 0,
+                                                  d_ztr, d_lptr, d_acctr, cnt);
+        SSI_LAUNCH_CHECK(ctx);
+    }
+    ctx->stats.last_units = units;
+    ctx->stats.last_flops = flops;
+    ctx->stats.mh_proposals = C * (S - 1);
+    return SSI_OK;
+}
+
+int ssi_mh_fetch_accepts(ssi_ctx* ctx) {
+    unsigned long long h = 0;
+    if (!ctx->bMhCnt.p) return SSI_OK;
+    SSI_CUDA(ctx, cudaMemcpyAsync(&h, ctx->bMhCnt.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.mh_accepts = (int64_t)h;
+    return SSI_OK;
+}

@@ -1,0 +1,184 @@
+"""Thin object wrapper over the C ABI: one Engine == one ssi_ctx == one GPU."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import SsiError, Stats, TERM_LL
+
+
+def _f32(a, order="F") -> np.ndarray:
+    return np.require(np.asarray(a, dtype=np.float32), requirements=["ALIGNED", "F_CONTIGUOUS" if order == "F" else "C_CONTIGUOUS"])
+
+
+def _ptr(a) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(None)
+
+
+class Engine:
+    """Owns a device context.  Matrices are passed in the reference's (Julia) orientation:
+    X (in0, N), Y (O, N), P (n, M), Z (M, B); they are handed to the library column-major."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.ssi_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise SsiError(rc, self._lib.ssi_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+        self.dims: tuple[int, ...] | None = None
+        self.M = 0
+        self.N = 0
+        self.n = 0
+
+    # ---- plumbing -------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise SsiError(rc, self._lib.ssi_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ssi_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_option(self, key: str, value: int):
+        self._check(self._lib.ssi_set_option(self._h, key.encode(), int(value)))
+
+    def set_stream(self, cuda_stream_handle: int | None):
+        self._check(self._lib.ssi_set_stream(self._h, C.c_void_p(cuda_stream_handle or None)))
+
+    def sync(self):
+        self._check(self._lib.ssi_sync(self._h))
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._check(self._lib.ssi_stats(self._h, C.byref(s)))
+        return s
+
+    # ---- captured state of the density closure -----------------------------------------
+    def set_model(self, dims: Sequence[int], acts: Sequence[int]):
+        dims_a = np.asarray(dims, dtype=np.int32)
+        acts_a = np.asarray(acts, dtype=np.int32)
+        if len(acts_a) != len(dims_a) - 1:
+            raise ValueError("need one activation per layer")
+        self._check(self._lib.ssi_set_model(self._h, len(acts_a), _ptr(dims_a), _ptr(acts_a)))
+        self.dims = tuple(int(d) for d in dims_a)
+        self.n = int(sum(dims_a[l] * dims_a[l + 1] + dims_a[l + 1] for l in range(len(acts_a))))
+
+    def set_data(self, X, Y):
+        X, Y = _f32(X), _f32(Y)
+        if X.ndim != 2 or Y.ndim != 2 or X.shape[1] != Y.shape[1]:
+            raise ValueError("X must be (in0, N) and Y (O, N)")
+        if self.dims is None or X.shape[0] != self.dims[0] or Y.shape[0] != self.dims[-1]:
+            raise ValueError("data shape does not match the model")
+        self._check(self._lib.ssi_set_data(self._h, _ptr(X), _ptr(Y), X.shape[1]))
+        self.N = int(X.shape[1])
+
+    def set_subspace(self, W_swa, P):
+        W_swa, P = _f32(W_swa), _f32(P)
+        if P.ndim != 2 or W_swa.ndim != 1 or P.shape[0] != W_swa.shape[0]:
+            raise ValueError("W_swa must be (n,) and P (n, M)")
+        self._check(self._lib.ssi_set_subspace(self._h, _ptr(W_swa), _ptr(P), P.shape[0], P.shape[1]))
+        self.M = int(P.shape[1])
+
+    # ---- density(z), batched -----------------------------------------------------------
+    def logpost(self, Z, sigma_m=1.0, sigma_p=1.0, sigma_z=1.0, mask=TERM_LL, return_terms=False):
+        Z = _f32(Z)
+        if Z.ndim == 1:
+            Z = Z.reshape(-1, 1, order="F")
+        if Z.shape[0] != self.M:
+            raise ValueError(f"Z must have M={self.M} rows")
+        B = Z.shape[1]
+        lp = np.empty(B, np.float64)
+        terms = np.empty((B, 3), np.float64) if return_terms else None
+        self._check(self._lib.ssi_logpost_batch(self._h, _ptr(Z), B, sigma_m, sigma_p, sigma_z, mask, _ptr(lp), _ptr(terms)))
+        return (lp, terms.T.copy()) if return_terms else lp
+
+    def logpost_dev(self, dZ_ptr: int, B: int, d_lp_ptr: int, sigma_m=1.0, sigma_p=1.0, sigma_z=1.0, mask=TERM_LL,
+                    d_terms_ptr: int | None = None):
+        """Device-pointer variant (asynchronous on the context stream)."""
+        self._check(self._lib.ssi_logpost_batch_dev(self._h, C.c_void_p(dZ_ptr), B, sigma_m, sigma_p, sigma_z, mask,
+                                                    C.c_void_p(d_lp_ptr), C.c_void_p(d_terms_ptr or None)))
+
+    def project(self, Z) -> np.ndarray:
+        """W_swa + P z for every column of Z: (n, B)."""
+        Z = _f32(Z)
+        if Z.ndim == 1:
+            Z = Z.reshape(-1, 1, order="F")
+        W = np.empty((self.n, Z.shape[1]), np.float32, order="F")
+        self._check(self._lib.ssi_project(self._h, _ptr(Z), Z.shape[1], _ptr(W)))
+        return W
+
+    # ---- RWMH ------------------------------------------------------------------------------
+    def mh_run(self, n_chains: int, n_steps: int, seed: int, sigma_z=1.0, sigma_m=1.0, sigma_p=1.0, mask=TERM_LL,
+               chain_offset: int = 0, z0=None, want_z=True, want_lp=True, want_accept=True):
+        """Returns (z_trace (M, n_chains, n_steps) f32, lp_trace (n_chains, n_steps) f64,
+        accept (n_chains, n_steps) u8); entries not requested are None."""
+        zt = np.empty((self.M, n_chains, n_steps), np.float32, order="F") if want_z else None
+        lt = np.empty((n_chains, n_steps), np.float64, order="F") if want_lp else None
+        at = np.empty((n_chains, n_steps), np.uint8, order="F") if want_accept else None
+        z0a = _f32(z0) if z0 is not None else None
+        if z0a is not None and z0a.shape != (self.M, n_chains):
+            raise ValueError("z0 must be (M, n_chains)")
+        self._check(self._lib.ssi_mh_run(self._h, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, mask,
+                                         _ptr(z0a), _ptr(zt), _ptr(lt), _ptr(at)))
+        return zt, lt, at
+
+    def mh_run_dev(self, n_chains: int, n_steps: int, seed: int, sigma_z=1.0, sigma_m=1.0, sigma_p=1.0, mask=TERM_LL,
+                   chain_offset: int = 0, d_z0: int | None = None, d_z_trace: int | None = None,
+                   d_lp_trace: int | None = None, d_accept: int | None = None):
+        self._check(self._lib.ssi_mh_run_dev(self._h, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, mask,
+                                             C.c_void_p(d_z0 or None), C.c_void_p(d_z_trace or None),
+                                             C.c_void_p(d_lp_trace or None), C.c_void_p(d_accept or None)))
+
+    def rng_replay(self, seed: int, chain: int, step: int, M: int | None = None):
+        M = self.M if M is None else M
+        eps = np.empty(M, np.float32)
+        e = C.c_double()
+        rc = self._lib.ssi_rng_replay(seed, chain, step, M, _ptr(eps), C.byref(e))
+        if rc != 0:
+            raise SsiError(rc, "ssi_rng_replay: bad arguments")
+        return eps, e.value
+
+    # ---- construction streams ----------------------------------------------------------------
+    def swa_begin(self, n: int, K_max: int):
+        self._check(self._lib.ssi_swa_begin(self._h, n, K_max))
+        self._swa_n = int(n)
+
+    def swa_push(self, W, n_scalar: float):
+        W = _f32(W).reshape(-1)
+        if W.shape[0] != self._swa_n:
+            raise ValueError("snapshot length does not match ssi_swa_begin")
+        self._check(self._lib.ssi_swa_push(self._h, _ptr(W), float(n_scalar)))
+
+    def swa_push_dev(self, dW_ptr: int, n_scalar: float):
+        self._check(self._lib.ssi_swa_push_dev(self._h, C.c_void_p(dW_ptr), float(n_scalar)))
+
+    def swa_columns(self) -> int:
+        return int(self._lib.ssi_swa_columns(self._h))
+
+    def swa_finish(self, M: int, install: bool = False, want_P: bool = True):
+        n, K = self._swa_n, self.swa_columns()
+        W_swa = np.empty(n, np.float32)
+        P = np.empty((n, M), np.float32, order="F") if want_P else None
+        s = np.empty(max(K, 1), np.float64)
+        self._check(self._lib.ssi_swa_finish(self._h, M, _ptr(W_swa), _ptr(P), _ptr(s), int(install)))
+        if install:
+            self.M = M
+        return W_swa, P, s[:K]

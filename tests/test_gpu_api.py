@@ -1,0 +1,42 @@
+"""The reference-facing functions (host mirror) end to end, README-style."""
+import numpy as np
+import pytest
+
+import ssi_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_readme_example(ssi, capsys):
+    """README.md:46-80 with the reference's sizes: 10-20-20-2, N=100, M=3, T=10, c=1, itr=10."""
+    rng = np.random.default_rng(0)
+    X = rng.random((10, 100)).astype(np.float32)
+    Y = rng.random((2, 100)).astype(np.float32)
+    data = ssi.DataLoader(X, Y, batchsize=20, shuffle=True, rng=rng)
+    m = ssi.Chain(ssi.Dense(10, 20, rng=rng), ssi.Dense(20, 20, rng=rng), ssi.Dense(20, 2, rng=rng))
+    L1 = lambda mm, x, y: ssi.mse(mm(x), y)
+    chn, lp, W_swa = ssi.subspace_inference(m, L1, data, ssi.ADAM(0.01), itr=10, T=10, c=1, M=3, seed=5)
+    assert len(chn) == 10 and chn[0].shape == (682,) and lp.shape == (10,) and W_swa.shape == (682,)
+    assert "Traing loss" in capsys.readouterr().out
+    # every returned lp is the oracle density of the returned weight vector (likelihood only)
+    for w, l in zip(chn, lp):
+        pred = orc.forward(w, m.dims, m.acts, X)
+        np.testing.assert_allclose(l, orc.gaussian_loglik(pred, Y, 1.0), rtol=1e-5)
+
+
+def test_construction_then_inference_alias(ssi):
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((13, 400)).astype(np.float32)
+    Y = rng.standard_normal((1, 400)).astype(np.float32)
+    data = ssi.DataLoader(X, Y, batchsize=100)
+    m = ssi.Chain(ssi.Dense(13, 50, ssi.relu, rng=rng), ssi.Dense(50, 1, rng=rng))
+    L = lambda mm, x, y: ssi.mse(mm(x), y)
+    W_swa, P = ssi.subspace_construction(m, L, data, ssi.Descent(0.05), T=5, c=1, M=5, print_freq=10)
+    assert W_swa.shape == (751,) and P.shape == (751, 5)
+    zt, lt = ssi.inference(m, data, W_swa, P, σ_z=0.1, σ_m=0.5, itr=20, M=5, alg=":mh", n_chains=8, seed=3)
+    assert zt.shape == (5, 8, 20) and lt.shape == (8, 20)
+    prob = orc.Problem(m.dims, m.acts, X, Y, W_swa, P)
+    ref = orc.density(prob, zt[:, 3, 19], 0.5)
+    np.testing.assert_allclose(lt[3, 19], ref, rtol=1e-5)
+    with pytest.raises(ValueError):
+        ssi.inference(m, data, W_swa, P, M=4)                # P has 5 columns

@@ -1,0 +1,97 @@
+"""Subspace construction streams vs the oracle: W_swa and P within 1e-4 (P up to column sign)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import ssi_oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+def _run(engine, snaps, ns, M, install=False):
+    n = snaps[0].shape[0]
+    engine.swa_begin(n, len(snaps))
+    for w, s in zip(snaps, ns):
+        engine.swa_push(w, s)
+    assert engine.swa_columns() == len(snaps)
+    return engine.swa_finish(M, install=install)
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def test_golden_construction(ssi, engine):
+    g = np.load(GOLD / "construct_small.npz")
+    W_swa, P, s = _run(engine, list(g["snapshots"]), g["n_scalars"], int(g["M"]))
+    assert _rel(W_swa, g["W_swa"]) < 1e-4
+    assert _rel(orc.align_signs(P.astype(np.float64), g["P"]), g["P"]) < 1e-4
+    np.testing.assert_allclose(s[:3], g["s"][:3], rtol=1e-5)
+
+
+@pytest.mark.parametrize("n,K,M", [(682, 15, 3), (1001, 40, 5), (4096, 100, 20), (37, 64, 4), (50000, 33, 20)])
+def test_random_snapshots_vs_oracle(ssi, engine, n, K, M):
+    rng = np.random.default_rng(n * 1000 + K)
+    w = rng.standard_normal(n) * 0.1
+    # a few dominant drift directions + noise, so that the top-M singular values are separated
+    dirs = rng.standard_normal((M, n)) * (2.0 ** -np.arange(M))[:, None]
+    snaps, ns = [], []
+    for k in range(K):
+        w = w + dirs.T @ rng.standard_normal(M) * 0.05 + 1e-3 * rng.standard_normal(n)
+        snaps.append(w.astype(np.float32))
+        ns.append(float(k // 4 + 1))          # several mini-batches share one epoch index (Q2)
+    W_swa, P, s = _run(engine, snaps, ns, M)
+    W_ref, P_ref, s_ref, A = orc.construct_from_snapshots(snaps, ns, M)
+    assert _rel(W_swa, W_ref) < 1e-4
+    np.testing.assert_allclose(s[:M], s_ref[:M], rtol=1e-4)
+    assert _rel(orc.align_signs(P.astype(np.float64), P_ref), P_ref) < 1e-4
+    # P columns orthogonal with norms s_k
+    G = P.astype(np.float64).T @ P.astype(np.float64)
+    np.testing.assert_allclose(G, np.diag(s_ref[:M] ** 2), atol=2e-4 * s_ref[0] ** 2)
+
+
+def test_more_columns_than_parameters(ssi, engine):
+    """README example: batchsize-1 loader, T=10 -> K = 1000 columns > n = 682 (Q3); here a
+    reduced K=300 > n=120 keeps the eigen-solve short."""
+    rng = np.random.default_rng(9)
+    n, K, M = 120, 300, 3
+    w = rng.standard_normal(n)
+    dirs = rng.standard_normal((M, n)) * np.array([4.0, 2.0, 1.0])[:, None]
+    snaps, ns = [], []
+    for k in range(K):
+        w = w + dirs.T @ rng.standard_normal(M) * 0.1 + 1e-3 * rng.standard_normal(n)
+        snaps.append(w.astype(np.float32))
+        ns.append(float(k // 100 + 1))
+    W_swa, P, s = _run(engine, snaps, ns, M)
+    W_ref, P_ref, s_ref, _ = orc.construct_from_snapshots(snaps, ns, M)
+    assert _rel(W_swa, W_ref) < 1e-4
+    assert _rel(orc.align_signs(P.astype(np.float64), P_ref), P_ref) < 1e-4
+    assert np.all(s[n:] < 1e-3 * s[0])       # rank <= n
+
+
+def test_rank_error_and_install(ssi, engine):
+    rng = np.random.default_rng(4)
+    dims, acts = (10, 20, 20, 2), (0, 0, 0)
+    n = orc.n_params(dims)
+    snaps = [orc.glorot_flat(rng, dims) for _ in range(6)]
+    engine.swa_begin(n, 6)
+    for k in range(2):
+        engine.swa_push(snaps[k], 1.0)
+    with pytest.raises(ssi.SsiError) as ei:
+        engine.swa_finish(3)                 # U[:,1:M] would throw in the reference
+    assert ei.value.code == -4
+    for k in range(2, 6):
+        engine.swa_push(snaps[k], 2.0)
+    with pytest.raises(ssi.SsiError):
+        engine.swa_push(snaps[0], 3.0)       # K_max reached
+    engine.set_model(dims, acts)
+    X = rng.random((10, 50)).astype(np.float32)
+    Y = rng.random((2, 50)).astype(np.float32)
+    engine.set_data(X, Y)
+    W_swa, P, _ = engine.swa_finish(3, install=True)
+    Z = rng.standard_normal((3, 4)).astype(np.float32)
+    lp = engine.logpost(Z)
+    ref, _ = orc.logpost_batch(orc.Problem(dims, acts, X, Y, W_swa, P), Z)
+    np.testing.assert_allclose(lp, ref, rtol=1e-5)

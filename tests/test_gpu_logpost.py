@@ -1,0 +1,134 @@
+"""Parity of the CUDA log-posterior path against the Float64 oracle and the golden fixtures.
+Tolerance: 1e-5 relative on every per-sample log-prob (north_star), FP32 device arithmetic."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import ssi_oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+RTOL = 1e-5
+
+
+def _setup(engine, prob):
+    engine.set_model(prob.dims, prob.acts)
+    engine.set_data(prob.X, prob.Y)
+    engine.set_subspace(prob.W_swa, prob.P)
+
+
+def _paths_for(ssi, prob):
+    paths = [ssi.PATH_LAYERED]
+    if orc.n_params(prob.dims) < 12000:
+        paths.append(ssi.PATH_FUSED)
+    return paths
+
+
+@pytest.mark.parametrize("name", ["readme", "uci_small", "wide_small"])
+def test_golden_all_terms(ssi, engine, name):
+    g = np.load(GOLD / f"logpost_{name}.npz")
+    prob = orc.Problem(tuple(int(d) for d in g["dims"]), tuple(int(a) for a in g["acts"]), g["X"], g["Y"], g["W_swa"], g["P"])
+    _setup(engine, prob)
+    sm, sp, sz = float(g["sigma_m"]), float(g["sigma_p"]), float(g["sigma_z"])
+    for path in _paths_for(ssi, prob) + [ssi.PATH_AUTO]:
+        engine.set_option("path", path)
+        lp, terms = engine.logpost(g["Z"], sm, sp, sz, mask=7, return_terms=True)
+        np.testing.assert_allclose(terms, g["terms"], rtol=RTOL, err_msg=f"path {path}")
+        np.testing.assert_allclose(lp, g["terms"].sum(axis=0), rtol=RTOL)
+        # reference as executed: likelihood only (Q1); sigma_p must not matter
+        lp_ll = engine.logpost(g["Z"], sm, 123.0, sz)
+        np.testing.assert_allclose(lp_ll, g["terms"][0], rtol=RTOL)
+        assert engine.stats().last_path == (path if path != ssi.PATH_AUTO else engine.stats().last_path)
+
+
+@pytest.mark.parametrize("dims,acts,N,M,B", [
+    ((10, 20, 20, 2), (0, 0, 0), 100, 3, 1),          # README, one z at a time like the reference
+    ((13, 50, 1), (1, 0), 777, 5, 37),                # ragged N, odd B
+    ((5, 7, 3), (2, 3), 130, 2, 9),                   # tanh / sigmoid, widths not multiples of 4
+    ((3, 1), (0,), 1, 1, 3),                          # single layer, single datapoint
+    ((33, 65, 17, 9, 4), (1, 2, 1, 0), 257, 6, 5),    # deeper chain
+])
+def test_random_shapes_vs_oracle(ssi, engine, dims, acts, N, M, B):
+    rng = np.random.default_rng(hash((dims, N, M, B)) % (2 ** 32))
+    n = orc.n_params(dims)
+    prob = orc.Problem(dims, acts, rng.standard_normal((dims[0], N)).astype(np.float32),
+                       rng.standard_normal((dims[-1], N)).astype(np.float32), orc.glorot_flat(rng, dims),
+                       (0.3 * rng.standard_normal((n, M))).astype(np.float32))
+    Z = rng.standard_normal((M, B)).astype(np.float32)
+    _setup(engine, prob)
+    ref, ref_terms = orc.logpost_batch(prob, Z, 0.7, 1.3, 0.9, mask=7)
+    for path in (ssi.PATH_FUSED, ssi.PATH_LAYERED):
+        engine.set_option("path", path)
+        lp, terms = engine.logpost(Z, 0.7, 1.3, 0.9, mask=7, return_terms=True)
+        np.testing.assert_allclose(terms, ref_terms, rtol=RTOL, err_msg=f"path {path}")
+        np.testing.assert_allclose(lp, ref, rtol=RTOL)
+
+
+def test_batch_invariance_bitwise(ssi, engine):
+    """A sample's lp must not depend on which other samples share the call (fixed-order
+    reductions): this is what makes chain sharding over GPUs reproduce the 1-GPU trace."""
+    prob = orc.make_problem("uci", N=3000)
+    _setup(engine, prob)
+    Z = (0.1 * np.random.default_rng(0).standard_normal((prob.M, 64))).astype(np.float32)
+    for path in (ssi.PATH_FUSED, ssi.PATH_LAYERED):
+        engine.set_option("path", path)
+        full = engine.logpost(Z, 0.1)
+        part = np.concatenate([engine.logpost(Z[:, :5], 0.1), engine.logpost(Z[:, 5:40], 0.1), engine.logpost(Z[:, 40:], 0.1)])
+        np.testing.assert_array_equal(full, part)
+
+
+def test_uci_full_size_properties(ssi, engine):
+    """Full C2 size (N=10k, B=4096): oracle on a sample of columns + permutation invariance."""
+    prob = orc.make_problem("uci")
+    _setup(engine, prob)
+    rng = np.random.default_rng(1)
+    Z = (0.1 * rng.standard_normal((prob.M, 4096))).astype(np.float32)
+    lp = engine.logpost(Z, 0.1)
+    idx = rng.choice(4096, 12, replace=False)
+    ref, _ = orc.logpost_batch(prob, Z[:, idx], 0.1)
+    np.testing.assert_allclose(lp[idx], ref, rtol=RTOL)
+    perm = rng.permutation(prob.N)
+    engine.set_data(prob.X[:, perm], prob.Y[:, perm])
+    lp2 = engine.logpost(Z[:, :256], 0.1)
+    np.testing.assert_allclose(lp2, lp[:256], rtol=2e-6)
+    assert engine.stats().last_units == 256 * prob.N
+
+
+def test_project_matches_oracle(ssi, engine):
+    prob = orc.make_problem("readme")
+    _setup(engine, prob)
+    Z = np.random.default_rng(2).standard_normal((3, 11)).astype(np.float32)
+    W = engine.project(Z)
+    ref = np.stack([orc.project(prob.W_swa, prob.P, Z[:, b]) for b in range(11)], axis=1)
+    np.testing.assert_allclose(W, ref, rtol=1e-6, atol=1e-6)
+
+
+def test_error_behaviour(ssi):
+    eng = ssi.Engine(0)
+    try:
+        with pytest.raises(ssi.SsiError) as ei:
+            eng._check(eng._lib.ssi_logpost_batch(eng._h, None, 0, 1.0, 1.0, 1.0, 1, None, None) or
+                       eng._lib.ssi_set_data(eng._h, None, None, 5))
+        assert ei.value.code in (-1, -3)
+        eng.set_model((4, 3, 2), (1, 0))
+        with pytest.raises(ssi.SsiError) as ei:
+            eng.set_subspace(np.zeros(5, np.float32), np.zeros((5, 2), np.float32))   # wrong n
+        assert ei.value.code == -1
+        prob_n = orc.n_params((4, 3, 2))
+        eng.set_subspace(np.zeros(prob_n, np.float32), np.zeros((prob_n, 2), np.float32))
+        eng.M = 2
+        with pytest.raises(ssi.SsiError) as ei:
+            eng.logpost(np.zeros((2, 1), np.float32))                                 # data not set
+        assert ei.value.code == -3
+        eng.set_data(np.zeros((4, 6), np.float32), np.zeros((2, 6), np.float32))
+        with pytest.raises(ssi.SsiError):
+            eng.logpost(np.zeros((2, 1), np.float32), sigma_m=0.0)
+        with pytest.raises(ssi.SsiError):
+            eng.logpost(np.zeros((2, 1), np.float32), mask=0)
+        assert eng.logpost(np.zeros((2, 0), np.float32)).shape == (0,)                # empty batch
+        # all-zero weights: pred = 0, lp = closed form of |Y|^2 = 0
+        lp = eng.logpost(np.zeros((2, 3), np.float32), sigma_m=2.0)
+        np.testing.assert_allclose(lp, -0.5 * 12 * np.log(2 * np.pi) - 12 * np.log(2.0), rtol=1e-12)
+    finally:
+        eng.close()

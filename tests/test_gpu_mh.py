@@ -1,0 +1,115 @@
+"""RWMH on the device vs the oracle: identical proposal/uniform stream, identical decisions."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import ssi_oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+def _setup(engine, prob):
+    engine.set_model(prob.dims, prob.acts)
+    engine.set_data(prob.X, prob.Y)
+    engine.set_subspace(prob.W_swa, prob.P)
+
+
+def _check_against_oracle(prob, zt, lt, at, seed, sigma_z, sigma_m, chain_ids, tie_tol=1e-6):
+    """Teacher-forced decision check: from the device's own state at t-1, the oracle (Float64,
+    replayed stream) must take the same decision unless the margin is within tie_tol*|lp|."""
+    near_ties = 0
+    for ci, c in enumerate(chain_ids):
+        z = zt[:, ci, :].T
+        np.testing.assert_array_equal(z[0], orc.propose_f32(np.zeros(prob.M, np.float32), sigma_z, orc.rng_normals(seed, c, 0, prob.M)))
+        for t in range(1, z.shape[0]):
+            zp = orc.propose_f32(z[t - 1], sigma_z, orc.rng_normals(seed, c, t, prob.M))
+            lp_prev = orc.density(prob, z[t - 1], sigma_m)
+            lp_prop = orc.density(prob, zp, sigma_m)
+            margin = lp_prop - lp_prev + orc.rng_exponential(seed, c, t)
+            if abs(margin) <= tie_tol * max(1.0, abs(lp_prev)):
+                near_ties += 1
+                continue
+            assert bool(at[ci, t]) == (margin > 0), f"decision differs at chain {c} step {t}, margin {margin}"
+            expect = zp if margin > 0 else z[t - 1]
+            np.testing.assert_allclose(z[t], expect, rtol=0, atol=np.abs(expect).max() * 2.4e-7 + 1e-12)
+            np.testing.assert_allclose(lt[ci, t], lp_prop if margin > 0 else lp_prev, rtol=1e-5)
+    return near_ties
+
+
+def test_golden_chain_free_running(ssi, engine):
+    """itr=10 on the README config, as README.md:74-79: free-running device chains equal the
+    oracle's traces (z bit-exact up to FP32 rounding of the state, decisions identical)."""
+    g = np.load(GOLD / "mh_readme.npz")
+    prob = orc.Problem(tuple(int(d) for d in g["dims"]), tuple(int(a) for a in g["acts"]), g["X"], g["Y"], g["W_swa"], g["P"])
+    _setup(engine, prob)
+    C, S = int(g["n_chains"]), int(g["n_steps"])
+    zt, lt, at = engine.mh_run(C, S, int(g["seed"]), sigma_z=1.0, sigma_m=1.0)
+    np.testing.assert_array_equal(at, g["accept"])
+    np.testing.assert_allclose(np.transpose(zt, (1, 2, 0)), g["z_trace"], rtol=0, atol=5e-7)
+    np.testing.assert_allclose(lt, g["lp_trace"], rtol=1e-5)
+    st = engine.stats()
+    assert st.mh_proposals == C * (S - 1) and st.mh_accepts == int(g["accept"][:, 1:].sum())
+
+
+def test_device_stream_equals_host_replay(ssi, engine):
+    prob = orc.make_problem("readme")
+    _setup(engine, prob)
+    # sigma huge -> chain state = cumulative proposals only when accepted; use sample 0 = sigma*eps_0
+    zt, _, _ = engine.mh_run(64, 1, 99, sigma_z=2.0, chain_offset=1000)
+    for c in (0, 1, 63):
+        eps, _ = engine.rng_replay(99, 1000 + c, 0)
+        np.testing.assert_allclose(zt[:, c, 0], 2.0 * eps, rtol=2.5e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("path", ["fused", "layered"])
+def test_decisions_teacher_forced_uci(ssi, engine, path):
+    prob = orc.make_problem("uci", N=2000)
+    _setup(engine, prob)
+    engine.set_option("path", {"fused": ssi.PATH_FUSED, "layered": ssi.PATH_LAYERED}[path])
+    C, S, seed = 6, 40, 2024
+    zt, lt, at = engine.mh_run(C, S, seed, sigma_z=0.02, sigma_m=0.1)
+    ties = _check_against_oracle(prob, zt, lt, at, seed, 0.02, 0.1, range(C))
+    assert ties <= 2
+    assert 0 < at[:, 1:].mean() < 1          # both outcomes are exercised
+
+
+def test_chain_sharding_is_bitwise_invariant(ssi, engine):
+    """Chains [0,32) in one call == chains [0,16) and [16,32) in two calls (what 2 GPUs do)."""
+    prob = orc.make_problem("uci", N=1500)
+    _setup(engine, prob)
+    full = engine.mh_run(32, 25, 7, sigma_z=0.05, sigma_m=0.1)
+    a = engine.mh_run(16, 25, 7, sigma_z=0.05, sigma_m=0.1, chain_offset=0)
+    b = engine.mh_run(16, 25, 7, sigma_z=0.05, sigma_m=0.1, chain_offset=16)
+    np.testing.assert_array_equal(full[0], np.concatenate([a[0], b[0]], axis=1))
+    np.testing.assert_array_equal(full[1], np.concatenate([a[1], b[1]], axis=0))
+    np.testing.assert_array_equal(full[2], np.concatenate([a[2], b[2]], axis=0))
+
+
+def test_z0_and_rejection_keeps_state(ssi, engine):
+    prob = orc.make_problem("readme")
+    _setup(engine, prob)
+    z0 = np.tile(np.array([[0.1], [0.2], [0.3]], np.float32), (1, 5))
+    # sigma_m tiny -> likelihood extremely peaked; huge proposals are (almost surely) rejected
+    zt, lt, at = engine.mh_run(5, 8, 3, sigma_z=50.0, sigma_m=1e-3, z0=z0)
+    np.testing.assert_array_equal(zt[:, :, 0], z0)
+    assert at[:, 0].all()
+    rej = at[:, 1:] == 0
+    assert rej.any()
+    for c in range(5):
+        for t in range(1, 8):
+            if not at[c, t]:
+                np.testing.assert_array_equal(zt[:, c, t], zt[:, c, t - 1])
+                assert lt[c, t] == lt[c, t - 1]
+
+
+def test_many_chains_full_c2(ssi, engine):
+    """C2 shape: 4096 chains on N=10k; a few steps, spot-checked against the oracle."""
+    prob = orc.make_problem("uci")
+    _setup(engine, prob)
+    C, S, seed = 4096, 6, 11
+    zt, lt, at = engine.mh_run(C, S, seed, sigma_z=0.01, sigma_m=0.1)
+    pick = [0, 1, 2047, 4095]
+    _check_against_oracle(prob, zt[:, pick, :], lt[pick], at[pick], seed, 0.01, 0.1, pick)
+    assert np.isfinite(lt).all()
