@@ -202,7 +202,11 @@ def main():
     eng.set_data(prob.X, prob.Y)
     eng.set_subspace(prob.W_swa, prob.P)
     eng.set_option("path", {"auto": 0, "fused": 1, "layered": 2, "tensor": 3}[args.path])
-    stream = torch.cuda.current_stream()
+    # a non-default stream: the library treats a NULL handle as "use the context's own stream",
+    # and CUDA events must be recorded on the stream the kernels are launched on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
 
     # this rank's shard of the global proposal batch (global ids rank*B .. rank*B+B-1)

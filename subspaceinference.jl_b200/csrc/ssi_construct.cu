@@ -63,64 +63,68 @@ int ssi_swa_push_device(ssi_ctx* ctx, const float* dW, double n_scalar) {
 }
 
 // ======================================================================================
-// K6: Gram G = A'A (FP32 products, FP64 across row chunks, fixed-order slab reduction)
+// K6: Gram G = A'A.  FP32 inputs, products and sums in FP64 (a*b of two floats is exact in
+// double), fixed-order slab reduction: the Gram route squares the condition number, so the
+// accumulation must not lose the small singular directions.
 // ======================================================================================
-#define GT 32
-#define GR 64
+#define GR 32
+template <int GT, int MT>   // GT x GT tile per CTA, MT x MT outputs per thread, (GT/MT)^2 == 256 threads
 __global__ void __launch_bounds__(256)
 k_gram_partial(const float* __restrict__ A, long long n, int K, int tiles, long long rows_per_slab,
                double* __restrict__ partial /* slabs x K x K */) {
-    __shared__ float As[GR][GT + 1];
-    __shared__ float Bs[GR][GT + 1];
+    __shared__ __align__(16) double As[GR][GT];
+    __shared__ __align__(16) double Bs[GR][GT];
     // blockIdx.y enumerates tile pairs (ta <= tb)
     int ta = 0, rem = blockIdx.y;
     while (rem >= tiles - ta) { rem -= tiles - ta; ++ta; }
     const int tb = ta + rem;
     const int a0 = ta * GT, b0 = tb * GT;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    constexpr int TPR = GT / MT;                 // threads per tile row (16)
+    const int tid = threadIdx.x, tx = tid % TPR, ty = tid / TPR;
     const long long r_begin = (long long)blockIdx.x * rows_per_slab;
     const long long r_end = min(n, r_begin + rows_per_slab);
 
-    double acc[2][2] = {{0, 0}, {0, 0}};
-    float facc[2][2] = {{0, 0}, {0, 0}};
-    int chunk = 0;
-    for (long long r0 = r_begin; r0 < r_end; r0 += GR, ++chunk) {
+    double acc[MT][MT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < MT; ++j) acc[i][j] = 0.0;
+
+    for (long long r0 = r_begin; r0 < r_end; r0 += GR) {
 #pragma unroll
         for (int s = 0; s < (GR * GT) / 256; ++s) {
             const int idx = tid + s * 256;
-            const int r = idx & (GR - 1), c = idx >> 6;
+            const int r = idx % GR, c = idx / GR;
             const bool rv = (r0 + r < r_end);
-            As[r][c] = (rv && a0 + c < K) ? A[(r0 + r) + (long long)(a0 + c) * n] : 0.0f;
-            Bs[r][c] = (rv && b0 + c < K) ? A[(r0 + r) + (long long)(b0 + c) * n] : 0.0f;
+            As[r][c] = (rv && a0 + c < K) ? (double)A[(r0 + r) + (long long)(a0 + c) * n] : 0.0;
+            Bs[r][c] = (rv && b0 + c < K) ? (double)A[(r0 + r) + (long long)(b0 + c) * n] : 0.0;
         }
         __syncthreads();
-#pragma unroll 8
+#pragma unroll 4
         for (int r = 0; r < GR; ++r) {
-            const float x0 = As[r][ty * 2], x1 = As[r][ty * 2 + 1];
-            const float y0 = Bs[r][tx * 2], y1 = Bs[r][tx * 2 + 1];
-            facc[0][0] = fmaf(x0, y0, facc[0][0]);
-            facc[0][1] = fmaf(x0, y1, facc[0][1]);
-            facc[1][0] = fmaf(x1, y0, facc[1][0]);
-            facc[1][1] = fmaf(x1, y1, facc[1][1]);
+            double x[MT], y[MT];
+#pragma unroll
+            for (int i = 0; i < MT; i += 2) {
+                const double2 xv = *reinterpret_cast<const double2*>(&As[r][ty * MT + i]);
+                const double2 yv = *reinterpret_cast<const double2*>(&Bs[r][tx * MT + i]);
+                x[i] = xv.x; x[i + 1] = xv.y; y[i] = yv.x; y[i + 1] = yv.y;
+            }
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < MT; ++j) acc[i][j] = fma(x[i], y[j], acc[i][j]);
         }
         __syncthreads();
-        if ((chunk & 3) == 3) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) { acc[i][j] += (double)facc[i][j]; facc[i][j] = 0.0f; }
-        }
     }
     double* out = partial + (long long)blockIdx.x * K * K;
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int a = a0 + ty * 2 + i, b = b0 + tx * 2 + j;
+        for (int j = 0; j < MT; ++j) {
+            const int a = a0 + ty * MT + i, b = b0 + tx * MT + j;
             if (a < K && b < K) {
-                const double v = acc[i][j] + (double)facc[i][j];
-                out[a + (long long)b * K] = v;
-                if (ta != tb) out[b + (long long)a * K] = v;
+                out[a + (long long)b * K] = acc[i][j];
+                if (ta != tb) out[b + (long long)a * K] = acc[i][j];
             }
         }
 }
@@ -134,6 +138,7 @@ __global__ void k_gram_reduce(const double* __restrict__ partial, int slabs, lon
 }
 
 int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int K, double* dG) {
+    const int GT = K <= 32 ? 32 : 64;
     const int tiles = (K + GT - 1) / GT;
     const int pairs = tiles * (tiles + 1) / 2;
     int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(2 * ctx->sm_count, (n + 1023) / 1024));
@@ -144,7 +149,8 @@ int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int K, double* dG)
     double* partial = (double*)ctx->bGram.p;
     if (pairs > 65535) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "too many deviation columns (K=%d)", K);
     dim3 grid(slabs, pairs);
-    k_gram_partial<<<grid, 256, 0, ctx->stream>>>(dA, n, K, tiles, rows_per, partial);
+    if (GT == 32) k_gram_partial<32, 2><<<grid, 256, 0, ctx->stream>>>(dA, n, K, tiles, rows_per, partial);
+    else          k_gram_partial<64, 4><<<grid, 256, 0, ctx->stream>>>(dA, n, K, tiles, rows_per, partial);
     SSI_LAUNCH_CHECK(ctx);
     const long long KK = (long long)K * K;
     k_gram_reduce<<<(unsigned)((KK + 255) / 256), 256, 0, ctx->stream>>>(partial, slabs, KK, dG);

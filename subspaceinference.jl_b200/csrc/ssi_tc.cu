@@ -1,10 +1,640 @@
-// ssi_tc.cu — tensor-core (tcgen05/TMEM/TMA) path.  Placeholder until the kernel lands.
+// ssi_tc.cu — tensor-core path of the batched log-posterior (wide Dense chains).
+//
+// Replaces, for a group of G samples at a time, the body of the reference's density(z)
+// (src/space_inference.jl:90-95):
+//     new_W = W_swa + P*z            -> k_tc_project_* : one pass over P for the whole group,
+//                                       weights written as split BF16 (hi, lo) K-major tiles
+//     Dense: sigma.(W*x .+ b)        -> k_tc_layer<HIDDEN>: TMA -> smem -> tcgen05.mma (TMEM
+//                                       accumulators) -> bias/activation epilogue -> split BF16
+//     last Dense + logpdf(MvNormal)  -> k_tc_layer<FINAL>: the same GEMM for the last hidden
+//                                       layer, with the (narrow) output layer and the squared
+//                                       error folded into the epilogue, per-warp FP64 partials
+//
+// Precision: tcgen05 has no FP32-input mode.  Every FP32 operand x is split into
+// hi = bf16(x), lo = bf16(x - hi) and each product is issued as hi*hi + hi*lo + lo*hi with FP32
+// accumulation in TMEM ("BF16x3").  Measured against the Float64 oracle this keeps lp within
+// ~2e-7 relative (tolerance 1e-5); the roofline denominator is therefore 1/3 of the BF16 peak.
+//
+// Orientation: D[m, n] = sum_k A[m, k] B[n, k] with m = datapoint (128 per tile, TMEM lane),
+// n = output feature (BN per tile, TMEM column), k = input feature.  A = activations
+// [N][K] (K contiguous), B = weights [out][K] (K contiguous), both K-major SWIZZLE_128B.
 #include "ssi_common.cuh"
 
-bool ssi_tc_supported(const ssi_ctx*) { return false; }
-int ssi_tc_prepare(ssi_ctx*) { return SSI_OK; }
-void ssi_tc_invalidate(ssi_ctx*) {}
-void ssi_tc_destroy(ssi_ctx*) {}
-int ssi_tc_sse(ssi_ctx* ctx, const float*, int64_t, double*) {
-    return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "tensor path not built");
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#define TC_BM 128
+#define TC_BK 64                 // bf16 elements per k-block = 128 bytes = one swizzle row
+#define TC_GMAX 16               // samples per group
+#define TC_OPMAX 12              // padded width of the fused output layer
+#define TC_SMEM_PIPE (192 * 1024)
+#define TC_THREADS 192           // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must not hang the GPU box; trap instead (2^31 cycles ~ 1 s).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > (1ll << 32)) {
+            printf("ssi_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, BF16 inputs, FP32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 consecutive columns: thread i of the warp gets columns [c, c+32) of lane (base_lane + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row atoms 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address            bits [0,14)
+    d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset = 1024 bits [32,46)
+    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, kind::f16: D=F32, A=B=BF16, both K-major, M=128, N=n
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------
+// the GEMM layer kernel
+// ---------------------------------------------------------------------------------------
+struct tc_params {
+    int N, G, m_tiles, n_tiles, k_blocks, BN, width, a_shared, act;
+    int stages, stage_bytes;
+    const float* bias;      // [G][width]
+    bf16* Hh;               // HIDDEN: [G][N][width]
+    bf16* Hl;
+    const float* Wlast;     // FINAL: [G][width][TC_OPMAX]
+    const float* blast;     // FINAL: [G][TC_OPMAX]
+    const float* Y;         // FINAL: O x N column-major
+    int O, act_last;
+    double* partials;       // FINAL: [G][m_tiles*4]
+};
+
+template <bool FINAL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+           const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const tc_params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by SWIZZLE_128B (TMA destination and UMMA descriptor base_offset = 0)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* s_bias = reinterpret_cast<float*>(smem + TC_SMEM_PIPE);                    // [2][256]
+    float* s_wl = s_bias + 2 * 256;                                                   // [2][256*TC_OPMAX]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_wl + 2 * 256 * TC_OPMAX);         // full[4] empty[4] tfull[2] tempty[2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + 4);
+    const uint32_t bar_tfull = smem_u32(s_bar + 8), bar_tempty = smem_u32(s_bar + 10);
+    const uint32_t smem_base = smem_u32(smem);
+    const int BN = p.BN;
+    const uint32_t a_bytes = TC_BM * TC_BK * 2, b_bytes = (uint32_t)BN * TC_BK * 2;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 128); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    const int n_work = p.G * p.m_tiles;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int g = w / p.m_tiles, mt = w % p.m_tiles;
+                for (int nt = 0; nt < p.n_tiles; ++nt) {
+                    for (int kb = 0; kb < p.k_blocks; ++kb) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t full = bar_full + 8 * stage;
+                        const uint32_t sA = smem_base + stage * p.stage_bytes;
+                        mbar_expect_tx(full, 2 * a_bytes + 2 * b_bytes);
+                        tma_load_3d(sA, &tmAh, full, kb * TC_BK, mt * TC_BM, p.a_shared ? 0 : g);
+                        tma_load_3d(sA + a_bytes, &tmAl, full, kb * TC_BK, mt * TC_BM, p.a_shared ? 0 : g);
+                        tma_load_3d(sA + 2 * a_bytes, &tmBh, full, kb * TC_BK, nt * BN, g);
+                        tma_load_3d(sA + 2 * a_bytes + b_bytes, &tmBl, full, kb * TC_BK, nt * BN, g);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t tile = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                for (int nt = 0; nt < p.n_tiles; ++nt, ++tile) {
+                    const uint32_t ab = tile & 1, aphase = (tile >> 1) & 1;
+                    mbar_wait(bar_tempty + 8 * ab, aphase ^ 1);        // epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + ab * 256;
+                    for (int kb = 0; kb < p.k_blocks; ++kb) {
+                        mbar_wait(bar_full + 8 * stage, phase);         // TMA bytes have landed
+                        tc_fence_after();
+                        const uint32_t sA = smem_base + stage * p.stage_bytes;
+                        const uint64_t ah = umma_desc_sw128(sA), al = umma_desc_sw128(sA + a_bytes);
+                        const uint64_t bh = umma_desc_sw128(sA + 2 * a_bytes), bl = umma_desc_sw128(sA + 2 * a_bytes + b_bytes);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; ++k) {
+                            const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 bytes per K=16 step inside the swizzle row
+                            umma_bf16(d_tmem, ah + ko, bh + ko, idesc, (kb | k) != 0);
+                            umma_bf16(d_tmem, ah + ko, bl + ko, idesc, 1);
+                            umma_bf16(d_tmem, al + ko, bh + ko, idesc, 1);
+                        }
+                        umma_commit(bar_empty + 8 * stage);            // frees the smem slot when the MMAs retire
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(bar_tfull + 8 * ab);                   // accumulator complete -> epilogue
+                }
+            }
+        }
+    } else {
+        // ================= epilogue (4 warps = 128 TMEM lanes) =================
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const int et = threadIdx.x - 64;             // 0..127
+        uint32_t tile = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int g = w / p.m_tiles, mt = w % p.m_tiles;
+            const long long m = (long long)mt * TC_BM + row;
+            const bool valid = m < p.N;
+            float pred[TC_OPMAX];
+#pragma unroll
+            for (int o = 0; o < TC_OPMAX; ++o) pred[o] = 0.0f;
+
+            for (int nt = 0; nt < p.n_tiles; ++nt, ++tile) {
+                const uint32_t ab = tile & 1, aphase = (tile >> 1) & 1;
+                float* sb = s_bias + ab * 256;
+                float* sw = s_wl + ab * 256 * TC_OPMAX;
+                // stage this tile's bias (and output-layer weights) while the MMAs run
+                for (int c = et; c < BN; c += 128) sb[c] = p.bias[(long long)g * p.width + nt * BN + c];
+                if (FINAL) {
+                    const float4* src = reinterpret_cast<const float4*>(p.Wlast + ((long long)g * p.width + nt * BN) * TC_OPMAX);
+                    float4* dst = reinterpret_cast<float4*>(sw);
+                    for (int c = et; c < BN * TC_OPMAX / 4; c += 128) dst[c] = src[c];
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                mbar_wait(bar_tfull + 8 * ab, aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (FINAL) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float h = ssi_act(__uint_as_float(v[j]) + sb[c0 + j], p.act);
+                            const float4* w4 = reinterpret_cast<const float4*>(sw + (c0 + j) * TC_OPMAX);
+#pragma unroll
+                            for (int o4 = 0; o4 < TC_OPMAX / 4; ++o4) {
+                                const float4 ww = w4[o4];
+                                pred[4 * o4 + 0] = fmaf(h, ww.x, pred[4 * o4 + 0]);
+                                pred[4 * o4 + 1] = fmaf(h, ww.y, pred[4 * o4 + 1]);
+                                pred[4 * o4 + 2] = fmaf(h, ww.z, pred[4 * o4 + 2]);
+                                pred[4 * o4 + 3] = fmaf(h, ww.w, pred[4 * o4 + 3]);
+                            }
+                        }
+                    } else {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float x0 = ssi_act(__uint_as_float(v[j]) + sb[c0 + j], p.act);
+                            const float x1 = ssi_act(__uint_as_float(v[j + 1]) + sb[c0 + j + 1], p.act);
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+                            const float2 hf = __bfloat1622float2(h2);
+                            const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+                            hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                            lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+                        }
+                        if (valid) {
+                            const long long off = ((long long)g * p.N + m) * p.width + nt * BN + c0;
+                            uint4* dh = reinterpret_cast<uint4*>(p.Hh + off);
+                            uint4* dl = reinterpret_cast<uint4*>(p.Hl + off);
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) {
+                                dh[s] = make_uint4(hi[4 * s], hi[4 * s + 1], hi[4 * s + 2], hi[4 * s + 3]);
+                                dl[s] = make_uint4(lo[4 * s], lo[4 * s + 1], lo[4 * s + 2], lo[4 * s + 3]);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(bar_tempty + 8 * ab);
+            }
+            if (FINAL) {
+                double sse = 0.0;
+                if (valid) {
+                    const float* bl = p.blast + (long long)g * TC_OPMAX;
+#pragma unroll
+                    for (int o = 0; o < TC_OPMAX; ++o) {
+                        if (o < p.O) {
+                            const float df = ssi_act(pred[o] + bl[o], p.act_last) - p.Y[o + m * p.O];
+                            sse += (double)df * (double)df;
+                        }
+                    }
+                }
+                sse = ssi_warp_sum(sse);
+                if (lane == 0) p.partials[(long long)g * (p.m_tiles * 4) + mt * 4 + q] = sse;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// operand preparation
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// X (in0 x N column-major == [N][in0]) -> Xh, Xl [N][Kp] (zero padded)
+__global__ void __launch_bounds__(256)
+k_tc_split_x(const float* __restrict__ X, long long N, int in0, int Kp, bf16* __restrict__ Xh, bf16* __restrict__ Xl) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N * Kp) return;
+    const long long j = e / Kp;
+    const int i = (int)(e % Kp);
+    bf16 hi, lo;
+    split_bf16(i < in0 ? X[j * in0 + i] : 0.0f, hi, lo);
+    Xh[e] = hi;
+    Xl[e] = lo;
+}
+
+// One Dense weight matrix of the group: flat (out x in, column-major: o + i*out) -> split BF16 [g][o][Kp].
+// Each block owns a 32(i) x 32(o) tile; P is read once for all G samples (K1, src/space_inference.jl:91).
+__global__ void __launch_bounds__(256)
+k_tc_project_w(const float* __restrict__ Wswa, const float* __restrict__ P, const float* __restrict__ Z,
+               long long n, int M, int G, long long w_off, int in, int out, int Kp,
+               bf16* __restrict__ Wh, bf16* __restrict__ Wl) {
+    __shared__ float zs[SSI_MAX_M * TC_GMAX];
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;    // 32 x 8
+    for (int e = threadIdx.x; e < M * G; e += 256) zs[e] = Z[e];
+    __syncthreads();
+    const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+    float acc[4][TC_GMAX];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty + 8 * r, o = o0 + tx;
+        const bool ok = (i < in) && (o < out);
+        const long long flat = w_off + o + (long long)i * out;
+        const float w0 = ok ? Wswa[flat] : 0.0f;
+#pragma unroll
+        for (int g = 0; g < TC_GMAX; ++g) acc[r][g] = w0;
+        if (ok) {
+            for (int m = 0; m < M; ++m) {
+                const float pv = P[flat + (long long)m * n];
+#pragma unroll
+                for (int g = 0; g < TC_GMAX; ++g) acc[r][g] = fmaf(pv, zs[m + g * M], acc[r][g]);
+            }
+        }
+    }
+#pragma unroll 1
+    for (int g = 0; g < G; ++g) {
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float v = 0.0f;
+#pragma unroll
+            for (int gg = 0; gg < TC_GMAX; ++gg) v = (gg == g) ? acc[r][gg] : v;   // keeps acc in registers
+            tile[ty + 8 * r][tx] = v;                                              // [i][o]
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int o = o0 + ty + 8 * r, i = i0 + tx;
+            if (o < out && i < Kp) {
+                bf16 hi, lo;
+                split_bf16(tile[tx][ty + 8 * r], hi, lo);
+                const long long dst = ((long long)g * out + o) * Kp + i;
+                Wh[dst] = hi;
+                Wl[dst] = lo;
+            }
+        }
+    }
+}
+
+// Vector-like pieces: dst[g][(e / inner) * dst_ld + (e % inner)] = (W_swa + P z_g)[src_off + e]
+// biases: inner = count, dst_ld = 0 (plain copy);  output layer W (O x width col-major): inner = O, dst_ld = TC_OPMAX
+__global__ void __launch_bounds__(256)
+k_tc_project_v(const float* __restrict__ Wswa, const float* __restrict__ P, const float* __restrict__ Z,
+               long long n, int M, int G, long long src_off, int count, int inner, int dst_ld, long long dst_gs,
+               float* __restrict__ dst) {
+    __shared__ float zs[SSI_MAX_M * TC_GMAX];
+    for (int e = threadIdx.x; e < M * G; e += 256) zs[e] = Z[e];
+    __syncthreads();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    const long long flat = src_off + e;
+    float acc[TC_GMAX];
+    const float w0 = Wswa[flat];
+#pragma unroll
+    for (int g = 0; g < TC_GMAX; ++g) acc[g] = w0;
+    for (int m = 0; m < M; ++m) {
+        const float pv = P[flat + (long long)m * n];
+#pragma unroll
+        for (int g = 0; g < TC_GMAX; ++g) acc[g] = fmaf(pv, zs[m + g * M], acc[g]);
+    }
+    const long long d = (long long)(e / inner) * dst_ld + (e % inner);
+#pragma unroll
+    for (int g = 0; g < TC_GMAX; ++g)
+        if (g < G) dst[(long long)g * dst_gs + d] = acc[g];
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct ssi_tc_state {
+    bool ready = false;
+    int nl = 0;                          // tensor layers = L - 1 (all but the fused output layer)
+    int Kp[SSI_MAX_LAYERS] = {0};
+    int width[SSI_MAX_LAYERS] = {0};
+    int BN[SSI_MAX_LAYERS] = {0};
+    int G = TC_GMAX;
+    bf16 *Xh = nullptr, *Xl = nullptr;
+    bf16 *Wh[SSI_MAX_LAYERS] = {nullptr}, *Wl[SSI_MAX_LAYERS] = {nullptr};
+    float* bias[SSI_MAX_LAYERS] = {nullptr};
+    float *Wlast = nullptr, *blast = nullptr;
+    bf16 *Hh[2] = {nullptr, nullptr}, *Hl[2] = {nullptr, nullptr};
+    double* partials = nullptr;
+    CUtensorMap tmAh[SSI_MAX_LAYERS], tmAl[SSI_MAX_LAYERS], tmBh[SSI_MAX_LAYERS], tmBl[SSI_MAX_LAYERS];
+    PFN_encodeTiled encode = nullptr;
+    size_t smem_bytes = 0;
+};
+
+static void tc_free(ssi_tc_state* s) {
+    cudaFree(s->Xh); cudaFree(s->Xl); cudaFree(s->Wlast); cudaFree(s->blast); cudaFree(s->partials);
+    for (int i = 0; i < 2; ++i) { cudaFree(s->Hh[i]); cudaFree(s->Hl[i]); }
+    for (int l = 0; l < SSI_MAX_LAYERS; ++l) { cudaFree(s->Wh[l]); cudaFree(s->Wl[l]); cudaFree(s->bias[l]); }
+    PFN_encodeTiled enc = s->encode;
+    *s = ssi_tc_state();
+    s->encode = enc;
+}
+
+void ssi_tc_invalidate(ssi_ctx* ctx) {
+    if (ctx->tc) ctx->tc->ready = false;
+}
+
+void ssi_tc_destroy(ssi_ctx* ctx) {
+    if (!ctx->tc) return;
+    tc_free(ctx->tc);
+    delete ctx->tc;
+    ctx->tc = nullptr;
+}
+
+bool ssi_tc_supported(const ssi_ctx* ctx) {
+    if (!ctx->has_model) return false;
+    const ssi_model_t& m = ctx->model;
+    if (m.L < 2 || m.dims[m.L] > TC_OPMAX || ctx->M > SSI_MAX_M) return false;
+    for (int l = 1; l < m.L; ++l)
+        if (m.dims[l] % 64 != 0) return false;
+    return true;
+}
+
+static int tc_make_map(ssi_ctx* ctx, CUtensorMap* map, void* base, uint64_t inner, uint64_t rows, uint64_t batch, uint32_t box_rows) {
+    cuuint64_t dims[3] = {inner, rows, batch};
+    cuuint64_t strides[2] = {inner * sizeof(bf16), inner * rows * sizeof(bf16)};
+    cuuint32_t box[3] = {TC_BK, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = ctx->tc->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ssi_fail(ctx, SSI_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SSI_OK;
+}
+
+int ssi_tc_prepare(ssi_ctx* ctx) {
+    if (!ssi_tc_supported(ctx)) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "tensor path: unsupported model shape");
+    if (!ctx->tc) ctx->tc = new ssi_tc_state();
+    ssi_tc_state* s = ctx->tc;
+    if (s->ready) return SSI_OK;
+    if (!s->encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SSI_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) return ssi_fail(ctx, SSI_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        s->encode = (PFN_encodeTiled)fn;
+    }
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    tc_free(s);
+    const ssi_model_t& m = ctx->model;
+    const int64_t N = ctx->N;
+    s->nl = m.L - 1;
+    s->G = ctx->opt_group > 0 ? std::min(ctx->opt_group, TC_GMAX) : TC_GMAX;
+    const int G = s->G;
+    int maxw = 0;
+    for (int l = 0; l < s->nl; ++l) {
+        s->Kp[l] = (m.dims[l] + TC_BK - 1) / TC_BK * TC_BK;
+        s->width[l] = m.dims[l + 1];
+        s->BN[l] = s->width[l] % 256 == 0 ? 256 : (s->width[l] % 128 == 0 ? 128 : 64);
+        if (l < s->nl - 1) maxw = std::max(maxw, s->width[l]);
+        SSI_CUDA(ctx, cudaMalloc(&s->Wh[l], sizeof(bf16) * (size_t)G * s->width[l] * s->Kp[l]));
+        SSI_CUDA(ctx, cudaMalloc(&s->Wl[l], sizeof(bf16) * (size_t)G * s->width[l] * s->Kp[l]));
+        SSI_CUDA(ctx, cudaMalloc(&s->bias[l], sizeof(float) * (size_t)G * s->width[l]));
+    }
+    const int wlast = s->width[s->nl - 1];
+    SSI_CUDA(ctx, cudaMalloc(&s->Wlast, sizeof(float) * (size_t)G * wlast * TC_OPMAX));
+    SSI_CUDA(ctx, cudaMalloc(&s->blast, sizeof(float) * (size_t)G * TC_OPMAX));
+    SSI_CUDA(ctx, cudaMemsetAsync(s->Wlast, 0, sizeof(float) * (size_t)G * wlast * TC_OPMAX, ctx->stream));
+    SSI_CUDA(ctx, cudaMemsetAsync(s->blast, 0, sizeof(float) * (size_t)G * TC_OPMAX, ctx->stream));
+    SSI_CUDA(ctx, cudaMalloc(&s->Xh, sizeof(bf16) * (size_t)N * s->Kp[0]));
+    SSI_CUDA(ctx, cudaMalloc(&s->Xl, sizeof(bf16) * (size_t)N * s->Kp[0]));
+    const int nbuf = s->nl >= 3 ? 2 : (s->nl == 2 ? 1 : 0);
+    for (int i = 0; i < nbuf; ++i) {
+        SSI_CUDA(ctx, cudaMalloc(&s->Hh[i], sizeof(bf16) * (size_t)G * N * maxw));
+        SSI_CUDA(ctx, cudaMalloc(&s->Hl[i], sizeof(bf16) * (size_t)G * N * maxw));
+    }
+    const int m_tiles = (int)((N + TC_BM - 1) / TC_BM);
+    SSI_CUDA(ctx, cudaMalloc(&s->partials, sizeof(double) * (size_t)G * m_tiles * 4));
+    {
+        const long long tot = (long long)N * s->Kp[0];
+        k_tc_split_x<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->dX, N, m.dims[0], s->Kp[0], s->Xh, s->Xl);
+        SSI_LAUNCH_CHECK(ctx);
+    }
+    for (int l = 0; l < s->nl; ++l) {
+        if (l == 0) {
+            SSI_TRY(tc_make_map(ctx, &s->tmAh[l], s->Xh, s->Kp[0], N, 1, TC_BM));
+            SSI_TRY(tc_make_map(ctx, &s->tmAl[l], s->Xl, s->Kp[0], N, 1, TC_BM));
+        } else {
+            // activations written by layer l-1: [G][N][width_{l-1}], K = width_{l-1} (a multiple of 64)
+            SSI_TRY(tc_make_map(ctx, &s->tmAh[l], s->Hh[(l - 1) & 1], s->width[l - 1], N, G, TC_BM));
+            SSI_TRY(tc_make_map(ctx, &s->tmAl[l], s->Hl[(l - 1) & 1], s->width[l - 1], N, G, TC_BM));
+        }
+        SSI_TRY(tc_make_map(ctx, &s->tmBh[l], s->Wh[l], s->Kp[l], s->width[l], G, s->BN[l]));
+        SSI_TRY(tc_make_map(ctx, &s->tmBl[l], s->Wl[l], s->Kp[l], s->width[l], G, s->BN[l]));
+    }
+    s->smem_bytes = 1024 + TC_SMEM_PIPE + sizeof(float) * (2 * 256 + 2 * 256 * TC_OPMAX) + 12 * 8 + 16;
+    SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_layer<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_layer<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    s->ready = true;
+    return SSI_OK;
+}
+
+int ssi_reduce_partials(ssi_ctx* ctx, const double* partials, int64_t B, int parts, double* d_out);
+
+int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
+    SSI_TRY(ssi_tc_prepare(ctx));
+    ssi_tc_state* s = ctx->tc;
+    const ssi_model_t& m = ctx->model;
+    const int64_t N = ctx->N, n = m.n;
+    const int M = ctx->M;
+    const int m_tiles = (int)((N + TC_BM - 1) / TC_BM);
+    const int parts = m_tiles * 4;
+    const int O = m.dims[m.L];
+
+    for (int64_t b0 = 0; b0 < B; b0 += s->G) {
+        const int G = (int)std::min<int64_t>(s->G, B - b0);
+        const float* Zg = dZ + b0 * M;
+        // ---- K1: project the group's weights straight into the GEMM operand layouts ----
+        for (int l = 0; l < s->nl; ++l) {
+            dim3 grid((s->Kp[l] + 31) / 32, (s->width[l] + 31) / 32);
+            k_tc_project_w<<<grid, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.w_off[l], m.dims[l], s->width[l],
+                                                         s->Kp[l], s->Wh[l], s->Wl[l]);
+            SSI_LAUNCH_CHECK(ctx);
+            k_tc_project_v<<<(s->width[l] + 255) / 256, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.b_off[l], s->width[l],
+                                                                           s->width[l], 0, s->width[l], s->bias[l]);
+            SSI_LAUNCH_CHECK(ctx);
+        }
+        {
+            const int wl = s->width[s->nl - 1];
+            const int cnt = wl * O;
+            k_tc_project_v<<<(cnt + 255) / 256, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.w_off[m.L - 1], cnt, O,
+                                                                     TC_OPMAX, (long long)wl * TC_OPMAX, s->Wlast);
+            SSI_LAUNCH_CHECK(ctx);
+            k_tc_project_v<<<1, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.b_off[m.L - 1], O, O, 0, TC_OPMAX, s->blast);
+            SSI_LAUNCH_CHECK(ctx);
+        }
+        // ---- the Dense chain ----
+        for (int l = 0; l < s->nl; ++l) {
+            tc_params p{};
+            p.N = (int)N; p.G = G; p.m_tiles = m_tiles;
+            p.BN = s->BN[l]; p.width = s->width[l];
+            p.n_tiles = s->width[l] / s->BN[l];
+            p.k_blocks = s->Kp[l] / TC_BK;
+            p.a_shared = (l == 0);
+            p.act = m.act[l];
+            p.stage_bytes = 2 * TC_BM * TC_BK * 2 + 2 * p.BN * TC_BK * 2;
+            p.stages = std::min(4, TC_SMEM_PIPE / p.stage_bytes);
+            p.bias = s->bias[l];
+            const int grid = std::min(ctx->sm_count, G * m_tiles);
+            if (l == s->nl - 1) {
+                p.Wlast = s->Wlast; p.blast = s->blast; p.Y = ctx->dY; p.O = O; p.act_last = m.act[m.L - 1];
+                p.partials = s->partials;
+                k_tc_layer<true><<<grid, TC_THREADS, s->smem_bytes, ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l], p);
+            } else {
+                p.Hh = s->Hh[l & 1]; p.Hl = s->Hl[l & 1];
+                k_tc_layer<false><<<grid, TC_THREADS, s->smem_bytes, ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l], p);
+            }
+            SSI_LAUNCH_CHECK(ctx);
+        }
+        SSI_TRY(ssi_reduce_partials(ctx, s->partials, G, parts, d_sse + b0));
+    }
+    return SSI_OK;
 }

@@ -1,0 +1,85 @@
+"""Tensor-core (tcgen05/TMEM/TMA, BF16x3 split precision) path vs the Float64 oracle."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import ssi_oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+RTOL = 1e-5
+
+
+def _setup(engine, prob):
+    engine.set_model(prob.dims, prob.acts)
+    engine.set_data(prob.X, prob.Y)
+    engine.set_subspace(prob.W_swa, prob.P)
+
+
+def _rand_problem(dims, acts, N, M, seed):
+    rng = np.random.default_rng(seed)
+    n = orc.n_params(dims)
+    X = rng.random((dims[0], N), dtype=np.float32)
+    Y = rng.standard_normal((dims[-1], N)).astype(np.float32)
+    return orc.Problem(dims, acts, X, Y, orc.glorot_flat(rng, dims), (0.05 * rng.standard_normal((n, M))).astype(np.float32)), rng
+
+
+def test_golden_wide_small_tensor_path(ssi, engine):
+    g = np.load(GOLD / "logpost_wide_small.npz")
+    prob = orc.Problem(tuple(int(d) for d in g["dims"]), tuple(int(a) for a in g["acts"]), g["X"], g["Y"], g["W_swa"], g["P"])
+    _setup(engine, prob)
+    engine.set_option("path", ssi.PATH_TENSOR)
+    lp, terms = engine.logpost(g["Z"], 1.0, 1.0, 1.0, mask=7, return_terms=True)
+    assert engine.stats().last_path == ssi.PATH_TENSOR
+    np.testing.assert_allclose(terms, g["terms"], rtol=RTOL)
+
+
+@pytest.mark.parametrize("dims,acts,N,M,B", [
+    ((64, 64, 3), (1, 0), 128, 2, 1),                       # one tile, one k-block, one sample
+    ((96, 128, 128, 10), (1, 1, 0), 300, 20, 8),            # ragged N, K padding 96 -> 128
+    ((784, 256, 512, 10), (1, 1, 0), 1000, 20, 19),         # BN=256, more than one group (G=16)
+    ((50, 192, 64, 320, 12), (2, 1, 3, 0), 513, 5, 3),      # 3 tensor layers (ping-pong), BN=64/320->64, tanh/sigmoid
+    ((20, 1024, 1), (1, 0), 2500, 3, 5),                    # single hidden layer, scalar output
+])
+def test_random_shapes_tensor_vs_oracle(ssi, engine, dims, acts, N, M, B):
+    prob, rng = _rand_problem(dims, acts, N, M, hash((dims, N)) % 2 ** 31)
+    Z = rng.standard_normal((M, B)).astype(np.float32)
+    _setup(engine, prob)
+    engine.set_option("path", ssi.PATH_TENSOR)
+    lp = engine.logpost(Z, 0.8)
+    ref, _ = orc.logpost_batch(prob, Z, 0.8)
+    np.testing.assert_allclose(lp, ref, rtol=RTOL)
+    # and against the FP32 SIMT path of the same library (tighter: both are FP32-grade)
+    engine.set_option("path", ssi.PATH_LAYERED)
+    lp_simt = engine.logpost(Z, 0.8)
+    np.testing.assert_allclose(lp, lp_simt, rtol=2e-6)
+
+
+def test_tensor_path_batch_invariance_and_mh(ssi, engine):
+    prob, rng = _rand_problem((128, 256, 256, 10), (1, 1, 0), 700, 20, 5)
+    _setup(engine, prob)
+    engine.set_option("path", ssi.PATH_TENSOR)
+    Z = (0.1 * rng.standard_normal((20, 40))).astype(np.float32)
+    full = engine.logpost(Z)
+    part = np.concatenate([engine.logpost(Z[:, :3]), engine.logpost(Z[:, 3:25]), engine.logpost(Z[:, 25:])])
+    np.testing.assert_array_equal(full, part)
+    zt, lt, at = engine.mh_run(24, 5, 77, sigma_z=0.05)
+    for c in (0, 23):
+        for t in (0, 4):
+            np.testing.assert_allclose(lt[c, t], orc.density(prob, zt[:, c, t]), rtol=RTOL)
+
+
+def test_auto_picks_tensor_for_wide(ssi, engine):
+    prob, rng = _rand_problem((128, 256, 256, 10), (1, 1, 0), 256, 20, 6)
+    _setup(engine, prob)
+    engine.set_option("path", ssi.PATH_AUTO)
+    engine.logpost(np.zeros((20, 2), np.float32))
+    assert engine.stats().last_path == ssi.PATH_TENSOR
+    with pytest.raises(ssi.SsiError):
+        engine.set_model((13, 50, 1), (1, 0))
+        engine.set_option("path", ssi.PATH_TENSOR)
+        engine.set_data(np.zeros((13, 4), np.float32), np.zeros((1, 4), np.float32))
+        n = orc.n_params((13, 50, 1))
+        engine.set_subspace(np.zeros(n, np.float32), np.zeros((n, 2), np.float32))
+        engine.logpost(np.zeros((2, 1), np.float32))       # hidden width 50 is not a multiple of 64
