@@ -46,6 +46,8 @@ struct ssi_ctx {
     // options
     int opt_path = SSI_PATH_AUTO;
     int opt_group = 0;
+    int opt_tc_nofuse = 0;    // debugging / A-B: compute the output layer as its own GEMM
+    int opt_tc_noorder = 0;   // debugging / A-B: sample-major work order on the first layer
 
     // model / data / subspace
     ssi_model_t model;
@@ -115,6 +117,7 @@ int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int K, double* dG)
 
 // tensor-core path (ssi_tc.cu)
 bool ssi_tc_supported(const ssi_ctx* ctx);
+bool ssi_tc_preferred(const ssi_ctx* ctx);   // AUTO picks the tensor path only when padding waste is small
 int  ssi_tc_prepare(ssi_ctx* ctx);        // after model+data(+subspace) change
 void ssi_tc_invalidate(ssi_ctx* ctx);
 void ssi_tc_destroy(ssi_ctx* ctx);

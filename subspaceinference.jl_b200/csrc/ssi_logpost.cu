@@ -445,7 +445,7 @@ static int run_layered(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) 
 // ======================================================================================
 static int choose_path(ssi_ctx* ctx) {
     if (ctx->opt_path != SSI_PATH_AUTO) return ctx->opt_path;
-    if (ssi_tc_supported(ctx)) return SSI_PATH_TENSOR;
+    if (ssi_tc_preferred(ctx)) return SSI_PATH_TENSOR;
     fused_desc_t d{};
     size_t smem = 0;
     if (fused_layout(ctx, d, smem) && smem <= 100 * 1024) return SSI_PATH_FUSED;

@@ -6,9 +6,11 @@
 //                                       weights written as split BF16 (hi, lo) K-major tiles
 //     Dense: sigma.(W*x .+ b)        -> k_tc_layer<HIDDEN>: TMA -> smem -> tcgen05.mma (TMEM
 //                                       accumulators) -> bias/activation epilogue -> split BF16
-//     last Dense + logpdf(MvNormal)  -> k_tc_layer<FINAL>: the same GEMM for the last hidden
-//                                       layer, with the (narrow) output layer and the squared
-//                                       error folded into the epilogue, per-warp FP64 partials
+//     last Dense + logpdf(MvNormal)  -> k_tc_layer<FINAL>: the same GEMM with N = O rounded up to
+//                                       16; the epilogue adds the bias, subtracts Y, squares and
+//                                       reduces to per-warp FP64 partials (nothing is stored)
+// Every Dense layer is one launch of the same warp-specialised GEMM; hidden widths and the
+// input width are zero-padded to multiples of 64, so any Dense chain is supported.
 //
 // Precision: tcgen05 has no FP32-input mode.  Every FP32 operand x is split into
 // hi = bf16(x), lo = bf16(x - hi) and each product is issued as hi*hi + hi*lo + lo*hi with FP32
@@ -28,8 +30,8 @@
 #define TC_BM 128
 #define TC_BK 64                 // bf16 elements per k-block = 128 bytes = one swizzle row
 #define TC_GMAX 16               // samples per group
-#define TC_OPMAX 12              // padded width of the fused output layer
 #define TC_SMEM_PIPE (192 * 1024)
+#define TC_SMEM_STORE (32 * 1024) // HIDDEN epilogue staging: 4 warps x 2 buffers x (hi, lo) x 32 rows x 64 B
 #define TC_THREADS 192           // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 
 typedef __nv_bfloat16 bf16;
@@ -79,6 +81,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// L2 eviction-priority policies (same encodings CUTLASS uses for SM90+ TMA cache hints)
+#define TC_EVICT_NORMAL 0x1000000000000000ull
+#define TC_EVICT_FIRST  0x12F0000000000000ull
+#define TC_EVICT_LAST   0x14F0000000000000ull
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -120,6 +132,47 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+// TMA store smem -> global (bulk async group)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+                 : "memory");
+}
+// 16 lanes x 64 columns in the mma-fragment layout: for each 8-column block i, thread t holds
+//   v[4i+0], v[4i+1] = (lane base + t/4,     columns 8i + 2(t%4) + {0,1})
+//   v[4i+2], v[4i+3] = (lane base + t/4 + 8, columns 8i + 2(t%4) + {0,1})
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t v[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row atoms 1024 B apart)
@@ -143,26 +196,54 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
 struct tc_params {
     int N, G, m_tiles, n_tiles, k_blocks, BN, width, a_shared, act;
     int stages, stage_bytes;
-    const float* bias;      // [G][width]
-    bf16* Hh;               // HIDDEN: [G][N][width]
-    bf16* Hl;
-    const float* Wlast;     // FINAL: [G][width][TC_OPMAX]
-    const float* blast;     // FINAL: [G][TC_OPMAX]
-    const float* Y;         // FINAL: O x N column-major
-    int O, act_last;
-    double* partials;       // FINAL: [G][m_tiles*4]
+    int mt_block;           // > 0: work order (mt block, sample, mt in block) so that concurrently running CTAs share A tiles
+    int n_work;
+    const float* bias;      // [G][width]  (width = padded out width of this layer)
+    const float* Y;         // FINAL / FUSED: O x N column-major
+    int O;                  // FINAL / FUSED: true output width
+    int act_out;            // FUSED: activation of the fused output layer
+    const float* Wout;      // FUSED: [G][width][TC_OP] output-layer weights, W[o, c] at [c][o]
+    const float* bout;      // FUSED: [G][TC_OP]
+    double* partials;       // FINAL / FUSED: [G][m_tiles*4]
 };
 
-template <bool FINAL>
+#define TC_MODE_HIDDEN 0    // store split-BF16 activations with TMA
+#define TC_MODE_FINAL  1    // this GEMM is the output layer: squared error in the epilogue
+#define TC_MODE_FUSED  2    // last hidden layer; the (narrow) output layer and the squared error are folded into the epilogue
+#define TC_OP 12            // FUSED: padded output width
+
+// shared-memory carve-up (offsets from the 1024-aligned dynamic base)
+//   [0, TC_SMEM_PIPE)                         operand ring: stage = A_hi | A_lo | B_hi | B_lo
+//   [TC_SMEM_PIPE, +TC_SMEM_STORE)            HIDDEN: per-warp TMA-store staging; FUSED: output-layer weight slices [2][256][TC_OP]
+//   then bias[2][256] floats, 12 mbarriers, TMEM base address
+#define TC_OFF_STORE TC_SMEM_PIPE
+#define TC_OFF_BIAS (TC_SMEM_PIPE + TC_SMEM_STORE)
+#define TC_OFF_BAR (TC_OFF_BIAS + 2 * 256 * 4)
+#define TC_SMEM_TOTAL (TC_OFF_BAR + 12 * 8 + 16)
+
+__device__ __forceinline__ bool tc_decode_work(const tc_params& p, int w, int& g, int& mt) {
+    if (p.mt_block > 0) {
+        const int per = p.G * p.mt_block;
+        const int blk = w / per, rem = w - blk * per;
+        g = rem / p.mt_block;
+        mt = blk * p.mt_block + (rem - g * p.mt_block);
+        return mt < p.m_tiles;
+    }
+    g = w / p.m_tiles;
+    mt = w - g * p.m_tiles;
+    return true;
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-           const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const tc_params p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // 1024-byte alignment is required by SWIZZLE_128B (TMA destination and UMMA descriptor base_offset = 0)
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* s_bias = reinterpret_cast<float*>(smem + TC_SMEM_PIPE);                    // [2][256]
-    float* s_wl = s_bias + 2 * 256;                                                   // [2][256*TC_OPMAX]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_wl + 2 * 256 * TC_OPMAX);         // full[4] empty[4] tfull[2] tempty[2]
+           const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+           const __grid_constant__ CUtensorMap tmSh, const __grid_constant__ CUtensorMap tmSl, const tc_params p) {
+    // SWIZZLE_128B (TMA destination, UMMA descriptor with base_offset = 0) needs a 1024-byte aligned base
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* s_bias = reinterpret_cast<float*>(smem + TC_OFF_BIAS);                     // [2][256]
+    float* s_wout = reinterpret_cast<float*>(smem + TC_OFF_STORE);                    // FUSED: [2][256*TC_OP]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);                 // full[4] empty[4] tfull[2] tempty[2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -173,10 +254,12 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
     const uint32_t a_bytes = TC_BM * TC_BK * 2, b_bytes = (uint32_t)BN * TC_BK * 2;
 
     if (threadIdx.x == 0) {
+        if (smem_base & 1023u) { printf("ssi_tc: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 128); }
         fence_barrier_init();
         tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+        if (MODE == TC_MODE_HIDDEN) { tma_prefetch_desc(&tmSh); tma_prefetch_desc(&tmSl); }
     }
     if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
     tc_fence_before();
@@ -184,25 +267,27 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    const int n_work = p.G * p.m_tiles;
-
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const int g = w / p.m_tiles, mt = w % p.m_tiles;
+            // weights are re-read by every CTA working on the sample: keep them in L2; a shared A (the dataset)
+            // likewise; per-sample activations are read by one CTA only
+            const uint64_t pol_a = p.a_shared ? TC_EVICT_LAST : TC_EVICT_NORMAL;
+            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+                int g, mt;
+                if (!tc_decode_work(p, w, g, mt)) continue;
                 for (int nt = 0; nt < p.n_tiles; ++nt) {
                     for (int kb = 0; kb < p.k_blocks; ++kb) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t full = bar_full + 8 * stage;
                         const uint32_t sA = smem_base + stage * p.stage_bytes;
                         mbar_expect_tx(full, 2 * a_bytes + 2 * b_bytes);
-                        tma_load_3d(sA, &tmAh, full, kb * TC_BK, mt * TC_BM, p.a_shared ? 0 : g);
-                        tma_load_3d(sA + a_bytes, &tmAl, full, kb * TC_BK, mt * TC_BM, p.a_shared ? 0 : g);
-                        tma_load_3d(sA + 2 * a_bytes, &tmBh, full, kb * TC_BK, nt * BN, g);
-                        tma_load_3d(sA + 2 * a_bytes + b_bytes, &tmBl, full, kb * TC_BK, nt * BN, g);
+                        tma_load_3d_hint(sA, &tmAh, full, kb * TC_BK, mt * TC_BM, p.a_shared ? 0 : g, pol_a);
+                        tma_load_3d_hint(sA + a_bytes, &tmAl, full, kb * TC_BK, mt * TC_BM, p.a_shared ? 0 : g, pol_a);
+                        tma_load_3d_hint(sA + 2 * a_bytes, &tmBh, full, kb * TC_BK, nt * BN, g, TC_EVICT_LAST);
+                        tma_load_3d_hint(sA + 2 * a_bytes + b_bytes, &tmBl, full, kb * TC_BK, nt * BN, g, TC_EVICT_LAST);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -215,7 +300,9 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
             int stage = 0;
             uint32_t phase = 0;
             uint32_t tile = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+                int g, mt;
+                if (!tc_decode_work(p, w, g, mt)) continue;
                 for (int nt = 0; nt < p.n_tiles; ++nt, ++tile) {
                     const uint32_t ab = tile & 1, aphase = (tile >> 1) & 1;
                     mbar_wait(bar_tempty + 8 * ab, aphase ^ 1);        // epilogue has drained this accumulator
@@ -244,51 +331,97 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
     } else {
         // ================= epilogue (4 warps = 128 TMEM lanes) =================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;
         const int et = threadIdx.x - 64;             // 0..127
+        // HIDDEN: this warp's TMA-store staging: [2 buffers][hi | lo][32 rows x 64 B], SWIZZLE_64B
+        const uint32_t stage_w = smem_base + TC_OFF_STORE + (uint32_t)(warp - 2) * 8192;
+        const uint32_t swz = (uint32_t)((lane >> 1) & 3);
+        uint32_t chunk_ctr = 0;
         uint32_t tile = 0;
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-            const int g = w / p.m_tiles, mt = w % p.m_tiles;
-            const long long m = (long long)mt * TC_BM + row;
-            const bool valid = m < p.N;
-            float pred[TC_OPMAX];
+        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            int g, mt;
+            if (!tc_decode_work(p, w, g, mt)) continue;
+            double sse = 0.0;
+            // FUSED: 4 rows per thread (see tmem_ld_16x256b_x8), partial sums over this thread's columns
+            float pred[4][TC_OP];
+            if (MODE == TC_MODE_FUSED) {
 #pragma unroll
-            for (int o = 0; o < TC_OPMAX; ++o) pred[o] = 0.0f;
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int o = 0; o < TC_OP; ++o) pred[r][o] = 0.0f;
+            }
 
             for (int nt = 0; nt < p.n_tiles; ++nt, ++tile) {
                 const uint32_t ab = tile & 1, aphase = (tile >> 1) & 1;
                 float* sb = s_bias + ab * 256;
-                float* sw = s_wl + ab * 256 * TC_OPMAX;
+                float* sw = s_wout + ab * 256 * TC_OP;
                 // stage this tile's bias (and output-layer weights) while the MMAs run
                 for (int c = et; c < BN; c += 128) sb[c] = p.bias[(long long)g * p.width + nt * BN + c];
-                if (FINAL) {
-                    const float4* src = reinterpret_cast<const float4*>(p.Wlast + ((long long)g * p.width + nt * BN) * TC_OPMAX);
+                if (MODE == TC_MODE_FUSED) {
+                    const float4* src = reinterpret_cast<const float4*>(p.Wout + ((long long)g * p.width + nt * BN) * TC_OP);
                     float4* dst = reinterpret_cast<float4*>(sw);
-                    for (int c = et; c < BN * TC_OPMAX / 4; c += 128) dst[c] = src[c];
+                    for (int c = et; c < BN * TC_OP / 4; c += 128) dst[c] = src[c];
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 mbar_wait(bar_tfull + 8 * ab, aphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c0, v);
-                    tmem_ld_wait();
-                    if (FINAL) {
+                if (MODE == TC_MODE_FINAL) {
+                    const long long m = (long long)mt * TC_BM + q * 32 + lane;
+                    const bool valid = m < p.N;
+                    for (int c0 = 0; c0 < BN; c0 += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(taddr + c0, v);
+                        tmem_ld_wait();
+                        if (valid) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float h = ssi_act(__uint_as_float(v[j]) + sb[c0 + j], p.act);
-                            const float4* w4 = reinterpret_cast<const float4*>(sw + (c0 + j) * TC_OPMAX);
-#pragma unroll
-                            for (int o4 = 0; o4 < TC_OPMAX / 4; ++o4) {
-                                const float4 ww = w4[o4];
-                                pred[4 * o4 + 0] = fmaf(h, ww.x, pred[4 * o4 + 0]);
-                                pred[4 * o4 + 1] = fmaf(h, ww.y, pred[4 * o4 + 1]);
-                                pred[4 * o4 + 2] = fmaf(h, ww.z, pred[4 * o4 + 2]);
-                                pred[4 * o4 + 3] = fmaf(h, ww.w, pred[4 * o4 + 3]);
+                            for (int j = 0; j < 16; ++j) {
+                                const int o = nt * BN + c0 + j;
+                                if (o < p.O) {
+                                    const float df = ssi_act(__uint_as_float(v[j]) + sb[c0 + j], p.act) - p.Y[o + m * p.O];
+                                    sse += (double)df * (double)df;
+                                }
                             }
                         }
-                    } else {
+                    }
+                } else if (MODE == TC_MODE_FUSED) {
+                    const int cq = 2 * (lane & 3);
+                    for (int cb = 0; cb < BN; cb += 64) {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld_16x256b_x8(taddr + cb, v0);                                   // lanes q*32 + [0,16)
+                        tmem_ld_16x256b_x8(taddr + ((uint32_t)16 << 16) + cb, v1);            // lanes q*32 + [16,32)
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int col = cb + 8 * i + cq + e;
+                                const float b = sb[col];
+                                const float4* w4 = reinterpret_cast<const float4*>(sw + col * TC_OP);
+                                float wv[TC_OP];
+#pragma unroll
+                                for (int o4 = 0; o4 < TC_OP / 4; ++o4) {
+                                    const float4 ww = w4[o4];
+                                    wv[4 * o4] = ww.x; wv[4 * o4 + 1] = ww.y; wv[4 * o4 + 2] = ww.z; wv[4 * o4 + 3] = ww.w;
+                                }
+                                const float h0 = ssi_act(__uint_as_float(v0[4 * i + e]) + b, p.act);
+                                const float h1 = ssi_act(__uint_as_float(v0[4 * i + 2 + e]) + b, p.act);
+                                const float h2 = ssi_act(__uint_as_float(v1[4 * i + e]) + b, p.act);
+                                const float h3 = ssi_act(__uint_as_float(v1[4 * i + 2 + e]) + b, p.act);
+#pragma unroll
+                                for (int o = 0; o < TC_OP; ++o) {
+                                    pred[0][o] = fmaf(h0, wv[o], pred[0][o]);
+                                    pred[1][o] = fmaf(h1, wv[o], pred[1][o]);
+                                    pred[2][o] = fmaf(h2, wv[o], pred[2][o]);
+                                    pred[3][o] = fmaf(h3, wv[o], pred[3][o]);
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + c0, v);
+                        tmem_ld_wait();
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
@@ -300,37 +433,57 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                             hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
                             lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
                         }
-                        if (valid) {
-                            const long long off = ((long long)g * p.N + m) * p.width + nt * BN + c0;
-                            uint4* dh = reinterpret_cast<uint4*>(p.Hh + off);
-                            uint4* dl = reinterpret_cast<uint4*>(p.Hl + off);
+                        // the TMA store that last read this staging buffer (two chunks ago) must have finished reading
+                        if (chunk_ctr >= 2) {
+                            if (lane == 0) tma_store_wait_read1();
+                            __syncwarp();
+                        }
+                        const uint32_t sh = stage_w + (chunk_ctr & 1) * 4096, sl = sh + 2048;
 #pragma unroll
-                            for (int s = 0; s < 4; ++s) {
-                                dh[s] = make_uint4(hi[4 * s], hi[4 * s + 1], hi[4 * s + 2], hi[4 * s + 3]);
-                                dl[s] = make_uint4(lo[4 * s], lo[4 * s + 1], lo[4 * s + 2], lo[4 * s + 3]);
-                            }
+                        for (int c = 0; c < 4; ++c) {
+                            const uint32_t off = (uint32_t)lane * 64 + (((uint32_t)c ^ swz) << 4);
+                            st_shared_v4(sh + off, hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                            st_shared_v4(sl + off, lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            // rows >= N are clipped by TMA; the activations are consumed by the next kernel, far
+                            // beyond L2 residency: do not let them evict the operands
+                            tma_store_3d_hint(&tmSh, sh, nt * BN + c0, mt * TC_BM + q * 32, g, TC_EVICT_FIRST);
+                            tma_store_3d_hint(&tmSl, sl, nt * BN + c0, mt * TC_BM + q * 32, g, TC_EVICT_FIRST);
+                            tma_store_commit();
                         }
                     }
                 }
                 tc_fence_before();
                 mbar_arrive(bar_tempty + 8 * ab);
             }
-            if (FINAL) {
-                double sse = 0.0;
-                if (valid) {
-                    const float* bl = p.blast + (long long)g * TC_OPMAX;
+            if (MODE == TC_MODE_FUSED) {
+                // the 4 threads of a quad hold the same 4 rows for interleaved columns: reduce across the quad,
+                // then quad member j finishes row j
+                const float* bo = p.bout + (long long)g * TC_OP;
 #pragma unroll
-                    for (int o = 0; o < TC_OPMAX; ++o) {
-                        if (o < p.O) {
-                            const float df = ssi_act(pred[o] + bl[o], p.act_last) - p.Y[o + m * p.O];
+                for (int r = 0; r < 4; ++r) {
+                    const long long m = (long long)mt * TC_BM + q * 32 + (r >> 1) * 16 + (lane >> 2) + 8 * (r & 1);
+#pragma unroll
+                    for (int o = 0; o < TC_OP; ++o) {
+                        float v = pred[r][o];
+                        v += __shfl_xor_sync(0xffffffffu, v, 1);
+                        v += __shfl_xor_sync(0xffffffffu, v, 2);
+                        if ((lane & 3) == r && o < p.O && m < p.N) {
+                            const float df = ssi_act(v + bo[o], p.act_out) - p.Y[o + m * p.O];
                             sse += (double)df * (double)df;
                         }
                     }
                 }
+            }
+            if (MODE != TC_MODE_HIDDEN) {
                 sse = ssi_warp_sum(sse);
                 if (lane == 0) p.partials[(long long)g * (p.m_tiles * 4) + mt * 4 + q] = sse;
             }
         }
+        if (MODE == TC_MODE_HIDDEN && lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -362,11 +515,12 @@ k_tc_split_x(const float* __restrict__ X, long long N, int in0, int Kp, bf16* __
     Xl[e] = lo;
 }
 
-// One Dense weight matrix of the group: flat (out x in, column-major: o + i*out) -> split BF16 [g][o][Kp].
-// Each block owns a 32(i) x 32(o) tile; P is read once for all G samples (K1, src/space_inference.jl:91).
+// One Dense weight matrix of the group: flat (out x in, column-major: o + i*out) -> split BF16 [g][o][Kp],
+// zero padded to out_pad rows and Kp columns.  Each block owns a 32(i) x 32(o) tile; P is read once for
+// all G samples (K1, src/space_inference.jl:91).
 __global__ void __launch_bounds__(256)
 k_tc_project_w(const float* __restrict__ Wswa, const float* __restrict__ P, const float* __restrict__ Z,
-               long long n, int M, int G, long long w_off, int in, int out, int Kp,
+               long long n, int M, int G, long long w_off, int in, int out, int out_pad, int Kp,
                bf16* __restrict__ Wh, bf16* __restrict__ Wl) {
     __shared__ float zs[SSI_MAX_M * TC_GMAX];
     __shared__ float tile[32][33];
@@ -405,10 +559,10 @@ k_tc_project_w(const float* __restrict__ Wswa, const float* __restrict__ P, cons
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int o = o0 + ty + 8 * r, i = i0 + tx;
-            if (o < out && i < Kp) {
+            if (o < out_pad && i < Kp) {
                 bf16 hi, lo;
                 split_bf16(tile[tx][ty + 8 * r], hi, lo);
-                const long long dst = ((long long)g * out + o) * Kp + i;
+                const long long dst = ((long long)g * out_pad + o) * Kp + i;
                 Wh[dst] = hi;
                 Wl[dst] = lo;
             }
@@ -416,8 +570,36 @@ k_tc_project_w(const float* __restrict__ Wswa, const float* __restrict__ P, cons
     }
 }
 
-// Vector-like pieces: dst[g][(e / inner) * dst_ld + (e % inner)] = (W_swa + P z_g)[src_off + e]
-// biases: inner = count, dst_ld = 0 (plain copy);  output layer W (O x width col-major): inner = O, dst_ld = TC_OPMAX
+// bias[g][o] = (W_swa + P z_g)[b_off + o] for o < out, 0 for the padded tail
+__global__ void __launch_bounds__(256)
+k_tc_project_b(const float* __restrict__ Wswa, const float* __restrict__ P, const float* __restrict__ Z,
+               long long n, int M, int G, long long b_off, int out, int out_pad, float* __restrict__ dst) {
+    __shared__ float zs[SSI_MAX_M * TC_GMAX];
+    for (int e = threadIdx.x; e < M * G; e += 256) zs[e] = Z[e];
+    __syncthreads();
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= out_pad) return;
+    float acc[TC_GMAX];
+#pragma unroll
+    for (int g = 0; g < TC_GMAX; ++g) acc[g] = 0.0f;
+    if (o < out) {
+        const long long flat = b_off + o;
+        const float w0 = Wswa[flat];
+#pragma unroll
+        for (int g = 0; g < TC_GMAX; ++g) acc[g] = w0;
+        for (int m = 0; m < M; ++m) {
+            const float pv = P[flat + (long long)m * n];
+#pragma unroll
+            for (int g = 0; g < TC_GMAX; ++g) acc[g] = fmaf(pv, zs[m + g * M], acc[g]);
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < TC_GMAX; ++g)
+        if (g < G) dst[(long long)g * out_pad + o] = acc[g];
+}
+
+// Fused output layer: W (O x width column-major, o + c*O) -> dst[g][c][TC_OP] (zero padded);
+// bias: inner = count -> dst[g][o].   dst[g][(e / inner) * dst_ld + (e % inner)] = (W_swa + P z_g)[src_off + e]
 __global__ void __launch_bounds__(256)
 k_tc_project_v(const float* __restrict__ Wswa, const float* __restrict__ P, const float* __restrict__ Z,
                long long n, int M, int G, long long src_off, int count, int inner, int dst_ld, long long dst_gs,
@@ -452,24 +634,25 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 struct ssi_tc_state {
     bool ready = false;
-    int nl = 0;                          // tensor layers = L - 1 (all but the fused output layer)
-    int Kp[SSI_MAX_LAYERS] = {0};
-    int width[SSI_MAX_LAYERS] = {0};
+    int nl = 0;                          // GEMM launches per group: L, or L-1 when the output layer is fused
+    bool fused_out = false;              // output layer folded into the last hidden layer's epilogue (O <= TC_OP, L >= 2)
+    float *Wout = nullptr, *bout = nullptr;
+    int Kp[SSI_MAX_LAYERS] = {0};        // padded input width of layer l
+    int width[SSI_MAX_LAYERS] = {0};     // padded output width of layer l
     int BN[SSI_MAX_LAYERS] = {0};
     int G = TC_GMAX;
     bf16 *Xh = nullptr, *Xl = nullptr;
     bf16 *Wh[SSI_MAX_LAYERS] = {nullptr}, *Wl[SSI_MAX_LAYERS] = {nullptr};
     float* bias[SSI_MAX_LAYERS] = {nullptr};
-    float *Wlast = nullptr, *blast = nullptr;
     bf16 *Hh[2] = {nullptr, nullptr}, *Hl[2] = {nullptr, nullptr};
     double* partials = nullptr;
     CUtensorMap tmAh[SSI_MAX_LAYERS], tmAl[SSI_MAX_LAYERS], tmBh[SSI_MAX_LAYERS], tmBl[SSI_MAX_LAYERS];
+    CUtensorMap tmSh[SSI_MAX_LAYERS], tmSl[SSI_MAX_LAYERS];
     PFN_encodeTiled encode = nullptr;
-    size_t smem_bytes = 0;
 };
 
 static void tc_free(ssi_tc_state* s) {
-    cudaFree(s->Xh); cudaFree(s->Xl); cudaFree(s->Wlast); cudaFree(s->blast); cudaFree(s->partials);
+    cudaFree(s->Xh); cudaFree(s->Xl); cudaFree(s->partials); cudaFree(s->Wout); cudaFree(s->bout);
     for (int i = 0; i < 2; ++i) { cudaFree(s->Hh[i]); cudaFree(s->Hl[i]); }
     for (int l = 0; l < SSI_MAX_LAYERS; ++l) { cudaFree(s->Wh[l]); cudaFree(s->Wl[l]); cudaFree(s->bias[l]); }
     PFN_encodeTiled enc = s->encode;
@@ -488,29 +671,43 @@ void ssi_tc_destroy(ssi_ctx* ctx) {
     ctx->tc = nullptr;
 }
 
+// Any Dense chain runs on this path (widths are zero-padded); AUTO prefers it when the padded
+// tensor-core work is not dominated by padding, i.e. the layers are wide.
 bool ssi_tc_supported(const ssi_ctx* ctx) {
     if (!ctx->has_model) return false;
     const ssi_model_t& m = ctx->model;
-    if (m.L < 2 || m.dims[m.L] > TC_OPMAX || ctx->M > SSI_MAX_M) return false;
-    for (int l = 1; l < m.L; ++l)
-        if (m.dims[l] % 64 != 0) return false;
+    if (m.dims[m.L] > 256 || ctx->M > SSI_MAX_M) return false;
     return true;
 }
 
-static int tc_make_map(ssi_ctx* ctx, CUtensorMap* map, void* base, uint64_t inner, uint64_t rows, uint64_t batch, uint32_t box_rows) {
+bool ssi_tc_preferred(const ssi_ctx* ctx) {
+    if (!ssi_tc_supported(ctx)) return false;
+    const ssi_model_t& m = ctx->model;
+    double real = 0, padded = 0;
+    for (int l = 0; l < m.L; ++l) {
+        const double kp = (m.dims[l] + 63) / 64 * 64;
+        const double np = l == m.L - 1 ? (m.dims[l + 1] + 15) / 16 * 16 : (m.dims[l + 1] + 63) / 64 * 64;
+        real += (double)m.dims[l] * m.dims[l + 1];
+        padded += kp * np;
+    }
+    return real >= 64.0 * 64.0 && padded <= 2.0 * real;
+}
+
+static int tc_make_map(ssi_ctx* ctx, CUtensorMap* map, void* base, uint64_t inner, uint64_t rows, uint64_t batch,
+                       uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz) {
     cuuint64_t dims[3] = {inner, rows, batch};
     cuuint64_t strides[2] = {inner * sizeof(bf16), inner * rows * sizeof(bf16)};
-    cuuint32_t box[3] = {TC_BK, box_rows, 1};
+    cuuint32_t box[3] = {box_inner, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = ctx->tc->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr,
-                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return ssi_fail(ctx, SSI_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return SSI_OK;
 }
 
 int ssi_tc_prepare(ssi_ctx* ctx) {
-    if (!ssi_tc_supported(ctx)) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "tensor path: unsupported model shape");
+    if (!ssi_tc_supported(ctx)) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "tensor path: output width > 256 is not supported");
     if (!ctx->tc) ctx->tc = new ssi_tc_state();
     ssi_tc_state* s = ctx->tc;
     if (s->ready) return SSI_OK;
@@ -525,27 +722,33 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
     tc_free(s);
     const ssi_model_t& m = ctx->model;
     const int64_t N = ctx->N;
-    s->nl = m.L - 1;
+    s->fused_out = (m.L >= 2 && m.dims[m.L] <= TC_OP && !ctx->opt_tc_nofuse);
+    s->nl = s->fused_out ? m.L - 1 : m.L;
     s->G = ctx->opt_group > 0 ? std::min(ctx->opt_group, TC_GMAX) : TC_GMAX;
     const int G = s->G;
     int maxw = 0;
     for (int l = 0; l < s->nl; ++l) {
+        const bool last = (l == m.L - 1);          // a true output layer computed as a GEMM
         s->Kp[l] = (m.dims[l] + TC_BK - 1) / TC_BK * TC_BK;
-        s->width[l] = m.dims[l + 1];
-        s->BN[l] = s->width[l] % 256 == 0 ? 256 : (s->width[l] % 128 == 0 ? 128 : 64);
+        s->width[l] = last ? (m.dims[l + 1] + 15) / 16 * 16 : (m.dims[l + 1] + 63) / 64 * 64;
+        if (last) s->BN[l] = s->width[l];            // <= 256, a multiple of 16
+        else s->BN[l] = s->width[l] % 256 == 0 ? 256 : (s->width[l] % 128 == 0 ? 128 : 64);
         if (l < s->nl - 1) maxw = std::max(maxw, s->width[l]);
-        SSI_CUDA(ctx, cudaMalloc(&s->Wh[l], sizeof(bf16) * (size_t)G * s->width[l] * s->Kp[l]));
-        SSI_CUDA(ctx, cudaMalloc(&s->Wl[l], sizeof(bf16) * (size_t)G * s->width[l] * s->Kp[l]));
+        const size_t wn = (size_t)G * s->width[l] * s->Kp[l];
+        SSI_CUDA(ctx, cudaMalloc(&s->Wh[l], sizeof(bf16) * wn));
+        SSI_CUDA(ctx, cudaMalloc(&s->Wl[l], sizeof(bf16) * wn));
         SSI_CUDA(ctx, cudaMalloc(&s->bias[l], sizeof(float) * (size_t)G * s->width[l]));
     }
-    const int wlast = s->width[s->nl - 1];
-    SSI_CUDA(ctx, cudaMalloc(&s->Wlast, sizeof(float) * (size_t)G * wlast * TC_OPMAX));
-    SSI_CUDA(ctx, cudaMalloc(&s->blast, sizeof(float) * (size_t)G * TC_OPMAX));
-    SSI_CUDA(ctx, cudaMemsetAsync(s->Wlast, 0, sizeof(float) * (size_t)G * wlast * TC_OPMAX, ctx->stream));
-    SSI_CUDA(ctx, cudaMemsetAsync(s->blast, 0, sizeof(float) * (size_t)G * TC_OPMAX, ctx->stream));
+    if (s->fused_out) {
+        const int wl = s->width[s->nl - 1];
+        SSI_CUDA(ctx, cudaMalloc(&s->Wout, sizeof(float) * (size_t)G * wl * TC_OP));
+        SSI_CUDA(ctx, cudaMalloc(&s->bout, sizeof(float) * (size_t)G * TC_OP));
+        SSI_CUDA(ctx, cudaMemsetAsync(s->Wout, 0, sizeof(float) * (size_t)G * wl * TC_OP, ctx->stream));
+        SSI_CUDA(ctx, cudaMemsetAsync(s->bout, 0, sizeof(float) * (size_t)G * TC_OP, ctx->stream));
+    }
     SSI_CUDA(ctx, cudaMalloc(&s->Xh, sizeof(bf16) * (size_t)N * s->Kp[0]));
     SSI_CUDA(ctx, cudaMalloc(&s->Xl, sizeof(bf16) * (size_t)N * s->Kp[0]));
-    const int nbuf = s->nl >= 3 ? 2 : (s->nl == 2 ? 1 : 0);
+    const int nbuf = s->nl >= 3 ? 2 : (s->nl == 2 ? 1 : 0);   // layers 0..nl-2 store activations
     for (int i = 0; i < nbuf; ++i) {
         SSI_CUDA(ctx, cudaMalloc(&s->Hh[i], sizeof(bf16) * (size_t)G * N * maxw));
         SSI_CUDA(ctx, cudaMalloc(&s->Hl[i], sizeof(bf16) * (size_t)G * N * maxw));
@@ -558,20 +761,29 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
         SSI_LAUNCH_CHECK(ctx);
     }
     for (int l = 0; l < s->nl; ++l) {
+        const CUtensorMapSwizzle S128 = CU_TENSOR_MAP_SWIZZLE_128B, S64 = CU_TENSOR_MAP_SWIZZLE_64B;
         if (l == 0) {
-            SSI_TRY(tc_make_map(ctx, &s->tmAh[l], s->Xh, s->Kp[0], N, 1, TC_BM));
-            SSI_TRY(tc_make_map(ctx, &s->tmAl[l], s->Xl, s->Kp[0], N, 1, TC_BM));
+            SSI_TRY(tc_make_map(ctx, &s->tmAh[l], s->Xh, s->Kp[0], N, 1, TC_BK, TC_BM, S128));
+            SSI_TRY(tc_make_map(ctx, &s->tmAl[l], s->Xl, s->Kp[0], N, 1, TC_BK, TC_BM, S128));
         } else {
-            // activations written by layer l-1: [G][N][width_{l-1}], K = width_{l-1} (a multiple of 64)
-            SSI_TRY(tc_make_map(ctx, &s->tmAh[l], s->Hh[(l - 1) & 1], s->width[l - 1], N, G, TC_BM));
-            SSI_TRY(tc_make_map(ctx, &s->tmAl[l], s->Hl[(l - 1) & 1], s->width[l - 1], N, G, TC_BM));
+            // activations written by layer l-1: [G][N][width_{l-1}], K = width_{l-1} = Kp[l]
+            SSI_TRY(tc_make_map(ctx, &s->tmAh[l], s->Hh[(l - 1) & 1], s->width[l - 1], N, G, TC_BK, TC_BM, S128));
+            SSI_TRY(tc_make_map(ctx, &s->tmAl[l], s->Hl[(l - 1) & 1], s->width[l - 1], N, G, TC_BK, TC_BM, S128));
         }
-        SSI_TRY(tc_make_map(ctx, &s->tmBh[l], s->Wh[l], s->Kp[l], s->width[l], G, s->BN[l]));
-        SSI_TRY(tc_make_map(ctx, &s->tmBl[l], s->Wl[l], s->Kp[l], s->width[l], G, s->BN[l]));
+        SSI_TRY(tc_make_map(ctx, &s->tmBh[l], s->Wh[l], s->Kp[l], s->width[l], G, TC_BK, s->BN[l], S128));
+        SSI_TRY(tc_make_map(ctx, &s->tmBl[l], s->Wl[l], s->Kp[l], s->width[l], G, TC_BK, s->BN[l], S128));
+        if (l < s->nl - 1) {
+            // epilogue stores of this layer's activations: 32 rows x 32 columns (64 B) per warp and chunk
+            SSI_TRY(tc_make_map(ctx, &s->tmSh[l], s->Hh[l & 1], s->width[l], N, G, 32, 32, S64));
+            SSI_TRY(tc_make_map(ctx, &s->tmSl[l], s->Hl[l & 1], s->width[l], N, G, 32, 32, S64));
+        } else {
+            s->tmSh[l] = s->tmAh[l];
+            s->tmSl[l] = s->tmAl[l];
+        }
     }
-    s->smem_bytes = 1024 + TC_SMEM_PIPE + sizeof(float) * (2 * 256 + 2 * 256 * TC_OPMAX) + 12 * 8 + 16;
-    SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_layer<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_layer<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_layer<TC_MODE_HIDDEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
+    SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_layer<TC_MODE_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
+    SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_layer<TC_MODE_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     s->ready = true;
     return SSI_OK;
@@ -587,7 +799,6 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
     const int M = ctx->M;
     const int m_tiles = (int)((N + TC_BM - 1) / TC_BM);
     const int parts = m_tiles * 4;
-    const int O = m.dims[m.L];
 
     for (int64_t b0 = 0; b0 < B; b0 += s->G) {
         const int G = (int)std::min<int64_t>(s->G, B - b0);
@@ -595,20 +806,20 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
         // ---- K1: project the group's weights straight into the GEMM operand layouts ----
         for (int l = 0; l < s->nl; ++l) {
             dim3 grid((s->Kp[l] + 31) / 32, (s->width[l] + 31) / 32);
-            k_tc_project_w<<<grid, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.w_off[l], m.dims[l], s->width[l],
-                                                         s->Kp[l], s->Wh[l], s->Wl[l]);
+            k_tc_project_w<<<grid, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.w_off[l], m.dims[l], m.dims[l + 1],
+                                                         s->width[l], s->Kp[l], s->Wh[l], s->Wl[l]);
             SSI_LAUNCH_CHECK(ctx);
-            k_tc_project_v<<<(s->width[l] + 255) / 256, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.b_off[l], s->width[l],
-                                                                           s->width[l], 0, s->width[l], s->bias[l]);
+            k_tc_project_b<<<(s->width[l] + 255) / 256, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.b_off[l],
+                                                                           m.dims[l + 1], s->width[l], s->bias[l]);
             SSI_LAUNCH_CHECK(ctx);
         }
-        {
-            const int wl = s->width[s->nl - 1];
-            const int cnt = wl * O;
+        if (s->fused_out) {
+            const int wl = s->width[s->nl - 1];          // padded width of the last hidden layer
+            const int O = m.dims[m.L], cnt = m.dims[m.L - 1] * O;
             k_tc_project_v<<<(cnt + 255) / 256, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.w_off[m.L - 1], cnt, O,
-                                                                     TC_OPMAX, (long long)wl * TC_OPMAX, s->Wlast);
+                                                                     TC_OP, (long long)wl * TC_OP, s->Wout);
             SSI_LAUNCH_CHECK(ctx);
-            k_tc_project_v<<<1, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.b_off[m.L - 1], O, O, 0, TC_OPMAX, s->blast);
+            k_tc_project_v<<<1, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.b_off[m.L - 1], O, O, 0, TC_OP, s->bout);
             SSI_LAUNCH_CHECK(ctx);
         }
         // ---- the Dense chain ----
@@ -621,16 +832,25 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
             p.a_shared = (l == 0);
             p.act = m.act[l];
             p.stage_bytes = 2 * TC_BM * TC_BK * 2 + 2 * p.BN * TC_BK * 2;
+            p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
             p.stages = std::min(4, TC_SMEM_PIPE / p.stage_bytes);
             p.bias = s->bias[l];
             const int grid = std::min(ctx->sm_count, G * m_tiles);
-            if (l == s->nl - 1) {
-                p.Wlast = s->Wlast; p.blast = s->blast; p.Y = ctx->dY; p.O = O; p.act_last = m.act[m.L - 1];
-                p.partials = s->partials;
-                k_tc_layer<true><<<grid, TC_THREADS, s->smem_bytes, ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l], p);
+            // a shared A operand (the dataset): run the group's samples side by side on the same m-tiles
+            p.mt_block = (p.a_shared && G > 1 && !ctx->opt_tc_noorder) ? std::max(1, (grid + G - 1) / G) : 0;
+            p.n_work = p.mt_block > 0 ? (m_tiles + p.mt_block - 1) / p.mt_block * p.mt_block * G : G * m_tiles;
+            p.Y = ctx->dY; p.O = m.dims[m.L]; p.partials = s->partials;
+            const bool last = (l == s->nl - 1);
+            if (last && s->fused_out) {
+                p.act_out = m.act[m.L - 1]; p.Wout = s->Wout; p.bout = s->bout;
+                k_tc_layer<TC_MODE_FUSED><<<grid, TC_THREADS, TC_SMEM_TOTAL, ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l],
+                                                                                          s->tmSh[l], s->tmSl[l], p);
+            } else if (last) {
+                k_tc_layer<TC_MODE_FINAL><<<grid, TC_THREADS, TC_SMEM_TOTAL, ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l],
+                                                                                          s->tmSh[l], s->tmSl[l], p);
             } else {
-                p.Hh = s->Hh[l & 1]; p.Hl = s->Hl[l & 1];
-                k_tc_layer<false><<<grid, TC_THREADS, s->smem_bytes, ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l], p);
+                k_tc_layer<TC_MODE_HIDDEN><<<grid, TC_THREADS, TC_SMEM_TOTAL, ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l],
+                                                                                           s->tmSh[l], s->tmSl[l], p);
             }
             SSI_LAUNCH_CHECK(ctx);
         }
