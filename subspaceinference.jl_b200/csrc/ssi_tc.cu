@@ -167,6 +167,13 @@ __device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t v[32
         : "r"(taddr)
         : "memory");
 }
+// same layout, 16 columns (two 8-column blocks): 8 registers
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t v[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -234,7 +241,19 @@ __device__ __forceinline__ bool tc_decode_work(const tc_params& p, int w, int& g
     return true;
 }
 
-template <int MODE>
+// activation as a compile-time constant: the epilogue stays straight-line code (a run-time switch per
+// element bloats the unrolled loops past the instruction cache)
+template <int ACT>
+__device__ __forceinline__ float tc_act(float v) {
+    if (ACT == SSI_ACT_RELU) return fmaxf(v, 0.0f);
+    if (ACT == SSI_ACT_TANH) return tanhf(v);
+    if (ACT == SSI_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+    return v;
+}
+
+__device__ __noinline__ float tc_act_rt(float v, int act) { return ssi_act(v, act); }
+
+template <int MODE, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
            const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -368,6 +387,7 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                 if (MODE == TC_MODE_FINAL) {
                     const long long m = (long long)mt * TC_BM + q * 32 + lane;
                     const bool valid = m < p.N;
+#pragma unroll 1
                     for (int c0 = 0; c0 < BN; c0 += 16) {
                         uint32_t v[16];
                         tmem_ld16(taddr + c0, v);
@@ -377,7 +397,7 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                             for (int j = 0; j < 16; ++j) {
                                 const int o = nt * BN + c0 + j;
                                 if (o < p.O) {
-                                    const float df = ssi_act(__uint_as_float(v[j]) + sb[c0 + j], p.act) - p.Y[o + m * p.O];
+                                    const float df = tc_act<ACT>(__uint_as_float(v[j]) + sb[c0 + j]) - p.Y[o + m * p.O];
                                     sse += (double)df * (double)df;
                                 }
                             }
@@ -385,13 +405,14 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                     }
                 } else if (MODE == TC_MODE_FUSED) {
                     const int cq = 2 * (lane & 3);
-                    for (int cb = 0; cb < BN; cb += 64) {
-                        uint32_t v0[32], v1[32];
-                        tmem_ld_16x256b_x8(taddr + cb, v0);                                   // lanes q*32 + [0,16)
-                        tmem_ld_16x256b_x8(taddr + ((uint32_t)16 << 16) + cb, v1);            // lanes q*32 + [16,32)
+#pragma unroll 1
+                    for (int cb = 0; cb < BN; cb += 16) {
+                        uint32_t v0[8], v1[8];
+                        tmem_ld_16x256b_x2(taddr + cb, v0);                                   // lanes q*32 + [0,16)
+                        tmem_ld_16x256b_x2(taddr + ((uint32_t)16 << 16) + cb, v1);            // lanes q*32 + [16,32)
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
+                        for (int i = 0; i < 2; ++i) {
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 const int col = cb + 8 * i + cq + e;
@@ -403,10 +424,10 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                                     const float4 ww = w4[o4];
                                     wv[4 * o4] = ww.x; wv[4 * o4 + 1] = ww.y; wv[4 * o4 + 2] = ww.z; wv[4 * o4 + 3] = ww.w;
                                 }
-                                const float h0 = ssi_act(__uint_as_float(v0[4 * i + e]) + b, p.act);
-                                const float h1 = ssi_act(__uint_as_float(v0[4 * i + 2 + e]) + b, p.act);
-                                const float h2 = ssi_act(__uint_as_float(v1[4 * i + e]) + b, p.act);
-                                const float h3 = ssi_act(__uint_as_float(v1[4 * i + 2 + e]) + b, p.act);
+                                const float h0 = tc_act<ACT>(__uint_as_float(v0[4 * i + e]) + b);
+                                const float h1 = tc_act<ACT>(__uint_as_float(v0[4 * i + 2 + e]) + b);
+                                const float h2 = tc_act<ACT>(__uint_as_float(v1[4 * i + e]) + b);
+                                const float h3 = tc_act<ACT>(__uint_as_float(v1[4 * i + 2 + e]) + b);
 #pragma unroll
                                 for (int o = 0; o < TC_OP; ++o) {
                                     pred[0][o] = fmaf(h0, wv[o], pred[0][o]);
@@ -418,6 +439,7 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                         }
                     }
                 } else {
+#pragma unroll 1
                     for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
                         uint32_t v[32];
                         tmem_ld32(taddr + c0, v);
@@ -425,8 +447,8 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
-                            const float x0 = ssi_act(__uint_as_float(v[j]) + sb[c0 + j], p.act);
-                            const float x1 = ssi_act(__uint_as_float(v[j + 1]) + sb[c0 + j + 1], p.act);
+                            const float x0 = tc_act<ACT>(__uint_as_float(v[j]) + sb[c0 + j]);
+                            const float x1 = tc_act<ACT>(__uint_as_float(v[j + 1]) + sb[c0 + j + 1]);
                             const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
                             const float2 hf = __bfloat1622float2(h2);
                             const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
@@ -463,16 +485,24 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                 // the 4 threads of a quad hold the same 4 rows for interleaved columns: reduce across the quad,
                 // then quad member j finishes row j
                 const float* bo = p.bout + (long long)g * TC_OP;
+                float mine[TC_OP];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    const long long m = (long long)mt * TC_BM + q * 32 + (r >> 1) * 16 + (lane >> 2) + 8 * (r & 1);
 #pragma unroll
                     for (int o = 0; o < TC_OP; ++o) {
                         float v = pred[r][o];
                         v += __shfl_xor_sync(0xffffffffu, v, 1);
                         v += __shfl_xor_sync(0xffffffffu, v, 2);
-                        if ((lane & 3) == r && o < p.O && m < p.N) {
-                            const float df = ssi_act(v + bo[o], p.act_out) - p.Y[o + m * p.O];
+                        if (r == 0 || (lane & 3) == r) mine[o] = v;
+                    }
+                }
+                const int r = lane & 3;
+                const long long m = (long long)mt * TC_BM + q * 32 + (r >> 1) * 16 + (lane >> 2) + 8 * (r & 1);
+                if (m < p.N) {
+#pragma unroll
+                    for (int o = 0; o < TC_OP; ++o) {
+                        if (o < p.O) {
+                            const float df = tc_act_rt(mine[o] + bo[o], p.act_out) - p.Y[o + m * p.O];
                             sse += (double)df * (double)df;
                         }
                     }
@@ -693,6 +723,23 @@ bool ssi_tc_preferred(const ssi_ctx* ctx) {
     return real >= 64.0 * 64.0 && padded <= 2.0 * real;
 }
 
+typedef void (*tc_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                            const CUtensorMap, const tc_params);
+template <int MODE>
+static tc_kernel_t tc_kernel_for_act(int act) {
+    switch (act) {
+        case SSI_ACT_RELU:    return k_tc_layer<MODE, SSI_ACT_RELU>;
+        case SSI_ACT_TANH:    return k_tc_layer<MODE, SSI_ACT_TANH>;
+        case SSI_ACT_SIGMOID: return k_tc_layer<MODE, SSI_ACT_SIGMOID>;
+        default:              return k_tc_layer<MODE, SSI_ACT_IDENTITY>;
+    }
+}
+static tc_kernel_t tc_kernel(int mode, int act) {
+    if (mode == TC_MODE_FUSED) return tc_kernel_for_act<TC_MODE_FUSED>(act);
+    if (mode == TC_MODE_FINAL) return tc_kernel_for_act<TC_MODE_FINAL>(act);
+    return tc_kernel_for_act<TC_MODE_HIDDEN>(act);
+}
+
 static int tc_make_map(ssi_ctx* ctx, CUtensorMap* map, void* base, uint64_t inner, uint64_t rows, uint64_t batch,
                        uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz) {
     cuuint64_t dims[3] = {inner, rows, batch};
@@ -781,9 +828,9 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
             s->tmSl[l] = s->tmAl[l];
         }
     }
-    SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_layer<TC_MODE_HIDDEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
-    SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_layer<TC_MODE_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
-    SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_layer<TC_MODE_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
+    for (int mode = 0; mode < 3; ++mode)
+        for (int act = 0; act < 4; ++act)
+            SSI_CUDA(ctx, cudaFuncSetAttribute(tc_kernel(mode, act), cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     s->ready = true;
     return SSI_OK;
@@ -841,17 +888,15 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
             p.n_work = p.mt_block > 0 ? (m_tiles + p.mt_block - 1) / p.mt_block * p.mt_block * G : G * m_tiles;
             p.Y = ctx->dY; p.O = m.dims[m.L]; p.partials = s->partials;
             const bool last = (l == s->nl - 1);
+            int mode = TC_MODE_HIDDEN;
             if (last && s->fused_out) {
+                mode = TC_MODE_FUSED;
                 p.act_out = m.act[m.L - 1]; p.Wout = s->Wout; p.bout = s->bout;
-                k_tc_layer<TC_MODE_FUSED><<<grid, TC_THREADS, TC_SMEM_TOTAL, ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l],
-                                                                                          s->tmSh[l], s->tmSl[l], p);
             } else if (last) {
-                k_tc_layer<TC_MODE_FINAL><<<grid, TC_THREADS, TC_SMEM_TOTAL, ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l],
-                                                                                          s->tmSh[l], s->tmSl[l], p);
-            } else {
-                k_tc_layer<TC_MODE_HIDDEN><<<grid, TC_THREADS, TC_SMEM_TOTAL, ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l],
-                                                                                           s->tmSh[l], s->tmSl[l], p);
+                mode = TC_MODE_FINAL;
             }
+            tc_kernel(mode, p.act)<<<grid, TC_THREADS, TC_SMEM_TOTAL, ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l],
+                                                                                   s->tmSh[l], s->tmSl[l], p);
             SSI_LAUNCH_CHECK(ctx);
         }
         SSI_TRY(ssi_reduce_partials(ctx, s->partials, G, parts, d_sse + b0));
