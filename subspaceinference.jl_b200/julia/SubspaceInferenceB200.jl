@@ -1,0 +1,136 @@
+# SubspaceInferenceB200.jl — thin `ccall` shim over libssi.so (include/ssi.h).
+#
+# Keeps the reference's Julia-visible signatures for the accelerated path:
+#   subspace_construction(model, cost, data, opt; T, c, M, print_freq)      src/subspace_construction.jl:26
+#   sub_inference(in_model, data, W_swa, P; σ_z, σ_m, σ_p, itr, M, alg, backend)   src/space_inference.jl:82-84
+#   subspace_inference(model, cost, data, opt; ...)                         src/space_inference.jl:33-35
+#   inference = sub_inference, alg=:mh ≡ :rwmh                              README.md:153-154
+# Everything numeric goes through the C ABI; there is no CUDA.jl code generation and no CPU
+# fallback.  NOT EXECUTED in the build container (no Julia toolchain there): the same ABI is
+# exercised by the Python ctypes mirror in subspaceinference.jl_b200/ and by tests/.
+module SubspaceInferenceB200
+
+using Flux
+using Flux: Data.DataLoader
+
+export subspace_construction, subspace_inference, sub_inference, inference
+
+const libssi = get(ENV, "LIBSSI", joinpath(@__DIR__, "..", "lib", "libssi.so"))
+
+const TERM_LL, TERM_PRIOR_W, TERM_PRIOR_Z = UInt32(1), UInt32(2), UInt32(4)
+
+# ---- plumbing ------------------------------------------------------------------------------
+mutable struct Ctx
+    h::Ptr{Cvoid}
+    function Ctx(device::Integer = 0)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:ssi_ctx_create, libssi), Cint, (Cint, Ref{Ptr{Cvoid}}), device, out)
+        rc == 0 || throw(unsafe_string(ccall((:ssi_last_error, libssi), Cstring, (Ptr{Cvoid},), C_NULL)))
+        c = new(out[])
+        finalizer(x -> ccall((:ssi_ctx_destroy, libssi), Cint, (Ptr{Cvoid},), x.h), c)
+        return c
+    end
+end
+
+# the reference throws Strings (src/space_inference.jl:42,103,162); so does the shim
+check(ctx::Ctx, rc) = rc == 0 ? nothing :
+    throw(unsafe_string(ccall((:ssi_last_error, libssi), Cstring, (Ptr{Cvoid},), ctx.h)))
+
+act_code(f) = f === identity ? 0 : f === relu ? 1 : f === tanh ? 2 : f === σ ? 3 :
+    throw("Error: activation is not supported on the device path")
+
+function describe(model::Chain)
+    all(l -> l isa Dense, model.layers) || throw("Error: density function is not avaliable for this model")
+    dims = Int32[size(model.layers[1].W, 2); [size(l.W, 1) for l in model.layers]...]
+    acts = Int32[act_code(l.σ) for l in model.layers]
+    return dims, acts
+end
+
+# same as the reference's extract_params (src/libs.jl:19-22): Flux.destructure order
+flat_params(model) = Float32.(first(Flux.destructure(model)))
+
+function set_problem!(ctx::Ctx, model::Chain, data, W_swa, P)
+    dims, acts = describe(model)
+    check(ctx, ccall((:ssi_set_model, libssi), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}),
+                     ctx.h, length(acts), dims, acts))
+    X = Matrix{Float32}(data.data[1]); Y = Matrix{Float32}(data.data[2])        # split_data, src/libs.jl:75-77
+    check(ctx, ccall((:ssi_set_data, libssi), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int64),
+                     ctx.h, X, Y, size(X, 2)))
+    Wf = Vector{Float32}(W_swa); Pf = Matrix{Float32}(P)                          # Float64 -> Float32 (documented, SURVEY Q7)
+    check(ctx, ccall((:ssi_set_subspace, libssi), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int64, Int32),
+                     ctx.h, Wf, Pf, length(Wf), size(Pf, 2)))
+end
+
+"""density(z) batched: one log-probability per column of Z (M×B).  Replaces the closure at
+src/space_inference.jl:90-95."""
+function logpost_batch(ctx::Ctx, Z::AbstractMatrix; σ_m = 1.0, σ_p = 1.0, σ_z = 1.0, mask = TERM_LL)
+    Zf = Matrix{Float32}(Z); lp = Vector{Float64}(undef, size(Zf, 2))
+    check(ctx, ccall((:ssi_logpost_batch, libssi), Cint,
+                     (Ptr{Cvoid}, Ptr{Float32}, Int64, Float64, Float64, Float64, UInt32, Ptr{Float64}, Ptr{Float64}),
+                     ctx.h, Zf, size(Zf, 2), σ_m, σ_p, σ_z, mask, lp, C_NULL))
+    return lp
+end
+
+# ---- public API ---------------------------------------------------------------------------------
+function subspace_construction(model, cost, data, opt; T = 10, c = 1, M = 3, print_freq = 1,
+                               ctx::Ctx = Ctx())
+    training_loss = 0.0
+    ps = Flux.params(model)
+    n = length(flat_params(model))
+    check(ctx, ccall((:ssi_swa_begin, libssi), Cint, (Ptr{Cvoid}, Int64, Int64), ctx.h, n, div(T, c) * length(data)))
+    for i in 1:T
+        for d in data
+            gs = gradient(ps) do                                  # the SGD step stays in Flux/Zygote (:39-43)
+                training_loss = cost(model, d...)
+                return training_loss
+            end
+            Flux.update!(opt, ps, gs)
+            if mod(i, c) == 0
+                W = flat_params(model)
+                check(ctx, ccall((:ssi_swa_push, libssi), Cint, (Ptr{Cvoid}, Ptr{Float32}, Float64), ctx.h, W, i / c))  # n = i/c (:46)
+            end
+        end
+        if (mod(i, print_freq) == 0) || (i == T)
+            println("Traing loss: ", training_loss, " Epoch: ", i)
+        end
+    end
+    W_swa = Vector{Float32}(undef, n); P = Matrix{Float32}(undef, n, M)
+    check(ctx, ccall((:ssi_swa_finish, libssi), Cint, (Ptr{Cvoid}, Int32, Ptr{Float32}, Ptr{Float32}, Ptr{Float64}, Int32),
+                     ctx.h, M, W_swa, P, C_NULL, 0))
+    return W_swa, P
+end
+
+function sub_inference(in_model, data, W_swa, P; σ_z = 1.0, σ_m = 1.0, σ_p = 1.0, itr = 100, M = 3,
+                       alg = :rwmh, backend = :forwarddiff,
+                       n_chains = 1, seed = rand(UInt64), prior_mask = TERM_LL, ctx::Ctx = Ctx())
+    (alg == :rwmh || alg == :mh) || throw("$alg is not available")            # :162; other samplers stay in the reference
+    size(P, 2) == M || throw(DimensionMismatch("P has $(size(P, 2)) columns but M = $M"))
+    set_problem!(ctx, in_model, data, W_swa, P)
+    zt = Array{Float32}(undef, M, n_chains, itr); lp = Matrix{Float64}(undef, n_chains, itr)
+    check(ctx, ccall((:ssi_mh_run, libssi), Cint,
+                     (Ptr{Cvoid}, Int64, Int64, UInt64, Int64, Float64, Float64, Float64, UInt32,
+                      Ptr{Float32}, Ptr{Float32}, Ptr{Float64}, Ptr{UInt8}),
+                     ctx.h, n_chains, itr, seed, 0, σ_z, σ_m, σ_p, prior_mask, C_NULL, zt, lp, C_NULL))
+    if n_chains == 1
+        # map(z -> W_swa + P*z.params, chm), map(z -> z.lp, chm)   (:125)
+        Wout = Matrix{Float32}(undef, length(W_swa), itr)
+        Z = Matrix{Float32}(zt[:, 1, :])
+        check(ctx, ccall((:ssi_project, libssi), Cint, (Ptr{Cvoid}, Ptr{Float32}, Int64, Ptr{Float32}), ctx.h, Z, itr, Wout))
+        return [Wout[:, t] for t in 1:itr], vec(lp[1, :])
+    end
+    return zt, lp
+end
+
+const inference = sub_inference
+
+function subspace_inference(model, cost, data, opt; σ_z = 1.0, σ_m = 1.0, σ_p = 1.0, itr = 1000, T = 25, c = 1,
+                            M = 20, print_freq = 1, alg = :rwmh, backend = :forwarddiff, method = :subspace, kw...)
+    method == :subspace || throw("Error: No method found")                        # :42 (diffusion_subspace is outside the device path)
+    ctx = Ctx()
+    W_swa, P = subspace_construction(model, cost, data, opt; T = T, c = c, M = M, print_freq = print_freq, ctx = ctx)
+    chn, lp = sub_inference(model, data, W_swa, P; σ_z = σ_z, σ_m = σ_m, σ_p = σ_p, itr = itr, M = M, alg = alg,
+                            backend = backend, ctx = ctx, kw...)
+    return chn, lp, W_swa
+end
+
+end # module
