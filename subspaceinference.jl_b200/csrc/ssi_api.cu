@@ -162,6 +162,7 @@ int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
         return SSI_OK;
     }
     if (!strcmp(key, "tc_nofuse")) { ctx->opt_tc_nofuse = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }
+    if (!strcmp(key, "tc_nobasis")) { ctx->opt_tc_nobasis = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "tc_noorder")) { ctx->opt_tc_noorder = value != 0; return SSI_OK; }
     return ssi_fail(ctx, SSI_ERR_ARG, "unknown option '%s'", key);
 }

@@ -47,7 +47,8 @@ struct ssi_ctx {
     int opt_path = SSI_PATH_AUTO;
     int opt_group = 0;
     int opt_tc_nofuse = 0;    // debugging / A-B: compute the output layer as its own GEMM
-    int opt_tc_noorder = 0;   // debugging / A-B: sample-major work order on the first layer
+    int opt_tc_noorder = 0;
+    int opt_tc_nobasis = 0;   // debugging / A-B: run the first layer as a GEMM instead of the affine-in-z basis combination   // debugging / A-B: sample-major work order on the first layer
 
     // model / data / subspace
     ssi_model_t model;
@@ -111,6 +112,7 @@ int ssi_use_device(ssi_ctx* ctx);
 int ssi_logpost_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m, double sigma_p,
                        double sigma_z, uint32_t mask, double* d_lp, double* d_terms);
 int ssi_project_device(ssi_ctx* ctx, const float* dZ, int64_t B, float* dW /* n x B */);
+int ssi_build_first_layer_bases(ssi_ctx* ctx, float* bases, int ld);
 int ssi_subspace_gram(ssi_ctx* ctx);   // fills dSubGram after set_subspace
 // Gram of an n x K column-major FP32 matrix (ld = n) into a K x K double matrix on device
 int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int K, double* dG);

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256)
 k_dense_simt(const float* __restrict__ A, long long a_bs, const float* __restrict__ bias, long long bias_bs,
              const float* __restrict__ Hin, long long hin_bs, float* __restrict__ Hout, long long hout_bs,
              const float* __restrict__ Y, double* __restrict__ partials,
-             int out, int in, long long N, int act) {
+             int out, int in, long long N, int act, int ld_out) {
     __shared__ __align__(16) float As[LK][LT];
     __shared__ __align__(16) float Bs[LK][LT + 4];
     __shared__ double red[32];
@@ -377,7 +377,7 @@ k_dense_simt(const float* __restrict__ A, long long a_bs, const float* __restric
                     const float df = v - Y[o + j * out];
                     sse += (double)df * (double)df;
                 } else {
-                    Hout[(long long)g * hout_bs + o + j * out] = v;
+                    Hout[(long long)g * hout_bs + o + j * ld_out] = v;
                 }
             }
         }
@@ -425,12 +425,12 @@ static int run_layered(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) 
             if (last) {
                 k_dense_simt<true><<<grid, 256, 0, ctx->stream>>>(dW + m.w_off[l], n, dW + m.b_off[l], n, hin, hin_bs,
                                                                  nullptr, 0, ctx->dY, partials + b0 * parts,
-                                                                 out, in, N, m.act[l]);
+                                                                 out, in, N, m.act[l], out);
             } else {
                 float* hout = hbuf[l & 1];
                 k_dense_simt<false><<<grid, 256, 0, ctx->stream>>>(dW + m.w_off[l], n, dW + m.b_off[l], n, hin, hin_bs,
                                                                   hout, (long long)out * N, nullptr, nullptr,
-                                                                  out, in, N, m.act[l]);
+                                                                  out, in, N, m.act[l], out);
                 hin = hout;
                 hin_bs = (long long)out * N;
             }
@@ -438,6 +438,20 @@ static int run_layered(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) 
         }
     }
     return ssi_reduce_partials(ctx, partials, B, parts, d_sse);
+}
+
+// First-layer bases for the tensor path: B_m = (column m of [P | W_swa])_layer0 applied to X, m = 0..M,
+// as FP32 pre-activations [m][N][ld] (bias parts included).  Exact FP32 SIMT GEMM, run once per (data, subspace).
+int ssi_build_first_layer_bases(ssi_ctx* ctx, float* bases, int ld) {
+    const ssi_model_t& m = ctx->model;
+    const int in = m.dims[0], out = m.dims[1];
+    const int64_t N = ctx->N;
+    dim3 grid((unsigned)((N + LT - 1) / LT), (out + LT - 1) / LT, ctx->M + 1);
+    k_dense_simt<false><<<grid, 256, 0, ctx->stream>>>(ctx->dP + m.w_off[0], m.n, ctx->dP + m.b_off[0], m.n, ctx->dX, 0,
+                                                      bases, (long long)N * ld, nullptr, nullptr, out, in, N,
+                                                      SSI_ACT_IDENTITY, ld);
+    SSI_LAUNCH_CHECK(ctx);
+    return SSI_OK;
 }
 
 // ======================================================================================

@@ -655,6 +655,54 @@ k_tc_project_v(const float* __restrict__ Wswa, const float* __restrict__ P, cons
         if (g < G) dst[(long long)g * dst_gs + d] = acc[g];
 }
 
+// First Dense layer without a GEMM.  The pre-activation is affine in z:
+//   (W1_swa + sum_m z_m P1_m) x + (b1_swa + sum_m z_m pb_m) = B_M(x) + sum_m z_m B_m(x),
+// with the M+1 basis pre-activations B_m = [P | W_swa]_m applied to the dataset computed once per
+// (data, subspace) in exact FP32.  Per sample this is M FMAs per activation instead of in0, and an
+// HBM stream instead of tensor-core work.  z of the group lives in constant memory so the FMAs take
+// it as a constant operand.
+__constant__ float c_zgroup[TC_GMAX * SSI_MAX_M];
+
+template <int ACT>
+__global__ void __launch_bounds__(256)
+k_tc_basis_layer(const float* __restrict__ bases /* [M+1][NW] */, long long NW, int M, int G,
+                 bf16* __restrict__ Hh, bf16* __restrict__ Hl /* [g][NW] */) {
+    const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (e >= NW) return;
+    const float2 b0 = __ldcs(reinterpret_cast<const float2*>(bases + (long long)M * NW + e));
+    float ax[TC_GMAX], ay[TC_GMAX];
+#pragma unroll
+    for (int g = 0; g < TC_GMAX; ++g) { ax[g] = b0.x; ay[g] = b0.y; }
+    for (int m = 0; m < M; ++m) {
+        const float2 b = __ldcs(reinterpret_cast<const float2*>(bases + (long long)m * NW + e));
+#pragma unroll
+        for (int g = 0; g < TC_GMAX; ++g) {
+            const float z = c_zgroup[g * SSI_MAX_M + m];
+            ax[g] = fmaf(z, b.x, ax[g]);
+            ay[g] = fmaf(z, b.y, ay[g]);
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < TC_GMAX; ++g) {
+        if (g < G) {
+            const float x0 = tc_act<ACT>(ax[g]), x1 = tc_act<ACT>(ay[g]);
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+            const float2 hf = __bfloat1622float2(h2);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+            __stcs(reinterpret_cast<unsigned int*>(Hh + (long long)g * NW + e), *reinterpret_cast<const unsigned int*>(&h2));
+            __stcs(reinterpret_cast<unsigned int*>(Hl + (long long)g * NW + e), *reinterpret_cast<const unsigned int*>(&l2));
+        }
+    }
+}
+
+// c_zgroup[g][m] <- Z[m + g*M]  (device to constant memory, stream ordered)
+__global__ void k_tc_pack_z(const float* __restrict__ Z, int M, int G, float* __restrict__ out /* [TC_GMAX][SSI_MAX_M] */) {
+    const int t = threadIdx.x + blockIdx.x * blockDim.x;
+    if (t >= TC_GMAX * SSI_MAX_M) return;
+    const int g = t / SSI_MAX_M, m = t % SSI_MAX_M;
+    out[t] = (g < G && m < M) ? Z[m + g * M] : 0.0f;
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -665,7 +713,11 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 struct ssi_tc_state {
     bool ready = false;
     int nl = 0;                          // GEMM launches per group: L, or L-1 when the output layer is fused
-    bool fused_out = false;              // output layer folded into the last hidden layer's epilogue (O <= TC_OP, L >= 2)
+    bool fused_out = false;              // output layer folded into the last hidden layer's epilogue (O <= TC_OP)
+    bool basis = false;                  // first layer = affine-in-z combination of precomputed bases (k_tc_basis_layer)
+    int l0 = 0;                          // first Dense layer that runs as a GEMM (1 when basis)
+    float* bases = nullptr;              // [M+1][N][width0] FP32
+    float* zpack = nullptr;              // staging for c_zgroup
     float *Wout = nullptr, *bout = nullptr;
     int Kp[SSI_MAX_LAYERS] = {0};        // padded input width of layer l
     int width[SSI_MAX_LAYERS] = {0};     // padded output width of layer l
@@ -682,7 +734,7 @@ struct ssi_tc_state {
 };
 
 static void tc_free(ssi_tc_state* s) {
-    cudaFree(s->Xh); cudaFree(s->Xl); cudaFree(s->partials); cudaFree(s->Wout); cudaFree(s->bout);
+    cudaFree(s->Xh); cudaFree(s->Xl); cudaFree(s->partials); cudaFree(s->Wout); cudaFree(s->bout); cudaFree(s->bases); cudaFree(s->zpack);
     for (int i = 0; i < 2; ++i) { cudaFree(s->Hh[i]); cudaFree(s->Hl[i]); }
     for (int l = 0; l < SSI_MAX_LAYERS; ++l) { cudaFree(s->Wh[l]); cudaFree(s->Wl[l]); cudaFree(s->bias[l]); }
     PFN_encodeTiled enc = s->encode;
@@ -769,7 +821,12 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
     tc_free(s);
     const ssi_model_t& m = ctx->model;
     const int64_t N = ctx->N;
-    s->fused_out = (m.L >= 2 && m.dims[m.L] <= TC_OP && !ctx->opt_tc_nofuse);
+    // first layer as a basis combination when a GEMM layer follows it and the bases fit comfortably in HBM
+    const int w0pad = (m.dims[1] + 63) / 64 * 64;
+    const double bases_bytes = (double)(ctx->M + 1) * (double)N * w0pad * sizeof(float);
+    s->basis = (m.L >= 2 && !ctx->opt_tc_nobasis && bases_bytes <= 16e9);
+    s->l0 = s->basis ? 1 : 0;
+    s->fused_out = (m.L - s->l0 >= 2 && m.dims[m.L] <= TC_OP && !ctx->opt_tc_nofuse);
     s->nl = s->fused_out ? m.L - 1 : m.L;
     s->G = ctx->opt_group > 0 ? std::min(ctx->opt_group, TC_GMAX) : TC_GMAX;
     const int G = s->G;
@@ -781,6 +838,7 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
         if (last) s->BN[l] = s->width[l];            // <= 256, a multiple of 16
         else s->BN[l] = s->width[l] % 256 == 0 ? 256 : (s->width[l] % 128 == 0 ? 128 : 64);
         if (l < s->nl - 1) maxw = std::max(maxw, s->width[l]);
+        if (l < s->l0) continue;                 // the basis layer has no GEMM operands
         const size_t wn = (size_t)G * s->width[l] * s->Kp[l];
         SSI_CUDA(ctx, cudaMalloc(&s->Wh[l], sizeof(bf16) * wn));
         SSI_CUDA(ctx, cudaMalloc(&s->Wl[l], sizeof(bf16) * wn));
@@ -793,8 +851,15 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
         SSI_CUDA(ctx, cudaMemsetAsync(s->Wout, 0, sizeof(float) * (size_t)G * wl * TC_OP, ctx->stream));
         SSI_CUDA(ctx, cudaMemsetAsync(s->bout, 0, sizeof(float) * (size_t)G * TC_OP, ctx->stream));
     }
-    SSI_CUDA(ctx, cudaMalloc(&s->Xh, sizeof(bf16) * (size_t)N * s->Kp[0]));
-    SSI_CUDA(ctx, cudaMalloc(&s->Xl, sizeof(bf16) * (size_t)N * s->Kp[0]));
+    if (s->basis) {
+        SSI_CUDA(ctx, cudaMalloc(&s->bases, (size_t)bases_bytes));
+        SSI_CUDA(ctx, cudaMalloc(&s->zpack, sizeof(float) * TC_GMAX * SSI_MAX_M));
+        if (w0pad != m.dims[1]) SSI_CUDA(ctx, cudaMemsetAsync(s->bases, 0, (size_t)bases_bytes, ctx->stream));
+        SSI_TRY(ssi_build_first_layer_bases(ctx, s->bases, w0pad));
+    } else {
+        SSI_CUDA(ctx, cudaMalloc(&s->Xh, sizeof(bf16) * (size_t)N * s->Kp[0]));
+        SSI_CUDA(ctx, cudaMalloc(&s->Xl, sizeof(bf16) * (size_t)N * s->Kp[0]));
+    }
     const int nbuf = s->nl >= 3 ? 2 : (s->nl == 2 ? 1 : 0);   // layers 0..nl-2 store activations
     for (int i = 0; i < nbuf; ++i) {
         SSI_CUDA(ctx, cudaMalloc(&s->Hh[i], sizeof(bf16) * (size_t)G * N * maxw));
@@ -802,12 +867,12 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
     }
     const int m_tiles = (int)((N + TC_BM - 1) / TC_BM);
     SSI_CUDA(ctx, cudaMalloc(&s->partials, sizeof(double) * (size_t)G * m_tiles * 4));
-    {
+    if (!s->basis) {
         const long long tot = (long long)N * s->Kp[0];
         k_tc_split_x<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->dX, N, m.dims[0], s->Kp[0], s->Xh, s->Xl);
         SSI_LAUNCH_CHECK(ctx);
     }
-    for (int l = 0; l < s->nl; ++l) {
+    for (int l = s->l0; l < s->nl; ++l) {
         const CUtensorMapSwizzle S128 = CU_TENSOR_MAP_SWIZZLE_128B, S64 = CU_TENSOR_MAP_SWIZZLE_64B;
         if (l == 0) {
             SSI_TRY(tc_make_map(ctx, &s->tmAh[l], s->Xh, s->Kp[0], N, 1, TC_BK, TC_BM, S128));
@@ -851,7 +916,7 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
         const int G = (int)std::min<int64_t>(s->G, B - b0);
         const float* Zg = dZ + b0 * M;
         // ---- K1: project the group's weights straight into the GEMM operand layouts ----
-        for (int l = 0; l < s->nl; ++l) {
+        for (int l = s->l0; l < s->nl; ++l) {
             dim3 grid((s->Kp[l] + 31) / 32, (s->width[l] + 31) / 32);
             k_tc_project_w<<<grid, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.w_off[l], m.dims[l], m.dims[l + 1],
                                                          s->width[l], s->Kp[l], s->Wh[l], s->Wl[l]);
@@ -870,7 +935,22 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
             SSI_LAUNCH_CHECK(ctx);
         }
         // ---- the Dense chain ----
-        for (int l = 0; l < s->nl; ++l) {
+        if (s->basis) {
+            k_tc_pack_z<<<(TC_GMAX * SSI_MAX_M + 255) / 256, 256, 0, ctx->stream>>>(Zg, M, G, s->zpack);
+            SSI_LAUNCH_CHECK(ctx);
+            SSI_CUDA(ctx, cudaMemcpyToSymbolAsync(c_zgroup, s->zpack, sizeof(float) * TC_GMAX * SSI_MAX_M, 0,
+                                                  cudaMemcpyDeviceToDevice, ctx->stream));
+            const long long NW = (long long)N * s->width[0];
+            const unsigned blocks = (unsigned)((NW / 2 + 255) / 256);
+            switch (m.act[0]) {
+                case SSI_ACT_RELU:    k_tc_basis_layer<SSI_ACT_RELU><<<blocks, 256, 0, ctx->stream>>>(s->bases, NW, M, G, s->Hh[0], s->Hl[0]); break;
+                case SSI_ACT_TANH:    k_tc_basis_layer<SSI_ACT_TANH><<<blocks, 256, 0, ctx->stream>>>(s->bases, NW, M, G, s->Hh[0], s->Hl[0]); break;
+                case SSI_ACT_SIGMOID: k_tc_basis_layer<SSI_ACT_SIGMOID><<<blocks, 256, 0, ctx->stream>>>(s->bases, NW, M, G, s->Hh[0], s->Hl[0]); break;
+                default:              k_tc_basis_layer<SSI_ACT_IDENTITY><<<blocks, 256, 0, ctx->stream>>>(s->bases, NW, M, G, s->Hh[0], s->Hl[0]); break;
+            }
+            SSI_LAUNCH_CHECK(ctx);
+        }
+        for (int l = s->l0; l < s->nl; ++l) {
             tc_params p{};
             p.N = (int)N; p.G = G; p.m_tiles = m_tiles;
             p.BN = s->BN[l]; p.width = s->width[l];

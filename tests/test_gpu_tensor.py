@@ -98,3 +98,28 @@ def test_narrow_chain_runs_padded_on_tensor_path(ssi, engine):
         engine.set_option("path", ssi.PATH_AUTO)
         engine.logpost(Z, 0.5)
         assert engine.stats().last_path == ssi.PATH_FUSED      # AUTO keeps small nets off the tensor path
+
+
+@pytest.mark.parametrize("dims,acts,N,M,B", [
+    ((96, 128, 128, 10), (1, 1, 0), 300, 20, 8),
+    ((784, 256, 512, 10), (1, 1, 0), 1000, 20, 19),
+    ((20, 1024, 1), (2, 0), 700, 3, 5),
+])
+def test_first_layer_gemm_vs_basis_and_unfused_output(ssi, engine, dims, acts, N, M, B):
+    """The first layer either runs as a GEMM (dataset tiles shared across the group's samples) or as the
+    affine-in-z combination of precomputed bases; the output layer is either fused into the last hidden
+    layer's epilogue or its own GEMM.  All four combinations must agree with the oracle."""
+    prob, rng = _rand_problem(dims, acts, N, M, 1234)
+    prob = orc.Problem(prob.dims, prob.acts, prob.X, prob.Y, prob.W_swa, (0.2 * prob.P).astype(np.float32))
+    Z = rng.standard_normal((M, B)).astype(np.float32)
+    _setup(engine, prob)
+    engine.set_option("path", ssi.PATH_TENSOR)
+    ref, _ = orc.logpost_batch(prob, Z, 0.8)
+    for nobasis in (0, 1):
+        for nofuse in (0, 1):
+            engine.set_option("tc_nobasis", nobasis)
+            engine.set_option("tc_nofuse", nofuse)
+            lp = engine.logpost(Z, 0.8)
+            np.testing.assert_allclose(lp, ref, rtol=RTOL, err_msg=f"nobasis={nobasis} nofuse={nofuse}")
+    engine.set_option("tc_noorder", 1)
+    np.testing.assert_allclose(engine.logpost(Z, 0.8), ref, rtol=RTOL)
