@@ -98,6 +98,11 @@ def cpu_reference(workload: str, budget_s: float, steps: int = 1, warmup: int = 
     per-layer BLAS GEMM over the full dataset, all host cores.  Bounded sample."""
     sys.path.insert(0, str(ROOT / "oracle"))
     import ssi_oracle as orc
+    try:        # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     name, _, sigma_m, zs = WORKLOADS[workload]
     prob = orc.make_problem(name)
     rng = np.random.default_rng(0)

@@ -16,30 +16,39 @@
 // ======================================================================================
 // K5: SWA mean + deviation column, one float4 stream (16 n bytes per snapshot)
 // ======================================================================================
+// mean' = mean + (w - mean)/(ns+1)  ( == (ns*mean + w)/(ns+1) ),  dev = w - mean' = (w - mean) * ns/(ns+1):
+// FP32 throughout, no cancellation beyond (w - mean) itself.  Two float4 per thread in flight.
 __global__ void __launch_bounds__(256)
 k_swa_push(const float* __restrict__ W, float* __restrict__ mean, float* __restrict__ dev,
-           long long n, double ns, double inv, int vec) {
+           long long n, float inv, float c, int vec) {
     const long long n4 = vec ? (n >> 2) : 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const float4* W4 = reinterpret_cast<const float4*>(W);
     float4* m4 = reinterpret_cast<float4*>(mean);
     float4* d4 = reinterpret_cast<float4*>(dev);
-    for (long long i = t0; i < n4; i += stride) {
-        const float4 w = __ldcs(W4 + i);
-        const float4 m = m4[i];
-        const double a0 = (ns * (double)m.x + (double)w.x) * inv;
-        const double a1 = (ns * (double)m.y + (double)w.y) * inv;
-        const double a2 = (ns * (double)m.z + (double)w.z) * inv;
-        const double a3 = (ns * (double)m.w + (double)w.w) * inv;
-        m4[i] = make_float4((float)a0, (float)a1, (float)a2, (float)a3);
-        __stcs(d4 + i, make_float4((float)((double)w.x - a0), (float)((double)w.y - a1),
-                                   (float)((double)w.z - a2), (float)((double)w.w - a3)));
+    long long i = t0;
+    for (; i + stride < n4; i += 2 * stride) {
+        const float4 w0 = __ldcs(W4 + i), w1 = __ldcs(W4 + i + stride);
+        const float4 a0 = m4[i], a1 = m4[i + stride];
+        const float4 e0 = make_float4(w0.x - a0.x, w0.y - a0.y, w0.z - a0.z, w0.w - a0.w);
+        const float4 e1 = make_float4(w1.x - a1.x, w1.y - a1.y, w1.z - a1.z, w1.w - a1.w);
+        m4[i] = make_float4(fmaf(e0.x, inv, a0.x), fmaf(e0.y, inv, a0.y), fmaf(e0.z, inv, a0.z), fmaf(e0.w, inv, a0.w));
+        m4[i + stride] = make_float4(fmaf(e1.x, inv, a1.x), fmaf(e1.y, inv, a1.y), fmaf(e1.z, inv, a1.z), fmaf(e1.w, inv, a1.w));
+        __stcs(d4 + i, make_float4(e0.x * c, e0.y * c, e0.z * c, e0.w * c));
+        __stcs(d4 + i + stride, make_float4(e1.x * c, e1.y * c, e1.z * c, e1.w * c));
     }
-    for (long long i = (n4 << 2) + t0; i < n; i += stride) {   // tail (n % 4)
-        const double a = (ns * (double)mean[i] + (double)W[i]) * inv;
-        mean[i] = (float)a;
-        dev[i] = (float)((double)W[i] - a);
+    for (; i < n4; i += stride) {
+        const float4 w0 = __ldcs(W4 + i);
+        const float4 a0 = m4[i];
+        const float4 e0 = make_float4(w0.x - a0.x, w0.y - a0.y, w0.z - a0.z, w0.w - a0.w);
+        m4[i] = make_float4(fmaf(e0.x, inv, a0.x), fmaf(e0.y, inv, a0.y), fmaf(e0.z, inv, a0.z), fmaf(e0.w, inv, a0.w));
+        __stcs(d4 + i, make_float4(e0.x * c, e0.y * c, e0.z * c, e0.w * c));
+    }
+    for (long long j = (n4 << 2) + t0; j < n; j += stride) {   // tail (n % 4), or everything when !vec
+        const float e = W[j] - mean[j];
+        mean[j] = fmaf(e, inv, mean[j]);
+        dev[j] = e * c;
     }
 }
 
@@ -53,7 +62,8 @@ int ssi_swa_push_device(ssi_ctx* ctx, const float* dW, double n_scalar) {
     const bool aligned = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(dW) & 15) == 0);
     const int blocks = ctx->sm_count * 8;
     // vec = 0: everything goes through the scalar tail loop
-    k_swa_push<<<blocks, 256, 0, ctx->stream>>>(dW, ctx->dSwaMean, col, n, n_scalar, 1.0 / (n_scalar + 1.0), aligned ? 1 : 0);
+    k_swa_push<<<blocks, 256, 0, ctx->stream>>>(dW, ctx->dSwaMean, col, n, (float)(1.0 / (n_scalar + 1.0)),
+                                                (float)(n_scalar / (n_scalar + 1.0)), aligned ? 1 : 0);
     SSI_LAUNCH_CHECK(ctx);
     ctx->swa_K++;
     ctx->stats.last_bytes = 16.0 * (double)n;
@@ -168,9 +178,14 @@ int ssi_subspace_gram(ssi_ctx* ctx) {
 // ======================================================================================
 #define JAC_MAXPAIRS 1024
 __global__ void __launch_bounds__(1024)
-k_jacobi(double* __restrict__ A /* K x K, destroyed */, double* __restrict__ V /* K x K out */, int K,
+k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg /* K x K out */, int K,
          int max_sweeps, double* __restrict__ lambda /* K, sorted desc */, int* __restrict__ order /* K */,
-         int* __restrict__ sweeps_out) {
+         int* __restrict__ sweeps_out, int use_smem) {
+    extern __shared__ double jac_smem[];
+    // both K x K matrices live in shared memory when they fit (K <= 104); the round-robin sweeps are
+    // latency bound, not bandwidth bound
+    double* A = use_smem ? jac_smem : Ag;
+    double* V = use_smem ? jac_smem + (size_t)K * K : Vg;
     __shared__ double cs[JAC_MAXPAIRS], sn[JAC_MAXPAIRS];
     __shared__ short pp[JAC_MAXPAIRS], qq[JAC_MAXPAIRS];
     __shared__ double red[32];
@@ -180,7 +195,10 @@ k_jacobi(double* __restrict__ A /* K x K, destroyed */, double* __restrict__ V /
     const int np = m / 2;
     const double tol = 4.0 * ((double)K * 2.220446049250313e-16) * ((double)K * 2.220446049250313e-16);
 
-    for (long long e = tid; e < (long long)K * K; e += nt) V[e] = ((e % K) == (e / K)) ? 1.0 : 0.0;
+    for (long long e = tid; e < (long long)K * K; e += nt) {
+        V[e] = ((e % K) == (e / K)) ? 1.0 : 0.0;
+        if (use_smem) A[e] = Ag[e];
+    }
     __syncthreads();
 
     int sweep = 0;
@@ -275,11 +293,43 @@ k_jacobi(double* __restrict__ A /* K x K, destroyed */, double* __restrict__ V /
         order[rank] = i;
     }
     if (tid == 0) *sweeps_out = sweep;
+    if (use_smem)
+        for (long long e = tid; e < (long long)K * K; e += nt) Vg[e] = V[e];
 }
 
 // ======================================================================================
 // K8: P = A V_M  (second pass over A; V_M staged in shared memory, zero-padded to MP columns)
 // ======================================================================================
+#define FORMP_CONST_MAX 16384
+__constant__ float c_formp_v[FORMP_CONST_MAX];     // V_M as [K][MP] floats, zero padded
+
+__global__ void k_pack_v(const double* __restrict__ V, const int* __restrict__ order, int K, int M, int MP, float* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= K * MP) return;
+    const int k = e / MP, j = e % MP;
+    out[e] = j < M ? (float)V[k + (long long)order[j] * K] : 0.0f;
+}
+
+// P = A V_M with V_M in the constant bank: the FMAs take V as a uniform operand, no shared-memory traffic
+template <int MP>
+__global__ void __launch_bounds__(256)
+k_form_p_const(const float* __restrict__ A, long long n, int K, int M, float* __restrict__ P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc[MP];
+#pragma unroll
+    for (int j = 0; j < MP; ++j) acc[j] = 0.0f;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const float d = __ldcs(A + i + (long long)k * n);
+#pragma unroll
+        for (int j = 0; j < MP; ++j) acc[j] = fmaf(d, c_formp_v[k * MP + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < MP; ++j)
+        if (j < M) __stcs(P + i + (long long)j * n, acc[j]);
+}
+
 template <int MP>
 __global__ void __launch_bounds__(256)
 k_form_p(const float* __restrict__ A, long long n, int K, const double* __restrict__ V, const int* __restrict__ order,
@@ -321,6 +371,16 @@ k_form_p(const float* __restrict__ A, long long n, int K, const double* __restri
 
 template <int MP>
 static int launch_form_p(ssi_ctx* ctx, const float* dA, int64_t n, int K, const double* dV, const int* dOrder, int M, float* dP) {
+    if ((size_t)K * MP <= FORMP_CONST_MAX) {
+        SSI_TRY(ssi_reserve(ctx, ctx->bSnap, sizeof(float) * FORMP_CONST_MAX));
+        float* stage = (float*)ctx->bSnap.p;
+        k_pack_v<<<(K * MP + 255) / 256, 256, 0, ctx->stream>>>(dV, dOrder, K, M, MP, stage);
+        SSI_LAUNCH_CHECK(ctx);
+        SSI_CUDA(ctx, cudaMemcpyToSymbolAsync(c_formp_v, stage, sizeof(float) * (size_t)K * MP, 0, cudaMemcpyDeviceToDevice, ctx->stream));
+        k_form_p_const<MP><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dA, n, K, M, dP);
+        SSI_LAUNCH_CHECK(ctx);
+        return SSI_OK;
+    }
     const size_t smem = sizeof(float) * (size_t)K * MP;
     const int in_smem = smem <= 160 * 1024;
     if (in_smem && smem > 48 * 1024)
@@ -352,7 +412,12 @@ int ssi_swa_factor_device(ssi_ctx* ctx, int M, float* dP_out, double* d_s, int* 
     int* dOrder = (int*)(dLam + K);
     int* dSweeps = dOrder + K;
     SSI_TRY(ssi_gram_device(ctx, ctx->dDev, n, K, dG));
-    k_jacobi<<<1, 1024, 0, ctx->stream>>>(dG, dV, K, 60, dLam, dOrder, dSweeps);
+    {
+        const size_t jsm = 2 * sizeof(double) * KK;
+        const int use_smem = jsm + 24 * 1024 <= ctx->smem_optin;
+        if (use_smem) SSI_CUDA(ctx, cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm));
+        k_jacobi<<<1, 1024, use_smem ? jsm : 0, ctx->stream>>>(dG, dV, K, 60, dLam, dOrder, dSweeps, use_smem);
+    }
     SSI_LAUNCH_CHECK(ctx);
     k_singular_values<<<(K + 127) / 128, 128, 0, ctx->stream>>>(dLam, K, d_s);
     SSI_LAUNCH_CHECK(ctx);
