@@ -65,6 +65,7 @@ extern "C" {
 #define SSI_PATH_FUSED    1        /* one CTA keeps a sample's whole network in shared memory */
 #define SSI_PATH_LAYERED  2        /* per-layer FP32 SIMT GEMMs (any shape)                  */
 #define SSI_PATH_TENSOR   3        /* tcgen05/TMEM/TMA split-precision GEMMs (wide layers)   */
+#define SSI_PATH_BASIS    4        /* one hidden layer, O <= 2: first layer affine in z       */
 
 typedef struct ssi_ctx ssi_ctx;
 
@@ -78,6 +79,10 @@ typedef struct ssi_stats_t {
     int64_t mh_proposals;      /* proposals in the last ssi_mh_run                                     */
     int32_t last_path;         /* SSI_PATH_* actually used by the last log-posterior evaluation        */
     int32_t sm_count;
+    int32_t gram_path;         /* last ssi_swa_finish: 1 FP64 SIMT Gram, 2 tensor-core Gram, 3 tensor-core Gram
+                                * rejected by the conditioning check and recomputed in FP64               */
+    int32_t jacobi_sweeps;     /* sweeps of the last eigen-solve                                         */
+    double gram_risk;          /* conditioning estimate of the tensor-core Gram       */
 } ssi_stats_t;
 
 int  ssi_version(void);
@@ -90,7 +95,8 @@ const char* ssi_last_error(const ssi_ctx* ctx);
 /* run on a caller-provided cudaStream_t (e.g. torch's current stream); NULL restores the ctx stream */
 int  ssi_set_stream(ssi_ctx* ctx, void* cuda_stream);
 int  ssi_sync(ssi_ctx* ctx);
-/* keys: "path" (SSI_PATH_*), "group" (samples evaluated per wave on the layered/tensor paths) */
+/* keys: "path" (SSI_PATH_*), "group" (samples per wave on the tensor path), and A/B switches used by the
+ * tests: "tc_nobasis", "tc_nofuse", "tc_noorder", "gram_fp64", "gram_chunk"  */
 int  ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value);
 int  ssi_stats(const ssi_ctx* ctx, ssi_stats_t* out);
 

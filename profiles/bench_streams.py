@@ -55,6 +55,8 @@ def main():
     out["finish_bytes_gb"] = (2 * 4.0 * a.n * a.K + 4.0 * a.n * a.M) / 1e9
     out["finish_gbs"] = out["finish_bytes_gb"] / (best_fin * 1e-3)
     out["finish_frac"] = out["finish_gbs"] / peaks["hbm_gbs"]
+    st = eng.stats()
+    out["gram_path"], out["gram_risk"], out["jacobi_sweeps"] = st.gram_path, st.gram_risk, st.jacobi_sweeps
     print(json.dumps(out))
     eng.close()
 

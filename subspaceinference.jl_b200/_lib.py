@@ -13,8 +13,8 @@ ERR_NAMES = {-1: "SSI_ERR_ARG", -2: "SSI_ERR_CUDA", -3: "SSI_ERR_STATE", -4: "SS
 
 ACT_IDENTITY, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
 TERM_LL, TERM_PRIOR_W, TERM_PRIOR_Z = 1, 2, 4
-PATH_AUTO, PATH_FUSED, PATH_LAYERED, PATH_TENSOR = 0, 1, 2, 3
-PATH_NAMES = {0: "auto", 1: "fused", 2: "layered", 3: "tensor"}
+PATH_AUTO, PATH_FUSED, PATH_LAYERED, PATH_TENSOR, PATH_BASIS = 0, 1, 2, 3, 4
+PATH_NAMES = {0: "auto", 1: "fused", 2: "layered", 3: "tensor", 4: "basis"}
 
 
 class SsiError(RuntimeError):
@@ -31,6 +31,7 @@ class Stats(C.Structure):
         ("last_ms", C.c_double), ("last_flops", C.c_double), ("last_bytes", C.c_double), ("last_units", C.c_double),
         ("kernel_launches", C.c_int64), ("mh_accepts", C.c_int64), ("mh_proposals", C.c_int64),
         ("last_path", C.c_int32), ("sm_count", C.c_int32),
+        ("gram_path", C.c_int32), ("jacobi_sweeps", C.c_int32), ("gram_risk", C.c_double),
     ]
 
 

@@ -117,6 +117,7 @@ int ssi_ctx_destroy(ssi_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ssi_tc_destroy(ctx);
+    ssi_b1_destroy(ctx);
     cudaFree(ctx->dX); cudaFree(ctx->dY); cudaFree(ctx->dP); cudaFree(ctx->dSubGram);
     cudaFree(ctx->dSwaMean); cudaFree(ctx->dDev);
     ssi_buf_t* bufs[] = {&ctx->bZ, &ctx->bLp, &ctx->bTerms, &ctx->bPartials, &ctx->bW, &ctx->bH0, &ctx->bH1, &ctx->bGram,
@@ -151,18 +152,22 @@ int ssi_sync(ssi_ctx* ctx) {
 int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return SSI_ERR_ARG;
     if (!strcmp(key, "path")) {
-        if (value < SSI_PATH_AUTO || value > SSI_PATH_TENSOR) return ssi_fail(ctx, SSI_ERR_ARG, "path must be one of SSI_PATH_*");
+        if (value < SSI_PATH_AUTO || value > SSI_PATH_BASIS) return ssi_fail(ctx, SSI_ERR_ARG, "path must be one of SSI_PATH_*");
         ctx->opt_path = (int)value;
         return SSI_OK;
     }
     if (!strcmp(key, "group")) {
         if (value < 0 || value > 4096) return ssi_fail(ctx, SSI_ERR_ARG, "group out of range");
         ctx->opt_group = (int)value;
-        ssi_tc_invalidate(ctx);
+        ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx);
         return SSI_OK;
     }
-    if (!strcmp(key, "tc_nofuse")) { ctx->opt_tc_nofuse = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }
-    if (!strcmp(key, "tc_nobasis")) { ctx->opt_tc_nobasis = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }
+    if (!strcmp(key, "tc_nofuse")) { ctx->opt_tc_nofuse = value != 0; ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx); return SSI_OK; }
+    // gram_fp64: 1 = always the FP64 SIMT Gram, 0 = tensor-core Gram guarded by the conditioning check (default),
+    // -1 = tensor-core Gram without the check (measurement only)
+    if (!strcmp(key, "gram_fp64")) { ctx->opt_gram_fp64 = (int)value; return SSI_OK; }
+    if (!strcmp(key, "gram_chunk")) { ctx->opt_gram_chunk = (int)value; return SSI_OK; }
+    if (!strcmp(key, "tc_nobasis")) { ctx->opt_tc_nobasis = value != 0; ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "tc_noorder")) { ctx->opt_tc_noorder = value != 0; return SSI_OK; }
     return ssi_fail(ctx, SSI_ERR_ARG, "unknown option '%s'", key);
 }
@@ -202,7 +207,7 @@ int ssi_set_model(ssi_ctx* ctx, int n_layers, const int32_t* dims, const int32_t
     ctx->model = m;
     ctx->has_model = true;
     if (shape_changed) { ctx->has_data = false; ctx->has_sub = false; }
-    ssi_tc_invalidate(ctx);
+    ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx);
     return SSI_OK;
 }
 
@@ -224,7 +229,7 @@ int ssi_set_data(ssi_ctx* ctx, const float* X, const float* Y, int64_t N) {
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->N = N;
     ctx->has_data = true;
-    ssi_tc_invalidate(ctx);
+    ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx);
     return SSI_OK;
 }
 
@@ -247,7 +252,7 @@ static int install_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, in
     SSI_TRY(ssi_subspace_gram(ctx));
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->has_sub = true;
-    ssi_tc_invalidate(ctx);
+    ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx);
     return SSI_OK;
 }
 
@@ -384,11 +389,13 @@ int ssi_swa_begin(ssi_ctx* ctx, int64_t n, int64_t K_max) {
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->dSwaMean); cudaFree(ctx->dDev);
     ctx->dSwaMean = ctx->dDev = nullptr;
-    ctx->swa_n = 0; ctx->swa_K = 0; ctx->swa_Kmax = 0;
+    ctx->swa_n = 0; ctx->swa_K = 0; ctx->swa_Kmax = 0; ctx->swa_ld = 0;
     SSI_CUDA(ctx, cudaMalloc(&ctx->dSwaMean, sizeof(float) * (size_t)n));
-    SSI_CUDA(ctx, cudaMalloc(&ctx->dDev, sizeof(float) * (size_t)n * K_max));
+    const int64_t ld = (n + 31) / 32 * 32;
+    SSI_CUDA(ctx, cudaMalloc(&ctx->dDev, sizeof(float) * (size_t)ld * K_max));
     SSI_CUDA(ctx, cudaMemsetAsync(ctx->dSwaMean, 0, sizeof(float) * (size_t)n, ctx->stream));   // W_swa = zeros (:31)
     ctx->swa_n = n;
+    ctx->swa_ld = ld;
     ctx->swa_Kmax = K_max;
     return SSI_OK;
 }
@@ -440,6 +447,7 @@ int ssi_swa_finish(ssi_ctx* ctx, int32_t M, float* W_swa_out, float* P_out, doub
     if (P_out) SSI_CUDA(ctx, cudaMemcpyAsync(P_out, dPout, sizeof(float) * (size_t)n * M, cudaMemcpyDeviceToHost, ctx->stream));
     if (s_out) SSI_CUDA(ctx, cudaMemcpyAsync(s_out, ds, sizeof(double) * (size_t)K, cudaMemcpyDeviceToHost, ctx->stream));
     SSI_TRY(ssi_sync(ctx));
+    ctx->stats.jacobi_sweeps = sweeps;
     if (sweeps >= 60) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "Jacobi eigen-solver did not converge in %d sweeps", sweeps);
     if (install) {
         if (!ctx->has_model || ctx->model.n != n)

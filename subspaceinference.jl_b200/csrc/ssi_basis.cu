@@ -1,0 +1,316 @@
+// ssi_basis.cu — BASIS path of the batched log-posterior: Chain(Dense(in, H, act), Dense(H, O)) with a narrow
+// output (O <= 2) and a small subspace (M <= 20), e.g. the UCI-style 13-50-1 network with 4096 chains.
+//
+// Replaces the body of the reference's density(z) (src/space_inference.jl:90-95) for that shape:
+//   * first Dense layer: the pre-activation is affine in z,
+//         (W1_swa + sum_m z_m P1_m) x + (b1_swa + sum_m z_m pb_m) = B_M(x) + sum_m z_m B_m(x),
+//     so the M+1 basis pre-activations B_m = [P | W_swa]_m applied to the dataset are computed ONCE per
+//     (data, subspace) in exact FP32 (ssi_build_first_layer_bases) and a sample costs M FMAs per hidden unit
+//     instead of `in` (K1 and the first GEMM of K2 fused away);
+//   * second Dense layer + logpdf(MvNormal): a dot product and a squared error in registers, reduced with
+//     warp shuffles to one FP64 partial per (sample, datapoint tile)  (K3).
+//
+// Mapping.  A CTA owns one tile of 64 datapoints (lane l holds datapoints 2l, 2l+1) and a block of samples;
+// each warp walks its share of the samples ST at a time.  The z of a warp's current samples are warp-uniform:
+// they are read from the constant bank into uniform registers, so the inner FMAs are `FFMA R, R, UR, R`
+// (full issue rate: one vector register per bank) and the basis tile is the only per-lane operand.
+// The basis tile lives in shared memory as [j][m][64] (conflict-free 8-byte reads); it is laid out per tile
+// in global memory once, so staging it is a contiguous copy.  Bound: FP32 FMA issue.
+#include "ssi_common.cuh"
+
+#include <algorithm>
+
+#define B1_TI 64
+#define B1_WARPS 8
+#define B1_THREADS (B1_WARPS * 32)
+#define B1_CONST_FLOATS 16384                 // 64 KB constant bank
+__constant__ float c_b1z[B1_CONST_FLOATS];    // [s][M], the samples of the current launch
+
+struct b1_params {
+    int N, H, O, n_tiles, S, s_per_cta, act_out, w2n;
+    long long n, w2_off, b2_off;
+    const float* tiles;     // [tile][H][M+1][B1_TI]
+    const float* PW;        // [P | W_swa], n x (M+1) column-major
+    const float* Z;         // [S][M] (device), the same samples as c_b1z
+    const float* Y;         // O x N column-major
+    double* partials;       // [S][n_tiles]
+};
+
+template <int ACT>
+__device__ __forceinline__ float b1_act(float v, int act_rt) {
+    if (ACT == SSI_ACT_RELU) return fmaxf(v, 0.0f);
+    if (ACT == SSI_ACT_TANH) return tanhf(v);
+    if (ACT == SSI_ACT_IDENTITY) return v;
+    return ssi_act(v, act_rt);
+}
+
+template <int M, int ST, int OT, int ACT>
+__global__ void __launch_bounds__(B1_THREADS, 2)
+k_logpost_basis1h(const b1_params p, const int act_hidden) {
+    extern __shared__ float4 b1_smem4[];
+    const int H = p.H;
+    float* sB = reinterpret_cast<float*>(b1_smem4);           // [H][M+1][64]
+    float* sP2 = sB + (size_t)H * (M + 1) * B1_TI;            // [M+1][w2n]: second-layer rows of [P | W_swa]: (j*OT + o), bias at j = H
+    float* sW2 = sP2 + (M + 1) * p.w2n;                       // per warp [H+1][ST][OT]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int s_begin = blockIdx.y * p.s_per_cta;
+    const int s_end = min(p.S, s_begin + p.s_per_cta);
+
+    {   // stage the basis tile (contiguous) and the second-layer rows
+        const float4* src = reinterpret_cast<const float4*>(p.tiles + (size_t)tile * H * (M + 1) * B1_TI);
+        float4* dst = reinterpret_cast<float4*>(sB);
+        const int n4 = H * (M + 1) * B1_TI / 4;
+        for (int e = tid; e < n4; e += B1_THREADS) dst[e] = __ldg(src + e);
+        for (int e = tid; e < (M + 1) * p.w2n; e += B1_THREADS) {
+            const int m = e / p.w2n, r = e - m * p.w2n;
+            const int j = r / OT, o = r - j * OT;
+            float v = 0.0f;
+            if (o < p.O && j <= H) v = p.PW[(j < H ? p.w2_off + o + (long long)j * p.O : p.b2_off + o) + (long long)m * p.n];
+            sP2[e] = v;
+        }
+    }
+    __syncthreads();
+
+    // this lane's datapoints and targets
+    const long long i0 = (long long)tile * B1_TI + 2 * lane;
+    float y[2][OT];
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+#pragma unroll
+        for (int o = 0; o < OT; ++o) y[d][o] = (i0 + d < p.N && o < p.O) ? p.Y[o + (i0 + d) * p.O] : 0.0f;
+
+    float* w2s = sW2 + warp * ((H + 1) * ST * OT);
+    const float* bl = sB + 2 * lane;
+
+    for (int s0 = s_begin + warp * ST; s0 < s_end; s0 += B1_WARPS * ST) {
+        // W2, b2 of this warp's ST samples:  (W_swa + P z)[second layer]   (src/space_inference.jl:91)
+        __syncwarp();
+        for (int e = lane; e < (H + 1) * ST * OT; e += 32) {
+            const int o = e % OT, t = (e / OT) % ST, j = e / (OT * ST);
+            const int s = min(s0 + t, p.S - 1);
+            const int r = j * OT + o;
+            float v = sP2[M * p.w2n + r];
+#pragma unroll
+            for (int m = 0; m < M; ++m) v = fmaf(sP2[m * p.w2n + r], p.Z[(long long)s * M + m], v);
+            w2s[e] = v;
+        }
+        __syncwarp();
+
+        // warp-uniform z of the ST samples (clamped: a partial block recomputes the last sample and drops it)
+        float z[ST][M];
+#pragma unroll
+        for (int t = 0; t < ST; ++t) {
+            const int s = min(s0 + t, p.S - 1);
+#pragma unroll
+            for (int m = 0; m < M; ++m) z[t][m] = c_b1z[s * M + m];
+        }
+
+        float pred[ST][2][OT];
+#pragma unroll
+        for (int t = 0; t < ST; ++t)
+#pragma unroll
+            for (int o = 0; o < OT; ++o) pred[t][0][o] = pred[t][1][o] = 0.0f;
+
+#pragma unroll 2
+        for (int j = 0; j < H; ++j) {
+            float2 b[M + 1];
+#pragma unroll
+            for (int m = 0; m <= M; ++m) b[m] = *reinterpret_cast<const float2*>(bl + (j * (M + 1) + m) * B1_TI);
+            float w[ST * OT];
+            if (ST * OT % 4 == 0) {
+#pragma unroll
+                for (int q = 0; q < ST * OT; q += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(w2s + j * ST * OT + q);
+                    w[q] = w4.x; w[q + 1] = w4.y; w[q + 2] = w4.z; w[q + 3] = w4.w;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < ST * OT; q += 2) {
+                    const float2 w2v = *reinterpret_cast<const float2*>(w2s + j * ST * OT + q);
+                    w[q] = w2v.x; w[q + 1] = w2v.y;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < ST; ++t) {
+                float x0 = b[M].x, x1 = b[M].y;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    x0 = fmaf(b[m].x, z[t][m], x0);
+                    x1 = fmaf(b[m].y, z[t][m], x1);
+                }
+                x0 = b1_act<ACT>(x0, act_hidden);
+                x1 = b1_act<ACT>(x1, act_hidden);
+#pragma unroll
+                for (int o = 0; o < OT; ++o) {
+                    pred[t][0][o] = fmaf(x0, w[t * OT + o], pred[t][0][o]);
+                    pred[t][1][o] = fmaf(x1, w[t * OT + o], pred[t][1][o]);
+                }
+            }
+        }
+
+        // output bias + activation, squared error, one FP64 partial per (sample, tile)   (:94)
+#pragma unroll
+        for (int t = 0; t < ST; ++t) {
+            double sse = 0.0;
+#pragma unroll
+            for (int o = 0; o < OT; ++o) {
+                const float b2 = w2s[(H * ST + t) * OT + o];
+#pragma unroll
+                for (int d = 0; d < 2; ++d) {
+                    if (o < p.O && i0 + d < p.N) {
+                        const float df = ssi_act(pred[t][d][o] + b2, p.act_out) - y[d][o];
+                        sse += (double)df * (double)df;
+                    }
+                }
+            }
+            sse = ssi_warp_sum(sse);
+            if (lane == 0 && s0 + t < s_end) p.partials[(long long)(s0 + t) * p.n_tiles + tile] = sse;
+        }
+    }
+}
+
+// tiles[tile][j][m][ii] = bases[m][tile*64 + ii][j]  (zero beyond N): one-time re-layout so that a CTA's
+// basis tile is one contiguous block
+__global__ void __launch_bounds__(256)
+k_b1_tile_layout(const float* __restrict__ bases, long long N, int ld, int H, int M1, float* __restrict__ tiles, long long total) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int ii = (int)(e % B1_TI);
+    const int m = (int)((e / B1_TI) % M1);
+    const int j = (int)((e / B1_TI / M1) % H);
+    const long long tile = e / B1_TI / M1 / H;
+    const long long i = tile * B1_TI + ii;
+    tiles[e] = i < N ? bases[((long long)m * N + i) * ld + j] : 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct ssi_b1_state {
+    bool ready = false;
+    float* tiles = nullptr;
+    int n_tiles = 0;
+};
+
+void ssi_b1_invalidate(ssi_ctx* ctx) {
+    if (ctx->b1) ctx->b1->ready = false;
+}
+
+void ssi_b1_destroy(ssi_ctx* ctx) {
+    if (!ctx->b1) return;
+    cudaFree(ctx->b1->tiles);
+    delete ctx->b1;
+    ctx->b1 = nullptr;
+}
+
+static int b1_st(int M) { return M <= 6 ? 8 : (M <= 12 ? 4 : 2); }   // samples per warp pass: ST * M uniform registers
+
+static size_t b1_smem_bytes(const ssi_ctx* ctx) {
+    const ssi_model_t& m = ctx->model;
+    const int H = m.dims[1], M = ctx->M, OT = m.dims[2] <= 1 ? 1 : 2;
+    const int w2n = ((H + 1) * OT + 3) / 4 * 4;
+    return sizeof(float) * ((size_t)H * (M + 1) * B1_TI + (size_t)(M + 1) * w2n + (size_t)B1_WARPS * (H + 1) * b1_st(M) * OT);
+}
+
+static bool b1_m_supported(int M) { return (M >= 1 && M <= 8) || M == 10 || M == 12 || M == 16 || M == 20; }
+
+bool ssi_b1_supported(const ssi_ctx* ctx) {
+    if (!ctx->has_model || !ctx->has_sub) return false;
+    const ssi_model_t& m = ctx->model;
+    if (m.L != 2 || m.dims[2] > 2 || !b1_m_supported(ctx->M)) return false;
+    if (ctx->N >= (1ll << 31) - B1_TI) return false;
+    // two CTAs per SM: the basis tile must leave room for both
+    return b1_smem_bytes(ctx) <= 110 * 1024;
+}
+
+int ssi_b1_prepare(ssi_ctx* ctx) {
+    if (!ssi_b1_supported(ctx)) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "basis path: needs Chain(Dense, Dense) with O <= 2 and a supported M");
+    if (!ctx->b1) ctx->b1 = new ssi_b1_state();
+    ssi_b1_state* s = ctx->b1;
+    if (s->ready) return SSI_OK;
+    const ssi_model_t& m = ctx->model;
+    const int H = m.dims[1], M1 = ctx->M + 1;
+    const int64_t N = ctx->N;
+    cudaFree(s->tiles);
+    s->tiles = nullptr;
+    s->n_tiles = (int)((N + B1_TI - 1) / B1_TI);
+    const long long total = (long long)s->n_tiles * H * M1 * B1_TI;
+    SSI_CUDA(ctx, cudaMalloc(&s->tiles, sizeof(float) * (size_t)total));
+    // bases [m][N][H] in scratch, exact FP32 (bias parts included)
+    SSI_TRY(ssi_reserve(ctx, ctx->bH0, sizeof(float) * (size_t)M1 * N * H));
+    SSI_TRY(ssi_build_first_layer_bases(ctx, (float*)ctx->bH0.p, H));
+    k_b1_tile_layout<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const float*)ctx->bH0.p, N, H, H, M1, s->tiles, total);
+    SSI_LAUNCH_CHECK(ctx);
+    s->ready = true;
+    return SSI_OK;
+}
+
+typedef void (*b1_kernel_t)(const b1_params, const int);
+
+template <int M, int OT>
+static b1_kernel_t b1_pick_act(int act) {
+    constexpr int ST = M <= 6 ? 8 : (M <= 12 ? 4 : 2);
+    switch (act) {
+        case SSI_ACT_RELU: return k_logpost_basis1h<M, ST, OT, SSI_ACT_RELU>;
+        case SSI_ACT_TANH: return k_logpost_basis1h<M, ST, OT, SSI_ACT_TANH>;
+        default:           return k_logpost_basis1h<M, ST, OT, -1>;
+    }
+}
+template <int OT>
+static b1_kernel_t b1_pick(int M, int act) {
+    switch (M) {
+        case 1: return b1_pick_act<1, OT>(act);
+        case 2: return b1_pick_act<2, OT>(act);
+        case 3: return b1_pick_act<3, OT>(act);
+        case 4: return b1_pick_act<4, OT>(act);
+        case 5: return b1_pick_act<5, OT>(act);
+        case 6: return b1_pick_act<6, OT>(act);
+        case 7: return b1_pick_act<7, OT>(act);
+        case 8: return b1_pick_act<8, OT>(act);
+        case 10: return b1_pick_act<10, OT>(act);
+        case 12: return b1_pick_act<12, OT>(act);
+        case 16: return b1_pick_act<16, OT>(act);
+        case 20: return b1_pick_act<20, OT>(act);
+        default: return nullptr;
+    }
+}
+
+int ssi_reduce_partials(ssi_ctx* ctx, const double* partials, int64_t B, int parts, double* d_out);
+
+int ssi_b1_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
+    SSI_TRY(ssi_b1_prepare(ctx));
+    ssi_b1_state* s = ctx->b1;
+    const ssi_model_t& m = ctx->model;
+    const int M = ctx->M, H = m.dims[1], O = m.dims[2], OT = O <= 1 ? 1 : 2;
+    b1_kernel_t kern = OT == 1 ? b1_pick<1>(M, m.act[0]) : b1_pick<2>(M, m.act[0]);
+    if (!kern) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "basis path: M=%d is not instantiated", M);
+    const size_t smem = b1_smem_bytes(ctx);
+    SSI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSI_TRY(ssi_reserve(ctx, ctx->bPartials, sizeof(double) * (size_t)B * s->n_tiles));
+    double* partials = (double*)ctx->bPartials.p;
+
+    const int ST = b1_st(M);
+    const int64_t max_s = (int64_t)(B1_CONST_FLOATS / M) / (B1_WARPS * ST) * (B1_WARPS * ST);
+    const int64_t n_sub = (B + max_s - 1) / max_s;
+    int64_t per = (B + n_sub - 1) / n_sub;
+    per = (per + B1_WARPS * ST - 1) / (B1_WARPS * ST) * (B1_WARPS * ST);
+    for (int64_t b0 = 0; b0 < B; b0 += per) {
+        const int S = (int)std::min<int64_t>(per, B - b0);
+        SSI_CUDA(ctx, cudaMemcpyToSymbolAsync(c_b1z, dZ + b0 * M, sizeof(float) * (size_t)S * M, 0, cudaMemcpyDeviceToDevice, ctx->stream));
+        b1_params p{};
+        p.N = (int)ctx->N; p.H = H; p.O = O; p.n_tiles = s->n_tiles; p.S = S; p.act_out = m.act[1];
+        p.w2n = ((H + 1) * OT + 3) / 4 * 4;
+        // samples per CTA: enough to amortise staging the basis tile, few enough to fill the machine several times over
+        int spc = 512;
+        while (spc > B1_WARPS * ST && (long long)s->n_tiles * ((S + spc - 1) / spc) < 8ll * ctx->sm_count) spc >>= 1;
+        p.s_per_cta = std::max(spc, B1_WARPS * ST);
+        p.n = m.n; p.w2_off = m.w_off[1]; p.b2_off = m.b_off[1];
+        p.tiles = s->tiles; p.PW = ctx->dP; p.Z = dZ + b0 * M; p.Y = ctx->dY;
+        p.partials = partials + b0 * s->n_tiles;
+        dim3 grid(s->n_tiles, (S + p.s_per_cta - 1) / p.s_per_cta);
+        kern<<<grid, B1_THREADS, smem, ctx->stream>>>(p, m.act[0]);
+        SSI_LAUNCH_CHECK(ctx);
+    }
+    return ssi_reduce_partials(ctx, partials, B, s->n_tiles, d_sse);
+}

@@ -32,6 +32,7 @@ struct ssi_buf_t {
 };
 
 struct ssi_tc_state;   // tensor-core path private state (ssi_tc.cu)
+struct ssi_b1_state;   // basis path private state (ssi_basis.cu)
 
 struct ssi_ctx {
     int device = 0;
@@ -48,6 +49,8 @@ struct ssi_ctx {
     int opt_group = 0;
     int opt_tc_nofuse = 0;    // debugging / A-B: compute the output layer as its own GEMM
     int opt_tc_noorder = 0;
+    int opt_gram_fp64 = 0;    // force the FP64 SIMT Gram (default: tensor-core TF32x2 Gram for large n, K <= 128)
+    int opt_gram_chunk = 0;   // tiles (32 rows) per FP32 accumulation chunk of the tensor-core Gram (default 32)
     int opt_tc_nobasis = 0;   // debugging / A-B: run the first layer as a GEMM instead of the affine-in-z basis combination   // debugging / A-B: sample-major work order on the first layer
 
     // model / data / subspace
@@ -70,12 +73,15 @@ struct ssi_ctx {
 
     // SWA / construction state
     int64_t swa_n = 0, swa_Kmax = 0, swa_K = 0;
+    int64_t swa_ld = 0;          // leading dimension of dDev: n rounded up to 32 (columns 128-byte aligned for float4 / TMA)
     float* dSwaMean = nullptr;   // n
     float* dDev = nullptr;       // n x K_max, column-major
     ssi_buf_t bSnap;
 
     // tensor-core path
     ssi_tc_state* tc = nullptr;
+    // basis path (one hidden layer, narrow output)
+    ssi_b1_state* b1 = nullptr;
 
     // stats
     ssi_stats_t stats{};
@@ -115,7 +121,10 @@ int ssi_project_device(ssi_ctx* ctx, const float* dZ, int64_t B, float* dW /* n 
 int ssi_build_first_layer_bases(ssi_ctx* ctx, float* bases, int ld);
 int ssi_subspace_gram(ssi_ctx* ctx);   // fills dSubGram after set_subspace
 // Gram of an n x K column-major FP32 matrix (ld = n) into a K x K double matrix on device
-int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int K, double* dG);
+// Gram of an n x K column-major FP32 matrix with leading dimension ld
+int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int K, double* dG, bool allow_tensor = true);
+bool ssi_gram_tc_usable(const ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int K);
+int ssi_gram_tc_device(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int K, double* dG);
 
 // tensor-core path (ssi_tc.cu)
 bool ssi_tc_supported(const ssi_ctx* ctx);
@@ -125,6 +134,13 @@ void ssi_tc_invalidate(ssi_ctx* ctx);
 void ssi_tc_destroy(ssi_ctx* ctx);
 // SSE (sum of squared errors) of B samples into d_sse (B doubles)
 int  ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse);
+
+// basis path (ssi_basis.cu): Chain(Dense, Dense) with O <= 2, small M
+bool ssi_b1_supported(const ssi_ctx* ctx);
+int  ssi_b1_prepare(ssi_ctx* ctx);
+void ssi_b1_invalidate(ssi_ctx* ctx);
+void ssi_b1_destroy(ssi_ctx* ctx);
+int  ssi_b1_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse);
 
 // ---- device helpers ---------------------------------------------------------------------
 __device__ __forceinline__ float ssi_act(float v, int act) {

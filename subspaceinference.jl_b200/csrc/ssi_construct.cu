@@ -57,9 +57,9 @@ int ssi_swa_push_device(ssi_ctx* ctx, const float* dW, double n_scalar) {
     if (ctx->swa_K >= ctx->swa_Kmax) return ssi_fail(ctx, SSI_ERR_ARG, "deviation matrix is full (K_max=%lld)", (long long)ctx->swa_Kmax);
     if (!(n_scalar >= 0)) return ssi_fail(ctx, SSI_ERR_ARG, "n_scalar must be >= 0");
     const int64_t n = ctx->swa_n;
-    float* col = ctx->dDev + ctx->swa_K * n;
+    float* col = ctx->dDev + ctx->swa_K * ctx->swa_ld;
     // float4 path needs 16-byte aligned columns: n % 4 == 0 or fall back to the scalar tail for all
-    const bool aligned = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(dW) & 15) == 0);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(dW) & 15) == 0);   // mean and the deviation column are aligned by construction
     const int blocks = ctx->sm_count * 8;
     // vec = 0: everything goes through the scalar tail loop
     k_swa_push<<<blocks, 256, 0, ctx->stream>>>(dW, ctx->dSwaMean, col, n, (float)(1.0 / (n_scalar + 1.0)),
@@ -80,7 +80,7 @@ int ssi_swa_push_device(ssi_ctx* ctx, const float* dW, double n_scalar) {
 #define GR 32
 template <int GT, int MT>   // GT x GT tile per CTA, MT x MT outputs per thread, (GT/MT)^2 == 256 threads
 __global__ void __launch_bounds__(256)
-k_gram_partial(const float* __restrict__ A, long long n, int K, int tiles, long long rows_per_slab,
+k_gram_partial(const float* __restrict__ A, long long n, long long ld, int K, int tiles, long long rows_per_slab,
                double* __restrict__ partial /* slabs x K x K */) {
     __shared__ __align__(16) double As[GR][GT];
     __shared__ __align__(16) double Bs[GR][GT];
@@ -106,8 +106,8 @@ k_gram_partial(const float* __restrict__ A, long long n, int K, int tiles, long 
             const int idx = tid + s * 256;
             const int r = idx % GR, c = idx / GR;
             const bool rv = (r0 + r < r_end);
-            As[r][c] = (rv && a0 + c < K) ? (double)A[(r0 + r) + (long long)(a0 + c) * n] : 0.0;
-            Bs[r][c] = (rv && b0 + c < K) ? (double)A[(r0 + r) + (long long)(b0 + c) * n] : 0.0;
+            As[r][c] = (rv && a0 + c < K) ? (double)A[(r0 + r) + (long long)(a0 + c) * ld] : 0.0;
+            Bs[r][c] = (rv && b0 + c < K) ? (double)A[(r0 + r) + (long long)(b0 + c) * ld] : 0.0;
         }
         __syncthreads();
 #pragma unroll 4
@@ -147,7 +147,8 @@ __global__ void k_gram_reduce(const double* __restrict__ partial, int slabs, lon
     G[e] = s;
 }
 
-int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int K, double* dG) {
+int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int K, double* dG, bool allow_tensor) {
+    if (allow_tensor && ssi_gram_tc_usable(ctx, dA, n, ld, K)) return ssi_gram_tc_device(ctx, dA, n, ld, K, dG);
     const int GT = K <= 32 ? 32 : 64;
     const int tiles = (K + GT - 1) / GT;
     const int pairs = tiles * (tiles + 1) / 2;
@@ -159,8 +160,8 @@ int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int K, double* dG)
     double* partial = (double*)ctx->bGram.p;
     if (pairs > 65535) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "too many deviation columns (K=%d)", K);
     dim3 grid(slabs, pairs);
-    if (GT == 32) k_gram_partial<32, 2><<<grid, 256, 0, ctx->stream>>>(dA, n, K, tiles, rows_per, partial);
-    else          k_gram_partial<64, 4><<<grid, 256, 0, ctx->stream>>>(dA, n, K, tiles, rows_per, partial);
+    if (GT == 32) k_gram_partial<32, 2><<<grid, 256, 0, ctx->stream>>>(dA, n, ld, K, tiles, rows_per, partial);
+    else          k_gram_partial<64, 4><<<grid, 256, 0, ctx->stream>>>(dA, n, ld, K, tiles, rows_per, partial);
     SSI_LAUNCH_CHECK(ctx);
     const long long KK = (long long)K * K;
     k_gram_reduce<<<(unsigned)((KK + 255) / 256), 256, 0, ctx->stream>>>(partial, slabs, KK, dG);
@@ -170,7 +171,8 @@ int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int K, double* dG)
 
 int ssi_subspace_gram(ssi_ctx* ctx) {
     // dP holds [P | W_swa] as an n x (M+1) column-major matrix
-    return ssi_gram_device(ctx, ctx->dP, ctx->model.n, ctx->M + 1, ctx->dSubGram);
+    // the prior's Gram stays on the exact FP64 path (K = M+1 is tiny)
+    return ssi_gram_device(ctx, ctx->dP, ctx->model.n, ctx->model.n, ctx->M + 1, ctx->dSubGram, false);
 }
 
 // ======================================================================================
@@ -184,8 +186,10 @@ k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg
     extern __shared__ double jac_smem[];
     // both K x K matrices live in shared memory when they fit (K <= 104); the round-robin sweeps are
     // latency bound, not bandwidth bound
+    // leading dimension: odd in shared memory so that the scattered (p, u) block accesses spread over the banks
+    const int ld = use_smem ? (K | 1) : K;
     double* A = use_smem ? jac_smem : Ag;
-    double* V = use_smem ? jac_smem + (size_t)K * K : Vg;
+    double* V = use_smem ? jac_smem + (size_t)ld * K : Vg;
     __shared__ double cs[JAC_MAXPAIRS], sn[JAC_MAXPAIRS];
     __shared__ short pp[JAC_MAXPAIRS], qq[JAC_MAXPAIRS];
     __shared__ double red[32];
@@ -196,8 +200,9 @@ k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg
     const double tol = 4.0 * ((double)K * 2.220446049250313e-16) * ((double)K * 2.220446049250313e-16);
 
     for (long long e = tid; e < (long long)K * K; e += nt) {
-        V[e] = ((e % K) == (e / K)) ? 1.0 : 0.0;
-        if (use_smem) A[e] = Ag[e];
+        const int r = (int)(e % K), c = (int)(e / K);
+        V[r + (long long)c * ld] = (r == c) ? 1.0 : 0.0;
+        if (use_smem) A[r + (long long)c * ld] = Ag[e];
     }
     __syncthreads();
 
@@ -206,9 +211,10 @@ k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg
         // convergence: off-diagonal mass relative to the whole matrix
         double off = 0.0, tot = 0.0;
         for (long long e = tid; e < (long long)K * K; e += nt) {
-            const double v = A[e];
+            const int r = (int)(e % K), c = (int)(e / K);
+            const double v = A[r + (long long)c * ld];
             tot += v * v;
-            if ((e % K) != (e / K)) off += v * v;
+            if (r != c) off += v * v;
         }
         off = ssi_block_sum(off, red);
         if (tid == 0) s_off = off;
@@ -226,9 +232,9 @@ k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg
                 if (p > q) { const int t = p; p = q; q = t; }
                 double c = 1.0, s = 0.0;
                 if (q < K) {
-                    const double apq = A[p + (long long)q * K];
+                    const double apq = A[p + (long long)q * ld];
                     if (apq != 0.0) {
-                        const double app = A[p + (long long)p * K], aqq = A[q + (long long)q * K];
+                        const double app = A[p + (long long)p * ld], aqq = A[q + (long long)q * ld];
                         const double tau = (aqq - app) / (2.0 * apq);
                         const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
                         c = 1.0 / sqrt(1.0 + t * t);
@@ -247,24 +253,24 @@ k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg
                 const double ck = cs[ik], sk = sn[ik], cl = cs[il], sl = sn[il];
                 if (q < 0 && v < 0) continue;
                 if (q < 0) {            // single row p, columns (u,v): only the column rotation
-                    const double a = A[p + (long long)u * K], b = A[p + (long long)v * K];
-                    A[p + (long long)u * K] = cl * a - sl * b;
-                    A[p + (long long)v * K] = sl * a + cl * b;
+                    const double a = A[p + (long long)u * ld], b = A[p + (long long)v * ld];
+                    A[p + (long long)u * ld] = cl * a - sl * b;
+                    A[p + (long long)v * ld] = sl * a + cl * b;
                 } else if (v < 0) {     // rows (p,q), single column u: only the row rotation
-                    const double a = A[p + (long long)u * K], b = A[q + (long long)u * K];
-                    A[p + (long long)u * K] = ck * a - sk * b;
-                    A[q + (long long)u * K] = sk * a + ck * b;
+                    const double a = A[p + (long long)u * ld], b = A[q + (long long)u * ld];
+                    A[p + (long long)u * ld] = ck * a - sk * b;
+                    A[q + (long long)u * ld] = sk * a + ck * b;
                 } else {
-                    double a_pu = A[p + (long long)u * K], a_pv = A[p + (long long)v * K];
-                    double a_qu = A[q + (long long)u * K], a_qv = A[q + (long long)v * K];
+                    double a_pu = A[p + (long long)u * ld], a_pv = A[p + (long long)v * ld];
+                    double a_qu = A[q + (long long)u * ld], a_qv = A[q + (long long)v * ld];
                     // columns (A J_l)
                     const double t_pu = cl * a_pu - sl * a_pv, t_pv = sl * a_pu + cl * a_pv;
                     const double t_qu = cl * a_qu - sl * a_qv, t_qv = sl * a_qu + cl * a_qv;
                     // rows (J_k' .)
-                    A[p + (long long)u * K] = ck * t_pu - sk * t_qu;
-                    A[q + (long long)u * K] = sk * t_pu + ck * t_qu;
-                    A[p + (long long)v * K] = ck * t_pv - sk * t_qv;
-                    A[q + (long long)v * K] = sk * t_pv + ck * t_qv;
+                    A[p + (long long)u * ld] = ck * t_pu - sk * t_qu;
+                    A[q + (long long)u * ld] = sk * t_pu + ck * t_qu;
+                    A[p + (long long)v * ld] = ck * t_pv - sk * t_qv;
+                    A[q + (long long)v * ld] = sk * t_pv + ck * t_qv;
                 }
             }
             // V <- V J
@@ -273,9 +279,9 @@ k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg
                 const int u = pp[il], v = qq[il];
                 if (v < 0) continue;
                 const double cl = cs[il], sl = sn[il];
-                const double a = V[k + (long long)u * K], b = V[k + (long long)v * K];
-                V[k + (long long)u * K] = cl * a - sl * b;
-                V[k + (long long)v * K] = sl * a + cl * b;
+                const double a = V[k + (long long)u * ld], b = V[k + (long long)v * ld];
+                V[k + (long long)u * ld] = cl * a - sl * b;
+                V[k + (long long)v * ld] = sl * a + cl * b;
             }
             __syncthreads();
         }
@@ -283,10 +289,10 @@ k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg
     __syncthreads();
     // rank sort of the diagonal, descending (ties by index)
     for (int i = tid; i < K; i += nt) {
-        const double li = A[i + (long long)i * K];
+        const double li = A[i + (long long)i * ld];
         int rank = 0;
         for (int j = 0; j < K; ++j) {
-            const double lj = A[j + (long long)j * K];
+            const double lj = A[j + (long long)j * ld];
             rank += (lj > li) || (lj == li && j < i);
         }
         lambda[rank] = li;
@@ -294,7 +300,7 @@ k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg
     }
     if (tid == 0) *sweeps_out = sweep;
     if (use_smem)
-        for (long long e = tid; e < (long long)K * K; e += nt) Vg[e] = V[e];
+        for (long long e = tid; e < (long long)K * K; e += nt) Vg[e] = V[(e % K) + (e / K) * ld];
 }
 
 // ======================================================================================
@@ -313,15 +319,15 @@ __global__ void k_pack_v(const double* __restrict__ V, const int* __restrict__ o
 // P = A V_M with V_M in the constant bank: the FMAs take V as a uniform operand, no shared-memory traffic
 template <int MP>
 __global__ void __launch_bounds__(256)
-k_form_p_const(const float* __restrict__ A, long long n, int K, int M, float* __restrict__ P) {
+k_form_p_const(const float* __restrict__ A, long long n, long long ld, int K, int M, float* __restrict__ P) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float acc[MP];
 #pragma unroll
     for (int j = 0; j < MP; ++j) acc[j] = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < K; ++k) {
-        const float d = __ldcs(A + i + (long long)k * n);
+        const float d = __ldcs(A + i + (long long)k * ld);
 #pragma unroll
         for (int j = 0; j < MP; ++j) acc[j] = fmaf(d, c_formp_v[k * MP + j], acc[j]);
     }
@@ -332,7 +338,7 @@ k_form_p_const(const float* __restrict__ A, long long n, int K, int M, float* __
 
 template <int MP>
 __global__ void __launch_bounds__(256)
-k_form_p(const float* __restrict__ A, long long n, int K, const double* __restrict__ V, const int* __restrict__ order,
+k_form_p(const float* __restrict__ A, long long n, long long ld, int K, const double* __restrict__ V, const int* __restrict__ order,
          int M, float* __restrict__ P, int vs_in_smem) {
     extern __shared__ float Vs[];   // K x MP
     if (vs_in_smem) {
@@ -348,7 +354,7 @@ k_form_p(const float* __restrict__ A, long long n, int K, const double* __restri
 #pragma unroll
     for (int j = 0; j < MP; ++j) acc[j] = 0.0f;
     for (int k = 0; k < K; ++k) {
-        const float d = __ldcs(A + i + (long long)k * n);
+        const float d = __ldcs(A + i + (long long)k * ld);
         if (vs_in_smem) {
 #pragma unroll
             for (int j = 0; j < MP; j += 4) {
@@ -370,14 +376,14 @@ k_form_p(const float* __restrict__ A, long long n, int K, const double* __restri
 }
 
 template <int MP>
-static int launch_form_p(ssi_ctx* ctx, const float* dA, int64_t n, int K, const double* dV, const int* dOrder, int M, float* dP) {
+static int launch_form_p(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int K, const double* dV, const int* dOrder, int M, float* dP) {
     if ((size_t)K * MP <= FORMP_CONST_MAX) {
         SSI_TRY(ssi_reserve(ctx, ctx->bSnap, sizeof(float) * FORMP_CONST_MAX));
         float* stage = (float*)ctx->bSnap.p;
         k_pack_v<<<(K * MP + 255) / 256, 256, 0, ctx->stream>>>(dV, dOrder, K, M, MP, stage);
         SSI_LAUNCH_CHECK(ctx);
         SSI_CUDA(ctx, cudaMemcpyToSymbolAsync(c_formp_v, stage, sizeof(float) * (size_t)K * MP, 0, cudaMemcpyDeviceToDevice, ctx->stream));
-        k_form_p_const<MP><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dA, n, K, M, dP);
+        k_form_p_const<MP><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dA, n, ld, K, M, dP);
         SSI_LAUNCH_CHECK(ctx);
         return SSI_OK;
     }
@@ -385,9 +391,34 @@ static int launch_form_p(ssi_ctx* ctx, const float* dA, int64_t n, int K, const 
     const int in_smem = smem <= 160 * 1024;
     if (in_smem && smem > 48 * 1024)
         SSI_CUDA(ctx, cudaFuncSetAttribute(k_form_p<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_form_p<MP><<<(unsigned)((n + 255) / 256), 256, in_smem ? smem : 0, ctx->stream>>>(dA, n, K, dV, dOrder, M, dP, in_smem);
+    k_form_p<MP><<<(unsigned)((n + 255) / 256), 256, in_smem ? smem : 0, ctx->stream>>>(dA, n, ld, K, dV, dOrder, M, dP, in_smem);
     SSI_LAUNCH_CHECK(ctx);
     return SSI_OK;
+}
+
+// Conditioning estimate for a Gram known to eps * lambda_0 (absolute).  For each wanted direction i < M:
+//   rotation into the neighbour j:  theta ~ eps lambda_0 / |lambda_i - lambda_j|, i.e. an error of
+//   sqrt(lambda_i / lambda_0) * theta in column i of P relative to the largest column;
+//   singular value:  |d s_i| / s_0 ~ eps sqrt(lambda_0 / lambda_i) / 2.
+#define GRAM_TC_EPS 1e-7
+#define GRAM_TC_RISK_MAX 1e-4   // measured: actual P error <= 0.4 x this estimate (tests/test_gpu_construct.py prints both)
+__global__ void k_gram_risk(const double* __restrict__ lambda, int K, int M, double eps, double* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    const double l0 = lambda[0];
+    double worst = 0.0;
+    if (l0 > 0.0) {
+        for (int i = 0; i < M && i < K; ++i) {
+            const double li = lambda[i];
+            if (li <= eps * eps * l0) continue;        // numerically zero direction: the column of P vanishes with it
+            double gap = 1e300;
+            if (i > 0) gap = fmin(gap, lambda[i - 1] - li);
+            if (i + 1 < K) gap = fmin(gap, li - lambda[i + 1]);
+            const double rot = gap > 0.0 ? eps * sqrt(li * l0) / gap : 1e300;
+            const double sv = 0.5 * eps * sqrt(l0 / li);
+            worst = fmax(worst, fmax(rot, 10.0 * sv));   // singular values are held to 1e-5 s_0, P to 1e-4
+        }
+    }
+    *out = worst;
 }
 
 __global__ void k_singular_values(const double* __restrict__ lambda, int K, double* __restrict__ s) {
@@ -405,30 +436,47 @@ int ssi_swa_factor_device(ssi_ctx* ctx, int M, float* dP_out, double* d_s, int* 
     if (K > 2 * JAC_MAXPAIRS) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "K=%d exceeds the eigen-solver limit %d", K, 2 * JAC_MAXPAIRS);
     // layout of bEig: G (K*K) | V (K*K) | lambda (K) | order (K ints) | sweeps (int)
     const size_t KK = (size_t)K * K;
-    SSI_TRY(ssi_reserve(ctx, ctx->bEig, sizeof(double) * (2 * KK + K) + sizeof(int) * (K + 2)));
+    SSI_TRY(ssi_reserve(ctx, ctx->bEig, sizeof(double) * (2 * KK + K + 1) + sizeof(int) * (K + 2)));
     double* dG = (double*)ctx->bEig.p;
     double* dV = dG + KK;
     double* dLam = dV + KK;
-    int* dOrder = (int*)(dLam + K);
+    double* dRisk = dLam + K;
+    int* dOrder = (int*)(dRisk + 1);
     int* dSweeps = dOrder + K;
-    SSI_TRY(ssi_gram_device(ctx, ctx->dDev, n, K, dG));
-    {
-        const size_t jsm = 2 * sizeof(double) * KK;
-        const int use_smem = jsm + 24 * 1024 <= ctx->smem_optin;
-        if (use_smem) SSI_CUDA(ctx, cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm));
+    const size_t jsm = 2 * sizeof(double) * (size_t)(K | 1) * K;
+    const int use_smem = jsm + 24 * 1024 <= ctx->smem_optin;
+    if (use_smem) SSI_CUDA(ctx, cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm));
+    bool tensor = ssi_gram_tc_usable(ctx, ctx->dDev, n, ctx->swa_ld, K);
+    ctx->stats.gram_risk = 0.0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        SSI_TRY(ssi_gram_device(ctx, ctx->dDev, n, ctx->swa_ld, K, dG, tensor));
         k_jacobi<<<1, 1024, use_smem ? jsm : 0, ctx->stream>>>(dG, dV, K, 60, dLam, dOrder, dSweeps, use_smem);
+        SSI_LAUNCH_CHECK(ctx);
+        if (!tensor) { ctx->stats.gram_path = attempt ? 3 : 1; break; }
+        // The tensor-core Gram is accurate to ~GRAM_TC_EPS of its largest entry.  That is ample when the M wanted
+        // directions are separated from their neighbours, but nearly degenerate eigenvalues rotate freely under such a
+        // perturbation: estimate the damage from the spectrum and redo the Gram in exact FP64 when it could exceed
+        // the 1e-4 parity bar (the estimate is pessimistic: measured errors are 0.03x-0.4x of it).  (One K-double read-back; ssi_swa_finish synchronises anyway.)
+        k_gram_risk<<<1, 32, 0, ctx->stream>>>(dLam, K, M, GRAM_TC_EPS, dRisk);
+        SSI_LAUNCH_CHECK(ctx);
+        double risk = 0.0;
+        SSI_CUDA(ctx, cudaMemcpyAsync(&risk, dRisk, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stats.gram_risk = risk;
+        if (risk <= GRAM_TC_RISK_MAX || ctx->opt_gram_fp64 < 0) { ctx->stats.gram_path = 2; break; }
+        tensor = false;
     }
-    SSI_LAUNCH_CHECK(ctx);
     k_singular_values<<<(K + 127) / 128, 128, 0, ctx->stream>>>(dLam, K, d_s);
     SSI_LAUNCH_CHECK(ctx);
     int rc;
-    if (M <= 4) rc = launch_form_p<4>(ctx, ctx->dDev, n, K, dV, dOrder, M, dP_out);
-    else if (M <= 8) rc = launch_form_p<8>(ctx, ctx->dDev, n, K, dV, dOrder, M, dP_out);
-    else if (M <= 16) rc = launch_form_p<16>(ctx, ctx->dDev, n, K, dV, dOrder, M, dP_out);
-    else if (M <= 24) rc = launch_form_p<24>(ctx, ctx->dDev, n, K, dV, dOrder, M, dP_out);
-    else if (M <= 32) rc = launch_form_p<32>(ctx, ctx->dDev, n, K, dV, dOrder, M, dP_out);
-    else if (M <= 48) rc = launch_form_p<48>(ctx, ctx->dDev, n, K, dV, dOrder, M, dP_out);
-    else rc = launch_form_p<64>(ctx, ctx->dDev, n, K, dV, dOrder, M, dP_out);
+    if (M <= 4) rc = launch_form_p<4>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
+    else if (M <= 8) rc = launch_form_p<8>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
+    else if (M <= 16) rc = launch_form_p<16>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
+    else if (M <= 20) rc = launch_form_p<20>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
+    else if (M <= 24) rc = launch_form_p<24>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
+    else if (M <= 32) rc = launch_form_p<32>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
+    else if (M <= 48) rc = launch_form_p<48>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
+    else rc = launch_form_p<64>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
     if (rc != SSI_OK) return rc;
     if (sweeps_host) {
         SSI_CUDA(ctx, cudaMemcpyAsync(sweeps_host, dSweeps, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

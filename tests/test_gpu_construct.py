@@ -95,3 +95,46 @@ def test_rank_error_and_install(ssi, engine):
     lp = engine.logpost(Z)
     ref, _ = orc.logpost_batch(orc.Problem(dims, acts, X, Y, W_swa, P), Z)
     np.testing.assert_allclose(lp, ref, rtol=1e-5)
+
+
+@pytest.mark.parametrize("n,K,M,expect_tensor", [
+    (70000, 100, 20, None),             # wanted directions reach into the noise floor: either Gram may be chosen
+    (131072, 20, 20, False),            # K = M with a nearly degenerate tail: the conditioning check must reject the tensor Gram
+    (65536 + 4 * 13 + 3, 37, 5, True),  # well separated spectrum: the tensor Gram must be kept
+])
+def test_tensor_core_gram_vs_oracle(ssi, engine, n, K, M, expect_tensor):
+    """Large n, K <= 128: the Gram runs on the tensor cores (TF32 hi/lo split, FP32 chunks drained to FP64).
+    P and W_swa must still match the Float64 oracle to 1e-4; the FP64 SIMT Gram is the cross-check."""
+    rng = np.random.default_rng(n + K)
+    w = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    dirs = rng.standard_normal((M, n)).astype(np.float32) * (1.6 ** -np.arange(M, dtype=np.float32))[:, None]
+    snaps, ns = [], []
+    for k in range(K):
+        w = w + (dirs.T @ rng.standard_normal(M).astype(np.float32)) * 0.05 + 1e-3 * rng.standard_normal(n).astype(np.float32)
+        snaps.append(w.copy())
+        ns.append(float(k + 1))
+    W_ref, P_ref, s_ref, _ = orc.construct_from_snapshots(snaps, ns, M)
+    res = {}
+    for fp64 in (-1, 0, 1):        # -1: tensor-core Gram unguarded (reported, not asserted), 0: guarded default, 1: FP64 SIMT Gram
+        engine.set_option("gram_fp64", fp64)
+        W_swa, P, s = _run(engine, snaps, ns, M)
+        st = engine.stats()
+        err_p = _rel(orc.align_signs(P.astype(np.float64), P_ref), P_ref)
+        print(f"n={n} K={K} M={M} gram_fp64={fp64}: gram_path={st.gram_path} risk={st.gram_risk:.3g} sweeps={st.jacobi_sweeps} "
+              f"err_P={err_p:.3g} err_s={np.abs(s[:M] - s_ref[:M]).max() / s_ref[0]:.3g}")
+        res[fp64] = s
+        if fp64 < 0:
+            assert st.gram_path == 2
+            continue
+        assert st.gram_path == (1 if fp64 else st.gram_path)
+        assert _rel(W_swa, W_ref) < 1e-4
+        assert err_p < 1e-4, f"fp64={fp64}"
+        # TF32 hi/lo products + FP32 chunks: the Gram is accurate to ~1e-7 of its largest entry, i.e. singular
+        # values to ~1e-5 of s_1 in absolute terms; the FP64 Gram resolves every one of them relatively
+        if st.gram_path != 2:
+            np.testing.assert_allclose(s[:M], s_ref[:M], rtol=1e-5)
+        else:
+            np.testing.assert_allclose(s[:M], s_ref[:M], rtol=0, atol=1e-5 * s_ref[0])
+        if fp64 == 0 and expect_tensor is not None:
+            assert (st.gram_path == 2) == expect_tensor, st.gram_risk
+    engine.set_option("gram_fp64", 0)

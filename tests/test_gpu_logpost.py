@@ -18,10 +18,17 @@ def _setup(engine, prob):
     engine.set_subspace(prob.W_swa, prob.P)
 
 
+def _basis_ok(prob):
+    M = prob.P.shape[1]
+    return len(prob.dims) == 3 and prob.dims[-1] <= 2 and (M <= 8 or M in (10, 12, 16, 20))
+
+
 def _paths_for(ssi, prob):
     paths = [ssi.PATH_LAYERED]
     if orc.n_params(prob.dims) < 12000:
         paths.append(ssi.PATH_FUSED)
+    if _basis_ok(prob):
+        paths.append(ssi.PATH_BASIS)
     return paths
 
 
@@ -48,6 +55,11 @@ def test_golden_all_terms(ssi, engine, name):
     ((5, 7, 3), (2, 3), 130, 2, 9),                   # tanh / sigmoid, widths not multiples of 4
     ((3, 1), (0,), 1, 1, 3),                          # single layer, single datapoint
     ((33, 65, 17, 9, 4), (1, 2, 1, 0), 257, 6, 5),    # deeper chain
+    ((13, 50, 1), (1, 0), 10000, 5, 130),             # C2 shape: BASIS path, samples not a multiple of the warp block
+    ((4, 9, 2), (2, 1), 65, 7, 70),                   # BASIS: tanh hidden, relu output, O = 2, ST = 4
+    ((6, 31, 1), (3, 0), 200, 12, 33),                # BASIS: sigmoid hidden, M = 12
+    ((3, 5, 2), (0, 2), 64, 20, 3),                   # BASIS: identity hidden, M = 20 (ST = 2), tanh output
+    ((8, 16, 1), (1, 0), 1, 1, 1),                    # BASIS: one datapoint, one sample, M = 1
 ])
 def test_random_shapes_vs_oracle(ssi, engine, dims, acts, N, M, B):
     rng = np.random.default_rng(hash((dims, N, M, B)) % (2 ** 32))
@@ -58,9 +70,11 @@ def test_random_shapes_vs_oracle(ssi, engine, dims, acts, N, M, B):
     Z = rng.standard_normal((M, B)).astype(np.float32)
     _setup(engine, prob)
     ref, ref_terms = orc.logpost_batch(prob, Z, 0.7, 1.3, 0.9, mask=7)
-    for path in (ssi.PATH_FUSED, ssi.PATH_LAYERED):
+    for path in (ssi.PATH_FUSED, ssi.PATH_LAYERED) + ((ssi.PATH_BASIS, ssi.PATH_AUTO) if _basis_ok(prob) else ()):
         engine.set_option("path", path)
         lp, terms = engine.logpost(Z, 0.7, 1.3, 0.9, mask=7, return_terms=True)
+        if path == ssi.PATH_AUTO:
+            assert engine.stats().last_path == ssi.PATH_BASIS
         np.testing.assert_allclose(terms, ref_terms, rtol=RTOL, err_msg=f"path {path}")
         np.testing.assert_allclose(lp, ref, rtol=RTOL)
 
@@ -71,7 +85,7 @@ def test_batch_invariance_bitwise(ssi, engine):
     prob = orc.make_problem("uci", N=3000)
     _setup(engine, prob)
     Z = (0.1 * np.random.default_rng(0).standard_normal((prob.M, 64))).astype(np.float32)
-    for path in (ssi.PATH_FUSED, ssi.PATH_LAYERED):
+    for path in (ssi.PATH_FUSED, ssi.PATH_LAYERED, ssi.PATH_BASIS):
         engine.set_option("path", path)
         full = engine.logpost(Z, 0.1)
         part = np.concatenate([engine.logpost(Z[:, :5], 0.1), engine.logpost(Z[:, 5:40], 0.1), engine.logpost(Z[:, 40:], 0.1)])
@@ -85,6 +99,7 @@ def test_uci_full_size_properties(ssi, engine):
     rng = np.random.default_rng(1)
     Z = (0.1 * rng.standard_normal((prob.M, 4096))).astype(np.float32)
     lp = engine.logpost(Z, 0.1)
+    assert engine.stats().last_path == ssi.PATH_BASIS          # AUTO: one hidden layer, O = 1, M = 5
     idx = rng.choice(4096, 12, replace=False)
     ref, _ = orc.logpost_batch(prob, Z[:, idx], 0.1)
     np.testing.assert_allclose(lp[idx], ref, rtol=RTOL)
@@ -93,6 +108,10 @@ def test_uci_full_size_properties(ssi, engine):
     lp2 = engine.logpost(Z[:, :256], 0.1)
     np.testing.assert_allclose(lp2, lp[:256], rtol=2e-6)
     assert engine.stats().last_units == 256 * prob.N
+    # the exact-FP32 FUSED path agrees on every sample of the big batch
+    engine.set_data(prob.X, prob.Y)
+    engine.set_option("path", ssi.PATH_FUSED)
+    np.testing.assert_allclose(engine.logpost(Z, 0.1), lp, rtol=2e-6)
 
 
 def test_project_matches_oracle(ssi, engine):

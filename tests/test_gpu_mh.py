@@ -63,11 +63,11 @@ def test_device_stream_equals_host_replay(ssi, engine):
         np.testing.assert_allclose(zt[:, c, 0], 2.0 * eps, rtol=2.5e-7, atol=1e-9)
 
 
-@pytest.mark.parametrize("path", ["fused", "layered"])
+@pytest.mark.parametrize("path", ["fused", "layered", "basis"])
 def test_decisions_teacher_forced_uci(ssi, engine, path):
     prob = orc.make_problem("uci", N=2000)
     _setup(engine, prob)
-    engine.set_option("path", {"fused": ssi.PATH_FUSED, "layered": ssi.PATH_LAYERED}[path])
+    engine.set_option("path", {"fused": ssi.PATH_FUSED, "layered": ssi.PATH_LAYERED, "basis": ssi.PATH_BASIS}[path])
     C, S, seed = 6, 40, 2024
     zt, lt, at = engine.mh_run(C, S, seed, sigma_z=0.02, sigma_m=0.1)
     ties = _check_against_oracle(prob, zt, lt, at, seed, 0.02, 0.1, range(C))

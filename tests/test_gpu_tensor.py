@@ -97,7 +97,8 @@ def test_narrow_chain_runs_padded_on_tensor_path(ssi, engine):
         np.testing.assert_allclose(engine.logpost(Z, 0.5), ref, rtol=RTOL)
         engine.set_option("path", ssi.PATH_AUTO)
         engine.logpost(Z, 0.5)
-        assert engine.stats().last_path == ssi.PATH_FUSED      # AUTO keeps small nets off the tensor path
+        # AUTO keeps small nets off the tensor path
+        assert engine.stats().last_path == (ssi.PATH_BASIS if len(dims) == 3 else ssi.PATH_FUSED)
 
 
 @pytest.mark.parametrize("dims,acts,N,M,B", [
