@@ -171,8 +171,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("SSI_BENCH_WORKLOAD", "wide"), choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="subspace points per GPU per step")
-    ap.add_argument("--path", default="auto", choices=["auto", "fused", "layered", "tensor"])
+    ap.add_argument("--path", default="auto", choices=["auto", "fused", "layered", "tensor", "basis"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library A/B switch, key=value (ssi_set_option); repeatable")
     args = ap.parse_args()
     if args.batch <= 0:
         args.batch = int(os.environ.get("SSI_BENCH_BATCH", WORKLOADS[args.workload][1]))
@@ -206,7 +207,10 @@ def main():
     eng.set_model(prob.dims, prob.acts)
     eng.set_data(prob.X, prob.Y)
     eng.set_subspace(prob.W_swa, prob.P)
-    eng.set_option("path", {"auto": 0, "fused": 1, "layered": 2, "tensor": 3}[args.path])
+    eng.set_option("path", {"auto": 0, "fused": 1, "layered": 2, "tensor": 3, "basis": 4}[args.path])
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     # a non-default stream: the library treats a NULL handle as "use the context's own stream",
     # and CUDA events must be recorded on the stream the kernels are launched on
     stream = torch.cuda.Stream(device=dev)

@@ -97,27 +97,29 @@ k_logpost_basis1h(const b1_params p, const int act_hidden) {
         }
         __syncwarp();
 
-        // warp-uniform z of the ST samples (clamped: a partial block recomputes the last sample and drops it)
-        float z[ST][M];
+        // warp-uniform z of the ST samples (clamped: a partial block recomputes the last sample and drops it),
+        // kept as pairs of adjacent samples: the inner products are packed FFMA2 (two samples per instruction; a
+        // three-register scalar FFMA issues at half rate on sm_100, the packed form does not lose that factor)
+        float2 z2[ST / 2][M];
 #pragma unroll
-        for (int t = 0; t < ST; ++t) {
-            const int s = min(s0 + t, p.S - 1);
+        for (int t = 0; t < ST; t += 2) {
+            const int sa = min(s0 + t, p.S - 1), sb = min(s0 + t + 1, p.S - 1);
 #pragma unroll
-            for (int m = 0; m < M; ++m) z[t][m] = c_b1z[s * M + m];
+            for (int m = 0; m < M; ++m) z2[t / 2][m] = make_float2(c_b1z[sa * M + m], c_b1z[sb * M + m]);
         }
 
-        float pred[ST][2][OT];
+        float2 pred[ST / 2][2][OT];      // [sample pair][datapoint][output] = (sample t, sample t+1)
 #pragma unroll
-        for (int t = 0; t < ST; ++t)
+        for (int t = 0; t < ST / 2; ++t)
 #pragma unroll
-            for (int o = 0; o < OT; ++o) pred[t][0][o] = pred[t][1][o] = 0.0f;
+            for (int o = 0; o < OT; ++o) pred[t][0][o] = pred[t][1][o] = make_float2(0.0f, 0.0f);
 
 #pragma unroll 2
         for (int j = 0; j < H; ++j) {
             float2 b[M + 1];
 #pragma unroll
             for (int m = 0; m <= M; ++m) b[m] = *reinterpret_cast<const float2*>(bl + (j * (M + 1) + m) * B1_TI);
-            float w[ST * OT];
+            float w[ST * OT];       // [sample][output]
             if (ST * OT % 4 == 0) {
 #pragma unroll
                 for (int q = 0; q < ST * OT; q += 4) {
@@ -132,19 +134,20 @@ k_logpost_basis1h(const b1_params p, const int act_hidden) {
                 }
             }
 #pragma unroll
-            for (int t = 0; t < ST; ++t) {
-                float x0 = b[M].x, x1 = b[M].y;
+            for (int d = 0; d < 2; ++d) {
+                float2 bd[M + 1];           // this datapoint's basis values, duplicated for the sample pair
 #pragma unroll
-                for (int m = 0; m < M; ++m) {
-                    x0 = fmaf(b[m].x, z[t][m], x0);
-                    x1 = fmaf(b[m].y, z[t][m], x1);
-                }
-                x0 = b1_act<ACT>(x0, act_hidden);
-                x1 = b1_act<ACT>(x1, act_hidden);
+                for (int m = 0; m <= M; ++m) { const float v = d ? b[m].y : b[m].x; bd[m] = make_float2(v, v); }
 #pragma unroll
-                for (int o = 0; o < OT; ++o) {
-                    pred[t][0][o] = fmaf(x0, w[t * OT + o], pred[t][0][o]);
-                    pred[t][1][o] = fmaf(x1, w[t * OT + o], pred[t][1][o]);
+                for (int t = 0; t < ST / 2; ++t) {
+                    float2 x = bd[M];
+#pragma unroll
+                    for (int m = 0; m < M; ++m) x = __ffma2_rn(bd[m], z2[t][m], x);
+                    x.x = b1_act<ACT>(x.x, act_hidden);
+                    x.y = b1_act<ACT>(x.y, act_hidden);
+#pragma unroll
+                    for (int o = 0; o < OT; ++o)
+                        pred[t][d][o] = __ffma2_rn(x, make_float2(w[(2 * t) * OT + o], w[(2 * t + 1) * OT + o]), pred[t][d][o]);
                 }
             }
         }
@@ -159,7 +162,8 @@ k_logpost_basis1h(const b1_params p, const int act_hidden) {
 #pragma unroll
                 for (int d = 0; d < 2; ++d) {
                     if (o < p.O && i0 + d < p.N) {
-                        const float df = ssi_act(pred[t][d][o] + b2, p.act_out) - y[d][o];
+                        const float pv = (t & 1) ? pred[t / 2][d][o].y : pred[t / 2][d][o].x;
+                        const float df = ssi_act(pv + b2, p.act_out) - y[d][o];
                         sse += (double)df * (double)df;
                     }
                 }

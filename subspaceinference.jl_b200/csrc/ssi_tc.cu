@@ -25,6 +25,7 @@
 #include "ssi_ptx.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 #define TC_BM 128
 #define TC_BK 64                 // bf16 elements per k-block = 128 bytes = one swizzle row
@@ -56,15 +57,20 @@ struct tc_params {
 #define TC_MODE_FINAL  1    // this GEMM is the output layer: squared error in the epilogue
 #define TC_MODE_FUSED  2    // last hidden layer; the (narrow) output layer and the squared error are folded into the epilogue
 #define TC_OP 12            // FUSED: padded output width
+static int tc_smem_total(int mode) {
+    return TC_SMEM_PIPE + 3072 + (mode == TC_MODE_HIDDEN ? TC_SMEM_STORE : (mode == TC_MODE_FUSED ? 2 * 256 * TC_OP * 4 : 0));
+}
 
 // shared-memory carve-up (offsets from the 1024-aligned dynamic base)
-//   [0, TC_SMEM_PIPE)                         operand ring: stage = A_hi | A_lo | B_hi | B_lo
-//   [TC_SMEM_PIPE, +TC_SMEM_STORE)            HIDDEN: per-warp TMA-store staging; FUSED: output-layer weight slices [2][256][TC_OP]
-//   then bias[2][256] floats, 12 mbarriers, TMEM base address
-#define TC_OFF_STORE TC_SMEM_PIPE
-#define TC_OFF_BIAS (TC_SMEM_PIPE + TC_SMEM_STORE)
+//   [0, TC_SMEM_PIPE)            operand ring: stage = A_hi | A_lo | B_hi | B_lo
+//   bias[2][256] floats, 12 mbarriers, TMEM base address
+//   staging area (last, size depends on the mode): HIDDEN per-warp TMA-store staging (32 KB);
+//   FUSED output-layer weight slices [2][256][TC_OP] (24 KB); FINAL nothing.
+// FUSED/FINAL leave >= 7 KB of the SM's 228 KB unused on purpose: the memory-bound basis-layer kernel of the NEXT
+// group (no shared memory, 1 KB reserved per CTA) is co-scheduled on the same SMs from a second stream.
+#define TC_OFF_BIAS TC_SMEM_PIPE
 #define TC_OFF_BAR (TC_OFF_BIAS + 2 * 256 * 4)
-#define TC_SMEM_TOTAL (TC_OFF_BAR + 12 * 8 + 16)
+#define TC_OFF_STORE (TC_OFF_BIAS + 3072)
 
 __device__ __forceinline__ bool tc_decode_work(const tc_params& p, int w, int& g, int& mt) {
     if (p.mt_block > 0) {
@@ -384,56 +390,69 @@ k_tc_split_x(const float* __restrict__ X, long long N, int in0, int Kp, bf16* __
 }
 
 // One Dense weight matrix of the group: flat (out x in, column-major: o + i*out) -> split BF16 [g][o][Kp],
-// zero padded to out_pad rows and Kp columns.  Each block owns a 32(i) x 32(o) tile; P is read once for
-// all G samples (K1, src/space_inference.jl:91).
+// zero padded to out_pad rows and Kp columns.  Each block owns a 16(i) x 16(o) tile and one element per thread:
+// P is read once for all G samples (K1, src/space_inference.jl:91) with 64-byte segments along o, the M loads of a
+// thread are issued four at a time, and the transposition to the K-major GEMM operand goes through shared memory
+// once per block, so that every (sample, o) row leaves as one 32-byte store along i.
+#define PW_T 16
 __global__ void __launch_bounds__(256)
 k_tc_project_w(const float* __restrict__ Wswa, const float* __restrict__ P, const float* __restrict__ Z,
                long long n, int M, int G, long long w_off, int in, int out, int out_pad, int Kp,
                bf16* __restrict__ Wh, bf16* __restrict__ Wl) {
-    __shared__ float zs[SSI_MAX_M * TC_GMAX];
-    __shared__ float tile[32][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;    // 32 x 8
-    for (int e = threadIdx.x; e < M * G; e += 256) zs[e] = Z[e];
+    __shared__ __align__(16) float zs[SSI_MAX_M][TC_GMAX];                 // [m][g], zero for g >= G
+    __shared__ __align__(16) bf16 sh[TC_GMAX][PW_T][PW_T], sl[TC_GMAX][PW_T][PW_T];   // [g][o][i]
+    const int tx = threadIdx.x & (PW_T - 1), ty = threadIdx.x >> 4;
+    for (int e = threadIdx.x; e < M * TC_GMAX; e += 256) {
+        const int m = e / TC_GMAX, g = e % TC_GMAX;
+        zs[m][g] = g < G ? Z[m + g * M] : 0.0f;
+    }
     __syncthreads();
-    const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
-    float acc[4][TC_GMAX];
+    const int i0 = blockIdx.x * PW_T, o0 = blockIdx.y * PW_T;
+    const int i = i0 + ty, o = o0 + tx;
+    const bool ok = (i < in) && (o < out);
+    const long long flat = w_off + o + (long long)i * out;
+    float acc[TC_GMAX];
+    const float w0 = ok ? Wswa[flat] : 0.0f;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int i = i0 + ty + 8 * r, o = o0 + tx;
-        const bool ok = (i < in) && (o < out);
-        const long long flat = w_off + o + (long long)i * out;
-        const float w0 = ok ? Wswa[flat] : 0.0f;
+    for (int g = 0; g < TC_GMAX; ++g) acc[g] = w0;
+    if (ok) {
+        for (int m0 = 0; m0 < M; m0 += 4) {
+            float pv[4];
 #pragma unroll
-        for (int g = 0; g < TC_GMAX; ++g) acc[r][g] = w0;
-        if (ok) {
-            for (int m = 0; m < M; ++m) {
-                const float pv = P[flat + (long long)m * n];
+            for (int r = 0; r < 4; ++r) pv[r] = (m0 + r < M) ? P[flat + (long long)(m0 + r) * n] : 0.0f;
 #pragma unroll
-                for (int g = 0; g < TC_GMAX; ++g) acc[r][g] = fmaf(pv, zs[m + g * M], acc[r][g]);
+            for (int r = 0; r < 4; ++r) {
+                const int m = min(m0 + r, M - 1);       // pv is zero past M
+#pragma unroll
+                for (int g = 0; g < TC_GMAX; g += 4) {
+                    const float4 z4 = *reinterpret_cast<const float4*>(&zs[m][g]);
+                    acc[g] = fmaf(pv[r], z4.x, acc[g]);
+                    acc[g + 1] = fmaf(pv[r], z4.y, acc[g + 1]);
+                    acc[g + 2] = fmaf(pv[r], z4.z, acc[g + 2]);
+                    acc[g + 3] = fmaf(pv[r], z4.w, acc[g + 3]);
+                }
             }
         }
     }
-#pragma unroll 1
-    for (int g = 0; g < G; ++g) {
-        __syncthreads();
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            float v = 0.0f;
-#pragma unroll
-            for (int gg = 0; gg < TC_GMAX; ++gg) v = (gg == g) ? acc[r][gg] : v;   // keeps acc in registers
-            tile[ty + 8 * r][tx] = v;                                              // [i][o]
-        }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int o = o0 + ty + 8 * r, i = i0 + tx;
-            if (o < out_pad && i < Kp) {
-                bf16 hi, lo;
-                split_bf16(tile[tx][ty + 8 * r], hi, lo);
-                const long long dst = ((long long)g * out_pad + o) * Kp + i;
-                Wh[dst] = hi;
-                Wl[dst] = lo;
-            }
+    for (int g = 0; g < TC_GMAX; ++g) {
+        bf16 hi, lo;
+        split_bf16(acc[g], hi, lo);
+        sh[g][tx][ty] = hi;
+        sl[g][tx][ty] = lo;
+    }
+    __syncthreads();
+    // (g, o) rows of 16 i = 32 bytes each
+    for (int c = threadIdx.x; c < G * PW_T; c += 256) {
+        const int g = c / PW_T, oo = c % PW_T;
+        if (o0 + oo < out_pad && i0 < Kp) {
+            const long long dst = ((long long)g * out_pad + o0 + oo) * Kp + i0;
+            const uint4* h4 = reinterpret_cast<const uint4*>(&sh[g][oo][0]);
+            const uint4* l4 = reinterpret_cast<const uint4*>(&sl[g][oo][0]);
+            uint4* dh = reinterpret_cast<uint4*>(Wh + dst);
+            uint4* dl = reinterpret_cast<uint4*>(Wl + dst);
+            dh[0] = h4[0]; dh[1] = h4[1];
+            dl[0] = l4[0]; dl[1] = l4[1];
         }
     }
 }
@@ -499,38 +518,52 @@ k_tc_project_v(const float* __restrict__ Wswa, const float* __restrict__ P, cons
 // (data, subspace) in exact FP32.  Per sample this is M FMAs per activation instead of in0, and an
 // HBM stream instead of tensor-core work.  z of the group lives in constant memory so the FMAs take
 // it as a constant operand.
-__constant__ float c_zgroup[TC_GMAX * SSI_MAX_M];    // [g][m]
 
 // Each thread owns two adjacent activations: all M+1 basis values are fetched up front (M+1 independent
 // 8-byte loads in flight per thread), then one output per sample is a chain of M FMAs whose z operand comes
 // from the constant bank (uniform across the warp).
+// z of the group is staged in shared memory and read with broadcast LDS.128 (the constant-bank route, one indexed
+// LDC per FMA operand, saturated the address-divergence unit: ncu showed pipe_adu at 82 %); the FMAs are packed
+// FFMA2 with z as the scalar operand.  Each thread walks TC_BASIS_ITERS adjacent-pair positions.
+#define TC_BASIS_THREADS 256
+#define TC_BASIS_ITERS 4
 template <int ACT, int MP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TC_BASIS_THREADS)
 k_tc_basis_layer(const float* __restrict__ bases /* [M+1][NW] */, long long NW, int M, int G,
+                 const float* __restrict__ zpack /* [TC_GMAX][SSI_MAX_M], zero padded */,
                  bf16* __restrict__ Hh, bf16* __restrict__ Hl /* [g][NW] */) {
-    const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
-    if (e >= NW) return;
-    float2 b[MP];
+    __shared__ __align__(16) float zs[TC_GMAX][MP];
+    for (int e = threadIdx.x; e < TC_GMAX * MP; e += TC_BASIS_THREADS) zs[e / MP][e % MP] = zpack[(e / MP) * SSI_MAX_M + (e % MP)];
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * (TC_BASIS_THREADS * TC_BASIS_ITERS * 2);
+#pragma unroll 1
+    for (int it = 0; it < TC_BASIS_ITERS; ++it) {
+        const long long e = base + ((long long)it * TC_BASIS_THREADS + threadIdx.x) * 2;
+        if (e >= NW) break;
+        float2 b[MP];
 #pragma unroll
-    for (int m = 0; m < MP; ++m)
-        b[m] = m < M ? __ldcs(reinterpret_cast<const float2*>(bases + (long long)m * NW + e)) : make_float2(0.f, 0.f);
-    const float2 b0 = __ldcs(reinterpret_cast<const float2*>(bases + (long long)M * NW + e));
-#pragma unroll 4
-    for (int g = 0; g < G; ++g) {
-        float x0 = b0.x, x1 = b0.y;
+        for (int m = 0; m < MP; ++m)
+            b[m] = m < M ? __ldcs(reinterpret_cast<const float2*>(bases + (long long)m * NW + e)) : make_float2(0.f, 0.f);
+        const float2 b0 = __ldcs(reinterpret_cast<const float2*>(bases + (long long)M * NW + e));
+#pragma unroll 2
+        for (int g = 0; g < G; ++g) {
+            float2 x = b0;
 #pragma unroll
-        for (int m = 0; m < MP; ++m) {
-            const float z = c_zgroup[g * SSI_MAX_M + m];     // zero for m >= M
-            x0 = fmaf(z, b[m].x, x0);
-            x1 = fmaf(z, b[m].y, x1);
+            for (int m = 0; m < MP; m += 4) {
+                const float4 z4 = *reinterpret_cast<const float4*>(&zs[g][m]);     // zero for m >= M
+                x = __ffma2_rn(b[m], make_float2(z4.x, z4.x), x);
+                x = __ffma2_rn(b[m + 1], make_float2(z4.y, z4.y), x);
+                x = __ffma2_rn(b[m + 2], make_float2(z4.z, z4.z), x);
+                x = __ffma2_rn(b[m + 3], make_float2(z4.w, z4.w), x);
+            }
+            const float x0 = tc_act<ACT>(x.x);
+            const float x1 = tc_act<ACT>(x.y);
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+            const float2 hf = __bfloat1622float2(h2);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+            __stcs(reinterpret_cast<unsigned int*>(Hh + (long long)g * NW + e), *reinterpret_cast<const unsigned int*>(&h2));
+            __stcs(reinterpret_cast<unsigned int*>(Hl + (long long)g * NW + e), *reinterpret_cast<const unsigned int*>(&l2));
         }
-        x0 = tc_act<ACT>(x0);
-        x1 = tc_act<ACT>(x1);
-        const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-        const float2 hf = __bfloat1622float2(h2);
-        const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
-        __stcs(reinterpret_cast<unsigned int*>(Hh + (long long)g * NW + e), *reinterpret_cast<const unsigned int*>(&h2));
-        __stcs(reinterpret_cast<unsigned int*>(Hl + (long long)g * NW + e), *reinterpret_cast<const unsigned int*>(&l2));
     }
 }
 
@@ -543,12 +576,13 @@ __global__ void k_tc_pack_z(const float* __restrict__ Z, int M, int G, float* __
 }
 
 template <int MP>
-static void tc_launch_basis(int act, unsigned blocks, cudaStream_t st, const float* bases, long long NW, int M, int G, bf16* Hh, bf16* Hl) {
+static void tc_launch_basis(int act, unsigned blocks, cudaStream_t st, const float* bases, long long NW, int M, int G, const float* zpack,
+                            bf16* Hh, bf16* Hl) {
     switch (act) {
-        case SSI_ACT_RELU:    k_tc_basis_layer<SSI_ACT_RELU, MP><<<blocks, 256, 0, st>>>(bases, NW, M, G, Hh, Hl); break;
-        case SSI_ACT_TANH:    k_tc_basis_layer<SSI_ACT_TANH, MP><<<blocks, 256, 0, st>>>(bases, NW, M, G, Hh, Hl); break;
-        case SSI_ACT_SIGMOID: k_tc_basis_layer<SSI_ACT_SIGMOID, MP><<<blocks, 256, 0, st>>>(bases, NW, M, G, Hh, Hl); break;
-        default:              k_tc_basis_layer<SSI_ACT_IDENTITY, MP><<<blocks, 256, 0, st>>>(bases, NW, M, G, Hh, Hl); break;
+        case SSI_ACT_RELU:    k_tc_basis_layer<SSI_ACT_RELU, MP><<<blocks, TC_BASIS_THREADS, 0, st>>>(bases, NW, M, G, zpack, Hh, Hl); break;
+        case SSI_ACT_TANH:    k_tc_basis_layer<SSI_ACT_TANH, MP><<<blocks, TC_BASIS_THREADS, 0, st>>>(bases, NW, M, G, zpack, Hh, Hl); break;
+        case SSI_ACT_SIGMOID: k_tc_basis_layer<SSI_ACT_SIGMOID, MP><<<blocks, TC_BASIS_THREADS, 0, st>>>(bases, NW, M, G, zpack, Hh, Hl); break;
+        default:              k_tc_basis_layer<SSI_ACT_IDENTITY, MP><<<blocks, TC_BASIS_THREADS, 0, st>>>(bases, NW, M, G, zpack, Hh, Hl); break;
     }
 }
 
@@ -566,7 +600,7 @@ struct ssi_tc_state {
     bool basis = false;                  // first layer = affine-in-z combination of precomputed bases (k_tc_basis_layer)
     int l0 = 0;                          // first Dense layer that runs as a GEMM (1 when basis)
     float* bases = nullptr;              // [M+1][N][width0] FP32
-    float* zpack = nullptr;              // staging for c_zgroup
+    float* zpack = nullptr;              // [TC_GMAX][SSI_MAX_M] z of the current group, zero padded
     float *Wout = nullptr, *bout = nullptr;
     int Kp[SSI_MAX_LAYERS] = {0};        // padded input width of layer l
     int width[SSI_MAX_LAYERS] = {0};     // padded output width of layer l
@@ -576,6 +610,12 @@ struct ssi_tc_state {
     bf16 *Wh[SSI_MAX_LAYERS] = {nullptr}, *Wl[SSI_MAX_LAYERS] = {nullptr};
     float* bias[SSI_MAX_LAYERS] = {nullptr};
     bf16 *Hh[2] = {nullptr, nullptr}, *Hl[2] = {nullptr, nullptr};
+    // basis-layer output, double buffered: the basis kernel of group g+1 runs on `side` while the GEMMs of group g
+    // read the other buffer
+    bf16 *Bh[2] = {nullptr, nullptr}, *Bl[2] = {nullptr, nullptr};
+    CUtensorMap tmBasisH[2], tmBasisL[2];
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_basis[2] = {nullptr, nullptr}, ev_gemm[2] = {nullptr, nullptr};
     double* partials = nullptr;
     CUtensorMap tmAh[SSI_MAX_LAYERS], tmAl[SSI_MAX_LAYERS], tmBh[SSI_MAX_LAYERS], tmBl[SSI_MAX_LAYERS];
     CUtensorMap tmSh[SSI_MAX_LAYERS], tmSl[SSI_MAX_LAYERS];
@@ -584,11 +624,13 @@ struct ssi_tc_state {
 
 static void tc_free(ssi_tc_state* s) {
     cudaFree(s->Xh); cudaFree(s->Xl); cudaFree(s->partials); cudaFree(s->Wout); cudaFree(s->bout); cudaFree(s->bases); cudaFree(s->zpack);
-    for (int i = 0; i < 2; ++i) { cudaFree(s->Hh[i]); cudaFree(s->Hl[i]); }
+    for (int i = 0; i < 2; ++i) { cudaFree(s->Hh[i]); cudaFree(s->Hl[i]); cudaFree(s->Bh[i]); cudaFree(s->Bl[i]); }
     for (int l = 0; l < SSI_MAX_LAYERS; ++l) { cudaFree(s->Wh[l]); cudaFree(s->Wl[l]); cudaFree(s->bias[l]); }
-    PFN_encodeTiled enc = s->encode;
-    *s = ssi_tc_state();
-    s->encode = enc;
+    // the side stream and its events survive a re-prepare
+    ssi_tc_state keep;
+    keep.encode = s->encode; keep.side = s->side; keep.ev_start = s->ev_start;
+    for (int i = 0; i < 2; ++i) { keep.ev_basis[i] = s->ev_basis[i]; keep.ev_gemm[i] = s->ev_gemm[i]; }
+    *s = keep;
 }
 
 void ssi_tc_invalidate(ssi_ctx* ctx) {
@@ -598,6 +640,12 @@ void ssi_tc_invalidate(ssi_ctx* ctx) {
 void ssi_tc_destroy(ssi_ctx* ctx) {
     if (!ctx->tc) return;
     tc_free(ctx->tc);
+    if (ctx->tc->side) cudaStreamDestroy(ctx->tc->side);
+    if (ctx->tc->ev_start) cudaEventDestroy(ctx->tc->ev_start);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->tc->ev_basis[i]) cudaEventDestroy(ctx->tc->ev_basis[i]);
+        if (ctx->tc->ev_gemm[i]) cudaEventDestroy(ctx->tc->ev_gemm[i]);
+    }
     delete ctx->tc;
     ctx->tc = nullptr;
 }
@@ -709,10 +757,29 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
         SSI_CUDA(ctx, cudaMalloc(&s->Xh, sizeof(bf16) * (size_t)N * s->Kp[0]));
         SSI_CUDA(ctx, cudaMalloc(&s->Xl, sizeof(bf16) * (size_t)N * s->Kp[0]));
     }
-    const int nbuf = s->nl >= 3 ? 2 : (s->nl == 2 ? 1 : 0);   // layers 0..nl-2 store activations
-    for (int i = 0; i < nbuf; ++i) {
+    // GEMM layers l0..nl-2 store their activations in H[l & 1]; the basis layer has its own double buffer
+    for (int l = s->l0; l <= s->nl - 2; ++l) {
+        const int i = l & 1;
+        if (s->Hh[i]) continue;
         SSI_CUDA(ctx, cudaMalloc(&s->Hh[i], sizeof(bf16) * (size_t)G * N * maxw));
         SSI_CUDA(ctx, cudaMalloc(&s->Hl[i], sizeof(bf16) * (size_t)G * N * maxw));
+    }
+    if (s->basis) {
+        const int nb = ctx->opt_tc_overlap ? 2 : 1;
+        for (int i = 0; i < nb; ++i) {
+            SSI_CUDA(ctx, cudaMalloc(&s->Bh[i], sizeof(bf16) * (size_t)G * N * s->width[0]));
+            SSI_CUDA(ctx, cudaMalloc(&s->Bl[i], sizeof(bf16) * (size_t)G * N * s->width[0]));
+        }
+        if (!s->side) {
+            int lo = 0, hi = 0;
+            SSI_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));     // lo = numerically largest = lowest priority
+            SSI_CUDA(ctx, cudaStreamCreateWithPriority(&s->side, cudaStreamNonBlocking, lo));
+            SSI_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_start, cudaEventDisableTiming));
+            for (int i = 0; i < 2; ++i) {
+                SSI_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_basis[i], cudaEventDisableTiming));
+                SSI_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_gemm[i], cudaEventDisableTiming));
+            }
+        }
     }
     const int m_tiles = (int)((N + TC_BM - 1) / TC_BM);
     SSI_CUDA(ctx, cudaMalloc(&s->partials, sizeof(double) * (size_t)G * m_tiles * 4));
@@ -726,6 +793,15 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
         if (l == 0) {
             SSI_TRY(tc_make_map(ctx, &s->tmAh[l], s->Xh, s->Kp[0], N, 1, TC_BK, TC_BM, S128));
             SSI_TRY(tc_make_map(ctx, &s->tmAl[l], s->Xl, s->Kp[0], N, 1, TC_BK, TC_BM, S128));
+        } else if (l == s->l0) {
+            // activations written by the basis layer: [G][N][width_0], one map per buffer
+            for (int i = 0; i < 2; ++i) {
+                if (!s->Bh[i]) continue;
+                SSI_TRY(tc_make_map(ctx, &s->tmBasisH[i], s->Bh[i], s->width[0], N, G, TC_BK, TC_BM, S128));
+                SSI_TRY(tc_make_map(ctx, &s->tmBasisL[i], s->Bl[i], s->width[0], N, G, TC_BK, TC_BM, S128));
+            }
+            s->tmAh[l] = s->tmBasisH[0];
+            s->tmAl[l] = s->tmBasisL[0];
         } else {
             // activations written by layer l-1: [G][N][width_{l-1}], K = width_{l-1} = Kp[l]
             SSI_TRY(tc_make_map(ctx, &s->tmAh[l], s->Hh[(l - 1) & 1], s->width[l - 1], N, G, TC_BK, TC_BM, S128));
@@ -744,7 +820,7 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
     }
     for (int mode = 0; mode < 3; ++mode)
         for (int act = 0; act < 4; ++act)
-            SSI_CUDA(ctx, cudaFuncSetAttribute(tc_kernel(mode, act), cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
+            SSI_CUDA(ctx, cudaFuncSetAttribute(tc_kernel(mode, act), cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_total(mode)));
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     s->ready = true;
     return SSI_OK;
@@ -761,12 +837,51 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
     const int m_tiles = (int)((N + TC_BM - 1) / TC_BM);
     const int parts = m_tiles * 4;
 
-    for (int64_t b0 = 0; b0 < B; b0 += s->G) {
+    // First layer as a basis combination: a pure HBM stream.  It runs on a second, low-priority stream one group
+    // ahead of the GEMMs, co-resident with the persistent GEMM kernel (which leaves it registers and shared memory),
+    // so the stream hides under the tensor-core work instead of preceding it.
+    const bool overlap = s->basis && s->Bh[1] != nullptr;
+    cudaStream_t bstream = overlap ? s->side : ctx->stream;
+    auto launch_basis = [&](int64_t b0, int buf) -> int {
+        const int G = (int)std::min<int64_t>(s->G, B - b0);
+        k_tc_pack_z<<<(TC_GMAX * SSI_MAX_M + 255) / 256, 256, 0, bstream>>>(dZ + b0 * M, M, G, s->zpack);
+        SSI_LAUNCH_CHECK(ctx);
+        const long long NW = (long long)N * s->width[0];
+        const long long per_cta = (long long)TC_BASIS_THREADS * TC_BASIS_ITERS * 2;
+        const unsigned blocks = (unsigned)((NW + per_cta - 1) / per_cta);
+        if (M <= 8) tc_launch_basis<8>(m.act[0], blocks, bstream, s->bases, NW, M, G, s->zpack, s->Bh[buf], s->Bl[buf]);
+        else if (M <= 12) tc_launch_basis<12>(m.act[0], blocks, bstream, s->bases, NW, M, G, s->zpack, s->Bh[buf], s->Bl[buf]);
+        else if (M <= 20) tc_launch_basis<20>(m.act[0], blocks, bstream, s->bases, NW, M, G, s->zpack, s->Bh[buf], s->Bl[buf]);
+        else if (M <= 32) tc_launch_basis<32>(m.act[0], blocks, bstream, s->bases, NW, M, G, s->zpack, s->Bh[buf], s->Bl[buf]);
+        else tc_launch_basis<SSI_MAX_M>(m.act[0], blocks, bstream, s->bases, NW, M, G, s->zpack, s->Bh[buf], s->Bl[buf]);
+        SSI_LAUNCH_CHECK(ctx);
+        if (overlap) SSI_CUDA(ctx, cudaEventRecord(s->ev_basis[buf], s->side));
+        return SSI_OK;
+    };
+    if (overlap) {
+        // everything already queued on the caller's stream (a previous call's GEMMs reading the basis buffers,
+        // the input Z) precedes the side stream's first write
+        SSI_CUDA(ctx, cudaEventRecord(s->ev_start, ctx->stream));
+        SSI_CUDA(ctx, cudaStreamWaitEvent(s->side, s->ev_start, 0));
+    }
+    if (s->basis) SSI_TRY(launch_basis(0, 0));
+
+    // SSI_TC_TRACE=1: time stamps (ms since the start of the call) of the first groups' basis and GEMM kernels
+    static const bool trace = getenv("SSI_TC_TRACE") != nullptr;
+    cudaEvent_t tr[1 + 4 * 4];
+    const int tr_groups = trace ? 4 : 0;
+    if (trace) {
+        for (auto& e : tr) cudaEventCreate(&e);
+        cudaEventRecord(tr[0], ctx->stream);
+    }
+    int64_t gi = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += s->G, ++gi) {
         const int G = (int)std::min<int64_t>(s->G, B - b0);
         const float* Zg = dZ + b0 * M;
+        const int buf = overlap ? (int)(gi & 1) : 0;
         // ---- K1: project the group's weights straight into the GEMM operand layouts ----
         for (int l = s->l0; l < s->nl; ++l) {
-            dim3 grid((s->Kp[l] + 31) / 32, (s->width[l] + 31) / 32);
+            dim3 grid(s->Kp[l] / PW_T, (s->width[l] + PW_T - 1) / PW_T);
             k_tc_project_w<<<grid, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.w_off[l], m.dims[l], m.dims[l + 1],
                                                          s->width[l], s->Kp[l], s->Wh[l], s->Wl[l]);
             SSI_LAUNCH_CHECK(ctx);
@@ -784,17 +899,10 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
             SSI_LAUNCH_CHECK(ctx);
         }
         // ---- the Dense chain ----
-        if (s->basis) {
-            k_tc_pack_z<<<(TC_GMAX * SSI_MAX_M + 255) / 256, 256, 0, ctx->stream>>>(Zg, M, G, s->zpack);
-            SSI_LAUNCH_CHECK(ctx);
-            SSI_CUDA(ctx, cudaMemcpyToSymbolAsync(c_zgroup, s->zpack, sizeof(float) * TC_GMAX * SSI_MAX_M, 0,
-                                                  cudaMemcpyDeviceToDevice, ctx->stream));
-            const long long NW = (long long)N * s->width[0];
-            const unsigned blocks = (unsigned)((NW / 2 + 255) / 256);
-            if (M <= 8) tc_launch_basis<8>(m.act[0], blocks, ctx->stream, s->bases, NW, M, G, s->Hh[0], s->Hl[0]);
-            else if (M <= 24) tc_launch_basis<24>(m.act[0], blocks, ctx->stream, s->bases, NW, M, G, s->Hh[0], s->Hl[0]);
-            else tc_launch_basis<SSI_MAX_M>(m.act[0], blocks, ctx->stream, s->bases, NW, M, G, s->Hh[0], s->Hl[0]);
-            SSI_LAUNCH_CHECK(ctx);
+        if (overlap) {
+            // the projection kernels need most of an SM's registers: the next basis layer starts behind them
+            SSI_CUDA(ctx, cudaEventRecord(s->ev_gemm[buf], ctx->stream));
+            SSI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s->ev_basis[buf], 0));
         }
         for (int l = s->l0; l < s->nl; ++l) {
             tc_params p{};
@@ -821,11 +929,39 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
             } else if (last) {
                 mode = TC_MODE_FINAL;
             }
-            tc_kernel(mode, p.act)<<<grid, TC_THREADS, TC_SMEM_TOTAL, ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l],
-                                                                                   s->tmSh[l], s->tmSl[l], p);
+            const bool from_basis = s->basis && l == s->l0;
+            if (from_basis && gi < tr_groups) cudaEventRecord(tr[1 + 4 * gi], ctx->stream);
+            tc_kernel(mode, p.act)<<<grid, TC_THREADS, tc_smem_total(mode), ctx->stream>>>(
+                from_basis ? s->tmBasisH[buf] : s->tmAh[l], from_basis ? s->tmBasisL[buf] : s->tmAl[l], s->tmBh[l], s->tmBl[l],
+                s->tmSh[l], s->tmSl[l], p);
             SSI_LAUNCH_CHECK(ctx);
+            if (from_basis && gi < tr_groups) cudaEventRecord(tr[2 + 4 * gi], ctx->stream);
+            if (from_basis && overlap) {
+                // the GEMM that reads basis buffer `buf` is queued: the next group's basis layer (other buffer; its
+                // previous reader finished before this group's projection) is launched next to it and shares the SMs
+                if (b0 + s->G < B) {
+                    SSI_CUDA(ctx, cudaStreamWaitEvent(s->side, s->ev_gemm[buf], 0));
+                    if (gi < tr_groups) cudaEventRecord(tr[3 + 4 * gi], s->side);
+                    SSI_TRY(launch_basis(b0 + s->G, buf ^ 1));
+                    if (gi < tr_groups) cudaEventRecord(tr[4 + 4 * gi], s->side);
+                }
+            }
         }
+        if (s->basis && !overlap && b0 + s->G < B) SSI_TRY(launch_basis(b0 + s->G, 0));
         SSI_TRY(ssi_reduce_partials(ctx, s->partials, G, parts, d_sse + b0));
+    }
+    if (trace) {
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);
+        if (overlap) cudaStreamSynchronize(s->side);
+        for (int g = 0; g < tr_groups && g < gi; ++g) {
+            float t[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; ++k)
+                if (cudaEventQuery(tr[1 + 4 * g + k]) == cudaSuccess) cudaEventElapsedTime(&t[k], tr[0], tr[1 + 4 * g + k]);
+            fprintf(stderr, "ssi_tc trace group %d: gemm [%.3f, %.3f] ms   next basis [%.3f, %.3f] ms\n", g, t[0], t[1], t[2], t[3]);
+        }
+        for (auto& e : tr) cudaEventDestroy(e);
+        cudaGetLastError();       // never-recorded trace events are not an error of the call
     }
     return SSI_OK;
 }
