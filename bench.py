@@ -37,7 +37,10 @@ WORKLOADS = {
     # name: (oracle problem name, default B per GPU, sigma_m, z scale)
     "wide": ("wide", 16384, 1.0, 0.1),
     "uci": ("uci", 4096, 0.1, 0.1),
+    # configs[1] as the sampler runs it: a step = MH_STEPS Metropolis-Hastings steps of 4096 chains per GPU, all on the device
+    "uci-mh": ("uci", 4096, 0.1, 0.01),
 }
+MH_STEPS = 100
 
 
 def load_peaks():
@@ -142,7 +145,9 @@ def workload_config(workload, B, world):
     dims = {"wide": (784, 1024, 1024, 10), "uci": (13, 50, 1)}[name]
     N = {"wide": 60000, "uci": 10000}[name]
     M = {"wide": 20, "uci": 5}[name]
-    return {"workload": f"{workload}: MLP {'-'.join(map(str, dims))}, N={N}, M={M}, batched log-posterior over {B} subspace points per GPU",
+    what = (f"{MH_STEPS} on-device RWMH steps of {B} chains per GPU (one batched log-posterior per step)" if workload.endswith("-mh")
+            else f"batched log-posterior over {B} subspace points per GPU")
+    return {"workload": f"{workload}: MLP {'-'.join(map(str, dims))}, N={N}, M={M}, {what}",
             "dims": list(dims), "N": N, "M": M, "batch_per_gpu": B, "global_batch": B * world,
             "parallelism": f"proposals sharded x{world}, W_swa/P/X/Y replicated, NCCL all-gather of lp",
             "l2": "inputs larger than L2 (X + per-sample activations stream through HBM); no explicit flush"}
@@ -226,17 +231,34 @@ def main():
     d_lp = torch.empty(B, dtype=torch.float64, device=dev)
     d_lp_all = torch.empty(B * world, dtype=torch.float64, device=dev) if world > 1 else None
 
+    mh = args.workload.endswith("-mh")
+    units_per_eval_batch = MH_STEPS if mh else 1
+    if mh:
+        d_lp_tr = torch.empty(B * MH_STEPS, dtype=torch.float64, device=dev)      # lp trace (n_chains x n_steps), stays on the device
+        d_z_tr = torch.empty(prob.M * B * MH_STEPS, dtype=torch.float32, device=dev)
+        lp_tr_host = torch.empty(B * MH_STEPS, dtype=torch.float64).pin_memory()
+        z_tr_host = torch.empty(prob.M * B * MH_STEPS, dtype=torch.float32).pin_memory()
+        d_lp = d_lp_tr[B * (MH_STEPS - 1):]
+        lp_host = lp_tr_host
+        Z_host = torch.from_numpy((zs * rng.standard_normal((B, prob.M))).astype(np.float32)).pin_memory()   # z0 of every chain
+
     def step_device():
-        eng.logpost_dev(dZ.data_ptr(), B, d_lp.data_ptr(), sigma_m=sigma_m)
+        if mh:
+            eng.mh_run_dev(B, MH_STEPS, 2024, sigma_z=zs, sigma_m=sigma_m, chain_offset=rank * B, d_z0=dZ.data_ptr(),
+                           d_z_trace=d_z_tr.data_ptr(), d_lp_trace=d_lp_tr.data_ptr())
+        else:
+            eng.logpost_dev(dZ.data_ptr(), B, d_lp.data_ptr(), sigma_m=sigma_m)
         if world > 1:
             dist.all_gather_into_tensor(d_lp_all, d_lp)
 
     def step_e2e():
         dZ.copy_(Z_host, non_blocking=True)
-        eng.logpost_dev(dZ.data_ptr(), B, d_lp.data_ptr(), sigma_m=sigma_m)
-        if world > 1:
-            dist.all_gather_into_tensor(d_lp_all, d_lp)
-        lp_host.copy_(d_lp, non_blocking=True)
+        step_device()
+        if mh:      # the caller takes the whole trace home, as sub_inference returns it
+            z_tr_host.copy_(d_z_tr, non_blocking=True)
+            lp_tr_host.copy_(d_lp_tr, non_blocking=True)
+        else:
+            lp_host.copy_(d_lp, non_blocking=True)
         stream.synchronize()          # the caller consumes lp every step
 
     def barrier():
@@ -260,10 +282,16 @@ def main():
     for _ in range(args.warmup):
         step_device()
     launches0 = eng.stats().kernel_launches
+    # the library brackets every launch of the path's dominant kernel with CUDA events on the launching stream
+    eng.set_option("time_dominant", 1)
     with ClockSampler(local_rank) as clk:
         ms_dev = timed(step_device, args.steps)
-    launches = eng.stats().kernel_launches - launches0
-    path_used = ssi.PATH_NAMES[eng.stats().last_path]
+    eng.sync()
+    st = eng.stats()
+    dom_ms, dom_n = st.dominant_ms, st.dominant_launches
+    eng.set_option("time_dominant", 0)
+    launches = st.kernel_launches - launches0
+    path_used = ssi.PATH_NAMES[st.last_path]
     step_e2e()
     e2e_steps = min(args.steps, 3)
     ms_e2e = timed(step_e2e, e2e_steps)
@@ -271,18 +299,34 @@ def main():
     # sanity: the timed path produced the oracle's numbers (one sample, checked after timing)
     if rank == 0:
         ref = orc.density(prob, Z_host[0].numpy().astype(np.float64), sigma_m)
-        got = float(lp_host[0])
+        got = float(lp_host[0])          # MH: trace entry (chain 0, step 0) = lp(z0)
         if not np.isfinite(got) or abs(got - ref) > 1e-5 * abs(ref):
             raise SystemExit(f"bench result mismatch vs oracle: {got} vs {ref}")
 
     if rank == 0:
         peaks = load_peaks()
-        units_step = float(B) * world * prob.N
+        units_step = float(B) * world * prob.N * units_per_eval_batch
         flops_unit = 2.0 * sum(a * b for a, b in zip(prob.dims[:-1], prob.dims[1:])) + 2.0 * orc.n_params(prob.dims) * prob.M / prob.N
         value = units_step * args.steps / (ms_dev * 1e-3)
         e2e = units_step * e2e_steps / (ms_e2e * 1e-3)
-        per_gpu_flops = flops_unit * B * prob.N * args.steps / (ms_dev * 1e-3)
+        per_gpu_flops = flops_unit * B * prob.N * units_per_eval_batch * args.steps / (ms_dev * 1e-3)
         peak_tf = peaks["bf16_tflops_sustained"]
+        # dominant kernel (rank 0): its own algorithmic flops per launch over its own average launch time
+        dims = prob.dims
+        if path_used == "tensor":      # k_tc_layer<FUSED>: every Dense layer after the first (the first is the basis-layer stream)
+            dom_name = "k_tc_layer<FUSED>: Dense layers 2..L as tcgen05 BF16x3 GEMM + fused output layer + squared error"
+            dom_flops_unit = 2.0 * sum(a * b for a, b in zip(dims[1:-1], dims[2:]))
+        else:
+            dom_name = {"basis": "k_logpost_basis1h: whole chain per (sample, datapoint), first layer affine in z",
+                        "fused": "k_logpost_fused: whole chain per (sample, datapoint)"}.get(path_used, path_used)
+            dom_flops_unit = flops_unit
+        units_launch = float(B) * prob.N * units_per_eval_batch * args.steps / max(dom_n, 1)
+        dom_avg_ms = dom_ms / max(dom_n, 1)
+        dom_tf = dom_flops_unit * units_launch / (dom_avg_ms * 1e-3) / 1e12 if dom_n else None
+        traffic = None
+        tfile = ROOT / "profiles" / "traffic.json"       # dram__bytes_read+write per launch from the committed ncu --set full capture
+        if tfile.exists():
+            traffic = json.loads(tfile.read_text()).get(f"{args.workload}:{path_used}", {}).get("bytes_per_launch")
         line = {
             "metric": "log-posterior evals/sec (samples x datapoints)", "value": value, "unit": "sample*datapoint/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
@@ -291,13 +335,21 @@ def main():
             "path": path_used,
             "clocks": clk.summary(),
             "e2e": {"value": e2e, "unit": "sample*datapoint/s", "h2d_bytes_per_step": int(Z_host.numel() * 4),
-                    "d2h_bytes_per_step": int(lp_host.numel() * 8), "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(lp_host.numel() * 8 + (z_tr_host.numel() * 4 if mh else 0)), "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "achieved": per_gpu_flops / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": per_gpu_flops / 1e12 / peak_tf, "traffic": None,
+            "roofline": {"bound": "tensor", "achieved": dom_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": (dom_tf / peak_tf) if dom_tf else None, "traffic": traffic,
+                         "kernel": dom_name, "launches": int(dom_n), "avg_launch_ms": dom_avg_ms,
+                         "share_of_step": dom_ms / ms_dev if ms_dev else None,
+                         "flops_per_unit": dom_flops_unit, "units_per_launch": units_launch,
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
-                         "flops_per_unit": flops_unit, "per": "GPU",
-                         "note": "algorithmic FP32 flops (padding and split-precision re-issue not counted)"},
+                         "note": "algorithmic FP32 flops of this kernel (padding not counted). FP32-grade results need 3 BF16 MMAs "
+                                 "per product (hi*hi + hi*lo + lo*hi), so the tensor pipe executes 3x this figure: "
+                                 "mma_frac = 3*frac is the share of the BF16 peak the kernel keeps busy",
+                         "mma_frac": (3.0 * dom_tf / peak_tf) if (dom_tf and path_used == "tensor") else None},
+            # the whole step (all kernels of the path), full algorithmic flops per unit incl. the first layer and the projection
+            "step_roofline": {"achieved": per_gpu_flops / 1e12, "peak": peak_tf, "unit": "TFLOP/s", "frac": per_gpu_flops / 1e12 / peak_tf,
+                              "flops_per_unit": flops_unit, "per": "GPU"},
         }
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_reference(args.workload, budget_s=15.0)

@@ -32,6 +32,7 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_int64), ("mh_accepts", C.c_int64), ("mh_proposals", C.c_int64),
         ("last_path", C.c_int32), ("sm_count", C.c_int32),
         ("gram_path", C.c_int32), ("jacobi_sweeps", C.c_int32), ("gram_risk", C.c_double),
+        ("dominant_ms", C.c_double), ("dominant_launches", C.c_int64),
     ]
 
 

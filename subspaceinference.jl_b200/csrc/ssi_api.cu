@@ -56,6 +56,34 @@ static void free_buf(ssi_buf_t& b) {
     b.cap = 0;
 }
 
+#define SSI_KT_MAX_PAIRS 16384
+void ssi_kt_begin(ssi_ctx* ctx) {
+    if (!ctx->opt_time_dominant || ctx->kt_used + 2 > 2 * SSI_KT_MAX_PAIRS) return;
+    while (ctx->kt_events.size() < ctx->kt_used + 2) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) { (void)cudaGetLastError(); return; }
+        ctx->kt_events.push_back(e);
+    }
+    cudaEventRecord(ctx->kt_events[ctx->kt_used], ctx->stream);
+}
+void ssi_kt_end(ssi_ctx* ctx) {
+    if (!ctx->opt_time_dominant || ctx->kt_events.size() < ctx->kt_used + 2) return;
+    cudaEventRecord(ctx->kt_events[ctx->kt_used + 1], ctx->stream);
+    ctx->kt_used += 2;
+}
+// after the stream has been synchronised
+void ssi_kt_collect(ssi_ctx* ctx) {
+    for (size_t i = 0; i + 1 < ctx->kt_used; i += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->kt_events[i], ctx->kt_events[i + 1]) == cudaSuccess) {
+            ctx->stats.dominant_ms += ms;
+            ctx->stats.dominant_launches++;
+        }
+    }
+    ctx->kt_used = 0;
+    (void)cudaGetLastError();
+}
+
 struct call_timer {
     ssi_ctx* ctx;
     explicit call_timer(ssi_ctx* c) : ctx(c) { cudaEventRecord(c->ev0, c->stream); }
@@ -123,6 +151,7 @@ int ssi_ctx_destroy(ssi_ctx* ctx) {
     ssi_buf_t* bufs[] = {&ctx->bZ, &ctx->bLp, &ctx->bTerms, &ctx->bPartials, &ctx->bW, &ctx->bH0, &ctx->bH1, &ctx->bGram,
                          &ctx->bEig, &ctx->bMisc, &ctx->bMhZ, &ctx->bMhZp, &ctx->bMhLp, &ctx->bMhLpP, &ctx->bMhCnt, &ctx->bSnap};
     for (ssi_buf_t* b : bufs) free_buf(*b);
+    for (cudaEvent_t e : ctx->kt_events) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->own_stream);
@@ -146,6 +175,7 @@ int ssi_sync(ssi_ctx* ctx) {
     if (cudaEventQuery(ctx->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess)
         ctx->stats.last_ms = ms;
     (void)cudaGetLastError();
+    ssi_kt_collect(ctx);
     return SSI_OK;
 }
 
@@ -168,6 +198,11 @@ int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
     if (!strcmp(key, "gram_fp64")) { ctx->opt_gram_fp64 = (int)value; return SSI_OK; }
     if (!strcmp(key, "gram_chunk")) { ctx->opt_gram_chunk = (int)value; return SSI_OK; }
     if (!strcmp(key, "tc_nobasis")) { ctx->opt_tc_nobasis = value != 0; ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx); return SSI_OK; }
+    if (!strcmp(key, "time_dominant")) {
+        ctx->opt_time_dominant = value != 0;
+        ctx->stats.dominant_ms = 0; ctx->stats.dominant_launches = 0; ctx->kt_used = 0;
+        return SSI_OK;
+    }
     if (!strcmp(key, "tc_overlap")) { ctx->opt_tc_overlap = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "tc_noorder")) { ctx->opt_tc_noorder = value != 0; return SSI_OK; }
     return ssi_fail(ctx, SSI_ERR_ARG, "unknown option '%s'", key);

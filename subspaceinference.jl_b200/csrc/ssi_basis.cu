@@ -313,8 +313,10 @@ int ssi_b1_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
         p.tiles = s->tiles; p.PW = ctx->dP; p.Z = dZ + b0 * M; p.Y = ctx->dY;
         p.partials = partials + b0 * s->n_tiles;
         dim3 grid(s->n_tiles, (S + p.s_per_cta - 1) / p.s_per_cta);
+        ssi_kt_begin(ctx);
         kern<<<grid, B1_THREADS, smem, ctx->stream>>>(p, m.act[0]);
         SSI_LAUNCH_CHECK(ctx);
+        ssi_kt_end(ctx);
     }
     return ssi_reduce_partials(ctx, partials, B, s->n_tiles, d_sse);
 }

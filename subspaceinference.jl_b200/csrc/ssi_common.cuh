@@ -86,7 +86,18 @@ struct ssi_ctx {
 
     // stats
     ssi_stats_t stats{};
+
+    // optional device timing of the path's dominant kernel (option "time_dominant"): event pairs recorded around
+    // each launch on the launching stream, summed into stats.dominant_ms at the next ssi_sync / ssi_stats
+    int opt_time_dominant = 0;
+    std::vector<cudaEvent_t> kt_events;
+    size_t kt_used = 0;
 };
+
+// bracket a launch of the dominant kernel (no-ops unless "time_dominant" is set)
+void ssi_kt_begin(ssi_ctx* ctx);
+void ssi_kt_end(ssi_ctx* ctx);
+void ssi_kt_collect(ssi_ctx* ctx);
 
 // ---- error plumbing -------------------------------------------------------------------
 int ssi_fail(ssi_ctx* ctx, int code, const char* fmt, ...);

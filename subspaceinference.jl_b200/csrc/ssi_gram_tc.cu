@@ -261,8 +261,10 @@ int ssi_gram_tc_device(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int
     p.partial = (double*)ctx->bGram.p;
     double* dS = p.partial + (size_t)grid * elems;
     SSI_CUDA(ctx, cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_TOTAL));
+    ssi_kt_begin(ctx);
     k_gram_tc<<<grid, GT_THREADS, GT_SMEM_TOTAL, ctx->stream>>>(map, p);
     SSI_LAUNCH_CHECK(ctx);
+    ssi_kt_end(ctx);
     k_gram_tc_sum<<<(elems + 127) / 128, 128, 0, ctx->stream>>>(p.partial, grid, elems, p.NP, dS);
     SSI_LAUNCH_CHECK(ctx);
     k_gram_tc_sym<<<(K * K + 255) / 256, 256, 0, ctx->stream>>>(dS, K, p.NP, dG);

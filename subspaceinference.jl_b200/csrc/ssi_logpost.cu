@@ -207,10 +207,12 @@ static int run_fused(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
     for (int64_t b0 = 0; b0 < B; b0 += 65535) {
         const int64_t nb = std::min<int64_t>(65535, B - b0);
         dim3 grid(n_chunks, (unsigned)nb);
+        ssi_kt_begin(ctx);
         k_logpost_fused<<<grid, FUSED_T, smem, ctx->stream>>>(d, ctx->dX, ctx->dY, ctx->dWswa, ctx->dP,
                                                              dZ + b0 * ctx->M, ctx->N, chunk, n_chunks,
                                                              partials + b0 * n_chunks);
         SSI_LAUNCH_CHECK(ctx);
+        ssi_kt_end(ctx);
     }
     extern int ssi_reduce_partials(ssi_ctx*, const double*, int64_t, int, double*);
     return ssi_reduce_partials(ctx, partials, B, n_chunks, d_sse);

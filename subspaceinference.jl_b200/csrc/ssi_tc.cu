@@ -931,10 +931,12 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
             }
             const bool from_basis = s->basis && l == s->l0;
             if (from_basis && gi < tr_groups) cudaEventRecord(tr[1 + 4 * gi], ctx->stream);
+            if (last) ssi_kt_begin(ctx);
             tc_kernel(mode, p.act)<<<grid, TC_THREADS, tc_smem_total(mode), ctx->stream>>>(
                 from_basis ? s->tmBasisH[buf] : s->tmAh[l], from_basis ? s->tmBasisL[buf] : s->tmAl[l], s->tmBh[l], s->tmBl[l],
                 s->tmSh[l], s->tmSl[l], p);
             SSI_LAUNCH_CHECK(ctx);
+            if (last) ssi_kt_end(ctx);
             if (from_basis && gi < tr_groups) cudaEventRecord(tr[2 + 4 * gi], ctx->stream);
             if (from_basis && overlap) {
                 // the GEMM that reads basis buffer `buf` is queued: the next group's basis layer (other buffer; its
