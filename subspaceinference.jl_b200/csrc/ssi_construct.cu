@@ -179,6 +179,7 @@ int ssi_subspace_gram(ssi_ctx* ctx) {
 // K7: symmetric eigen-solve, parallel cyclic Jacobi (round-robin pairs), FP64, one CTA
 // ======================================================================================
 #define JAC_MAXPAIRS 1024
+#define JAC_W 64                       // threads along the fast (row) index of the rotation updates
 __global__ void __launch_bounds__(1024)
 k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg /* K x K out */, int K,
          int max_sweeps, double* __restrict__ lambda /* K, sorted desc */, int* __restrict__ order /* K */,
@@ -195,6 +196,7 @@ k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg
     __shared__ double red[32];
     __shared__ double s_off, s_tot;
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int jx = tid & (JAC_W - 1), jy = tid / JAC_W, jrows = nt / JAC_W;
     const int m = (K + 1) & ~1;          // even number of players; index K (if any) is a bye
     const int np = m / 2;
     const double tol = 4.0 * ((double)K * 2.220446049250313e-16) * ((double)K * 2.220446049250313e-16);
@@ -246,42 +248,51 @@ k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg
                 pp[i] = (short)p; qq[i] = (short)q; cs[i] = c; sn[i] = s;
             }
             __syncthreads();
-            // A <- J' A J, one 2x2 block per (pair_k, pair_l): no cross-block hazards
-            for (int e = tid; e < np * np; e += nt) {
-                const int ik = e / np, il = e % np;
-                const int p = pp[ik], q = qq[ik], u = pp[il], v = qq[il];
-                const double ck = cs[ik], sk = sn[ik], cl = cs[il], sl = sn[il];
-                if (q < 0 && v < 0) continue;
-                if (q < 0) {            // single row p, columns (u,v): only the column rotation
-                    const double a = A[p + (long long)u * ld], b = A[p + (long long)v * ld];
-                    A[p + (long long)u * ld] = cl * a - sl * b;
-                    A[p + (long long)v * ld] = sl * a + cl * b;
-                } else if (v < 0) {     // rows (p,q), single column u: only the row rotation
-                    const double a = A[p + (long long)u * ld], b = A[q + (long long)u * ld];
-                    A[p + (long long)u * ld] = ck * a - sk * b;
-                    A[q + (long long)u * ld] = sk * a + ck * b;
-                } else {
-                    double a_pu = A[p + (long long)u * ld], a_pv = A[p + (long long)v * ld];
-                    double a_qu = A[q + (long long)u * ld], a_qv = A[q + (long long)v * ld];
-                    // columns (A J_l)
-                    const double t_pu = cl * a_pu - sl * a_pv, t_pv = sl * a_pu + cl * a_pv;
-                    const double t_qu = cl * a_qu - sl * a_qv, t_qv = sl * a_qu + cl * a_qv;
-                    // rows (J_k' .)
-                    A[p + (long long)u * ld] = ck * t_pu - sk * t_qu;
-                    A[q + (long long)u * ld] = sk * t_pu + ck * t_qu;
-                    A[p + (long long)v * ld] = ck * t_pv - sk * t_qv;
-                    A[q + (long long)v * ld] = sk * t_pv + ck * t_qv;
+            // A <- J' A J, one 2x2 block per (pair_k, pair_l): no cross-block hazards.  Threads are laid out
+            // (jx = pair_k fastest, jy = pair_l): consecutive pairs own consecutive rows p (and q), so a warp's
+            // accesses to a column are contiguous in shared memory.
+            for (int il = jy; il < np; il += jrows) {
+                const int u = pp[il], v = qq[il];
+                const double cl = cs[il], sl = sn[il];
+                double* Au = A + u * ld;
+                double* Av = A + (v < 0 ? u : v) * ld;
+                for (int ik = jx; ik < np; ik += JAC_W) {
+                    const int p = pp[ik], q = qq[ik];
+                    const double ck = cs[ik], sk = sn[ik];
+                    if (q < 0 && v < 0) continue;
+                    if (q < 0) {            // single row p, columns (u,v): only the column rotation
+                        const double a = Au[p], b = Av[p];
+                        Au[p] = cl * a - sl * b;
+                        Av[p] = sl * a + cl * b;
+                    } else if (v < 0) {     // rows (p,q), single column u: only the row rotation
+                        const double a = Au[p], b = Au[q];
+                        Au[p] = ck * a - sk * b;
+                        Au[q] = sk * a + ck * b;
+                    } else {
+                        const double a_pu = Au[p], a_pv = Av[p], a_qu = Au[q], a_qv = Av[q];
+                        // columns (A J_l)
+                        const double t_pu = cl * a_pu - sl * a_pv, t_pv = sl * a_pu + cl * a_pv;
+                        const double t_qu = cl * a_qu - sl * a_qv, t_qv = sl * a_qu + cl * a_qv;
+                        // rows (J_k' .)
+                        Au[p] = ck * t_pu - sk * t_qu;
+                        Au[q] = sk * t_pu + ck * t_qu;
+                        Av[p] = ck * t_pv - sk * t_qv;
+                        Av[q] = sk * t_pv + ck * t_qv;
+                    }
                 }
             }
-            // V <- V J
-            for (int e = tid; e < np * K; e += nt) {
-                const int il = e / K, k = e % K;
+            // V <- V J   (jx = row k fastest: contiguous column accesses)
+            for (int il = jy; il < np; il += jrows) {
                 const int u = pp[il], v = qq[il];
                 if (v < 0) continue;
                 const double cl = cs[il], sl = sn[il];
-                const double a = V[k + (long long)u * ld], b = V[k + (long long)v * ld];
-                V[k + (long long)u * ld] = cl * a - sl * b;
-                V[k + (long long)v * ld] = sl * a + cl * b;
+                double* Vu = V + u * ld;
+                double* Vv = V + v * ld;
+                for (int k = jx; k < K; k += JAC_W) {
+                    const double a = Vu[k], b = Vv[k];
+                    Vu[k] = cl * a - sl * b;
+                    Vv[k] = sl * a + cl * b;
+                }
             }
             __syncthreads();
         }
@@ -316,24 +327,54 @@ __global__ void k_pack_v(const double* __restrict__ V, const int* __restrict__ o
     out[e] = j < M ? (float)V[k + (long long)order[j] * K] : 0.0f;
 }
 
-// P = A V_M with V_M in the constant bank: the FMAs take V as a uniform operand, no shared-memory traffic
+// P = A V_M with V_M in the constant bank: the FMAs take V as a uniform operand, no shared-memory traffic.
+// Four consecutive rows per thread (one 16-byte load per column: a warp reads 512 contiguous bytes of each column).
 template <int MP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_form_p_const(const float* __restrict__ A, long long n, long long ld, int K, int M, float* __restrict__ P) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= n) return;
-    float acc[MP];
+    float acc[4][MP];
 #pragma unroll
-    for (int j = 0; j < MP; ++j) acc[j] = 0.0f;
-#pragma unroll 8
-    for (int k = 0; k < K; ++k) {
-        const float d = __ldcs(A + i + (long long)k * ld);
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int j = 0; j < MP; ++j) acc[j] = fmaf(d, c_formp_v[k * MP + j], acc[j]);
+        for (int j = 0; j < MP; ++j) acc[r][j] = 0.0f;
+    if (i + 3 < n) {
+        // 10 independent 16-byte loads in flight per thread (latency-bound otherwise: ncu showed 48 % DRAM, 24 % occupancy)
+#pragma unroll 10
+        for (int k = 0; k < K; ++k) {
+            const float4 d = __ldcs(reinterpret_cast<const float4*>(A + i + (long long)k * ld));
+#pragma unroll
+            for (int j = 0; j < MP; ++j) {
+                const float v = c_formp_v[k * MP + j];
+                acc[0][j] = fmaf(d.x, v, acc[0][j]);
+                acc[1][j] = fmaf(d.y, v, acc[1][j]);
+                acc[2][j] = fmaf(d.z, v, acc[2][j]);
+                acc[3][j] = fmaf(d.w, v, acc[3][j]);
+            }
+        }
+    } else {
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (i + r < n) {
+                    const float d = A[i + r + (long long)k * ld];
+#pragma unroll
+                    for (int j = 0; j < MP; ++j) acc[r][j] = fmaf(d, c_formp_v[k * MP + j], acc[r][j]);
+                }
     }
+    const bool vec = (i + 3 < n) && ((n & 3) == 0);      // columns of P are n apart: 16-byte stores need n % 4 == 0
 #pragma unroll
-    for (int j = 0; j < MP; ++j)
-        if (j < M) __stcs(P + i + (long long)j * n, acc[j]);
+    for (int j = 0; j < MP; ++j) {
+        if (j >= M) break;
+        if (vec) {
+            __stcs(reinterpret_cast<float4*>(P + i + (long long)j * n), make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]));
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (i + r < n) P[i + r + (long long)j * n] = acc[r][j];
+        }
+    }
 }
 
 template <int MP>
@@ -383,7 +424,7 @@ static int launch_form_p(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, i
         k_pack_v<<<(K * MP + 255) / 256, 256, 0, ctx->stream>>>(dV, dOrder, K, M, MP, stage);
         SSI_LAUNCH_CHECK(ctx);
         SSI_CUDA(ctx, cudaMemcpyToSymbolAsync(c_formp_v, stage, sizeof(float) * (size_t)K * MP, 0, cudaMemcpyDeviceToDevice, ctx->stream));
-        k_form_p_const<MP><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dA, n, ld, K, M, dP);
+        k_form_p_const<MP><<<(unsigned)((n + 511) / 512), 128, 0, ctx->stream>>>(dA, n, ld, K, M, dP);
         SSI_LAUNCH_CHECK(ctx);
         return SSI_OK;
     }
