@@ -141,6 +141,14 @@ int  ssi_rng_replay(uint64_t seed, int64_t chain, int64_t step, int32_t M, float
 /* map(z -> W_swa + P*z, chm) (src/space_inference.jl:125): W_out n x B column-major (host) */
 int  ssi_project(ssi_ctx* ctx, const float* Z, int64_t B, float* W_out);
 
+/* ---- posterior-predictive sweep: the step AFTER the path in every docs example -------
+ * docs/src/nn_example.md:207-216 (for every sample: m1 = re(W); trajectories[:, i] = m1(inp)) and
+ * src/plotting.jl:8-9 (mean / std of the trajectories).  Z: M x B subspace samples, Xg: in0 x Ng grid (host).
+ * mean_out / std_out: O x Ng doubles = mean(trajectories, dims=2), std(trajectories, dims=2) (corrected, B-1; NaN for
+ * B == 1 as in Julia); preds_out: O x Ng x B floats (the trajectories) or NULL.  The data set need not be set.    */
+int  ssi_predict_batch(ssi_ctx* ctx, const float* Z, int64_t B, const float* Xg, int64_t Ng,
+                       float* preds_out, double* mean_out, double* std_out);
+
 /* ---- subspace construction streams (src/subspace_construction.jl:31,44-52,61-65) ---- */
 /* W_swa <- zeros(n) (:31), deviation matrix with room for K_max columns (:33)             */
 int  ssi_swa_begin(ssi_ctx* ctx, int64_t n, int64_t K_max);
@@ -154,6 +162,20 @@ int  ssi_swa_push_dev(ssi_ctx* ctx, const float* dW, double n_scalar);
 int  ssi_swa_finish(ssi_ctx* ctx, int32_t M, float* W_swa_out, float* P_out, double* s_out, int32_t install);
 /* number of columns collected so far */
 int64_t ssi_swa_columns(const ssi_ctx* ctx);
+
+/* Row-sharded construction over several GPUs (one process and one context per GPU): every rank pushes ITS ROW SHARD of
+ * each snapshot (n = shard length), then
+ *   ssi_swa_gram_dev    Gram of the local deviation columns into a caller-provided DEVICE buffer (K x K doubles,
+ *                       column-major); exact != 0 forces the FP64 kernel.  The host all-reduces (sums) it across ranks
+ *                       (ncclAllReduce / torch.distributed): the only collective of the construction path;
+ *   ssi_swa_finish_gram replicated eigen-solve of the reduced Gram, then W_swa / P ROWS of the local shard (host
+ *                       pointers, any NULL) and the K singular values.  Returns SSI_RETRY_EXACT (> 0) when
+ *                       gram_exact == 0 and the conditioning check rejects a tensor-core Gram: every rank sees the same
+ *                       spectrum, so every rank then repeats both calls with exact = gram_exact = 1.                   */
+#define SSI_RETRY_EXACT 1
+int  ssi_swa_gram_dev(ssi_ctx* ctx, double* dG_out, int32_t exact);
+int  ssi_swa_finish_gram(ssi_ctx* ctx, int32_t M, const double* dG, int32_t gram_exact,
+                         float* W_swa_out, float* P_out, double* s_out, int32_t install);
 
 #ifdef __cplusplus
 }

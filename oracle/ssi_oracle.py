@@ -297,6 +297,20 @@ def rwmh_chain(prob: Problem, n_steps: int, seed: int, chain: int, sigma_z=1.0, 
     return z_tr, lp_tr, acc, margin
 
 
+def predictive_sweep(dims, acts, W_swa: np.ndarray, P: np.ndarray, Z: np.ndarray, Xg: np.ndarray):
+    """docs/src/nn_example.md:207-216: ``for i in 1:itr; m1 = re(all_chain[i]); trajectories[:, i] = m1(inp)'``, then
+    src/plotting.jl:8-9: ``mean(trajectories, dims=2)``, ``std(trajectories, dims=2)`` (Julia's std is the corrected
+    estimator; one trajectory gives NaN).  Returns (trajectories (O, Ng, B), mean (O, Ng), std (O, Ng))."""
+    Z = np.asarray(Z, np.float64)
+    if Z.ndim == 1:
+        Z = Z[:, None]
+    Xg = np.asarray(Xg, np.float64)
+    traj = np.stack([forward(project(W_swa, P, Z[:, b]), dims, acts, Xg) for b in range(Z.shape[1])], axis=2)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sd = traj.std(axis=2, ddof=1) if Z.shape[1] > 1 else np.full(traj.shape[:2], np.nan)
+    return traj, traj.mean(axis=2), sd
+
+
 def samples_to_weights(prob: Problem, z_trace: np.ndarray) -> np.ndarray:
     """``map(z -> W_swa + P*z.params, chm)`` (src/space_inference.jl:125): (n_steps, n)."""
     return np.stack([project(prob.W_swa, prob.P, z) for z in z_trace])

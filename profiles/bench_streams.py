@@ -23,12 +23,21 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     a = ap.parse_args()
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6650.0}
-    dev = torch.device("cuda", 0)
+    import os
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:       # row-sharded construction: --n is the TOTAL parameter count, each rank holds n/world rows
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        r0, r1 = ssi.shard_rows(a.n, rank, world)
+        n_total, a.n = a.n, r1 - r0
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    eng = ssi.Engine(0)
+    eng = ssi.Engine(local)
     eng.set_stream(stream.cuda_stream)
-    g = torch.Generator(device=dev).manual_seed(4)
+    g = torch.Generator(device=dev).manual_seed(4 + rank)
     w = 0.05 * torch.randn(a.n, device=dev, generator=g)
     snaps = []
     for t in range(a.K):                       # W_t = W_0 + cumulative 1e-3 N(0,1) steps
@@ -46,19 +55,44 @@ def main():
         e1.record(stream)
         stream.synchronize()
         best_push = min(best_push, e0.elapsed_time(e1) / a.K)
-        eng._check(eng._lib.ssi_swa_finish(eng._h, a.M, None, None, None, 0))
-        best_fin = min(best_fin, eng.stats().last_ms)
+        if world > 1:
+            K = eng.swa_columns()
+            G = torch.empty(K * K, dtype=torch.float64, device=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0.record(stream)
+            eng.swa_gram_dev(G.data_ptr(), False)
+            dist.all_reduce(G)                                  # on `stream` (torch's current stream): ordered after the Gram
+            out_f = eng.swa_finish_gram(a.M, G.data_ptr(), gram_exact=False, want_P=False)
+            e1.record(stream)
+            stream.synchronize()
+            assert out_f is not None, "conditioning check asked for the exact Gram"
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best_fin = min(best_fin, float(t.item()))
+        else:
+            eng._check(eng._lib.ssi_swa_finish(eng._h, a.M, None, None, None, 0))
+            best_fin = min(best_fin, eng.stats().last_ms)
+    if world > 1:
+        t = torch.tensor([best_push], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best_push = float(t.item())
+        out["n_gpus"], out["n"], out["rows_per_gpu"] = world, n_total, a.n
+        a.n = n_total                                           # aggregate bytes over all ranks
     out["swa_push_ms"] = best_push
     out["swa_push_gbs"] = 16.0 * a.n / (best_push * 1e-3) / 1e9
-    out["swa_push_frac"] = out["swa_push_gbs"] / peaks["hbm_gbs"]
+    out["swa_push_frac"] = out["swa_push_gbs"] / (peaks["hbm_gbs"] * world)
     out["finish_ms"] = best_fin                       # gram + jacobi + P
     out["finish_bytes_gb"] = (2 * 4.0 * a.n * a.K + 4.0 * a.n * a.M) / 1e9
     out["finish_gbs"] = out["finish_bytes_gb"] / (best_fin * 1e-3)
-    out["finish_frac"] = out["finish_gbs"] / peaks["hbm_gbs"]
+    out["finish_frac"] = out["finish_gbs"] / (peaks["hbm_gbs"] * world)
     st = eng.stats()
     out["gram_path"], out["gram_risk"], out["jacobi_sweeps"] = st.gram_path, st.gram_risk, st.jacobi_sweeps
-    print(json.dumps(out))
+    if rank == 0:
+        print(json.dumps(out))
     eng.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

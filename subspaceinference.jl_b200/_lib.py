@@ -57,12 +57,16 @@ SIGNATURES = {
     "ssi_mh_run_dev": (C.c_int, [_p, _i64, _i64, _u64, _i64, _dbl, _dbl, _dbl, _u32, _p, _p, _p, _p]),
     "ssi_rng_replay": (C.c_int, [_u64, _i64, _i64, _i32, _p, _p]),
     "ssi_project": (C.c_int, [_p, _p, _i64, _p]),
+    "ssi_predict_batch": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _p, _p]),
     "ssi_swa_begin": (C.c_int, [_p, _i64, _i64]),
     "ssi_swa_push": (C.c_int, [_p, _p, _dbl]),
     "ssi_swa_push_dev": (C.c_int, [_p, _p, _dbl]),
     "ssi_swa_finish": (C.c_int, [_p, _i32, _p, _p, _p, _i32]),
     "ssi_swa_columns": (_i64, [_p]),
+    "ssi_swa_gram_dev": (C.c_int, [_p, _p, _i32]),
+    "ssi_swa_finish_gram": (C.c_int, [_p, _i32, _p, _i32, _p, _p, _p, _i32]),
 }
+RETRY_EXACT = 1
 
 _lib = None
 

@@ -24,11 +24,24 @@ def _sym(s) -> str:
     return str(s).lstrip(":")
 
 
+def shard_rows(n: int, rank: int, world: int):
+    """[begin, end) of the flat-parameter rows rank owns in a row-sharded construction; multiples of 32 so
+    that every shard keeps the aligned fast paths."""
+    per = -(-n // world)
+    per = -(-per // 32) * 32
+    return min(n, rank * per), min(n, (rank + 1) * per)
+
+
 def subspace_construction(model, cost, data, opt, *, T: int = 10, c: int = 1, M: int = 3, print_freq: int = 1,
-                          engine: Engine | None = None, device: int = 0, install: bool = False):
+                          engine: Engine | None = None, device: int = 0, install: bool = False,
+                          shard: tuple[int, int] | None = None, all_reduce=None):
     """(W_swa, P) from SGD snapshots.  The per-mini-batch training step is host plumbing
     (src/subspace_construction.jl:39-43); the moment recurrence, deviation matrix, Gram,
-    eigen-solve and P = U_M S_M run on the device (:44-52, :61-65)."""
+    eigen-solve and P = U_M S_M run on the device (:44-52, :61-65).
+
+    shard=(rank, world) with all_reduce=fn: row-sharded construction over `world` GPUs.  Every rank trains the same
+    replica and pushes rows shard_rows(n, rank, world) of each snapshot; the K x K Gram is summed across ranks by
+    `all_reduce` (the only collective) and the function returns the rank's ROWS of W_swa and P."""
     if not isinstance(model, Chain):
         raise TypeError("Error: model_re function is not available for this model")   # src/libs.jl:59
     own = engine is None
@@ -37,18 +50,24 @@ def subspace_construction(model, cost, data, opt, *, T: int = 10, c: int = 1, M:
         n = int(extract_params(model).shape[0])
         n_batches = len(data)
         K_max = max(1, (T // c) * n_batches)
-        eng.swa_begin(n, K_max)
+        r0, r1 = shard_rows(n, *shard) if shard is not None else (0, n)
+        if shard is not None and (all_reduce is None or install):
+            raise ValueError("a sharded construction needs all_reduce and cannot install its (partial) subspace")
+        eng.swa_begin(r1 - r0, K_max)
         training_loss = 0.0
         for i in range(1, T + 1):
             for x, y in data:
                 training_loss = train_step(model, cost, opt, x, y)
                 if i % c == 0:
-                    eng.swa_push(extract_params(model), i / c)          # n = i/c (:46), epoch index (Q2)
+                    eng.swa_push(extract_params(model)[r0:r1], i / c)   # n = i/c (:46), epoch index (Q2)
             if i % print_freq == 0 or i == T:
                 print("Traing loss: ", training_loss, " Epoch: ", i)    # (sic) :56-58
         if install:
             eng.set_model(model.dims, model.acts)
-        W_swa, P, _ = eng.swa_finish(M, install=install)
+        if shard is not None:
+            W_swa, P, _ = eng.swa_finish_sharded(M, all_reduce)
+        else:
+            W_swa, P, _ = eng.swa_finish(M, install=install)
         return W_swa, P
     finally:
         if own:
@@ -93,6 +112,26 @@ def sub_inference(in_model, data, W_swa, P, *, σ_z: float = 1.0, σ_m: float = 
 
 
 inference = sub_inference
+
+
+def predictive(in_model, W_swa, P, z_samples, inp, *, return_trajectories: bool = True,
+               engine: Engine | None = None, device: int = 0):
+    """The sweep every docs example runs on the samples (docs/src/nn_example.md:207-216, src/plotting.jl:8-9):
+    trajectories[:, i] = re(W_swa + P z_i)(inp), their mean and (corrected) std over the samples.  `z_samples` is
+    (M, B) — e.g. sub_inference(..., return_z=True)[0][:, 0, :]; `inp` is (in0, Ng).
+    Returns (trajectories (O, Ng, B) or None, mean (O, Ng), std (O, Ng))."""
+    if not isinstance(in_model, Chain):
+        raise TypeError("Error: model_re function is not available for this model")   # src/libs.jl:59
+    own = engine is None
+    eng = engine or Engine(device)
+    try:
+        eng.set_model(in_model.dims, in_model.acts)
+        eng.set_subspace(W_swa, P)
+        out = eng.predict(z_samples, inp, return_trajectories=return_trajectories)
+        return (out[2], out[0], out[1]) if return_trajectories else (None, out[0], out[1])
+    finally:
+        if own:
+            eng.close()
 
 
 def subspace_inference(model, cost, data, opt, *, σ_z: float = 1.0, σ_m: float = 1.0, σ_p: float = 1.0,

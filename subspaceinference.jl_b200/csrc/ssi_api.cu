@@ -12,6 +12,9 @@ int ssi_mh_device(ssi_ctx*, int64_t, int64_t, uint64_t, int64_t, double, double,
 int ssi_mh_fetch_accepts(ssi_ctx*);
 int ssi_swa_push_device(ssi_ctx*, const float*, double);
 int ssi_swa_factor_device(ssi_ctx*, int, float*, double*, int*);
+int ssi_swa_gram_stage(ssi_ctx*, bool, double*, bool*);
+int ssi_swa_eigen_stage(ssi_ctx*, int, const double*, bool, bool*);
+int ssi_swa_p_stage(ssi_ctx*, int, float*, double*, int*);
 
 static std::mutex g_err_mu;
 static std::string g_create_err;
@@ -418,6 +421,40 @@ int ssi_project(ssi_ctx* ctx, const float* Z, int64_t B, float* W_out) {
     return SSI_OK;
 }
 
+int ssi_predict_batch(ssi_ctx* ctx, const float* Z, int64_t B, const float* Xg, int64_t Ng,
+                      float* preds_out, double* mean_out, double* std_out) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (!ctx->has_model || !ctx->has_sub) return ssi_fail(ctx, SSI_ERR_STATE, "model and subspace must be set before predicting");
+    if (B < 0 || Ng < 0) return ssi_fail(ctx, SSI_ERR_ARG, "B and Ng must be non-negative");
+    if (B == 0 || Ng == 0) return SSI_OK;
+    if (!Z || !Xg) return ssi_fail(ctx, SSI_ERR_ARG, "Z and Xg must be non-NULL");
+    SSI_TRY(ssi_use_device(ctx));
+    const ssi_model_t& m = ctx->model;
+    const int O = m.dims[m.L], in0 = m.dims[0];
+    const size_t ON = (size_t)O * Ng;
+    // staging: Z | Xg | mean, m2, std (doubles) | preds (optional)
+    SSI_TRY(ssi_reserve(ctx, ctx->bZ, sizeof(float) * (size_t)ctx->M * B));
+    SSI_TRY(ssi_reserve(ctx, ctx->bLp, sizeof(float) * (size_t)in0 * Ng));
+    SSI_TRY(ssi_reserve(ctx, ctx->bTerms, sizeof(double) * 3 * ON));
+    if (preds_out) SSI_TRY(ssi_reserve(ctx, ctx->bMisc, sizeof(float) * ON * (size_t)B));
+    float* dZ = (float*)ctx->bZ.p;
+    float* dXg = (float*)ctx->bLp.p;
+    double* d_mean = (double*)ctx->bTerms.p;
+    double* d_m2 = d_mean + ON;
+    double* d_std = d_m2 + ON;
+    float* d_preds = preds_out ? (float*)ctx->bMisc.p : nullptr;
+    SSI_CUDA(ctx, cudaMemcpyAsync(dZ, Z, sizeof(float) * (size_t)ctx->M * B, cudaMemcpyHostToDevice, ctx->stream));
+    SSI_CUDA(ctx, cudaMemcpyAsync(dXg, Xg, sizeof(float) * (size_t)in0 * Ng, cudaMemcpyHostToDevice, ctx->stream));
+    call_timer t(ctx);
+    const int rc = ssi_predict_device(ctx, dZ, B, dXg, Ng, d_preds, d_mean, d_std, d_m2);
+    t.stop(false);
+    if (rc != SSI_OK) return rc;
+    if (mean_out) SSI_CUDA(ctx, cudaMemcpyAsync(mean_out, d_mean, sizeof(double) * ON, cudaMemcpyDeviceToHost, ctx->stream));
+    if (std_out) SSI_CUDA(ctx, cudaMemcpyAsync(std_out, d_std, sizeof(double) * ON, cudaMemcpyDeviceToHost, ctx->stream));
+    if (preds_out) SSI_CUDA(ctx, cudaMemcpyAsync(preds_out, d_preds, sizeof(float) * ON * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    return ssi_sync(ctx);
+}
+
 int ssi_swa_begin(ssi_ctx* ctx, int64_t n, int64_t K_max) {
     if (!ctx) return SSI_ERR_ARG;
     if (n < 1 || K_max < 1) return ssi_fail(ctx, SSI_ERR_ARG, "n and K_max must be positive");
@@ -462,29 +499,18 @@ int ssi_swa_push(ssi_ctx* ctx, const float* W, double n_scalar) {
 
 int64_t ssi_swa_columns(const ssi_ctx* ctx) { return ctx ? ctx->swa_K : -1; }
 
-int ssi_swa_finish(ssi_ctx* ctx, int32_t M, float* W_swa_out, float* P_out, double* s_out, int32_t install) {
-    if (!ctx) return SSI_ERR_ARG;
-    if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
-    if (M < 1) return ssi_fail(ctx, SSI_ERR_ARG, "M must be positive");
-    SSI_TRY(ssi_use_device(ctx));
+// copies the results of a factorisation to the host and optionally installs them as the context's subspace
+static int swa_deliver(ssi_ctx* ctx, int M, float* dPout, double* ds, int sweeps_dummy, float* W_swa_out, float* P_out, double* s_out,
+                       int* sweeps, int32_t install) {
+    (void)sweeps_dummy;
     const int64_t n = ctx->swa_n;
     const int K = (int)ctx->swa_K;
-    // scratch: P (n x M floats) | s (K doubles)
-    const size_t off_s = (sizeof(float) * (size_t)n * M + 255) / 256 * 256;
-    SSI_TRY(ssi_reserve(ctx, ctx->bW, off_s + sizeof(double) * (size_t)(K > 0 ? K : 1)));
-    float* dPout = (float*)ctx->bW.p;
-    double* ds = (double*)((char*)ctx->bW.p + off_s);
-    int sweeps = 0;
-    call_timer t(ctx);
-    const int rc = ssi_swa_factor_device(ctx, M, dPout, ds, &sweeps);
-    t.stop(false);
-    if (rc != SSI_OK) return rc;
     if (W_swa_out) SSI_CUDA(ctx, cudaMemcpyAsync(W_swa_out, ctx->dSwaMean, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     if (P_out) SSI_CUDA(ctx, cudaMemcpyAsync(P_out, dPout, sizeof(float) * (size_t)n * M, cudaMemcpyDeviceToHost, ctx->stream));
     if (s_out) SSI_CUDA(ctx, cudaMemcpyAsync(s_out, ds, sizeof(double) * (size_t)K, cudaMemcpyDeviceToHost, ctx->stream));
     SSI_TRY(ssi_sync(ctx));
-    ctx->stats.jacobi_sweeps = sweeps;
-    if (sweeps >= 60) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "Jacobi eigen-solver did not converge in %d sweeps", sweeps);
+    ctx->stats.jacobi_sweeps = *sweeps;
+    if (*sweeps >= 60) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "Jacobi eigen-solver did not converge in %d sweeps", *sweeps);
     if (install) {
         if (!ctx->has_model || ctx->model.n != n)
             return ssi_fail(ctx, SSI_ERR_STATE, "install requested but the model (n=%lld) does not match the snapshots (n=%lld)",
@@ -492,6 +518,71 @@ int ssi_swa_finish(ssi_ctx* ctx, int32_t M, float* W_swa_out, float* P_out, doub
         return install_subspace(ctx, ctx->dSwaMean, dPout, n, M, cudaMemcpyDeviceToDevice);
     }
     return SSI_OK;
+}
+
+static int swa_scratch(ssi_ctx* ctx, int M, float** dPout, double** ds) {
+    const int64_t n = ctx->swa_n;
+    const int K = (int)ctx->swa_K;
+    // scratch: P (n x M floats) | s (K doubles)
+    const size_t off_s = (sizeof(float) * (size_t)n * M + 255) / 256 * 256;
+    SSI_TRY(ssi_reserve(ctx, ctx->bW, off_s + sizeof(double) * (size_t)(K > 0 ? K : 1)));
+    *dPout = (float*)ctx->bW.p;
+    *ds = (double*)((char*)ctx->bW.p + off_s);
+    return SSI_OK;
+}
+
+int ssi_swa_finish(ssi_ctx* ctx, int32_t M, float* W_swa_out, float* P_out, double* s_out, int32_t install) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
+    if (M < 1) return ssi_fail(ctx, SSI_ERR_ARG, "M must be positive");
+    SSI_TRY(ssi_use_device(ctx));
+    float* dPout;
+    double* ds;
+    SSI_TRY(swa_scratch(ctx, M, &dPout, &ds));
+    int sweeps = 0;
+    call_timer t(ctx);
+    const int rc = ssi_swa_factor_device(ctx, M, dPout, ds, &sweeps);
+    t.stop(false);
+    if (rc != SSI_OK) return rc;
+    return swa_deliver(ctx, M, dPout, ds, 0, W_swa_out, P_out, s_out, &sweeps, install);
+}
+
+int ssi_swa_gram_dev(ssi_ctx* ctx, double* dG_out, int32_t exact) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (ctx->swa_n <= 0 || ctx->swa_K <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "no snapshots have been pushed");
+    if (!dG_out) return ssi_fail(ctx, SSI_ERR_ARG, "G_out must be a device pointer to K x K doubles");
+    SSI_TRY(ssi_use_device(ctx));
+    call_timer t(ctx);
+    bool tensor = false;
+    const int rc = ssi_swa_gram_stage(ctx, exact != 0 || ctx->opt_gram_fp64 > 0, dG_out, &tensor);
+    t.stop(false);
+    ctx->stats.gram_path = tensor ? 2 : 1;
+    return rc;
+}
+
+int ssi_swa_finish_gram(ssi_ctx* ctx, int32_t M, const double* dG, int32_t gram_exact, float* W_swa_out, float* P_out,
+                        double* s_out, int32_t install) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
+    if (M < 1) return ssi_fail(ctx, SSI_ERR_ARG, "M must be positive");
+    if (!dG) return ssi_fail(ctx, SSI_ERR_ARG, "G must be a device pointer to the (all-reduced) K x K Gram");
+    if (ctx->swa_K < M) return ssi_fail(ctx, SSI_ERR_RANK, "deviation matrix has %lld columns, cannot take M=%d", (long long)ctx->swa_K, M);
+    if (M > SSI_MAX_M) return ssi_fail(ctx, SSI_ERR_ARG, "M=%d exceeds the supported maximum %d", M, SSI_MAX_M);
+    SSI_TRY(ssi_use_device(ctx));
+    float* dPout;
+    double* ds;
+    SSI_TRY(swa_scratch(ctx, M, &dPout, &ds));
+    int sweeps = 0;
+    call_timer t(ctx);
+    bool need_exact = false;
+    int rc = ssi_swa_eigen_stage(ctx, M, dG, gram_exact == 0, &need_exact);
+    if (rc != SSI_OK) return rc;
+    if (need_exact) { t.stop(false); return SSI_RETRY_EXACT; }      // same spectrum on every rank: every rank retries
+    rc = ssi_swa_p_stage(ctx, M, dPout, ds, &sweeps);
+    t.stop(false);
+    if (rc != SSI_OK) return rc;
+    if (gram_exact) ctx->stats.gram_path = 3;
+    return swa_deliver(ctx, M, dPout, ds, 0, W_swa_out, P_out, s_out, &sweeps, install);
 }
 
 }  // extern "C"

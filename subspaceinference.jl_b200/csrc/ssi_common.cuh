@@ -130,6 +130,8 @@ int ssi_use_device(ssi_ctx* ctx);
 int ssi_logpost_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m, double sigma_p,
                        double sigma_z, uint32_t mask, double* d_lp, double* d_terms);
 int ssi_project_device(ssi_ctx* ctx, const float* dZ, int64_t B, float* dW /* n x B */);
+int ssi_predict_device(ssi_ctx* ctx, const float* dZ, int64_t B, const float* dXg, int64_t Ng,
+                       float* d_preds, double* d_mean, double* d_std, double* d_m2);
 int ssi_build_first_layer_bases(ssi_ctx* ctx, float* bases, int ld);
 int ssi_subspace_gram(ssi_ctx* ctx);   // fills dSubGram after set_subspace
 // Gram of an n x K column-major FP32 matrix (ld = n) into a K x K double matrix on device

@@ -467,63 +467,113 @@ __global__ void k_singular_values(const double* __restrict__ lambda, int K, doub
     if (i < K) s[i] = sqrt(fmax(lambda[i], 0.0));
 }
 
-// Gram + eigen + P for the collected deviation matrix; leaves P (n x M) in dP_out (device),
-// singular values (K doubles) in d_s.
-int ssi_swa_factor_device(ssi_ctx* ctx, int M, float* dP_out, double* d_s, int* sweeps_host) {
-    const int64_t n = ctx->swa_n;
-    const int K = (int)ctx->swa_K;
-    if (K < M || n < M) return ssi_fail(ctx, SSI_ERR_RANK, "deviation matrix is %lld x %d, cannot take M=%d columns", (long long)n, K, M);
-    if (M > SSI_MAX_M) return ssi_fail(ctx, SSI_ERR_ARG, "M=%d exceeds the supported maximum %d", M, SSI_MAX_M);
-    if (K > 2 * JAC_MAXPAIRS) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "K=%d exceeds the eigen-solver limit %d", K, 2 * JAC_MAXPAIRS);
-    // layout of bEig: G (K*K) | V (K*K) | lambda (K) | order (K ints) | sweeps (int)
+// ---- stages of ssi_swa_finish.  Single GPU: gram -> eigen (-> exact gram -> eigen) -> P.  Row-sharded over several
+// GPUs: every rank runs the gram stage on its row shard, the host all-reduces the K x K Gram, every rank
+// runs the (replicated) eigen stage and forms the P rows of its shard.
+struct swa_eig_t {
+    double *dG, *dV, *dLam, *dRisk;
+    int *dOrder, *dSweeps;
+};
+static int swa_eig_layout(ssi_ctx* ctx, int K, swa_eig_t& e) {
+    // layout of bEig: G (K*K) | V (K*K) | lambda (K) | risk | order (K ints) | sweeps (int)
     const size_t KK = (size_t)K * K;
     SSI_TRY(ssi_reserve(ctx, ctx->bEig, sizeof(double) * (2 * KK + K + 1) + sizeof(int) * (K + 2)));
-    double* dG = (double*)ctx->bEig.p;
-    double* dV = dG + KK;
-    double* dLam = dV + KK;
-    double* dRisk = dLam + K;
-    int* dOrder = (int*)(dRisk + 1);
-    int* dSweeps = dOrder + K;
+    e.dG = (double*)ctx->bEig.p;
+    e.dV = e.dG + KK;
+    e.dLam = e.dV + KK;
+    e.dRisk = e.dLam + K;
+    e.dOrder = (int*)(e.dRisk + 1);
+    e.dSweeps = e.dOrder + K;
+    return SSI_OK;
+}
+static int swa_check_shape(ssi_ctx* ctx, int M) {
+    const int K = (int)ctx->swa_K;
+    if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
+    if (K < M) return ssi_fail(ctx, SSI_ERR_RANK, "deviation matrix has %d columns, cannot take M=%d", K, M);
+    if (M > SSI_MAX_M) return ssi_fail(ctx, SSI_ERR_ARG, "M=%d exceeds the supported maximum %d", M, SSI_MAX_M);
+    if (K > 2 * JAC_MAXPAIRS) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "K=%d exceeds the eigen-solver limit %d", K, 2 * JAC_MAXPAIRS);
+    return SSI_OK;
+}
+
+// Gram of the local deviation columns into dG_dst (K x K doubles, device).  exact = FP64 SIMT kernel.
+int ssi_swa_gram_stage(ssi_ctx* ctx, bool exact, double* dG_dst, bool* used_tensor) {
+    const int64_t n = ctx->swa_n;
+    const int K = (int)ctx->swa_K;
+    const bool tensor = !exact && ssi_gram_tc_usable(ctx, ctx->dDev, n, ctx->swa_ld, K);
+    if (used_tensor) *used_tensor = tensor;
+    return ssi_gram_device(ctx, ctx->dDev, n, ctx->swa_ld, K, dG_dst, tensor);
+}
+
+// Eigen-solve of the Gram in dG_src (device; copied, not destroyed).  With `check`, evaluates the conditioning estimate
+// of a tensor-core Gram and reports through *need_exact whether the Gram has to be recomputed exactly (synchronises).
+int ssi_swa_eigen_stage(ssi_ctx* ctx, int M, const double* dG_src, bool check, bool* need_exact) {
+    const int K = (int)ctx->swa_K;
+    swa_eig_t e;
+    SSI_TRY(swa_eig_layout(ctx, K, e));
+    if (dG_src != e.dG)
+        SSI_CUDA(ctx, cudaMemcpyAsync(e.dG, dG_src, sizeof(double) * (size_t)K * K, cudaMemcpyDeviceToDevice, ctx->stream));
     const size_t jsm = 2 * sizeof(double) * (size_t)(K | 1) * K;
     const int use_smem = jsm + 24 * 1024 <= ctx->smem_optin;
     if (use_smem) SSI_CUDA(ctx, cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm));
-    bool tensor = ssi_gram_tc_usable(ctx, ctx->dDev, n, ctx->swa_ld, K);
-    ctx->stats.gram_risk = 0.0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        SSI_TRY(ssi_gram_device(ctx, ctx->dDev, n, ctx->swa_ld, K, dG, tensor));
-        k_jacobi<<<1, 1024, use_smem ? jsm : 0, ctx->stream>>>(dG, dV, K, 60, dLam, dOrder, dSweeps, use_smem);
-        SSI_LAUNCH_CHECK(ctx);
-        if (!tensor) { ctx->stats.gram_path = attempt ? 3 : 1; break; }
-        // The tensor-core Gram is accurate to ~GRAM_TC_EPS of its largest entry.  That is ample when the M wanted
-        // directions are separated from their neighbours, but nearly degenerate eigenvalues rotate freely under such a
-        // perturbation: estimate the damage from the spectrum and redo the Gram in exact FP64 when it could exceed
-        // the 1e-4 parity bar (the estimate is pessimistic: measured errors are 0.03x-0.4x of it).  (One K-double read-back; ssi_swa_finish synchronises anyway.)
-        k_gram_risk<<<1, 32, 0, ctx->stream>>>(dLam, K, M, GRAM_TC_EPS, dRisk);
-        SSI_LAUNCH_CHECK(ctx);
-        double risk = 0.0;
-        SSI_CUDA(ctx, cudaMemcpyAsync(&risk, dRisk, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->stats.gram_risk = risk;
-        if (risk <= GRAM_TC_RISK_MAX || ctx->opt_gram_fp64 < 0) { ctx->stats.gram_path = 2; break; }
-        tensor = false;
-    }
-    k_singular_values<<<(K + 127) / 128, 128, 0, ctx->stream>>>(dLam, K, d_s);
+    k_jacobi<<<1, 1024, use_smem ? jsm : 0, ctx->stream>>>(e.dG, e.dV, K, 60, e.dLam, e.dOrder, e.dSweeps, use_smem);
+    SSI_LAUNCH_CHECK(ctx);
+    if (need_exact) *need_exact = false;
+    if (!check) return SSI_OK;
+    // The tensor-core Gram is accurate to ~GRAM_TC_EPS of its largest entry.  That is ample when the M wanted
+    // directions are separated from their neighbours, but nearly degenerate eigenvalues rotate freely under such a
+    // perturbation: estimate the damage from the spectrum and ask for the exact FP64 Gram when it could exceed the 1e-4
+    // parity bar (the estimate is pessimistic: measured errors are 0.03x-0.4x of it).  One double is read back.
+    k_gram_risk<<<1, 32, 0, ctx->stream>>>(e.dLam, K, M, GRAM_TC_EPS, e.dRisk);
+    SSI_LAUNCH_CHECK(ctx);
+    double risk = 0.0;
+    SSI_CUDA(ctx, cudaMemcpyAsync(&risk, e.dRisk, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.gram_risk = risk;
+    if (need_exact) *need_exact = (risk > GRAM_TC_RISK_MAX) && ctx->opt_gram_fp64 >= 0;
+    return SSI_OK;
+}
+
+// singular values (K doubles, device) and P rows of the local shard (n x M, device) from the last eigen stage
+int ssi_swa_p_stage(ssi_ctx* ctx, int M, float* dP_out, double* d_s, int* sweeps_host) {
+    const int64_t n = ctx->swa_n;
+    const int K = (int)ctx->swa_K;
+    swa_eig_t e;
+    SSI_TRY(swa_eig_layout(ctx, K, e));
+    k_singular_values<<<(K + 127) / 128, 128, 0, ctx->stream>>>(e.dLam, K, d_s);
     SSI_LAUNCH_CHECK(ctx);
     int rc;
-    if (M <= 4) rc = launch_form_p<4>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
-    else if (M <= 8) rc = launch_form_p<8>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
-    else if (M <= 16) rc = launch_form_p<16>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
-    else if (M <= 20) rc = launch_form_p<20>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
-    else if (M <= 24) rc = launch_form_p<24>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
-    else if (M <= 32) rc = launch_form_p<32>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
-    else if (M <= 48) rc = launch_form_p<48>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
-    else rc = launch_form_p<64>(ctx, ctx->dDev, n, ctx->swa_ld, K, dV, dOrder, M, dP_out);
+    if (M <= 4) rc = launch_form_p<4>(ctx, ctx->dDev, n, ctx->swa_ld, K, e.dV, e.dOrder, M, dP_out);
+    else if (M <= 8) rc = launch_form_p<8>(ctx, ctx->dDev, n, ctx->swa_ld, K, e.dV, e.dOrder, M, dP_out);
+    else if (M <= 16) rc = launch_form_p<16>(ctx, ctx->dDev, n, ctx->swa_ld, K, e.dV, e.dOrder, M, dP_out);
+    else if (M <= 20) rc = launch_form_p<20>(ctx, ctx->dDev, n, ctx->swa_ld, K, e.dV, e.dOrder, M, dP_out);
+    else if (M <= 24) rc = launch_form_p<24>(ctx, ctx->dDev, n, ctx->swa_ld, K, e.dV, e.dOrder, M, dP_out);
+    else if (M <= 32) rc = launch_form_p<32>(ctx, ctx->dDev, n, ctx->swa_ld, K, e.dV, e.dOrder, M, dP_out);
+    else if (M <= 48) rc = launch_form_p<48>(ctx, ctx->dDev, n, ctx->swa_ld, K, e.dV, e.dOrder, M, dP_out);
+    else rc = launch_form_p<64>(ctx, ctx->dDev, n, ctx->swa_ld, K, e.dV, e.dOrder, M, dP_out);
     if (rc != SSI_OK) return rc;
-    if (sweeps_host) {
-        SSI_CUDA(ctx, cudaMemcpyAsync(sweeps_host, dSweeps, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    }
+    if (sweeps_host) SSI_CUDA(ctx, cudaMemcpyAsync(sweeps_host, e.dSweeps, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.last_bytes = 4.0 * (double)n * K * 2 + 4.0 * (double)n * M;
     ctx->stats.last_flops = 2.0 * (double)n * K * K + 2.0 * (double)n * K * M;
     ctx->stats.last_units = 0;
     return SSI_OK;
+}
+
+// Gram + eigen + P for the collected deviation matrix; leaves P (n x M) in dP_out (device),
+// singular values (K doubles) in d_s.
+int ssi_swa_factor_device(ssi_ctx* ctx, int M, float* dP_out, double* d_s, int* sweeps_host) {
+    SSI_TRY(swa_check_shape(ctx, M));
+    if (ctx->swa_n < M) return ssi_fail(ctx, SSI_ERR_RANK, "deviation matrix is %lld x %d, cannot take M=%d columns", (long long)ctx->swa_n, (int)ctx->swa_K, M);
+    swa_eig_t e;
+    SSI_TRY(swa_eig_layout(ctx, (int)ctx->swa_K, e));
+    ctx->stats.gram_risk = 0.0;
+    bool tensor = false, need_exact = false;
+    SSI_TRY(ssi_swa_gram_stage(ctx, ctx->opt_gram_fp64 > 0, e.dG, &tensor));
+    SSI_TRY(ssi_swa_eigen_stage(ctx, M, e.dG, tensor, &need_exact));
+    ctx->stats.gram_path = tensor ? 2 : 1;
+    if (need_exact) {
+        SSI_TRY(ssi_swa_gram_stage(ctx, true, e.dG, nullptr));
+        SSI_TRY(ssi_swa_eigen_stage(ctx, M, e.dG, false, nullptr));
+        ctx->stats.gram_path = 3;
+    }
+    return ssi_swa_p_stage(ctx, M, dP_out, d_s, sweeps_host);
 }

@@ -442,6 +442,95 @@ static int run_layered(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) 
     return ssi_reduce_partials(ctx, partials, B, parts, d_sse);
 }
 
+// ======================================================================================
+// posterior-predictive sweep (the step after the path in every docs example)
+// ======================================================================================
+// Replaces, for B subspace samples at once, the user loop of docs/src/nn_example.md:207-216
+//     for i in 1:itr;  m1 = re(all_chain[i]);  trajectories[:, i] = m1(inp)';  end
+// and the moments plot_predictive takes of it (src/plotting.jl:8-9): mean(trajectories, dims=2) and
+// std(trajectories, dims=2) (Julia's corrected estimator, B-1).  The itr x n weight vectors are never materialised on
+// the host; predictions are folded into running (count, mean, M2) per grid point group by group (Chan's merge).
+__global__ void __launch_bounds__(256)
+k_pred_moments(const float* __restrict__ preds /* [G][ON] */, int G, long long ON, long long cnt_prev,
+               double* __restrict__ mean, double* __restrict__ m2) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ON) return;
+    double gm = 0.0;
+    for (int g = 0; g < G; ++g) gm += (double)preds[(long long)g * ON + e];
+    gm /= (double)G;
+    double gm2 = 0.0;
+    for (int g = 0; g < G; ++g) {
+        const double d = (double)preds[(long long)g * ON + e] - gm;
+        gm2 += d * d;
+    }
+    if (cnt_prev == 0) {
+        mean[e] = gm;
+        m2[e] = gm2;
+    } else {
+        const double tot = (double)(cnt_prev + G);
+        const double delta = gm - mean[e];
+        mean[e] += delta * (double)G / tot;
+        m2[e] += gm2 + delta * delta * (double)cnt_prev * (double)G / tot;
+    }
+}
+
+__global__ void k_pred_std(const double* __restrict__ m2, long long ON, long long B, double* __restrict__ sd) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ON) return;
+    sd[e] = B > 1 ? sqrt(m2[e] / (double)(B - 1)) : nan("");      // std of one trajectory is NaN in Julia (0/0)
+}
+
+// dZ (M x B), dXg (in0 x Ng) device; d_preds (O x Ng x B) optional; d_mean, d_std (O x Ng doubles); d_m2 scratch (O x Ng)
+int ssi_predict_device(ssi_ctx* ctx, const float* dZ, int64_t B, const float* dXg, int64_t Ng,
+                       float* d_preds, double* d_mean, double* d_std, double* d_m2) {
+    const ssi_model_t& m = ctx->model;
+    const int64_t n = m.n;
+    const int O = m.dims[m.L];
+    const long long ON = (long long)O * Ng;
+    int hid = 1;
+    for (int l = 1; l < m.L; ++l) hid = std::max(hid, m.dims[l]);
+    const double per_sample = (2.0 * hid + O) * (double)Ng * sizeof(float) + (double)n * sizeof(float);
+    int G = (int)std::max(1.0, std::min(64.0, 2e9 / per_sample));
+    G = (int)std::min<int64_t>(G, B);
+    SSI_TRY(ssi_reserve(ctx, ctx->bW, sizeof(float) * (size_t)n * G));
+    if (m.L > 1) {
+        SSI_TRY(ssi_reserve(ctx, ctx->bH0, sizeof(float) * (size_t)hid * Ng * G));
+        if (m.L > 2) SSI_TRY(ssi_reserve(ctx, ctx->bH1, sizeof(float) * (size_t)hid * Ng * G));
+    }
+    SSI_TRY(ssi_reserve(ctx, ctx->bPartials, sizeof(float) * (size_t)ON * G));
+    float* dW = (float*)ctx->bW.p;
+    float* hbuf[2] = {(float*)ctx->bH0.p, (float*)ctx->bH1.p};
+    float* pg = (float*)ctx->bPartials.p;
+    const int tiles_j = (int)((Ng + LT - 1) / LT);
+    for (int64_t b0 = 0; b0 < B; b0 += G) {
+        const int g = (int)std::min<int64_t>(G, B - b0);
+        SSI_TRY(ssi_project_device(ctx, dZ + b0 * ctx->M, g, dW));
+        const float* hin = dXg;
+        long long hin_bs = 0;
+        for (int l = 0; l < m.L; ++l) {
+            const int in = m.dims[l], out = m.dims[l + 1];
+            const bool last = (l == m.L - 1);
+            float* hout = last ? pg : hbuf[l & 1];
+            dim3 grid(tiles_j, (out + LT - 1) / LT, g);
+            k_dense_simt<false><<<grid, 256, 0, ctx->stream>>>(dW + m.w_off[l], n, dW + m.b_off[l], n, hin, hin_bs, hout,
+                                                              (long long)out * Ng, nullptr, nullptr, out, in, Ng, m.act[l], out);
+            SSI_LAUNCH_CHECK(ctx);
+            hin = hout;
+            hin_bs = (long long)out * Ng;
+        }
+        k_pred_moments<<<(unsigned)((ON + 255) / 256), 256, 0, ctx->stream>>>(pg, g, ON, b0, d_mean, d_m2);
+        SSI_LAUNCH_CHECK(ctx);
+        if (d_preds)
+            SSI_CUDA(ctx, cudaMemcpyAsync(d_preds + b0 * ON, pg, sizeof(float) * (size_t)ON * g, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    k_pred_std<<<(unsigned)((ON + 255) / 256), 256, 0, ctx->stream>>>(d_m2, ON, B, d_std);
+    SSI_LAUNCH_CHECK(ctx);
+    ctx->stats.last_units = (double)B * (double)Ng;
+    ctx->stats.last_flops = (double)B * ((double)Ng * m.flops_per_point + 2.0 * (double)n * ctx->M);
+    ctx->stats.last_bytes = 0;
+    return SSI_OK;
+}
+
 // First-layer bases for the tensor path: B_m = (column m of [P | W_swa])_layer0 applied to X, m = 0..M,
 // as FP32 pre-activations [m][N][ld] (bias parts included).  Exact FP32 SIMT GEMM, run once per (data, subspace).
 int ssi_build_first_layer_bases(ssi_ctx* ctx, float* bases, int ld) {

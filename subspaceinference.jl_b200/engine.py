@@ -7,7 +7,7 @@ from typing import Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import SsiError, Stats, TERM_LL
+from ._lib import RETRY_EXACT, SsiError, Stats, TERM_LL
 
 
 def _f32(a, order="F") -> np.ndarray:
@@ -125,6 +125,23 @@ class Engine:
         self._check(self._lib.ssi_project(self._h, _ptr(Z), Z.shape[1], _ptr(W)))
         return W
 
+    def predict(self, Z, Xg, return_trajectories: bool = False):
+        """Posterior-predictive sweep: (mean, std[, trajectories]) of re(W_swa + P z)(Xg) over the columns of Z.
+        mean/std are (O, Ng) float64 (std corrected, as Julia's), trajectories (O, Ng, B) float32."""
+        Z, Xg = _f32(Z), _f32(Xg)
+        if Z.ndim == 1:
+            Z = Z.reshape(-1, 1, order="F")
+        if Z.shape[0] != self.M:
+            raise ValueError(f"Z must have M={self.M} rows")
+        if Xg.ndim != 2 or self.dims is None or Xg.shape[0] != self.dims[0]:
+            raise ValueError("Xg must be (in0, Ng)")
+        B, Ng, O = Z.shape[1], Xg.shape[1], self.dims[-1]
+        mean = np.empty((O, Ng), np.float64, order="F")
+        std = np.empty((O, Ng), np.float64, order="F")
+        traj = np.empty((O, Ng, B), np.float32, order="F") if return_trajectories else None
+        self._check(self._lib.ssi_predict_batch(self._h, _ptr(Z), B, _ptr(Xg), Ng, _ptr(traj), _ptr(mean), _ptr(std)))
+        return (mean, std, traj) if return_trajectories else (mean, std)
+
     # ---- RWMH ------------------------------------------------------------------------------
     def mh_run(self, n_chains: int, n_steps: int, seed: int, sigma_z=1.0, sigma_m=1.0, sigma_p=1.0, mask=TERM_LL,
                chain_offset: int = 0, z0=None, want_z=True, want_lp=True, want_accept=True):
@@ -172,6 +189,42 @@ class Engine:
 
     def swa_columns(self) -> int:
         return int(self._lib.ssi_swa_columns(self._h))
+
+    def swa_gram_dev(self, dG_ptr: int, exact: bool = False):
+        """Gram of the local row shard's deviation columns into a device buffer of K x K doubles (to be all-reduced)."""
+        self._check(self._lib.ssi_swa_gram_dev(self._h, C.c_void_p(dG_ptr), int(exact)))
+
+    def swa_finish_gram(self, M: int, dG_ptr: int, gram_exact: bool = False, install: bool = False, want_P: bool = True):
+        """Eigen-solve of the all-reduced Gram + W_swa / P rows of the local shard.  Returns None when the conditioning
+        check asks for the exact Gram (SSI_RETRY_EXACT): repeat swa_gram_dev(exact=True), all-reduce, and call again
+        with gram_exact=True."""
+        n, K = self._swa_n, self.swa_columns()
+        W_swa = np.empty(n, np.float32)
+        P = np.empty((n, M), np.float32, order="F") if want_P else None
+        s = np.empty(max(K, 1), np.float64)
+        rc = self._lib.ssi_swa_finish_gram(self._h, M, C.c_void_p(dG_ptr), int(gram_exact), _ptr(W_swa), _ptr(P), _ptr(s), int(install))
+        if rc == RETRY_EXACT:
+            return None
+        self._check(rc)
+        if install:
+            self.M = M
+        return W_swa, P, s[:K]
+
+    def swa_finish_sharded(self, M: int, all_reduce, install: bool = False):
+        """Row-sharded finish: `all_reduce(tensor)` sums a CUDA float64 tensor in place across the ranks that hold the
+        other row shards (e.g. torch.distributed.all_reduce).  The only collective of the construction path."""
+        import torch
+        K = self.swa_columns()
+        G = torch.empty(K * K, dtype=torch.float64, device=f"cuda:{self.device}")
+        for exact in (False, True):
+            self.swa_gram_dev(G.data_ptr(), exact)
+            self.sync()
+            all_reduce(G)
+            torch.cuda.synchronize(self.device)
+            out = self.swa_finish_gram(M, G.data_ptr(), gram_exact=exact, install=install)
+            if out is not None:
+                return out
+        raise RuntimeError("unreachable: the exact Gram is never rejected")
 
     def swa_finish(self, M: int, install: bool = False, want_P: bool = True):
         n, K = self._swa_n, self.swa_columns()

@@ -40,3 +40,30 @@ def test_construction_then_inference_alias(ssi):
     np.testing.assert_allclose(lt[3, 19], ref, rtol=1e-5)
     with pytest.raises(ValueError):
         ssi.inference(m, data, W_swa, P, M=4)                # P has 5 columns
+
+
+@pytest.mark.parametrize("dims,acts,M,B,Ng", [
+    ((2, 200, 50, 50, 50, 1), (1, 1, 1, 1, 0), 20, 100, 100),    # the docs' network and grid (nn_example.md:112-118, 207)
+    ((10, 20, 20, 2), (0, 0, 0), 3, 10, 37),                      # README network
+    ((13, 50, 1), (1, 0), 5, 1, 5),                               # one trajectory: std is NaN, as in Julia
+    ((4, 300, 3), (2, 3), 6, 130, 1000),                          # several groups of samples
+])
+def test_posterior_predictive_sweep_vs_oracle(ssi, engine, dims, acts, M, B, Ng):
+    rng = np.random.default_rng(B + Ng)
+    n = orc.n_params(dims)
+    W_swa, P = orc.glorot_flat(rng, dims), (0.1 * rng.standard_normal((n, M))).astype(np.float32)
+    Z = rng.standard_normal((M, B)).astype(np.float32)
+    Xg = rng.uniform(-3, 3, (dims[0], Ng)).astype(np.float32)
+    engine.set_model(dims, acts)
+    engine.set_subspace(W_swa, P)                  # no data set: the sweep does not need it
+    mean, std, traj = engine.predict(Z, Xg, return_trajectories=True)
+    t_ref, m_ref, s_ref = orc.predictive_sweep(dims, acts, W_swa, P, Z, Xg)
+    scale = np.abs(t_ref).max()
+    np.testing.assert_allclose(traj, t_ref, rtol=1e-5, atol=1e-5 * scale)       # FP32 forward vs Float64 oracle
+    np.testing.assert_allclose(mean, m_ref, rtol=1e-5, atol=1e-5 * scale)
+    if B > 1:
+        np.testing.assert_allclose(std, s_ref, rtol=1e-4, atol=1e-5 * scale)
+    else:
+        assert np.isnan(std).all()
+    mean2, std2 = engine.predict(Z, Xg)            # without trajectories: same moments
+    np.testing.assert_array_equal(mean2, mean)

@@ -138,3 +138,50 @@ def test_tensor_core_gram_vs_oracle(ssi, engine, n, K, M, expect_tensor):
         if fp64 == 0 and expect_tensor is not None:
             assert (st.gram_path == 2) == expect_tensor, st.gram_risk
     engine.set_option("gram_fp64", 0)
+
+
+@pytest.mark.parametrize("n,K,M", [(1003, 12, 4), (150000, 24, 6)])
+def test_row_sharded_construction_matches_single_context(ssi, n, K, M):
+    """rows sharded over two contexts (what two ranks do), Grams summed (the all-reduce), replicated
+    eigen-solve, P rows per shard.  The stacked result must equal the single-context construction and the oracle."""
+    import torch
+    rng = np.random.default_rng(n)
+    w = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    dirs = rng.standard_normal((M + 2, n)).astype(np.float32) * (2.0 ** -np.arange(M + 2, dtype=np.float32))[:, None]
+    snaps, ns = [], []
+    for k in range(K):
+        w = w + (dirs.T @ rng.standard_normal(M + 2).astype(np.float32)) * 0.05
+        snaps.append(w.copy())
+        ns.append(float(k // 3 + 1))
+    W_ref, P_ref, s_ref, _ = orc.construct_from_snapshots(snaps, ns, M)
+    from subspaceinference_jl_b200.api import shard_rows
+    engs = [ssi.Engine(0), ssi.Engine(0)]
+    try:
+        rows = [shard_rows(n, r, 2) for r in range(2)]
+        assert rows[0][0] == 0 and rows[0][1] == rows[1][0] and rows[1][1] == n
+        for e, (b, t) in zip(engs, rows):
+            e.swa_begin(t - b, K)
+            for wk, sk in zip(snaps, ns):
+                e.swa_push(wk[b:t], sk)
+        out = None
+        for exact in (False, True):
+            Gs = [torch.empty(K * K, dtype=torch.float64, device="cuda:0") for _ in engs]
+            for e, G in zip(engs, Gs):
+                e.swa_gram_dev(G.data_ptr(), exact)
+                e.sync()
+            G = Gs[0] + Gs[1]                                  # the all-reduce
+            torch.cuda.synchronize()
+            outs = [e.swa_finish_gram(M, G.data_ptr(), gram_exact=exact) for e in engs]
+            assert (outs[0] is None) == (outs[1] is None)      # every rank takes the same decision
+            if outs[0] is not None:
+                out = outs
+                break
+        W_swa = np.concatenate([o[0] for o in out])
+        P = np.concatenate([o[1] for o in out], axis=0)
+        np.testing.assert_array_equal(out[0][2], out[1][2])    # replicated spectrum
+        assert _rel(W_swa, W_ref) < 1e-4
+        assert _rel(orc.align_signs(P.astype(np.float64), P_ref), P_ref) < 1e-4
+        np.testing.assert_allclose(out[0][2][:M], s_ref[:M], rtol=1e-4)
+    finally:
+        for e in engs:
+            e.close()

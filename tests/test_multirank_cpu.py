@@ -66,3 +66,56 @@ def test_shard_ranges_cover_everything():
             b, e = shard_range(n, r, w)
             ids += list(range(b, e))
         assert ids == list(range(n))
+
+
+def _construct_worker(rank, world, port, out_dir):
+    """Row-sharded construction with the oracle as the per-rank device: shard rows, local Gram, ONE all-reduce of the
+    K x K Gram, replicated eigen-solve, local P rows (ssi_swa_gram_dev / ssi_swa_finish_gram)."""
+    import ssi_oracle as orc
+    from subspaceinference_jl_b200.api import shard_rows
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    snaps, ns, M = _construct_case()
+    n = snaps[0].shape[0]
+    b, e = shard_rows(n, rank, world)
+    mean = np.zeros(e - b)
+    cols = []
+    for w, s in zip(snaps, ns):                      # Q2/Q4 recurrence on the shard
+        mean = (s * mean + w[b:e].astype(np.float64)) / (s + 1.0)
+        cols.append(w[b:e].astype(np.float64) - mean)
+    A = np.stack(cols, axis=1)
+    G = torch.from_numpy(A.T @ A)
+    dist.all_reduce(G)                               # the only collective of the construction path
+    lam, V = np.linalg.eigh(G.numpy())
+    order = np.argsort(-lam)[:M]
+    sizes = [shard_rows(n, r, world)[1] - shard_rows(n, r, world)[0] for r in range(world)]
+    P_rows = torch.zeros((max(sizes), M), dtype=torch.float64)        # all_gather wants equal shapes: pad the last shard
+    P_rows[:e - b] = torch.from_numpy(A @ V[:, order])
+    gathered = [torch.empty_like(P_rows) for _ in range(world)]
+    dist.all_gather(gathered, P_rows)
+    if rank == 0:
+        np.save(Path(out_dir) / "P.npy", torch.cat([g[:sz] for g, sz in zip(gathered, sizes)]).numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _construct_case():
+    rng = np.random.default_rng(3)
+    n, K, M = 301, 9, 3
+    w = rng.standard_normal(n).astype(np.float32)
+    snaps, ns = [], []
+    for k in range(K):
+        w = w + 0.1 * rng.standard_normal(n).astype(np.float32) * (1.0 + (np.arange(n) % 7 == 0))
+        snaps.append(w.copy())
+        ns.append(float(k // 2 + 1))
+    return snaps, ns, M
+
+
+def test_two_rank_row_sharded_construction(tmp_path):
+    import ssi_oracle as orc
+    port = _free_port()
+    mp.spawn(_construct_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    snaps, ns, M = _construct_case()
+    _, P_ref, _, _ = orc.construct_from_snapshots(snaps, ns, M)
+    P = np.load(tmp_path / "P.npy")
+    np.testing.assert_allclose(orc.align_signs(P, P_ref), P_ref, rtol=0, atol=1e-9 * np.abs(P_ref).max())

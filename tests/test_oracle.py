@@ -179,3 +179,32 @@ def test_golden_construction():
     np.testing.assert_allclose(W_swa, g["W_swa"], rtol=1e-12)
     np.testing.assert_allclose(orc.align_signs(P, g["P"]), g["P"], rtol=1e-8, atol=1e-12)
     np.testing.assert_allclose(s, g["s"], rtol=1e-10, atol=1e-12)
+
+
+def test_predictive_sweep_against_torch_float64():
+    """The sweep after the path (docs/src/nn_example.md:207-216, src/plotting.jl:8-9): trajectories, mean, corrected std."""
+    import torch
+    rng = np.random.default_rng(11)
+    dims, acts, M, B, Ng = (3, 8, 5, 2), (2, 1, 0), 4, 7, 13
+    n = orc.n_params(dims)
+    W_swa, P = orc.glorot_flat(rng, dims), (0.2 * rng.standard_normal((n, M))).astype(np.float32)
+    Z, Xg = rng.standard_normal((M, B)), rng.standard_normal((dims[0], Ng))
+    traj, mu, sd = orc.predictive_sweep(dims, acts, W_swa, P, Z, Xg)
+    assert traj.shape == (2, Ng, B)
+    ref = []
+    for b in range(B):
+        w = torch.from_numpy(W_swa.astype(np.float64) + P.astype(np.float64) @ Z[:, b])
+        h, off = torch.from_numpy(Xg), 0
+        for l, act in enumerate(acts):
+            i, o = dims[l], dims[l + 1]
+            Wl = w[off:off + i * o].reshape(i, o).T          # column-major (o, i)
+            off += i * o
+            h = Wl @ h + w[off:off + o][:, None]
+            off += o
+            h = [lambda x: x, torch.relu, torch.tanh, torch.sigmoid][act](h)
+        ref.append(h)
+    ref = torch.stack(ref, dim=2)
+    np.testing.assert_allclose(traj, ref.numpy(), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(mu, ref.mean(dim=2).numpy(), rtol=1e-12)
+    np.testing.assert_allclose(sd, ref.std(dim=2, unbiased=True).numpy(), rtol=1e-11)
+    assert np.isnan(orc.predictive_sweep(dims, acts, W_swa, P, Z[:, :1], Xg)[2]).all()
