@@ -13,7 +13,7 @@ module SubspaceInferenceB200
 using Flux
 using Flux: Data.DataLoader
 
-export subspace_construction, subspace_inference, sub_inference, inference
+export subspace_construction, subspace_inference, sub_inference, inference, predictive
 
 const libssi = get(ENV, "LIBSSI", joinpath(@__DIR__, "..", "lib", "libssi.so"))
 
@@ -122,6 +122,22 @@ function sub_inference(in_model, data, W_swa, P; σ_z = 1.0, σ_m = 1.0, σ_p = 
 end
 
 const inference = sub_inference
+
+# The sweep of docs/src/nn_example.md:207-216 + src/plotting.jl:8-9 on the device: trajectories[:, :, i] = re(W_swa + P z_i)(inp),
+# their mean and (corrected) std over the samples.  Z is M x B (subspace samples), inp is in0 x Ng.
+function predictive(in_model, W_swa, P, Z::AbstractMatrix, inp::AbstractMatrix; ctx::Ctx = Ctx(), trajectories::Bool = true)
+    dims, acts = describe(in_model)
+    check(ctx, ccall((:ssi_set_model, libssi), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}), ctx.h, length(acts), dims, acts))
+    check(ctx, ccall((:ssi_set_subspace, libssi), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int64, Int32),
+                     ctx.h, Float32.(W_swa), Float32.(P), length(W_swa), size(P, 2)))
+    O, Ng, B = Int(dims[end]), size(inp, 2), size(Z, 2)
+    traj = trajectories ? Array{Float32}(undef, O, Ng, B) : nothing
+    μ = Matrix{Float64}(undef, O, Ng); σ = Matrix{Float64}(undef, O, Ng)
+    check(ctx, ccall((:ssi_predict_batch, libssi), Cint,
+                     (Ptr{Cvoid}, Ptr{Float32}, Int64, Ptr{Float32}, Int64, Ptr{Float32}, Ptr{Float64}, Ptr{Float64}),
+                     ctx.h, Float32.(Z), B, Float32.(inp), Ng, trajectories ? traj : C_NULL, μ, σ))
+    return traj, μ, σ
+end
 
 function subspace_inference(model, cost, data, opt; σ_z = 1.0, σ_m = 1.0, σ_p = 1.0, itr = 1000, T = 25, c = 1,
                             M = 20, print_freq = 1, alg = :rwmh, backend = :forwarddiff, method = :subspace, kw...)
