@@ -121,6 +121,17 @@ int  ssi_logpost_batch_dev(ssi_ctx* ctx, const float* dZ, int64_t B,
                            double sigma_m, double sigma_p, double sigma_z, uint32_t prior_mask,
                            double* d_lp_out, double* d_terms_out);
 
+/* ---- l_pi_grad(theta) = (density(theta), gradient(density, theta)), batched ------------
+ * src/space_inference.jl:107 (AD backends src/libs.jl:23-34): the closure the :mala, :hmc and :nuts branches
+ * (:117-120, :139-160) hand to their samplers.  One reverse pass per sample instead of ForwardDiff's M forward passes.
+ * Z: M x B (host); lp_out: B doubles; grad_out: M x B doubles (d lp / d z), same prior_mask semantics as above.       */
+int  ssi_logpost_grad_batch(ssi_ctx* ctx, const float* Z, int64_t B,
+                            double sigma_m, double sigma_p, double sigma_z, uint32_t prior_mask,
+                            double* lp_out, double* grad_out);
+int  ssi_logpost_grad_batch_dev(ssi_ctx* ctx, const float* dZ, int64_t B,
+                                double sigma_m, double sigma_p, double sigma_z, uint32_t prior_mask,
+                                double* d_lp_out, double* d_grad_out);
+
 /* ---- sample(DensityModel(density), RWMH(MvNormal(zeros(M), sigma_z)), itr) ----------
  * src/space_inference.jl:111-116.  n_chains independent chains, global ids
  * chain_offset .. chain_offset+n_chains-1.  Sample 0 of each chain is a draw from the

@@ -173,6 +173,49 @@ def density(prob: Problem, z, sigma_m=1.0, sigma_p=1.0, sigma_z=1.0, mask=TERM_L
             + (pz if mask & TERM_PRIOR_Z else 0.0))
 
 
+def _act_deriv_from_output(h: np.ndarray, act: int) -> np.ndarray:
+    """act'(pre) written in terms of the output h = act(pre) (NNlib: identity, relu, tanh, sigmoid)."""
+    if act == 1:
+        return (h > 0).astype(np.float64)
+    if act == 2:
+        return 1.0 - h * h
+    if act == 3:
+        return h * (1.0 - h)
+    return np.ones_like(h)
+
+
+def density_and_grad(prob: Problem, z, sigma_m=1.0, sigma_p=1.0, sigma_z=1.0, mask=TERM_LL):
+    """``l_pi_grad(theta) = (density(theta), gradient(density, theta))`` (src/space_inference.jl:107), the closure of
+    the :mala/:hmc/:nuts branches.  The reference differentiates ``density`` with ForwardDiff/ReverseDiff/Zygote
+    (src/libs.jl:23-34); the derivative is restated analytically here (reverse mode through the Dense chain, then
+    ``P' grad_W``) and pinned against torch autograd and central differences in tests/test_oracle.py."""
+    z = np.asarray(z, np.float64)
+    w = project(prob.W_swa, prob.P, z)
+    layers = restructure(w, prob.dims)
+    hs = [np.asarray(prob.X, np.float64)]
+    for (W, b), act in zip(layers, prob.acts):
+        hs.append(_activate(W @ hs[-1] + b[:, None], act))
+    lp = density(prob, z, sigma_m, sigma_p, sigma_z, mask)
+    gw = np.zeros_like(w)
+    if mask & TERM_LL:
+        delta = -(hs[-1] - np.asarray(prob.Y, np.float64)) / (sigma_m * sigma_m) * _act_deriv_from_output(hs[-1], prob.acts[-1])
+        offs = layer_offsets(prob.dims)
+        for l in range(len(layers) - 1, -1, -1):
+            W, _ = layers[l]
+            w0, b0, _, dout = offs[l]
+            gw[w0:b0] = (delta @ hs[l].T).reshape(-1, order="F")       # vec(W_l) is column-major (o + i*out)
+            gw[b0:b0 + dout] = delta.sum(axis=1)
+            if l > 0:
+                delta = (W.T @ delta) * _act_deriv_from_output(hs[l], prob.acts[l - 1])
+    P = np.asarray(prob.P, np.float64)
+    g = P.T @ gw
+    if mask & TERM_PRIOR_W:
+        g = g - P.T @ w / (sigma_p * sigma_p)
+    if mask & TERM_PRIOR_Z:
+        g = g - z / (sigma_z * sigma_z)
+    return lp, g
+
+
 def logpost_batch(prob: Problem, Z, sigma_m=1.0, sigma_p=1.0, sigma_z=1.0, mask=TERM_LL):
     """Batched restatement: one ``density`` call per column of Z (M, B).
     Returns (lp (B,), terms (3, B))."""

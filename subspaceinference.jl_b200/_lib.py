@@ -53,6 +53,8 @@ SIGNATURES = {
     "ssi_set_subspace": (C.c_int, [_p, _p, _p, _i64, _i32]),
     "ssi_logpost_batch": (C.c_int, [_p, _p, _i64, _dbl, _dbl, _dbl, _u32, _p, _p]),
     "ssi_logpost_batch_dev": (C.c_int, [_p, _p, _i64, _dbl, _dbl, _dbl, _u32, _p, _p]),
+    "ssi_logpost_grad_batch": (C.c_int, [_p, _p, _i64, _dbl, _dbl, _dbl, _u32, _p, _p]),
+    "ssi_logpost_grad_batch_dev": (C.c_int, [_p, _p, _i64, _dbl, _dbl, _dbl, _u32, _p, _p]),
     "ssi_mh_run": (C.c_int, [_p, _i64, _i64, _u64, _i64, _dbl, _dbl, _dbl, _u32, _p, _p, _p, _p]),
     "ssi_mh_run_dev": (C.c_int, [_p, _i64, _i64, _u64, _i64, _dbl, _dbl, _dbl, _u32, _p, _p, _p, _p]),
     "ssi_rng_replay": (C.c_int, [_u64, _i64, _i64, _i32, _p, _p]),

@@ -152,7 +152,7 @@ int ssi_ctx_destroy(ssi_ctx* ctx) {
     cudaFree(ctx->dX); cudaFree(ctx->dY); cudaFree(ctx->dP); cudaFree(ctx->dSubGram);
     cudaFree(ctx->dSwaMean); cudaFree(ctx->dDev);
     ssi_buf_t* bufs[] = {&ctx->bZ, &ctx->bLp, &ctx->bTerms, &ctx->bPartials, &ctx->bW, &ctx->bH0, &ctx->bH1, &ctx->bGram,
-                         &ctx->bEig, &ctx->bMisc, &ctx->bMhZ, &ctx->bMhZp, &ctx->bMhLp, &ctx->bMhLpP, &ctx->bMhCnt, &ctx->bSnap};
+                         &ctx->bEig, &ctx->bMisc, &ctx->bGradW, &ctx->bGradP, &ctx->bMhZ, &ctx->bMhZp, &ctx->bMhLp, &ctx->bMhLpP, &ctx->bMhCnt, &ctx->bSnap};
     for (ssi_buf_t* b : bufs) free_buf(*b);
     for (cudaEvent_t e : ctx->kt_events) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev0);
@@ -310,6 +310,42 @@ int ssi_logpost_batch_dev(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma
     const int rc = ssi_logpost_device(ctx, dZ, B, sigma_m, sigma_p, sigma_z, prior_mask, d_lp_out, d_terms_out);
     t.stop(false);
     return rc;
+}
+
+int ssi_logpost_grad_batch_dev(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m, double sigma_p, double sigma_z,
+                               uint32_t prior_mask, double* d_lp_out, double* d_grad_out) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (B < 0 || (B > 0 && (!dZ || !d_lp_out || !d_grad_out)))
+        return ssi_fail(ctx, SSI_ERR_ARG, "Z, lp_out and grad_out must be non-NULL, B >= 0");
+    SSI_TRY(ssi_use_device(ctx));
+    call_timer t(ctx);
+    const int rc = ssi_logpost_grad_device(ctx, dZ, B, sigma_m, sigma_p, sigma_z, prior_mask, d_lp_out, d_grad_out);
+    t.stop(false);
+    return rc;
+}
+
+int ssi_logpost_grad_batch(ssi_ctx* ctx, const float* Z, int64_t B, double sigma_m, double sigma_p, double sigma_z,
+                           uint32_t prior_mask, double* lp_out, double* grad_out) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (B < 0 || (B > 0 && (!Z || !lp_out || !grad_out)))
+        return ssi_fail(ctx, SSI_ERR_ARG, "Z, lp_out and grad_out must be non-NULL, B >= 0");
+    if (!ctx->has_model || !ctx->has_data || !ctx->has_sub)
+        return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before evaluating the gradient");
+    if (B == 0) return SSI_OK;
+    SSI_TRY(ssi_use_device(ctx));
+    const size_t bz = sizeof(float) * (size_t)ctx->M * B;
+    SSI_TRY(ssi_reserve(ctx, ctx->bZ, bz));
+    SSI_TRY(ssi_reserve(ctx, ctx->bLp, sizeof(double) * (size_t)B));
+    SSI_TRY(ssi_reserve(ctx, ctx->bTerms, sizeof(double) * (size_t)ctx->M * B));
+    SSI_CUDA(ctx, cudaMemcpyAsync(ctx->bZ.p, Z, bz, cudaMemcpyHostToDevice, ctx->stream));
+    call_timer t(ctx);
+    const int rc = ssi_logpost_grad_device(ctx, (const float*)ctx->bZ.p, B, sigma_m, sigma_p, sigma_z, prior_mask,
+                                           (double*)ctx->bLp.p, (double*)ctx->bTerms.p);
+    t.stop(false);
+    if (rc != SSI_OK) return rc;
+    SSI_CUDA(ctx, cudaMemcpyAsync(lp_out, ctx->bLp.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    SSI_CUDA(ctx, cudaMemcpyAsync(grad_out, ctx->bTerms.p, sizeof(double) * (size_t)ctx->M * B, cudaMemcpyDeviceToHost, ctx->stream));
+    return ssi_sync(ctx);
 }
 
 int ssi_logpost_batch(ssi_ctx* ctx, const float* Z, int64_t B, double sigma_m, double sigma_p, double sigma_z,

@@ -67,7 +67,7 @@ struct ssi_ctx {
     double* dSubGram = nullptr;
 
     // scratch
-    ssi_buf_t bZ, bLp, bTerms, bPartials, bW, bH0, bH1, bGram, bEig, bMisc;
+    ssi_buf_t bZ, bLp, bTerms, bPartials, bW, bH0, bH1, bGram, bEig, bMisc, bGradW, bGradP;
 
     // MH state
     ssi_buf_t bMhZ, bMhZp, bMhLp, bMhLpP, bMhCnt;
@@ -130,6 +130,11 @@ int ssi_use_device(ssi_ctx* ctx);
 int ssi_logpost_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m, double sigma_p,
                        double sigma_z, uint32_t mask, double* d_lp, double* d_terms);
 int ssi_project_device(ssi_ctx* ctx, const float* dZ, int64_t B, float* dW /* n x B */);
+int ssi_logpost_finalize(ssi_ctx* ctx, const double* d_sse, const float* dZ, int64_t B, double sigma_m, double sigma_p,
+                         double sigma_z, uint32_t mask, double* d_lp, double* d_terms);
+// value and gradient (M x B doubles) of the log-posterior of B device-resident subspace points (ssi_grad.cu)
+int ssi_logpost_grad_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m, double sigma_p, double sigma_z,
+                            uint32_t mask, double* d_lp, double* d_grad);
 int ssi_predict_device(ssi_ctx* ctx, const float* dZ, int64_t B, const float* dXg, int64_t Ng,
                        float* d_preds, double* d_mean, double* d_std, double* d_m2);
 int ssi_build_first_layer_bases(ssi_ctx* ctx, float* bases, int ld);

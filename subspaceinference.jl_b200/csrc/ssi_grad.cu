@@ -1,0 +1,294 @@
+// ssi_grad.cu — value and gradient of the subspace log-posterior, batched over B subspace points.
+//
+// Replaces the reference's gradient closure  l_pi_grad(theta) = (density(theta), backend.gradient(density, theta))
+// (src/space_inference.jl:107; backends src/libs.jl:23-34: ForwardDiff by default, i.e. M dual-number forward passes
+// per gradient) that feeds the :mala, :hmc and :nuts samplers (:117-120, :139-160).  Here one reverse pass per sample:
+//
+//     W = W_swa + P z                      k_project                                  (K1)
+//     H_l = act_l(W_l H_{l-1} + b_l)       k_gemm_simt, all activations kept
+//     delta_L = -(pred - y)/sigma_m^2 * act_L'(pred)        (+ the squared error for lp)
+//     gW_l = delta_l H_{l-1}',  gb_l = rowsum(delta_l),  delta_{l-1} = (W_l' delta_l) * act_{l-1}'(H_{l-1})
+//     grad_z = P' [gW ; gb]  (+ prior terms evaluated in M-space)
+//
+// Every contraction is one launch of the same strided FP32 SIMT GEMM (64x64 tile, 4x4 per thread); reductions are
+// two-stage with a fixed order, so a sample's gradient does not depend on the rest of the batch.  FP32 storage, FP64
+// final accumulation of the squared error.  This is the correctness-first version of SURVEY 8(f)-1: any Dense chain,
+// CUDA cores only.
+#include "ssi_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+#define GT_T 64
+#define GT_K 16
+#define GT_LD 68          // padded tile rows: float4 aligned, transposed fills spread over the banks
+
+struct gemm_t {
+    // C(o, j) = sum_k A(o, k) B(k, j) for batch b = blockIdx.z; all strides in elements
+    const float* A; long long a_so, a_sk, a_sb;
+    const float* B; long long b_sk, b_sj, b_sb;
+    float* C;       long long c_so, c_sj, c_sb;
+    int O, J;
+    long long K;            // contraction length (per batch when split > 0: the last batch may be shorter)
+    long long split;        // > 0: batch b covers k in [b*split, min(K, (b+1)*split))
+    int epi;                // 0 plain, 1 bias + activation, 2 multiply by act'(Hprev(o, j))
+    int act;
+    const float* bias; long long bias_sb;
+    const float* Hprev; long long h_sb;       // indexed like C
+};
+
+__device__ __forceinline__ float act_deriv_from_output(float h, int act) {
+    switch (act) {
+        case SSI_ACT_RELU:    return h > 0.0f ? 1.0f : 0.0f;
+        case SSI_ACT_TANH:    return 1.0f - h * h;
+        case SSI_ACT_SIGMOID: return h * (1.0f - h);
+        default:              return 1.0f;
+    }
+}
+
+template <bool A_KFAST, bool B_JFAST>
+__global__ void __launch_bounds__(256)
+k_gemm_simt(const gemm_t p) {
+    __shared__ __align__(16) float As[GT_K][GT_LD];
+    __shared__ __align__(16) float Bs[GT_K][GT_LD];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int o0 = blockIdx.y * GT_T, j0 = blockIdx.x * GT_T;
+    const long long b = blockIdx.z;
+    long long k_begin = 0, k_end = p.K;
+    if (p.split > 0) { k_begin = b * p.split; k_end = min(p.K, k_begin + p.split); }
+    const float* A = p.A + (p.split > 0 ? 0 : b * p.a_sb);
+    const float* Bm = p.B + (p.split > 0 ? 0 : b * p.b_sb);
+
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+
+    for (long long k0 = k_begin; k0 < k_end; k0 += GT_K) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int idx = tid + s * 256;
+            const int o = A_KFAST ? (idx >> 4) : (idx & (GT_T - 1));
+            const int k = A_KFAST ? (idx & (GT_K - 1)) : (idx >> 6);
+            As[k][o] = (o0 + o < p.O && k0 + k < k_end) ? A[(long long)(o0 + o) * p.a_so + (k0 + k) * p.a_sk] : 0.0f;
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int idx = tid + s * 256;
+            const int j = B_JFAST ? (idx & (GT_T - 1)) : (idx >> 4);
+            const int k = B_JFAST ? (idx >> 6) : (idx & (GT_K - 1));
+            Bs[k][j] = (j0 + j < p.J && k0 + k < k_end) ? Bm[(k0 + k) * p.b_sk + (long long)(j0 + j) * p.b_sj] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GT_K; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[k][tx * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][ty * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(a[r], bb[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int j = j0 + ty * 4 + c;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int o = o0 + tx * 4 + r;
+            if (o < p.O && j < p.J) {
+                float v = acc[r][c];
+                const long long ci = (long long)o * p.c_so + (long long)j * p.c_sj;
+                if (p.epi == 1) v = ssi_act(v + p.bias[b * p.bias_sb + o], p.act);
+                else if (p.epi == 2) v *= act_deriv_from_output(p.Hprev[b * p.h_sb + ci], p.act);
+                p.C[b * p.c_sb + ci] = v;
+            }
+        }
+    }
+}
+
+static int launch_gemm(ssi_ctx* ctx, const gemm_t& g, int batches, bool a_kfast, bool b_jfast) {
+    dim3 grid((g.J + GT_T - 1) / GT_T, (g.O + GT_T - 1) / GT_T, batches);
+    if (grid.y > 65535 || grid.z > 65535) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "gradient path: shape too large for one launch");
+    if (a_kfast && b_jfast) k_gemm_simt<true, true><<<grid, 256, 0, ctx->stream>>>(g);
+    else if (a_kfast) k_gemm_simt<true, false><<<grid, 256, 0, ctx->stream>>>(g);
+    else if (b_jfast) k_gemm_simt<false, true><<<grid, 256, 0, ctx->stream>>>(g);
+    else k_gemm_simt<false, false><<<grid, 256, 0, ctx->stream>>>(g);
+    SSI_LAUNCH_CHECK(ctx);
+    return SSI_OK;
+}
+
+// delta_L(o, j) = -(pred - y) * coef * act_L'(pred), and the per-(sample, chunk) squared-error partials.
+// One block per (chunk of 256 datapoints, sample); all O outputs of a datapoint by the same thread.
+__global__ void __launch_bounds__(256)
+k_grad_delta_out(const float* __restrict__ pred, long long pred_sb, const float* __restrict__ Y, float* __restrict__ delta,
+                 long long delta_sb, long long N, int O, int act, float coef, int n_chunks,
+                 double* __restrict__ partials /* [g][n_chunks] */) {
+    __shared__ double red[32];
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long g = blockIdx.y;
+    double sse = 0.0;
+    if (j < N) {
+        for (int o = 0; o < O; ++o) {
+            const long long e = o + j * O;
+            const float pv = pred[g * pred_sb + e];
+            const float df = pv - Y[e];
+            sse += (double)df * (double)df;
+            delta[g * delta_sb + e] = -df * coef * act_deriv_from_output(pv, act);
+        }
+    }
+    const double tot = ssi_block_sum(sse, red);
+    if (threadIdx.x == 0) partials[g * n_chunks + blockIdx.x] = tot;
+}
+
+// gb(o) = sum_j delta(o, j): one warp per (sample, o), fixed order
+__global__ void __launch_bounds__(256)
+k_grad_rowsum(const float* __restrict__ delta, long long d_sb, int O, long long N, float* __restrict__ out, long long out_sb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o = blockIdx.x * 8 + warp;
+    const long long g = blockIdx.y;
+    if (o >= O) return;
+    float s = 0.0f;
+    for (long long j = lane; j < N; j += 32) s += delta[g * d_sb + o + j * O];
+    s = ssi_warp_sum(s);
+    if (lane == 0) out[g * out_sb + o] = s;
+}
+
+// grad_z(m, g) = sum_s part[s][m + g*M]  (+ prior terms), fixed order
+__global__ void k_grad_finish(const float* __restrict__ part, int S, int M, int G, const float* __restrict__ Z,
+                              const double* __restrict__ Gsub /* (M+1)x(M+1) */, double inv_sp2, double inv_sz2, uint32_t mask,
+                              double* __restrict__ grad /* M x G */) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M * G) return;
+    const int m = e % M, g = e / M;
+    double v = 0.0;
+    if (mask & SSI_TERM_LL)
+        for (int s = 0; s < S; ++s) v += (double)part[(long long)s * M * G + e];
+    if (mask & SSI_TERM_PRIOR_W) {          // -(P'W_swa + P'P z)/sigma_p^2
+        const int ld = M + 1;
+        double w = Gsub[m * ld + M];
+        for (int k = 0; k < M; ++k) w += Gsub[m * ld + k] * (double)Z[k + g * M];
+        v -= w * inv_sp2;
+    }
+    if (mask & SSI_TERM_PRIOR_Z) v -= (double)Z[m + g * M] * inv_sz2;
+    grad[e] = v;
+}
+
+int ssi_reduce_partials(ssi_ctx* ctx, const double* partials, int64_t B, int parts, double* d_out);
+int ssi_logpost_finalize(ssi_ctx* ctx, const double* d_sse, const float* dZ, int64_t B, double sigma_m, double sigma_p,
+                         double sigma_z, uint32_t mask, double* d_lp, double* d_terms);
+
+int ssi_logpost_grad_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m, double sigma_p, double sigma_z,
+                            uint32_t mask, double* d_lp, double* d_grad) {
+    if (!ctx->has_model || !ctx->has_data || !ctx->has_sub)
+        return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before evaluating the gradient");
+    if (B <= 0) return SSI_OK;
+    if (!(sigma_m > 0) || !(sigma_p > 0) || !(sigma_z > 0))
+        return ssi_fail(ctx, SSI_ERR_ARG, "sigma_m, sigma_p, sigma_z must be positive");
+    if ((mask & ~(SSI_TERM_LL | SSI_TERM_PRIOR_W | SSI_TERM_PRIOR_Z)) || mask == 0)
+        return ssi_fail(ctx, SSI_ERR_ARG, "prior_mask must be a non-empty OR of SSI_TERM_*");
+    const ssi_model_t& m = ctx->model;
+    const int64_t N = ctx->N, n = m.n;
+    const int M = ctx->M, L = m.L, O = m.dims[L];
+    if (N >= (1ll << 31) || n >= (1ll << 31)) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "gradient path: N and n must fit 31 bits");
+
+    // per-sample scratch: weights n, gradient n, activations sum(out_l) x N, two delta buffers maxw x N
+    long long act_elems = 0;
+    int maxw = 0;
+    long long h_off[SSI_MAX_LAYERS + 1];
+    h_off[0] = 0;
+    for (int l = 1; l <= L; ++l) { h_off[l] = act_elems; act_elems += (long long)m.dims[l] * N; maxw = std::max(maxw, m.dims[l]); }
+    const double per_sample = 4.0 * (2.0 * n + (double)act_elems + 2.0 * maxw * (double)N);
+    int G = (int)std::max(1.0, std::min(64.0, 6e9 / per_sample));
+    G = (int)std::min<int64_t>(G, B);
+    const long long split = 4096;                       // rows of P per partial of the final projection
+    const int S = (int)((n + split - 1) / split);
+    const int n_chunks = (int)((N + 255) / 256);
+    SSI_TRY(ssi_reserve(ctx, ctx->bW, sizeof(float) * (size_t)n * G));
+    SSI_TRY(ssi_reserve(ctx, ctx->bGradW, sizeof(float) * (size_t)n * G));
+    SSI_TRY(ssi_reserve(ctx, ctx->bH0, sizeof(float) * (size_t)act_elems * G));
+    SSI_TRY(ssi_reserve(ctx, ctx->bH1, sizeof(float) * (size_t)2 * maxw * N * G));
+    SSI_TRY(ssi_reserve(ctx, ctx->bPartials, sizeof(double) * (size_t)B * n_chunks));
+    SSI_TRY(ssi_reserve(ctx, ctx->bGradP, sizeof(float) * (size_t)S * M * G));
+    SSI_TRY(ssi_reserve(ctx, ctx->bMisc, sizeof(double) * (size_t)B));
+    float* dW = (float*)ctx->bW.p;
+    float* gW = (float*)ctx->bGradW.p;
+    float* H = (float*)ctx->bH0.p;                      // [g][act_elems]
+    float* D[2] = {(float*)ctx->bH1.p, (float*)ctx->bH1.p + (size_t)maxw * N * G};   // [g][maxw x N] each
+    double* partials = (double*)ctx->bPartials.p;
+    float* gpart = (float*)ctx->bGradP.p;
+    double* d_sse = (double*)ctx->bMisc.p;
+    const long long d_sb = (long long)maxw * N;
+    const float coef = (mask & SSI_TERM_LL) ? (float)(1.0 / (sigma_m * sigma_m)) : 0.0f;
+
+    for (int64_t b0 = 0; b0 < B; b0 += G) {
+        const int g = (int)std::min<int64_t>(G, B - b0);
+        SSI_TRY(ssi_project_device(ctx, dZ + b0 * M, g, dW));
+        // ---- forward, every activation kept ----
+        for (int l = 0; l < L; ++l) {
+            const int in = m.dims[l], out = m.dims[l + 1];
+            gemm_t q{};
+            q.A = dW + m.w_off[l]; q.a_so = 1; q.a_sk = out; q.a_sb = n;
+            q.B = l == 0 ? ctx->dX : H + h_off[l]; q.b_sk = 1; q.b_sj = in; q.b_sb = l == 0 ? 0 : act_elems;
+            q.C = H + h_off[l + 1]; q.c_so = 1; q.c_sj = out; q.c_sb = act_elems;
+            q.O = out; q.J = (int)N; q.K = in; q.split = 0;
+            q.epi = 1; q.act = m.act[l]; q.bias = dW + m.b_off[l]; q.bias_sb = n;
+            SSI_TRY(launch_gemm(ctx, q, g, false, false));
+        }
+        // ---- output delta + squared error ----
+        {
+            dim3 grid(n_chunks, g);
+            k_grad_delta_out<<<grid, 256, 0, ctx->stream>>>(H + h_off[L], act_elems, ctx->dY, D[L & 1], d_sb, N, O, m.act[L - 1], coef,
+                                                           n_chunks, partials + b0 * n_chunks);
+            SSI_LAUNCH_CHECK(ctx);
+        }
+        // ---- backward ----
+        for (int l = L - 1; l >= 0; --l) {
+            const int in = m.dims[l], out = m.dims[l + 1];
+            const float* delta = D[(l + 1) & 1];
+            // gW_l(o, i) = sum_j delta(o, j) H_{l-1}(i, j)
+            gemm_t q{};
+            q.A = delta; q.a_so = 1; q.a_sk = out; q.a_sb = d_sb;
+            q.B = l == 0 ? ctx->dX : H + h_off[l]; q.b_sk = in; q.b_sj = 1; q.b_sb = l == 0 ? 0 : act_elems;
+            q.C = gW + m.w_off[l]; q.c_so = 1; q.c_sj = out; q.c_sb = n;
+            q.O = out; q.J = in; q.K = N; q.split = 0; q.epi = 0;
+            SSI_TRY(launch_gemm(ctx, q, g, false, true));
+            dim3 rg((out + 7) / 8, g);
+            k_grad_rowsum<<<rg, 256, 0, ctx->stream>>>(delta, d_sb, out, N, gW + m.b_off[l], n);
+            SSI_LAUNCH_CHECK(ctx);
+            if (l > 0) {
+                // delta_{l-1}(i, j) = sum_o W_l(o, i) delta_l(o, j) * act_{l-1}'(H_{l-1}(i, j))
+                gemm_t r{};
+                r.A = dW + m.w_off[l]; r.a_so = out; r.a_sk = 1; r.a_sb = n;
+                r.B = delta; r.b_sk = 1; r.b_sj = out; r.b_sb = d_sb;
+                r.C = D[l & 1]; r.c_so = 1; r.c_sj = in; r.c_sb = d_sb;
+                r.O = in; r.J = (int)N; r.K = out; r.split = 0;
+                r.epi = 2; r.act = m.act[l - 1]; r.Hprev = H + h_off[l]; r.h_sb = act_elems;
+                SSI_TRY(launch_gemm(ctx, r, g, true, false));
+            }
+        }
+        // ---- grad_z = P' gW, split over rows of P, then fixed-order sum (+ priors) ----
+        {
+            gemm_t q{};
+            q.A = ctx->dP; q.a_so = n; q.a_sk = 1; q.a_sb = 0;
+            q.B = gW; q.b_sk = 1; q.b_sj = n; q.b_sb = 0;
+            q.C = gpart; q.c_so = 1; q.c_sj = M; q.c_sb = (long long)M * g;
+            q.O = M; q.J = g; q.K = n; q.split = split; q.epi = 0;
+            SSI_TRY(launch_gemm(ctx, q, S, true, false));
+            k_grad_finish<<<(M * g + 127) / 128, 128, 0, ctx->stream>>>(gpart, S, M, g, dZ + b0 * M, ctx->dSubGram,
+                                                                      1.0 / (sigma_p * sigma_p), 1.0 / (sigma_z * sigma_z), mask,
+                                                                      d_grad + b0 * M);
+            SSI_LAUNCH_CHECK(ctx);
+        }
+    }
+    SSI_TRY(ssi_reduce_partials(ctx, partials, B, n_chunks, d_sse));
+    SSI_TRY(ssi_logpost_finalize(ctx, d_sse, dZ, B, sigma_m, sigma_p, sigma_z, mask, d_lp, nullptr));
+    ctx->stats.last_units = (double)B * (double)N;
+    ctx->stats.last_flops = 3.0 * (double)B * ((double)N * m.flops_per_point) + 4.0 * (double)B * (double)n * M;
+    ctx->stats.last_bytes = 0;
+    return SSI_OK;
+}

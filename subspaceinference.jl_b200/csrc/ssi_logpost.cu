@@ -545,6 +545,26 @@ int ssi_build_first_layer_bases(ssi_ctx* ctx, float* bases, int ld) {
     return SSI_OK;
 }
 
+// SSE (+ the M-space prior terms) -> log-probabilities: the closed form of logpdf(MvNormal(vec(pred), sigma_m), vec(Y))
+int ssi_logpost_finalize(ssi_ctx* ctx, const double* d_sse, const float* dZ, int64_t B, double sigma_m, double sigma_p,
+                         double sigma_z, uint32_t mask, double* d_lp, double* d_terms) {
+    const ssi_model_t& m = ctx->model;
+    const double LOG_2PI = 1.8378770664093454835606594728112;
+    const double k = (double)m.dims[m.L] * (double)ctx->N;
+    finalize_args_t a;
+    a.c_ll = -0.5 * k * LOG_2PI - k * std::log(sigma_m);
+    a.inv2sm2 = 1.0 / (2.0 * sigma_m * sigma_m);
+    a.c_w = -0.5 * (double)m.n * LOG_2PI - (double)m.n * std::log(sigma_p);
+    a.inv2sp2 = 1.0 / (2.0 * sigma_p * sigma_p);
+    a.c_z = -0.5 * (double)ctx->M * LOG_2PI - (double)ctx->M * std::log(sigma_z);
+    a.inv2sz2 = 1.0 / (2.0 * sigma_z * sigma_z);
+    a.mask = mask;
+    a.M = ctx->M;
+    k_finalize<<<(unsigned)((B + 127) / 128), 128, 0, ctx->stream>>>(a, d_sse, dZ, ctx->dSubGram, B, d_lp, d_terms);
+    SSI_LAUNCH_CHECK(ctx);
+    return SSI_OK;
+}
+
 // ======================================================================================
 // dispatch
 // ======================================================================================
@@ -592,21 +612,8 @@ int ssi_logpost_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m,
     if (rc != SSI_OK) return rc;
     ctx->stats.last_path = path;
 
+    SSI_TRY(ssi_logpost_finalize(ctx, d_sse, dZ, B, sigma_m, sigma_p, sigma_z, mask, d_lp, d_terms));
     const ssi_model_t& m = ctx->model;
-    const double LOG_2PI = 1.8378770664093454835606594728112;
-    const double k = (double)m.dims[m.L] * (double)ctx->N;
-    finalize_args_t a;
-    a.c_ll = -0.5 * k * LOG_2PI - k * std::log(sigma_m);
-    a.inv2sm2 = 1.0 / (2.0 * sigma_m * sigma_m);
-    a.c_w = -0.5 * (double)m.n * LOG_2PI - (double)m.n * std::log(sigma_p);
-    a.inv2sp2 = 1.0 / (2.0 * sigma_p * sigma_p);
-    a.c_z = -0.5 * (double)ctx->M * LOG_2PI - (double)ctx->M * std::log(sigma_z);
-    a.inv2sz2 = 1.0 / (2.0 * sigma_z * sigma_z);
-    a.mask = mask;
-    a.M = ctx->M;
-    k_finalize<<<(unsigned)((B + 127) / 128), 128, 0, ctx->stream>>>(a, d_sse, dZ, ctx->dSubGram, B, d_lp, d_terms);
-    SSI_LAUNCH_CHECK(ctx);
-
     ctx->stats.last_units = (double)B * (double)ctx->N;
     ctx->stats.last_flops = (double)B * ((double)ctx->N * m.flops_per_point + 2.0 * (double)m.n * ctx->M);
     ctx->stats.last_bytes = 0;

@@ -116,6 +116,24 @@ class Engine:
         self._check(self._lib.ssi_logpost_batch_dev(self._h, C.c_void_p(dZ_ptr), B, sigma_m, sigma_p, sigma_z, mask,
                                                     C.c_void_p(d_lp_ptr), C.c_void_p(d_terms_ptr or None)))
 
+    def logpost_grad(self, Z, sigma_m=1.0, sigma_p=1.0, sigma_z=1.0, mask=TERM_LL):
+        """(lp (B,), grad (M, B)) — the reference's l_pi_grad closure (src/space_inference.jl:107), batched."""
+        Z = _f32(Z)
+        if Z.ndim == 1:
+            Z = Z.reshape(-1, 1, order="F")
+        if Z.shape[0] != self.M:
+            raise ValueError(f"Z must have M={self.M} rows")
+        B = Z.shape[1]
+        lp = np.empty(B, np.float64)
+        grad = np.empty((self.M, B), np.float64, order="F")
+        self._check(self._lib.ssi_logpost_grad_batch(self._h, _ptr(Z), B, sigma_m, sigma_p, sigma_z, mask, _ptr(lp), _ptr(grad)))
+        return lp, grad
+
+    def logpost_grad_dev(self, dZ_ptr: int, B: int, d_lp_ptr: int, d_grad_ptr: int, sigma_m=1.0, sigma_p=1.0, sigma_z=1.0,
+                         mask=TERM_LL):
+        self._check(self._lib.ssi_logpost_grad_batch_dev(self._h, C.c_void_p(dZ_ptr), B, sigma_m, sigma_p, sigma_z, mask,
+                                                         C.c_void_p(d_lp_ptr), C.c_void_p(d_grad_ptr)))
+
     def project(self, Z) -> np.ndarray:
         """W_swa + P z for every column of Z: (n, B)."""
         Z = _f32(Z)

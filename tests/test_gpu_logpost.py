@@ -151,3 +151,34 @@ def test_error_behaviour(ssi):
         np.testing.assert_allclose(lp, -0.5 * 12 * np.log(2 * np.pi) - 12 * np.log(2.0), rtol=1e-12)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("dims,acts,N,M,B", [
+    ((10, 20, 20, 2), (0, 0, 0), 100, 3, 5),          # README network
+    ((13, 50, 1), (1, 0), 3000, 5, 70),               # UCI shape, more than one group of samples
+    ((5, 7, 3), (2, 3), 130, 2, 9),                   # tanh / sigmoid, ragged widths
+    ((3, 1), (0,), 1, 1, 3),                          # single layer, single datapoint
+    ((33, 65, 17, 9, 4), (1, 2, 1, 0), 257, 6, 4),    # deeper chain
+    ((96, 128, 128, 10), (1, 1, 0), 300, 20, 3),      # wide-ish chain: several tiles per GEMM, split projection
+])
+def test_gradient_vs_oracle(ssi, engine, dims, acts, N, M, B):
+    """l_pi_grad (src/space_inference.jl:107) batched: value within 1e-5 relative, gradient within 1e-4 of its norm
+    (FP32 reverse pass vs the Float64 oracle), for every combination of terms."""
+    rng = np.random.default_rng(hash((dims, N, M, B, "g")) % (2 ** 32))
+    n = orc.n_params(dims)
+    prob = orc.Problem(dims, acts, rng.standard_normal((dims[0], N)).astype(np.float32),
+                       rng.standard_normal((dims[-1], N)).astype(np.float32), orc.glorot_flat(rng, dims),
+                       (0.3 * rng.standard_normal((n, M))).astype(np.float32))
+    Z = (0.5 * rng.standard_normal((M, B))).astype(np.float32)
+    _setup(engine, prob)
+    for mask in (1, 7, 2, 4):
+        lp, grad = engine.logpost_grad(Z, 0.7, 1.3, 0.9, mask=mask)
+        for b in range(B):
+            lp_ref, g_ref = orc.density_and_grad(prob, Z[:, b].astype(np.float64), 0.7, 1.3, 0.9, mask)
+            assert abs(lp[b] - lp_ref) <= RTOL * abs(lp_ref)
+            np.testing.assert_allclose(grad[:, b], g_ref, rtol=0, atol=1e-4 * max(np.linalg.norm(g_ref), 1e-12), err_msg=f"mask {mask} sample {b}")
+    # a sample's gradient does not depend on the rest of the batch
+    lp_a, g_a = engine.logpost_grad(Z[:, :2], 0.7, 1.3, 0.9, mask=7)
+    lp_b, g_b = engine.logpost_grad(Z, 0.7, 1.3, 0.9, mask=7)
+    np.testing.assert_array_equal(g_a, g_b[:, :2])
+    np.testing.assert_array_equal(lp_a, lp_b[:2])

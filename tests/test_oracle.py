@@ -208,3 +208,45 @@ def test_predictive_sweep_against_torch_float64():
     np.testing.assert_allclose(mu, ref.mean(dim=2).numpy(), rtol=1e-12)
     np.testing.assert_allclose(sd, ref.std(dim=2, unbiased=True).numpy(), rtol=1e-11)
     assert np.isnan(orc.predictive_sweep(dims, acts, W_swa, P, Z[:, :1], Xg)[2]).all()
+
+
+@pytest.mark.parametrize("dims,acts", [((3, 6, 4, 2), (2, 3, 0)), ((5, 9, 1), (1, 0)), ((4, 3), (2,))])
+def test_density_gradient_against_torch_autograd_and_central_differences(dims, acts):
+    """l_pi_grad (src/space_inference.jl:107): the analytic reverse-mode restatement vs torch autograd (Float64) and
+    central differences, with every combination of terms."""
+    import torch
+    rng = np.random.default_rng(sum(dims))
+    n, M, N = orc.n_params(dims), 4, 17
+    prob = orc.Problem(dims, acts, rng.standard_normal((dims[0], N)).astype(np.float32),
+                       rng.standard_normal((dims[-1], N)).astype(np.float32), orc.glorot_flat(rng, dims),
+                       (0.3 * rng.standard_normal((n, M))).astype(np.float32))
+    z = rng.standard_normal(M)
+    sm, sp, sz = 0.7, 1.3, 0.9
+    for mask in (1, 2, 4, 3, 7):
+        lp, g = orc.density_and_grad(prob, z, sm, sp, sz, mask)
+        assert lp == orc.density(prob, z, sm, sp, sz, mask)
+        # central differences
+        fd = np.array([(orc.density(prob, z + 1e-6 * e, sm, sp, sz, mask) - orc.density(prob, z - 1e-6 * e, sm, sp, sz, mask)) / 2e-6
+                       for e in np.eye(M)])
+        np.testing.assert_allclose(g, fd, rtol=2e-5, atol=1e-6 * max(1.0, np.abs(g).max()))
+        # torch autograd
+        zt = torch.tensor(z, dtype=torch.float64, requires_grad=True)
+        w = torch.from_numpy(prob.W_swa.astype(np.float64)) + torch.from_numpy(prob.P.astype(np.float64)) @ zt
+        h, off = torch.from_numpy(prob.X.astype(np.float64)), 0
+        for l, act in enumerate(acts):
+            i, o = dims[l], dims[l + 1]
+            Wl = w[off:off + i * o].reshape(i, o).T
+            off += i * o
+            h = Wl @ h + w[off:off + o][:, None]
+            off += o
+            h = [lambda x: x, torch.relu, torch.tanh, torch.sigmoid][act](h)
+        Y = torch.from_numpy(prob.Y.astype(np.float64))
+        tot = 0.0
+        if mask & 1:
+            tot = tot - ((h - Y) ** 2).sum() / (2 * sm * sm)
+        if mask & 2:
+            tot = tot - (w ** 2).sum() / (2 * sp * sp)
+        if mask & 4:
+            tot = tot - (zt ** 2).sum() / (2 * sz * sz)
+        tot.backward()
+        np.testing.assert_allclose(g, zt.grad.numpy(), rtol=1e-10, atol=1e-12)
