@@ -39,6 +39,8 @@ WORKLOADS = {
     "uci": ("uci", 4096, 0.1, 0.1),
     # configs[1] as the sampler runs it: a step = MH_STEPS Metropolis-Hastings steps of 4096 chains per GPU, all on the device
     "uci-mh": ("uci", 4096, 0.1, 0.01),
+    # the same with the Metropolis-adjusted Langevin sampler (value + gradient per step; units are still forward evaluations)
+    "uci-mala": ("uci", 4096, 0.1, 0.01),
 }
 MH_STEPS = 100
 
@@ -145,7 +147,8 @@ def workload_config(workload, B, world):
     dims = {"wide": (784, 1024, 1024, 10), "uci": (13, 50, 1)}[name]
     N = {"wide": 60000, "uci": 10000}[name]
     M = {"wide": 20, "uci": 5}[name]
-    what = (f"{MH_STEPS} on-device RWMH steps of {B} chains per GPU (one batched log-posterior per step)" if workload.endswith("-mh")
+    what = (f"{MH_STEPS} on-device {'MALA' if workload.endswith('-mala') else 'RWMH'} steps of {B} chains per GPU (one batched "
+            f"log-posterior{' + gradient' if workload.endswith('-mala') else ''} per step)" if workload.endswith(("-mh", "-mala"))
             else f"batched log-posterior over {B} subspace points per GPU")
     return {"workload": f"{workload}: MLP {'-'.join(map(str, dims))}, N={N}, M={M}, {what}",
             "dims": list(dims), "N": N, "M": M, "batch_per_gpu": B, "global_batch": B * world,
@@ -231,7 +234,8 @@ def main():
     d_lp = torch.empty(B, dtype=torch.float64, device=dev)
     d_lp_all = torch.empty(B * world, dtype=torch.float64, device=dev) if world > 1 else None
 
-    mh = args.workload.endswith("-mh")
+    mh = args.workload.endswith(("-mh", "-mala"))
+    mh_kind = "mala" if args.workload.endswith("-mala") else "rwmh"
     units_per_eval_batch = MH_STEPS if mh else 1
     if mh:
         d_lp_tr = torch.empty(B * MH_STEPS, dtype=torch.float64, device=dev)      # lp trace (n_chains x n_steps), stays on the device
@@ -245,7 +249,7 @@ def main():
     def step_device():
         if mh:
             eng.mh_run_dev(B, MH_STEPS, 2024, sigma_z=zs, sigma_m=sigma_m, chain_offset=rank * B, d_z0=dZ.data_ptr(),
-                           d_z_trace=d_z_tr.data_ptr(), d_lp_trace=d_lp_tr.data_ptr())
+                           d_z_trace=d_z_tr.data_ptr(), d_lp_trace=d_lp_tr.data_ptr(), kind=mh_kind)
         else:
             eng.logpost_dev(dZ.data_ptr(), B, d_lp.data_ptr(), sigma_m=sigma_m)
         if world > 1:

@@ -147,6 +147,20 @@ int  ssi_mh_run_dev(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t se
                     double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask,
                     const float* d_z0_or_null,
                     float* d_z_trace, double* d_lp_trace, uint8_t* d_accept_trace);
+/* ---- sample(DensityModel(density), MALA(x -> MvNormal((sigma_z^2/2) .* x, sigma_z)), itr; init_params=...) ---------
+ * src/space_inference.jl:117-120.  Same arguments, streams and trace layouts as ssi_mh_run.  Sample 0 is z0 (or a draw
+ * sigma_z*eps(chain,0), the reference's init_params); step t proposes z' = z + (sigma_z^2/2) grad lp(z) + sigma_z*eps(chain,t)
+ * and accepts iff -e(chain,t) < lp' - lp + log q(z|z') - log q(z'|z) with q(a|b) = N(a; b + (sigma_z^2/2) grad lp(b),
+ * sigma_z^2 I) (the Metropolis-adjusted Langevin step as AdvancedMH documents it; the pinned 0.6.2 source is not
+ * vendored).  Values and gradients come from ssi_logpost_grad_batch_dev.                              */
+int  ssi_mala_run(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+                  double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask,
+                  const float* z0_or_null,
+                  float* z_trace, double* lp_trace, uint8_t* accept_trace);
+int  ssi_mala_run_dev(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+                      double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask,
+                      const float* d_z0_or_null,
+                      float* d_z_trace, double* d_lp_trace, uint8_t* d_accept_trace);
 /* host replay of the device stream: eps_out (M floats, N(0,1)) and e_out (Exp(1)) of (chain, step) */
 int  ssi_rng_replay(uint64_t seed, int64_t chain, int64_t step, int32_t M, float* eps_out, double* e_out);
 /* map(z -> W_swa + P*z, chm) (src/space_inference.jl:125): W_out n x B column-major (host) */

@@ -57,6 +57,8 @@ SIGNATURES = {
     "ssi_logpost_grad_batch_dev": (C.c_int, [_p, _p, _i64, _dbl, _dbl, _dbl, _u32, _p, _p]),
     "ssi_mh_run": (C.c_int, [_p, _i64, _i64, _u64, _i64, _dbl, _dbl, _dbl, _u32, _p, _p, _p, _p]),
     "ssi_mh_run_dev": (C.c_int, [_p, _i64, _i64, _u64, _i64, _dbl, _dbl, _dbl, _u32, _p, _p, _p, _p]),
+    "ssi_mala_run": (C.c_int, [_p, _i64, _i64, _u64, _i64, _dbl, _dbl, _dbl, _u32, _p, _p, _p, _p]),
+    "ssi_mala_run_dev": (C.c_int, [_p, _i64, _i64, _u64, _i64, _dbl, _dbl, _dbl, _u32, _p, _p, _p, _p]),
     "ssi_rng_replay": (C.c_int, [_u64, _i64, _i64, _i32, _p, _p]),
     "ssi_project": (C.c_int, [_p, _p, _i64, _p]),
     "ssi_predict_batch": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _p, _p]),

@@ -84,9 +84,9 @@ def sub_inference(in_model, data, W_swa, P, *, σ_z: float = 1.0, σ_m: float = 
     subspace samples (materialising itr x n_chains weight vectors is what the device path
     avoids; use Engine.project on the samples you need) and lp is (n_chains, itr)."""
     a = _sym(alg)
-    if a not in _RWMH_ALIASES:
-        if a in ("mala", "advi", "hmc", "nuts"):
-            raise NotImplementedError(f"{a} is not available on the device path")
+    if a not in _RWMH_ALIASES and a != "mala":
+        if a in ("advi", "hmc", "nuts"):
+            raise NotImplementedError(f"{a} is not available on the device path (Engine.logpost_grad is its l_pi_grad)")
         raise ValueError(f"{a} is not available")                         # src/space_inference.jl:162
     if not isinstance(in_model, Chain):
         raise TypeError("Error: density function is not avaliable for this model")   # :103
@@ -101,7 +101,7 @@ def sub_inference(in_model, data, W_swa, P, *, σ_z: float = 1.0, σ_m: float = 
         eng.set_data(X, Y)
         eng.set_subspace(W_swa, P)
         zt, lt, _ = eng.mh_run(n_chains, itr, seed, sigma_z=σ_z, sigma_m=σ_m, sigma_p=σ_p, mask=prior_mask,
-                               chain_offset=chain_offset, want_accept=False)
+                               chain_offset=chain_offset, want_accept=False, kind="mala" if a == "mala" else "rwmh")
         if n_chains == 1 and not return_z:
             W = eng.project(zt[:, 0, :])                                  # map(z -> W_swa + P*z, chm)
             return [W[:, t].copy() for t in range(itr)], lt[0].copy()

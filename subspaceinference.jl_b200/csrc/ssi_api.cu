@@ -7,7 +7,7 @@
 #include <cmath>
 #include <mutex>
 
-int ssi_mh_device(ssi_ctx*, int64_t, int64_t, uint64_t, int64_t, double, double, double, uint32_t,
+int ssi_mh_device(ssi_ctx*, int, int64_t, int64_t, uint64_t, int64_t, double, double, double, uint32_t,
                   const float*, float*, double*, uint8_t*);
 int ssi_mh_fetch_accepts(ssi_ctx*);
 int ssi_swa_push_device(ssi_ctx*, const float*, double);
@@ -152,7 +152,7 @@ int ssi_ctx_destroy(ssi_ctx* ctx) {
     cudaFree(ctx->dX); cudaFree(ctx->dY); cudaFree(ctx->dP); cudaFree(ctx->dSubGram);
     cudaFree(ctx->dSwaMean); cudaFree(ctx->dDev);
     ssi_buf_t* bufs[] = {&ctx->bZ, &ctx->bLp, &ctx->bTerms, &ctx->bPartials, &ctx->bW, &ctx->bH0, &ctx->bH1, &ctx->bGram,
-                         &ctx->bEig, &ctx->bMisc, &ctx->bGradW, &ctx->bGradP, &ctx->bMhZ, &ctx->bMhZp, &ctx->bMhLp, &ctx->bMhLpP, &ctx->bMhCnt, &ctx->bSnap};
+                         &ctx->bEig, &ctx->bMisc, &ctx->bGradW, &ctx->bGradP, &ctx->bMhZ, &ctx->bMhZp, &ctx->bMhLp, &ctx->bMhLpP, &ctx->bMhCnt, &ctx->bMhG, &ctx->bSnap};
     for (ssi_buf_t* b : bufs) free_buf(*b);
     for (cudaEvent_t e : ctx->kt_events) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev0);
@@ -372,21 +372,33 @@ int ssi_logpost_batch(ssi_ctx* ctx, const float* Z, int64_t B, double sigma_m, d
     return ssi_sync(ctx);
 }
 
-int ssi_mh_run_dev(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
-                   double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* d_z0,
-                   float* d_z_trace, double* d_lp_trace, uint8_t* d_accept_trace) {
+static int mh_run_dev(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+                      double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* d_z0,
+                      float* d_z_trace, double* d_lp_trace, uint8_t* d_accept_trace) {
     if (!ctx) return SSI_ERR_ARG;
     SSI_TRY(ssi_use_device(ctx));
     call_timer t(ctx);
-    const int rc = ssi_mh_device(ctx, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask,
+    const int rc = ssi_mh_device(ctx, kind, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask,
                                  d_z0, d_z_trace, d_lp_trace, d_accept_trace);
     t.stop(false);
     return rc;
 }
+int ssi_mh_run_dev(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+                   double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* d_z0,
+                   float* d_z_trace, double* d_lp_trace, uint8_t* d_accept_trace) {
+    return mh_run_dev(ctx, 0, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask, d_z0, d_z_trace,
+                      d_lp_trace, d_accept_trace);
+}
+int ssi_mala_run_dev(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+                     double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* d_z0,
+                     float* d_z_trace, double* d_lp_trace, uint8_t* d_accept_trace) {
+    return mh_run_dev(ctx, 1, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask, d_z0, d_z_trace,
+                      d_lp_trace, d_accept_trace);
+}
 
-int ssi_mh_run(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
-               double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* z0,
-               float* z_trace, double* lp_trace, uint8_t* accept_trace) {
+static int mh_run_host(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+                       double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* z0,
+                       float* z_trace, double* lp_trace, uint8_t* accept_trace) {
     if (!ctx) return SSI_ERR_ARG;
     if (!ctx->has_model || !ctx->has_data || !ctx->has_sub)
         return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before sampling");
@@ -410,7 +422,7 @@ int ssi_mh_run(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, i
         SSI_CUDA(ctx, cudaMemcpyAsync(dz0, z0, bz0, cudaMemcpyHostToDevice, ctx->stream));
     }
     call_timer t(ctx);
-    const int rc = ssi_mh_device(ctx, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask,
+    const int rc = ssi_mh_device(ctx, kind, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask,
                                  dz0, dzt, dlt, dat);
     t.stop(false);
     if (rc != SSI_OK) return rc;
@@ -419,6 +431,18 @@ int ssi_mh_run(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, i
     if (accept_trace) SSI_CUDA(ctx, cudaMemcpyAsync(accept_trace, dat, ba, cudaMemcpyDeviceToHost, ctx->stream));
     SSI_TRY(ssi_sync(ctx));
     return ssi_mh_fetch_accepts(ctx);
+}
+int ssi_mh_run(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+               double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* z0,
+               float* z_trace, double* lp_trace, uint8_t* accept_trace) {
+    return mh_run_host(ctx, 0, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask, z0, z_trace, lp_trace,
+                       accept_trace);
+}
+int ssi_mala_run(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+                 double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* z0,
+                 float* z_trace, double* lp_trace, uint8_t* accept_trace) {
+    return mh_run_host(ctx, 1, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask, z0, z_trace, lp_trace,
+                       accept_trace);
 }
 
 int ssi_rng_replay(uint64_t seed, int64_t chain, int64_t step, int32_t M, float* eps_out, double* e_out) {

@@ -70,7 +70,7 @@ struct ssi_ctx {
     ssi_buf_t bZ, bLp, bTerms, bPartials, bW, bH0, bH1, bGram, bEig, bMisc, bGradW, bGradP;
 
     // MH state
-    ssi_buf_t bMhZ, bMhZp, bMhLp, bMhLpP, bMhCnt;
+    ssi_buf_t bMhZ, bMhZp, bMhLp, bMhLpP, bMhCnt, bMhG;
 
     // SWA / construction state
     int64_t swa_n = 0, swa_Kmax = 0, swa_K = 0;

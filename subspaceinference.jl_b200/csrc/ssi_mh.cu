@@ -14,9 +14,10 @@
 #include <algorithm>
 
 // zp[m,c] = z[m,c] + sigma_z * eps(chain_off + c, step, m); with init: z = 0.
+// With a gradient (MALA): zp = (z + float(sigma_z^2/2 * grad)) + sigma_z * eps.
 __global__ void __launch_bounds__(256)
 k_mh_propose(const float* __restrict__ z, float* __restrict__ zp, long long n_chains, int M, unsigned long long seed,
-             long long chain_off, unsigned step, float sigma_z, int init) {
+             long long chain_off, unsigned step, float sigma_z, int init, const double* __restrict__ grad, double half_s2) {
     // one thread per (chain, block of 4 normals)
     const int nblk = (M + 3) >> 2;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -29,7 +30,8 @@ k_mh_propose(const float* __restrict__ z, float* __restrict__ zp, long long n_ch
     for (int r = 0; r < 4; ++r) {
         const int m = blk * 4 + r;
         if (m < M) {
-            const float base = init ? 0.0f : z[m + c * M];
+            float base = init ? 0.0f : z[m + c * M];
+            if (grad && !init) base = __fadd_rn(base, (float)(half_s2 * grad[m + c * M]));
             zp[m + c * M] = __fmaf_rn(sigma_z, e[r], base);
         }
     }
@@ -40,7 +42,8 @@ __global__ void __launch_bounds__(256)
 k_mh_accept(float* __restrict__ z, const float* __restrict__ zp, double* __restrict__ lp, const double* __restrict__ lpp,
             long long n_chains, int M, unsigned long long seed, long long chain_off, unsigned step, int force,
             float* __restrict__ z_trace, double* __restrict__ lp_trace, unsigned char* __restrict__ acc_trace,
-            unsigned long long* __restrict__ n_acc) {
+            unsigned long long* __restrict__ n_acc,
+            double* __restrict__ g, const double* __restrict__ gp, double half_s2, double inv2s2) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned accepted = 0;
     if (c < n_chains) {
@@ -49,12 +52,25 @@ k_mh_accept(float* __restrict__ z, const float* __restrict__ zp, double* __restr
             acc = true;
         } else {
             const double e = ssi_exp1(seed, (uint32_t)(chain_off + c), step);
-            const double log_alpha = lpp[c] - lp[c];
+            double log_alpha = lpp[c] - lp[c];
+            if (g) {
+                // MALA: + log q(z | z') - log q(z' | z),  q(a | b) = N(a; b + (sigma^2/2) grad(b), sigma^2 I)
+                double fwd = 0.0, rev = 0.0;
+                for (int m = 0; m < M; ++m) {
+                    const double a = (double)z[m + c * M], b = (double)zp[m + c * M];
+                    const double df = b - a - half_s2 * g[m + c * M];
+                    const double dr = a - b - half_s2 * gp[m + c * M];
+                    fwd += df * df;
+                    rev += dr * dr;
+                }
+                log_alpha += (fwd - rev) * inv2s2;
+            }
             acc = (-e < log_alpha);          // NaN proposal density -> reject
         }
         if (acc) {
             lp[c] = lpp[c];
             for (int m = 0; m < M; ++m) z[m + c * M] = zp[m + c * M];
+            if (g) for (int m = 0; m < M; ++m) g[m + c * M] = gp[m + c * M];
         }
         if (z_trace) {
             float* dst = z_trace + ((long long)step * n_chains + c) * M;
@@ -68,7 +84,11 @@ k_mh_accept(float* __restrict__ z, const float* __restrict__ zp, double* __restr
     if ((threadIdx.x & 31) == 0 && warp_cnt) atomicAdd(n_acc, (unsigned long long)warp_cnt);
 }
 
-int ssi_mh_device(ssi_ctx* ctx, int64_t C, int64_t S, uint64_t seed, int64_t chain_off,
+// kind 0: RWMH (src/space_inference.jl:113-116).  kind 1: MALA (:117-120,
+//   `MALA(x -> MvNormal((sigma_z^2 / 2) .* x, sigma_z))`, init_params = rand(MvNormal(zeros(M), sigma_z))): the proposal is
+//   z' = z + (sigma_z^2/2) grad lp(z) + sigma_z eps, accepted iff -e < lp' - lp + log q(z|z') - log q(z'|z); value and
+//   gradient of every chain's proposal come from one batched reverse pass (ssi_logpost_grad_device) per step.
+int ssi_mh_device(ssi_ctx* ctx, int kind, int64_t C, int64_t S, uint64_t seed, int64_t chain_off,
                   double sigma_z, double sigma_m, double sigma_p, uint32_t mask,
                   const float* d_z0, float* d_ztr, double* d_lptr, uint8_t* d_acctr) {
     if (!ctx->has_model || !ctx->has_data || !ctx->has_sub)
@@ -82,6 +102,13 @@ int ssi_mh_device(ssi_ctx* ctx, int64_t C, int64_t S, uint64_t seed, int64_t cha
     SSI_TRY(ssi_reserve(ctx, ctx->bMhLp, sizeof(double) * (size_t)C));
     SSI_TRY(ssi_reserve(ctx, ctx->bMhLpP, sizeof(double) * (size_t)C));
     SSI_TRY(ssi_reserve(ctx, ctx->bMhCnt, sizeof(unsigned long long)));
+    double *g = nullptr, *gp = nullptr;
+    if (kind == 1) {
+        SSI_TRY(ssi_reserve(ctx, ctx->bMhG, sizeof(double) * 2 * (size_t)M * C));
+        g = (double*)ctx->bMhG.p;
+        gp = g + (size_t)M * C;
+    }
+    const double half_s2 = 0.5 * sigma_z * sigma_z, inv2s2 = 1.0 / (2.0 * sigma_z * sigma_z);
     float* z = (float*)ctx->bMhZ.p;
     float* zp = (float*)ctx->bMhZp.p;
     double* lp = (double*)ctx->bMhLp.p;
@@ -100,14 +127,15 @@ int ssi_mh_device(ssi_ctx* ctx, int64_t C, int64_t S, uint64_t seed, int64_t cha
         if (t == 0 && d_z0) {
             SSI_CUDA(ctx, cudaMemcpyAsync(zp, d_z0, sizeof(float) * (size_t)M * C, cudaMemcpyDeviceToDevice, ctx->stream));
         } else {
-            k_mh_propose<<<g_prop, 256, 0, ctx->stream>>>(z, zp, C, M, seed, chain_off, (unsigned)t, (float)sigma_z, t == 0);
+            k_mh_propose<<<g_prop, 256, 0, ctx->stream>>>(z, zp, C, M, seed, chain_off, (unsigned)t, (float)sigma_z, t == 0, g, half_s2);
             SSI_LAUNCH_CHECK(ctx);
         }
-        SSI_TRY(ssi_logpost_device(ctx, zp, C, sigma_m, sigma_p, sigma_z, mask, lpp, nullptr));
+        if (kind == 1) SSI_TRY(ssi_logpost_grad_device(ctx, zp, C, sigma_m, sigma_p, sigma_z, mask, lpp, gp));
+        else SSI_TRY(ssi_logpost_device(ctx, zp, C, sigma_m, sigma_p, sigma_z, mask, lpp, nullptr));
         units += ctx->stats.last_units;
         flops += ctx->stats.last_flops;
         k_mh_accept<<<g_acc, 256, 0, ctx->stream>>>(z, zp, lp, lpp, C, M, seed, chain_off, (unsigned)t, t == 0,
-                                                  d_ztr, d_lptr, d_acctr, cnt);
+                                                  d_ztr, d_lptr, d_acctr, cnt, g, gp, half_s2, inv2s2);
         SSI_LAUNCH_CHECK(ctx);
     }
     ctx->stats.last_units = units;

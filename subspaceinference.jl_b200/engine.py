@@ -162,7 +162,7 @@ class Engine:
 
     # ---- RWMH ------------------------------------------------------------------------------
     def mh_run(self, n_chains: int, n_steps: int, seed: int, sigma_z=1.0, sigma_m=1.0, sigma_p=1.0, mask=TERM_LL,
-               chain_offset: int = 0, z0=None, want_z=True, want_lp=True, want_accept=True):
+               chain_offset: int = 0, z0=None, want_z=True, want_lp=True, want_accept=True, kind: str = "rwmh"):
         """Returns (z_trace (M, n_chains, n_steps) f32, lp_trace (n_chains, n_steps) f64,
         accept (n_chains, n_steps) u8); entries not requested are None."""
         zt = np.empty((self.M, n_chains, n_steps), np.float32, order="F") if want_z else None
@@ -171,14 +171,20 @@ class Engine:
         z0a = _f32(z0) if z0 is not None else None
         if z0a is not None and z0a.shape != (self.M, n_chains):
             raise ValueError("z0 must be (M, n_chains)")
-        self._check(self._lib.ssi_mh_run(self._h, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, mask,
-                                         _ptr(z0a), _ptr(zt), _ptr(lt), _ptr(at)))
+        fn = {"rwmh": self._lib.ssi_mh_run, "mala": self._lib.ssi_mala_run}[kind]
+        self._check(fn(self._h, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, mask,
+                       _ptr(z0a), _ptr(zt), _ptr(lt), _ptr(at)))
         return zt, lt, at
+
+    def mala_run(self, *a, **kw):
+        """MALA with the same arguments as mh_run (src/space_inference.jl:117-120)."""
+        return self.mh_run(*a, kind="mala", **kw)
 
     def mh_run_dev(self, n_chains: int, n_steps: int, seed: int, sigma_z=1.0, sigma_m=1.0, sigma_p=1.0, mask=TERM_LL,
                    chain_offset: int = 0, d_z0: int | None = None, d_z_trace: int | None = None,
-                   d_lp_trace: int | None = None, d_accept: int | None = None):
-        self._check(self._lib.ssi_mh_run_dev(self._h, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, mask,
+                   d_lp_trace: int | None = None, d_accept: int | None = None, kind: str = "rwmh"):
+        fn = {"rwmh": self._lib.ssi_mh_run_dev, "mala": self._lib.ssi_mala_run_dev}[kind]
+        self._check(fn(self._h, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, mask,
                                              C.c_void_p(d_z0 or None), C.c_void_p(d_z_trace or None),
                                              C.c_void_p(d_lp_trace or None), C.c_void_p(d_accept or None)))
 

@@ -113,3 +113,44 @@ def test_many_chains_full_c2(ssi, engine):
     pick = [0, 1, 2047, 4095]
     _check_against_oracle(prob, zt[:, pick, :], lt[pick], at[pick], seed, 0.01, 0.1, pick)
     assert np.isfinite(lt).all()
+
+
+@pytest.mark.parametrize("name,N,sigma_z,sigma_m", [("uci", 1500, 0.02, 0.1), ("readme", None, 0.45, 1.0)])
+def test_mala_decisions_teacher_forced(ssi, engine, name, N, sigma_z, sigma_m):
+    """MALA (src/space_inference.jl:117-120) on the device vs the oracle, teacher-forced: from the device's own state at
+    t-1 the Float64 oracle, on the replayed stream, must propose the same point (up to the FP32 gradient in the drift)
+    and take the same decision unless the margin is a near tie."""
+    prob = orc.make_problem(name, N=N) if N else orc.make_problem(name)
+    _setup(engine, prob)
+    C, S, seed = 5, 25, 77
+    zt, lt, at = engine.mala_run(C, S, seed, sigma_z=sigma_z, sigma_m=sigma_m)
+    near_ties = 0
+    for c in range(C):
+        z = zt[:, c, :].T
+        np.testing.assert_array_equal(z[0], orc.propose_f32(np.zeros(prob.M, np.float32), sigma_z, orc.rng_normals(seed, c, 0, prob.M)))
+        assert at[c, 0] == 1
+        for t in range(1, S):
+            lp_prev, g_prev = orc.density_and_grad(prob, z[t - 1], sigma_m)
+            zp = orc.mala_propose_f32(z[t - 1], g_prev, sigma_z, orc.rng_normals(seed, c, t, prob.M))
+            lp_prop, g_prop = orc.density_and_grad(prob, zp, sigma_m)
+            margin = orc.mala_log_alpha(z[t - 1], zp, lp_prev, lp_prop, g_prev, g_prop, sigma_z) + orc.rng_exponential(seed, c, t)
+            np.testing.assert_allclose(lt[c, t - 1], lp_prev, rtol=1e-5)
+            if abs(margin) <= 1e-5 * max(1.0, abs(lp_prev)):       # the drift carries an FP32 gradient: wider tie band than RWMH
+                near_ties += 1
+                continue
+            assert bool(at[c, t]) == (margin > 0), f"decision differs at chain {c} step {t}, margin {margin}"
+            expect = zp if margin > 0 else z[t - 1]
+            drift = 0.5 * sigma_z ** 2 * np.abs(g_prev).max()
+            np.testing.assert_allclose(z[t], expect, rtol=0, atol=2e-4 * drift + np.abs(expect).max() * 2.4e-7 + 1e-12)
+    assert near_ties <= 3
+    assert 0 < at[:, 1:].mean() < 1          # both outcomes are exercised
+
+
+def test_mala_chain_sharding_is_bitwise_invariant(ssi, engine):
+    prob = orc.make_problem("uci", N=1000)
+    _setup(engine, prob)
+    full = engine.mala_run(12, 10, 5, sigma_z=0.02, sigma_m=0.1)
+    a = engine.mala_run(6, 10, 5, sigma_z=0.02, sigma_m=0.1, chain_offset=0)
+    b = engine.mala_run(6, 10, 5, sigma_z=0.02, sigma_m=0.1, chain_offset=6)
+    np.testing.assert_array_equal(full[0], np.concatenate([a[0], b[0]], axis=1))
+    np.testing.assert_array_equal(full[1], np.concatenate([a[1], b[1]], axis=0))
