@@ -174,6 +174,145 @@ k_logpost_basis1h(const b1_params p, const int act_hidden) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// value + gradient for the same shape with a scalar output (O = 1): forward-mode tangents in registers.
+//   d pred / d z_m = pb2_m + sum_j [ P2_m[j] h_j + w2_j act'(h_j) B_m(x)[j] ]
+// is accumulated next to pred in the same pass over the hidden units (2M more packed FMAs per unit and hidden unit), then
+//   d lp / d z_m = sum_i e_i * d pred_i / d z_m,   e_i = -(pred_i - y_i)/sigma_m^2 * act_out'(pred_i),
+// is reduced over the tile's datapoints with warp shuffles: one float partial per (tile, sample, m), summed in fixed
+// order by k_grad_finish.  This is what l_pi_grad (src/space_inference.jl:107) costs on this path: ~2.5x a density
+// evaluation instead of ForwardDiff's M+1 forward passes.  Same mapping as k_logpost_basis1h with ST = 4 samples per warp
+// pass (the tangents need M x 4 more accumulators).
+#define B1G_ST 4
+template <int M, int ACT>
+__global__ void __launch_bounds__(B1_THREADS, 2)
+k_logpost_basis1h_grad(const b1_params p, const int act_hidden, const float coef, float* __restrict__ gpart, const long long slab) {
+    constexpr int ST = B1G_ST;
+    extern __shared__ float4 b1_smem4[];
+    const int H = p.H;
+    float* sB = reinterpret_cast<float*>(b1_smem4);           // [H][M+1][64]
+    float* sP2 = sB + (size_t)H * (M + 1) * B1_TI;            // [M+1][w2n]: second-layer rows of [P | W_swa] (j), bias at j = H
+    float* sW2 = sP2 + (M + 1) * p.w2n;                       // per warp [H+1][ST]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int s_begin = blockIdx.y * p.s_per_cta;
+    const int s_end = min(p.S, s_begin + p.s_per_cta);
+    {
+        const float4* src = reinterpret_cast<const float4*>(p.tiles + (size_t)tile * H * (M + 1) * B1_TI);
+        float4* dst = reinterpret_cast<float4*>(sB);
+        const int n4 = H * (M + 1) * B1_TI / 4;
+        for (int e = tid; e < n4; e += B1_THREADS) dst[e] = __ldg(src + e);
+        for (int e = tid; e < (M + 1) * p.w2n; e += B1_THREADS) {
+            const int m = e / p.w2n, j = e - m * p.w2n;
+            float v = 0.0f;
+            if (j <= H) v = p.PW[(j < H ? p.w2_off + j : p.b2_off) + (long long)m * p.n];
+            sP2[e] = v;
+        }
+    }
+    __syncthreads();
+    const long long i0 = (long long)tile * B1_TI + 2 * lane;
+    const float y0 = i0 < p.N ? p.Y[i0] : 0.0f, y1 = i0 + 1 < p.N ? p.Y[i0 + 1] : 0.0f;
+    float* w2s = sW2 + warp * ((H + 1) * ST);
+    const float* bl = sB + 2 * lane;
+
+    for (int s0 = s_begin + warp * ST; s0 < s_end; s0 += B1_WARPS * ST) {
+        __syncwarp();
+        for (int e = lane; e < (H + 1) * ST; e += 32) {
+            const int t = e % ST, j = e / ST;
+            const int s = min(s0 + t, p.S - 1);
+            float v = sP2[M * p.w2n + j];
+#pragma unroll
+            for (int m = 0; m < M; ++m) v = fmaf(sP2[m * p.w2n + j], p.Z[(long long)s * M + m], v);
+            w2s[e] = v;
+        }
+        __syncwarp();
+        float2 z2[ST / 2][M];
+#pragma unroll
+        for (int t = 0; t < ST; t += 2) {
+            const int sa = min(s0 + t, p.S - 1), sb = min(s0 + t + 1, p.S - 1);
+#pragma unroll
+            for (int m = 0; m < M; ++m) z2[t / 2][m] = make_float2(c_b1z[sa * M + m], c_b1z[sb * M + m]);
+        }
+        float2 pred[ST / 2][2];          // [sample pair][datapoint]
+        float2 dp[ST / 2][2][M];         // d pred / d z_m (without the bias row, added at the end)
+#pragma unroll
+        for (int t = 0; t < ST / 2; ++t)
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                pred[t][d] = make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int m = 0; m < M; ++m) dp[t][d][m] = make_float2(0.0f, 0.0f);
+            }
+
+#pragma unroll 1
+        for (int j = 0; j < H; ++j) {
+            float2 b[M + 1];
+#pragma unroll
+            for (int m = 0; m <= M; ++m) b[m] = *reinterpret_cast<const float2*>(bl + (j * (M + 1) + m) * B1_TI);
+            const float4 w4 = *reinterpret_cast<const float4*>(w2s + j * ST);
+            const float2 wp[2] = {make_float2(w4.x, w4.y), make_float2(w4.z, w4.w)};
+            float p2[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) p2[m] = sP2[m * p.w2n + j];
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+#pragma unroll
+                for (int t = 0; t < ST / 2; ++t) {
+                    const float bM = d ? b[M].y : b[M].x;
+                    float2 x = make_float2(bM, bM);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) { const float bv = d ? b[m].y : b[m].x; x = __ffma2_rn(make_float2(bv, bv), z2[t][m], x); }
+                    float2 h, c;
+                    h.x = b1_act<ACT>(x.x, act_hidden);
+                    h.y = b1_act<ACT>(x.y, act_hidden);
+                    const int a = ACT < 0 ? act_hidden : ACT;
+                    c.x = wp[t].x * act_deriv_from_output(h.x, a);       // w2_j act'(h_j)
+                    c.y = wp[t].y * act_deriv_from_output(h.y, a);
+                    pred[t][d] = __ffma2_rn(h, wp[t], pred[t][d]);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const float bv = d ? b[m].y : b[m].x;
+                        dp[t][d][m] = __ffma2_rn(h, make_float2(p2[m], p2[m]), dp[t][d][m]);
+                        dp[t][d][m] = __ffma2_rn(c, make_float2(bv, bv), dp[t][d][m]);
+                    }
+                }
+            }
+        }
+        // residuals, squared error, e_i, and the reduction of e_i * d pred_i / d z_m over the tile's datapoints
+#pragma unroll
+        for (int t = 0; t < ST; ++t) {
+            const float b2 = w2s[H * ST + t];
+            double sse = 0.0;
+            float g[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) g[m] = 0.0f;
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                if (i0 + d < p.N) {
+                    const float pv = ssi_act(((t & 1) ? pred[t / 2][d].y : pred[t / 2][d].x) + b2, p.act_out);
+                    const float df = pv - (d ? y1 : y0);
+                    sse += (double)df * (double)df;
+                    const float e = -df * coef * act_deriv_from_output(pv, p.act_out);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const float dpm = ((t & 1) ? dp[t / 2][d][m].y : dp[t / 2][d][m].x) + sP2[m * p.w2n + H];   // + pb2_m
+                        g[m] = fmaf(e, dpm, g[m]);
+                    }
+                }
+            }
+            sse = ssi_warp_sum(sse);
+#pragma unroll
+            for (int m = 0; m < M; ++m) g[m] = ssi_warp_sum(g[m]);
+            if (lane == 0 && s0 + t < s_end) {
+                p.partials[(long long)(s0 + t) * p.n_tiles + tile] = sse;
+                float* dst = gpart + (long long)tile * slab + (long long)(s0 + t) * M;
+#pragma unroll
+                for (int m = 0; m < M; ++m) dst[m] = g[m];
+            }
+        }
+    }
+}
+
 // tiles[tile][j][m][ii] = bases[m][tile*64 + ii][j]  (zero beyond N): one-time re-layout so that a CTA's
 // basis tile is one contiguous block
 __global__ void __launch_bounds__(256)
@@ -281,6 +420,84 @@ static b1_kernel_t b1_pick(int M, int act) {
 }
 
 int ssi_reduce_partials(ssi_ctx* ctx, const double* partials, int64_t B, int parts, double* d_out);
+
+typedef void (*b1g_kernel_t)(const b1_params, const int, const float, float*, const long long);
+template <int M>
+static b1g_kernel_t b1g_pick_act(int act) {
+    switch (act) {
+        case SSI_ACT_RELU: return k_logpost_basis1h_grad<M, SSI_ACT_RELU>;
+        case SSI_ACT_TANH: return k_logpost_basis1h_grad<M, SSI_ACT_TANH>;
+        default:           return k_logpost_basis1h_grad<M, -1>;
+    }
+}
+static b1g_kernel_t b1g_pick(int M, int act) {
+    switch (M) {
+        case 1: return b1g_pick_act<1>(act);
+        case 2: return b1g_pick_act<2>(act);
+        case 3: return b1g_pick_act<3>(act);
+        case 4: return b1g_pick_act<4>(act);
+        case 5: return b1g_pick_act<5>(act);
+        case 6: return b1g_pick_act<6>(act);
+        case 7: return b1g_pick_act<7>(act);
+        case 8: return b1g_pick_act<8>(act);
+        default: return nullptr;
+    }
+}
+
+static size_t b1g_smem_bytes(const ssi_ctx* ctx) {
+    const ssi_model_t& m = ctx->model;
+    const int H = m.dims[1], M = ctx->M;
+    const int w2n = (H + 1 + 3) / 4 * 4;
+    return sizeof(float) * ((size_t)H * (M + 1) * B1_TI + (size_t)(M + 1) * w2n + (size_t)B1_WARPS * (H + 1) * B1G_ST);
+}
+
+// the fast value+gradient path: one hidden layer, scalar output, M <= 8 (tangent accumulators live in registers)
+bool ssi_b1_grad_supported(const ssi_ctx* ctx) {
+    return ssi_b1_supported(ctx) && ctx->model.dims[2] == 1 && ctx->M <= 8 && b1g_smem_bytes(ctx) <= 110 * 1024;
+}
+
+int ssi_b1_grad_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double coef, double* d_sse, float** d_gpart, int* n_parts) {
+    SSI_TRY(ssi_b1_prepare(ctx));
+    ssi_b1_state* s = ctx->b1;
+    const ssi_model_t& m = ctx->model;
+    const int M = ctx->M, H = m.dims[1];
+    b1g_kernel_t kern = b1g_pick(M, m.act[0]);
+    if (!kern) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "basis gradient path: M=%d is not instantiated", M);
+    const size_t smem = b1g_smem_bytes(ctx);
+    SSI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSI_TRY(ssi_reserve(ctx, ctx->bPartials, sizeof(double) * (size_t)B * s->n_tiles));
+    SSI_TRY(ssi_reserve(ctx, ctx->bGradP, sizeof(float) * (size_t)s->n_tiles * M * B));
+    double* partials = (double*)ctx->bPartials.p;
+    float* gpart = (float*)ctx->bGradP.p;
+    const long long slab = (long long)M * B;
+
+    const int ST = B1G_ST;
+    const int64_t max_s = (int64_t)(B1_CONST_FLOATS / M) / (B1_WARPS * ST) * (B1_WARPS * ST);
+    const int64_t n_sub = (B + max_s - 1) / max_s;
+    int64_t per = (B + n_sub - 1) / n_sub;
+    per = (per + B1_WARPS * ST - 1) / (B1_WARPS * ST) * (B1_WARPS * ST);
+    for (int64_t b0 = 0; b0 < B; b0 += per) {
+        const int S = (int)std::min<int64_t>(per, B - b0);
+        SSI_CUDA(ctx, cudaMemcpyToSymbolAsync(c_b1z, dZ + b0 * M, sizeof(float) * (size_t)S * M, 0, cudaMemcpyDeviceToDevice, ctx->stream));
+        b1_params p{};
+        p.N = (int)ctx->N; p.H = H; p.O = 1; p.n_tiles = s->n_tiles; p.S = S; p.act_out = m.act[1];
+        p.w2n = (H + 1 + 3) / 4 * 4;
+        int spc = 256;
+        while (spc > B1_WARPS * ST && (long long)s->n_tiles * ((S + spc - 1) / spc) < 8ll * ctx->sm_count) spc >>= 1;
+        p.s_per_cta = std::max(spc, B1_WARPS * ST);
+        p.n = m.n; p.w2_off = m.w_off[1]; p.b2_off = m.b_off[1];
+        p.tiles = s->tiles; p.PW = ctx->dP; p.Z = dZ + b0 * M; p.Y = ctx->dY;
+        p.partials = partials + b0 * s->n_tiles;
+        dim3 grid(s->n_tiles, (S + p.s_per_cta - 1) / p.s_per_cta);
+        ssi_kt_begin(ctx);
+        kern<<<grid, B1_THREADS, smem, ctx->stream>>>(p, m.act[0], (float)coef, gpart + b0 * M, slab);
+        SSI_LAUNCH_CHECK(ctx);
+        ssi_kt_end(ctx);
+    }
+    *d_gpart = gpart;
+    *n_parts = s->n_tiles;
+    return ssi_reduce_partials(ctx, partials, B, s->n_tiles, d_sse);
+}
 
 int ssi_b1_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
     SSI_TRY(ssi_b1_prepare(ctx));

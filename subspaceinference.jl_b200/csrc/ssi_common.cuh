@@ -160,6 +160,9 @@ int  ssi_b1_prepare(ssi_ctx* ctx);
 void ssi_b1_invalidate(ssi_ctx* ctx);
 void ssi_b1_destroy(ssi_ctx* ctx);
 int  ssi_b1_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse);
+// value + likelihood gradient: SSE (B doubles) and per-tile gradient partials [n_tiles][M x B] floats (returned pointer)
+bool ssi_b1_grad_supported(const ssi_ctx* ctx);
+int  ssi_b1_grad_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double coef, double* d_sse, float** d_gpart, int* n_parts);
 
 // ---- device helpers ---------------------------------------------------------------------
 __device__ __forceinline__ float ssi_act(float v, int act) {
@@ -168,6 +171,16 @@ __device__ __forceinline__ float ssi_act(float v, int act) {
         case SSI_ACT_TANH:    return tanhf(v);
         case SSI_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
         default:              return v;
+    }
+}
+
+// act'(pre) written in terms of the output h = act(pre)
+__device__ __forceinline__ float act_deriv_from_output(float h, int act) {
+    switch (act) {
+        case SSI_ACT_RELU:    return h > 0.0f ? 1.0f : 0.0f;
+        case SSI_ACT_TANH:    return 1.0f - h * h;
+        case SSI_ACT_SIGMOID: return h * (1.0f - h);
+        default:              return 1.0f;
     }
 }
 

@@ -37,15 +37,6 @@ struct gemm_t {
     const float* Hprev; long long h_sb;       // indexed like C
 };
 
-__device__ __forceinline__ float act_deriv_from_output(float h, int act) {
-    switch (act) {
-        case SSI_ACT_RELU:    return h > 0.0f ? 1.0f : 0.0f;
-        case SSI_ACT_TANH:    return 1.0f - h * h;
-        case SSI_ACT_SIGMOID: return h * (1.0f - h);
-        default:              return 1.0f;
-    }
-}
-
 template <bool A_KFAST, bool B_JFAST>
 __global__ void __launch_bounds__(256)
 k_gemm_simt(const gemm_t p) {
@@ -159,7 +150,7 @@ k_grad_rowsum(const float* __restrict__ delta, long long d_sb, int O, long long 
 }
 
 // grad_z(m, g) = sum_s part[s][m + g*M]  (+ prior terms), fixed order
-__global__ void k_grad_finish(const float* __restrict__ part, int S, int M, int G, const float* __restrict__ Z,
+__global__ void k_grad_finish(const float* __restrict__ part, int S, int M, int G, long long slab, const float* __restrict__ Z,
                               const double* __restrict__ Gsub /* (M+1)x(M+1) */, double inv_sp2, double inv_sz2, uint32_t mask,
                               double* __restrict__ grad /* M x G */) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,7 +158,7 @@ __global__ void k_grad_finish(const float* __restrict__ part, int S, int M, int 
     const int m = e % M, g = e / M;
     double v = 0.0;
     if (mask & SSI_TERM_LL)
-        for (int s = 0; s < S; ++s) v += (double)part[(long long)s * M * G + e];
+        for (int s = 0; s < S; ++s) v += (double)part[(long long)s * slab + e];
     if (mask & SSI_TERM_PRIOR_W) {          // -(P'W_swa + P'P z)/sigma_p^2
         const int ld = M + 1;
         double w = Gsub[m * ld + M];
@@ -195,6 +186,29 @@ int ssi_logpost_grad_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sig
     const int64_t N = ctx->N, n = m.n;
     const int M = ctx->M, L = m.L, O = m.dims[L];
     if (N >= (1ll << 31) || n >= (1ll << 31)) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "gradient path: N and n must fit 31 bits");
+
+    // one hidden layer, scalar output: forward-mode tangents in registers next to the BASIS forward pass (ssi_basis.cu)
+    if (ssi_b1_grad_supported(ctx) && (ctx->opt_path == SSI_PATH_AUTO || ctx->opt_path == SSI_PATH_BASIS)) {
+        SSI_TRY(ssi_reserve(ctx, ctx->bMisc, sizeof(double) * (size_t)B));
+        double* d_sse1 = (double*)ctx->bMisc.p;
+        float* gpart1 = nullptr;
+        int S1 = 0;
+        SSI_TRY(ssi_b1_grad_sse(ctx, dZ, B, (mask & SSI_TERM_LL) ? 1.0 / (sigma_m * sigma_m) : 0.0, d_sse1, &gpart1, &S1));
+        const int per = 32768 / M;                      // k_grad_finish indexes M x G with ints
+        for (int64_t b0 = 0; b0 < B; b0 += per) {
+            const int g = (int)std::min<int64_t>(per, B - b0);
+            k_grad_finish<<<(M * g + 127) / 128, 128, 0, ctx->stream>>>(gpart1 + b0 * M, S1, M, g, (long long)M * B, dZ + b0 * M,
+                                                                      ctx->dSubGram, 1.0 / (sigma_p * sigma_p),
+                                                                      1.0 / (sigma_z * sigma_z), mask, d_grad + b0 * M);
+            SSI_LAUNCH_CHECK(ctx);
+        }
+        SSI_TRY(ssi_logpost_finalize(ctx, d_sse1, dZ, B, sigma_m, sigma_p, sigma_z, mask, d_lp, nullptr));
+        ctx->stats.last_path = SSI_PATH_BASIS;
+        ctx->stats.last_units = (double)B * (double)N;
+        ctx->stats.last_flops = 3.0 * (double)B * ((double)N * m.flops_per_point) + 4.0 * (double)B * (double)n * M;
+        ctx->stats.last_bytes = 0;
+        return SSI_OK;
+    }
 
     // per-sample scratch: weights n, gradient n, activations sum(out_l) x N, two delta buffers maxw x N
     long long act_elems = 0;
@@ -279,7 +293,7 @@ int ssi_logpost_grad_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sig
             q.C = gpart; q.c_so = 1; q.c_sj = M; q.c_sb = (long long)M * g;
             q.O = M; q.J = g; q.K = n; q.split = split; q.epi = 0;
             SSI_TRY(launch_gemm(ctx, q, S, true, false));
-            k_grad_finish<<<(M * g + 127) / 128, 128, 0, ctx->stream>>>(gpart, S, M, g, dZ + b0 * M, ctx->dSubGram,
+            k_grad_finish<<<(M * g + 127) / 128, 128, 0, ctx->stream>>>(gpart, S, M, g, (long long)M * g, dZ + b0 * M, ctx->dSubGram,
                                                                       1.0 / (sigma_p * sigma_p), 1.0 / (sigma_z * sigma_z), mask,
                                                                       d_grad + b0 * M);
             SSI_LAUNCH_CHECK(ctx);
@@ -287,6 +301,7 @@ int ssi_logpost_grad_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sig
     }
     SSI_TRY(ssi_reduce_partials(ctx, partials, B, n_chunks, d_sse));
     SSI_TRY(ssi_logpost_finalize(ctx, d_sse, dZ, B, sigma_m, sigma_p, sigma_z, mask, d_lp, nullptr));
+    ctx->stats.last_path = SSI_PATH_LAYERED;
     ctx->stats.last_units = (double)B * (double)N;
     ctx->stats.last_flops = 3.0 * (double)B * ((double)N * m.flops_per_point) + 4.0 * (double)B * (double)n * M;
     ctx->stats.last_bytes = 0;

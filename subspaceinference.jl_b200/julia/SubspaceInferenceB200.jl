@@ -72,6 +72,16 @@ function logpost_batch(ctx::Ctx, Z::AbstractMatrix; σ_m = 1.0, σ_p = 1.0, σ_z
 end
 
 # ---- public API ---------------------------------------------------------------------------------
+# l_pi_grad(theta) = (density(theta), gradient(density, theta))  (src/space_inference.jl:107), batched over the columns of Z:
+# what AdvancedHMC's Hamiltonian(metric, density, l_pi_grad) (:146) needs, one reverse pass instead of ForwardDiff's M forward passes.
+function logpost_grad(ctx::Ctx, Z::AbstractMatrix; σ_m = 1.0, σ_p = 1.0, σ_z = 1.0, mask = TERM_LL)
+    B = size(Z, 2); lp = Vector{Float64}(undef, B); g = Matrix{Float64}(undef, size(Z, 1), B)
+    check(ctx, ccall((:ssi_logpost_grad_batch, libssi), Cint,
+                     (Ptr{Cvoid}, Ptr{Float32}, Int64, Float64, Float64, Float64, UInt32, Ptr{Float64}, Ptr{Float64}),
+                     ctx.h, Float32.(Z), B, σ_m, σ_p, σ_z, mask, lp, g))
+    return lp, g
+end
+
 function subspace_construction(model, cost, data, opt; T = 10, c = 1, M = 3, print_freq = 1,
                                ctx::Ctx = Ctx())
     training_loss = 0.0
@@ -103,11 +113,13 @@ end
 function sub_inference(in_model, data, W_swa, P; σ_z = 1.0, σ_m = 1.0, σ_p = 1.0, itr = 100, M = 3,
                        alg = :rwmh, backend = :forwarddiff,
                        n_chains = 1, seed = rand(UInt64), prior_mask = TERM_LL, ctx::Ctx = Ctx())
-    (alg == :rwmh || alg == :mh) || throw("$alg is not available")            # :162; other samplers stay in the reference
+    # :rwmh / :mh (:113-116) and :mala (:117-120) run on the device; :hmc / :nuts / :advi stay in the reference and can take
+    # logpost_grad below as their l_pi_grad (:107)
+    (alg == :rwmh || alg == :mh || alg == :mala) || throw("$alg is not available")            # :162
     size(P, 2) == M || throw(DimensionMismatch("P has $(size(P, 2)) columns but M = $M"))
     set_problem!(ctx, in_model, data, W_swa, P)
     zt = Array{Float32}(undef, M, n_chains, itr); lp = Matrix{Float64}(undef, n_chains, itr)
-    check(ctx, ccall((:ssi_mh_run, libssi), Cint,
+    check(ctx, ccall((alg == :mala ? :ssi_mala_run : :ssi_mh_run, libssi), Cint,
                      (Ptr{Cvoid}, Int64, Int64, UInt64, Int64, Float64, Float64, Float64, UInt32,
                       Ptr{Float32}, Ptr{Float32}, Ptr{Float64}, Ptr{UInt8}),
                      ctx.h, n_chains, itr, seed, 0, σ_z, σ_m, σ_p, prior_mask, C_NULL, zt, lp, C_NULL))

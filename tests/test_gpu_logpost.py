@@ -155,7 +155,9 @@ def test_error_behaviour(ssi):
 
 @pytest.mark.parametrize("dims,acts,N,M,B", [
     ((10, 20, 20, 2), (0, 0, 0), 100, 3, 5),          # README network
-    ((13, 50, 1), (1, 0), 3000, 5, 70),               # UCI shape, more than one group of samples
+    ((13, 50, 1), (1, 0), 3000, 5, 70),               # UCI shape, more than one group of samples (fast forward-mode path)
+    ((6, 31, 1), (2, 3), 200, 8, 37),                 # fast path: tanh hidden, sigmoid output, M = 8
+    ((4, 9, 1), (3, 1), 65, 1, 5),                    # fast path: sigmoid hidden, relu output, M = 1
     ((5, 7, 3), (2, 3), 130, 2, 9),                   # tanh / sigmoid, ragged widths
     ((3, 1), (0,), 1, 1, 3),                          # single layer, single datapoint
     ((33, 65, 17, 9, 4), (1, 2, 1, 0), 257, 6, 4),    # deeper chain
@@ -177,6 +179,16 @@ def test_gradient_vs_oracle(ssi, engine, dims, acts, N, M, B):
             lp_ref, g_ref = orc.density_and_grad(prob, Z[:, b].astype(np.float64), 0.7, 1.3, 0.9, mask)
             assert abs(lp[b] - lp_ref) <= RTOL * abs(lp_ref)
             np.testing.assert_allclose(grad[:, b], g_ref, rtol=0, atol=1e-4 * max(np.linalg.norm(g_ref), 1e-12), err_msg=f"mask {mask} sample {b}")
+    fast = len(dims) == 3 and dims[-1] == 1 and M <= 8
+    assert engine.stats().last_path == (ssi.PATH_BASIS if fast else ssi.PATH_LAYERED)
+    if fast:        # the generic reverse-mode path must agree with the forward-mode fast path
+        lp_f, g_f = engine.logpost_grad(Z, 0.7, 1.3, 0.9, mask=1)
+        engine.set_option("path", ssi.PATH_LAYERED)
+        lp_g, g_g = engine.logpost_grad(Z, 0.7, 1.3, 0.9, mask=1)
+        assert engine.stats().last_path == ssi.PATH_LAYERED
+        engine.set_option("path", ssi.PATH_AUTO)
+        np.testing.assert_allclose(lp_f, lp_g, rtol=2e-6)
+        np.testing.assert_allclose(g_f, g_g, rtol=0, atol=2e-4 * np.abs(g_g).max())
     # a sample's gradient does not depend on the rest of the batch
     lp_a, g_a = engine.logpost_grad(Z[:, :2], 0.7, 1.3, 0.9, mask=7)
     lp_b, g_b = engine.logpost_grad(Z, 0.7, 1.3, 0.9, mask=7)
