@@ -272,3 +272,25 @@ def test_mala_restatement_satisfies_detailed_balance():
         assert abs(lhs - rhs) < 1e-8 * max(1.0, abs(lhs))
     zt, lt, acc, _ = orc.mala_chain(prob, 6, 3, 0, sigma_z=0.05)
     assert acc[0] == 1 and zt.shape == (6, prob.M) and np.isfinite(lt).all()
+
+
+def test_next_rows_golden_fixture_is_reproduced():
+    """tests/golden/next_rows.npz (gradient, MALA, predictive sweep) is what the oracle computes today."""
+    g = np.load(Path(__file__).parent / "golden" / "next_rows.npz")
+    for name in ("readme", "uci"):
+        prob = orc.Problem(tuple(int(d) for d in g[f"{name}_dims"]), tuple(int(a) for a in g[f"{name}_acts"]), g[f"{name}_X"],
+                           g[f"{name}_Y"], g[f"{name}_W_swa"], g[f"{name}_P"])
+        sm, sp, sz = g[f"{name}_sig"]
+        for k, mask in enumerate((1, 3, 7)):
+            for b in range(g[f"{name}_Z"].shape[1]):
+                lp, grad = orc.density_and_grad(prob, g[f"{name}_Z"][:, b].astype(np.float64), sm, sp, sz, mask)
+                np.testing.assert_allclose(lp, g[f"{name}_lp"][k, b], rtol=1e-12)
+                np.testing.assert_allclose(grad, g[f"{name}_grad"][k, :, b], rtol=1e-9, atol=1e-9)
+    prob = orc.make_problem("readme")
+    for c in range(3):
+        z, lp, acc, _ = orc.mala_chain(prob, 8, int(g["mala_seed"]), c, sigma_z=float(g["mala_sigma_z"]))
+        np.testing.assert_array_equal(acc, g["mala_accept"][c])
+        np.testing.assert_array_equal(z, g["mala_z"][c])
+    traj, mu, sd = orc.predictive_sweep(prob.dims, prob.acts, prob.W_swa, prob.P, g["pred_Z"], g["pred_Xg"])
+    np.testing.assert_allclose(mu, g["pred_mean"], rtol=1e-12)
+    np.testing.assert_allclose(sd, g["pred_std"], rtol=1e-10)
