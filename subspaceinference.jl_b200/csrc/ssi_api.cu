@@ -206,7 +206,7 @@ int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
         ctx->stats.dominant_ms = 0; ctx->stats.dominant_launches = 0; ctx->kt_used = 0;
         return SSI_OK;
     }
-    if (!strcmp(key, "tc_overlap")) { ctx->opt_tc_overlap = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }
+    if (!strcmp(key, "tc_simt_basis")) { ctx->opt_tc_simt_basis = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "tc_noorder")) { ctx->opt_tc_noorder = value != 0; return SSI_OK; }
     return ssi_fail(ctx, SSI_ERR_ARG, "unknown option '%s'", key);
 }

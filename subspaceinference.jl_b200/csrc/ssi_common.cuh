@@ -49,7 +49,7 @@ struct ssi_ctx {
     int opt_group = 0;
     int opt_tc_nofuse = 0;    // debugging / A-B: compute the output layer as its own GEMM
     int opt_tc_noorder = 0;
-    int opt_tc_overlap = 0;   // A-B: basis layer of group g+1 on a second stream next to the GEMMs of group g (measured: no gain)
+    int opt_tc_simt_basis = 0; // A-B: first layer as the FP32 SIMT basis combination instead of the tensor-core one
     int opt_gram_fp64 = 0;    // force the FP64 SIMT Gram (default: tensor-core TF32x2 Gram for large n, K <= 128)
     int opt_gram_chunk = 0;   // tiles (32 rows) per FP32 accumulation chunk of the tensor-core Gram (default 32)
     int opt_tc_nobasis = 0;   // debugging / A-B: run the first layer as a GEMM instead of the affine-in-z basis combination   // debugging / A-B: sample-major work order on the first layer

@@ -567,6 +567,193 @@ k_tc_basis_layer(const float* __restrict__ bases /* [M+1][NW] */, long long NW, 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// the same first layer ON THE TENSOR CORES: with z augmented by a constant 1 it is one GEMM
+//     pre[s, e] = sum_{m <= M} zaug[s, m] * basesT[e, m],      e = (datapoint, hidden unit),  K = M+1 <= 32
+// whose M dimension is the SAMPLES (up to 128 per group = the 128 TMEM lanes), N = 256 activations per tile and K = 32.
+// The bases are re-laid out once as K-major split-BF16 rows [e][32] (64 bytes = one SWIZZLE_64B row); z of the group
+// sits in shared memory as the A operand for the whole kernel.  BF16x3 (hi*hi + hi*lo + lo*hi), FP32 accumulate in TMEM.
+// The FP32 FMA work of k_tc_basis_layer disappears (6 small MMAs per 256 activations of 128 samples) and the bases are
+// read once per 128 samples instead of once per 32: the layer becomes a pure HBM stream of its own output.
+// Roles as in k_tc_layer: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue (activation, hi/lo split, TMA store to
+// H1[s][e] viewed as a [samples][N*width] matrix).
+#define TB_N 256
+#define TB_STAGES 2                                // the kernel writes 4x what it reads: shared memory goes to the store side
+#define TB_SBUF 3                                  // TMA-store staging buffers per epilogue warp (hi | lo, 2 x 4 KB each): the output
+                                                   // stream is bound by the bytes in flight, 2 buffers gave 2.7 TB/s
+#define TB_STAGE_BYTES (2 * TB_N * 64)            // basesT hi | lo
+#define TB_OFF_Z (TB_STAGES * TB_STAGE_BYTES)      // zaug hi (128 x 64 B) | lo
+#define TB_OFF_STORE (TB_OFF_Z + 2 * 128 * 64)
+#define TB_OFF_BAR (TB_OFF_STORE + 4 * TB_SBUF * 8192)
+#define TB_SMEM_TOTAL (TB_OFF_BAR + 16 * 8 + 16)
+
+template <int ACT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__ CUtensorMap tmZl,
+               const __grid_constant__ CUtensorMap tmTh, const __grid_constant__ CUtensorMap tmTl,
+               const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl, const int n_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + TB_OFF_BAR);     // full[4] empty[4] tfull[2] tempty[2] zfull
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + 8 * TB_STAGES;
+    const uint32_t bar_tfull = bar_empty + 8 * TB_STAGES, bar_tempty = bar_tfull + 16, bar_z = bar_tempty + 16;
+
+    if (threadIdx.x == 0) {
+        if (smem_base & 1023u) { printf("ssi_tc: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+        for (int s = 0; s < TB_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 128); }
+        mbar_init(bar_z, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmZh); tma_prefetch_desc(&tmZl); tma_prefetch_desc(&tmTh); tma_prefetch_desc(&tmTl);
+        tma_prefetch_desc(&tmOh); tma_prefetch_desc(&tmOl);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(bar_z, 2 * 128 * 64);
+            tma_load_3d_hint(smem_base + TB_OFF_Z, &tmZh, bar_z, 0, 0, 0, TC_EVICT_LAST);
+            tma_load_3d_hint(smem_base + TB_OFF_Z + 128 * 64, &tmZl, bar_z, 0, 0, 0, TC_EVICT_LAST);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                const uint32_t full = bar_full + 8 * stage;
+                const uint32_t sB = smem_base + stage * TB_STAGE_BYTES;
+                mbar_expect_tx(full, TB_STAGE_BYTES);
+                tma_load_3d_hint(sB, &tmTh, full, 0, t * TB_N, 0, TC_EVICT_FIRST);          // read once per group of samples
+                tma_load_3d_hint(sB + TB_N * 64, &tmTl, full, 0, t * TB_N, 0, TC_EVICT_FIRST);
+                if (++stage == TB_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(TB_N);
+            mbar_wait(bar_z, 0);
+            tc_fence_after();
+            const uint64_t zh = umma_desc_sw64(smem_base + TB_OFF_Z), zl = umma_desc_sw64(smem_base + TB_OFF_Z + 128 * 64);
+            int stage = 0;
+            uint32_t phase = 0, tile = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile) {
+                const uint32_t ab = tile & 1, aphase = (tile >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * ab, aphase ^ 1);
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + ab * 256;
+                const uint32_t sB = smem_base + stage * TB_STAGE_BYTES;
+                const uint64_t bh = umma_desc_sw64(sB), bl = umma_desc_sw64(sB + TB_N * 64);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const uint64_t ko = (uint64_t)(k * 32 >> 4);       // +32 bytes per K=16 step inside the 64-byte row
+                    umma_bf16(d_tmem, zh + ko, bh + ko, idesc, k != 0);
+                    umma_bf16(d_tmem, zh + ko, bl + ko, idesc, 1);
+                    umma_bf16(d_tmem, zl + ko, bh + ko, idesc, 1);
+                }
+                umma_commit(bar_empty + 8 * stage);
+                umma_commit(bar_tfull + 8 * ab);
+                if (++stage == TB_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        // staging: per warp TB_SBUF buffers of (hi | lo) x [32 samples][64 activations] = 2 x 4 KB, SWIZZLE_128B.  128-byte
+        // rows: the TMA store engine is bound by rows per cycle (64-byte rows capped the kernel at 2.2 TB/s of writes)
+        const uint32_t stage_w = smem_base + TB_OFF_STORE + (uint32_t)(warp - 2) * (TB_SBUF * 8192);
+        const uint32_t swz = (uint32_t)(lane & 7);
+        uint32_t chunk_ctr = 0, tile = 0, sbuf = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile) {
+            const uint32_t ab = tile & 1, aphase = (tile >> 1) & 1;
+            mbar_wait(bar_tfull + 8 * ab, aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
+#pragma unroll 1
+            for (int c0 = 0; c0 < TB_N; c0 += 64, ++chunk_ctr) {
+                if (chunk_ctr >= TB_SBUF) {
+                    if (lane == 0) tma_store_wait_read<TB_SBUF - 1>();
+                    __syncwarp();
+                }
+                const uint32_t sh = stage_w + sbuf * 8192, sl = sh + 4096;
+                if (++sbuf == TB_SBUF) sbuf = 0;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0 + 32 * half, v);
+                    tmem_ld_wait();
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const float x0 = tc_act<ACT>(__uint_as_float(v[j]));
+                        const float x1 = tc_act<ACT>(__uint_as_float(v[j + 1]));
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+                        const float2 hf = __bfloat1622float2(h2);
+                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+                        hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                        lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t off = (uint32_t)lane * 128 + ((((uint32_t)(4 * half + c)) ^ swz) << 4);
+                        st_shared_v4(sh + off, hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                        st_shared_v4(sl + off, lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    // rows = samples (rows >= G are clipped by TMA), columns = activations e of this tile
+                    tma_store_3d_hint(&tmOh, sh, t * TB_N + c0, q * 32, 0, TC_EVICT_FIRST);
+                    tma_store_3d_hint(&tmOl, sl, t * TB_N + c0, q * 32, 0, TC_EVICT_FIRST);
+                    tma_store_commit();
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * ab);
+        }
+        if (lane == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// zaug[s][m] = z[m, s] (m < M), 1 (m == M: the W_swa basis), 0 (padding and s >= G), split BF16, [128][32]
+__global__ void k_tc_pack_zaug(const float* __restrict__ Z, int M, int G, bf16* __restrict__ zh, bf16* __restrict__ zl) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 128 * 32) return;
+    const int s = t >> 5, m = t & 31;
+    const float v = s < G ? (m < M ? Z[m + s * M] : (m == M ? 1.0f : 0.0f)) : 0.0f;
+    bf16 hi, lo;
+    split_bf16(v, hi, lo);
+    zh[t] = hi;
+    zl[t] = lo;
+}
+
+// basesT[e][m] (K-major, 32 BF16 = 64 bytes per activation e, split hi / lo)  <-  bases[m][e] FP32, m <= M
+__global__ void __launch_bounds__(256)
+k_tc_bases_kmajor(const float* __restrict__ bases, long long NW, int M1, bf16* __restrict__ th, bf16* __restrict__ tl) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= NW) return;
+    __align__(16) bf16 hi[32], lo[32];
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {
+        const float v = m < M1 ? bases[(long long)m * NW + e] : 0.0f;
+        split_bf16(v, hi[m], lo[m]);
+    }
+    uint4* dh = reinterpret_cast<uint4*>(th + e * 32);
+    uint4* dl = reinterpret_cast<uint4*>(tl + e * 32);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { dh[c] = reinterpret_cast<const uint4*>(hi)[c]; dl[c] = reinterpret_cast<const uint4*>(lo)[c]; }
+}
+
 // zpack[g][m] <- Z[m + g*M], zero padded  (staging for the device-to-constant copy)
 __global__ void k_tc_pack_z(const float* __restrict__ Z, int M, int G, float* __restrict__ out /* [TC_GMAX][SSI_MAX_M] */) {
     const int t = threadIdx.x + blockIdx.x * blockDim.x;
@@ -605,17 +792,18 @@ struct ssi_tc_state {
     int Kp[SSI_MAX_LAYERS] = {0};        // padded input width of layer l
     int width[SSI_MAX_LAYERS] = {0};     // padded output width of layer l
     int BN[SSI_MAX_LAYERS] = {0};
-    int G = TC_GMAX;
+    int G = TC_GMAX;                     // samples per group (multiples of TC_GMAX are handled TC_GMAX at a time by the SIMT kernels)
     bf16 *Xh = nullptr, *Xl = nullptr;
     bf16 *Wh[SSI_MAX_LAYERS] = {nullptr}, *Wl[SSI_MAX_LAYERS] = {nullptr};
     float* bias[SSI_MAX_LAYERS] = {nullptr};
     bf16 *Hh[2] = {nullptr, nullptr}, *Hl[2] = {nullptr, nullptr};
-    // basis-layer output, double buffered: the basis kernel of group g+1 runs on `side` while the GEMMs of group g
-    // read the other buffer
-    bf16 *Bh[2] = {nullptr, nullptr}, *Bl[2] = {nullptr, nullptr};
-    CUtensorMap tmBasisH[2], tmBasisL[2];
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_basis[2] = {nullptr, nullptr}, ev_gemm[2] = {nullptr, nullptr};
+    // basis-layer output [G][N][width0] (hi, lo) and its tensor maps as the A operand of the first GEMM layer
+    bf16 *Bh = nullptr, *Bl = nullptr;
+    CUtensorMap tmBasisH, tmBasisL;
+    // basis layer on the tensor cores (k_tc_basis_mma): K-major split-BF16 bases [N*width0][32], z of the group [128][32]
+    bool basis_mma = false;
+    bf16 *Th = nullptr, *Tl = nullptr, *Zh = nullptr, *Zl = nullptr;
+    CUtensorMap tmZh, tmZl, tmTh, tmTl, tmOh, tmOl;
     double* partials = nullptr;
     CUtensorMap tmAh[SSI_MAX_LAYERS], tmAl[SSI_MAX_LAYERS], tmBh[SSI_MAX_LAYERS], tmBl[SSI_MAX_LAYERS];
     CUtensorMap tmSh[SSI_MAX_LAYERS], tmSl[SSI_MAX_LAYERS];
@@ -624,13 +812,12 @@ struct ssi_tc_state {
 
 static void tc_free(ssi_tc_state* s) {
     cudaFree(s->Xh); cudaFree(s->Xl); cudaFree(s->partials); cudaFree(s->Wout); cudaFree(s->bout); cudaFree(s->bases); cudaFree(s->zpack);
-    for (int i = 0; i < 2; ++i) { cudaFree(s->Hh[i]); cudaFree(s->Hl[i]); cudaFree(s->Bh[i]); cudaFree(s->Bl[i]); }
+    for (int i = 0; i < 2; ++i) { cudaFree(s->Hh[i]); cudaFree(s->Hl[i]); }
+    cudaFree(s->Bh); cudaFree(s->Bl); cudaFree(s->Th); cudaFree(s->Tl); cudaFree(s->Zh); cudaFree(s->Zl);
     for (int l = 0; l < SSI_MAX_LAYERS; ++l) { cudaFree(s->Wh[l]); cudaFree(s->Wl[l]); cudaFree(s->bias[l]); }
-    // the side stream and its events survive a re-prepare
-    ssi_tc_state keep;
-    keep.encode = s->encode; keep.side = s->side; keep.ev_start = s->ev_start;
-    for (int i = 0; i < 2; ++i) { keep.ev_basis[i] = s->ev_basis[i]; keep.ev_gemm[i] = s->ev_gemm[i]; }
-    *s = keep;
+    PFN_encodeTiled enc = s->encode;
+    *s = ssi_tc_state();
+    s->encode = enc;
 }
 
 void ssi_tc_invalidate(ssi_ctx* ctx) {
@@ -640,12 +827,6 @@ void ssi_tc_invalidate(ssi_ctx* ctx) {
 void ssi_tc_destroy(ssi_ctx* ctx) {
     if (!ctx->tc) return;
     tc_free(ctx->tc);
-    if (ctx->tc->side) cudaStreamDestroy(ctx->tc->side);
-    if (ctx->tc->ev_start) cudaEventDestroy(ctx->tc->ev_start);
-    for (int i = 0; i < 2; ++i) {
-        if (ctx->tc->ev_basis[i]) cudaEventDestroy(ctx->tc->ev_basis[i]);
-        if (ctx->tc->ev_gemm[i]) cudaEventDestroy(ctx->tc->ev_gemm[i]);
-    }
     delete ctx->tc;
     ctx->tc = nullptr;
 }
@@ -725,7 +906,11 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
     s->l0 = s->basis ? 1 : 0;
     s->fused_out = (m.L - s->l0 >= 2 && m.dims[m.L] <= TC_OP && !ctx->opt_tc_nofuse);
     s->nl = s->fused_out ? m.L - 1 : m.L;
-    s->G = ctx->opt_group > 0 ? std::min(ctx->opt_group, TC_GMAX) : TC_GMAX;
+    // the basis layer runs on the tensor cores when z (plus the constant 1) fits one K = 32 block; its M dimension is the
+    // samples, so a group is then 128 samples (the bases are read once per group)
+    s->basis_mma = s->basis && ctx->M + 1 <= 32 && !ctx->opt_tc_simt_basis;
+    const int gmax = s->basis_mma ? 128 : TC_GMAX;
+    s->G = ctx->opt_group > 0 ? std::min(ctx->opt_group, gmax) : gmax;
     const int G = s->G;
     int maxw = 0;
     for (int l = 0; l < s->nl; ++l) {
@@ -765,20 +950,16 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
         SSI_CUDA(ctx, cudaMalloc(&s->Hl[i], sizeof(bf16) * (size_t)G * N * maxw));
     }
     if (s->basis) {
-        const int nb = ctx->opt_tc_overlap ? 2 : 1;
-        for (int i = 0; i < nb; ++i) {
-            SSI_CUDA(ctx, cudaMalloc(&s->Bh[i], sizeof(bf16) * (size_t)G * N * s->width[0]));
-            SSI_CUDA(ctx, cudaMalloc(&s->Bl[i], sizeof(bf16) * (size_t)G * N * s->width[0]));
-        }
-        if (!s->side) {
-            int lo = 0, hi = 0;
-            SSI_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));     // lo = numerically largest = lowest priority
-            SSI_CUDA(ctx, cudaStreamCreateWithPriority(&s->side, cudaStreamNonBlocking, lo));
-            SSI_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_start, cudaEventDisableTiming));
-            for (int i = 0; i < 2; ++i) {
-                SSI_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_basis[i], cudaEventDisableTiming));
-                SSI_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_gemm[i], cudaEventDisableTiming));
-            }
+        const size_t NW = (size_t)N * s->width[0];
+        SSI_CUDA(ctx, cudaMalloc(&s->Bh, sizeof(bf16) * (size_t)G * NW));
+        SSI_CUDA(ctx, cudaMalloc(&s->Bl, sizeof(bf16) * (size_t)G * NW));
+        if (s->basis_mma) {
+            SSI_CUDA(ctx, cudaMalloc(&s->Th, sizeof(bf16) * NW * 32));
+            SSI_CUDA(ctx, cudaMalloc(&s->Tl, sizeof(bf16) * NW * 32));
+            SSI_CUDA(ctx, cudaMalloc(&s->Zh, sizeof(bf16) * 128 * 32));
+            SSI_CUDA(ctx, cudaMalloc(&s->Zl, sizeof(bf16) * 128 * 32));
+            k_tc_bases_kmajor<<<(unsigned)((NW + 255) / 256), 256, 0, ctx->stream>>>(s->bases, (long long)NW, ctx->M + 1, s->Th, s->Tl);
+            SSI_LAUNCH_CHECK(ctx);
         }
     }
     const int m_tiles = (int)((N + TC_BM - 1) / TC_BM);
@@ -794,14 +975,11 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
             SSI_TRY(tc_make_map(ctx, &s->tmAh[l], s->Xh, s->Kp[0], N, 1, TC_BK, TC_BM, S128));
             SSI_TRY(tc_make_map(ctx, &s->tmAl[l], s->Xl, s->Kp[0], N, 1, TC_BK, TC_BM, S128));
         } else if (l == s->l0) {
-            // activations written by the basis layer: [G][N][width_0], one map per buffer
-            for (int i = 0; i < 2; ++i) {
-                if (!s->Bh[i]) continue;
-                SSI_TRY(tc_make_map(ctx, &s->tmBasisH[i], s->Bh[i], s->width[0], N, G, TC_BK, TC_BM, S128));
-                SSI_TRY(tc_make_map(ctx, &s->tmBasisL[i], s->Bl[i], s->width[0], N, G, TC_BK, TC_BM, S128));
-            }
-            s->tmAh[l] = s->tmBasisH[0];
-            s->tmAl[l] = s->tmBasisL[0];
+            // activations written by the basis layer: [G][N][width_0]
+            SSI_TRY(tc_make_map(ctx, &s->tmBasisH, s->Bh, s->width[0], N, G, TC_BK, TC_BM, S128));
+            SSI_TRY(tc_make_map(ctx, &s->tmBasisL, s->Bl, s->width[0], N, G, TC_BK, TC_BM, S128));
+            s->tmAh[l] = s->tmBasisH;
+            s->tmAl[l] = s->tmBasisL;
         } else {
             // activations written by layer l-1: [G][N][width_{l-1}], K = width_{l-1} = Kp[l]
             SSI_TRY(tc_make_map(ctx, &s->tmAh[l], s->Hh[(l - 1) & 1], s->width[l - 1], N, G, TC_BK, TC_BM, S128));
@@ -821,6 +999,21 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
     for (int mode = 0; mode < 3; ++mode)
         for (int act = 0; act < 4; ++act)
             SSI_CUDA(ctx, cudaFuncSetAttribute(tc_kernel(mode, act), cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_total(mode)));
+    if (s->basis_mma) {
+        const CUtensorMapSwizzle S64 = CU_TENSOR_MAP_SWIZZLE_64B;
+        const uint64_t NW = (uint64_t)N * s->width[0];
+        SSI_TRY(tc_make_map(ctx, &s->tmZh, s->Zh, 32, 128, 1, 32, 128, S64));
+        SSI_TRY(tc_make_map(ctx, &s->tmZl, s->Zl, 32, 128, 1, 32, 128, S64));
+        SSI_TRY(tc_make_map(ctx, &s->tmTh, s->Th, 32, NW, 1, 32, TB_N, S64));
+        SSI_TRY(tc_make_map(ctx, &s->tmTl, s->Tl, 32, NW, 1, 32, TB_N, S64));
+        // the group's activations as a [samples][N*width0] matrix: boxes of 32 samples x 64 activations from the epilogue
+        SSI_TRY(tc_make_map(ctx, &s->tmOh, s->Bh, NW, (uint64_t)G, 1, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+        SSI_TRY(tc_make_map(ctx, &s->tmOl, s->Bl, NW, (uint64_t)G, 1, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+        SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_basis_mma<SSI_ACT_IDENTITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_TOTAL));
+        SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_basis_mma<SSI_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_TOTAL));
+        SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_basis_mma<SSI_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_TOTAL));
+        SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_basis_mma<SSI_ACT_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_TOTAL));
+    }
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     s->ready = true;
     return SSI_OK;
@@ -836,74 +1029,67 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
     const int M = ctx->M;
     const int m_tiles = (int)((N + TC_BM - 1) / TC_BM);
     const int parts = m_tiles * 4;
+    const long long NW = s->basis ? (long long)N * s->width[0] : 0;
 
-    // First layer as a basis combination: a pure HBM stream.  It runs on a second, low-priority stream one group
-    // ahead of the GEMMs, co-resident with the persistent GEMM kernel (which leaves it registers and shared memory),
-    // so the stream hides under the tensor-core work instead of preceding it.
-    const bool overlap = s->basis && s->Bh[1] != nullptr;
-    cudaStream_t bstream = overlap ? s->side : ctx->stream;
-    auto launch_basis = [&](int64_t b0, int buf) -> int {
+    for (int64_t b0 = 0; b0 < B; b0 += s->G) {
         const int G = (int)std::min<int64_t>(s->G, B - b0);
-        k_tc_pack_z<<<(TC_GMAX * SSI_MAX_M + 255) / 256, 256, 0, bstream>>>(dZ + b0 * M, M, G, s->zpack);
-        SSI_LAUNCH_CHECK(ctx);
-        const long long NW = (long long)N * s->width[0];
-        const long long per_cta = (long long)TC_BASIS_THREADS * TC_BASIS_ITERS * 2;
-        const unsigned blocks = (unsigned)((NW + per_cta - 1) / per_cta);
-        if (M <= 8) tc_launch_basis<8>(m.act[0], blocks, bstream, s->bases, NW, M, G, s->zpack, s->Bh[buf], s->Bl[buf]);
-        else if (M <= 12) tc_launch_basis<12>(m.act[0], blocks, bstream, s->bases, NW, M, G, s->zpack, s->Bh[buf], s->Bl[buf]);
-        else if (M <= 20) tc_launch_basis<20>(m.act[0], blocks, bstream, s->bases, NW, M, G, s->zpack, s->Bh[buf], s->Bl[buf]);
-        else if (M <= 32) tc_launch_basis<32>(m.act[0], blocks, bstream, s->bases, NW, M, G, s->zpack, s->Bh[buf], s->Bl[buf]);
-        else tc_launch_basis<SSI_MAX_M>(m.act[0], blocks, bstream, s->bases, NW, M, G, s->zpack, s->Bh[buf], s->Bl[buf]);
-        SSI_LAUNCH_CHECK(ctx);
-        if (overlap) SSI_CUDA(ctx, cudaEventRecord(s->ev_basis[buf], s->side));
-        return SSI_OK;
-    };
-    if (overlap) {
-        // everything already queued on the caller's stream (a previous call's GEMMs reading the basis buffers,
-        // the input Z) precedes the side stream's first write
-        SSI_CUDA(ctx, cudaEventRecord(s->ev_start, ctx->stream));
-        SSI_CUDA(ctx, cudaStreamWaitEvent(s->side, s->ev_start, 0));
-    }
-    if (s->basis) SSI_TRY(launch_basis(0, 0));
-
-    // SSI_TC_TRACE=1: time stamps (ms since the start of the call) of the first groups' basis and GEMM kernels
-    static const bool trace = getenv("SSI_TC_TRACE") != nullptr;
-    cudaEvent_t tr[1 + 4 * 4];
-    const int tr_groups = trace ? 4 : 0;
-    if (trace) {
-        for (auto& e : tr) cudaEventCreate(&e);
-        cudaEventRecord(tr[0], ctx->stream);
-    }
-    int64_t gi = 0;
-    for (int64_t b0 = 0; b0 < B; b0 += s->G, ++gi) {
-        const int G = (int)std::min<int64_t>(s->G, B - b0);
-        const float* Zg = dZ + b0 * M;
-        const int buf = overlap ? (int)(gi & 1) : 0;
-        // ---- K1: project the group's weights straight into the GEMM operand layouts ----
-        for (int l = s->l0; l < s->nl; ++l) {
-            dim3 grid(s->Kp[l] / PW_T, (s->width[l] + PW_T - 1) / PW_T);
-            k_tc_project_w<<<grid, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.w_off[l], m.dims[l], m.dims[l + 1],
-                                                         s->width[l], s->Kp[l], s->Wh[l], s->Wl[l]);
+        // ---- first layer as a combination of the precomputed bases ----
+        if (s->basis_mma) {
+            k_tc_pack_zaug<<<(128 * 32 + 255) / 256, 256, 0, ctx->stream>>>(dZ + b0 * M, M, G, s->Zh, s->Zl);
             SSI_LAUNCH_CHECK(ctx);
-            k_tc_project_b<<<(s->width[l] + 255) / 256, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.b_off[l],
-                                                                           m.dims[l + 1], s->width[l], s->bias[l]);
+            const int n_tiles = (int)((NW + TB_N - 1) / TB_N);
+            const int grid = std::min(ctx->sm_count, n_tiles);
+            switch (m.act[0]) {
+                case SSI_ACT_RELU:    k_tc_basis_mma<SSI_ACT_RELU><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles); break;
+                case SSI_ACT_TANH:    k_tc_basis_mma<SSI_ACT_TANH><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles); break;
+                case SSI_ACT_SIGMOID: k_tc_basis_mma<SSI_ACT_SIGMOID><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles); break;
+                default:              k_tc_basis_mma<SSI_ACT_IDENTITY><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles); break;
+            }
             SSI_LAUNCH_CHECK(ctx);
         }
-        if (s->fused_out) {
-            const int wl = s->width[s->nl - 1];          // padded width of the last hidden layer
-            const int O = m.dims[m.L], cnt = m.dims[m.L - 1] * O;
-            k_tc_project_v<<<(cnt + 255) / 256, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.w_off[m.L - 1], cnt, O,
-                                                                     TC_OP, (long long)wl * TC_OP, s->Wout);
-            SSI_LAUNCH_CHECK(ctx);
-            k_tc_project_v<<<1, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, G, m.b_off[m.L - 1], O, O, 0, TC_OP, s->bout);
-            SSI_LAUNCH_CHECK(ctx);
+        // ---- the SIMT kernels take TC_GMAX samples at a time ----
+        for (int g0 = 0; g0 < G; g0 += TC_GMAX) {
+            const int gs = std::min(TC_GMAX, G - g0);
+            const float* Zg = dZ + (b0 + g0) * M;
+            if (s->basis && !s->basis_mma) {
+                k_tc_pack_z<<<(TC_GMAX * SSI_MAX_M + 255) / 256, 256, 0, ctx->stream>>>(Zg, M, gs, s->zpack);
+                SSI_LAUNCH_CHECK(ctx);
+                const long long per_cta = (long long)TC_BASIS_THREADS * TC_BASIS_ITERS * 2;
+                const unsigned blocks = (unsigned)((NW + per_cta - 1) / per_cta);
+                bf16* oh = s->Bh + (long long)g0 * NW;
+                bf16* ol = s->Bl + (long long)g0 * NW;
+                if (M <= 8) tc_launch_basis<8>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol);
+                else if (M <= 12) tc_launch_basis<12>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol);
+                else if (M <= 20) tc_launch_basis<20>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol);
+                else if (M <= 32) tc_launch_basis<32>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol);
+                else tc_launch_basis<SSI_MAX_M>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol);
+                SSI_LAUNCH_CHECK(ctx);
+            }
+            // K1: project the samples' weights straight into the GEMM operand layouts
+            for (int l = s->l0; l < s->nl; ++l) {
+                const size_t wo = (size_t)g0 * s->width[l] * s->Kp[l];
+                dim3 grid(s->Kp[l] / PW_T, (s->width[l] + PW_T - 1) / PW_T);
+                k_tc_project_w<<<grid, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, gs, m.w_off[l], m.dims[l], m.dims[l + 1],
+                                                             s->width[l], s->Kp[l], s->Wh[l] + wo, s->Wl[l] + wo);
+                SSI_LAUNCH_CHECK(ctx);
+                k_tc_project_b<<<(s->width[l] + 255) / 256, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, gs, m.b_off[l],
+                                                                               m.dims[l + 1], s->width[l],
+                                                                               s->bias[l] + (size_t)g0 * s->width[l]);
+                SSI_LAUNCH_CHECK(ctx);
+            }
+            if (s->fused_out) {
+                const int wl = s->width[s->nl - 1];          // padded width of the last hidden layer
+                const int O = m.dims[m.L], cnt = m.dims[m.L - 1] * O;
+                k_tc_project_v<<<(cnt + 255) / 256, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, gs, m.w_off[m.L - 1], cnt, O,
+                                                                         TC_OP, (long long)wl * TC_OP,
+                                                                         s->Wout + (size_t)g0 * wl * TC_OP);
+                SSI_LAUNCH_CHECK(ctx);
+                k_tc_project_v<<<1, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, gs, m.b_off[m.L - 1], O, O, 0, TC_OP,
+                                                         s->bout + (size_t)g0 * TC_OP);
+                SSI_LAUNCH_CHECK(ctx);
+            }
         }
-        // ---- the Dense chain ----
-        if (overlap) {
-            // the projection kernels need most of an SM's registers: the next basis layer starts behind them
-            SSI_CUDA(ctx, cudaEventRecord(s->ev_gemm[buf], ctx->stream));
-            SSI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s->ev_basis[buf], 0));
-        }
+        // ---- the remaining Dense layers as GEMMs over the whole group ----
         for (int l = s->l0; l < s->nl; ++l) {
             tc_params p{};
             p.N = (int)N; p.G = G; p.m_tiles = m_tiles;
@@ -929,41 +1115,13 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
             } else if (last) {
                 mode = TC_MODE_FINAL;
             }
-            const bool from_basis = s->basis && l == s->l0;
-            if (from_basis && gi < tr_groups) cudaEventRecord(tr[1 + 4 * gi], ctx->stream);
             if (last) ssi_kt_begin(ctx);
-            tc_kernel(mode, p.act)<<<grid, TC_THREADS, tc_smem_total(mode), ctx->stream>>>(
-                from_basis ? s->tmBasisH[buf] : s->tmAh[l], from_basis ? s->tmBasisL[buf] : s->tmAl[l], s->tmBh[l], s->tmBl[l],
-                s->tmSh[l], s->tmSl[l], p);
+            tc_kernel(mode, p.act)<<<grid, TC_THREADS, tc_smem_total(mode), ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l],
+                                                                                          s->tmSh[l], s->tmSl[l], p);
             SSI_LAUNCH_CHECK(ctx);
             if (last) ssi_kt_end(ctx);
-            if (from_basis && gi < tr_groups) cudaEventRecord(tr[2 + 4 * gi], ctx->stream);
-            if (from_basis && overlap) {
-                // the GEMM that reads basis buffer `buf` is queued: the next group's basis layer (other buffer; its
-                // previous reader finished before this group's projection) is launched next to it and shares the SMs
-                if (b0 + s->G < B) {
-                    SSI_CUDA(ctx, cudaStreamWaitEvent(s->side, s->ev_gemm[buf], 0));
-                    if (gi < tr_groups) cudaEventRecord(tr[3 + 4 * gi], s->side);
-                    SSI_TRY(launch_basis(b0 + s->G, buf ^ 1));
-                    if (gi < tr_groups) cudaEventRecord(tr[4 + 4 * gi], s->side);
-                }
-            }
         }
-        if (s->basis && !overlap && b0 + s->G < B) SSI_TRY(launch_basis(b0 + s->G, 0));
         SSI_TRY(ssi_reduce_partials(ctx, s->partials, G, parts, d_sse + b0));
-    }
-    if (trace) {
-        cudaGetLastError();
-        cudaStreamSynchronize(ctx->stream);
-        if (overlap) cudaStreamSynchronize(s->side);
-        for (int g = 0; g < tr_groups && g < gi; ++g) {
-            float t[4] = {0, 0, 0, 0};
-            for (int k = 0; k < 4; ++k)
-                if (cudaEventQuery(tr[1 + 4 * g + k]) == cudaSuccess) cudaEventElapsedTime(&t[k], tr[0], tr[1 + 4 * g + k]);
-            fprintf(stderr, "ssi_tc trace group %d: gemm [%.3f, %.3f] ms   next basis [%.3f, %.3f] ms\n", g, t[0], t[1], t[2], t[3]);
-        }
-        for (auto& e : tr) cudaEventDestroy(e);
-        cudaGetLastError();       // never-recorded trace events are not an error of the call
     }
     return SSI_OK;
 }
