@@ -578,6 +578,7 @@ k_tc_basis_layer(const float* __restrict__ bases /* [M+1][NW] */, long long NW, 
 // Roles as in k_tc_layer: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue (activation, hi/lo split, TMA store to
 // H1[s][e] viewed as a [samples][N*width] matrix).
 #define TB_N 256
+#define TB_LO_DIRECT 0                            // A-B: lo halves of the output by direct 16-byte stores instead of TMA (measured: 32 ms vs 8.7 ms)
 #define TB_STAGES 2                                // the kernel writes 4x what it reads: shared memory goes to the store side
 #define TB_SBUF 3                                  // TMA-store staging buffers per epilogue warp (hi | lo, 2 x 4 KB each): the output
                                                    // stream is bound by the bytes in flight, 2 buffers gave 2.7 TB/s
@@ -591,7 +592,8 @@ template <int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__ CUtensorMap tmZl,
                const __grid_constant__ CUtensorMap tmTh, const __grid_constant__ CUtensorMap tmTl,
-               const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl, const int n_tiles) {
+               const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl, const int n_tiles,
+               bf16* __restrict__ out_lo, const long long NW, const int rows) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + TB_OFF_BAR);     // full[4] empty[4] tfull[2] tempty[2] zfull
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
@@ -700,7 +702,18 @@ k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__
                     for (int c = 0; c < 4; ++c) {
                         const uint32_t off = (uint32_t)lane * 128 + ((((uint32_t)(4 * half + c)) ^ swz) << 4);
                         st_shared_v4(sh + off, hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-                        st_shared_v4(sl + off, lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                        if (!TB_LO_DIRECT) st_shared_v4(sl + off, lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                    }
+                    if (TB_LO_DIRECT) {
+                        // (experiment) the lo halves leave through the LSU, 64 contiguous bytes per thread (lane = sample row):
+                        // 32 scattered 16-byte pieces per store instruction turned out 4x slower than the TMA route
+                        const long long e0 = (long long)t * TB_N + c0 + 32 * half;
+                        const int row = q * 32 + lane;
+                        if (row < rows && e0 + 32 <= NW) {
+                            uint4* dst = reinterpret_cast<uint4*>(out_lo + (long long)row * NW + e0);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) __stcs(dst + c, make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]));
+                        }
                     }
                 }
                 fence_proxy_async();
@@ -708,7 +721,7 @@ k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__
                 if (lane == 0) {
                     // rows = samples (rows >= G are clipped by TMA), columns = activations e of this tile
                     tma_store_3d_hint(&tmOh, sh, t * TB_N + c0, q * 32, 0, TC_EVICT_FIRST);
-                    tma_store_3d_hint(&tmOl, sl, t * TB_N + c0, q * 32, 0, TC_EVICT_FIRST);
+                    if (!TB_LO_DIRECT) tma_store_3d_hint(&tmOl, sl, t * TB_N + c0, q * 32, 0, TC_EVICT_FIRST);
                     tma_store_commit();
                 }
             }
@@ -909,7 +922,20 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
     // the basis layer runs on the tensor cores when z (plus the constant 1) fits one K = 32 block; its M dimension is the
     // samples, so a group is then 128 samples (the bases are read once per group)
     s->basis_mma = s->basis && ctx->M + 1 <= 32 && !ctx->opt_tc_simt_basis;
-    const int gmax = s->basis_mma ? 128 : TC_GMAX;
+    int gmax = s->basis_mma ? 128 : TC_GMAX;
+    {
+        // per-sample device memory of a group: split-BF16 activations of every stored layer + GEMM weights; keep a group
+        // under ~96 GB of the 180 GB (the bases, the dataset and the caller's buffers need room too)
+        double per_sample = 0;
+        int stored = 0;
+        for (int l = 0; l < m.L - 1; ++l) {
+            const double wpad = (m.dims[l + 1] + 63) / 64 * 64;
+            if (stored < 3) per_sample += 4.0 * (double)N * wpad;      // at most the basis buffer + two ping-pong buffers
+            ++stored;
+            per_sample += 4.0 * wpad * ((m.dims[l] + 63) / 64 * 64);
+        }
+        while (gmax > TC_GMAX && per_sample * gmax > 96e9) gmax -= TC_GMAX;
+    }
     s->G = ctx->opt_group > 0 ? std::min(ctx->opt_group, gmax) : gmax;
     const int G = s->G;
     int maxw = 0;
@@ -1040,10 +1066,10 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
             const int n_tiles = (int)((NW + TB_N - 1) / TB_N);
             const int grid = std::min(ctx->sm_count, n_tiles);
             switch (m.act[0]) {
-                case SSI_ACT_RELU:    k_tc_basis_mma<SSI_ACT_RELU><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles); break;
-                case SSI_ACT_TANH:    k_tc_basis_mma<SSI_ACT_TANH><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles); break;
-                case SSI_ACT_SIGMOID: k_tc_basis_mma<SSI_ACT_SIGMOID><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles); break;
-                default:              k_tc_basis_mma<SSI_ACT_IDENTITY><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles); break;
+                case SSI_ACT_RELU:    k_tc_basis_mma<SSI_ACT_RELU><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles, s->Bl, NW, s->G); break;
+                case SSI_ACT_TANH:    k_tc_basis_mma<SSI_ACT_TANH><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles, s->Bl, NW, s->G); break;
+                case SSI_ACT_SIGMOID: k_tc_basis_mma<SSI_ACT_SIGMOID><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles, s->Bl, NW, s->G); break;
+                default:              k_tc_basis_mma<SSI_ACT_IDENTITY><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles, s->Bl, NW, s->G); break;
             }
             SSI_LAUNCH_CHECK(ctx);
         }
