@@ -124,3 +124,31 @@ def test_first_layer_gemm_vs_basis_and_unfused_output(ssi, engine, dims, acts, N
             np.testing.assert_allclose(lp, ref, rtol=RTOL, err_msg=f"nobasis={nobasis} nofuse={nofuse}")
     engine.set_option("tc_noorder", 1)
     np.testing.assert_allclose(engine.logpost(Z, 0.8), ref, rtol=RTOL)
+
+
+@pytest.mark.parametrize("dims,acts,N,M,B,group", [
+    ((64, 192, 128, 3), (1, 2, 0), 517, 20, 150, 0),     # two groups of 128 + a ragged one; tanh second layer
+    ((40, 128, 10), (3, 0), 260, 31, 40, 0),             # M + 1 = 32: the largest subspace the tensor-core first layer takes
+    ((40, 128, 10), (1, 0), 260, 40, 37, 0),             # M + 1 > 32: FP32 SIMT basis layer, groups of 32
+    ((96, 128, 128, 10), (1, 1, 0), 300, 20, 70, 48),    # group size that is not a multiple of 32
+])
+def test_first_layer_on_tensor_cores_vs_simt_basis(ssi, engine, dims, acts, N, M, B, group):
+    """The first layer as a K = M+1 GEMM over the samples (k_tc_basis_mma) and as the FP32 SIMT combination
+    (k_tc_basis_layer) must both match the oracle; groups of up to 128 samples, ragged last group."""
+    prob, rng = _rand_problem(dims, acts, N, M, 99)
+    prob = orc.Problem(prob.dims, prob.acts, prob.X, prob.Y, prob.W_swa, (0.2 * prob.P).astype(np.float32))
+    Z = rng.standard_normal((M, B)).astype(np.float32)
+    _setup(engine, prob)
+    engine.set_option("path", ssi.PATH_TENSOR)
+    if group:
+        engine.set_option("group", group)
+    ref, _ = orc.logpost_batch(prob, Z, 0.8)
+    out = {}
+    for simt in (0, 1):
+        engine.set_option("tc_simt_basis", simt)
+        out[simt] = engine.logpost(Z, 0.8)
+        np.testing.assert_allclose(out[simt], ref, rtol=RTOL, err_msg=f"tc_simt_basis={simt}")
+        assert engine.stats().last_path == ssi.PATH_TENSOR
+    # a sample's value does not depend on the group it lands in
+    engine.set_option("tc_simt_basis", 0)
+    np.testing.assert_array_equal(engine.logpost(Z[:, 5:9], 0.8), out[0][5:9])
