@@ -24,6 +24,8 @@
  *     process (and one context) per GPU and shard chains by `chain_offset`; the
  *     counter-based RNG is keyed on the GLOBAL chain id so results do not depend on
  *     the number of GPUs.
+ *   - ssi_swa_finish / ssi_swa_finish_gram stage V_M in the device's constant bank: do not run them concurrently from two
+ *     host threads on contexts of the SAME device (every other entry point is independent across contexts).
  *   - there is no CPU fallback: every compute entry point fails with SSI_ERR_CUDA when
  *     no sm_100 device is usable.
  */

@@ -12,8 +12,8 @@
 //
 // Mapping.  A CTA owns one tile of 64 datapoints (lane l holds datapoints 2l, 2l+1) and a block of samples;
 // each warp walks its share of the samples ST at a time.  The z of a warp's current samples are warp-uniform:
-// they are read from the constant bank into uniform registers, so the inner FMAs are `FFMA R, R, UR, R`
-// (full issue rate: one vector register per bank) and the basis tile is the only per-lane operand.
+// they are loaded once per pass into registers as pairs of adjacent samples, so the inner products are packed FFMA2 with the
+// basis value as the scalar operand, and the basis tile is the only per-lane operand.
 // The basis tile lives in shared memory as [j][m][64] (conflict-free 8-byte reads); it is laid out per tile
 // in global memory once, so staging it is a contiguous copy.  Bound: FP32 FMA issue.
 #include "ssi_common.cuh"
@@ -23,15 +23,14 @@
 #define B1_TI 64
 #define B1_WARPS 8
 #define B1_THREADS (B1_WARPS * 32)
-#define B1_CONST_FLOATS 16384                 // 64 KB constant bank
-__constant__ float c_b1z[B1_CONST_FLOATS];    // [s][M], the samples of the current launch
 
 struct b1_params {
     int N, H, O, n_tiles, S, s_per_cta, act_out, w2n;
     long long n, w2_off, b2_off;
     const float* tiles;     // [tile][H][M+1][B1_TI]
     const float* PW;        // [P | W_swa], n x (M+1) column-major
-    const float* Z;         // [S][M] (device), the same samples as c_b1z
+    const float* Z;         // [S][M] (device)
+    const float* W2;        // [S/ST][H+1][ST][OT]: second-layer weights (j < H) and bias (j = H) of every sample, k_b1_project_w2
     const float* Y;         // O x N column-major
     double* partials;       // [S][n_tiles]
 };
@@ -50,25 +49,16 @@ k_logpost_basis1h(const b1_params p, const int act_hidden) {
     extern __shared__ float4 b1_smem4[];
     const int H = p.H;
     float* sB = reinterpret_cast<float*>(b1_smem4);           // [H][M+1][64]
-    float* sP2 = sB + (size_t)H * (M + 1) * B1_TI;            // [M+1][w2n]: second-layer rows of [P | W_swa]: (j*OT + o), bias at j = H
-    float* sW2 = sP2 + (M + 1) * p.w2n;                       // per warp [H+1][ST][OT]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x;
     const int s_begin = blockIdx.y * p.s_per_cta;
     const int s_end = min(p.S, s_begin + p.s_per_cta);
 
-    {   // stage the basis tile (contiguous) and the second-layer rows
+    {   // stage the basis tile (contiguous)
         const float4* src = reinterpret_cast<const float4*>(p.tiles + (size_t)tile * H * (M + 1) * B1_TI);
         float4* dst = reinterpret_cast<float4*>(sB);
         const int n4 = H * (M + 1) * B1_TI / 4;
         for (int e = tid; e < n4; e += B1_THREADS) dst[e] = __ldg(src + e);
-        for (int e = tid; e < (M + 1) * p.w2n; e += B1_THREADS) {
-            const int m = e / p.w2n, r = e - m * p.w2n;
-            const int j = r / OT, o = r - j * OT;
-            float v = 0.0f;
-            if (o < p.O && j <= H) v = p.PW[(j < H ? p.w2_off + o + (long long)j * p.O : p.b2_off + o) + (long long)m * p.n];
-            sP2[e] = v;
-        }
     }
     __syncthreads();
 
@@ -80,22 +70,12 @@ k_logpost_basis1h(const b1_params p, const int act_hidden) {
 #pragma unroll
         for (int o = 0; o < OT; ++o) y[d][o] = (i0 + d < p.N && o < p.O) ? p.Y[o + (i0 + d) * p.O] : 0.0f;
 
-    float* w2s = sW2 + warp * ((H + 1) * ST * OT);
     const float* bl = sB + 2 * lane;
 
     for (int s0 = s_begin + warp * ST; s0 < s_end; s0 += B1_WARPS * ST) {
-        // W2, b2 of this warp's ST samples:  (W_swa + P z)[second layer]   (src/space_inference.jl:91)
-        __syncwarp();
-        for (int e = lane; e < (H + 1) * ST * OT; e += 32) {
-            const int o = e % OT, t = (e / OT) % ST, j = e / (OT * ST);
-            const int s = min(s0 + t, p.S - 1);
-            const int r = j * OT + o;
-            float v = sP2[M * p.w2n + r];
-#pragma unroll
-            for (int m = 0; m < M; ++m) v = fmaf(sP2[m * p.w2n + r], p.Z[(long long)s * M + m], v);
-            w2s[e] = v;
-        }
-        __syncwarp();
+        // second-layer weights and bias of this warp's ST samples, (W_swa + P z)[second layer] (src/space_inference.jl:91),
+        // projected once per call by k_b1_project_w2: warp-uniform 16-byte loads that hit L1
+        const float* w2s = p.W2 + (size_t)(s0 / ST) * (H + 1) * ST * OT;
 
         // warp-uniform z of the ST samples (clamped: a partial block recomputes the last sample and drops it),
         // kept as pairs of adjacent samples: the inner products are packed FFMA2 (two samples per instruction; a
@@ -105,7 +85,7 @@ k_logpost_basis1h(const b1_params p, const int act_hidden) {
         for (int t = 0; t < ST; t += 2) {
             const int sa = min(s0 + t, p.S - 1), sb = min(s0 + t + 1, p.S - 1);
 #pragma unroll
-            for (int m = 0; m < M; ++m) z2[t / 2][m] = make_float2(c_b1z[sa * M + m], c_b1z[sb * M + m]);
+            for (int m = 0; m < M; ++m) z2[t / 2][m] = make_float2(__ldg(p.Z + (long long)sa * M + m), __ldg(p.Z + (long long)sb * M + m));
         }
 
         float2 pred[ST / 2][2][OT];      // [sample pair][datapoint][output] = (sample t, sample t+1)
@@ -123,13 +103,13 @@ k_logpost_basis1h(const b1_params p, const int act_hidden) {
             if (ST * OT % 4 == 0) {
 #pragma unroll
                 for (int q = 0; q < ST * OT; q += 4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(w2s + j * ST * OT + q);
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(w2s + j * ST * OT + q));
                     w[q] = w4.x; w[q + 1] = w4.y; w[q + 2] = w4.z; w[q + 3] = w4.w;
                 }
             } else {
 #pragma unroll
                 for (int q = 0; q < ST * OT; q += 2) {
-                    const float2 w2v = *reinterpret_cast<const float2*>(w2s + j * ST * OT + q);
+                    const float2 w2v = __ldg(reinterpret_cast<const float2*>(w2s + j * ST * OT + q));
                     w[q] = w2v.x; w[q + 1] = w2v.y;
                 }
             }
@@ -158,7 +138,7 @@ k_logpost_basis1h(const b1_params p, const int act_hidden) {
             double sse = 0.0;
 #pragma unroll
             for (int o = 0; o < OT; ++o) {
-                const float b2 = w2s[(H * ST + t) * OT + o];
+                const float b2 = __ldg(w2s + (H * ST + t) * OT + o);
 #pragma unroll
                 for (int d = 0; d < 2; ++d) {
                     if (o < p.O && i0 + d < p.N) {
@@ -192,7 +172,6 @@ k_logpost_basis1h_grad(const b1_params p, const int act_hidden, const float coef
     const int H = p.H;
     float* sB = reinterpret_cast<float*>(b1_smem4);           // [H][M+1][64]
     float* sP2 = sB + (size_t)H * (M + 1) * B1_TI;            // [M+1][w2n]: second-layer rows of [P | W_swa] (j), bias at j = H
-    float* sW2 = sP2 + (M + 1) * p.w2n;                       // per warp [H+1][ST]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x;
     const int s_begin = blockIdx.y * p.s_per_cta;
@@ -212,26 +191,16 @@ k_logpost_basis1h_grad(const b1_params p, const int act_hidden, const float coef
     __syncthreads();
     const long long i0 = (long long)tile * B1_TI + 2 * lane;
     const float y0 = i0 < p.N ? p.Y[i0] : 0.0f, y1 = i0 + 1 < p.N ? p.Y[i0 + 1] : 0.0f;
-    float* w2s = sW2 + warp * ((H + 1) * ST);
     const float* bl = sB + 2 * lane;
 
     for (int s0 = s_begin + warp * ST; s0 < s_end; s0 += B1_WARPS * ST) {
-        __syncwarp();
-        for (int e = lane; e < (H + 1) * ST; e += 32) {
-            const int t = e % ST, j = e / ST;
-            const int s = min(s0 + t, p.S - 1);
-            float v = sP2[M * p.w2n + j];
-#pragma unroll
-            for (int m = 0; m < M; ++m) v = fmaf(sP2[m * p.w2n + j], p.Z[(long long)s * M + m], v);
-            w2s[e] = v;
-        }
-        __syncwarp();
+        const float* w2s = p.W2 + (size_t)(s0 / ST) * (H + 1) * ST;
         float2 z2[ST / 2][M];
 #pragma unroll
         for (int t = 0; t < ST; t += 2) {
             const int sa = min(s0 + t, p.S - 1), sb = min(s0 + t + 1, p.S - 1);
 #pragma unroll
-            for (int m = 0; m < M; ++m) z2[t / 2][m] = make_float2(c_b1z[sa * M + m], c_b1z[sb * M + m]);
+            for (int m = 0; m < M; ++m) z2[t / 2][m] = make_float2(__ldg(p.Z + (long long)sa * M + m), __ldg(p.Z + (long long)sb * M + m));
         }
         float2 pred[ST / 2][2];          // [sample pair][datapoint]
         float2 dp[ST / 2][2][M];         // d pred / d z_m (without the bias row, added at the end)
@@ -249,7 +218,7 @@ k_logpost_basis1h_grad(const b1_params p, const int act_hidden, const float coef
             float2 b[M + 1];
 #pragma unroll
             for (int m = 0; m <= M; ++m) b[m] = *reinterpret_cast<const float2*>(bl + (j * (M + 1) + m) * B1_TI);
-            const float4 w4 = *reinterpret_cast<const float4*>(w2s + j * ST);
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(w2s + j * ST));
             const float2 wp[2] = {make_float2(w4.x, w4.y), make_float2(w4.z, w4.w)};
             float p2[M];
 #pragma unroll
@@ -281,7 +250,7 @@ k_logpost_basis1h_grad(const b1_params p, const int act_hidden, const float coef
         // residuals, squared error, e_i, and the reduction of e_i * d pred_i / d z_m over the tile's datapoints
 #pragma unroll
         for (int t = 0; t < ST; ++t) {
-            const float b2 = w2s[H * ST + t];
+            const float b2 = __ldg(w2s + H * ST + t);
             double sse = 0.0;
             float g[M];
 #pragma unroll
@@ -311,6 +280,27 @@ k_logpost_basis1h_grad(const b1_params p, const int act_hidden, const float coef
             }
         }
     }
+}
+
+// W2[s / ST][j][s % ST][o] = (W_swa + P z_s)[second layer]: weight (o, j) for j < H, bias o for j = H; zero for o >= O and for the
+// samples that pad the last block of ST  (K1 for the second layer, once per call)
+__global__ void __launch_bounds__(256)
+k_b1_project_w2(const float* __restrict__ PW, const float* __restrict__ Z, long long n, int M, int S, int H, int O, int OT, int ST,
+                long long w2_off, long long b2_off, float* __restrict__ out, long long total) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int o = (int)(e % OT);
+    const int t = (int)((e / OT) % ST);
+    const int j = (int)((e / OT / ST) % (H + 1));
+    const long long blk = e / OT / ST / (H + 1);
+    const long long s = blk * ST + t;
+    float v = 0.0f;
+    if (o < O && s < S) {
+        const long long k = j < H ? w2_off + o + (long long)j * O : b2_off + o;
+        v = PW[k + (long long)M * n];
+        for (int m = 0; m < M; ++m) v = fmaf(PW[k + (long long)m * n], Z[s * M + m], v);
+    }
+    out[e] = v;
 }
 
 // tiles[tile][j][m][ii] = bases[m][tile*64 + ii][j]  (zero beyond N): one-time re-layout so that a CTA's
@@ -352,8 +342,8 @@ static int b1_st(int M) { return M <= 6 ? 8 : (M <= 12 ? 4 : 2); }   // samples 
 static size_t b1_smem_bytes(const ssi_ctx* ctx) {
     const ssi_model_t& m = ctx->model;
     const int H = m.dims[1], M = ctx->M, OT = m.dims[2] <= 1 ? 1 : 2;
-    const int w2n = ((H + 1) * OT + 3) / 4 * 4;
-    return sizeof(float) * ((size_t)H * (M + 1) * B1_TI + (size_t)(M + 1) * w2n + (size_t)B1_WARPS * (H + 1) * b1_st(M) * OT);
+    (void)OT;
+    return sizeof(float) * ((size_t)H * (M + 1) * B1_TI);
 }
 
 static bool b1_m_supported(int M) { return (M >= 1 && M <= 8) || M == 10 || M == 12 || M == 16 || M == 20; }
@@ -421,6 +411,20 @@ static b1_kernel_t b1_pick(int M, int act) {
 
 int ssi_reduce_partials(ssi_ctx* ctx, const double* partials, int64_t B, int parts, double* d_out);
 
+// second-layer weights of the S samples of one launch, in blocks of ST samples; returns the device pointer (ctx scratch)
+static int b1_project_w2(ssi_ctx* ctx, const float* dZs, int S, int ST, int OT, const float** out) {
+    const ssi_model_t& m = ctx->model;
+    const int H = m.dims[1];
+    const long long blocks = (S + ST - 1) / ST;
+    const long long total = blocks * (H + 1) * ST * OT;
+    SSI_TRY(ssi_reserve(ctx, ctx->bW, sizeof(float) * (size_t)total));
+    k_b1_project_w2<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->dP, dZs, m.n, ctx->M, S, H, m.dims[2], OT, ST,
+                                                                             m.w_off[1], m.b_off[1], (float*)ctx->bW.p, total);
+    SSI_LAUNCH_CHECK(ctx);
+    *out = (const float*)ctx->bW.p;
+    return SSI_OK;
+}
+
 typedef void (*b1g_kernel_t)(const b1_params, const int, const float, float*, const long long);
 template <int M>
 static b1g_kernel_t b1g_pick_act(int act) {
@@ -448,7 +452,7 @@ static size_t b1g_smem_bytes(const ssi_ctx* ctx) {
     const ssi_model_t& m = ctx->model;
     const int H = m.dims[1], M = ctx->M;
     const int w2n = (H + 1 + 3) / 4 * 4;
-    return sizeof(float) * ((size_t)H * (M + 1) * B1_TI + (size_t)(M + 1) * w2n + (size_t)B1_WARPS * (H + 1) * B1G_ST);
+    return sizeof(float) * ((size_t)H * (M + 1) * B1_TI + (size_t)(M + 1) * w2n);
 }
 
 // the fast value+gradient path: one hidden layer, scalar output, M <= 8 (tangent accumulators live in registers)
@@ -472,13 +476,10 @@ int ssi_b1_grad_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double coef, doubl
     const long long slab = (long long)M * B;
 
     const int ST = B1G_ST;
-    const int64_t max_s = (int64_t)(B1_CONST_FLOATS / M) / (B1_WARPS * ST) * (B1_WARPS * ST);
-    const int64_t n_sub = (B + max_s - 1) / max_s;
-    int64_t per = (B + n_sub - 1) / n_sub;
-    per = (per + B1_WARPS * ST - 1) / (B1_WARPS * ST) * (B1_WARPS * ST);
+    // one launch per 2^20 samples (int indices inside the kernel); the warp-uniform z are read from global memory
+    const int64_t per = 1 << 20;
     for (int64_t b0 = 0; b0 < B; b0 += per) {
         const int S = (int)std::min<int64_t>(per, B - b0);
-        SSI_CUDA(ctx, cudaMemcpyToSymbolAsync(c_b1z, dZ + b0 * M, sizeof(float) * (size_t)S * M, 0, cudaMemcpyDeviceToDevice, ctx->stream));
         b1_params p{};
         p.N = (int)ctx->N; p.H = H; p.O = 1; p.n_tiles = s->n_tiles; p.S = S; p.act_out = m.act[1];
         p.w2n = (H + 1 + 3) / 4 * 4;
@@ -488,6 +489,7 @@ int ssi_b1_grad_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double coef, doubl
         p.n = m.n; p.w2_off = m.w_off[1]; p.b2_off = m.b_off[1];
         p.tiles = s->tiles; p.PW = ctx->dP; p.Z = dZ + b0 * M; p.Y = ctx->dY;
         p.partials = partials + b0 * s->n_tiles;
+        SSI_TRY(b1_project_w2(ctx, p.Z, S, ST, 1, &p.W2));
         dim3 grid(s->n_tiles, (S + p.s_per_cta - 1) / p.s_per_cta);
         ssi_kt_begin(ctx);
         kern<<<grid, B1_THREADS, smem, ctx->stream>>>(p, m.act[0], (float)coef, gpart + b0 * M, slab);
@@ -512,13 +514,10 @@ int ssi_b1_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
     double* partials = (double*)ctx->bPartials.p;
 
     const int ST = b1_st(M);
-    const int64_t max_s = (int64_t)(B1_CONST_FLOATS / M) / (B1_WARPS * ST) * (B1_WARPS * ST);
-    const int64_t n_sub = (B + max_s - 1) / max_s;
-    int64_t per = (B + n_sub - 1) / n_sub;
-    per = (per + B1_WARPS * ST - 1) / (B1_WARPS * ST) * (B1_WARPS * ST);
+    // one launch per 2^20 samples (int indices inside the kernel); the warp-uniform z are read from global memory
+    const int64_t per = 1 << 20;
     for (int64_t b0 = 0; b0 < B; b0 += per) {
         const int S = (int)std::min<int64_t>(per, B - b0);
-        SSI_CUDA(ctx, cudaMemcpyToSymbolAsync(c_b1z, dZ + b0 * M, sizeof(float) * (size_t)S * M, 0, cudaMemcpyDeviceToDevice, ctx->stream));
         b1_params p{};
         p.N = (int)ctx->N; p.H = H; p.O = O; p.n_tiles = s->n_tiles; p.S = S; p.act_out = m.act[1];
         p.w2n = ((H + 1) * OT + 3) / 4 * 4;
@@ -529,6 +528,7 @@ int ssi_b1_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
         p.n = m.n; p.w2_off = m.w_off[1]; p.b2_off = m.b_off[1];
         p.tiles = s->tiles; p.PW = ctx->dP; p.Z = dZ + b0 * M; p.Y = ctx->dY;
         p.partials = partials + b0 * s->n_tiles;
+        SSI_TRY(b1_project_w2(ctx, p.Z, S, ST, OT, &p.W2));
         dim3 grid(s->n_tiles, (S + p.s_per_cta - 1) / p.s_per_cta);
         ssi_kt_begin(ctx);
         kern<<<grid, B1_THREADS, smem, ctx->stream>>>(p, m.act[0]);
