@@ -131,6 +131,8 @@ def test_first_layer_gemm_vs_basis_and_unfused_output(ssi, engine, dims, acts, N
     ((40, 128, 10), (3, 0), 260, 31, 40, 0),             # M + 1 = 32: the largest subspace the tensor-core first layer takes
     ((40, 128, 10), (1, 0), 260, 40, 37, 0),             # M + 1 > 32: FP32 SIMT basis layer, groups of 32
     ((96, 128, 128, 10), (1, 1, 0), 300, 20, 70, 48),    # group size that is not a multiple of 32
+    ((32, 128, 64, 20), (1, 1, 0), 200, 6, 10, 0),       # O > 12: the output layer is its own GEMM (FINAL epilogue)
+    ((24, 64, 128, 64, 192, 5), (1, 2, 3, 1, 0), 130, 9, 6, 0),   # deep chain: HIDDEN epilogues ping-pong between the two buffers
 ])
 def test_first_layer_on_tensor_cores_vs_simt_basis(ssi, engine, dims, acts, N, M, B, group):
     """The first layer as a K = M+1 GEMM over the samples (k_tc_basis_mma) and as the FP32 SIMT combination
