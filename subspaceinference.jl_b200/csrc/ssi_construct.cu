@@ -235,8 +235,10 @@ k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg
                 double c = 1.0, s = 0.0;
                 if (q < K) {
                     const double apq = A[p + (long long)q * ld];
-                    if (apq != 0.0) {
-                        const double app = A[p + (long long)p * ld], aqq = A[q + (long long)q * ld];
+                    const double app = A[p + (long long)p * ld], aqq = A[q + (long long)q * ld];
+                    // a rotation that cannot change the diagonal at working precision is skipped (c = 1, s = 0 exactly), and
+                    // so is every 2x2 block update whose two rotations are both the identity: late sweeps touch little
+                    if (fabs(apq) > 1.1102230246251565e-16 * sqrt(fabs(app * aqq))) {
                         const double tau = (aqq - app) / (2.0 * apq);
                         const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
                         c = 1.0 / sqrt(1.0 + t * t);
@@ -260,6 +262,7 @@ k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg
                     const int p = pp[ik], q = qq[ik];
                     const double ck = cs[ik], sk = sn[ik];
                     if (q < 0 && v < 0) continue;
+                    if (sk == 0.0 && sl == 0.0) continue;
                     if (q < 0) {            // single row p, columns (u,v): only the column rotation
                         const double a = Au[p], b = Av[p];
                         Au[p] = cl * a - sl * b;
@@ -286,6 +289,7 @@ k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg
                 const int u = pp[il], v = qq[il];
                 if (v < 0) continue;
                 const double cl = cs[il], sl = sn[il];
+                if (sl == 0.0) continue;
                 double* Vu = V + u * ld;
                 double* Vv = V + v * ld;
                 for (int k = jx; k < K; k += JAC_W) {
