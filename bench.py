@@ -12,7 +12,8 @@ Workloads (BASELINE.json configs):
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload wide|uci] [--batch B]
   python bench.py --impl reference ...      # the CPU restatement of the reference's path
 
-`value` is timed with CUDA events with Z already resident in HBM; `e2e` goes through the
+Synthetic inputs come from workloads.py (NumPy); oracle/ is touched only as the checker after the timed region and by the
+CPU-baseline / --impl reference legs.  `value` is timed with CUDA events with Z already resident in HBM; `e2e` goes through the
 reference-facing host call (host Z in pinned memory -> H2D -> kernels -> D2H of lp) every step.
 Multi-GPU: proposals are sharded across ranks (no data-path collective); lp is all-gathered
 (NCCL) inside the step, as the sampler needs it.
@@ -141,12 +142,9 @@ def cpu_reference(workload: str, budget_s: float, steps: int = 1, warmup: int = 
 
 
 def workload_config(workload, B, world):
-    sys.path.insert(0, str(ROOT / "oracle"))
-    import ssi_oracle as orc
+    import workloads
     name = WORKLOADS[workload][0]
-    dims = {"wide": (784, 1024, 1024, 10), "uci": (13, 50, 1)}[name]
-    N = {"wide": 60000, "uci": 10000}[name]
-    M = {"wide": 20, "uci": 5}[name]
+    dims, _, M, N, _ = workloads.CONFIGS[name]
     what = (f"{MH_STEPS} on-device {'MALA' if workload.endswith('-mala') else 'RWMH'} steps of {B} chains per GPU (one batched "
             f"log-posterior{' + gradient' if workload.endswith('-mala') else ''} per step)" if workload.endswith(("-mh", "-mala"))
             else f"batched log-posterior over {B} subspace points per GPU")
@@ -196,9 +194,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    sys.path.insert(0, str(ROOT / "oracle"))
-    import ssi_oracle as orc
     import subspaceinference_jl_b200 as ssi
+    import workloads              # synthetic inputs (NumPy); the oracle is only the checker after the timed region
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -209,7 +206,7 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     name, _, sigma_m, zs = WORKLOADS[args.workload]
-    prob = orc.make_problem(name)
+    prob = workloads.make(name)
     B = args.batch
     eng = ssi.Engine(local_rank)
     eng.set_model(prob.dims, prob.acts)
@@ -302,7 +299,10 @@ def main():
 
     # sanity: the timed path produced the oracle's numbers (one sample, checked after timing)
     if rank == 0:
-        ref = orc.density(prob, Z_host[0].numpy().astype(np.float64), sigma_m)
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import ssi_oracle as orc
+        ref = orc.density(orc.Problem(prob.dims, prob.acts, prob.X, prob.Y, prob.W_swa, prob.P),
+                          Z_host[0].numpy().astype(np.float64), sigma_m)
         got = float(lp_host[0])          # MH: trace entry (chain 0, step 0) = lp(z0)
         if not np.isfinite(got) or abs(got - ref) > 1e-5 * abs(ref):
             raise SystemExit(f"bench result mismatch vs oracle: {got} vs {ref}")
@@ -310,7 +310,7 @@ def main():
     if rank == 0:
         peaks = load_peaks()
         units_step = float(B) * world * prob.N * units_per_eval_batch
-        flops_unit = 2.0 * sum(a * b for a, b in zip(prob.dims[:-1], prob.dims[1:])) + 2.0 * orc.n_params(prob.dims) * prob.M / prob.N
+        flops_unit = 2.0 * sum(a * b for a, b in zip(prob.dims[:-1], prob.dims[1:])) + 2.0 * prob.n * prob.M / prob.N
         value = units_step * args.steps / (ms_dev * 1e-3)
         e2e = units_step * e2e_steps / (ms_e2e * 1e-3)
         per_gpu_flops = flops_unit * B * prob.N * units_per_eval_batch * args.steps / (ms_dev * 1e-3)

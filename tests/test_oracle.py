@@ -294,3 +294,15 @@ def test_next_rows_golden_fixture_is_reproduced():
     traj, mu, sd = orc.predictive_sweep(prob.dims, prob.acts, prob.W_swa, prob.P, g["pred_Z"], g["pred_Xg"])
     np.testing.assert_allclose(mu, g["pred_mean"], rtol=1e-12)
     np.testing.assert_allclose(sd, g["pred_std"], rtol=1e-10)
+
+
+def test_bench_workloads_match_the_oracle_problems():
+    """workloads.py (what bench.py times) generates exactly the problems the oracle-based tests use."""
+    import sys
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    import workloads
+    for name, N in (("readme", None), ("uci", 300), ("wide", 40)):
+        a, b = workloads.make(name, N=N), orc.make_problem(name, N=N)
+        assert tuple(a.dims) == tuple(b.dims) and tuple(a.acts) == tuple(b.acts) and a.M == b.M and a.N == b.N
+        for k in ("X", "Y", "W_swa", "P"):
+            np.testing.assert_array_equal(getattr(a, k), getattr(b, k))
