@@ -667,7 +667,11 @@ k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__
         // staging: per warp TB_SBUF buffers of (hi | lo) x [32 samples][64 activations] = 2 x 4 KB, SWIZZLE_128B.  128-byte
         // rows: the TMA store engine is bound by rows per cycle (64-byte rows capped the kernel at 2.2 TB/s of writes).
         // Also measured and dropped: one 256-byte 1-D bulk copy per lane and half tile (10.3 ms against 8.7 ms: the engine
-        // then pays per instruction), and the lo halves through the LSU (32 ms).
+        // then pays per instruction); the lo halves through the LSU, scattered (32 ms) or read back transposed and
+        // coalesced (8.8 ms: no gain); and two output layouts that make these stores (nearly) sequential, [e/64][sample][64]
+        // and [datapoint][sample][width]: the layer drops to 6.7 / 7.6 ms, but the GEMM kernel that reads the activations
+        // then loses its contiguous 256 KB A tiles and slows from 32.0 to 34.3 / 34.5 ms per 128 samples (DRAM reads
+        // 57 -> 75 GB), a net loss.
         const uint32_t stage_w = smem_base + TB_OFF_STORE + (uint32_t)(warp - 2) * (TB_SBUF * 8192);
         const uint32_t swz = (uint32_t)(lane & 7);
         uint32_t chunk_ctr = 0, tile = 0, sbuf = 0;
