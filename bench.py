@@ -42,7 +42,10 @@ WORKLOADS = {
     "uci-mh": ("uci", 4096, 0.1, 0.01),
     # the same with the Metropolis-adjusted Langevin sampler (value + gradient per step; units are still forward evaluations)
     "uci-mala": ("uci", 4096, 0.1, 0.01),
+    # configs[4] per GPU: 8192 of the 65536 chains in the M=20 subspace of the wide MLP, samples and log-probs gathered with NCCL
+    "wide-mh": ("wide", 8192, 1.0, 0.02),
 }
+MH_STEPS_BY_WORKLOAD = {"wide-mh": 2}      # a wide MH step is 8192 x 60000 units (~3 s): two per bench step
 MH_STEPS = 100
 
 
@@ -143,6 +146,7 @@ def cpu_reference(workload: str, budget_s: float, steps: int = 1, warmup: int = 
 
 def workload_config(workload, B, world):
     import workloads
+    MH_STEPS = MH_STEPS_BY_WORKLOAD.get(workload, 100)
     name = WORKLOADS[workload][0]
     dims, _, M, N, _ = workloads.CONFIGS[name]
     what = (f"{MH_STEPS} on-device {'MALA' if workload.endswith('-mala') else 'RWMH'} steps of {B} chains per GPU (one batched "
@@ -150,7 +154,9 @@ def workload_config(workload, B, world):
             else f"batched log-posterior over {B} subspace points per GPU")
     return {"workload": f"{workload}: MLP {'-'.join(map(str, dims))}, N={N}, M={M}, {what}",
             "dims": list(dims), "N": N, "M": M, "batch_per_gpu": B, "global_batch": B * world,
-            "parallelism": f"proposals sharded x{world}, W_swa/P/X/Y replicated, NCCL all-gather of lp",
+            "parallelism": (f"chains sharded x{world}, W_swa/P/X/Y replicated, NCCL all-gather of the z and lp traces"
+                            if workload.endswith(("-mh", "-mala")) else
+                            f"proposals sharded x{world}, W_swa/P/X/Y replicated, NCCL all-gather of lp"),
             "l2": "inputs larger than L2 (X + per-sample activations stream through HBM); no explicit flush"}
 
 
@@ -233,6 +239,8 @@ def main():
 
     mh = args.workload.endswith(("-mh", "-mala"))
     mh_kind = "mala" if args.workload.endswith("-mala") else "rwmh"
+    MH_STEPS = MH_STEPS_BY_WORKLOAD.get(args.workload, 100)
+    d_tr_all = None
     units_per_eval_batch = MH_STEPS if mh else 1
     if mh:
         d_lp_tr = torch.empty(B * MH_STEPS, dtype=torch.float64, device=dev)      # lp trace (n_chains x n_steps), stays on the device
@@ -242,6 +250,9 @@ def main():
         d_lp = d_lp_tr[B * (MH_STEPS - 1):]
         lp_host = lp_tr_host
         Z_host = torch.from_numpy((zs * rng.standard_normal((B, prob.M))).astype(np.float32)).pin_memory()   # z0 of every chain
+        if world > 1:      # every rank ends up with all chains' samples and log-probs (the only collectives)
+            d_tr_all = (torch.empty(world * d_z_tr.numel(), dtype=torch.float32, device=dev),
+                        torch.empty(world * d_lp_tr.numel(), dtype=torch.float64, device=dev))
 
     def step_device():
         if mh:
@@ -250,7 +261,11 @@ def main():
         else:
             eng.logpost_dev(dZ.data_ptr(), B, d_lp.data_ptr(), sigma_m=sigma_m)
         if world > 1:
-            dist.all_gather_into_tensor(d_lp_all, d_lp)
+            if mh:
+                dist.all_gather_into_tensor(d_tr_all[0], d_z_tr)
+                dist.all_gather_into_tensor(d_tr_all[1], d_lp_tr)
+            else:
+                dist.all_gather_into_tensor(d_lp_all, d_lp)
 
     def step_e2e():
         dZ.copy_(Z_host, non_blocking=True)
