@@ -149,6 +149,7 @@ int ssi_ctx_destroy(ssi_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ssi_tc_destroy(ctx);
     ssi_b1_destroy(ctx);
+    ssi_bm_destroy(ctx);
     cudaFree(ctx->dX); cudaFree(ctx->dY); cudaFree(ctx->dP); cudaFree(ctx->dSubGram);
     cudaFree(ctx->dSwaMean); cudaFree(ctx->dDev);
     ssi_buf_t* bufs[] = {&ctx->bZ, &ctx->bLp, &ctx->bTerms, &ctx->bPartials, &ctx->bW, &ctx->bH0, &ctx->bH1, &ctx->bGram,
@@ -192,20 +193,21 @@ int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
     if (!strcmp(key, "group")) {
         if (value < 0 || value > 4096) return ssi_fail(ctx, SSI_ERR_ARG, "group out of range");
         ctx->opt_group = (int)value;
-        ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx);
+        ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx); ssi_bm_invalidate(ctx);
         return SSI_OK;
     }
-    if (!strcmp(key, "tc_nofuse")) { ctx->opt_tc_nofuse = value != 0; ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx); return SSI_OK; }
+    if (!strcmp(key, "tc_nofuse")) { ctx->opt_tc_nofuse = value != 0; ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx); ssi_bm_invalidate(ctx); return SSI_OK; }
     // gram_fp64: 1 = always the FP64 SIMT Gram, 0 = tensor-core Gram guarded by the conditioning check (default),
     // -1 = tensor-core Gram without the check (measurement only)
     if (!strcmp(key, "gram_fp64")) { ctx->opt_gram_fp64 = (int)value; return SSI_OK; }
     if (!strcmp(key, "gram_chunk")) { ctx->opt_gram_chunk = (int)value; return SSI_OK; }
-    if (!strcmp(key, "tc_nobasis")) { ctx->opt_tc_nobasis = value != 0; ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx); return SSI_OK; }
+    if (!strcmp(key, "tc_nobasis")) { ctx->opt_tc_nobasis = value != 0; ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx); ssi_bm_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "time_dominant")) {
         ctx->opt_time_dominant = value != 0;
         ctx->stats.dominant_ms = 0; ctx->stats.dominant_launches = 0; ctx->kt_used = 0;
         return SSI_OK;
     }
+    if (!strcmp(key, "b1_simt")) { ctx->opt_b1_simt = value != 0; return SSI_OK; }
     if (!strcmp(key, "tc_simt_basis")) { ctx->opt_tc_simt_basis = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "tc_noorder")) { ctx->opt_tc_noorder = value != 0; return SSI_OK; }
     return ssi_fail(ctx, SSI_ERR_ARG, "unknown option '%s'", key);
@@ -246,7 +248,7 @@ int ssi_set_model(ssi_ctx* ctx, int n_layers, const int32_t* dims, const int32_t
     ctx->model = m;
     ctx->has_model = true;
     if (shape_changed) { ctx->has_data = false; ctx->has_sub = false; }
-    ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx);
+    ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx); ssi_bm_invalidate(ctx);
     return SSI_OK;
 }
 
@@ -268,7 +270,7 @@ int ssi_set_data(ssi_ctx* ctx, const float* X, const float* Y, int64_t N) {
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->N = N;
     ctx->has_data = true;
-    ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx);
+    ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx); ssi_bm_invalidate(ctx);
     return SSI_OK;
 }
 
@@ -291,7 +293,7 @@ static int install_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, in
     SSI_TRY(ssi_subspace_gram(ctx));
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->has_sub = true;
-    ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx);
+    ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx); ssi_bm_invalidate(ctx);
     return SSI_OK;
 }
 

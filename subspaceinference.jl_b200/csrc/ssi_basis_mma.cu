@@ -1,0 +1,393 @@
+// ssi_basis_mma.cu — the BASIS path on the tensor cores: Chain(Dense(in, H, act), Dense(H, 1)) with H <= 64 and M + 1 <= 32,
+// many samples ("stack samples along the MMA M dimension").  BASELINE configs[1]: 13-50-1 with 4096 chains.
+//
+// The first layer is affine in z (see ssi_basis.cu): with z augmented by a constant 1,
+//     pre[s, e] = sum_{m <= M} zaug[s, m] * basesT[e, m],     e = (datapoint i, hidden unit j) = i*Hp + j,   K = 16 or 32,
+// is a GEMM whose M dimension is the SAMPLES.  A CTA owns 256 samples (two 128-row A operands resident in shared memory
+// for the whole kernel) and walks tiles of 128 activations (128/Hp datapoints): the basis tile is fetched once by TMA and
+// multiplied with both sample groups (three-way BF16 split of both operands, six products, FP32 accumulate in TMEM, two 128-column accumulators
+// per group so that the MMAs of tile t+1 run under the epilogue of tile t).  The epilogue never stores the hidden layer: lane = sample, so each thread keeps ITS sample's second-layer
+// weights in registers, applies the activation to its 256 TMEM columns, folds them into Hp-long dot products (the output
+// layer), subtracts y and accumulates the squared error in FP64.  One FP64 partial per (sample, CTA) leaves the kernel.
+//
+// Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-9 epilogue (warp w: TMEM lane quarter w % 4 of
+// sample group (w - 2) / 4).  Bound: epilogue instruction issue (~2.2 instructions per hidden unit and sample).
+#include "ssi_common.cuh"
+#include "ssi_ptx.cuh"
+
+#include <algorithm>
+
+typedef __nv_bfloat16 bf16;
+
+#define BM_THREADS 320
+#define BM_N 128                       // activations per tile (4 accumulators of 128 TMEM columns: 2 sample groups x 2 buffers)
+#define BM_STAGES 4
+#define BM_MAXHP 64
+
+struct bm_params {
+    int n_tiles;            // ceil(N * Hp / 256)
+    int Hp, H, N, S;        // padded / true hidden width, datapoints, samples of this launch
+    int act_out;
+    int parts;              // CTAs per block of 256 samples = partials per sample
+    const float* W2;        // [S][H + 1]: second-layer weights and bias of every sample
+    const float* Y;         // N targets
+    double* partials;       // [S][parts]
+};
+
+template <int ACT>
+__device__ __forceinline__ float bm_act(float v) {
+    if (ACT == SSI_ACT_RELU) return fmaxf(v, 0.0f);
+    if (ACT == SSI_ACT_TANH) return tanhf(v);
+    if (ACT == SSI_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+    return v;
+}
+
+// KB = 16 (SWIZZLE_32B rows of 32 bytes) or 32 (SWIZZLE_64B rows of 64 bytes)
+template <int KB>
+__device__ __forceinline__ uint64_t bm_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * KB * 2) >> 4) << 32;           // stride between 8-row groups
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(KB == 16 ? 6 : 4) << 61;            // SWIZZLE_32B : SWIZZLE_64B
+    return d;
+}
+
+template <int ACT, int KB, int HP>
+__global__ void __launch_bounds__(BM_THREADS, 1)
+k_b1_mma(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmT, const bm_params p) {
+    constexpr uint32_t ROW = KB * 2;                       // bytes per operand row
+    constexpr uint32_t B_TILE = BM_N * ROW;                // one of (hi, mid, lo)
+    constexpr uint32_t STAGE = 3 * B_TILE;
+    constexpr uint32_t Z_TILE = 128 * ROW;                 // one sample group, one of (hi, mid, lo)
+    constexpr uint32_t OFF_Z = BM_STAGES * STAGE;          // [group][part]
+    constexpr uint32_t OFF_BAR = OFF_Z + 6 * Z_TILE;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);     // full[4] empty[4] tfull[2][2] tempty[2][2] zfull
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 20);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + 8 * BM_STAGES;
+    const uint32_t bar_tfull = bar_empty + 8 * BM_STAGES, bar_tempty = bar_tfull + 32, bar_z = bar_tempty + 32;
+    const int block = blockIdx.y;                          // block of 256 samples
+
+    if (threadIdx.x == 0) {
+        if (smem_base & 1023u) { printf("ssi_basis_mma: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+        for (int s = 0; s < BM_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 4; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 128); }
+        mbar_init(bar_z, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmT);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(bar_z, 6 * Z_TILE);
+            for (int g = 0; g < 2; ++g)
+                for (int part = 0; part < 3; ++part)
+                    tma_load_3d_hint(smem_base + OFF_Z + (3 * g + part) * Z_TILE, &tmZ, bar_z, 0, (block * 2 + g) * 128, part, TC_EVICT_LAST);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                const uint32_t full = bar_full + 8 * stage;
+                const uint32_t sB = smem_base + stage * STAGE;
+                mbar_expect_tx(full, STAGE);
+                for (int part = 0; part < 3; ++part)      // every block of samples re-reads the bases: keep them in L2
+                    tma_load_3d_hint(sB + part * B_TILE, &tmT, full, 0, t * BM_N, part, TC_EVICT_LAST);
+                if (++stage == BM_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(BM_N);
+            mbar_wait(bar_z, 0);
+            tc_fence_after();
+            int stage = 0;
+            uint32_t phase = 0, it = 0;
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t sB = smem_base + stage * STAGE;
+                const uint64_t bh = bm_desc<KB>(sB), bm = bm_desc<KB>(sB + B_TILE), bl = bm_desc<KB>(sB + 2 * B_TILE);
+#pragma unroll
+                const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
+                for (int g = 0; g < 2; ++g) {
+                    mbar_wait(bar_tempty + 8 * (2 * g + ab), aphase ^ 1);   // the epilogue two tiles back has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (2 * g + ab) * 128;
+                    const uint64_t zh = bm_desc<KB>(smem_base + OFF_Z + (3 * g) * Z_TILE);
+                    const uint64_t zm = bm_desc<KB>(smem_base + OFF_Z + (3 * g + 1) * Z_TILE);
+                    const uint64_t zl = bm_desc<KB>(smem_base + OFF_Z + (3 * g + 2) * Z_TILE);
+                    // every operand is split three ways, x = hi + mid + lo (24 bits), and the six products down to 2^-16 of
+                    // hi*hi are kept (smallest first): the tensor pipe has room (the kernel is bound by its epilogue), and
+                    // this layer's result is squared and summed straight into lp, with no wider layer behind it
+#pragma unroll
+                    for (int k = 0; k < KB / 16; ++k) {
+                        const uint64_t ko = (uint64_t)(k * 32 >> 4);
+                        umma_bf16(d_tmem, zm + ko, bm + ko, idesc, k != 0);
+                        umma_bf16(d_tmem, zl + ko, bh + ko, idesc, 1);
+                        umma_bf16(d_tmem, zh + ko, bl + ko, idesc, 1);
+                        umma_bf16(d_tmem, zm + ko, bh + ko, idesc, 1);
+                        umma_bf16(d_tmem, zh + ko, bm + ko, idesc, 1);
+                        umma_bf16(d_tmem, zh + ko, bh + ko, idesc, 1);
+                    }
+                    umma_commit(bar_tfull + 8 * (2 * g + ab));
+                }
+                umma_commit(bar_empty + 8 * stage);
+                if (++stage == BM_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3, g = (warp - 2) >> 2;      // a warp may only touch TMEM lanes [32 (warp % 4), +32)
+        const long long srow = (long long)block * 256 + g * 128 + q * 32 + lane;      // this thread's sample
+        const bool valid = srow < p.S;
+        // second-layer weights and bias of this sample, in registers for the whole kernel (zero for padded hidden units)
+        float w[HP];
+#pragma unroll
+        for (int j = 0; j < HP; ++j) w[j] = (valid && j < p.H) ? __ldg(p.W2 + srow * (p.H + 1) + j) : 0.0f;
+        const float b2 = valid ? __ldg(p.W2 + srow * (p.H + 1) + p.H) : 0.0f;
+        // squared errors: FP32 over 16 tiles (32-64 datapoints), then FP64 (one DFMA per datapoint and thread throttled the
+        // FP64 pipe: 16 % of the kernel's stall samples)
+        double sse = 0.0;
+        float sse_part = 0.0f;
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+            const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
+            const long long i_base = (long long)t * (BM_N / HP);
+            float yv[BM_N / HP];                                    // targets of this tile's datapoints, fetched before the wait
+#pragma unroll
+            for (int d = 0; d < BM_N / HP; ++d) yv[d] = (i_base + d < p.N) ? __ldg(p.Y + i_base + d) : 0.0f;
+            mbar_wait(bar_tfull + 8 * (2 * g + ab), aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (2 * g + ab) * 128;
+            // software pipeline over the chunks of 32 columns: the TMEM load of chunk c+1 is in flight while chunk c is
+            // folded into four independent partial dot products (a single accumulator would be a 64-long dependent FMA chain)
+            uint32_t v[2][32];
+            tmem_ld32(taddr, v[0]);
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int c = 0; c < BM_N / 32; ++c) {
+                tmem_ld_wait();
+                if (c + 1 < BM_N / 32) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                const int j0 = (c * 32) % HP;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    acc[j & 3] = fmaf(bm_act<ACT>(__uint_as_float(v[c & 1][j])), w[j0 + j], acc[j & 3]);
+                if (((c + 1) * 32) % HP == 0) {                      // a datapoint is complete
+                    const int d = (c * 32) / HP;
+                    const float pred = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+                    if (i_base + d < p.N) {
+                        const float df = ssi_act(pred + b2, p.act_out) - yv[d];
+                        sse_part = fmaf(df, df, sse_part);
+                    }
+                    acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * (2 * g + ab));
+            if ((it & 15) == 15) { sse += (double)sse_part; sse_part = 0.0f; }
+        }
+        sse += (double)sse_part;
+        if (valid) p.partials[srow * p.parts + blockIdx.x] = sse;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+__device__ __forceinline__ void bm_split3(float v, bf16& hi, bf16& mid, bf16& lo) {
+    hi = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hi);
+    mid = __float2bfloat16_rn(r1);
+    lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+}
+
+// zaug[part][s][m]: z[m, s] (m < M), 1 (m == M), 0 (padding, and rows s >= S up to a multiple of 256), split three ways
+__global__ void k_bm_pack_zaug(const float* __restrict__ Z, int M, long long S, long long S_pad, int KB, bf16* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S_pad * KB) return;
+    const long long s = t / KB;
+    const int m = (int)(t % KB);
+    const float v = s < S ? (m < M ? Z[m + s * M] : (m == M ? 1.0f : 0.0f)) : 0.0f;
+    bf16 hi, mid, lo;
+    bm_split3(v, hi, mid, lo);
+    out[t] = hi;
+    out[S_pad * KB + t] = mid;
+    out[2 * S_pad * KB + t] = lo;
+}
+
+// basesT[part][i*Hp + j][m] (K-major, KB BF16 per activation, split three ways)  <-  bases[m][i][j] FP32 (ld = H), zero padding
+__global__ void __launch_bounds__(256)
+k_bm_bases_kmajor(const float* __restrict__ bases, long long N, int H, int Hp, int M1, int KB, bf16* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = N * Hp * KB;
+    if (t >= total) return;
+    const int m = (int)(t % KB);
+    const long long e = t / KB;
+    const int j = (int)(e % Hp);
+    const long long i = e / Hp;
+    const float v = (m < M1 && j < H) ? bases[((long long)m * N + i) * H + j] : 0.0f;
+    bf16 hi, mid, lo;
+    bm_split3(v, hi, mid, lo);
+    out[t] = hi;
+    out[total + t] = mid;
+    out[2 * total + t] = lo;
+}
+
+// W2[s][j] = (W_swa + P z_s)[second layer]: weight j < H, bias at j = H
+__global__ void __launch_bounds__(256)
+k_bm_project_w2(const float* __restrict__ PW, const float* __restrict__ Z, long long n, int M, long long S, int H,
+                long long w2_off, long long b2_off, float* __restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S * (H + 1)) return;
+    const long long s = e / (H + 1);
+    const int j = (int)(e % (H + 1));
+    const long long k = j < H ? w2_off + j : b2_off;
+    float v = PW[k + (long long)M * n];
+    for (int m = 0; m < M; ++m) v = fmaf(PW[k + (long long)m * n], Z[s * M + m], v);
+    out[e] = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct ssi_bm_state {
+    bool ready = false;
+    int KB = 16, Hp = 64;
+    long long n_tiles = 0;
+    bf16* T = nullptr;                       // basesT [3][N*Hp][KB]  (hi, mid, lo)
+    CUtensorMap tmT;
+    PFN_encodeTiled encode = nullptr;
+};
+
+void ssi_bm_invalidate(ssi_ctx* ctx) {
+    if (ctx->bm) ctx->bm->ready = false;
+}
+void ssi_bm_destroy(ssi_ctx* ctx) {
+    if (!ctx->bm) return;
+    cudaFree(ctx->bm->T);
+    delete ctx->bm;
+    ctx->bm = nullptr;
+}
+
+bool ssi_bm_supported(const ssi_ctx* ctx) {
+    if (!ctx->has_model || !ctx->has_sub || !ctx->has_data) return false;
+    const ssi_model_t& m = ctx->model;
+    if (m.L != 2 || m.dims[2] != 1 || m.dims[1] > BM_MAXHP || ctx->M + 1 > 32) return false;
+    const long long Hp = m.dims[1] <= 32 ? 32 : 64;
+    return ctx->N * Hp < (1ll << 31) && !ctx->opt_b1_simt;
+}
+
+static int bm_make_map(ssi_ctx* ctx, CUtensorMap* map, void* base, uint64_t inner, uint64_t rows, uint32_t box_rows) {
+    cuuint64_t dims[3] = {inner, rows, 3};          // third dimension: the (hi, mid, lo) parts
+    cuuint64_t strides[2] = {inner * sizeof(bf16), inner * rows * sizeof(bf16)};
+    cuuint32_t box[3] = {(cuuint32_t)inner, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapSwizzle swz = inner == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const CUresult r = ctx->bm->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ssi_fail(ctx, SSI_ERR_CUDA, "cuTensorMapEncodeTiled (basis mma) failed with CUresult %d", (int)r);
+    return SSI_OK;
+}
+
+static int bm_prepare(ssi_ctx* ctx) {
+    if (!ctx->bm) ctx->bm = new ssi_bm_state();
+    ssi_bm_state* s = ctx->bm;
+    if (s->ready) return SSI_OK;
+    if (!s->encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SSI_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) return ssi_fail(ctx, SSI_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        s->encode = (PFN_encodeTiled)fn;
+    }
+    const ssi_model_t& m = ctx->model;
+    const int H = m.dims[1], M1 = ctx->M + 1;
+    const long long N = ctx->N;
+    s->KB = M1 <= 16 ? 16 : 32;
+    s->Hp = H <= 32 ? 32 : 64;
+    const long long NW = N * s->Hp;
+    s->n_tiles = (NW + BM_N - 1) / BM_N;
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(s->T);
+    s->T = nullptr;
+    SSI_CUDA(ctx, cudaMalloc(&s->T, sizeof(bf16) * 3 * (size_t)NW * s->KB));
+    // bases [m][N][H] in scratch, exact FP32 (bias parts included), then the K-major split-BF16 copy
+    SSI_TRY(ssi_reserve(ctx, ctx->bH0, sizeof(float) * (size_t)M1 * N * H));
+    SSI_TRY(ssi_build_first_layer_bases(ctx, (float*)ctx->bH0.p, H));
+    const long long total = NW * s->KB;
+    k_bm_bases_kmajor<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const float*)ctx->bH0.p, N, H, s->Hp, M1, s->KB, s->T);
+    SSI_LAUNCH_CHECK(ctx);
+    SSI_TRY(bm_make_map(ctx, &s->tmT, s->T, s->KB, (uint64_t)NW, BM_N));
+    s->ready = true;
+    return SSI_OK;
+}
+
+typedef void (*bm_kernel_t)(const CUtensorMap, const CUtensorMap, const bm_params);
+template <int KB, int HP>
+static bm_kernel_t bm_pick(int act) {
+    switch (act) {
+        case SSI_ACT_RELU:    return k_b1_mma<SSI_ACT_RELU, KB, HP>;
+        case SSI_ACT_TANH:    return k_b1_mma<SSI_ACT_TANH, KB, HP>;
+        case SSI_ACT_SIGMOID: return k_b1_mma<SSI_ACT_SIGMOID, KB, HP>;
+        default:              return k_b1_mma<SSI_ACT_IDENTITY, KB, HP>;
+    }
+}
+
+int ssi_reduce_partials(ssi_ctx* ctx, const double* partials, int64_t B, int parts, double* d_out);
+
+int ssi_bm_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
+    SSI_TRY(bm_prepare(ctx));
+    ssi_bm_state* s = ctx->bm;
+    const ssi_model_t& m = ctx->model;
+    const int M = ctx->M, H = m.dims[1], KB = s->KB, Hp = s->Hp;
+    bm_kernel_t kern = KB == 16 ? (Hp == 32 ? bm_pick<16, 32>(m.act[0]) : bm_pick<16, 64>(m.act[0]))
+                                : (Hp == 32 ? bm_pick<32, 32>(m.act[0]) : bm_pick<32, 64>(m.act[0]));
+    // at least 120 KB so that exactly one CTA (which allocates all 512 TMEM columns) is resident per SM
+    const size_t smem = std::max<size_t>((size_t)BM_STAGES * 3 * BM_N * KB * 2 + 6 * 128 * KB * 2 + 24 * 8 + 16, 120 * 1024);
+    SSI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    const int64_t n_blocks = (B + 255) / 256;
+    const int64_t S_pad = n_blocks * 256;
+    // CTAs per block of 256 samples = partial sums per sample.  It depends on the dataset and the device only, never on B,
+    // so a sample's summation order (hence its lp, bit for bit) is the same whatever else shares the call.
+    const int parts = (int)std::min<int64_t>(s->n_tiles, ctx->sm_count);
+    // scratch: zaug [3][S_pad][KB] bf16, W2 [B][H+1] floats, partials [B][parts] doubles
+    const size_t off_w2 = (3 * sizeof(bf16) * (size_t)S_pad * KB + 255) / 256 * 256;
+    SSI_TRY(ssi_reserve(ctx, ctx->bW, off_w2 + sizeof(float) * (size_t)B * (H + 1)));
+    SSI_TRY(ssi_reserve(ctx, ctx->bPartials, sizeof(double) * (size_t)B * parts));
+    bf16* zaug = (bf16*)ctx->bW.p;
+    float* W2 = (float*)((char*)ctx->bW.p + off_w2);
+    double* partials = (double*)ctx->bPartials.p;
+    k_bm_pack_zaug<<<(unsigned)((S_pad * KB + 255) / 256), 256, 0, ctx->stream>>>(dZ, M, B, S_pad, KB, zaug);
+    SSI_LAUNCH_CHECK(ctx);
+    k_bm_project_w2<<<(unsigned)((B * (H + 1) + 255) / 256), 256, 0, ctx->stream>>>(ctx->dP, dZ, m.n, M, B, H, m.w_off[1], m.b_off[1], W2);
+    SSI_LAUNCH_CHECK(ctx);
+    CUtensorMap tmZ;
+    SSI_TRY(bm_make_map(ctx, &tmZ, zaug, KB, (uint64_t)S_pad, 128));
+    bm_params p{};
+    p.n_tiles = (int)s->n_tiles; p.Hp = Hp; p.H = H; p.N = (int)ctx->N; p.S = (int)B; p.act_out = m.act[1]; p.parts = parts;
+    p.W2 = W2; p.Y = ctx->dY; p.partials = partials;
+    if (n_blocks > 65535) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "basis mma path: more than 16.7M samples per call");
+    dim3 grid(parts, (unsigned)n_blocks);
+    ssi_kt_begin(ctx);
+    kern<<<grid, BM_THREADS, smem, ctx->stream>>>(tmZ, s->tmT, p);
+    SSI_LAUNCH_CHECK(ctx);
+    ssi_kt_end(ctx);
+    return ssi_reduce_partials(ctx, partials, B, parts, d_sse);
+}

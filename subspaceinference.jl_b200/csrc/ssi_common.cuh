@@ -33,6 +33,7 @@ struct ssi_buf_t {
 
 struct ssi_tc_state;   // tensor-core path private state (ssi_tc.cu)
 struct ssi_b1_state;   // basis path private state (ssi_basis.cu)
+struct ssi_bm_state;   // basis path on the tensor cores (ssi_basis_mma.cu)
 
 struct ssi_ctx {
     int device = 0;
@@ -49,6 +50,7 @@ struct ssi_ctx {
     int opt_group = 0;
     int opt_tc_nofuse = 0;    // debugging / A-B: compute the output layer as its own GEMM
     int opt_tc_noorder = 0;
+    int opt_b1_simt = 0;       // A-B: BASIS path on CUDA cores (k_logpost_basis1h) instead of the tensor-core kernel (k_b1_mma)
     int opt_tc_simt_basis = 0; // A-B: first layer as the FP32 SIMT basis combination instead of the tensor-core one
     int opt_gram_fp64 = 0;    // force the FP64 SIMT Gram (default: tensor-core TF32x2 Gram for large n, K <= 128)
     int opt_gram_chunk = 0;   // tiles (32 rows) per FP32 accumulation chunk of the tensor-core Gram (default 32)
@@ -83,6 +85,7 @@ struct ssi_ctx {
     ssi_tc_state* tc = nullptr;
     // basis path (one hidden layer, narrow output)
     ssi_b1_state* b1 = nullptr;
+    ssi_bm_state* bm = nullptr;
 
     // stats
     ssi_stats_t stats{};
@@ -163,6 +166,12 @@ int  ssi_b1_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse);
 // value + likelihood gradient: SSE (B doubles) and per-tile gradient partials [n_tiles][M x B] floats (returned pointer)
 bool ssi_b1_grad_supported(const ssi_ctx* ctx);
 int  ssi_b1_grad_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double coef, double* d_sse, float** d_gpart, int* n_parts);
+
+// basis path on the tensor cores (ssi_basis_mma.cu): O = 1, H <= 64, M + 1 <= 32
+bool ssi_bm_supported(const ssi_ctx* ctx);
+void ssi_bm_invalidate(ssi_ctx* ctx);
+void ssi_bm_destroy(ssi_ctx* ctx);
+int  ssi_bm_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse);
 
 // ---- device helpers ---------------------------------------------------------------------
 __device__ __forceinline__ float ssi_act(float v, int act) {

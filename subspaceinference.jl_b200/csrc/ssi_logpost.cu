@@ -571,7 +571,7 @@ int ssi_logpost_finalize(ssi_ctx* ctx, const double* d_sse, const float* dZ, int
 static int choose_path(ssi_ctx* ctx) {
     if (ctx->opt_path != SSI_PATH_AUTO) return ctx->opt_path;
     if (ssi_tc_preferred(ctx)) return SSI_PATH_TENSOR;
-    if (ssi_b1_supported(ctx)) return SSI_PATH_BASIS;
+    if (ssi_bm_supported(ctx) || ssi_b1_supported(ctx)) return SSI_PATH_BASIS;
     fused_desc_t d{};
     size_t smem = 0;
     if (fused_layout(ctx, d, smem) && smem <= 100 * 1024) return SSI_PATH_FUSED;
@@ -596,8 +596,11 @@ int ssi_logpost_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m,
         if (!ssi_tc_supported(ctx)) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "tensor path does not support this model shape");
         rc = ssi_tc_sse(ctx, dZ, B, d_sse);
     } else if (path == SSI_PATH_BASIS) {
-        if (!ssi_b1_supported(ctx)) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "basis path needs Chain(Dense, Dense) with O <= 2 and M in {1..8, 10, 12, 16, 20}");
-        rc = ssi_b1_sse(ctx, dZ, B, d_sse);
+        // scalar output, H <= 64, M + 1 <= 32: samples along the MMA M dimension (ssi_basis_mma.cu); else CUDA cores
+        if (ssi_bm_supported(ctx)) rc = ssi_bm_sse(ctx, dZ, B, d_sse);
+        else if (ssi_b1_supported(ctx)) rc = ssi_b1_sse(ctx, dZ, B, d_sse);
+        else return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "basis path needs Chain(Dense, Dense) with O = 1, H <= 64, M <= 31 (tensor cores) or "
+                                                       "O <= 2, M in {1..8, 10, 12, 16, 20} and a basis tile that fits shared memory (CUDA cores)");
     } else if (path == SSI_PATH_FUSED) {
         fused_desc_t d{};
         size_t smem = 0;

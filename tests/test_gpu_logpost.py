@@ -194,3 +194,36 @@ def test_gradient_vs_oracle(ssi, engine, dims, acts, N, M, B):
     lp_b, g_b = engine.logpost_grad(Z, 0.7, 1.3, 0.9, mask=7)
     np.testing.assert_array_equal(g_a, g_b[:, :2])
     np.testing.assert_array_equal(lp_a, lp_b[:2])
+
+
+@pytest.mark.parametrize("dims,acts,N,M,B", [
+    ((13, 50, 1), (1, 0), 10000, 5, 700),      # C2 shape: K = 16, Hp = 64, three blocks of 256 samples (ragged)
+    ((13, 50, 1), (1, 0), 333, 5, 1),          # a single sample, ragged datapoint tail
+    ((6, 31, 1), (3, 2), 200, 12, 33),         # Hp = 32, sigmoid hidden (padded units must cancel), tanh output
+    ((4, 64, 1), (2, 0), 65, 20, 300),         # K = 32 (M + 1 = 21), H = 64 exactly
+    ((5, 17, 1), (0, 1), 1, 31, 5),            # M + 1 = 32, one datapoint, identity hidden, relu output
+])
+def test_basis_path_on_tensor_cores_vs_oracle(ssi, engine, dims, acts, N, M, B):
+    """BASIS path, tensor-core kernel (samples along the MMA M dimension) and CUDA-core kernel: both within 1e-5 of the
+    Float64 oracle; the tensor-core result of a sample is bitwise independent of the batch it arrives in."""
+    rng = np.random.default_rng(hash((dims, N, M, B, "bm")) % (2 ** 32))
+    n = orc.n_params(dims)
+    prob = orc.Problem(dims, acts, rng.standard_normal((dims[0], N)).astype(np.float32),
+                       rng.standard_normal((dims[-1], N)).astype(np.float32), orc.glorot_flat(rng, dims),
+                       (0.3 * rng.standard_normal((n, M))).astype(np.float32))
+    Z = (0.7 * rng.standard_normal((M, B))).astype(np.float32)
+    _setup(engine, prob)
+    ref, _ = orc.logpost_batch(prob, Z, 0.7)
+    out = {}
+    for simt in (0, 1):
+        engine.set_option("b1_simt", simt)
+        try:
+            out[simt] = engine.logpost(Z, 0.7)
+        except ssi.SsiError as e:          # the CUDA-core kernel does not take every shape the tensor-core kernel takes
+            assert simt == 1 and e.code == -5
+            continue
+        assert engine.stats().last_path == (ssi.PATH_BASIS if simt == 0 else engine.stats().last_path)
+        np.testing.assert_allclose(out[simt], ref, rtol=RTOL, err_msg=f"b1_simt={simt}")
+    engine.set_option("b1_simt", 0)
+    k = min(B, 3)
+    np.testing.assert_array_equal(engine.logpost(Z[:, B - k:], 0.7), out[0][B - k:])
