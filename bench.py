@@ -336,7 +336,8 @@ def main():
             dom_name = "k_tc_layer<FUSED>: Dense layers 2..L as tcgen05 BF16x3 GEMM + fused output layer + squared error"
             dom_flops_unit = 2.0 * sum(a * b for a, b in zip(dims[1:-1], dims[2:]))
         else:
-            dom_name = {"basis": "k_logpost_basis1h: whole chain per (sample, datapoint), first layer affine in z",
+            dom_name = {"basis": "BASIS path (first layer affine in z): k_b1_mma on the tensor cores for the density, k_logpost_basis1h_grad "
+                                 "on CUDA cores for value+gradient (MALA)",
                         "fused": "k_logpost_fused: whole chain per (sample, datapoint)"}.get(path_used, path_used)
             dom_flops_unit = flops_unit
         units_launch = float(B) * prob.N * units_per_eval_batch * args.steps / max(dom_n, 1)
