@@ -11,11 +11,17 @@
 // layer), subtracts y and accumulates the squared error in FP64.  One FP64 partial per (sample, CTA) leaves the kernel.
 //
 // Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-9 epilogue (warp w: TMEM lane quarter w % 4 of
-// sample group (w - 2) / 4).  Bound: epilogue instruction issue (~2.2 instructions per hidden unit and sample).
+// sample group (w - 2) / 4).  Bound: the epilogue (register-file bandwidth of the dot products with per-sample weights).
+//
+// PACKED operands (M + 1 <= 8): K = 16 leaves most of the contraction index empty (6 of 16 for M = 5), so the six
+// (z part, basis part) products are laid side by side ALONG K instead of being issued as six MMAs: column c = term*(M+1) + m
+// of the packed operands holds (z_part[term][m], basis_part[term][m]), 6 (M+1) <= 48 columns = at most three K=16 slabs.
+// Same bytes in shared memory as the three (hi, mid, lo) tiles, half the MMAs.
 #include "ssi_common.cuh"
 #include "ssi_ptx.cuh"
 
 #include <algorithm>
+#include <cmath>
 
 typedef __nv_bfloat16 bf16;
 
@@ -28,8 +34,10 @@ struct bm_params {
     int n_tiles;            // ceil(N * Hp / 256)
     int Hp, H, N, S;        // padded / true hidden width, datapoints, samples of this launch
     int act_out;
-    int parts;              // CTAs per block of 256 samples = partials per sample
-    const float* W2;        // [S][H + 1]: second-layer weights and bias of every sample
+    int parts;              // partial sums per sample (tile t belongs to part t % parts); a CTA walks parts blockIdx.x, +gridDim.x, ..
+    int ns;                 // operand slabs per tile: 3 (hi, mid, lo) or, packed, ceil(6 (M+1) / 16)
+    const float* W2;        // [S][Hp]: second-layer weights of every sample (zero beyond H)
+    const float* B2;        // [S]: second-layer bias of every sample
     const float* Y;         // N targets
     double* partials;       // [S][parts]
 };
@@ -54,7 +62,7 @@ __device__ __forceinline__ uint64_t bm_desc(uint32_t smem_addr) {
     return d;
 }
 
-template <int ACT, int KB, int HP>
+template <int ACT, int KB, int HP, bool PACKED, bool OUT_ID, int VAR>
 __global__ void __launch_bounds__(BM_THREADS, 1)
 k_b1_mma(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmT, const bm_params p) {
     constexpr uint32_t ROW = KB * 2;                       // bytes per operand row
@@ -88,21 +96,23 @@ k_b1_mma(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtens
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_expect_tx(bar_z, 6 * Z_TILE);
+            const int ns = PACKED ? p.ns : 3;
+            mbar_expect_tx(bar_z, 2 * ns * Z_TILE);
             for (int g = 0; g < 2; ++g)
-                for (int part = 0; part < 3; ++part)
+                for (int part = 0; part < ns; ++part)
                     tma_load_3d_hint(smem_base + OFF_Z + (3 * g + part) * Z_TILE, &tmZ, bar_z, 0, (block * 2 + g) * 128, part, TC_EVICT_LAST);
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                const uint32_t full = bar_full + 8 * stage;
-                const uint32_t sB = smem_base + stage * STAGE;
-                mbar_expect_tx(full, STAGE);
-                for (int part = 0; part < 3; ++part)      // every block of samples re-reads the bases: keep them in L2
-                    tma_load_3d_hint(sB + part * B_TILE, &tmT, full, 0, t * BM_N, part, TC_EVICT_LAST);
-                if (++stage == BM_STAGES) { stage = 0; phase ^= 1; }
-            }
+            for (int pp = blockIdx.x; pp < p.parts; pp += gridDim.x)
+                for (int t = pp; t < p.n_tiles; t += p.parts) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t full = bar_full + 8 * stage;
+                    const uint32_t sB = smem_base + stage * STAGE;
+                    mbar_expect_tx(full, ns * B_TILE);
+                    for (int part = 0; part < ns; ++part)     // every block of samples re-reads the bases: keep them in L2
+                        tma_load_3d_hint(sB + part * B_TILE, &tmT, full, 0, t * BM_N, part, TC_EVICT_LAST);
+                    if (++stage == BM_STAGES) { stage = 0; phase ^= 1; }
+                }
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -111,91 +121,149 @@ k_b1_mma(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtens
             tc_fence_after();
             int stage = 0;
             uint32_t phase = 0, it = 0;
-            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
-                mbar_wait(bar_full + 8 * stage, phase);
-                tc_fence_after();
-                const uint32_t sB = smem_base + stage * STAGE;
-                const uint64_t bh = bm_desc<KB>(sB), bm = bm_desc<KB>(sB + B_TILE), bl = bm_desc<KB>(sB + 2 * B_TILE);
-#pragma unroll
-                const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
-                for (int g = 0; g < 2; ++g) {
-                    mbar_wait(bar_tempty + 8 * (2 * g + ab), aphase ^ 1);   // the epilogue two tiles back has drained this accumulator
+            for (int pp = blockIdx.x; pp < p.parts; pp += gridDim.x)
+                for (int t = pp; t < p.n_tiles; t += p.parts, ++it) {
+                    mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (2 * g + ab) * 128;
-                    const uint64_t zh = bm_desc<KB>(smem_base + OFF_Z + (3 * g) * Z_TILE);
-                    const uint64_t zm = bm_desc<KB>(smem_base + OFF_Z + (3 * g + 1) * Z_TILE);
-                    const uint64_t zl = bm_desc<KB>(smem_base + OFF_Z + (3 * g + 2) * Z_TILE);
-                    // every operand is split three ways, x = hi + mid + lo (24 bits), and the six products down to 2^-16 of
-                    // hi*hi are kept (smallest first): the tensor pipe has room (the kernel is bound by its epilogue), and
-                    // this layer's result is squared and summed straight into lp, with no wider layer behind it
+                    const uint32_t sB = smem_base + stage * STAGE;
+                    const uint64_t bh = bm_desc<KB>(sB), bm = bm_desc<KB>(sB + B_TILE), bl = bm_desc<KB>(sB + 2 * B_TILE);
+                    const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
+                    for (int g = 0; g < 2; ++g) {
+                        mbar_wait(bar_tempty + 8 * (2 * g + ab), aphase ^ 1);   // the epilogue two tiles back has drained this accumulator
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + (2 * g + ab) * 128;
+                        const uint64_t zh = bm_desc<KB>(smem_base + OFF_Z + (3 * g) * Z_TILE);
+                        const uint64_t zm = bm_desc<KB>(smem_base + OFF_Z + (3 * g + 1) * Z_TILE);
+                        const uint64_t zl = bm_desc<KB>(smem_base + OFF_Z + (3 * g + 2) * Z_TILE);
+                        if (PACKED) {
+                            // the six products sit side by side along K (see the header): one MMA per 16-column slab
+                            umma_bf16(d_tmem, zh, bh, idesc, 0);
+                            if (p.ns > 1) umma_bf16(d_tmem, zm, bm, idesc, 1);
+                            if (p.ns > 2) umma_bf16(d_tmem, zl, bl, idesc, 1);
+                        } else {
+                            // every operand is split three ways, x = hi + mid + lo (24 bits), and the six products down to 2^-16 of
+                            // hi*hi are kept (smallest first): this layer's result is squared and summed straight into lp, with
+                            // no wider layer behind it
 #pragma unroll
-                    for (int k = 0; k < KB / 16; ++k) {
-                        const uint64_t ko = (uint64_t)(k * 32 >> 4);
-                        umma_bf16(d_tmem, zm + ko, bm + ko, idesc, k != 0);
-                        umma_bf16(d_tmem, zl + ko, bh + ko, idesc, 1);
-                        umma_bf16(d_tmem, zh + ko, bl + ko, idesc, 1);
-                        umma_bf16(d_tmem, zm + ko, bh + ko, idesc, 1);
-                        umma_bf16(d_tmem, zh + ko, bm + ko, idesc, 1);
-                        umma_bf16(d_tmem, zh + ko, bh + ko, idesc, 1);
+                            for (int k = 0; k < KB / 16; ++k) {
+                                const uint64_t ko = (uint64_t)(k * 32 >> 4);
+                                umma_bf16(d_tmem, zm + ko, bm + ko, idesc, k != 0);
+                                umma_bf16(d_tmem, zl + ko, bh + ko, idesc, 1);
+                                umma_bf16(d_tmem, zh + ko, bl + ko, idesc, 1);
+                                umma_bf16(d_tmem, zm + ko, bh + ko, idesc, 1);
+                                umma_bf16(d_tmem, zh + ko, bm + ko, idesc, 1);
+                                umma_bf16(d_tmem, zh + ko, bh + ko, idesc, 1);
+                            }
+                        }
+                        umma_commit(bar_tfull + 8 * (2 * g + ab));
                     }
-                    umma_commit(bar_tfull + 8 * (2 * g + ab));
+                    umma_commit(bar_empty + 8 * stage);
+                    if (++stage == BM_STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(bar_empty + 8 * stage);
-                if (++stage == BM_STAGES) { stage = 0; phase ^= 1; }
-            }
         }
     } else {
         const int q = warp & 3, g = (warp - 2) >> 2;      // a warp may only touch TMEM lanes [32 (warp % 4), +32)
         const long long srow = (long long)block * 256 + g * 128 + q * 32 + lane;      // this thread's sample
         const bool valid = srow < p.S;
-        // second-layer weights and bias of this sample, in registers for the whole kernel (zero for padded hidden units)
-        float w[HP];
+        // second-layer weights and bias of this sample, in registers for the whole kernel (zero for padded hidden units).
+        // ReLU, VAR 0: relu(x) w = (w/2) x + (w/2) |x| -- a packed FFMA2 for two hidden units' linear parts and an FFMA with the
+        // free |.| operand modifier each, all on the FMA pipes.  VAR 1: clamp with FMNMX (ALU pipe), then one FFMA2 per pair.
+        constexpr bool HALF = ACT == SSI_ACT_RELU && VAR == 0;
+        constexpr int DPT = BM_N / HP;                     // datapoints per tile
+        float2 wh[HP / 2];
+        {
+            const float4* wrow = reinterpret_cast<const float4*>(p.W2 + srow * HP);
+            const float sc = HALF ? 0.5f : 1.0f;
 #pragma unroll
-        for (int j = 0; j < HP; ++j) w[j] = (valid && j < p.H) ? __ldg(p.W2 + srow * (p.H + 1) + j) : 0.0f;
-        const float b2 = valid ? __ldg(p.W2 + srow * (p.H + 1) + p.H) : 0.0f;
-        // squared errors: FP32 over 16 tiles (32-64 datapoints), then FP64 (one DFMA per datapoint and thread throttled the
-        // FP64 pipe: 16 % of the kernel's stall samples)
-        double sse = 0.0;
-        float sse_part = 0.0f;
+            for (int j = 0; j < HP / 4; ++j) {
+                const float4 w4 = valid ? __ldg(wrow + j) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                wh[2 * j] = make_float2(sc * w4.x, sc * w4.y);
+                wh[2 * j + 1] = make_float2(sc * w4.z, sc * w4.w);
+            }
+        }
+        const float b2 = valid ? __ldg(p.B2 + srow) : 0.0f;
+        const int N = p.N, parts = p.parts, n_tiles = p.n_tiles, gx = (int)gridDim.x;
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (2 * g) * 128;
+        const uint32_t bar_f = bar_tfull + 16 * g, bar_e = bar_tempty + 16 * g;
+
+        // Software pipeline over the tile's chunks of 32 columns: the TMEM load of chunk c+1 is in flight while chunk c is folded
+        // into partial dot products; the accumulator is handed back to the MMA warp as soon as its last chunk sits in
+        // registers.  (Prefetching the next tile's first chunk as well costs registers the kernel does not have: 168 is the
+        // ceiling with 10 warps, three of them on one scheduler, and the spills made it 25 % slower.)
+        int pp = blockIdx.x, t = pp;                        // parts >= gridDim.x and n_tiles >= parts: the first tile exists
         uint32_t it = 0;
-        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
-            const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
-            const long long i_base = (long long)t * (BM_N / HP);
-            float yv[BM_N / HP];                                    // targets of this tile's datapoints, fetched before the wait
+        float s_hi = 0.0f, s_lo = 0.0f;                     // squared errors of the current part, two-float (error-free) sum
+        uint32_t v[2][32];
+        while (true) {
+            int tn = t + parts, ppn = pp;
+            if (tn >= n_tiles) { ppn = pp + gx; tn = ppn; }
+            const bool more = ppn < parts;
+            const uint32_t ab = it & 1;
+            const int i_base = t * DPT;
+            float yv[DPT];                                  // targets of this tile's datapoints (needed one datapoint from now)
 #pragma unroll
-            for (int d = 0; d < BM_N / HP; ++d) yv[d] = (i_base + d < p.N) ? __ldg(p.Y + i_base + d) : 0.0f;
-            mbar_wait(bar_tfull + 8 * (2 * g + ab), aphase);
+            for (int d = 0; d < DPT; ++d) yv[d] = (i_base + d < N) ? __ldg(p.Y + i_base + d) : 0.0f;
+            float sse_t = 0.0f;
+            constexpr int NL = HALF ? 2 : 4;                // independent FFMA2 chains
+            float2 lin[NL];
+#pragma unroll
+            for (int i = 0; i < NL; ++i) lin[i] = make_float2(0.0f, 0.0f);
+            float ab4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            mbar_wait(bar_f + 8 * ab, (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (2 * g + ab) * 128;
-            // software pipeline over the chunks of 32 columns: the TMEM load of chunk c+1 is in flight while chunk c is
-            // folded into four independent partial dot products (a single accumulator would be a 64-long dependent FMA chain)
-            uint32_t v[2][32];
-            tmem_ld32(taddr, v[0]);
-            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            tmem_ld32(taddr0 + ab * 128, v[0]);
 #pragma unroll
             for (int c = 0; c < BM_N / 32; ++c) {
                 tmem_ld_wait();
-                if (c + 1 < BM_N / 32) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                if (c + 1 < BM_N / 32) tmem_ld32(taddr0 + ab * 128 + (c + 1) * 32, v[(c + 1) & 1]);
+                else {
+                    tc_fence_before();
+                    mbar_arrive(bar_e + 8 * ab);             // the whole accumulator is in registers
+                }
                 const int j0 = (c * 32) % HP;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    acc[j & 3] = fmaf(bm_act<ACT>(__uint_as_float(v[c & 1][j])), w[j0 + j], acc[j & 3]);
-                if (((c + 1) * 32) % HP == 0) {                      // a datapoint is complete
-                    const int d = (c * 32) / HP;
-                    const float pred = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-                    if (i_base + d < p.N) {
-                        const float df = ssi_act(pred + b2, p.act_out) - yv[d];
-                        sse_part = fmaf(df, df, sse_part);
+                for (int j = 0; j < 32; j += 2) {
+                    float2 x = make_float2(__uint_as_float(v[c & 1][j]), __uint_as_float(v[c & 1][j + 1]));
+                    const float2 w2 = wh[(j0 + j) >> 1];
+                    if (HALF) {
+                        ab4[j & 3] = fmaf(fabsf(x.x), w2.x, ab4[j & 3]);
+                        ab4[(j + 1) & 3] = fmaf(fabsf(x.y), w2.y, ab4[(j + 1) & 3]);
+                        lin[(j >> 1) & 1] = __ffma2_rn(x, w2, lin[(j >> 1) & 1]);
+                    } else {
+                        x.x = bm_act<ACT>(x.x);
+                        x.y = bm_act<ACT>(x.y);
+                        lin[(j >> 1) & (NL - 1)] = __ffma2_rn(x, w2, lin[(j >> 1) & (NL - 1)]);
                     }
-                    acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
+                }
+                if (((c + 1) * 32) % HP == 0) {              // a datapoint is complete
+                    const int d = (c * 32) / HP;
+                    float pre = (lin[0].x + lin[0].y) + (lin[1].x + lin[1].y);
+                    if (NL == 4) pre += (lin[NL - 2].x + lin[NL - 2].y) + (lin[NL - 1].x + lin[NL - 1].y);
+                    if (HALF) pre += (ab4[0] + ab4[1]) + (ab4[2] + ab4[3]);
+                    pre += b2;
+                    if (!OUT_ID) pre = ssi_act(pre, p.act_out);
+                    const float df = (i_base + d < N) ? pre - yv[d] : 0.0f;
+                    sse_t = fmaf(df, df, sse_t);
+#pragma unroll
+                    for (int i = 0; i < NL; ++i) lin[i] = make_float2(0.0f, 0.0f);
+                    ab4[0] = ab4[1] = ab4[2] = ab4[3] = 0.0f;
                 }
             }
-            tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * (2 * g + ab));
-            if ((it & 15) == 15) { sse += (double)sse_part; sse_part = 0.0f; }
+            {   // (s_hi, s_lo) += sse_t without rounding error (TwoSum); no FP64 in the loop (a DADD per tile throttled the FP64 pipe)
+                const float s = s_hi + sse_t;
+                const float bb = s - s_hi;
+                s_lo += (s_hi - (s - bb)) + (sse_t - bb);
+                s_hi = s;
+            }
+            if (ppn != pp) {
+                if (valid) p.partials[srow * parts + pp] = (double)s_hi + (double)s_lo;
+                s_hi = s_lo = 0.0f;
+            }
+            if (!more) break;
+            pp = ppn;
+            t = tn;
+            ++it;
         }
-        sse += (double)sse_part;
-        if (valid) p.partials[srow * p.parts + blockIdx.x] = sse;
     }
     tc_fence_before();
     __syncthreads();
@@ -212,13 +280,32 @@ __device__ __forceinline__ void bm_split3(float v, bf16& hi, bf16& mid, bf16& lo
     lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
 }
 
-// zaug[part][s][m]: z[m, s] (m < M), 1 (m == M), 0 (padding, and rows s >= S up to a multiple of 256), split three ways
-__global__ void k_bm_pack_zaug(const float* __restrict__ Z, int M, long long S, long long S_pad, int KB, bf16* __restrict__ out) {
+// which of (hi, mid, lo) = (0, 1, 2) the packed operands take for product `term`, smallest product first:
+// (z, basis) = (mid,mid) (lo,hi) (hi,lo) (mid,hi) (hi,mid) (hi,hi)
+__device__ __forceinline__ int bm_term_zpart(int term) { return term == 0 || term == 3 ? 1 : (term == 1 ? 2 : 0); }
+__device__ __forceinline__ int bm_term_bpart(int term) { return term == 0 || term == 4 ? 1 : (term == 2 ? 2 : 0); }
+__device__ __forceinline__ bf16 bm_part(float v, int part) {
+    bf16 hi, mid, lo;
+    bm_split3(v, hi, mid, lo);
+    return part == 0 ? hi : (part == 1 ? mid : lo);
+}
+
+// zaug[slab][s][k]: z[m, s] (m < M), 1 (m == M), 0 (padding, and rows s >= S up to a multiple of 256).
+// classic: slab = part of the three-way split, k = m;  packed (KB = 16): column c = slab*16 + k = term*(M+1) + m
+__global__ void k_bm_pack_zaug(const float* __restrict__ Z, int M, long long S, long long S_pad, int KB, int packed_ns, bf16* __restrict__ out) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= S_pad * KB) return;
     const long long s = t / KB;
-    const int m = (int)(t % KB);
-    const float v = s < S ? (m < M ? Z[m + s * M] : (m == M ? 1.0f : 0.0f)) : 0.0f;
+    const int k = (int)(t % KB);
+    if (packed_ns) {
+        for (int slab = 0; slab < packed_ns; ++slab) {
+            const int c = slab * 16 + k, term = c / (M + 1), m = c % (M + 1);
+            const float v = (s < S && term < 6) ? (m < M ? Z[m + s * M] : 1.0f) : 0.0f;
+            out[(long long)slab * S_pad * KB + t] = bm_part(v, bm_term_zpart(term));
+        }
+        return;
+    }
+    const float v = s < S ? (k < M ? Z[k + s * M] : (k == M ? 1.0f : 0.0f)) : 0.0f;
     bf16 hi, mid, lo;
     bm_split3(v, hi, mid, lo);
     out[t] = hi;
@@ -226,17 +313,25 @@ __global__ void k_bm_pack_zaug(const float* __restrict__ Z, int M, long long S, 
     out[2 * S_pad * KB + t] = lo;
 }
 
-// basesT[part][i*Hp + j][m] (K-major, KB BF16 per activation, split three ways)  <-  bases[m][i][j] FP32 (ld = H), zero padding
+// basesT[slab][i*Hp + j][k] (K-major, KB BF16 per activation)  <-  bases[m][i][j] FP32 (ld = H), zero padding; slabs as above
 __global__ void __launch_bounds__(256)
-k_bm_bases_kmajor(const float* __restrict__ bases, long long N, int H, int Hp, int M1, int KB, bf16* __restrict__ out) {
+k_bm_bases_kmajor(const float* __restrict__ bases, long long N, int H, int Hp, int M1, int KB, int packed_ns, bf16* __restrict__ out) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = N * Hp * KB;
     if (t >= total) return;
-    const int m = (int)(t % KB);
+    const int k = (int)(t % KB);
     const long long e = t / KB;
     const int j = (int)(e % Hp);
     const long long i = e / Hp;
-    const float v = (m < M1 && j < H) ? bases[((long long)m * N + i) * H + j] : 0.0f;
+    if (packed_ns) {
+        for (int slab = 0; slab < packed_ns; ++slab) {
+            const int c = slab * 16 + k, term = c / M1, m = c % M1;
+            const float v = (term < 6 && j < H) ? bases[((long long)m * N + i) * H + j] : 0.0f;
+            out[(long long)slab * total + t] = bm_part(v, bm_term_bpart(term));
+        }
+        return;
+    }
+    const float v = (k < M1 && j < H) ? bases[((long long)k * N + i) * H + j] : 0.0f;
     bf16 hi, mid, lo;
     bm_split3(v, hi, mid, lo);
     out[t] = hi;
@@ -244,18 +339,22 @@ k_bm_bases_kmajor(const float* __restrict__ bases, long long N, int H, int Hp, i
     out[2 * total + t] = lo;
 }
 
-// W2[s][j] = (W_swa + P z_s)[second layer]: weight j < H, bias at j = H
+// W2[s][j] = (W_swa + P z_s)[second layer weight j] for j < H, 0 for H <= j < Hp;  B2[s] = its bias
 __global__ void __launch_bounds__(256)
-k_bm_project_w2(const float* __restrict__ PW, const float* __restrict__ Z, long long n, int M, long long S, int H,
-                long long w2_off, long long b2_off, float* __restrict__ out) {
+k_bm_project_w2(const float* __restrict__ PW, const float* __restrict__ Z, long long n, int M, long long S, int H, int Hp,
+                long long w2_off, long long b2_off, float* __restrict__ W2, float* __restrict__ B2) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= S * (H + 1)) return;
-    const long long s = e / (H + 1);
-    const int j = (int)(e % (H + 1));
-    const long long k = j < H ? w2_off + j : b2_off;
-    float v = PW[k + (long long)M * n];
-    for (int m = 0; m < M; ++m) v = fmaf(PW[k + (long long)m * n], Z[s * M + m], v);
-    out[e] = v;
+    if (e >= S * (Hp + 1)) return;
+    const long long s = e / (Hp + 1);
+    const int j = (int)(e % (Hp + 1));
+    float v = 0.0f;
+    if (j < H || j == Hp) {
+        const long long k = j < H ? w2_off + j : b2_off;
+        v = PW[k + (long long)M * n];
+        for (int m = 0; m < M; ++m) v = fmaf(PW[k + (long long)m * n], Z[s * M + m], v);
+    }
+    if (j == Hp) B2[s] = v;
+    else W2[s * Hp + j] = v;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -268,8 +367,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 struct ssi_bm_state {
     bool ready = false;
     int KB = 16, Hp = 64;
+    int packed_ns = 0;                       // 0: three-way split as three slabs; else packed products, this many K=16 slabs
     long long n_tiles = 0;
-    bf16* T = nullptr;                       // basesT [3][N*Hp][KB]  (hi, mid, lo)
+    bf16* T = nullptr;                       // basesT [slabs][N*Hp][KB]
     CUtensorMap tmT;
     PFN_encodeTiled encode = nullptr;
 };
@@ -292,8 +392,8 @@ bool ssi_bm_supported(const ssi_ctx* ctx) {
     return ctx->N * Hp < (1ll << 31) && !ctx->opt_b1_simt;
 }
 
-static int bm_make_map(ssi_ctx* ctx, CUtensorMap* map, void* base, uint64_t inner, uint64_t rows, uint32_t box_rows) {
-    cuuint64_t dims[3] = {inner, rows, 3};          // third dimension: the (hi, mid, lo) parts
+static int bm_make_map(ssi_ctx* ctx, CUtensorMap* map, void* base, uint64_t inner, uint64_t rows, uint32_t box_rows, int slabs) {
+    cuuint64_t dims[3] = {inner, rows, (cuuint64_t)slabs};          // third dimension: the operand slabs
     cuuint64_t strides[2] = {inner * sizeof(bf16), inner * rows * sizeof(bf16)};
     cuuint32_t box[3] = {(cuuint32_t)inner, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
@@ -321,32 +421,38 @@ static int bm_prepare(ssi_ctx* ctx) {
     const long long N = ctx->N;
     s->KB = M1 <= 16 ? 16 : 32;
     s->Hp = H <= 32 ? 32 : 64;
+    s->packed_ns = (M1 <= 8 && !ctx->opt_bm_nopack) ? (6 * M1 + 15) / 16 : 0;
+    const int slabs = s->packed_ns ? s->packed_ns : 3;
     const long long NW = N * s->Hp;
     s->n_tiles = (NW + BM_N - 1) / BM_N;
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(s->T);
     s->T = nullptr;
-    SSI_CUDA(ctx, cudaMalloc(&s->T, sizeof(bf16) * 3 * (size_t)NW * s->KB));
+    SSI_CUDA(ctx, cudaMalloc(&s->T, sizeof(bf16) * slabs * (size_t)NW * s->KB));
     // bases [m][N][H] in scratch, exact FP32 (bias parts included), then the K-major split-BF16 copy
     SSI_TRY(ssi_reserve(ctx, ctx->bH0, sizeof(float) * (size_t)M1 * N * H));
     SSI_TRY(ssi_build_first_layer_bases(ctx, (float*)ctx->bH0.p, H));
     const long long total = NW * s->KB;
-    k_bm_bases_kmajor<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const float*)ctx->bH0.p, N, H, s->Hp, M1, s->KB, s->T);
+    k_bm_bases_kmajor<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const float*)ctx->bH0.p, N, H, s->Hp, M1, s->KB, s->packed_ns, s->T);
     SSI_LAUNCH_CHECK(ctx);
-    SSI_TRY(bm_make_map(ctx, &s->tmT, s->T, s->KB, (uint64_t)NW, BM_N));
+    SSI_TRY(bm_make_map(ctx, &s->tmT, s->T, s->KB, (uint64_t)NW, BM_N, slabs));
     s->ready = true;
     return SSI_OK;
 }
 
 typedef void (*bm_kernel_t)(const CUtensorMap, const CUtensorMap, const bm_params);
-template <int KB, int HP>
-static bm_kernel_t bm_pick(int act) {
+template <int KB, int HP, bool PACKED, bool OUT_ID>
+static bm_kernel_t bm_pick_act(int act, int var) {
     switch (act) {
-        case SSI_ACT_RELU:    return k_b1_mma<SSI_ACT_RELU, KB, HP>;
-        case SSI_ACT_TANH:    return k_b1_mma<SSI_ACT_TANH, KB, HP>;
-        case SSI_ACT_SIGMOID: return k_b1_mma<SSI_ACT_SIGMOID, KB, HP>;
-        default:              return k_b1_mma<SSI_ACT_IDENTITY, KB, HP>;
+        case SSI_ACT_RELU:    return var == 1 ? k_b1_mma<SSI_ACT_RELU, KB, HP, PACKED, OUT_ID, 1> : k_b1_mma<SSI_ACT_RELU, KB, HP, PACKED, OUT_ID, 0>;
+        case SSI_ACT_TANH:    return k_b1_mma<SSI_ACT_TANH, KB, HP, PACKED, OUT_ID, 0>;
+        case SSI_ACT_SIGMOID: return k_b1_mma<SSI_ACT_SIGMOID, KB, HP, PACKED, OUT_ID, 0>;
+        default:              return k_b1_mma<SSI_ACT_IDENTITY, KB, HP, PACKED, OUT_ID, 0>;
     }
+}
+template <int KB, int HP, bool PACKED>
+static bm_kernel_t bm_pick(int act, int act_out, int var) {
+    return act_out == SSI_ACT_IDENTITY ? bm_pick_act<KB, HP, PACKED, true>(act, var) : bm_pick_act<KB, HP, PACKED, false>(act, var);
 }
 
 int ssi_reduce_partials(ssi_ctx* ctx, const double* partials, int64_t B, int parts, double* d_out);
@@ -356,35 +462,48 @@ int ssi_bm_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
     ssi_bm_state* s = ctx->bm;
     const ssi_model_t& m = ctx->model;
     const int M = ctx->M, H = m.dims[1], KB = s->KB, Hp = s->Hp;
-    bm_kernel_t kern = KB == 16 ? (Hp == 32 ? bm_pick<16, 32>(m.act[0]) : bm_pick<16, 64>(m.act[0]))
-                                : (Hp == 32 ? bm_pick<32, 32>(m.act[0]) : bm_pick<32, 64>(m.act[0]));
+    const int slabs = s->packed_ns ? s->packed_ns : 3;
+    const int a0 = m.act[0], a1 = m.act[1], var = ctx->opt_bm_variant;
+    bm_kernel_t kern = s->packed_ns ? (Hp == 32 ? bm_pick<16, 32, true>(a0, a1, var) : bm_pick<16, 64, true>(a0, a1, var))
+                     : KB == 16     ? (Hp == 32 ? bm_pick<16, 32, false>(a0, a1, var) : bm_pick<16, 64, false>(a0, a1, var))
+                                    : (Hp == 32 ? bm_pick<32, 32, false>(a0, a1, var) : bm_pick<32, 64, false>(a0, a1, var));
     // at least 120 KB so that exactly one CTA (which allocates all 512 TMEM columns) is resident per SM
     const size_t smem = std::max<size_t>((size_t)BM_STAGES * 3 * BM_N * KB * 2 + 6 * 128 * KB * 2 + 24 * 8 + 16, 120 * 1024);
     SSI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     const int64_t n_blocks = (B + 255) / 256;
     const int64_t S_pad = n_blocks * 256;
-    // CTAs per block of 256 samples = partial sums per sample.  It depends on the dataset and the device only, never on B,
-    // so a sample's summation order (hence its lp, bit for bit) is the same whatever else shares the call.
+    // Partial sums per sample: tile t belongs to part t % parts.  `parts` depends on the dataset and the device only, never
+    // on B, so a sample's summation order (hence its lp, bit for bit) is the same whatever else shares the call.
     const int parts = (int)std::min<int64_t>(s->n_tiles, ctx->sm_count);
-    // scratch: zaug [3][S_pad][KB] bf16, W2 [B][H+1] floats, partials [B][parts] doubles
-    const size_t off_w2 = (3 * sizeof(bf16) * (size_t)S_pad * KB + 255) / 256 * 256;
-    SSI_TRY(ssi_reserve(ctx, ctx->bW, off_w2 + sizeof(float) * (size_t)B * (H + 1)));
+    // A CTA walks `ppc` parts of one block of samples (its z operands and second-layer weights are loaded once): with many
+    // blocks, fewer and longer CTAs amortise the pipeline fill.  Keep at least three full waves of CTAs.
+    int gx = parts;
+    for (int ppc = 8; ppc > 1; ppc >>= 1) {
+        const int g = (parts + ppc - 1) / ppc;
+        const double waves = (double)g * (double)n_blocks / ctx->sm_count;
+        if (waves >= 3.0 && waves / std::ceil(waves) >= 0.9) { gx = g; break; }
+    }
+    // scratch: zaug [slabs][S_pad][KB] bf16, W2 [B][Hp] + B2 [B] floats, partials [B][parts] doubles
+    const size_t off_w2 = (slabs * sizeof(bf16) * (size_t)S_pad * KB + 255) / 256 * 256;
+    SSI_TRY(ssi_reserve(ctx, ctx->bW, off_w2 + sizeof(float) * (size_t)B * (Hp + 1)));
     SSI_TRY(ssi_reserve(ctx, ctx->bPartials, sizeof(double) * (size_t)B * parts));
     bf16* zaug = (bf16*)ctx->bW.p;
     float* W2 = (float*)((char*)ctx->bW.p + off_w2);
+    float* B2 = W2 + (size_t)B * Hp;
     double* partials = (double*)ctx->bPartials.p;
-    k_bm_pack_zaug<<<(unsigned)((S_pad * KB + 255) / 256), 256, 0, ctx->stream>>>(dZ, M, B, S_pad, KB, zaug);
+    k_bm_pack_zaug<<<(unsigned)((S_pad * KB + 255) / 256), 256, 0, ctx->stream>>>(dZ, M, B, S_pad, KB, s->packed_ns, zaug);
     SSI_LAUNCH_CHECK(ctx);
-    k_bm_project_w2<<<(unsigned)((B * (H + 1) + 255) / 256), 256, 0, ctx->stream>>>(ctx->dP, dZ, m.n, M, B, H, m.w_off[1], m.b_off[1], W2);
+    k_bm_project_w2<<<(unsigned)((B * (Hp + 1) + 255) / 256), 256, 0, ctx->stream>>>(ctx->dP, dZ, m.n, M, B, H, Hp, m.w_off[1], m.b_off[1], W2, B2);
     SSI_LAUNCH_CHECK(ctx);
     CUtensorMap tmZ;
-    SSI_TRY(bm_make_map(ctx, &tmZ, zaug, KB, (uint64_t)S_pad, 128));
+    SSI_TRY(bm_make_map(ctx, &tmZ, zaug, KB, (uint64_t)S_pad, 128, slabs));
     bm_params p{};
     p.n_tiles = (int)s->n_tiles; p.Hp = Hp; p.H = H; p.N = (int)ctx->N; p.S = (int)B; p.act_out = m.act[1]; p.parts = parts;
-    p.W2 = W2; p.Y = ctx->dY; p.partials = partials;
+    p.ns = slabs;
+    p.W2 = W2; p.B2 = B2; p.Y = ctx->dY; p.partials = partials;
     if (n_blocks > 65535) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "basis mma path: more than 16.7M samples per call");
-    dim3 grid(parts, (unsigned)n_blocks);
+    dim3 grid(gx, (unsigned)n_blocks);
     ssi_kt_begin(ctx);
     kern<<<grid, BM_THREADS, smem, ctx->stream>>>(tmZ, s->tmT, p);
     SSI_LAUNCH_CHECK(ctx);

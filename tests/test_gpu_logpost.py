@@ -202,6 +202,9 @@ def test_gradient_vs_oracle(ssi, engine, dims, acts, N, M, B):
     ((6, 31, 1), (3, 2), 200, 12, 33),         # Hp = 32, sigmoid hidden (padded units must cancel), tanh output
     ((4, 64, 1), (2, 0), 65, 20, 300),         # K = 32 (M + 1 = 21), H = 64 exactly
     ((5, 17, 1), (0, 1), 1, 31, 5),            # M + 1 = 32, one datapoint, identity hidden, relu output
+    ((7, 40, 1), (1, 0), 4001, 1, 2500),       # M + 1 = 2: one packed K slab; 10 blocks of samples (several parts per CTA)
+    ((9, 64, 1), (1, 1), 777, 7, 300),         # M + 1 = 8: three packed slabs, all 48 columns used; relu output
+    ((3, 20, 1), (2, 3), 150, 4, 40),          # two packed slabs, Hp = 32, tanh hidden, sigmoid output
 ])
 def test_basis_path_on_tensor_cores_vs_oracle(ssi, engine, dims, acts, N, M, B):
     """BASIS path, tensor-core kernel (samples along the MMA M dimension) and CUDA-core kernel: both within 1e-5 of the
@@ -227,3 +230,9 @@ def test_basis_path_on_tensor_cores_vs_oracle(ssi, engine, dims, acts, N, M, B):
     engine.set_option("b1_simt", 0)
     k = min(B, 3)
     np.testing.assert_array_equal(engine.logpost(Z[:, B - k:], 0.7), out[0][B - k:])
+    # A-B switches of the tensor-core kernel: six MMAs of a three-way split instead of products packed along K; the
+    # ReLU-by-|x| epilogue
+    for key in ("bm_nopack", "bm_variant"):
+        engine.set_option(key, 1 if key == "bm_nopack" else 0)
+        np.testing.assert_allclose(engine.logpost(Z, 0.7), ref, rtol=RTOL, err_msg=key)
+        engine.set_option(key, 0 if key == "bm_nopack" else 1)

@@ -154,3 +154,34 @@ def test_first_layer_on_tensor_cores_vs_simt_basis(ssi, engine, dims, acts, N, M
     # a sample's value does not depend on the group it lands in
     engine.set_option("tc_simt_basis", 0)
     np.testing.assert_array_equal(engine.logpost(Z[:, 5:9], 0.8), out[0][5:9])
+
+
+def test_wide_full_size_properties(ssi, engine):
+    """Full C3 size (784-1024-1024-10, N = 60000, M = 20): oracle on a few samples, additivity of the likelihood over a
+    split of the dataset, datapoint-permutation invariance, and bitwise batch invariance across a group boundary."""
+    prob = orc.make_problem("wide")
+    assert prob.N == 60000 and prob.dims == (784, 1024, 1024, 10)
+    _setup(engine, prob)
+    rng = np.random.default_rng(7)
+    B = 131                                                    # 128 + 3: crosses a group of samples
+    Z = (0.1 * rng.standard_normal((prob.M, B))).astype(np.float32)
+    lp = engine.logpost(Z, 1.0)
+    assert engine.stats().last_path == ssi.PATH_TENSOR and engine.stats().last_units == B * prob.N
+    idx = np.array([0, 127, 130])
+    ref, _ = orc.logpost_batch(prob, Z[:, idx], 1.0)
+    np.testing.assert_allclose(lp[idx], ref, rtol=RTOL)
+    print("full-size wide: max rel err vs oracle %.2e" % np.abs(lp[idx] / ref - 1).max())
+    # a sample's value does not depend on its batch
+    np.testing.assert_array_equal(engine.logpost(Z[:, 126:131], 1.0), lp[126:131])
+    # Gaussian likelihood is additive over datapoints: lp(all) = lp(first 25000) + lp(rest) (the -k/2 log(2 pi sigma^2) terms add too)
+    Zs = Z[:, :4]
+    cut = 25000
+    engine.set_data(prob.X[:, :cut], prob.Y[:, :cut])
+    lp_a = engine.logpost(Zs, 1.0)
+    engine.set_data(prob.X[:, cut:], prob.Y[:, cut:])
+    lp_b = engine.logpost(Zs, 1.0)
+    np.testing.assert_allclose(lp_a + lp_b, lp[:4], rtol=2e-6)
+    # permuting the datapoints changes only the summation order
+    perm = rng.permutation(prob.N)
+    engine.set_data(prob.X[:, perm], prob.Y[:, perm])
+    np.testing.assert_allclose(engine.logpost(Zs, 1.0), lp[:4], rtol=2e-6)
