@@ -190,6 +190,27 @@ int  ssi_swa_finish(ssi_ctx* ctx, int32_t M, float* W_swa_out, float* P_out, dou
 /* number of columns collected so far */
 int64_t ssi_swa_columns(const ssi_ctx* ctx);
 
+/* ---- the step before the path: mini-batch training on the device ----------------------------------
+ * Replaces, for a Dense chain with cost = Flux.Losses.mse(m(x), y), the reference's training step
+ *     gs = gradient(ps) do training_loss = cost(d...) end; Flux.update!(opt, ps, gs)     src/subspace_construction.jl:39-43
+ * so that snapshots feed the SWA recurrence without a host round trip.  Needs ssi_set_model and ssi_set_data (the
+ * DataLoader's full X, Y: src/libs.jl:75-77); weights are in the flat layout of src/libs.jl:19-22.
+ *   ssi_train_begin      W0 (n floats, host) = Flux.params of the freshly built model; optimiser 0 = Descent(eta),
+ *                        1 = ADAM(eta, (beta1, beta2)) with eps = 1e-8 (Flux 0.11.2 update rule)
+ *   ssi_train_step       one mini-batch: columns idx[0..nb) of the data set (host indices, a shuffled DataLoader) or, with
+ *                        idx == NULL, the contiguous columns [j0, j0 + nb).  loss_out (host, may be NULL) receives
+ *                        training_loss, the mean squared error BEFORE the update; asking for it synchronises.
+ *   ssi_train_snapshot   W_swa <- (ns W_swa + W)/(ns + 1), deviation column <- W - W_swa (:44-52) from the device weights;
+ *                        ssi_swa_begin(n, K_max) must have been called with the model's n
+ *   ssi_train_get_weights  copy the current weights to the host (n floats)                                            */
+#define SSI_OPT_DESCENT 0
+#define SSI_OPT_ADAM 1
+int  ssi_train_begin(ssi_ctx* ctx, const float* W0, int32_t optimiser, double eta, double beta1, double beta2);
+int  ssi_train_step(ssi_ctx* ctx, const int64_t* idx, int64_t j0, int64_t nb, double* loss_out);
+int  ssi_train_snapshot(ssi_ctx* ctx, double n_scalar);
+int  ssi_train_get_weights(ssi_ctx* ctx, float* W_out);
+int  ssi_train_end(ssi_ctx* ctx);
+
 /* Row-sharded construction over several GPUs (one process and one context per GPU): every rank pushes ITS ROW SHARD of
  * each snapshot (n = shard length), then
  *   ssi_swa_gram_dev    Gram of the local deviation columns into a caller-provided DEVICE buffer (K x K doubles,

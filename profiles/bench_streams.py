@@ -15,12 +15,51 @@ sys.path.insert(0, str(ROOT))
 import subspaceinference_jl_b200 as ssi  # noqa: E402
 
 
+def train_section(eng, stream, dims=(784, 2048, 2048, 2048, 10), N=8192, nb=512, steps=20):
+    """One mini-batch step (forward, backward, ADAM, snapshot push) of the C4 model on the device, and the same step
+    through the host restatement (torch CPU autograd) for scale."""
+    import time
+    rng = np.random.default_rng(4)
+    acts = (ssi.relu,) * (len(dims) - 2) + (ssi.identity,)
+    m = ssi.Chain(*[ssi.Dense(dims[l], dims[l + 1], acts[l], rng=rng) for l in range(len(dims) - 1)])
+    X = rng.random((dims[0], N), dtype=np.float32)
+    Y = rng.standard_normal((dims[-1], N)).astype(np.float32)
+    eng.set_model(m.dims, m.acts)
+    eng.set_data(X, Y)
+    n = int(ssi.extract_params(m).shape[0])
+    eng.swa_begin(n, steps + 4)
+    eng.train_begin(ssi.extract_params(m), "adam", 1e-3)
+    for w in range(3):
+        eng.train_step((w * nb, nb), want_loss=False)
+    stream.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(steps):
+        eng.train_step(((k % (N // nb)) * nb, nb), want_loss=False)
+        eng.train_snapshot(float(k + 1))
+    e1.record(stream)
+    stream.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    eng.train_end()
+    opt = ssi.ADAM(1e-3)
+    cost = lambda mm, x, y: ssi.mse(mm(x), y)
+    ssi.train_step(m, cost, opt, X[:, :nb], Y[:, :nb])
+    t0 = time.perf_counter()
+    ssi.train_step(m, cost, opt, X[:, nb:2 * nb], Y[:, nb:2 * nb])
+    host_ms = (time.perf_counter() - t0) * 1e3
+    flops = 3.0 * nb * 2.0 * sum(dims[l] * dims[l + 1] for l in range(len(dims) - 1))
+    return {"model": "-".join(map(str, dims)), "n": n, "batch": nb, "optimiser": "ADAM", "step_plus_snapshot_ms": ms,
+            "tflops_fp32": flops / (ms * 1e-3) / 1e12, "host_step_ms": host_ms, "host_threads": torch.get_num_threads(),
+            "note": "device: SIMT FP32 GEMMs (correctness-first 'next' row); host: torch CPU autograd + snapshot copy not included"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=10020874)      # 784-2048-2048-2048-10
     ap.add_argument("--K", type=int, default=100)
     ap.add_argument("--M", type=int, default=20)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--train", action="store_true", help="also time the on-device training step (SURVEY 8(f)-3) on the C4 model")
     a = ap.parse_args()
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6650.0}
     import os
@@ -88,6 +127,8 @@ def main():
     out["finish_frac"] = out["finish_gbs"] / (peaks["hbm_gbs"] * world)
     st = eng.stats()
     out["gram_path"], out["gram_risk"], out["jacobi_sweeps"] = st.gram_path, st.gram_risk, st.jacobi_sweeps
+    if a.train and world == 1:
+        out["train"] = train_section(eng, stream)
     if rank == 0:
         print(json.dumps(out))
     eng.close()

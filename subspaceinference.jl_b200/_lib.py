@@ -67,6 +67,11 @@ SIGNATURES = {
     "ssi_swa_push_dev": (C.c_int, [_p, _p, _dbl]),
     "ssi_swa_finish": (C.c_int, [_p, _i32, _p, _p, _p, _i32]),
     "ssi_swa_columns": (_i64, [_p]),
+    "ssi_train_begin": (C.c_int, [_p, _p, C.c_int32, _dbl, _dbl, _dbl]),
+    "ssi_train_step": (C.c_int, [_p, _p, _i64, _i64, _p]),
+    "ssi_train_snapshot": (C.c_int, [_p, _dbl]),
+    "ssi_train_get_weights": (C.c_int, [_p, _p]),
+    "ssi_train_end": (C.c_int, [_p]),
     "ssi_swa_gram_dev": (C.c_int, [_p, _p, _i32]),
     "ssi_swa_finish_gram": (C.c_int, [_p, _i32, _p, _i32, _p, _p, _p, _i32]),
 }

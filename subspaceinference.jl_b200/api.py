@@ -15,7 +15,7 @@ import numpy as np
 
 from ._lib import TERM_LL
 from .engine import Engine
-from .flux import Chain, DataLoader, extract_params, split_data, train_step
+from .flux import ADAM, Chain, DataLoader, Descent, extract_params, load_params, split_data, train_step
 
 _RWMH_ALIASES = ("rwmh", "mh")
 
@@ -34,14 +34,20 @@ def shard_rows(n: int, rank: int, world: int):
 
 def subspace_construction(model, cost, data, opt, *, T: int = 10, c: int = 1, M: int = 3, print_freq: int = 1,
                           engine: Engine | None = None, device: int = 0, install: bool = False,
-                          shard: tuple[int, int] | None = None, all_reduce=None):
+                          shard: tuple[int, int] | None = None, all_reduce=None, device_train: bool = False):
     """(W_swa, P) from SGD snapshots.  The per-mini-batch training step is host plumbing
     (src/subspace_construction.jl:39-43); the moment recurrence, deviation matrix, Gram,
     eigen-solve and P = U_M S_M run on the device (:44-52, :61-65).
 
     shard=(rank, world) with all_reduce=fn: row-sharded construction over `world` GPUs.  Every rank trains the same
     replica and pushes rows shard_rows(n, rank, world) of each snapshot; the K x K Gram is summed across ranks by
-    `all_reduce` (the only collective) and the function returns the rank's ROWS of W_swa and P."""
+    `all_reduce` (the only collective) and the function returns the rank's ROWS of W_swa and P.
+
+    device_train=True keeps the training step itself on the device: forward, backward and the
+    Descent/ADAM update run in the library and every snapshot goes device-to-device into the SWA recurrence.  It is
+    defined for cost = mse(model(x), y) (the cost of README.md:86 and the docs' regression examples); the first
+    mini-batch's device loss is checked against `cost` and any other cost raises.  `model` receives the trained
+    weights at the end, as it would from the host loop."""
     if not isinstance(model, Chain):
         raise TypeError("Error: model_re function is not available for this model")   # src/libs.jl:59
     own = engine is None
@@ -55,6 +61,11 @@ def subspace_construction(model, cost, data, opt, *, T: int = 10, c: int = 1, M:
             raise ValueError("a sharded construction needs all_reduce and cannot install its (partial) subspace")
         eng.swa_begin(r1 - r0, K_max)
         training_loss = 0.0
+        if device_train:
+            if shard is not None:
+                raise ValueError("device_train pushes whole snapshots: it cannot be combined with a row shard")
+            training_loss = _train_on_device(eng, model, cost, data, opt, T, c, print_freq)
+            T = 0                                              # the host loop below has nothing left to do
         for i in range(1, T + 1):
             for x, y in data:
                 training_loss = train_step(model, cost, opt, x, y)
@@ -72,6 +83,46 @@ def subspace_construction(model, cost, data, opt, *, T: int = 10, c: int = 1, M:
     finally:
         if own:
             eng.close()
+
+
+def _train_on_device(eng: Engine, model, cost, data, opt, T: int, c: int, print_freq: int) -> float:
+    """The epoch loop of src/subspace_construction.jl:37-58 with the mini-batch step and the snapshot push on the device."""
+    if isinstance(opt, ADAM):
+        kind, eta, beta = "adam", opt.eta, opt.beta
+        if opt.state:
+            raise ValueError("device_train needs a fresh optimiser (ADAM state lives on the device)")
+    elif isinstance(opt, Descent):
+        kind, eta, beta = "descent", opt.eta, (0.9, 0.999)
+    else:
+        raise TypeError("device_train supports Descent and ADAM")
+    X, Y = split_data(data)
+    eng.set_model(model.dims, model.acts)
+    eng.set_data(X, Y)
+    eng.train_begin(extract_params(model), kind, eta, beta)
+    training_loss, checked = 0.0, False
+    try:
+        for i in range(1, T + 1):
+            for sel in data.index_batches():
+                if not checked:                                # the device step assumes cost = mse(model(x), y)
+                    import torch
+                    with torch.no_grad():
+                        host = float(cost(model, torch.as_tensor(np.asarray(X[..., sel], np.float32)),
+                                          torch.as_tensor(np.asarray(Y[..., sel], np.float32))))
+                contiguous = len(sel) > 0 and int(sel[-1]) - int(sel[0]) == len(sel) - 1 and bool(np.all(np.diff(sel) == 1))
+                training_loss = eng.train_step((int(sel[0]), len(sel)) if contiguous else sel)
+                if not checked:
+                    if abs(training_loss - host) > 1e-4 * max(1.0, abs(host)):
+                        raise ValueError("device_train: cost(model, x, y) is not mse(model(x), y) "
+                                         f"(host {host:.6g}, device {training_loss:.6g})")
+                    checked = True
+                if i % c == 0:
+                    eng.train_snapshot(i / c)                  # n = i/c (:46), epoch index (Q2)
+            if i % print_freq == 0 or i == T:
+                print("Traing loss: ", training_loss, " Epoch: ", i)    # (sic) :56-58
+        load_params(model, eng.train_weights())
+    finally:
+        eng.train_end()
+    return training_loss
 
 
 def sub_inference(in_model, data, W_swa, P, *, σ_z: float = 1.0, σ_m: float = 1.0, σ_p: float = 1.0, itr: int = 100,

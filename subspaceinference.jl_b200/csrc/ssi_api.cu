@@ -150,6 +150,7 @@ int ssi_ctx_destroy(ssi_ctx* ctx) {
     ssi_tc_destroy(ctx);
     ssi_b1_destroy(ctx);
     ssi_bm_destroy(ctx);
+    ssi_train_destroy(ctx);
     cudaFree(ctx->dX); cudaFree(ctx->dY); cudaFree(ctx->dP); cudaFree(ctx->dSubGram);
     cudaFree(ctx->dSwaMean); cudaFree(ctx->dDev);
     ssi_buf_t* bufs[] = {&ctx->bZ, &ctx->bLp, &ctx->bTerms, &ctx->bPartials, &ctx->bW, &ctx->bH0, &ctx->bH1, &ctx->bGram,
@@ -251,6 +252,7 @@ int ssi_set_model(ssi_ctx* ctx, int n_layers, const int32_t* dims, const int32_t
     ctx->has_model = true;
     if (shape_changed) { ctx->has_data = false; ctx->has_sub = false; }
     ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx); ssi_bm_invalidate(ctx);
+    if (ctx->train) { cudaStreamSynchronize(ctx->stream); ssi_train_destroy(ctx); }      // its weights had the old model's layout
     return SSI_OK;
 }
 
@@ -562,6 +564,53 @@ int ssi_swa_push(ssi_ctx* ctx, const float* W, double n_scalar) {
 }
 
 int64_t ssi_swa_columns(const ssi_ctx* ctx) { return ctx ? ctx->swa_K : -1; }
+
+// ---- on-device training step (the step before the path) ---------------------------------
+int ssi_train_begin(ssi_ctx* ctx, const float* W0, int32_t optimiser, double eta, double beta1, double beta2) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (!W0) return ssi_fail(ctx, SSI_ERR_ARG, "W0 must be non-NULL");
+    SSI_TRY(ssi_use_device(ctx));
+    return ssi_train_begin_impl(ctx, W0, optimiser, eta, beta1, beta2);
+}
+
+int ssi_train_step(ssi_ctx* ctx, const int64_t* idx, int64_t j0, int64_t nb, double* loss_out) {
+    if (!ctx) return SSI_ERR_ARG;
+    SSI_TRY(ssi_use_device(ctx));
+    call_timer t(ctx);
+    const int rc = ssi_train_step_impl(ctx, idx, j0, nb, loss_out);
+    t.stop(false);
+    return rc;
+}
+
+int ssi_train_snapshot(ssi_ctx* ctx, double n_scalar) {
+    if (!ctx) return SSI_ERR_ARG;
+    const float* dW = ssi_train_weights_device(ctx);
+    if (!dW) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_train_begin has not been called");
+    if (ctx->swa_n != ctx->model.n) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin(n = %lld parameters) must precede ssi_train_snapshot", (long long)ctx->model.n);
+    SSI_TRY(ssi_use_device(ctx));
+    call_timer t(ctx);
+    const int rc = ssi_swa_push_device(ctx, dW, n_scalar);
+    t.stop(false);
+    return rc;
+}
+
+int ssi_train_get_weights(ssi_ctx* ctx, float* W_out) {
+    if (!ctx) return SSI_ERR_ARG;
+    const float* dW = ssi_train_weights_device(ctx);
+    if (!dW) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_train_begin has not been called");
+    if (!W_out) return ssi_fail(ctx, SSI_ERR_ARG, "W_out must be non-NULL");
+    SSI_TRY(ssi_use_device(ctx));
+    SSI_CUDA(ctx, cudaMemcpyAsync(W_out, dW, sizeof(float) * (size_t)ctx->model.n, cudaMemcpyDeviceToHost, ctx->stream));
+    return ssi_sync(ctx);
+}
+
+int ssi_train_end(ssi_ctx* ctx) {
+    if (!ctx) return SSI_ERR_ARG;
+    SSI_TRY(ssi_use_device(ctx));
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ssi_train_destroy(ctx);
+    return SSI_OK;
+}
 
 // copies the results of a factorisation to the host and optionally installs them as the context's subspace
 static int swa_deliver(ssi_ctx* ctx, int M, float* dPout, double* ds, int sweeps_dummy, float* W_swa_out, float* P_out, double* s_out,

@@ -34,6 +34,7 @@ struct ssi_buf_t {
 struct ssi_tc_state;   // tensor-core path private state (ssi_tc.cu)
 struct ssi_b1_state;   // basis path private state (ssi_basis.cu)
 struct ssi_bm_state;   // basis path on the tensor cores (ssi_basis_mma.cu)
+struct ssi_train_state; // on-device training step (ssi_train.cu)
 
 struct ssi_ctx {
     int device = 0;
@@ -87,6 +88,8 @@ struct ssi_ctx {
     // basis path (one hidden layer, narrow output)
     ssi_b1_state* b1 = nullptr;
     ssi_bm_state* bm = nullptr;
+    // mini-batch training state (the step before the path)
+    ssi_train_state* train = nullptr;
 
     // stats
     ssi_stats_t stats{};
@@ -173,6 +176,11 @@ bool ssi_bm_supported(const ssi_ctx* ctx);
 void ssi_bm_invalidate(ssi_ctx* ctx);
 void ssi_bm_destroy(ssi_ctx* ctx);
 int  ssi_bm_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse);
+// on-device training step (ssi_train.cu)
+void ssi_train_destroy(ssi_ctx* ctx);
+int  ssi_train_begin_impl(ssi_ctx* ctx, const float* W0, int kind, double eta, double b1, double b2);
+int  ssi_train_step_impl(ssi_ctx* ctx, const int64_t* idx, int64_t j0, int64_t nb, double* loss_out);
+const float* ssi_train_weights_device(ssi_ctx* ctx);
 
 // ---- device helpers ---------------------------------------------------------------------
 __device__ __forceinline__ float ssi_act(float v, int act) {

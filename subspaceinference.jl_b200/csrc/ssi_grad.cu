@@ -15,6 +15,7 @@
 // final accumulation of the squared error.  This is the correctness-first version of SURVEY 8(f)-1: any Dense chain,
 // CUDA cores only.
 #include "ssi_common.cuh"
+#include "ssi_gemm.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -22,20 +23,6 @@
 #define GT_T 64
 #define GT_K 16
 #define GT_LD 68          // padded tile rows: float4 aligned, transposed fills spread over the banks
-
-struct gemm_t {
-    // C(o, j) = sum_k A(o, k) B(k, j) for batch b = blockIdx.z; all strides in elements
-    const float* A; long long a_so, a_sk, a_sb;
-    const float* B; long long b_sk, b_sj, b_sb;
-    float* C;       long long c_so, c_sj, c_sb;
-    int O, J;
-    long long K;            // contraction length (per batch when split > 0: the last batch may be shorter)
-    long long split;        // > 0: batch b covers k in [b*split, min(K, (b+1)*split))
-    int epi;                // 0 plain, 1 bias + activation, 2 multiply by act'(Hprev(o, j))
-    int act;
-    const float* bias; long long bias_sb;
-    const float* Hprev; long long h_sb;       // indexed like C
-};
 
 template <bool A_KFAST, bool B_JFAST>
 __global__ void __launch_bounds__(256)
@@ -102,7 +89,7 @@ k_gemm_simt(const gemm_t p) {
     }
 }
 
-static int launch_gemm(ssi_ctx* ctx, const gemm_t& g, int batches, bool a_kfast, bool b_jfast) {
+int ssi_launch_gemm(ssi_ctx* ctx, const gemm_t& g, int batches, bool a_kfast, bool b_jfast) {
     dim3 grid((g.J + GT_T - 1) / GT_T, (g.O + GT_T - 1) / GT_T, batches);
     if (grid.y > 65535 || grid.z > 65535) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "gradient path: shape too large for one launch");
     if (a_kfast && b_jfast) k_gemm_simt<true, true><<<grid, 256, 0, ctx->stream>>>(g);
@@ -147,6 +134,20 @@ k_grad_rowsum(const float* __restrict__ delta, long long d_sb, int O, long long 
     for (long long j = lane; j < N; j += 32) s += delta[g * d_sb + o + j * O];
     s = ssi_warp_sum(s);
     if (lane == 0) out[g * out_sb + o] = s;
+}
+
+int ssi_launch_delta_out(ssi_ctx* ctx, const float* pred, long long pred_sb, const float* Y, float* delta, long long delta_sb,
+                         long long N, int O, int act, float coef, int n_chunks, int g, double* partials) {
+    dim3 grid(n_chunks, g);
+    k_grad_delta_out<<<grid, 256, 0, ctx->stream>>>(pred, pred_sb, Y, delta, delta_sb, N, O, act, coef, n_chunks, partials);
+    SSI_LAUNCH_CHECK(ctx);
+    return SSI_OK;
+}
+int ssi_launch_rowsum(ssi_ctx* ctx, const float* delta, long long d_sb, int O, long long N, int g, float* out, long long out_sb) {
+    dim3 rg((O + 7) / 8, g);
+    k_grad_rowsum<<<rg, 256, 0, ctx->stream>>>(delta, d_sb, O, N, out, out_sb);
+    SSI_LAUNCH_CHECK(ctx);
+    return SSI_OK;
 }
 
 // grad_z(m, g) = sum_s part[s][m + g*M]  (+ prior terms), fixed order
@@ -251,7 +252,7 @@ int ssi_logpost_grad_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sig
             q.C = H + h_off[l + 1]; q.c_so = 1; q.c_sj = out; q.c_sb = act_elems;
             q.O = out; q.J = (int)N; q.K = in; q.split = 0;
             q.epi = 1; q.act = m.act[l]; q.bias = dW + m.b_off[l]; q.bias_sb = n;
-            SSI_TRY(launch_gemm(ctx, q, g, false, false));
+            SSI_TRY(ssi_launch_gemm(ctx, q, g, false, false));
         }
         // ---- output delta + squared error ----
         {
@@ -270,7 +271,7 @@ int ssi_logpost_grad_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sig
             q.B = l == 0 ? ctx->dX : H + h_off[l]; q.b_sk = in; q.b_sj = 1; q.b_sb = l == 0 ? 0 : act_elems;
             q.C = gW + m.w_off[l]; q.c_so = 1; q.c_sj = out; q.c_sb = n;
             q.O = out; q.J = in; q.K = N; q.split = 0; q.epi = 0;
-            SSI_TRY(launch_gemm(ctx, q, g, false, true));
+            SSI_TRY(ssi_launch_gemm(ctx, q, g, false, true));
             dim3 rg((out + 7) / 8, g);
             k_grad_rowsum<<<rg, 256, 0, ctx->stream>>>(delta, d_sb, out, N, gW + m.b_off[l], n);
             SSI_LAUNCH_CHECK(ctx);
@@ -282,7 +283,7 @@ int ssi_logpost_grad_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sig
                 r.C = D[l & 1]; r.c_so = 1; r.c_sj = in; r.c_sb = d_sb;
                 r.O = in; r.J = (int)N; r.K = out; r.split = 0;
                 r.epi = 2; r.act = m.act[l - 1]; r.Hprev = H + h_off[l]; r.h_sb = act_elems;
-                SSI_TRY(launch_gemm(ctx, r, g, true, false));
+                SSI_TRY(ssi_launch_gemm(ctx, r, g, true, false));
             }
         }
         // ---- grad_z = P' gW, split over rows of P, then fixed-order sum (+ priors) ----
@@ -292,7 +293,7 @@ int ssi_logpost_grad_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sig
             q.B = gW; q.b_sk = 1; q.b_sj = n; q.b_sb = 0;
             q.C = gpart; q.c_so = 1; q.c_sj = M; q.c_sb = (long long)M * g;
             q.O = M; q.J = g; q.K = n; q.split = split; q.epi = 0;
-            SSI_TRY(launch_gemm(ctx, q, S, true, false));
+            SSI_TRY(ssi_launch_gemm(ctx, q, S, true, false));
             k_grad_finish<<<(M * g + 127) / 128, 128, 0, ctx->stream>>>(gpart, S, M, g, (long long)M * g, dZ + b0 * M, ctx->dSubGram,
                                                                       1.0 / (sigma_p * sigma_p), 1.0 / (sigma_z * sigma_z), mask,
                                                                       d_grad + b0 * M);

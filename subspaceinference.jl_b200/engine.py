@@ -211,6 +211,43 @@ class Engine:
     def swa_push_dev(self, dW_ptr: int, n_scalar: float):
         self._check(self._lib.ssi_swa_push_dev(self._h, C.c_void_p(dW_ptr), float(n_scalar)))
 
+    # ---- the step before the path: mini-batch training on the device (include/ssi.h, ssi_train_*) ----
+    def train_begin(self, W0, optimiser: str = "descent", eta: float = 0.1, beta=(0.9, 0.999)):
+        """Start training from the flat weights W0 (src/libs.jl:19-22 layout).  optimiser: "descent" | "adam"."""
+        kinds = {"descent": 0, "adam": 1}
+        if optimiser not in kinds:
+            raise ValueError("optimiser must be 'descent' or 'adam'")
+        W0 = _f32(W0).reshape(-1)
+        if W0.shape[0] != self.n:
+            raise ValueError("W0 does not have the model's number of parameters")
+        self._check(self._lib.ssi_train_begin(self._h, _ptr(W0), kinds[optimiser], float(eta), float(beta[0]), float(beta[1])))
+
+    def train_step(self, batch, *, want_loss: bool = True):
+        """One mini-batch of `gradient + update!` (src/subspace_construction.jl:39-43) with cost = mse(m(x), y).
+        batch: an array of observation indices, or a (start, count) tuple for contiguous columns.  Returns
+        training_loss (before the update) or None."""
+        loss = C.c_double(0.0)
+        lp = C.byref(loss) if want_loss else None
+        if isinstance(batch, tuple):
+            rc = self._lib.ssi_train_step(self._h, None, int(batch[0]), int(batch[1]), lp)
+        else:
+            idx = np.ascontiguousarray(np.asarray(batch, dtype=np.int64).reshape(-1))
+            rc = self._lib.ssi_train_step(self._h, _ptr(idx), 0, int(idx.shape[0]), lp)
+        self._check(rc)
+        return float(loss.value) if want_loss else None
+
+    def train_snapshot(self, n_scalar: float):
+        """swa_push of the device-resident weights (no host round trip)."""
+        self._check(self._lib.ssi_train_snapshot(self._h, float(n_scalar)))
+
+    def train_weights(self) -> np.ndarray:
+        W = np.empty(self.n, np.float32)
+        self._check(self._lib.ssi_train_get_weights(self._h, _ptr(W)))
+        return W
+
+    def train_end(self):
+        self._check(self._lib.ssi_train_end(self._h))
+
     def swa_columns(self) -> int:
         return int(self._lib.ssi_swa_columns(self._h))
 

@@ -125,12 +125,17 @@ class DataLoader:
         n = self.data[0].shape[-1]
         return (n + self.batchsize - 1) // self.batchsize
 
-    def __iter__(self) -> Iterator[tuple[np.ndarray, np.ndarray]]:
-        X, Y = self.data
-        n = X.shape[-1]
+    def index_batches(self) -> Iterator[np.ndarray]:
+        """The observation indices of one epoch's mini-batches (what __iter__ slices with); the on-device training step
+        takes these instead of the data."""
+        n = self.data[0].shape[-1]
         idx = self._rng.permutation(n) if self.shuffle else np.arange(n)
         for s in range(0, n, self.batchsize):
-            sel = idx[s:s + self.batchsize]
+            yield idx[s:s + self.batchsize]
+
+    def __iter__(self) -> Iterator[tuple[np.ndarray, np.ndarray]]:
+        X, Y = self.data
+        for sel in self.index_batches():
             yield X[..., sel], Y[..., sel]
 
 

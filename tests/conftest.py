@@ -9,6 +9,12 @@ for p in (ROOT, ROOT / "oracle"):
         sys.path.insert(0, str(p))
 
 
+def stable_seed(*key) -> int:
+    """Seed from a test's parameters that is the same in every process (hash() of a str is salted per process)."""
+    import zlib
+    return zlib.crc32(repr(key).encode())
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
