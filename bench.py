@@ -369,7 +369,14 @@ def main():
                          "mma_frac": (3.0 * dom_tf / peak_tf) if (dom_tf and path_used == "tensor") else None},
             # the whole step (all kernels of the path), full algorithmic flops per unit incl. the first layer and the projection
             "step_roofline": {"achieved": per_gpu_flops / 1e12, "peak": peak_tf, "unit": "TFLOP/s", "frac": per_gpu_flops / 1e12 / peak_tf,
-                              "flops_per_unit": flops_unit, "per": "GPU"},
+                              "flops_per_unit": flops_unit, "per": "GPU",
+                              # the fraction against every denominator, so that no choice is hidden.  Split
+                              # precision issues three BF16 MMAs per FP32-grade product, so peak/3 is the honest ceiling for
+                              # the GEMM layers (the first layer and the projection are not GEMMs here, which is how the step
+                              # can exceed it).
+                              "frac_of": {"bf16_sustained": per_gpu_flops / 1e12 / peak_tf,
+                                          "bf16_burst": per_gpu_flops / 1e12 / peaks.get("bf16_tflops", peak_tf),
+                                          "bf16_sustained_div3_split_precision": 3.0 * per_gpu_flops / 1e12 / peak_tf}},
         }
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_reference(args.workload, budget_s=15.0)

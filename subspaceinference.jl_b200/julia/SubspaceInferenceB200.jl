@@ -82,12 +82,38 @@ function logpost_grad(ctx::Ctx, Z::AbstractMatrix; σ_m = 1.0, σ_p = 1.0, σ_z 
     return lp, g
 end
 
+# device_train = true keeps the mini-batch step itself on the device (ssi_train_*; cost must be mse(model(x), y), opt Descent or
+# ADAM): snapshots then go device-to-device into the SWA recurrence.  Mini-batches are contiguous windows of the data set
+# (a DataLoader without shuffle); pass index vectors to ssi_train_step for a shuffled one.
 function subspace_construction(model, cost, data, opt; T = 10, c = 1, M = 3, print_freq = 1,
-                               ctx::Ctx = Ctx())
+                               ctx::Ctx = Ctx(), device_train::Bool = false)
     training_loss = 0.0
     ps = Flux.params(model)
     n = length(flat_params(model))
     check(ctx, ccall((:ssi_swa_begin, libssi), Cint, (Ptr{Cvoid}, Int64, Int64), ctx.h, n, div(T, c) * length(data)))
+    if device_train
+        dims, acts = describe(model)
+        check(ctx, ccall((:ssi_set_model, libssi), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}), ctx.h, length(acts), dims, acts))
+        X = Matrix{Float32}(data.data[1]); Y = Matrix{Float32}(data.data[2]); N = size(X, 2)
+        check(ctx, ccall((:ssi_set_data, libssi), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int64), ctx.h, X, Y, N))
+        kind, β = opt isa Flux.ADAM ? (Int32(1), opt.beta) : (Int32(0), (0.9, 0.999))
+        check(ctx, ccall((:ssi_train_begin, libssi), Cint, (Ptr{Cvoid}, Ptr{Float32}, Int32, Float64, Float64, Float64),
+                         ctx.h, flat_params(model), kind, opt.eta, β[1], β[2]))
+        loss = Ref{Float64}(0.0)
+        for i in 1:T
+            for j0 in 0:data.batchsize:(N - 1)
+                check(ctx, ccall((:ssi_train_step, libssi), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Int64, Ptr{Float64}),
+                                 ctx.h, C_NULL, j0, min(data.batchsize, N - j0), loss))             # was :39-43
+                mod(i, c) == 0 && check(ctx, ccall((:ssi_train_snapshot, libssi), Cint, (Ptr{Cvoid}, Float64), ctx.h, i / c))
+            end
+            ((mod(i, print_freq) == 0) || (i == T)) && println("Traing loss: ", loss[], " Epoch: ", i)
+        end
+        W = Vector{Float32}(undef, n)
+        check(ctx, ccall((:ssi_train_get_weights, libssi), Cint, (Ptr{Cvoid}, Ptr{Float32}), ctx.h, W))
+        Flux.loadparams!(model, Flux.params(Flux.destructure(model)[2](W)))
+        check(ctx, ccall((:ssi_train_end, libssi), Cint, (Ptr{Cvoid},), ctx.h))
+        T = 0
+    end
     for i in 1:T
         for d in data
             gs = gradient(ps) do                                  # the SGD step stays in Flux/Zygote (:39-43)
