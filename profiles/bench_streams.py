@@ -59,6 +59,7 @@ def main():
     ap.add_argument("--K", type=int, default=100)
     ap.add_argument("--M", type=int, default=20)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (ssi_set_option), repeatable")
     ap.add_argument("--train", action="store_true", help="also time the on-device training step (SURVEY 8(f)-3) on the C4 model")
     a = ap.parse_args()
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6650.0}
@@ -76,6 +77,9 @@ def main():
     torch.cuda.set_stream(stream)
     eng = ssi.Engine(local)
     eng.set_stream(stream.cuda_stream)
+    for kv in a.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     g = torch.Generator(device=dev).manual_seed(4 + rank)
     w = 0.05 * torch.randn(a.n, device=dev, generator=g)
     snaps = []
