@@ -5,8 +5,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libssi.so"
+# SSI_LIB_PATH: load another build of the same library (A-B measurements of two builds in one GPU session)
+LIB_PATH = Path(os.environ["SSI_LIB_PATH"]).resolve() if os.environ.get("SSI_LIB_PATH") else PKG / "lib" / "libssi.so"
 
 SSI_OK = 0
 ERR_NAMES = {-1: "SSI_ERR_ARG", -2: "SSI_ERR_CUDA", -3: "SSI_ERR_STATE", -4: "SSI_ERR_RANK", -5: "SSI_ERR_UNSUPPORTED"}

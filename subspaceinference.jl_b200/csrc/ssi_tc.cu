@@ -41,6 +41,7 @@ typedef __nv_bfloat16 bf16;
 // ---------------------------------------------------------------------------------------
 struct tc_params {
     int N, G, m_tiles, n_tiles, k_blocks, BN, width, a_shared, act;
+    int a_il;               // A operand planes interleaved per k-block: row = [kb][hi 64 | lo 64] (the basis layer's output)
     int stages, stage_bytes;
     int mt_block;           // > 0: work order (mt block, sample, mt in block) so that concurrently running CTAs share A tiles
     int n_work;
@@ -147,8 +148,9 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                         const uint32_t full = bar_full + 8 * stage;
                         const uint32_t sA = smem_base + stage * p.stage_bytes;
                         mbar_expect_tx(full, 2 * a_bytes + 2 * b_bytes);
-                        tma_load_3d_hint(sA, &tmAh, full, kb * TC_BK, mt * TC_BM, p.a_shared ? 0 : g, pol_a);
-                        tma_load_3d_hint(sA + a_bytes, &tmAl, full, kb * TC_BK, mt * TC_BM, p.a_shared ? 0 : g, pol_a);
+                        const int ka = p.a_il ? 2 * kb * TC_BK : kb * TC_BK;
+                        tma_load_3d_hint(sA, &tmAh, full, ka, mt * TC_BM, p.a_shared ? 0 : g, pol_a);
+                        tma_load_3d_hint(sA + a_bytes, &tmAl, full, p.a_il ? ka + TC_BK : ka, mt * TC_BM, p.a_shared ? 0 : g, pol_a);
                         tma_load_3d_hint(sA + 2 * a_bytes, &tmBh, full, kb * TC_BK, nt * BN, g, TC_EVICT_LAST);
                         tma_load_3d_hint(sA + 2 * a_bytes + b_bytes, &tmBl, full, kb * TC_BK, nt * BN, g, TC_EVICT_LAST);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -561,8 +563,10 @@ k_tc_basis_layer(const float* __restrict__ bases /* [M+1][NW] */, long long NW, 
             const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
             const float2 hf = __bfloat1622float2(h2);
             const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
-            __stcs(reinterpret_cast<unsigned int*>(Hh + (long long)g * NW + e), *reinterpret_cast<const unsigned int*>(&h2));
-            __stcs(reinterpret_cast<unsigned int*>(Hl + (long long)g * NW + e), *reinterpret_cast<const unsigned int*>(&l2));
+            // interleaved output: 64 hi then 64 lo halves per block of 64 activations (see k_tc_basis_mma)
+            bf16* o = Hh + 2 * ((long long)g * NW + (e & ~63ll)) + (e & 63);
+            __stcs(reinterpret_cast<unsigned int*>(o), *reinterpret_cast<const unsigned int*>(&h2));
+            __stcs(reinterpret_cast<unsigned int*>(o + 64), *reinterpret_cast<const unsigned int*>(&l2));
         }
     }
 }
@@ -578,7 +582,6 @@ k_tc_basis_layer(const float* __restrict__ bases /* [M+1][NW] */, long long NW, 
 // Roles as in k_tc_layer: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue (activation, hi/lo split, TMA store to
 // H1[s][e] viewed as a [samples][N*width] matrix).
 #define TB_N 256
-#define TB_LO_DIRECT 0                            // A-B: lo halves of the output by direct 16-byte stores instead of TMA (measured: 32 ms vs 8.7 ms)
 #define TB_STAGES 2                                // the kernel writes 4x what it reads: shared memory goes to the store side
 #define TB_SBUF 3                                  // TMA-store staging buffers per epilogue warp (hi | lo, 2 x 4 KB each): the output
                                                    // stream is bound by the bytes in flight, 2 buffers gave 2.7 TB/s
@@ -592,8 +595,7 @@ template <int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__ CUtensorMap tmZl,
                const __grid_constant__ CUtensorMap tmTh, const __grid_constant__ CUtensorMap tmTl,
-               const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl, const int n_tiles,
-               bf16* __restrict__ out_lo, const long long NW, const int rows) {
+               const __grid_constant__ CUtensorMap tmO, const int n_tiles) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + TB_OFF_BAR);     // full[4] empty[4] tfull[2] tempty[2] zfull
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
@@ -609,7 +611,7 @@ k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__
         mbar_init(bar_z, 1);
         fence_barrier_init();
         tma_prefetch_desc(&tmZh); tma_prefetch_desc(&tmZl); tma_prefetch_desc(&tmTh); tma_prefetch_desc(&tmTl);
-        tma_prefetch_desc(&tmOh); tma_prefetch_desc(&tmOl);
+        tma_prefetch_desc(&tmO);
     }
     if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
     tc_fence_before();
@@ -664,16 +666,19 @@ k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__
         }
     } else {
         const int q = warp & 3;
-        // staging: per warp TB_SBUF buffers of (hi | lo) x [32 samples][64 activations] = 2 x 4 KB, SWIZZLE_128B.  128-byte
-        // rows: the TMA store engine is bound by rows per cycle (64-byte rows capped the kernel at 2.2 TB/s of writes).
-        // Also measured and dropped: one 256-byte 1-D bulk copy per lane and half tile (10.3 ms against 8.7 ms: the engine
-        // then pays per instruction); the lo halves through the LSU, scattered (32 ms) or read back transposed and
-        // coalesced (8.8 ms: no gain); and two output layouts that make these stores (nearly) sequential, [e/64][sample][64]
-        // and [datapoint][sample][width]: the layer drops to 6.7 / 7.6 ms, but the GEMM kernel that reads the activations
-        // then loses its contiguous 256 KB A tiles and slows from 32.0 to 34.3 / 34.5 ms per 128 samples (DRAM reads
-        // 57 -> 75 GB), a net loss.
+        // staging: per warp TB_SBUF buffers of [32 samples][hi | lo][64 activations] = 8 KB, SWIZZLE_128B.  The TMA store engine is
+        // bound by ROWS: lone 64-byte rows capped the kernel at 2.2 TB/s of writes, lone 128-byte rows (hi and lo planes as two
+        // tensors) at 3.6 TB/s = 8.7 ms per 128 samples.  Interleaving the planes per block of 64 activations makes every
+        // sample's (hi, lo) segments ADJACENT in memory, one box row pair = 256 contiguous bytes: 7.3 ms (4.3 TB/s of writes next
+        // to 1.1 TB/s of basis reads, i.e. the HBM roofline; profiles/micro/tma_store_rows.cu measures 4.5 -> 5.8 TB/s for the
+        // store engine alone).  The GEMM reads the same rows as before (hi tile of k-block kb at column 128 kb, lo at 128 kb + 64).
+        // Also measured and dropped: one 256-byte 1-D bulk copy per lane and half tile (10.3 ms: the engine then pays per
+        // instruction); the lo halves through the LSU, scattered (32 ms) or read back transposed and coalesced (8.8 ms); and
+        // two output layouts that make these stores (nearly) sequential, [e/64][sample][64] and [datapoint][sample][width]:
+        // the layer drops to 6.7 / 7.6 ms, but the GEMM kernel that reads the activations then loses its contiguous A tiles
+        // and slows from 32.0 to 34.3 / 34.5 ms per 128 samples (DRAM reads 57 -> 75 GB), a net loss.
         const uint32_t stage_w = smem_base + TB_OFF_STORE + (uint32_t)(warp - 2) * (TB_SBUF * 8192);
-        const uint32_t swz = (uint32_t)(lane & 7);
+        const uint32_t swz_h = (uint32_t)((2 * lane) & 7), swz_l = (uint32_t)((2 * lane + 1) & 7);     // SWIZZLE_128B: chunk ^ (row & 7)
         uint32_t chunk_ctr = 0, tile = 0, sbuf = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile) {
             const uint32_t ab = tile & 1, aphase = (tile >> 1) & 1;
@@ -686,7 +691,8 @@ k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__
                     if (lane == 0) tma_store_wait_read<TB_SBUF - 1>();
                     __syncwarp();
                 }
-                const uint32_t sh = stage_w + sbuf * 8192, sl = sh + 4096;
+                // staging box [32 samples][hi | lo][128 B]: row 2*lane is the sample's hi segment, row 2*lane + 1 its lo segment
+                const uint32_t sh = stage_w + sbuf * 8192;
                 if (++sbuf == TB_SBUF) sbuf = 0;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -706,28 +712,17 @@ k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__
                     }
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const uint32_t off = (uint32_t)lane * 128 + ((((uint32_t)(4 * half + c)) ^ swz) << 4);
-                        st_shared_v4(sh + off, hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-                        if (!TB_LO_DIRECT) st_shared_v4(sl + off, lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
-                    }
-                    if (TB_LO_DIRECT) {
-                        // (experiment) the lo halves leave through the LSU, 64 contiguous bytes per thread (lane = sample row):
-                        // 32 scattered 16-byte pieces per store instruction turned out 4x slower than the TMA route
-                        const long long e0 = (long long)t * TB_N + c0 + 32 * half;
-                        const int row = q * 32 + lane;
-                        if (row < rows && e0 + 32 <= NW) {
-                            uint4* dst = reinterpret_cast<uint4*>(out_lo + (long long)row * NW + e0);
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) __stcs(dst + c, make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]));
-                        }
+                        const uint32_t ch = (uint32_t)(4 * half + c);
+                        st_shared_v4(sh + (uint32_t)lane * 256 + ((ch ^ swz_h) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                        st_shared_v4(sh + (uint32_t)lane * 256 + 128 + ((ch ^ swz_l) << 4), lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
                     }
                 }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
                     // rows = samples (rows >= G are clipped by TMA), columns = activations e of this tile
-                    tma_store_3d_hint(&tmOh, sh, t * TB_N + c0, q * 32, 0, TC_EVICT_FIRST);
-                    if (!TB_LO_DIRECT) tma_store_3d_hint(&tmOl, sl, t * TB_N + c0, q * 32, 0, TC_EVICT_FIRST);
+                    // one store of 32 x 256 contiguous bytes: segment index = 2 * (64-activation block), hi and lo adjacent
+                    tma_store_3d_hint(&tmO, sh, 0, 2 * ((t * TB_N + c0) >> 6), q * 32, TC_EVICT_FIRST);
                     tma_store_commit();
                 }
             }
@@ -817,12 +812,12 @@ struct ssi_tc_state {
     float* bias[SSI_MAX_LAYERS] = {nullptr};
     bf16 *Hh[2] = {nullptr, nullptr}, *Hl[2] = {nullptr, nullptr};
     // basis-layer output [G][N][width0] (hi, lo) and its tensor maps as the A operand of the first GEMM layer
-    bf16 *Bh = nullptr, *Bl = nullptr;
+    bf16* Bh = nullptr;                      // basis layer output [G][N][width/64][hi 64 | lo 64] (planes interleaved per k-block)
     CUtensorMap tmBasisH, tmBasisL;
     // basis layer on the tensor cores (k_tc_basis_mma): K-major split-BF16 bases [N*width0][32], z of the group [128][32]
     bool basis_mma = false;
     bf16 *Th = nullptr, *Tl = nullptr, *Zh = nullptr, *Zl = nullptr;
-    CUtensorMap tmZh, tmZl, tmTh, tmTl, tmOh, tmOl;
+    CUtensorMap tmZh, tmZl, tmTh, tmTl, tmO;
     double* partials = nullptr;
     CUtensorMap tmAh[SSI_MAX_LAYERS], tmAl[SSI_MAX_LAYERS], tmBh[SSI_MAX_LAYERS], tmBl[SSI_MAX_LAYERS];
     CUtensorMap tmSh[SSI_MAX_LAYERS], tmSl[SSI_MAX_LAYERS];
@@ -832,7 +827,7 @@ struct ssi_tc_state {
 static void tc_free(ssi_tc_state* s) {
     cudaFree(s->Xh); cudaFree(s->Xl); cudaFree(s->partials); cudaFree(s->Wout); cudaFree(s->bout); cudaFree(s->bases); cudaFree(s->zpack);
     for (int i = 0; i < 2; ++i) { cudaFree(s->Hh[i]); cudaFree(s->Hl[i]); }
-    cudaFree(s->Bh); cudaFree(s->Bl); cudaFree(s->Th); cudaFree(s->Tl); cudaFree(s->Zh); cudaFree(s->Zl);
+    cudaFree(s->Bh); cudaFree(s->Th); cudaFree(s->Tl); cudaFree(s->Zh); cudaFree(s->Zl);
     for (int l = 0; l < SSI_MAX_LAYERS; ++l) { cudaFree(s->Wh[l]); cudaFree(s->Wl[l]); cudaFree(s->bias[l]); }
     PFN_encodeTiled enc = s->encode;
     *s = ssi_tc_state();
@@ -983,8 +978,7 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
     }
     if (s->basis) {
         const size_t NW = (size_t)N * s->width[0];
-        SSI_CUDA(ctx, cudaMalloc(&s->Bh, sizeof(bf16) * (size_t)G * NW));
-        SSI_CUDA(ctx, cudaMalloc(&s->Bl, sizeof(bf16) * (size_t)G * NW));
+        SSI_CUDA(ctx, cudaMalloc(&s->Bh, sizeof(bf16) * 2 * (size_t)G * NW));
         if (s->basis_mma) {
             SSI_CUDA(ctx, cudaMalloc(&s->Th, sizeof(bf16) * NW * 32));
             SSI_CUDA(ctx, cudaMalloc(&s->Tl, sizeof(bf16) * NW * 32));
@@ -1008,8 +1002,9 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
             SSI_TRY(tc_make_map(ctx, &s->tmAl[l], s->Xl, s->Kp[0], N, 1, TC_BK, TC_BM, S128));
         } else if (l == s->l0) {
             // activations written by the basis layer: [G][N][width_0]
-            SSI_TRY(tc_make_map(ctx, &s->tmBasisH, s->Bh, s->width[0], N, G, TC_BK, TC_BM, S128));
-            SSI_TRY(tc_make_map(ctx, &s->tmBasisL, s->Bl, s->width[0], N, G, TC_BK, TC_BM, S128));
+            // rows of 2 * width: [kb][hi 64 | lo 64]; the hi tile of k-block kb sits at column 128 kb, the lo tile at 128 kb + 64
+            SSI_TRY(tc_make_map(ctx, &s->tmBasisH, s->Bh, 2 * (uint64_t)s->width[0], N, G, TC_BK, TC_BM, S128));
+            s->tmBasisL = s->tmBasisH;
             s->tmAh[l] = s->tmBasisH;
             s->tmAl[l] = s->tmBasisL;
         } else {
@@ -1039,8 +1034,18 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
         SSI_TRY(tc_make_map(ctx, &s->tmTh, s->Th, 32, NW, 1, 32, TB_N, S64));
         SSI_TRY(tc_make_map(ctx, &s->tmTl, s->Tl, 32, NW, 1, 32, TB_N, S64));
         // the group's activations as a [samples][N*width0] matrix: boxes of 32 samples x 64 activations from the epilogue
-        SSI_TRY(tc_make_map(ctx, &s->tmOh, s->Bh, NW, (uint64_t)G, 1, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B));
-        SSI_TRY(tc_make_map(ctx, &s->tmOl, s->Bl, NW, (uint64_t)G, 1, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+        {   // store view: [samples][128-byte segments][64]; a box takes the (hi, lo) segment pair of 32 samples = 256 contiguous
+            // bytes per sample (adjacent 128-byte rows: 5.8 TB/s through the TMA store engine against 4.5 for lone rows,
+            // profiles/micro/tma_store_rows.cu)
+            cuuint64_t dims[3] = {64, 2 * (cuuint64_t)NW / 64, (cuuint64_t)G};
+            cuuint64_t strides[2] = {128, 2 * (cuuint64_t)NW * sizeof(bf16)};
+            cuuint32_t box[3] = {64, 2, 32};
+            cuuint32_t estr[3] = {1, 1, 1};
+            const CUresult r = s->encode(&s->tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, s->Bh, dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return ssi_fail(ctx, SSI_ERR_CUDA, "cuTensorMapEncodeTiled (basis store) failed with CUresult %d", (int)r);
+        }
         SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_basis_mma<SSI_ACT_IDENTITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_TOTAL));
         SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_basis_mma<SSI_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_TOTAL));
         SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_basis_mma<SSI_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_TOTAL));
@@ -1072,10 +1077,10 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
             const int n_tiles = (int)((NW + TB_N - 1) / TB_N);
             const int grid = std::min(ctx->sm_count, n_tiles);
             switch (m.act[0]) {
-                case SSI_ACT_RELU:    k_tc_basis_mma<SSI_ACT_RELU><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles, s->Bl, NW, s->G); break;
-                case SSI_ACT_TANH:    k_tc_basis_mma<SSI_ACT_TANH><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles, s->Bl, NW, s->G); break;
-                case SSI_ACT_SIGMOID: k_tc_basis_mma<SSI_ACT_SIGMOID><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles, s->Bl, NW, s->G); break;
-                default:              k_tc_basis_mma<SSI_ACT_IDENTITY><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmOh, s->tmOl, n_tiles, s->Bl, NW, s->G); break;
+                case SSI_ACT_RELU:    k_tc_basis_mma<SSI_ACT_RELU><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmO, n_tiles); break;
+                case SSI_ACT_TANH:    k_tc_basis_mma<SSI_ACT_TANH><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmO, n_tiles); break;
+                case SSI_ACT_SIGMOID: k_tc_basis_mma<SSI_ACT_SIGMOID><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmO, n_tiles); break;
+                default:              k_tc_basis_mma<SSI_ACT_IDENTITY><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmO, n_tiles); break;
             }
             SSI_LAUNCH_CHECK(ctx);
         }
@@ -1088,8 +1093,8 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
                 SSI_LAUNCH_CHECK(ctx);
                 const long long per_cta = (long long)TC_BASIS_THREADS * TC_BASIS_ITERS * 2;
                 const unsigned blocks = (unsigned)((NW + per_cta - 1) / per_cta);
-                bf16* oh = s->Bh + (long long)g0 * NW;
-                bf16* ol = s->Bl + (long long)g0 * NW;
+                bf16* oh = s->Bh + 2 * (long long)g0 * NW;
+                bf16* ol = nullptr;                                 // lo halves are interleaved behind the hi halves
                 if (M <= 8) tc_launch_basis<8>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol);
                 else if (M <= 12) tc_launch_basis<12>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol);
                 else if (M <= 20) tc_launch_basis<20>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol);
@@ -1129,6 +1134,7 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
             p.n_tiles = s->width[l] / s->BN[l];
             p.k_blocks = s->Kp[l] / TC_BK;
             p.a_shared = (l == 0);
+            p.a_il = (l == 1 && s->basis) ? 1 : 0;
             p.act = m.act[l];
             p.stage_bytes = 2 * TC_BM * TC_BK * 2 + 2 * p.BN * TC_BK * 2;
             p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
