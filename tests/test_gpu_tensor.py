@@ -57,6 +57,10 @@ def test_random_shapes_tensor_vs_oracle(ssi, engine, dims, acts, N, M, B):
     lp = engine.logpost(Z, 0.8)
     ref, _ = orc.logpost_batch(prob, Z, 0.8)
     np.testing.assert_allclose(lp, ref, rtol=RTOL)
+    # A-B variant: 2-CTA clusters that share the weight tiles by TMA multicast (odd tile counts exercise the dummy row block)
+    engine.set_option("tc_cluster", 1)
+    np.testing.assert_allclose(engine.logpost(Z, 0.8), ref, rtol=RTOL)
+    engine.set_option("tc_cluster", 0)
     # the FP32 SIMT path of the same library must agree with the oracle at least as well
     engine.set_option("path", ssi.PATH_LAYERED)
     lp_simt = engine.logpost(Z, 0.8)
