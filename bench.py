@@ -330,6 +330,7 @@ def main():
         e2e = units_step * e2e_steps / (ms_e2e * 1e-3)
         per_gpu_flops = flops_unit * B * prob.N * units_per_eval_batch * args.steps / (ms_dev * 1e-3)
         peak_tf = peaks["bf16_tflops_sustained"]
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
         # dominant kernel (rank 0): its own algorithmic flops per launch over its own average launch time
         dims = prob.dims
         if path_used == "tensor":      # k_tc_layer<FUSED>: every Dense layer after the first (the first is the basis-layer stream)
@@ -366,7 +367,11 @@ def main():
                          "note": "algorithmic FP32 flops of this kernel (padding not counted). FP32-grade results need 3 BF16 MMAs "
                                  "per product (hi*hi + hi*lo + lo*hi), so the tensor pipe executes 3x this figure: "
                                  "mma_frac = 3*frac is the share of the BF16 peak the kernel keeps busy",
-                         "mma_frac": (3.0 * dom_tf / peak_tf) if (dom_tf and path_used == "tensor") else None},
+                         "mma_frac": (3.0 * dom_tf / peak_tf) if (dom_tf and path_used == "tensor") else None,
+                         # a 13-50-1 net has no GEMM to speak of: against the FP32 CUDA-core peak (128 FMA/clk/SM at the maximum SM
+                         # clock) the same figure reads as follows (> 1 is possible because the first layer runs on the tensor cores)
+                         "frac_of_fp32_simt_peak": ((dom_tf / (sm_count * 128 * 2 * clk.summary()["sm_max_mhz"] * 1e6 / 1e12))
+                                                    if (dom_tf and path_used != "tensor") else None)},
             # the whole step (all kernels of the path), full algorithmic flops per unit incl. the first layer and the projection
             "step_roofline": {"achieved": per_gpu_flops / 1e12, "peak": peak_tf, "unit": "TFLOP/s", "frac": per_gpu_flops / 1e12 / peak_tf,
                               "flops_per_unit": flops_unit, "per": "GPU",
