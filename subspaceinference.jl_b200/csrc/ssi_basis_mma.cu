@@ -10,8 +10,8 @@
 // weights in registers, applies the activation to its 256 TMEM columns, folds them into Hp-long dot products (the output
 // layer), subtracts y and accumulates the squared error in FP64.  One FP64 partial per (sample, CTA) leaves the kernel.
 //
-// Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-9 epilogue (warp w: TMEM lane quarter w % 4 of
-// sample group (w - 2) / 4).  Bound: the epilogue (register-file bandwidth of the dot products with per-sample weights).
+// Roles: warp 0 TMA producer, warps 1 and 10 MMA issuers (one per sample group; warp 1 also allocates TMEM), warps 2-9 epilogue
+// (warp w: TMEM lane quarter w % 4 of sample group (w - 2) / 4).  Bound: the epilogue (register-file bandwidth of the dot products with per-sample weights).
 //
 // PACKED operands (M + 1 <= 8): K = 16 leaves most of the contraction index empty (6 of 16 for M = 5), so the six
 // (z part, basis part) products are laid side by side ALONG K instead of being issued as six MMAs: column c = term*(M+1) + m
@@ -25,9 +25,16 @@
 
 typedef __nv_bfloat16 bf16;
 
-#define BM_THREADS 320
-#define BM_N 128                       // activations per tile (4 accumulators of 128 TMEM columns: 2 sample groups x 2 buffers)
+#define BM_THREADS 352
+// Activations per tile: NT = (datapoints per tile) x HP <= 128 (4 accumulators of 128 TMEM columns: 2 sample groups x 2 buffers).
+// HP, the hidden width rounded up, is one of 32, 40, 48, 56, 64: the epilogue walks a datapoint's columns in TMEM chunks of
+// 32, 16 and 8 columns, so H = 50 costs 56 columns of work, not 64.
 #define BM_STAGES 4
+__host__ __device__ constexpr int bm_dpt(int hp) { return hp == 32 ? 4 : 2; }                      // datapoints per tile
+__host__ __device__ constexpr int bm_nt(int hp) { return bm_dpt(hp) * hp; }
+__host__ __device__ constexpr int bm_nchunk(int hp) { return hp == 32 ? 1 : (hp == 56 ? 3 : 2); }   // TMEM chunks per datapoint
+__host__ __device__ constexpr int bm_chunk_size(int hp, int i) { return i == 0 ? 32 : (hp == 64 ? 32 : (hp == 40 ? 8 : (i == 1 ? 16 : 8))); }
+__host__ __device__ constexpr int bm_chunk_off(int hp, int i) { return i == 0 ? 0 : (i == 1 ? 32 : 48); }
 #define BM_MAXHP 64
 
 struct bm_params {
@@ -50,6 +57,33 @@ __device__ __forceinline__ float bm_act(float v) {
     return v;
 }
 
+// issue the TMEM load of SZ consecutive columns of this thread's lane
+template <int SZ>
+__device__ __forceinline__ void bm_tmem_ld(uint32_t taddr, uint32_t* v) {
+    if (SZ == 32) tmem_ld32(taddr, v);
+    else if (SZ == 16) tmem_ld16(taddr, v);
+    else tmem_ld8(taddr, v);
+}
+
+// fold SZ hidden units (TMEM columns in v, second-layer weights in wh) into the partial dot products
+template <int ACT, bool HALF, int NL, int SZ>
+__device__ __forceinline__ void bm_fold(const uint32_t* v, const float2* wh, float2* lin, float* ab4) {
+#pragma unroll
+    for (int j = 0; j < SZ; j += 2) {
+        float2 x = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+        const float2 w2 = wh[j >> 1];
+        if (HALF) {
+            ab4[j & 3] = fmaf(fabsf(x.x), w2.x, ab4[j & 3]);
+            ab4[(j + 1) & 3] = fmaf(fabsf(x.y), w2.y, ab4[(j + 1) & 3]);
+            lin[(j >> 1) & 1] = __ffma2_rn(x, w2, lin[(j >> 1) & 1]);
+        } else {
+            x.x = bm_act<ACT>(x.x);
+            x.y = bm_act<ACT>(x.y);
+            lin[(j >> 1) & (NL - 1)] = __ffma2_rn(x, w2, lin[(j >> 1) & (NL - 1)]);
+        }
+    }
+}
+
 // KB = 16 (SWIZZLE_32B rows of 32 bytes) or 32 (SWIZZLE_64B rows of 64 bytes)
 template <int KB>
 __device__ __forceinline__ uint64_t bm_desc(uint32_t smem_addr) {
@@ -66,6 +100,7 @@ template <int ACT, int KB, int HP, bool PACKED, bool OUT_ID, int VAR>
 __global__ void __launch_bounds__(BM_THREADS, 1)
 k_b1_mma(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmT, const bm_params p) {
     constexpr uint32_t ROW = KB * 2;                       // bytes per operand row
+    constexpr int BM_N = bm_nt(HP);
     constexpr uint32_t B_TILE = BM_N * ROW;                // one of (hi, mid, lo)
     constexpr uint32_t STAGE = 3 * B_TILE;
     constexpr uint32_t Z_TILE = 128 * ROW;                 // one sample group, one of (hi, mid, lo)
@@ -82,7 +117,7 @@ k_b1_mma(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtens
 
     if (threadIdx.x == 0) {
         if (smem_base & 1023u) { printf("ssi_basis_mma: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
-        for (int s = 0; s < BM_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < BM_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 2); }
         for (int b = 0; b < 4; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 128); }
         mbar_init(bar_z, 1);
         fence_barrier_init();
@@ -114,8 +149,11 @@ k_b1_mma(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtens
                     if (++stage == BM_STAGES) { stage = 0; phase ^= 1; }
                 }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 10) {
+        // one MMA issuer per sample group (warp 1: group 0, warp 10: group 1).  The tiles are tiny (three to twelve MMAs), so a
+        // single issuing thread that serves both groups is bound by its own chain of mbarrier waits, not by the tensor pipe.
         if (lane == 0) {
+            const int g = warp == 1 ? 0 : 1;
             const uint32_t idesc = umma_idesc_bf16(BM_N);
             mbar_wait(bar_z, 0);
             tc_fence_after();
@@ -128,7 +166,7 @@ k_b1_mma(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtens
                     const uint32_t sB = smem_base + stage * STAGE;
                     const uint64_t bh = bm_desc<KB>(sB), bm = bm_desc<KB>(sB + B_TILE), bl = bm_desc<KB>(sB + 2 * B_TILE);
                     const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
-                    for (int g = 0; g < 2; ++g) {
+                    {
                         mbar_wait(bar_tempty + 8 * (2 * g + ab), aphase ^ 1);   // the epilogue two tiles back has drained this accumulator
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + (2 * g + ab) * 128;
@@ -162,7 +200,7 @@ k_b1_mma(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtens
                 }
         }
     } else {
-        const int q = warp & 3, g = (warp - 2) >> 2;      // a warp may only touch TMEM lanes [32 (warp % 4), +32)
+        const int q = warp & 3, g = (warp - 2) >> 2;      // warps 2-9; a warp may only touch TMEM lanes [32 (warp % 4), +32)
         const long long srow = (long long)block * 256 + g * 128 + q * 32 + lane;      // this thread's sample
         const bool valid = srow < p.S;
         // second-layer weights and bias of this sample, in registers for the whole kernel (zero for padded hidden units).
@@ -186,14 +224,16 @@ k_b1_mma(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtens
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (2 * g) * 128;
         const uint32_t bar_f = bar_tfull + 16 * g, bar_e = bar_tempty + 16 * g;
 
-        // Software pipeline over the tile's chunks of 32 columns: the TMEM load of chunk c+1 is in flight while chunk c is folded
-        // into partial dot products; the accumulator is handed back to the MMA warp as soon as its last chunk sits in
-        // registers.  (Prefetching the next tile's first chunk as well costs registers the kernel does not have: 168 is the
-        // ceiling with 10 warps, three of them on one scheduler, and the spills made it 25 % slower.)
+        // Software pipeline over the tile's TMEM chunks (per datapoint 32 [+16] [+8] or 32+32 columns, consecutive chunks in
+        // different registers): the load of the next chunk is in flight while this one is folded into partial dot products;
+        // the accumulator is handed back to the MMA warp as soon as its last chunk sits in registers.  (Prefetching the next
+        // tile's first chunk as well costs registers the kernel does not have: 168 is the ceiling with 10 warps, three of
+        // them on one scheduler, and the spills made it 25 % slower.)
         int pp = blockIdx.x, t = pp;                        // parts >= gridDim.x and n_tiles >= parts: the first tile exists
         uint32_t it = 0;
         float s_hi = 0.0f, s_lo = 0.0f;                     // squared errors of the current part, two-float (error-free) sum
-        uint32_t v[2][32];
+        constexpr int NC = bm_nchunk(HP);
+        uint32_t v[HP == 32 ? 64 : (HP > 32 ? HP : 32)];    // HP = 32: two 32-column buffers alternate between datapoints
         while (true) {
             int tn = t + parts, ppn = pp;
             if (tn >= n_tiles) { ppn = pp + gx; tn = ppn; }
@@ -211,42 +251,44 @@ k_b1_mma(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtens
             float ab4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             mbar_wait(bar_f + 8 * ab, (it >> 1) & 1);
             tc_fence_after();
-            tmem_ld32(taddr0 + ab * 128, v[0]);
+            const uint32_t ta = taddr0 + ab * 128;
+            bm_tmem_ld<32>(ta, v);
 #pragma unroll
-            for (int c = 0; c < BM_N / 32; ++c) {
-                tmem_ld_wait();
-                if (c + 1 < BM_N / 32) tmem_ld32(taddr0 + ab * 128 + (c + 1) * 32, v[(c + 1) & 1]);
-                else {
-                    tc_fence_before();
-                    mbar_arrive(bar_e + 8 * ab);             // the whole accumulator is in registers
-                }
-                const int j0 = (c * 32) % HP;
+            for (int d = 0; d < DPT; ++d) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float2 x = make_float2(__uint_as_float(v[c & 1][j]), __uint_as_float(v[c & 1][j + 1]));
-                    const float2 w2 = wh[(j0 + j) >> 1];
-                    if (HALF) {
-                        ab4[j & 3] = fmaf(fabsf(x.x), w2.x, ab4[j & 3]);
-                        ab4[(j + 1) & 3] = fmaf(fabsf(x.y), w2.y, ab4[(j + 1) & 3]);
-                        lin[(j >> 1) & 1] = __ffma2_rn(x, w2, lin[(j >> 1) & 1]);
+                for (int i = 0; i < NC; ++i) {
+                            const int sz = bm_chunk_size(HP, i), off = bm_chunk_off(HP, i);
+                    const int boff = HP == 32 ? (d & 1) * 32 : off;              // registers of this chunk
+                    // next chunk: (d, i + 1) or (d + 1, 0)
+                    const bool last = (d == DPT - 1) && (i == NC - 1);
+                    const int dn = (i == NC - 1) ? d + 1 : d, in_ = (i == NC - 1) ? 0 : i + 1;
+                    const int szn = bm_chunk_size(HP, in_), offn = bm_chunk_off(HP, in_);
+                    const int boffn = HP == 32 ? (dn & 1) * 32 : offn;
+                    tmem_ld_wait();
+                    if (!last) {
+                        const uint32_t tan = ta + dn * HP + offn;
+                        if (szn == 32) bm_tmem_ld<32>(tan, v + boffn);
+                        else if (szn == 16) bm_tmem_ld<16>(tan, v + boffn);
+                        else bm_tmem_ld<8>(tan, v + boffn);
                     } else {
-                        x.x = bm_act<ACT>(x.x);
-                        x.y = bm_act<ACT>(x.y);
-                        lin[(j >> 1) & (NL - 1)] = __ffma2_rn(x, w2, lin[(j >> 1) & (NL - 1)]);
+                        tc_fence_before();
+                        mbar_arrive(bar_e + 8 * ab);         // the whole accumulator is in registers
                     }
-                }
-                if (((c + 1) * 32) % HP == 0) {              // a datapoint is complete
-                    const int d = (c * 32) / HP;
-                    float pre = (lin[0].x + lin[0].y) + (lin[1].x + lin[1].y);
-                    if (NL == 4) pre += (lin[NL - 2].x + lin[NL - 2].y) + (lin[NL - 1].x + lin[NL - 1].y);
-                    if (HALF) pre += (ab4[0] + ab4[1]) + (ab4[2] + ab4[3]);
-                    pre += b2;
-                    if (!OUT_ID) pre = ssi_act(pre, p.act_out);
-                    const float df = (i_base + d < N) ? pre - yv[d] : 0.0f;
-                    sse_t = fmaf(df, df, sse_t);
+                    if (sz == 32) bm_fold<ACT, HALF, NL, 32>(v + boff, wh + (off >> 1), lin, ab4);
+                    else if (sz == 16) bm_fold<ACT, HALF, NL, 16>(v + boff, wh + (off >> 1), lin, ab4);
+                    else bm_fold<ACT, HALF, NL, 8>(v + boff, wh + (off >> 1), lin, ab4);
+                    if (i == NC - 1) {                       // a datapoint is complete
+                        float pre = (lin[0].x + lin[0].y) + (lin[1].x + lin[1].y);
+                        if (NL == 4) pre += (lin[NL - 2].x + lin[NL - 2].y) + (lin[NL - 1].x + lin[NL - 1].y);
+                        if (HALF) pre += (ab4[0] + ab4[1]) + (ab4[2] + ab4[3]);
+                        pre += b2;
+                        if (!OUT_ID) pre = ssi_act(pre, p.act_out);
+                        const float df = (i_base + d < N) ? pre - yv[d] : 0.0f;
+                        sse_t = fmaf(df, df, sse_t);
 #pragma unroll
-                    for (int i = 0; i < NL; ++i) lin[i] = make_float2(0.0f, 0.0f);
-                    ab4[0] = ab4[1] = ab4[2] = ab4[3] = 0.0f;
+                        for (int k = 0; k < NL; ++k) lin[k] = make_float2(0.0f, 0.0f);
+                        ab4[0] = ab4[1] = ab4[2] = ab4[3] = 0.0f;
+                    }
                 }
             }
             {   // (s_hi, s_lo) += sse_t without rounding error (TwoSum); no FP64 in the loop (a DADD per tile throttled the FP64 pipe)
@@ -388,7 +430,7 @@ bool ssi_bm_supported(const ssi_ctx* ctx) {
     if (!ctx->has_model || !ctx->has_sub || !ctx->has_data) return false;
     const ssi_model_t& m = ctx->model;
     if (m.L != 2 || m.dims[2] != 1 || m.dims[1] > BM_MAXHP || ctx->M + 1 > 32) return false;
-    const long long Hp = m.dims[1] <= 32 ? 32 : 64;
+    const long long Hp = 64;
     return ctx->N * Hp < (1ll << 31) && !ctx->opt_b1_simt;
 }
 
@@ -420,11 +462,12 @@ static int bm_prepare(ssi_ctx* ctx) {
     const int H = m.dims[1], M1 = ctx->M + 1;
     const long long N = ctx->N;
     s->KB = M1 <= 16 ? 16 : 32;
-    s->Hp = H <= 32 ? 32 : 64;
+    s->Hp = H <= 32 ? 32 : (H <= 40 ? 40 : (H <= 48 ? 48 : (H <= 56 ? 56 : 64)));
     s->packed_ns = (M1 <= 8 && !ctx->opt_bm_nopack) ? (6 * M1 + 15) / 16 : 0;
     const int slabs = s->packed_ns ? s->packed_ns : 3;
     const long long NW = N * s->Hp;
-    s->n_tiles = (NW + BM_N - 1) / BM_N;
+    const int NT = bm_nt(s->Hp);
+    s->n_tiles = (NW + NT - 1) / NT;
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(s->T);
     s->T = nullptr;
@@ -435,7 +478,7 @@ static int bm_prepare(ssi_ctx* ctx) {
     const long long total = NW * s->KB;
     k_bm_bases_kmajor<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const float*)ctx->bH0.p, N, H, s->Hp, M1, s->KB, s->packed_ns, s->T);
     SSI_LAUNCH_CHECK(ctx);
-    SSI_TRY(bm_make_map(ctx, &s->tmT, s->T, s->KB, (uint64_t)NW, BM_N, slabs));
+    SSI_TRY(bm_make_map(ctx, &s->tmT, s->T, s->KB, (uint64_t)NW, NT, slabs));
     s->ready = true;
     return SSI_OK;
 }
@@ -464,11 +507,16 @@ int ssi_bm_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
     const int M = ctx->M, H = m.dims[1], KB = s->KB, Hp = s->Hp;
     const int slabs = s->packed_ns ? s->packed_ns : 3;
     const int a0 = m.act[0], a1 = m.act[1], var = ctx->opt_bm_variant;
-    bm_kernel_t kern = s->packed_ns ? (Hp == 32 ? bm_pick<16, 32, true>(a0, a1, var) : bm_pick<16, 64, true>(a0, a1, var))
-                     : KB == 16     ? (Hp == 32 ? bm_pick<16, 32, false>(a0, a1, var) : bm_pick<16, 64, false>(a0, a1, var))
-                                    : (Hp == 32 ? bm_pick<32, 32, false>(a0, a1, var) : bm_pick<32, 64, false>(a0, a1, var));
+    bm_kernel_t kern = nullptr;
+#define BM_PICK_HP(HPV)                                                                                      \
+    if (Hp == HPV)                                                                                           \
+        kern = s->packed_ns ? bm_pick<16, HPV, true>(a0, a1, var)                                            \
+                            : (KB == 16 ? bm_pick<16, HPV, false>(a0, a1, var) : bm_pick<32, HPV, false>(a0, a1, var));
+    BM_PICK_HP(32) BM_PICK_HP(40) BM_PICK_HP(48) BM_PICK_HP(56) BM_PICK_HP(64)
+#undef BM_PICK_HP
+    if (!kern) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "basis mma path: no kernel for padded hidden width %d", Hp);
     // at least 120 KB so that exactly one CTA (which allocates all 512 TMEM columns) is resident per SM
-    const size_t smem = std::max<size_t>((size_t)BM_STAGES * 3 * BM_N * KB * 2 + 6 * 128 * KB * 2 + 24 * 8 + 16, 120 * 1024);
+    const size_t smem = std::max<size_t>((size_t)BM_STAGES * 3 * 128 * KB * 2 + 6 * 128 * KB * 2 + 24 * 8 + 16, 120 * 1024);
     SSI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     const int64_t n_blocks = (B + 255) / 256;
