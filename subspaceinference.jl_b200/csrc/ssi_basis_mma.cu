@@ -65,22 +65,27 @@ __device__ __forceinline__ void bm_tmem_ld(uint32_t taddr, uint32_t* v) {
     else tmem_ld8(taddr, v);
 }
 
-// fold SZ hidden units (TMEM columns in v, second-layer weights in wh) into the partial dot products
-template <int ACT, bool HALF, int NL, int SZ>
+// fold SZ hidden units (TMEM columns in v, second-layer weights in wh) into the partial dot products.
+// ReLU variants (MODE): 0 every pair as (w/2) x + (w/2) |x| (FFMA2 + two FFMA with the |.| operand modifier: FMA pipes only);
+// 1 (default) every pair clamped with FMNMX (ALU pipe) then one FFMA2.  Measured on the UCI config: 373 us against 333 us, and
+// a mix of the two (one pair in four as in 0, which would balance the ALU and FMA pipes on paper) 377 us: what counts is
+// register-file traffic, six operand reads per hidden unit for 0 against four for 1.
+// Chunks start at multiples of 8 pairs, so the local pair index decides like the global one (bm_pair_half).
+__host__ __device__ constexpr bool bm_pair_half(int mode, int pair) { return mode == 0 || (mode == 2 && (pair & 3) == 3); }
+template <int ACT, int MODE, int NL, int SZ>
 __device__ __forceinline__ void bm_fold(const uint32_t* v, const float2* wh, float2* lin, float* ab4) {
 #pragma unroll
     for (int j = 0; j < SZ; j += 2) {
         float2 x = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
         const float2 w2 = wh[j >> 1];
-        if (HALF) {
+        if (ACT == SSI_ACT_RELU && bm_pair_half(MODE, j >> 1)) {
             ab4[j & 3] = fmaf(fabsf(x.x), w2.x, ab4[j & 3]);
             ab4[(j + 1) & 3] = fmaf(fabsf(x.y), w2.y, ab4[(j + 1) & 3]);
-            lin[(j >> 1) & 1] = __ffma2_rn(x, w2, lin[(j >> 1) & 1]);
         } else {
             x.x = bm_act<ACT>(x.x);
             x.y = bm_act<ACT>(x.y);
-            lin[(j >> 1) & (NL - 1)] = __ffma2_rn(x, w2, lin[(j >> 1) & (NL - 1)]);
         }
+        lin[(j >> 1) & (NL - 1)] = __ffma2_rn(x, w2, lin[(j >> 1) & (NL - 1)]);
     }
 }
 
@@ -206,17 +211,18 @@ k_b1_mma(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtens
         // second-layer weights and bias of this sample, in registers for the whole kernel (zero for padded hidden units).
         // ReLU, VAR 0: relu(x) w = (w/2) x + (w/2) |x| -- a packed FFMA2 for two hidden units' linear parts and an FFMA with the
         // free |.| operand modifier each, all on the FMA pipes.  VAR 1: clamp with FMNMX (ALU pipe), then one FFMA2 per pair.
-        constexpr bool HALF = ACT == SSI_ACT_RELU && VAR == 0;
+        constexpr bool HALF = ACT == SSI_ACT_RELU && VAR != 1;          // some pairs use the |x| form: their weights are halved
         constexpr int DPT = BM_N / HP;                     // datapoints per tile
         float2 wh[HP / 2];
         {
             const float4* wrow = reinterpret_cast<const float4*>(p.W2 + srow * HP);
-            const float sc = HALF ? 0.5f : 1.0f;
 #pragma unroll
             for (int j = 0; j < HP / 4; ++j) {
                 const float4 w4 = valid ? __ldg(wrow + j) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                wh[2 * j] = make_float2(sc * w4.x, sc * w4.y);
-                wh[2 * j + 1] = make_float2(sc * w4.z, sc * w4.w);
+                const float s0 = (ACT == SSI_ACT_RELU && bm_pair_half(VAR, 2 * j)) ? 0.5f : 1.0f;
+                const float s1 = (ACT == SSI_ACT_RELU && bm_pair_half(VAR, 2 * j + 1)) ? 0.5f : 1.0f;
+                wh[2 * j] = make_float2(s0 * w4.x, s0 * w4.y);
+                wh[2 * j + 1] = make_float2(s1 * w4.z, s1 * w4.w);
             }
         }
         const float b2 = valid ? __ldg(p.B2 + srow) : 0.0f;
@@ -244,7 +250,7 @@ k_b1_mma(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtens
 #pragma unroll
             for (int d = 0; d < DPT; ++d) yv[d] = (i_base + d < N) ? __ldg(p.Y + i_base + d) : 0.0f;
             float sse_t = 0.0f;
-            constexpr int NL = HALF ? 2 : 4;                // independent FFMA2 chains
+            constexpr int NL = (ACT == SSI_ACT_RELU && VAR == 0) ? 2 : 4;      // independent FFMA2 chains
             float2 lin[NL];
 #pragma unroll
             for (int i = 0; i < NL; ++i) lin[i] = make_float2(0.0f, 0.0f);
@@ -274,9 +280,9 @@ k_b1_mma(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtens
                         tc_fence_before();
                         mbar_arrive(bar_e + 8 * ab);         // the whole accumulator is in registers
                     }
-                    if (sz == 32) bm_fold<ACT, HALF, NL, 32>(v + boff, wh + (off >> 1), lin, ab4);
-                    else if (sz == 16) bm_fold<ACT, HALF, NL, 16>(v + boff, wh + (off >> 1), lin, ab4);
-                    else bm_fold<ACT, HALF, NL, 8>(v + boff, wh + (off >> 1), lin, ab4);
+                    if (sz == 32) bm_fold<ACT, VAR, NL, 32>(v + boff, wh + (off >> 1), lin, ab4);
+                    else if (sz == 16) bm_fold<ACT, VAR, NL, 16>(v + boff, wh + (off >> 1), lin, ab4);
+                    else bm_fold<ACT, VAR, NL, 8>(v + boff, wh + (off >> 1), lin, ab4);
                     if (i == NC - 1) {                       // a datapoint is complete
                         float pre = (lin[0].x + lin[0].y) + (lin[1].x + lin[1].y);
                         if (NL == 4) pre += (lin[NL - 2].x + lin[NL - 2].y) + (lin[NL - 1].x + lin[NL - 1].y);
