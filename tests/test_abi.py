@@ -76,3 +76,36 @@ def test_host_mirror_shapes(ssi):
         ssi.sub_inference(m, dl, w, np.zeros((682, 3), np.float32), alg="bogus")
     with pytest.raises(ValueError):
         ssi.subspace_inference(m, None, dl, None, method="nope")
+
+
+def test_training_step_host_restatement(ssi):
+    """The host restatement of `gradient + Flux.update!` that the device trainer is checked against (tests/test_gpu_train.py):
+    the loader's index batches are what its iteration slices with, a Descent step is W -= eta * dL/dW with L = mse, and ADAM's
+    first step moves every weight by eta * sign(g) (Flux 0.11 rule with bias correction)."""
+    import ssi_oracle as orc
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((4, 11)).astype(np.float32)
+    Y = rng.standard_normal((2, 11)).astype(np.float32)
+    dl = ssi.DataLoader(X, Y, batchsize=4, shuffle=True, rng=np.random.default_rng(9))
+    dl2 = ssi.DataLoader(X, Y, batchsize=4, shuffle=True, rng=np.random.default_rng(9))
+    for sel, (xb, yb) in zip(dl.index_batches(), dl2):
+        np.testing.assert_array_equal(xb, X[:, sel])
+        np.testing.assert_array_equal(yb, Y[:, sel])
+    # single linear layer: dL/dW = 2/(O nb) (W x + b - y) x'
+    m = ssi.Chain(ssi.Dense(4, 2, rng=rng))
+    w0 = ssi.extract_params(m).astype(np.float64)
+    W0, b0 = w0[:8].reshape(4, 2).T, w0[8:]
+    cost = lambda mm, x, y: ssi.mse(mm(x), y)
+    loss = ssi.train_step(m, cost, ssi.Descent(0.1), X, Y)
+    resid = W0 @ X + b0[:, None] - Y
+    np.testing.assert_allclose(loss, np.mean(resid ** 2), rtol=1e-5)
+    gW, gb = 2.0 / resid.size * resid @ X.T, 2.0 / resid.size * resid.sum(axis=1)
+    w1 = ssi.extract_params(m)
+    np.testing.assert_allclose(w1[:8].reshape(4, 2).T, W0 - 0.1 * gW, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(w1[8:], b0 - 0.1 * gb, rtol=1e-5, atol=1e-6)
+    m2 = ssi.Chain(ssi.Dense(4, 2, rng=rng))
+    before = ssi.extract_params(m2).copy()
+    ssi.train_step(m2, cost, ssi.ADAM(0.01), X, Y)
+    step = ssi.extract_params(m2) - before
+    np.testing.assert_allclose(np.abs(step), 0.01, rtol=1e-3)
+    assert orc.n_params(m2.dims) == step.shape[0]
