@@ -4,11 +4,12 @@
 // The first layer is affine in z (see ssi_basis.cu): with z augmented by a constant 1,
 //     pre[s, e] = sum_{m <= M} zaug[s, m] * basesT[e, m],     e = (datapoint i, hidden unit j) = i*Hp + j,   K = 16 or 32,
 // is a GEMM whose M dimension is the SAMPLES.  A CTA owns 256 samples (two 128-row A operands resident in shared memory
-// for the whole kernel) and walks tiles of 128 activations (128/Hp datapoints): the basis tile is fetched once by TMA and
-// multiplied with both sample groups (three-way BF16 split of both operands, six products, FP32 accumulate in TMEM, two 128-column accumulators
-// per group so that the MMAs of tile t+1 run under the epilogue of tile t).  The epilogue never stores the hidden layer: lane = sample, so each thread keeps ITS sample's second-layer
-// weights in registers, applies the activation to its 256 TMEM columns, folds them into Hp-long dot products (the output
-// layer), subtracts y and accumulates the squared error in FP64.  One FP64 partial per (sample, CTA) leaves the kernel.
+// for the whole kernel) and walks tiles of 2 or 4 datapoints (NT = 2 Hp or 4 x 32 activations <= 128): the basis tile is
+// fetched once by TMA and multiplied with both sample groups (three-way BF16 split of both operands, six products, FP32
+// accumulate in TMEM, two 128-column accumulators per group so that the MMAs of tile t+1 run under the epilogue of tile t).
+// The epilogue never stores the hidden layer: lane = sample, so each thread keeps ITS sample's second-layer weights in
+// registers, applies the activation to its TMEM columns, folds them into Hp-long dot products (the output layer), subtracts y
+// and accumulates the squared error in an error-free two-float sum.  One FP64 partial per (sample, part) leaves the kernel.
 //
 // Roles: warp 0 TMA producer, warps 1 and 10 MMA issuers (one per sample group; warp 1 also allocates TMEM), warps 2-9 epilogue
 // (warp w: TMEM lane quarter w % 4 of sample group (w - 2) / 4).  Bound: the epilogue (register-file bandwidth of the dot products with per-sample weights).
