@@ -188,10 +188,12 @@ def predictive(in_model, W_swa, P, z_samples, inp, *, return_trajectories: bool 
 def subspace_inference(model, cost, data, opt, *, σ_z: float = 1.0, σ_m: float = 1.0, σ_p: float = 1.0,
                        itr: int = 1000, T: int = 25, c: int = 1, M: int = 20, print_freq: int = 1, alg="rwmh",
                        backend="forwarddiff", method="subspace", **kw):
-    """construct -> sample -> (chn, lp, W_swa)   (src/space_inference.jl:33-54)."""
+    """construct -> sample -> (chn, lp, W_swa)   (src/space_inference.jl:33-54).  device_train=True (not in the reference) keeps
+    the training step of the construction on the device as well, see subspace_construction."""
+    device_train = bool(kw.pop("device_train", False))
     if _sym(method) == "subspace":
         W_swa, P = subspace_construction(model, cost, data, opt, T=T, c=c, M=M, print_freq=print_freq,
-                                         device=kw.get("device", 0))
+                                         device=kw.get("device", 0), device_train=device_train)
     elif _sym(method) == "diffusion":
         raise NotImplementedError("diffusion_subspace is not available on the device path")
     else:

@@ -87,3 +87,18 @@ def test_device_training_rejects_other_costs(ssi):
         ssi.subspace_construction(m, l1, ssi.DataLoader(X, Y, batchsize=10), ssi.Descent(0.1), T=2, c=1, M=2, device_train=True)
     with pytest.raises(TypeError):
         ssi.subspace_construction(m, l1, ssi.DataLoader(X, Y, batchsize=10), object(), T=2, c=1, M=2, device_train=True)
+
+
+def test_whole_pipeline_on_the_device(ssi, capsys):
+    """subspace_inference(..., device_train=True): training, snapshots, construction and sampling without the weights
+    leaving the device between the steps; every returned lp is the oracle density of the returned weight vector."""
+    rng = np.random.default_rng(21)
+    X = rng.random((10, 100)).astype(np.float32)
+    Y = rng.random((2, 100)).astype(np.float32)
+    data = ssi.DataLoader(X, Y, batchsize=20, shuffle=True, rng=np.random.default_rng(1))
+    m = _model(ssi, (10, 20, 20, 2), (0, 0, 0), rng)
+    chn, lp, W_swa = ssi.subspace_inference(m, lambda mm, x, y: ssi.mse(mm(x), y), data, ssi.ADAM(0.01), itr=8, T=6, c=1, M=3,
+                                            seed=2, device_train=True)
+    assert len(chn) == 8 and W_swa.shape == (682,) and "Traing loss" in capsys.readouterr().out
+    for w, l in zip(chn, lp):
+        np.testing.assert_allclose(l, orc.gaussian_loglik(orc.forward(w, m.dims, m.acts, X), Y, 1.0), rtol=1e-5)
