@@ -332,50 +332,58 @@ __global__ void k_pack_v(const double* __restrict__ V, const int* __restrict__ o
 }
 
 // P = A V_M with V_M in the constant bank: the FMAs take V as a uniform operand, no shared-memory traffic.
-// Four consecutive rows per thread (one 16-byte load per column: a warp reads 512 contiguous bytes of each column).
-template <int MP>
+// R consecutive rows per thread (one 4R-byte load per column: a warp reads 128 R contiguous bytes of each column); R = 4 while
+// the R x MP accumulators fit the register file (MP <= 20), 2 up to MP = 32, 1 beyond (4 x 64 accumulators spilled 15 KB).
+template <int MP, int R>
 __global__ void __launch_bounds__(128)
 k_form_p_const(const float* __restrict__ A, long long n, long long ld, int K, int M, float* __restrict__ P) {
-    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * R;
     if (i >= n) return;
-    float acc[4][MP];
+    float acc[R][MP];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int j = 0; j < MP; ++j) acc[r][j] = 0.0f;
-    if (i + 3 < n) {
-        // 10 independent 16-byte loads in flight per thread (latency-bound otherwise: ncu showed 48 % DRAM, 24 % occupancy)
+    if (i + R - 1 < n) {
+        // 10 independent loads in flight per thread (latency-bound otherwise: ncu showed 48 % DRAM, 24 % occupancy)
 #pragma unroll 10
         for (int k = 0; k < K; ++k) {
-            const float4 d = __ldcs(reinterpret_cast<const float4*>(A + i + (long long)k * ld));
+            float d[R];
+            if (R == 4) {
+                const float4 d4 = __ldcs(reinterpret_cast<const float4*>(A + i + (long long)k * ld));
+                d[0] = d4.x; d[1 % R] = d4.y; d[2 % R] = d4.z; d[3 % R] = d4.w;
+            } else if (R == 2) {
+                const float2 d2 = __ldcs(reinterpret_cast<const float2*>(A + i + (long long)k * ld));
+                d[0] = d2.x; d[1 % R] = d2.y;
+            } else {
+                d[0] = __ldcs(A + i + (long long)k * ld);
+            }
 #pragma unroll
             for (int j = 0; j < MP; ++j) {
                 const float v = c_formp_v[k * MP + j];
-                acc[0][j] = fmaf(d.x, v, acc[0][j]);
-                acc[1][j] = fmaf(d.y, v, acc[1][j]);
-                acc[2][j] = fmaf(d.z, v, acc[2][j]);
-                acc[3][j] = fmaf(d.w, v, acc[3][j]);
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r][j] = fmaf(d[r], v, acc[r][j]);
             }
         }
     } else {
         for (int k = 0; k < K; ++k)
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < R; ++r)
                 if (i + r < n) {
                     const float d = A[i + r + (long long)k * ld];
 #pragma unroll
                     for (int j = 0; j < MP; ++j) acc[r][j] = fmaf(d, c_formp_v[k * MP + j], acc[r][j]);
                 }
     }
-    const bool vec = (i + 3 < n) && ((n & 3) == 0);      // columns of P are n apart: 16-byte stores need n % 4 == 0
+    const bool vec = (R == 4) && (i + 3 < n) && ((n & 3) == 0);      // columns of P are n apart: 16-byte stores need n % 4 == 0
 #pragma unroll
     for (int j = 0; j < MP; ++j) {
         if (j >= M) break;
         if (vec) {
-            __stcs(reinterpret_cast<float4*>(P + i + (long long)j * n), make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]));
+            __stcs(reinterpret_cast<float4*>(P + i + (long long)j * n), make_float4(acc[0][j], acc[1 % R][j], acc[2 % R][j], acc[3 % R][j]));
         } else {
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < R; ++r)
                 if (i + r < n) P[i + r + (long long)j * n] = acc[r][j];
         }
     }
@@ -428,7 +436,8 @@ static int launch_form_p(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, i
         k_pack_v<<<(K * MP + 255) / 256, 256, 0, ctx->stream>>>(dV, dOrder, K, M, MP, stage);
         SSI_LAUNCH_CHECK(ctx);
         SSI_CUDA(ctx, cudaMemcpyToSymbolAsync(c_formp_v, stage, sizeof(float) * (size_t)K * MP, 0, cudaMemcpyDeviceToDevice, ctx->stream));
-        k_form_p_const<MP><<<(unsigned)((n + 511) / 512), 128, 0, ctx->stream>>>(dA, n, ld, K, M, dP);
+        constexpr int R = MP <= 20 ? 4 : (MP <= 32 ? 2 : 1);
+        k_form_p_const<MP, R><<<(unsigned)((n + 128 * R - 1) / (128 * R)), 128, 0, ctx->stream>>>(dA, n, ld, K, M, dP);
         SSI_LAUNCH_CHECK(ctx);
         return SSI_OK;
     }

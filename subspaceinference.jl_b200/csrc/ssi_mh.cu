@@ -120,8 +120,6 @@ int ssi_mh_device(ssi_ctx* ctx, int kind, int64_t C, int64_t S, uint64_t seed, i
     const unsigned g_prop = (unsigned)((C * nblk + 255) / 256);
     const unsigned g_acc = (unsigned)((C + 255) / 256);
     double units = 0, flops = 0;
-    int64_t launches0 = ctx->stats.kernel_launches;
-    (void)launches0;
 
     for (int64_t t = 0; t < S; ++t) {
         if (t == 0 && d_z0) {

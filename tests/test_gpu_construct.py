@@ -31,6 +31,29 @@ def test_golden_construction(ssi, engine):
     np.testing.assert_allclose(s[:3], g["s"][:3], rtol=1e-5)
 
 
+@pytest.mark.parametrize("n,K,M", [(3001, 64, 30), (2050, 70, 40), (1203, 90, 64)])
+def test_wide_subspaces(ssi, engine, n, K, M):
+    """M > 20: k_form_p_const runs with 2 rows (M <= 32) or 1 row (beyond) per thread.  M strong directions with a 5 % ladder
+    of scales, so that every wanted singular vector is well separated."""
+    rng = np.random.default_rng(n + K + M)
+    w = rng.standard_normal(n) * 0.1
+    dirs = rng.standard_normal((M, n)) * (0.95 ** np.arange(M))[:, None]
+    snaps, ns = [], []
+    for k in range(K):
+        w = w + dirs.T @ rng.standard_normal(M) * 0.05 + 1e-5 * rng.standard_normal(n)
+        snaps.append(w.astype(np.float32))
+        ns.append(float(k + 1))
+    W_swa, P, s = _run(engine, snaps, ns, M)
+    W_ref, P_ref, s_ref, A = orc.construct_from_snapshots(snaps, ns, M)
+    assert _rel(W_swa, W_ref) < 1e-4
+    np.testing.assert_allclose(s[:M], s_ref[:M], rtol=1e-4)
+    # rank-M projector (insensitive to rotations inside clusters of close singular values), then column by column
+    x = rng.standard_normal(n)
+    Pd = P.astype(np.float64)
+    assert _rel(Pd @ (Pd.T @ x), P_ref @ (P_ref.T @ x)) < 2e-4
+    assert _rel(orc.align_signs(Pd, P_ref), P_ref) < 2e-3
+
+
 @pytest.mark.parametrize("n,K,M", [(682, 15, 3), (1001, 40, 5), (4096, 100, 20), (37, 64, 4), (50000, 33, 20)])
 def test_random_snapshots_vs_oracle(ssi, engine, n, K, M):
     rng = np.random.default_rng(n * 1000 + K)
