@@ -15,8 +15,8 @@
 //     into per-CTA FP64 partials (each thread owns its elements: plain load-add-store, no atomics) and
 //     reset; a final kernel sums the per-CTA partials in fixed order and symmetrises.
 //
-// Roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-5 converters,
-// warps 6-9 drain.  TMEM: 2 x (HH | HL) x 128 columns = 512.  Shared memory: 8 raw FP32 tiles (TMA) + 2 (H | L) operand pairs.
+// Roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-5 converters (one tile each),
+// warps 6-9 drain.  TMEM: 2 x (HH | HL) x 128 columns = 512.  Shared memory: 6 slots of (H | L) tile pairs.
 #include "ssi_common.cuh"
 #include "ssi_ptx.cuh"
 
@@ -24,15 +24,16 @@
 
 #define GT_ROWS 32                   // rows of A per tile (= 128 bytes of FP32 = one swizzle row)
 #define GT_TILE_BYTES (128 * 128)    // [128 columns of A][32 rows] FP32
-// Two rings.  RAW: TMA destinations (FP32 tiles as they sit in HBM), deep, because a tile gathers one 128-byte segment
-// from each of the K columns (K different DRAM pages) and its latency tail is long; a slot is free again as soon as
-// the converter warps have read it.  OPS: (H | L) operand pairs for the tensor core, shallow.
-#define GT_RAW_STAGES 8
-#define GT_OP_STAGES 2
+// One ring of (H | L) slot pairs.  TMA lands the FP32 tile in the first half of a slot; ONE converter warp per tile (four
+// tiles are being split at any time) overwrites it with H in place and writes L behind it; the slot returns to the producer
+// when its MMAs have retired.  Deep, because a tile gathers one 128-byte segment from each of the K columns (K different
+// DRAM pages).  (An earlier version had all four converter warps share each tile and separate raw / operand rings: the same
+// 1.2 ms at n = 10M, K = 100 -- neither the converters' latency chain nor the FP32 chunk length is what holds the kernel at
+// 52 % of the HBM peak; tensor pipe, shared memory and DRAM all sit near half.)
+#define GT_SLOTS 6
 #define GT_THREADS 320
-#define GT_OFF_OPS (GT_RAW_STAGES * GT_TILE_BYTES)
-#define GT_OFF_BAR (GT_OFF_OPS + GT_OP_STAGES * 2 * GT_TILE_BYTES)
-#define GT_NBAR (2 * GT_RAW_STAGES + 2 * GT_OP_STAGES + 4)
+#define GT_OFF_BAR (GT_SLOTS * 2 * GT_TILE_BYTES)
+#define GT_NBAR (3 * GT_SLOTS + 4)
 #define GT_SMEM_TOTAL (GT_OFF_BAR + GT_NBAR * 8 + 16)
 
 struct gram_tc_params {
@@ -47,19 +48,17 @@ struct gram_tc_params {
 __global__ void __launch_bounds__(GT_THREADS, 1)
 k_gram_tc(const __grid_constant__ CUtensorMap tmA, const gram_tc_params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    // barriers: raw_full[R] raw_empty[R] op_full[O] op_empty[O] tfull[2] tempty[2]
+    // barriers: raw_full[S] op_full[S] op_empty[S] tfull[2] tempty[2]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + GT_OFF_BAR);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + GT_NBAR);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bar_rfull = smem_u32(s_bar), bar_rempty = bar_rfull + 8 * GT_RAW_STAGES;
-    const uint32_t bar_ofull = bar_rempty + 8 * GT_RAW_STAGES, bar_oempty = bar_ofull + 8 * GT_OP_STAGES;
-    const uint32_t bar_tfull = bar_oempty + 8 * GT_OP_STAGES, bar_tempty = bar_tfull + 16;
+    const uint32_t bar_rfull = smem_u32(s_bar), bar_ofull = bar_rfull + 8 * GT_SLOTS, bar_oempty = bar_ofull + 8 * GT_SLOTS;
+    const uint32_t bar_tfull = bar_oempty + 8 * GT_SLOTS, bar_tempty = bar_tfull + 16;
 
     if (threadIdx.x == 0) {
         if (smem_base & 1023u) { printf("ssi_gram_tc: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
-        for (int s = 0; s < GT_RAW_STAGES; ++s) { mbar_init(bar_rfull + 8 * s, 1); mbar_init(bar_rempty + 8 * s, 128); }
-        for (int s = 0; s < GT_OP_STAGES; ++s) { mbar_init(bar_ofull + 8 * s, 128); mbar_init(bar_oempty + 8 * s, 1); }
+        for (int s = 0; s < GT_SLOTS; ++s) { mbar_init(bar_rfull + 8 * s, 1); mbar_init(bar_ofull + 8 * s, 32); mbar_init(bar_oempty + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 128); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
@@ -81,12 +80,12 @@ k_gram_tc(const __grid_constant__ CUtensorMap tmA, const gram_tc_params p) {
             int stage = 0;
             uint32_t phase = 0;
             for (long long t = t_begin; t < t_end; ++t) {
-                mbar_wait(bar_rempty + 8 * stage, phase ^ 1);
+                mbar_wait(bar_oempty + 8 * stage, phase ^ 1);          // the MMAs that read this slot have retired
                 mbar_expect_tx(bar_rfull + 8 * stage, GT_TILE_BYTES);
                 // A is streamed exactly once: do not let it evict the FP64 partials from L2.  (Tried and dropped, no
                 // gain: issuing several row blocks back to back, or by 32-column groups with the row blocks innermost.)
-                tma_load_2d_hint(smem_base + stage * GT_TILE_BYTES, &tmA, bar_rfull + 8 * stage, (int)(t * GT_ROWS), 0, TC_EVICT_FIRST);
-                if (++stage == GT_RAW_STAGES) { stage = 0; phase ^= 1; }
+                tma_load_2d_hint(smem_base + stage * 2 * GT_TILE_BYTES, &tmA, bar_rfull + 8 * stage, (int)(t * GT_ROWS), 0, TC_EVICT_FIRST);
+                if (++stage == GT_SLOTS) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -108,54 +107,50 @@ k_gram_tc(const __grid_constant__ CUtensorMap tmA, const gram_tc_params p) {
                 for (bool first = true; t < c_end; ++t, first = false) {
                     mbar_wait(bar_ofull + 8 * stage, phase);            // H and L tiles are ready
                     tc_fence_after();
-                    const uint64_t dh = umma_desc_sw128(smem_base + GT_OFF_OPS + stage * 2 * GT_TILE_BYTES);
+                    const uint64_t dh = umma_desc_sw128(smem_base + stage * 2 * GT_TILE_BYTES);
 #pragma unroll
                     for (int k = 0; k < GT_ROWS / 8; ++k) {
                         const uint64_t ko = (uint64_t)(k * 32 >> 4);    // 8 TF32 = 32 bytes per k-step
                         umma_tf32(d_acc, dh + ko, dh + ko, idesc, !(first && k == 0));
                     }
                     umma_commit(bar_oempty + 8 * stage);
-                    if (++stage == GT_OP_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == GT_SLOTS) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(bar_tfull + 8 * ab);
             }
         }
     } else if (warp < 6) {
-        // ================= converters: split the FP32 tile into TF32 hi / lo =================
-        const int ct = threadIdx.x - 64;          // 0..127
-        int rs = 0, os = 0;
-        uint32_t rphase = 0, ophase = 0;
-        for (long long t = 0; t < my_tiles; ++t) {
-            mbar_wait(bar_rfull + 8 * rs, rphase);
-            const float4* X = reinterpret_cast<const float4*>(smem + rs * GT_TILE_BYTES);
-            float4 x[GT_TILE_BYTES / 16 / 128];
-#pragma unroll
-            for (int r = 0; r < GT_TILE_BYTES / 16 / 128; ++r) x[r] = X[ct + r * 128];
-
-            mbar_wait(bar_oempty + 8 * os, ophase ^ 1);              // the MMAs that read this operand slot have retired
-            float4* H = reinterpret_cast<float4*>(smem + GT_OFF_OPS + os * 2 * GT_TILE_BYTES);
+        // ================= converters: split the FP32 tile into TF32 hi / lo, one warp per tile =================
+        const int cw = warp - 2;                  // 0..3: this warp takes tiles cw, cw + 4, ...
+        for (long long t = cw; t < my_tiles; t += 4) {
+            const int slot = (int)(t % GT_SLOTS);
+            const uint32_t ph = (uint32_t)((t / GT_SLOTS) & 1);
+            mbar_wait(bar_rfull + 8 * slot, ph);
+            float4* H = reinterpret_cast<float4*>(smem + (size_t)slot * 2 * GT_TILE_BYTES);
             float4* L = H + GT_TILE_BYTES / 16;
+            // the split is element-wise at identical offsets, so it is independent of the 128-byte swizzle
+#pragma unroll 1
+            for (int r0 = 0; r0 < GT_TILE_BYTES / 16 / 32; r0 += 8) {
+                float4 x[8];
 #pragma unroll
-            for (int r = 0; r < GT_TILE_BYTES / 16 / 128; ++r) {
-                // the split is element-wise at identical offsets, so it is independent of the 128-byte swizzle
-                float4 h, l;
-                h.x = __uint_as_float(__float_as_uint(x[r].x) & 0xFFFFE000u);
-                h.y = __uint_as_float(__float_as_uint(x[r].y) & 0xFFFFE000u);
-                h.z = __uint_as_float(__float_as_uint(x[r].z) & 0xFFFFE000u);
-                h.w = __uint_as_float(__float_as_uint(x[r].w) & 0xFFFFE000u);
-                l.x = __uint_as_float(__float_as_uint(x[r].x - h.x) & 0xFFFFE000u);
-                l.y = __uint_as_float(__float_as_uint(x[r].y - h.y) & 0xFFFFE000u);
-                l.z = __uint_as_float(__float_as_uint(x[r].z - h.z) & 0xFFFFE000u);
-                l.w = __uint_as_float(__float_as_uint(x[r].w - h.w) & 0xFFFFE000u);
-                H[ct + r * 128] = h;
-                L[ct + r * 128] = l;
+                for (int r = 0; r < 8; ++r) x[r] = H[lane + (r0 + r) * 32];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(x[r].x) & 0xFFFFE000u);
+                    h.y = __uint_as_float(__float_as_uint(x[r].y) & 0xFFFFE000u);
+                    h.z = __uint_as_float(__float_as_uint(x[r].z) & 0xFFFFE000u);
+                    h.w = __uint_as_float(__float_as_uint(x[r].w) & 0xFFFFE000u);
+                    l.x = __uint_as_float(__float_as_uint(x[r].x - h.x) & 0xFFFFE000u);
+                    l.y = __uint_as_float(__float_as_uint(x[r].y - h.y) & 0xFFFFE000u);
+                    l.z = __uint_as_float(__float_as_uint(x[r].z - h.z) & 0xFFFFE000u);
+                    l.w = __uint_as_float(__float_as_uint(x[r].w - h.w) & 0xFFFFE000u);
+                    H[lane + (r0 + r) * 32] = h;
+                    L[lane + (r0 + r) * 32] = l;
+                }
             }
-            // the raw slot has been read (its values were consumed above): TMA may refill it, long before the MMAs run
-            mbar_arrive(bar_rempty + 8 * rs);
-            if (++rs == GT_RAW_STAGES) { rs = 0; rphase ^= 1; }
             fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core (async proxy)
-            mbar_arrive(bar_ofull + 8 * os);
-            if (++os == GT_OP_STAGES) { os = 0; ophase ^= 1; }
+            mbar_arrive(bar_ofull + 8 * slot);
         }
     } else {
         // ================= drain: TMEM chunk sums -> FP64 per-CTA partials =================
