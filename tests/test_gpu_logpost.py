@@ -206,6 +206,8 @@ def test_gradient_vs_oracle(ssi, engine, dims, acts, N, M, B):
     ((7, 40, 1), (1, 0), 4001, 1, 2500),       # M + 1 = 2: one packed K slab; 10 blocks of samples (several parts per CTA)
     ((9, 64, 1), (1, 1), 777, 7, 300),         # M + 1 = 8: three packed slabs, all 48 columns used; relu output
     ((3, 20, 1), (2, 3), 150, 4, 40),          # two packed slabs, Hp = 32, tanh hidden, sigmoid output
+    ((11, 44, 1), (1, 0), 501, 9, 130),        # Hp = 48 (TMEM chunks 32 + 16), M + 1 = 10: three-way split as six MMAs, K = 16
+    ((8, 37, 1), (3, 0), 77, 2, 9),            # Hp = 40 (chunks 32 + 8), odd number of datapoints: half-empty last tile
 ])
 def test_basis_path_on_tensor_cores_vs_oracle(ssi, engine, dims, acts, N, M, B):
     """BASIS path, tensor-core kernel (samples along the MMA M dimension) and CUDA-core kernel: both within 1e-5 of the
