@@ -208,6 +208,8 @@ int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
         ctx->stats.dominant_ms = 0; ctx->stats.dominant_launches = 0; ctx->kt_used = 0;
         return SSI_OK;
     }
+    if (!strcmp(key, "tc_alast")) { ctx->opt_tc_alast = value != 0; return SSI_OK; }
+    if (!strcmp(key, "tc_nokrev")) { ctx->opt_tc_nokrev = value != 0; return SSI_OK; }
     if (!strcmp(key, "tc_cluster")) { ctx->opt_tc_cluster = value != 0; return SSI_OK; }
     if (!strcmp(key, "b1_simt")) { ctx->opt_b1_simt = value != 0; return SSI_OK; }
     if (!strcmp(key, "bm_nopack")) { ctx->opt_bm_nopack = value != 0; ssi_bm_invalidate(ctx); return SSI_OK; }

@@ -51,6 +51,8 @@ struct ssi_ctx {
     int opt_group = 0;
     int opt_tc_nofuse = 0;    // debugging / A-B: compute the output layer as its own GEMM
     int opt_tc_noorder = 0;
+    int opt_tc_alast = 1;     // evict-first hint on the last read of a row block's activations (A-B: 0)
+    int opt_tc_nokrev = 0;    // A-B: every feature tile reads the k-blocks in ascending order
     int opt_tc_cluster = 0;   // A-B: GEMM layers with per-sample activations as 2-CTA clusters sharing the weight tiles by TMA multicast
     int opt_bm_nopack = 0, opt_bm_variant = 1;     // A-B inside k_b1_mma: unpacked operands; ReLU epilogue variant
     int opt_b1_simt = 0;       // A-B: BASIS path on CUDA cores (k_logpost_basis1h) instead of the tensor-core kernel (k_b1_mma)

@@ -41,6 +41,8 @@ typedef __nv_bfloat16 bf16;
 // ---------------------------------------------------------------------------------------
 struct tc_params {
     int N, G, m_tiles, n_tiles, k_blocks, BN, width, a_shared, act;
+    int a_last_first;       // A loads of the last feature tile carry the evict-first hint
+    int k_rev;              // odd feature tiles read the k-blocks in descending order (L2 reuse of the A row block)
     int a_il;               // A operand planes interleaved per k-block: row = [kb][hi 64 | lo 64] (the basis layer's output)
     int stages, stage_bytes;
     int mt_block;           // > 0: work order (mt block, sample, mt in block) so that concurrently running CTAs share A tiles
@@ -162,17 +164,22 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                         const uint32_t full = bar_full + 8 * stage;
                         const uint32_t sA = smem_base + stage * p.stage_bytes;
                         mbar_expect_tx(full, 2 * a_bytes + 2 * b_bytes);
-                        const int ka = p.a_il ? 2 * kb * TC_BK : kb * TC_BK;
-                        tma_load_3d_hint(sA, &tmAh, full, ka, mt * TC_BM, p.a_shared ? 0 : g, pol_a);
-                        tma_load_3d_hint(sA + a_bytes, &tmAl, full, p.a_il ? ka + TC_BK : ka, mt * TC_BM, p.a_shared ? 0 : g, pol_a);
+                        // odd feature tiles walk the k-blocks backwards: the A k-blocks read last for tile nt are the first ones tile
+                        // nt + 1 wants, which is what an LRU-like L2 still holds when a round of A tiles slightly exceeds it
+                        const int kbe = (p.k_rev && (nt & 1)) ? p.k_blocks - 1 - kb : kb;
+                        const int ka = p.a_il ? 2 * kbe * TC_BK : kbe * TC_BK;
+                        // the last feature tile is the last reader of this row block's activations: let them go first
+                        const uint64_t pa = (p.a_last_first && !p.a_shared && nt == p.n_tiles - 1) ? TC_EVICT_FIRST : pol_a;
+                        tma_load_3d_hint(sA, &tmAh, full, ka, mt * TC_BM, p.a_shared ? 0 : g, pa);
+                        tma_load_3d_hint(sA + a_bytes, &tmAl, full, p.a_il ? ka + TC_BK : ka, mt * TC_BM, p.a_shared ? 0 : g, pa);
                         if (CL) {
                             // this CTA's half of the rows of each weight plane, delivered to both CTAs (the maps' box is BN/2 rows)
                             const uint32_t ho = crank * (b_bytes / 2);
-                            tma_load_3d_multicast_hint(sA + 2 * a_bytes + ho, &tmBh, full, kb * TC_BK, nt * BN + (int)crank * (BN / 2), g, 3, TC_EVICT_LAST);
-                            tma_load_3d_multicast_hint(sA + 2 * a_bytes + b_bytes + ho, &tmBl, full, kb * TC_BK, nt * BN + (int)crank * (BN / 2), g, 3, TC_EVICT_LAST);
+                            tma_load_3d_multicast_hint(sA + 2 * a_bytes + ho, &tmBh, full, kbe * TC_BK, nt * BN + (int)crank * (BN / 2), g, 3, TC_EVICT_LAST);
+                            tma_load_3d_multicast_hint(sA + 2 * a_bytes + b_bytes + ho, &tmBl, full, kbe * TC_BK, nt * BN + (int)crank * (BN / 2), g, 3, TC_EVICT_LAST);
                         } else {
-                            tma_load_3d_hint(sA + 2 * a_bytes, &tmBh, full, kb * TC_BK, nt * BN, g, TC_EVICT_LAST);
-                            tma_load_3d_hint(sA + 2 * a_bytes + b_bytes, &tmBl, full, kb * TC_BK, nt * BN, g, TC_EVICT_LAST);
+                            tma_load_3d_hint(sA + 2 * a_bytes, &tmBh, full, kbe * TC_BK, nt * BN, g, TC_EVICT_LAST);
+                            tma_load_3d_hint(sA + 2 * a_bytes + b_bytes, &tmBl, full, kbe * TC_BK, nt * BN, g, TC_EVICT_LAST);
                         }
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
@@ -1163,6 +1170,8 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
             p.k_blocks = s->Kp[l] / TC_BK;
             p.a_shared = (l == 0);
             p.a_il = (l == 1 && s->basis) ? 1 : 0;
+            p.k_rev = (!p.a_shared && !ctx->opt_tc_nokrev) ? 1 : 0;
+            p.a_last_first = ctx->opt_tc_alast;
             p.act = m.act[l];
             p.stage_bytes = 2 * TC_BM * TC_BK * 2 + 2 * p.BN * TC_BK * 2;
             p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
