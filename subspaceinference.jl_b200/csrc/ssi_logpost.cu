@@ -254,14 +254,18 @@ __global__ void k_finalize(const finalize_args_t a, const double* __restrict__ s
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int M = a.M, ld = M + 1;
-    // |W_swa + P z|^2 = w'w + 2 (P'w)'z + z'(P'P)z, from the Gram of [P | W_swa]
-    double w2 = G[M * ld + M], z2 = 0.0;
-    for (int i = 0; i < M; ++i) {
-        const double zi = (double)Z[i + b * M];
-        z2 += zi * zi;
-        double row = 0.0;
-        for (int j = 0; j < M; ++j) row += G[i * ld + j] * (double)Z[j + b * M];
-        w2 += zi * (row + 2.0 * G[i * ld + M]);
+    // |W_swa + P z|^2 = w'w + 2 (P'w)'z + z'(P'P)z, from the Gram of [P | W_swa]; skipped when only the likelihood is asked
+    // for (the reference's density as executed): the M^2 FP64 loop was most of this kernel's time in the MH loop
+    double w2 = 0.0, z2 = 0.0;
+    if (terms || (a.mask & (SSI_TERM_PRIOR_W | SSI_TERM_PRIOR_Z))) {
+        w2 = G[M * ld + M];
+        for (int i = 0; i < M; ++i) {
+            const double zi = (double)Z[i + b * M];
+            z2 += zi * zi;
+            double row = 0.0;
+            for (int j = 0; j < M; ++j) row += G[i * ld + j] * (double)Z[j + b * M];
+            w2 += zi * (row + 2.0 * G[i * ld + M]);
+        }
     }
     const double ll = a.c_ll - sse[b] * a.inv2sm2;
     const double pw = a.c_w - w2 * a.inv2sp2;
