@@ -100,7 +100,7 @@ const char* ssi_last_error(const ssi_ctx* ctx);
 int  ssi_set_stream(ssi_ctx* ctx, void* cuda_stream);
 int  ssi_sync(ssi_ctx* ctx);
 /* keys: "path" (SSI_PATH_*), "group" (samples per wave on the tensor path), and A/B switches used by the
- * tests: "tc_nobasis", "tc_nofuse", "tc_noorder", "tc_simt_basis", "tc_cluster", "tc_nokrev", "tc_alast", "b1_simt", "bm_nopack", "bm_variant", "gram_fp64", "gram_chunk" (see DESIGN.md); "time_dominant" (0/1) brackets every
+ * tests: "tc_nobasis", "tc_nofuse", "tc_noorder", "tc_simt_basis", "tc_cluster", "tc_nokrev", "tc_alast", "tc_k32", "b1_simt", "bm_nopack", "bm_variant", "gram_fp64", "gram_chunk" (see DESIGN.md); "time_dominant" (0/1) brackets every
  * launch of the path's dominant kernel with CUDA events (ssi_stats_t.dominant_ms) */
 int  ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value);
 int  ssi_stats(const ssi_ctx* ctx, ssi_stats_t* out);

@@ -208,6 +208,7 @@ int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
         ctx->stats.dominant_ms = 0; ctx->stats.dominant_launches = 0; ctx->kt_used = 0;
         return SSI_OK;
     }
+    if (!strcmp(key, "tc_k32")) { ctx->opt_tc_k32 = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "tc_alast")) { ctx->opt_tc_alast = value != 0; return SSI_OK; }
     if (!strcmp(key, "tc_nokrev")) { ctx->opt_tc_nokrev = value != 0; return SSI_OK; }
     if (!strcmp(key, "tc_cluster")) { ctx->opt_tc_cluster = value != 0; return SSI_OK; }

@@ -51,6 +51,7 @@ struct ssi_ctx {
     int opt_group = 0;
     int opt_tc_nofuse = 0;    // debugging / A-B: compute the output layer as its own GEMM
     int opt_tc_noorder = 0;
+    int opt_tc_k32 = 0;       // A-B: K-major bases always 32 columns wide
     int opt_tc_alast = 1;     // evict-first hint on the last read of a row block's activations (A-B: 0)
     int opt_tc_nokrev = 0;    // A-B: every feature tile reads the k-blocks in ascending order
     int opt_tc_cluster = 0;   // A-B: GEMM layers with per-sample activations as 2-CTA clusters sharing the weight tiles by TMA multicast

@@ -781,9 +781,11 @@ __global__ void k_tc_pack_zaug(const float* __restrict__ Z, int M, int G, bf16* 
     zl[t] = lo;
 }
 
-// basesT[e][m] (K-major, 32 BF16 = 64 bytes per activation e, split hi / lo)  <-  bases[m][e] FP32, m <= M
+// basesT[e][m] (K-major, KT BF16 per activation e, split hi / lo)  <-  bases[m][e] FP32, m <= M.  KT = 24 when M + 1 <= 24 (48-byte
+// rows; the TMA box stays 32 wide and the 8 columns past the tensor's edge arrive as zeros), else 32: the kernel that reads
+// this stream is HBM-bound and a quarter of a 32-wide row would be padding for M = 20.
 __global__ void __launch_bounds__(256)
-k_tc_bases_kmajor(const float* __restrict__ bases, long long NW, int M1, bf16* __restrict__ th, bf16* __restrict__ tl) {
+k_tc_bases_kmajor(const float* __restrict__ bases, long long NW, int M1, int KT, bf16* __restrict__ th, bf16* __restrict__ tl) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= NW) return;
     __align__(16) bf16 hi[32], lo[32];
@@ -792,10 +794,11 @@ k_tc_bases_kmajor(const float* __restrict__ bases, long long NW, int M1, bf16* _
         const float v = m < M1 ? bases[(long long)m * NW + e] : 0.0f;
         split_bf16(v, hi[m], lo[m]);
     }
-    uint4* dh = reinterpret_cast<uint4*>(th + e * 32);
-    uint4* dl = reinterpret_cast<uint4*>(tl + e * 32);
+    uint4* dh = reinterpret_cast<uint4*>(th + e * KT);
+    uint4* dl = reinterpret_cast<uint4*>(tl + e * KT);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { dh[c] = reinterpret_cast<const uint4*>(hi)[c]; dl[c] = reinterpret_cast<const uint4*>(lo)[c]; }
+    for (int c = 0; c < 4; ++c)
+        if (c * 8 < KT) { dh[c] = reinterpret_cast<const uint4*>(hi)[c]; dl[c] = reinterpret_cast<const uint4*>(lo)[c]; }
 }
 
 // zpack[g][m] <- Z[m + g*M], zero padded  (staging for the device-to-constant copy)
@@ -848,6 +851,7 @@ struct ssi_tc_state {
     bool basis_mma = false;
     bf16 *Th = nullptr, *Tl = nullptr, *Zh = nullptr, *Zl = nullptr;
     CUtensorMap tmZh, tmZl, tmTh, tmTl, tmO;
+    int KT = 32;                             // columns per row of Th / Tl (24 or 32)
     double* partials = nullptr;
     CUtensorMap tmAh[SSI_MAX_LAYERS], tmAl[SSI_MAX_LAYERS], tmBh[SSI_MAX_LAYERS], tmBl[SSI_MAX_LAYERS];
     CUtensorMap tmBh2[SSI_MAX_LAYERS], tmBl2[SSI_MAX_LAYERS];     // boxes of BN/2 rows (cluster mode)
@@ -1011,11 +1015,12 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
         const size_t NW = (size_t)N * s->width[0];
         SSI_CUDA(ctx, cudaMalloc(&s->Bh, sizeof(bf16) * 2 * (size_t)G * NW));
         if (s->basis_mma) {
-            SSI_CUDA(ctx, cudaMalloc(&s->Th, sizeof(bf16) * NW * 32));
-            SSI_CUDA(ctx, cudaMalloc(&s->Tl, sizeof(bf16) * NW * 32));
+            s->KT = (ctx->M + 1 <= 24 && !ctx->opt_tc_k32) ? 24 : 32;
+            SSI_CUDA(ctx, cudaMalloc(&s->Th, sizeof(bf16) * NW * s->KT));
+            SSI_CUDA(ctx, cudaMalloc(&s->Tl, sizeof(bf16) * NW * s->KT));
             SSI_CUDA(ctx, cudaMalloc(&s->Zh, sizeof(bf16) * 128 * 32));
             SSI_CUDA(ctx, cudaMalloc(&s->Zl, sizeof(bf16) * 128 * 32));
-            k_tc_bases_kmajor<<<(unsigned)((NW + 255) / 256), 256, 0, ctx->stream>>>(s->bases, (long long)NW, ctx->M + 1, s->Th, s->Tl);
+            k_tc_bases_kmajor<<<(unsigned)((NW + 255) / 256), 256, 0, ctx->stream>>>(s->bases, (long long)NW, ctx->M + 1, s->KT, s->Th, s->Tl);
             SSI_LAUNCH_CHECK(ctx);
         }
     }
@@ -1066,8 +1071,8 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
         const uint64_t NW = (uint64_t)N * s->width[0];
         SSI_TRY(tc_make_map(ctx, &s->tmZh, s->Zh, 32, 128, 1, 32, 128, S64));
         SSI_TRY(tc_make_map(ctx, &s->tmZl, s->Zl, 32, 128, 1, 32, 128, S64));
-        SSI_TRY(tc_make_map(ctx, &s->tmTh, s->Th, 32, NW, 1, 32, TB_N, S64));
-        SSI_TRY(tc_make_map(ctx, &s->tmTl, s->Tl, 32, NW, 1, 32, TB_N, S64));
+        SSI_TRY(tc_make_map(ctx, &s->tmTh, s->Th, (uint64_t)s->KT, NW, 1, 32, TB_N, S64));
+        SSI_TRY(tc_make_map(ctx, &s->tmTl, s->Tl, (uint64_t)s->KT, NW, 1, 32, TB_N, S64));
         // the group's activations as a [samples][N*width0] matrix: boxes of 32 samples x 64 activations from the epilogue
         {   // store view: [samples][128-byte segments][64]; a box takes the (hi, lo) segment pair of 32 samples = 256 contiguous
             // bytes per sample (adjacent 128-byte rows: 5.8 TB/s through the TMA store engine against 4.5 for lone rows,
