@@ -20,12 +20,13 @@
  *     column-major) followed by b_l                 src/libs.jl:55-57, :19-22
  *   - the caller owns every buffer for the duration of the call only; the context owns
  *     all device memory and its stream; set_* calls copy.
- *   - a context is bound to ONE device and is not re-entrant.  Multi-GPU runs use one
- *     process (and one context) per GPU and shard chains by `chain_offset`; the
- *     counter-based RNG is keyed on the GLOBAL chain id so results do not depend on
- *     the number of GPUs.
- *   - ssi_swa_finish / ssi_swa_finish_gram stage V_M in the device's constant bank: do not run them concurrently from two
- *     host threads on contexts of the SAME device (every other entry point is independent across contexts).
+ *   - a context is not re-entrant.  ssi_ctx_create binds it to ONE device; ssi_ctx_create_multi returns a context that
+ *     drives several devices from the one calling process (the reference is a single Julia process,
+ *     src/space_inference.jl:82-84): set_* calls are replicated, the batched host-pointer calls shard samples / chains
+ *     across the devices and every device lands its slice in the caller's host arrays.  Alternatively one process (and
+ *     one context) per GPU shards chains by `chain_offset`.  Either way the counter-based RNG is keyed on the GLOBAL
+ *     chain id, so results do not depend on the number of GPUs.
+ *   - distinct contexts are independent (no shared mutable state), also on the same device.
  *   - there is no CPU fallback: every compute entry point fails with SSI_ERR_CUDA when
  *     no sm_100 device is usable.
  */
@@ -38,7 +39,7 @@
 extern "C" {
 #endif
 
-#define SSI_VERSION 100            /* 0.1.0 */
+#define SSI_VERSION 200            /* 0.2.0 */
 
 /* error codes */
 #define SSI_OK             0
@@ -47,6 +48,9 @@ extern "C" {
 #define SSI_ERR_STATE     -3       /* model / data / subspace not set */
 #define SSI_ERR_RANK      -4       /* deviation matrix has fewer than M usable columns */
 #define SSI_ERR_UNSUPPORTED -5
+#define SSI_ERR_RANGE     -6       /* asynchronous (*_dev) tensor-path results since the last ssi_sync are invalid: an
+                                    * activation left the calibrated FP16 range; the context has switched to BF16 planes,
+                                    * repeat the calls (the host-pointer entry points repeat by themselves)             */
 
 /* activation codes for ssi_set_model (Flux/NNlib: identity, relu, tanh, sigmoid) */
 #define SSI_ACT_IDENTITY 0
@@ -87,21 +91,36 @@ typedef struct ssi_stats_t {
     double gram_risk;          /* conditioning estimate of the tensor-core Gram       */
     double dominant_ms;        /* with option "time_dominant": summed device time of the path's dominant   */
     int64_t dominant_launches; /* kernel since the option was set (CUDA events on the launching stream)    */
+    double finish_gram_ms;     /* last ssi_swa_finish, CUDA events on the context stream: Gram (K6),        */
+    double finish_eigen_ms;    /* eigen-solve + conditioning check (K7),                                    */
+    double finish_p_ms;        /* P = A V_M (K8)                                                            */
+    int64_t tc_range_fallbacks;/* tensor path: evaluations repeated on BF16 planes because an activation left the   */
+                               /* calibrated range of the FP16 planes; 0 in normal operation   */
 } ssi_stats_t;
 
 int  ssi_version(void);
 
 /* ---- lifecycle ------------------------------------------------------------------- */
 int  ssi_ctx_create(int device, ssi_ctx** out);
+/* One context over n_dev devices: W_swa, P, X, Y are replicated on every device; ssi_logpost_batch,
+ * ssi_logpost_grad_batch, ssi_mh_run, ssi_mala_run, ssi_mh_run_from, ssi_mh_get_state and ssi_project split their B samples /
+ * n_chains chains into contiguous ranges, one per device (chains keep their global ids: traces are bit-identical to a
+ * one-device run); ssi_predict_batch, ssi_swa_* and ssi_train_* run on devices[0] (an installed subspace is replicated).
+ * The *_dev entry points and ssi_set_stream take pointers / streams of ONE device and return SSI_ERR_UNSUPPORTED here.
+ * ssi_stats reports the maximum over devices for times and the sum for work and counters.                          */
+int  ssi_ctx_create_multi(const int32_t* devices, int32_t n_dev, ssi_ctx** out);
+int  ssi_ctx_devices(const ssi_ctx* ctx);       /* number of devices the context drives */
 int  ssi_ctx_destroy(ssi_ctx* ctx);
 /* message of the last failure on `ctx` (or of the last failed ssi_ctx_create when ctx==NULL) */
 const char* ssi_last_error(const ssi_ctx* ctx);
 /* run on a caller-provided cudaStream_t (e.g. torch's current stream); NULL restores the ctx stream */
 int  ssi_set_stream(ssi_ctx* ctx, void* cuda_stream);
 int  ssi_sync(ssi_ctx* ctx);
-/* keys: "path" (SSI_PATH_*), "group" (samples per wave on the tensor path), and A/B switches used by the
- * tests: "tc_nobasis", "tc_nofuse", "tc_noorder", "tc_simt_basis", "tc_cluster", "tc_nokrev", "tc_alast", "tc_k32", "b1_simt", "bm_nopack", "bm_variant", "gram_fp64", "gram_chunk" (see DESIGN.md); "time_dominant" (0/1) brackets every
- * launch of the path's dominant kernel with CUDA events (ssi_stats_t.dominant_ms) */
+/* keys: "path" (SSI_PATH_*), "group" (samples per wave on the tensor path), "tc_precision" (operand planes of the tensor
+ * path: 1 = mixed BF16/FP16 planes, the default; 0 = BF16x3), and A/B switches used by the tests: "tc_nobasis", "tc_nofuse",
+ * "tc_noorder", "tc_simt_basis", "tc_nokrev", "tc_alast", "tc_k32", "b1_simt", "bm_nopack", "bm_variant", "gram_fp64",
+ * "gram_chunk" (see DESIGN.md); "time_dominant" (0/1) brackets every launch of the path's dominant kernel with CUDA events
+ * (ssi_stats_t.dominant_ms) */
 int  ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value);
 int  ssi_stats(const ssi_ctx* ctx, ssi_stats_t* out);
 
@@ -163,6 +182,20 @@ int  ssi_mala_run_dev(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t 
                       double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask,
                       const float* d_z0_or_null,
                       float* d_z_trace, double* d_lp_trace, uint8_t* d_accept_trace);
+/* ---- checkpoint / resume of the chains (the docs save and reload around sampling, docs/src/nn_example.md:158,168) ----
+ * The RNG is counter-based, so a chain is resumable from (seed, step, z): ssi_mh_get_state returns the final state of the last
+ * run's chains (z_out M x n_chains floats, lp_out n_chains doubles, host, either may be NULL); ssi_mh_run_from continues them:
+ * kind 0 = RWMH, 1 = MALA; z_state (M x n_chains) is the state after step step_offset - 1, steps step_offset ..
+ * step_offset + n_steps - 1 draw from the Philox counters of those steps and fill trace rows 0 .. n_steps - 1.  The state's
+ * log-density (and gradient) is re-evaluated, which is deterministic: run(0..S) is bit-identical to run(0..S/2) followed by
+ * run_from(S/2..S).  step_offset == 0 is ssi_mh_run / ssi_mala_run (z_state = z0 or NULL).                                */
+int  ssi_mh_get_state(ssi_ctx* ctx, float* z_out, double* lp_out);
+int  ssi_mh_run_from(ssi_ctx* ctx, int32_t kind, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+                     int64_t step_offset, double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask,
+                     const float* z_state, float* z_trace, double* lp_trace, uint8_t* accept_trace);
+int  ssi_mh_run_from_dev(ssi_ctx* ctx, int32_t kind, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+                         int64_t step_offset, double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask,
+                         const float* d_z_state, float* d_z_trace, double* d_lp_trace, uint8_t* d_accept_trace);
 /* host replay of the device stream: eps_out (M floats, N(0,1)) and e_out (Exp(1)) of (chain, step) */
 int  ssi_rng_replay(uint64_t seed, int64_t chain, int64_t step, int32_t M, float* eps_out, double* e_out);
 /* map(z -> W_swa + P*z, chm) (src/space_inference.jl:125): W_out n x B column-major (host) */

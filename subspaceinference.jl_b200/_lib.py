@@ -12,7 +12,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["SSI_LIB_PATH"]).resolve() if os.environ.get("SSI_LIB_PATH") else PKG / "lib" / "libssi.so"
 
 SSI_OK = 0
-ERR_NAMES = {-1: "SSI_ERR_ARG", -2: "SSI_ERR_CUDA", -3: "SSI_ERR_STATE", -4: "SSI_ERR_RANK", -5: "SSI_ERR_UNSUPPORTED"}
+ERR_NAMES = {-1: "SSI_ERR_ARG", -2: "SSI_ERR_CUDA", -3: "SSI_ERR_STATE", -4: "SSI_ERR_RANK", -5: "SSI_ERR_UNSUPPORTED", -6: "SSI_ERR_RANGE"}
 
 ACT_IDENTITY, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
 TERM_LL, TERM_PRIOR_W, TERM_PRIOR_Z = 1, 2, 4
@@ -36,6 +36,8 @@ class Stats(C.Structure):
         ("last_path", C.c_int32), ("sm_count", C.c_int32),
         ("gram_path", C.c_int32), ("jacobi_sweeps", C.c_int32), ("gram_risk", C.c_double),
         ("dominant_ms", C.c_double), ("dominant_launches", C.c_int64),
+        ("finish_gram_ms", C.c_double), ("finish_eigen_ms", C.c_double), ("finish_p_ms", C.c_double),
+        ("tc_range_fallbacks", C.c_int64),
     ]
 
 
@@ -45,6 +47,8 @@ _p, _i64, _i32, _u32, _u64, _dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32,
 SIGNATURES = {
     "ssi_version": (C.c_int, []),
     "ssi_ctx_create": (C.c_int, [C.c_int, C.POINTER(_p)]),
+    "ssi_ctx_create_multi": (C.c_int, [_p, _i32, C.POINTER(_p)]),
+    "ssi_ctx_devices": (C.c_int, [_p]),
     "ssi_ctx_destroy": (C.c_int, [_p]),
     "ssi_last_error": (C.c_char_p, [_p]),
     "ssi_set_stream": (C.c_int, [_p, _p]),
@@ -62,6 +66,9 @@ SIGNATURES = {
     "ssi_mh_run_dev": (C.c_int, [_p, _i64, _i64, _u64, _i64, _dbl, _dbl, _dbl, _u32, _p, _p, _p, _p]),
     "ssi_mala_run": (C.c_int, [_p, _i64, _i64, _u64, _i64, _dbl, _dbl, _dbl, _u32, _p, _p, _p, _p]),
     "ssi_mala_run_dev": (C.c_int, [_p, _i64, _i64, _u64, _i64, _dbl, _dbl, _dbl, _u32, _p, _p, _p, _p]),
+    "ssi_mh_get_state": (C.c_int, [_p, _p, _p]),
+    "ssi_mh_run_from": (C.c_int, [_p, _i32, _i64, _i64, _u64, _i64, _i64, _dbl, _dbl, _dbl, _u32, _p, _p, _p, _p]),
+    "ssi_mh_run_from_dev": (C.c_int, [_p, _i32, _i64, _i64, _u64, _i64, _i64, _dbl, _dbl, _dbl, _u32, _p, _p, _p, _p]),
     "ssi_rng_replay": (C.c_int, [_u64, _i64, _i64, _i32, _p, _p]),
     "ssi_project": (C.c_int, [_p, _p, _i64, _p]),
     "ssi_predict_batch": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _p, _p]),

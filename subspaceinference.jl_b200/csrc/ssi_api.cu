@@ -7,7 +7,7 @@
 #include <cmath>
 #include <mutex>
 
-int ssi_mh_device(ssi_ctx*, int, int64_t, int64_t, uint64_t, int64_t, double, double, double, uint32_t,
+int ssi_mh_device(ssi_ctx*, int, int64_t, int64_t, uint64_t, int64_t, int64_t, double, double, double, uint32_t,
                   const float*, float*, double*, uint8_t*);
 int ssi_mh_fetch_accepts(ssi_ctx*);
 int ssi_swa_push_device(ssi_ctx*, const float*, double);
@@ -143,8 +143,13 @@ int ssi_ctx_create(int device, ssi_ctx** out) {
     return SSI_OK;
 }
 
+int ssi_ctx_create_multi(const int32_t* devices, int32_t n_dev, ssi_ctx** out) { return ssi_multi_create(devices, n_dev, out); }
+
+int ssi_ctx_devices(const ssi_ctx* ctx) { return ctx ? (ctx->is_multi() ? (int)ctx->children.size() : 1) : 0; }
+
 int ssi_ctx_destroy(ssi_ctx* ctx) {
     if (!ctx) return SSI_OK;
+    if (ctx->is_multi()) return ssi_multi_destroy(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ssi_tc_destroy(ctx);
@@ -159,6 +164,8 @@ int ssi_ctx_destroy(ssi_ctx* ctx) {
     for (cudaEvent_t e : ctx->kt_events) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t ev : ctx->ev_stage)
+        if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return SSI_OK;
@@ -166,6 +173,7 @@ int ssi_ctx_destroy(ssi_ctx* ctx) {
 
 int ssi_set_stream(ssi_ctx* ctx, void* cuda_stream) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NO_MULTI(ctx, "caller-provided streams");
     SSI_TRY(ssi_use_device(ctx));
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
@@ -174,18 +182,43 @@ int ssi_set_stream(ssi_ctx* ctx, void* cuda_stream) {
 
 int ssi_sync(ssi_ctx* ctx) {
     if (!ctx) return SSI_ERR_ARG;
+    if (ctx->is_multi()) return ssi_multi_sync(ctx);
+    SSI_TRY(ssi_sync_internal(ctx));
+    // asynchronous tensor-path evaluations cannot be repeated behind the caller's back: report them
+    bool exceeded = false;
+    SSI_TRY(ssi_tc_range_exceeded(ctx, &exceeded));
+    if (exceeded)
+        return ssi_fail(ctx, SSI_ERR_RANGE, "an activation left the calibrated FP16 range of the tensor path: results of the *_dev calls since "
+                                            "the last ssi_sync are invalid; the context now uses BF16 planes, repeat those calls");
+    return SSI_OK;
+}
+
+}  // extern "C"
+
+int ssi_sync_internal(ssi_ctx* ctx) {
     SSI_TRY(ssi_use_device(ctx));
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     if (cudaEventQuery(ctx->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess)
         ctx->stats.last_ms = ms;
+    if (ctx->stage_pending) {
+        float g = 0, e = 0, f = 0;
+        if (cudaEventElapsedTime(&g, ctx->ev_stage[0], ctx->ev_stage[1]) == cudaSuccess && cudaEventElapsedTime(&e, ctx->ev_stage[1], ctx->ev_stage[2]) == cudaSuccess &&
+            cudaEventElapsedTime(&f, ctx->ev_stage[2], ctx->ev_stage[3]) == cudaSuccess) {
+            ctx->stats.finish_gram_ms = g; ctx->stats.finish_eigen_ms = e; ctx->stats.finish_p_ms = f;
+        }
+        ctx->stage_pending = false;
+    }
     (void)cudaGetLastError();
     ssi_kt_collect(ctx);
     return SSI_OK;
 }
 
+extern "C" {
+
 int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return SSI_ERR_ARG;
+    if (ctx->is_multi()) return ssi_multi_set_option(ctx, key, value);
     if (!strcmp(key, "path")) {
         if (value < SSI_PATH_AUTO || value > SSI_PATH_BASIS) return ssi_fail(ctx, SSI_ERR_ARG, "path must be one of SSI_PATH_*");
         ctx->opt_path = (int)value;
@@ -211,7 +244,7 @@ int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
     if (!strcmp(key, "tc_k32")) { ctx->opt_tc_k32 = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "tc_alast")) { ctx->opt_tc_alast = value != 0; return SSI_OK; }
     if (!strcmp(key, "tc_nokrev")) { ctx->opt_tc_nokrev = value != 0; return SSI_OK; }
-    if (!strcmp(key, "tc_cluster")) { ctx->opt_tc_cluster = value != 0; return SSI_OK; }
+    if (!strcmp(key, "tc_precision")) { ctx->opt_tc_prec = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "b1_simt")) { ctx->opt_b1_simt = value != 0; return SSI_OK; }
     if (!strcmp(key, "bm_nopack")) { ctx->opt_bm_nopack = value != 0; ssi_bm_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "bm_variant")) { ctx->opt_bm_variant = (int)value; return SSI_OK; }
@@ -222,12 +255,14 @@ int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
 
 int ssi_stats(const ssi_ctx* ctx, ssi_stats_t* out) {
     if (!ctx || !out) return SSI_ERR_ARG;
+    if (ctx->is_multi()) return ssi_multi_stats(ctx, out);
     *out = ctx->stats;
     return SSI_OK;
 }
 
 int ssi_set_model(ssi_ctx* ctx, int n_layers, const int32_t* dims, const int32_t* act) {
     if (!ctx) return SSI_ERR_ARG;
+    if (ctx->is_multi()) return ssi_multi_set_model(ctx, n_layers, dims, act);
     if (n_layers < 1 || n_layers > SSI_MAX_LAYERS || !dims || !act)
         return ssi_fail(ctx, SSI_ERR_ARG, "n_layers must be in [1,%d] and dims/act non-NULL", SSI_MAX_LAYERS);
     ssi_model_t m;
@@ -262,6 +297,7 @@ int ssi_set_model(ssi_ctx* ctx, int n_layers, const int32_t* dims, const int32_t
 
 int ssi_set_data(ssi_ctx* ctx, const float* X, const float* Y, int64_t N) {
     if (!ctx) return SSI_ERR_ARG;
+    if (ctx->is_multi()) return ssi_multi_set_data(ctx, X, Y, N);
     if (!ctx->has_model) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_set_model must be called before ssi_set_data");
     if (!X || !Y || N < 1) return ssi_fail(ctx, SSI_ERR_ARG, "X, Y must be non-NULL and N >= 1");
     SSI_TRY(ssi_use_device(ctx));
@@ -308,6 +344,7 @@ static int install_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, in
 int ssi_set_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, int64_t n, int32_t M) {
     if (!ctx) return SSI_ERR_ARG;
     if (!W_swa || !P) return ssi_fail(ctx, SSI_ERR_ARG, "W_swa and P must be non-NULL");
+    if (ctx->is_multi()) return ssi_multi_set_subspace(ctx, W_swa, P, n, M);
     return install_subspace(ctx, W_swa, P, n, M, cudaMemcpyHostToDevice);
 }
 
@@ -315,6 +352,7 @@ int ssi_logpost_batch_dev(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma
                           uint32_t prior_mask, double* d_lp_out, double* d_terms_out) {
     if (!ctx) return SSI_ERR_ARG;
     if (B < 0 || (B > 0 && (!dZ || !d_lp_out))) return ssi_fail(ctx, SSI_ERR_ARG, "Z and lp_out must be non-NULL, B >= 0");
+    SSI_NO_MULTI(ctx, "device-pointer entry points");
     SSI_TRY(ssi_use_device(ctx));
     call_timer t(ctx);
     const int rc = ssi_logpost_device(ctx, dZ, B, sigma_m, sigma_p, sigma_z, prior_mask, d_lp_out, d_terms_out);
@@ -327,6 +365,7 @@ int ssi_logpost_grad_batch_dev(ssi_ctx* ctx, const float* dZ, int64_t B, double 
     if (!ctx) return SSI_ERR_ARG;
     if (B < 0 || (B > 0 && (!dZ || !d_lp_out || !d_grad_out)))
         return ssi_fail(ctx, SSI_ERR_ARG, "Z, lp_out and grad_out must be non-NULL, B >= 0");
+    SSI_NO_MULTI(ctx, "device-pointer entry points");
     SSI_TRY(ssi_use_device(ctx));
     call_timer t(ctx);
     const int rc = ssi_logpost_grad_device(ctx, dZ, B, sigma_m, sigma_p, sigma_z, prior_mask, d_lp_out, d_grad_out);
@@ -339,6 +378,7 @@ int ssi_logpost_grad_batch(ssi_ctx* ctx, const float* Z, int64_t B, double sigma
     if (!ctx) return SSI_ERR_ARG;
     if (B < 0 || (B > 0 && (!Z || !lp_out || !grad_out)))
         return ssi_fail(ctx, SSI_ERR_ARG, "Z, lp_out and grad_out must be non-NULL, B >= 0");
+    if (ctx->is_multi()) return ssi_multi_logpost(ctx, 1, Z, B, sigma_m, sigma_p, sigma_z, prior_mask, lp_out, grad_out);
     if (!ctx->has_model || !ctx->has_data || !ctx->has_sub)
         return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before evaluating the gradient");
     if (B == 0) return SSI_OK;
@@ -355,13 +395,14 @@ int ssi_logpost_grad_batch(ssi_ctx* ctx, const float* Z, int64_t B, double sigma
     if (rc != SSI_OK) return rc;
     SSI_CUDA(ctx, cudaMemcpyAsync(lp_out, ctx->bLp.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
     SSI_CUDA(ctx, cudaMemcpyAsync(grad_out, ctx->bTerms.p, sizeof(double) * (size_t)ctx->M * B, cudaMemcpyDeviceToHost, ctx->stream));
-    return ssi_sync(ctx);
+    return ssi_sync_internal(ctx);
 }
 
 int ssi_logpost_batch(ssi_ctx* ctx, const float* Z, int64_t B, double sigma_m, double sigma_p, double sigma_z,
                       uint32_t prior_mask, double* lp_out, double* terms_out) {
     if (!ctx) return SSI_ERR_ARG;
     if (B < 0 || (B > 0 && (!Z || !lp_out))) return ssi_fail(ctx, SSI_ERR_ARG, "Z and lp_out must be non-NULL, B >= 0");
+    if (ctx->is_multi()) return ssi_multi_logpost(ctx, 0, Z, B, sigma_m, sigma_p, sigma_z, prior_mask, lp_out, terms_out);
     if (!ctx->has_model || !ctx->has_data || !ctx->has_sub)
         return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before evaluating the log-posterior");
     if (B == 0) return SSI_OK;
@@ -371,24 +412,32 @@ int ssi_logpost_batch(ssi_ctx* ctx, const float* Z, int64_t B, double sigma_m, d
     SSI_TRY(ssi_reserve(ctx, ctx->bLp, sizeof(double) * (size_t)B));
     if (terms_out) SSI_TRY(ssi_reserve(ctx, ctx->bTerms, sizeof(double) * 3 * (size_t)B));
     SSI_CUDA(ctx, cudaMemcpyAsync(ctx->bZ.p, Z, bz, cudaMemcpyHostToDevice, ctx->stream));
-    call_timer t(ctx);
-    const int rc = ssi_logpost_device(ctx, (const float*)ctx->bZ.p, B, sigma_m, sigma_p, sigma_z, prior_mask,
-                                      (double*)ctx->bLp.p, terms_out ? (double*)ctx->bTerms.p : nullptr);
-    t.stop(false);
-    if (rc != SSI_OK) return rc;
-    SSI_CUDA(ctx, cudaMemcpyAsync(lp_out, ctx->bLp.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
-    if (terms_out)
-        SSI_CUDA(ctx, cudaMemcpyAsync(terms_out, ctx->bTerms.p, sizeof(double) * 3 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
-    return ssi_sync(ctx);
+    // second attempt only if the tensor path's FP16 planes overflowed (it then runs on BF16 planes)
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        call_timer t(ctx);
+        const int rc = ssi_logpost_device(ctx, (const float*)ctx->bZ.p, B, sigma_m, sigma_p, sigma_z, prior_mask,
+                                          (double*)ctx->bLp.p, terms_out ? (double*)ctx->bTerms.p : nullptr);
+        t.stop(false);
+        if (rc != SSI_OK) return rc;
+        SSI_CUDA(ctx, cudaMemcpyAsync(lp_out, ctx->bLp.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+        if (terms_out)
+            SSI_CUDA(ctx, cudaMemcpyAsync(terms_out, ctx->bTerms.p, sizeof(double) * 3 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+        SSI_TRY(ssi_sync_internal(ctx));
+        bool exceeded = false;
+        SSI_TRY(ssi_tc_range_exceeded(ctx, &exceeded));
+        if (!exceeded) break;
+    }
+    return SSI_OK;
 }
 
-static int mh_run_dev(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+static int mh_run_dev(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset, int64_t step_offset,
                       double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* d_z0,
                       float* d_z_trace, double* d_lp_trace, uint8_t* d_accept_trace) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NO_MULTI(ctx, "device-pointer entry points");
     SSI_TRY(ssi_use_device(ctx));
     call_timer t(ctx);
-    const int rc = ssi_mh_device(ctx, kind, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask,
+    const int rc = ssi_mh_device(ctx, kind, n_chains, n_steps, seed, chain_offset, step_offset, sigma_z, sigma_m, sigma_p, prior_mask,
                                  d_z0, d_z_trace, d_lp_trace, d_accept_trace);
     t.stop(false);
     return rc;
@@ -396,20 +445,30 @@ static int mh_run_dev(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_steps,
 int ssi_mh_run_dev(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
                    double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* d_z0,
                    float* d_z_trace, double* d_lp_trace, uint8_t* d_accept_trace) {
-    return mh_run_dev(ctx, 0, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask, d_z0, d_z_trace,
+    return mh_run_dev(ctx, 0, n_chains, n_steps, seed, chain_offset, 0, sigma_z, sigma_m, sigma_p, prior_mask, d_z0, d_z_trace,
                       d_lp_trace, d_accept_trace);
 }
 int ssi_mala_run_dev(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
                      double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* d_z0,
                      float* d_z_trace, double* d_lp_trace, uint8_t* d_accept_trace) {
-    return mh_run_dev(ctx, 1, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask, d_z0, d_z_trace,
+    return mh_run_dev(ctx, 1, n_chains, n_steps, seed, chain_offset, 0, sigma_z, sigma_m, sigma_p, prior_mask, d_z0, d_z_trace,
                       d_lp_trace, d_accept_trace);
 }
+int ssi_mh_run_from_dev(ssi_ctx* ctx, int32_t kind, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
+                        int64_t step_offset, double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask,
+                        const float* d_z_state, float* d_z_trace, double* d_lp_trace, uint8_t* d_accept_trace) {
+    if (ctx && kind != 0 && kind != 1) return ssi_fail(ctx, SSI_ERR_ARG, "kind must be 0 (RWMH) or 1 (MALA)");
+    return mh_run_dev(ctx, kind, n_chains, n_steps, seed, chain_offset, step_offset, sigma_z, sigma_m, sigma_p, prior_mask, d_z_state,
+                      d_z_trace, d_lp_trace, d_accept_trace);
+}
 
-static int mh_run_host(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
-                       double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* z0,
-                       float* z_trace, double* lp_trace, uint8_t* accept_trace) {
-    if (!ctx) return SSI_ERR_ARG;
+}  // extern "C"
+
+// Host-pointer run of the chains [c0, c0 + n_chains) of a trace that holds ld_chains chains per step (ld_chains == n_chains
+// and c0 == 0 for a single-device context; a multi-device context hands every device its slice of the same host arrays).
+int ssi_mh_run_host_slice(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset, int64_t step_offset,
+                          double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* z0,
+                          float* z_trace, double* lp_trace, uint8_t* accept_trace, int64_t ld_chains, int64_t c0) {
     if (!ctx->has_model || !ctx->has_data || !ctx->has_sub)
         return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before sampling");
     if (n_chains <= 0 || n_steps <= 0) return ssi_fail(ctx, SSI_ERR_ARG, "n_chains and n_steps must be positive");
@@ -429,30 +488,80 @@ static int mh_run_host(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_steps
     float* dz0 = nullptr;
     if (z0) {
         dz0 = (float*)(base + off_z0);
-        SSI_CUDA(ctx, cudaMemcpyAsync(dz0, z0, bz0, cudaMemcpyHostToDevice, ctx->stream));
+        SSI_CUDA(ctx, cudaMemcpyAsync(dz0, z0 + (size_t)c0 * ctx->M, bz0, cudaMemcpyHostToDevice, ctx->stream));
     }
-    call_timer t(ctx);
-    const int rc = ssi_mh_device(ctx, kind, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask,
-                                 dz0, dzt, dlt, dat);
-    t.stop(false);
-    if (rc != SSI_OK) return rc;
-    if (z_trace) SSI_CUDA(ctx, cudaMemcpyAsync(z_trace, dzt, bz, cudaMemcpyDeviceToHost, ctx->stream));
-    if (lp_trace) SSI_CUDA(ctx, cudaMemcpyAsync(lp_trace, dlt, bl, cudaMemcpyDeviceToHost, ctx->stream));
-    if (accept_trace) SSI_CUDA(ctx, cudaMemcpyAsync(accept_trace, dat, ba, cudaMemcpyDeviceToHost, ctx->stream));
-    SSI_TRY(ssi_sync(ctx));
+    for (int attempt = 0; attempt < 2; ++attempt) {      // repeated only if the tensor path's FP16 planes overflowed
+        call_timer t(ctx);
+        const int rc = ssi_mh_device(ctx, kind, n_chains, n_steps, seed, chain_offset, step_offset, sigma_z, sigma_m, sigma_p, prior_mask,
+                                     dz0, dzt, dlt, dat);
+        t.stop(false);
+        if (rc != SSI_OK) return rc;
+        SSI_TRY(ssi_sync_internal(ctx));
+        bool exceeded = false;
+        SSI_TRY(ssi_tc_range_exceeded(ctx, &exceeded));
+        if (!exceeded) break;
+    }
+    // a step's row of the device trace is this device's n_chains chains; in the host trace rows are ld_chains chains apart
+    const size_t rz = sizeof(float) * (size_t)ctx->M * n_chains, rl = sizeof(double) * (size_t)n_chains, ra = (size_t)n_chains;
+    if (z_trace) SSI_CUDA(ctx, cudaMemcpy2DAsync(z_trace + (size_t)c0 * ctx->M, sizeof(float) * (size_t)ctx->M * ld_chains, dzt, rz, rz, (size_t)n_steps,
+                                                 cudaMemcpyDeviceToHost, ctx->stream));
+    if (lp_trace) SSI_CUDA(ctx, cudaMemcpy2DAsync(lp_trace + c0, sizeof(double) * (size_t)ld_chains, dlt, rl, rl, (size_t)n_steps,
+                                                  cudaMemcpyDeviceToHost, ctx->stream));
+    if (accept_trace) SSI_CUDA(ctx, cudaMemcpy2DAsync(accept_trace + c0, (size_t)ld_chains, dat, ra, ra, (size_t)n_steps,
+                                                      cudaMemcpyDeviceToHost, ctx->stream));
+    SSI_TRY(ssi_sync_internal(ctx));
     return ssi_mh_fetch_accepts(ctx);
+}
+extern "C" {
+
+static int mh_run_host(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset, int64_t step_offset,
+                       double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* z0,
+                       float* z_trace, double* lp_trace, uint8_t* accept_trace) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (ctx->is_multi())
+        return ssi_multi_mh_run(ctx, kind, n_chains, n_steps, seed, chain_offset, step_offset, sigma_z, sigma_m, sigma_p, prior_mask, z0,
+                                z_trace, lp_trace, accept_trace);
+    return ssi_mh_run_host_slice(ctx, kind, n_chains, n_steps, seed, chain_offset, step_offset, sigma_z, sigma_m, sigma_p, prior_mask, z0,
+                                 z_trace, lp_trace, accept_trace, n_chains, 0);
 }
 int ssi_mh_run(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
                double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* z0,
                float* z_trace, double* lp_trace, uint8_t* accept_trace) {
-    return mh_run_host(ctx, 0, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask, z0, z_trace, lp_trace,
+    return mh_run_host(ctx, 0, n_chains, n_steps, seed, chain_offset, 0, sigma_z, sigma_m, sigma_p, prior_mask, z0, z_trace, lp_trace,
                        accept_trace);
 }
 int ssi_mala_run(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
                  double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* z0,
                  float* z_trace, double* lp_trace, uint8_t* accept_trace) {
-    return mh_run_host(ctx, 1, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, prior_mask, z0, z_trace, lp_trace,
+    return mh_run_host(ctx, 1, n_chains, n_steps, seed, chain_offset, 0, sigma_z, sigma_m, sigma_p, prior_mask, z0, z_trace, lp_trace,
                        accept_trace);
+}
+int ssi_mh_run_from(ssi_ctx* ctx, int32_t kind, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset, int64_t step_offset,
+                    double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* z_state,
+                    float* z_trace, double* lp_trace, uint8_t* accept_trace) {
+    if (ctx && kind != 0 && kind != 1) return ssi_fail(ctx, SSI_ERR_ARG, "kind must be 0 (RWMH) or 1 (MALA)");
+    if (ctx && step_offset > 0 && !z_state) return ssi_fail(ctx, SSI_ERR_ARG, "a continued run (step_offset > 0) needs the chain state z");
+    return mh_run_host(ctx, kind, n_chains, n_steps, seed, chain_offset, step_offset, sigma_z, sigma_m, sigma_p, prior_mask, z_state,
+                       z_trace, lp_trace, accept_trace);
+}
+
+}  // extern "C"
+
+// final (z, lp) of the chains of the last run on this context: what a caller saves to continue later with ssi_mh_run_from
+int ssi_mh_get_state_slice(ssi_ctx* ctx, float* z_out, double* lp_out) {
+    if (ctx->mh_chains <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "no chains have been run on this context");
+    SSI_TRY(ssi_use_device(ctx));
+    if (z_out) SSI_CUDA(ctx, cudaMemcpyAsync(z_out, ctx->bMhZ.p, sizeof(float) * (size_t)ctx->M * ctx->mh_chains, cudaMemcpyDeviceToHost, ctx->stream));
+    if (lp_out) SSI_CUDA(ctx, cudaMemcpyAsync(lp_out, ctx->bMhLp.p, sizeof(double) * (size_t)ctx->mh_chains, cudaMemcpyDeviceToHost, ctx->stream));
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SSI_OK;
+}
+extern "C" {
+
+int ssi_mh_get_state(ssi_ctx* ctx, float* z_out, double* lp_out) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (ctx->is_multi()) return ssi_multi_mh_get_state(ctx, z_out, lp_out);
+    return ssi_mh_get_state_slice(ctx, z_out, lp_out);
 }
 
 int ssi_rng_replay(uint64_t seed, int64_t chain, int64_t step, int32_t M, float* eps_out, double* e_out) {
@@ -470,6 +579,7 @@ int ssi_rng_replay(uint64_t seed, int64_t chain, int64_t step, int32_t M, float*
 
 int ssi_project(ssi_ctx* ctx, const float* Z, int64_t B, float* W_out) {
     if (!ctx) return SSI_ERR_ARG;
+    if (ctx->is_multi()) return ssi_multi_project(ctx, Z, B, W_out);
     if (!ctx->has_model || !ctx->has_sub) return ssi_fail(ctx, SSI_ERR_STATE, "model and subspace must be set");
     if (B < 0 || (B > 0 && (!Z || !W_out))) return ssi_fail(ctx, SSI_ERR_ARG, "Z and W_out must be non-NULL");
     if (B == 0) return SSI_OK;
@@ -491,9 +601,23 @@ int ssi_project(ssi_ctx* ctx, const float* Z, int64_t B, float* W_out) {
     return SSI_OK;
 }
 
+// The sweep reduces over the samples (mean / std per grid point) and the construction streams hold one deviation matrix:
+// on a multi-device context they run on its first device.
+#define SSI_FIRST_DEVICE(ctx, call)                                                      \
+    do {                                                                                 \
+        if ((ctx)->is_multi()) {                                                         \
+            ssi_ctx* parent__ = (ctx);                                                   \
+            (ctx) = parent__->children[0];                                               \
+            const int rc__ = (call);                                                     \
+            if (rc__ < 0) parent__->err = (ctx)->err;                                    \
+            return rc__;                                                                 \
+        }                                                                                \
+    } while (0)
+
 int ssi_predict_batch(ssi_ctx* ctx, const float* Z, int64_t B, const float* Xg, int64_t Ng,
                       float* preds_out, double* mean_out, double* std_out) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_FIRST_DEVICE(ctx, ssi_predict_batch(ctx, Z, B, Xg, Ng, preds_out, mean_out, std_out));
     if (!ctx->has_model || !ctx->has_sub) return ssi_fail(ctx, SSI_ERR_STATE, "model and subspace must be set before predicting");
     if (B < 0 || Ng < 0) return ssi_fail(ctx, SSI_ERR_ARG, "B and Ng must be non-negative");
     if (B == 0 || Ng == 0) return SSI_OK;
@@ -522,11 +646,12 @@ int ssi_predict_batch(ssi_ctx* ctx, const float* Z, int64_t B, const float* Xg, 
     if (mean_out) SSI_CUDA(ctx, cudaMemcpyAsync(mean_out, d_mean, sizeof(double) * ON, cudaMemcpyDeviceToHost, ctx->stream));
     if (std_out) SSI_CUDA(ctx, cudaMemcpyAsync(std_out, d_std, sizeof(double) * ON, cudaMemcpyDeviceToHost, ctx->stream));
     if (preds_out) SSI_CUDA(ctx, cudaMemcpyAsync(preds_out, d_preds, sizeof(float) * ON * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
-    return ssi_sync(ctx);
+    return ssi_sync_internal(ctx);
 }
 
 int ssi_swa_begin(ssi_ctx* ctx, int64_t n, int64_t K_max) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_FIRST_DEVICE(ctx, ssi_swa_begin(ctx, n, K_max));
     if (n < 1 || K_max < 1) return ssi_fail(ctx, SSI_ERR_ARG, "n and K_max must be positive");
     SSI_TRY(ssi_use_device(ctx));
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -545,6 +670,7 @@ int ssi_swa_begin(ssi_ctx* ctx, int64_t n, int64_t K_max) {
 
 int ssi_swa_push_dev(ssi_ctx* ctx, const float* dW, double n_scalar) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NO_MULTI(ctx, "device-pointer entry points");
     if (!dW) return ssi_fail(ctx, SSI_ERR_ARG, "W must be non-NULL");
     SSI_TRY(ssi_use_device(ctx));
     call_timer t(ctx);
@@ -555,6 +681,7 @@ int ssi_swa_push_dev(ssi_ctx* ctx, const float* dW, double n_scalar) {
 
 int ssi_swa_push(ssi_ctx* ctx, const float* W, double n_scalar) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_FIRST_DEVICE(ctx, ssi_swa_push(ctx, W, n_scalar));
     if (!W) return ssi_fail(ctx, SSI_ERR_ARG, "W must be non-NULL");
     if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
     SSI_TRY(ssi_use_device(ctx));
@@ -564,14 +691,15 @@ int ssi_swa_push(ssi_ctx* ctx, const float* W, double n_scalar) {
     const int rc = ssi_swa_push_device(ctx, (const float*)ctx->bSnap.p, n_scalar);
     t.stop(false);
     if (rc != SSI_OK) return rc;
-    return ssi_sync(ctx);   // the caller may reuse W immediately
+    return ssi_sync_internal(ctx);   // the caller may reuse W immediately
 }
 
-int64_t ssi_swa_columns(const ssi_ctx* ctx) { return ctx ? ctx->swa_K : -1; }
+int64_t ssi_swa_columns(const ssi_ctx* ctx) { return ctx ? (ctx->is_multi() ? ctx->children[0]->swa_K : ctx->swa_K) : -1; }
 
 // ---- on-device training step (the step before the path) ---------------------------------
 int ssi_train_begin(ssi_ctx* ctx, const float* W0, int32_t optimiser, double eta, double beta1, double beta2) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_FIRST_DEVICE(ctx, ssi_train_begin(ctx, W0, optimiser, eta, beta1, beta2));
     if (!W0) return ssi_fail(ctx, SSI_ERR_ARG, "W0 must be non-NULL");
     SSI_TRY(ssi_use_device(ctx));
     return ssi_train_begin_impl(ctx, W0, optimiser, eta, beta1, beta2);
@@ -579,6 +707,7 @@ int ssi_train_begin(ssi_ctx* ctx, const float* W0, int32_t optimiser, double eta
 
 int ssi_train_step(ssi_ctx* ctx, const int64_t* idx, int64_t j0, int64_t nb, double* loss_out) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_FIRST_DEVICE(ctx, ssi_train_step(ctx, idx, j0, nb, loss_out));
     SSI_TRY(ssi_use_device(ctx));
     call_timer t(ctx);
     const int rc = ssi_train_step_impl(ctx, idx, j0, nb, loss_out);
@@ -588,6 +717,7 @@ int ssi_train_step(ssi_ctx* ctx, const int64_t* idx, int64_t j0, int64_t nb, dou
 
 int ssi_train_snapshot(ssi_ctx* ctx, double n_scalar) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_FIRST_DEVICE(ctx, ssi_train_snapshot(ctx, n_scalar));
     const float* dW = ssi_train_weights_device(ctx);
     if (!dW) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_train_begin has not been called");
     if (ctx->swa_n != ctx->model.n) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin(n = %lld parameters) must precede ssi_train_snapshot", (long long)ctx->model.n);
@@ -600,16 +730,18 @@ int ssi_train_snapshot(ssi_ctx* ctx, double n_scalar) {
 
 int ssi_train_get_weights(ssi_ctx* ctx, float* W_out) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_FIRST_DEVICE(ctx, ssi_train_get_weights(ctx, W_out));
     const float* dW = ssi_train_weights_device(ctx);
     if (!dW) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_train_begin has not been called");
     if (!W_out) return ssi_fail(ctx, SSI_ERR_ARG, "W_out must be non-NULL");
     SSI_TRY(ssi_use_device(ctx));
     SSI_CUDA(ctx, cudaMemcpyAsync(W_out, dW, sizeof(float) * (size_t)ctx->model.n, cudaMemcpyDeviceToHost, ctx->stream));
-    return ssi_sync(ctx);
+    return ssi_sync_internal(ctx);
 }
 
 int ssi_train_end(ssi_ctx* ctx) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_FIRST_DEVICE(ctx, ssi_train_end(ctx));
     SSI_TRY(ssi_use_device(ctx));
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ssi_train_destroy(ctx);
@@ -625,9 +757,9 @@ static int swa_deliver(ssi_ctx* ctx, int M, float* dPout, double* ds, int sweeps
     if (W_swa_out) SSI_CUDA(ctx, cudaMemcpyAsync(W_swa_out, ctx->dSwaMean, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     if (P_out) SSI_CUDA(ctx, cudaMemcpyAsync(P_out, dPout, sizeof(float) * (size_t)n * M, cudaMemcpyDeviceToHost, ctx->stream));
     if (s_out) SSI_CUDA(ctx, cudaMemcpyAsync(s_out, ds, sizeof(double) * (size_t)K, cudaMemcpyDeviceToHost, ctx->stream));
-    SSI_TRY(ssi_sync(ctx));
+    SSI_TRY(ssi_sync_internal(ctx));
     ctx->stats.jacobi_sweeps = *sweeps;
-    if (*sweeps >= 60) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "Jacobi eigen-solver did not converge in %d sweeps", *sweeps);
+    if (*sweeps > 60) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "Jacobi eigen-solver did not converge in 60 sweeps");
     if (install) {
         if (!ctx->has_model || ctx->model.n != n)
             return ssi_fail(ctx, SSI_ERR_STATE, "install requested but the model (n=%lld) does not match the snapshots (n=%lld)",
@@ -650,6 +782,7 @@ static int swa_scratch(ssi_ctx* ctx, int M, float** dPout, double** ds) {
 
 int ssi_swa_finish(ssi_ctx* ctx, int32_t M, float* W_swa_out, float* P_out, double* s_out, int32_t install) {
     if (!ctx) return SSI_ERR_ARG;
+    if (ctx->is_multi()) return ssi_multi_swa_finish(ctx, M, W_swa_out, P_out, s_out, install);
     if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
     if (M < 1) return ssi_fail(ctx, SSI_ERR_ARG, "M must be positive");
     SSI_TRY(ssi_use_device(ctx));
@@ -666,6 +799,7 @@ int ssi_swa_finish(ssi_ctx* ctx, int32_t M, float* W_swa_out, float* P_out, doub
 
 int ssi_swa_gram_dev(ssi_ctx* ctx, double* dG_out, int32_t exact) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NO_MULTI(ctx, "device-pointer entry points");
     if (ctx->swa_n <= 0 || ctx->swa_K <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "no snapshots have been pushed");
     if (!dG_out) return ssi_fail(ctx, SSI_ERR_ARG, "G_out must be a device pointer to K x K doubles");
     SSI_TRY(ssi_use_device(ctx));
@@ -680,6 +814,7 @@ int ssi_swa_gram_dev(ssi_ctx* ctx, double* dG_out, int32_t exact) {
 int ssi_swa_finish_gram(ssi_ctx* ctx, int32_t M, const double* dG, int32_t gram_exact, float* W_swa_out, float* P_out,
                         double* s_out, int32_t install) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NO_MULTI(ctx, "device-pointer entry points");
     if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
     if (M < 1) return ssi_fail(ctx, SSI_ERR_ARG, "M must be positive");
     if (!dG) return ssi_fail(ctx, SSI_ERR_ARG, "G must be a device pointer to the (all-reduced) K x K Gram");

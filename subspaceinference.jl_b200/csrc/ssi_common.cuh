@@ -37,6 +37,10 @@ struct ssi_bm_state;   // basis path on the tensor cores (ssi_basis_mma.cu)
 struct ssi_train_state; // on-device training step (ssi_train.cu)
 
 struct ssi_ctx {
+    // A multi-device context (ssi_ctx_create_multi) owns one ordinary context per device and no device state of its own:
+    // set_* calls are replicated, batched calls are sharded by sample / chain index.
+    std::vector<ssi_ctx*> children;
+    bool is_multi() const { return !children.empty(); }
     int device = 0;
     int sm_count = 0;
     int cc_major = 0, cc_minor = 0;
@@ -44,6 +48,8 @@ struct ssi_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};   // boundaries of the stages of ssi_swa_finish
+    bool stage_pending = false;
     std::string err;
 
     // options
@@ -54,7 +60,7 @@ struct ssi_ctx {
     int opt_tc_k32 = 0;       // A-B: K-major bases always 32 columns wide
     int opt_tc_alast = 1;     // evict-first hint on the last read of a row block's activations (A-B: 0)
     int opt_tc_nokrev = 0;    // A-B: every feature tile reads the k-blocks in ascending order
-    int opt_tc_cluster = 0;   // A-B: GEMM layers with per-sample activations as 2-CTA clusters sharing the weight tiles by TMA multicast
+    int opt_tc_prec = 1;      // operand planes of the tensor path: 1 mixed BF16/FP16 (default), 0 BF16x3 (round 1)
     int opt_bm_nopack = 0, opt_bm_variant = 1;     // A-B inside k_b1_mma: unpacked operands; ReLU epilogue variant
     int opt_b1_simt = 0;       // A-B: BASIS path on CUDA cores (k_logpost_basis1h) instead of the tensor-core kernel (k_b1_mma)
     int opt_tc_simt_basis = 0; // A-B: first layer as the FP32 SIMT basis combination instead of the tensor-core one
@@ -79,6 +85,7 @@ struct ssi_ctx {
 
     // MH state
     ssi_buf_t bMhZ, bMhZp, bMhLp, bMhLpP, bMhCnt, bMhG;
+    int64_t mh_chains = 0;       // chains of the last run (ssi_mh_get_state)
 
     // SWA / construction state
     int64_t swa_n = 0, swa_Kmax = 0, swa_K = 0;
@@ -121,6 +128,13 @@ int ssi_fail(ssi_ctx* ctx, int code, const char* fmt, ...);
                             __FILE__, __LINE__, cudaGetErrorString(e__));                \
     } while (0)
 
+// entry points a multi-device context does not take (device pointers belong to one device)
+#define SSI_NO_MULTI(ctx, what)                                                          \
+    do {                                                                                 \
+        if ((ctx)->is_multi())                                                           \
+            return ssi_fail((ctx), SSI_ERR_UNSUPPORTED, "%s are not available on a multi-device context: use the host-pointer call", what); \
+    } while (0)
+
 #define SSI_TRY(expr)                                                                    \
     do {                                                                                 \
         int rc__ = (expr);                                                               \
@@ -135,6 +149,30 @@ int ssi_fail(ssi_ctx* ctx, int code, const char* fmt, ...);
 
 int ssi_reserve(ssi_ctx* ctx, ssi_buf_t& b, size_t bytes);
 int ssi_use_device(ssi_ctx* ctx);
+int ssi_sync_internal(ssi_ctx* ctx);     // stream sync + timers, without the public ssi_sync's range report
+
+// ---- multi-device dispatch (ssi_multi.cu) ------------------------------------------------
+int ssi_multi_create(const int32_t* devices, int32_t n_dev, ssi_ctx** out);
+int ssi_multi_destroy(ssi_ctx* ctx);
+int ssi_multi_sync(ssi_ctx* ctx);
+int ssi_multi_set_option(ssi_ctx* ctx, const char* key, int64_t value);
+int ssi_multi_stats(const ssi_ctx* ctx, ssi_stats_t* out);
+int ssi_multi_set_model(ssi_ctx* ctx, int n_layers, const int32_t* dims, const int32_t* act);
+int ssi_multi_set_data(ssi_ctx* ctx, const float* X, const float* Y, int64_t N);
+int ssi_multi_set_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, int64_t n, int32_t M);
+int ssi_multi_logpost(ssi_ctx* ctx, int grad, const float* Z, int64_t B, double sigma_m, double sigma_p, double sigma_z, uint32_t mask,
+                      double* lp_out, double* second_out);
+int ssi_multi_mh_run(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset, int64_t step_offset,
+                     double sigma_z, double sigma_m, double sigma_p, uint32_t mask, const float* z0,
+                     float* z_trace, double* lp_trace, uint8_t* accept_trace);
+int ssi_multi_mh_get_state(ssi_ctx* ctx, float* z_out, double* lp_out);
+int ssi_multi_project(ssi_ctx* ctx, const float* Z, int64_t B, float* W_out);
+int ssi_multi_swa_finish(ssi_ctx* ctx, int32_t M, float* W_swa_out, float* P_out, double* s_out, int32_t install);
+// per-device halves of the host-pointer MH entry points (ssi_api.cu)
+int ssi_mh_run_host_slice(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset, int64_t step_offset,
+                          double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* z0,
+                          float* z_trace, double* lp_trace, uint8_t* accept_trace, int64_t ld_chains, int64_t c0);
+int ssi_mh_get_state_slice(ssi_ctx* ctx, float* z_out, double* lp_out);
 
 // ---- entry points between translation units --------------------------------------------
 // log-posterior of B device-resident subspace points; d_lp (B) and optional d_terms (3 x B)
@@ -164,6 +202,8 @@ void ssi_tc_invalidate(ssi_ctx* ctx);
 void ssi_tc_destroy(ssi_ctx* ctx);
 // SSE (sum of squared errors) of B samples into d_sse (B doubles)
 int  ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse);
+// FP16 planes: has an evaluation since the last check left the calibrated range?  (synchronises; switches to BF16 planes)
+int  ssi_tc_range_exceeded(ssi_ctx* ctx, bool* exceeded);
 
 // basis path (ssi_basis.cu): Chain(Dense, Dense) with O <= 2, small M
 bool ssi_b1_supported(const ssi_ctx* ctx);

@@ -176,146 +176,139 @@ int ssi_subspace_gram(ssi_ctx* ctx) {
 }
 
 // ======================================================================================
-// K7: symmetric eigen-solve, parallel cyclic Jacobi (round-robin pairs), FP64, one CTA
+// K7: symmetric eigen-solve of the K x K Gram, FP64.
+//
+// One-sided (Hestenes) Jacobi on the COLUMNS of G: a rotation of columns (p, q) needs their three inner products
+// (|g_p|^2, |g_q|^2, g_p.g_q) and touches those two columns only, so a half warp owns a pair, the inner products are
+// shuffle reductions and ONE barrier per round-robin round is all the synchronisation there is (the two-sided solver of
+// round 1 rotated rows and columns: two block-wide barriers per round around a serial rotation-parameter phase, 3.9 us
+// per round, 4.6 ms at K = 100).  When the columns are mutually orthogonal, G V = U S with U = V for a symmetric
+// positive semi-definite G: column i has norm lambda_i and direction v_i.  Accuracy: the rotations are orthogonal to
+// working precision by construction (c = rsqrt(1 + t^2), s = t c), small columns are never mixed into large ones beyond
+// eps, and the wanted (largest) eigenpairs come out with relative accuracy eps * lambda_0 / lambda_i.
+//   K <= 160: one CTA, the matrix lives in shared memory.  Larger K (README's batchsize-1 loader gives K = 1000, SURVEY
+//   Q3): a cooperative grid with the matrix in global memory (L2-resident) and a grid barrier per round; no pair tables,
+//   so K is limited by memory only (ssi_swa_* accept K <= 16384).
 // ======================================================================================
-#define JAC_MAXPAIRS 1024
-#define JAC_W 64                       // threads along the fast (row) index of the rotation updates
-__global__ void __launch_bounds__(1024)
-k_jacobi(double* __restrict__ Ag /* K x K, destroyed */, double* __restrict__ Vg /* K x K out */, int K,
-         int max_sweeps, double* __restrict__ lambda /* K, sorted desc */, int* __restrict__ order /* K */,
-         int* __restrict__ sweeps_out, int use_smem) {
-    extern __shared__ double jac_smem[];
-    // both K x K matrices live in shared memory when they fit (K <= 104); the round-robin sweeps are
-    // latency bound, not bandwidth bound
-    // leading dimension: odd in shared memory so that the scattered (p, u) block accesses spread over the banks
-    const int ld = use_smem ? (K | 1) : K;
-    double* A = use_smem ? jac_smem : Ag;
-    double* V = use_smem ? jac_smem + (size_t)ld * K : Vg;
-    __shared__ double cs[JAC_MAXPAIRS], sn[JAC_MAXPAIRS];
-    __shared__ short pp[JAC_MAXPAIRS], qq[JAC_MAXPAIRS];
-    __shared__ double red[32];
-    __shared__ double s_off, s_tot;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int jx = tid & (JAC_W - 1), jy = tid / JAC_W, jrows = nt / JAC_W;
-    const int m = (K + 1) & ~1;          // even number of players; index K (if any) is a bye
-    const int np = m / 2;
-    const double tol = 4.0 * ((double)K * 2.220446049250313e-16) * ((double)K * 2.220446049250313e-16);
-
-    for (long long e = tid; e < (long long)K * K; e += nt) {
-        const int r = (int)(e % K), c = (int)(e / K);
-        V[r + (long long)c * ld] = (r == c) ? 1.0 : 0.0;
-        if (use_smem) A[r + (long long)c * ld] = Ag[e];
-    }
+#define OSJ_THREADS 1024
+#define OSJ_SMEM_KMAX 160
+#define OSJ_KMAX 16384
+__device__ __forceinline__ void osj_grid_barrier(unsigned* counter, unsigned& target, unsigned nblocks) {
     __syncthreads();
-
-    int sweep = 0;
-    for (; sweep < max_sweeps; ++sweep) {
-        // convergence: off-diagonal mass relative to the whole matrix
-        double off = 0.0, tot = 0.0;
-        for (long long e = tid; e < (long long)K * K; e += nt) {
-            const int r = (int)(e % K), c = (int)(e / K);
-            const double v = A[r + (long long)c * ld];
-            tot += v * v;
-            if (r != c) off += v * v;
+    if (nblocks > 1) {
+        if (threadIdx.x == 0) {
+            target += nblocks;
+            __threadfence();
+            atomicAdd(counter, 1u);
+            while (*reinterpret_cast<volatile unsigned*>(counter) < target) { }
+            __threadfence();
         }
-        off = ssi_block_sum(off, red);
-        if (tid == 0) s_off = off;
-        tot = ssi_block_sum(tot, red);
-        if (tid == 0) s_tot = tot;
         __syncthreads();
-        if (s_off <= tol * s_tot || s_tot == 0.0) break;
+    }
+}
 
+__global__ void __launch_bounds__(OSJ_THREADS)
+k_osj(double* __restrict__ Gg /* K x K column-major; on exit the rotated columns G V */, int K, int max_sweeps,
+      unsigned* __restrict__ sync_counter /* zeroed */, unsigned* __restrict__ rot_count /* [3], zeroed */,
+      int* __restrict__ sweeps_out, int use_smem) {
+    extern __shared__ double osj_smem[];
+    double* G = use_smem ? osj_smem : Gg;
+    __shared__ double red[32];
+    __shared__ double s_null;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const unsigned nb = gridDim.x;
+    unsigned target = 0;
+    // columns whose squared norm is below (K eps trace)^2 are numerically in the null space: pairs of two such columns
+    // are left alone (they are never among the wanted directions)
+    double tr = 0.0;
+    for (int i = tid; i < K; i += nt) tr += fabs(Gg[i + (long long)i * K]);
+    tr = ssi_block_sum(tr, red);
+    if (tid == 0) { const double e = (double)K * 2.220446049250313e-16 * tr; s_null = e * e; }
+    if (use_smem)
+        for (long long e = tid; e < (long long)K * K; e += nt) G[e] = Gg[e];
+    __syncthreads();
+    const double nul = s_null;
+    const double tol = (double)K * 2.220446049250313e-16, tol2 = tol * tol;
+
+    const int m = (K + 1) & ~1;                  // even number of players; index K (if any) is a bye
+    const int np = m / 2;
+    const int hw = (blockIdx.x * nt + tid) >> 4, n_hw = (nb * nt) >> 4;      // half warps: one per column pair
+    const int hl = tid & 15;
+    const unsigned hmask = 0xffffu << (tid & 16);
+    int sweep = 0;
+    bool converged = false;
+    for (; sweep < max_sweeps; ++sweep) {
+        unsigned* cnt = rot_count + (sweep % 3);
+        if (blockIdx.x == 0 && tid == 0) rot_count[(sweep + 1) % 3] = 0;       // next sweep's counter (idle since sweep - 2)
         for (int r = 0; r < m - 1; ++r) {
-            // pairs of this round + their rotations
-            for (int i = tid; i < np; i += nt) {
+            for (int i = hw; i < np; i += n_hw) {
                 int p, q;
                 if (i == 0) { p = m - 1; q = r; }
                 else { p = (r + i) % (m - 1); q = (r - i + (m - 1)) % (m - 1); }
                 if (p > q) { const int t = p; p = q; q = t; }
-                double c = 1.0, s = 0.0;
-                if (q < K) {
-                    const double apq = A[p + (long long)q * ld];
-                    const double app = A[p + (long long)p * ld], aqq = A[q + (long long)q * ld];
-                    // a rotation that cannot change the diagonal at working precision is skipped (c = 1, s = 0 exactly), and
-                    // so is every 2x2 block update whose two rotations are both the identity: late sweeps touch little
-                    if (fabs(apq) > 1.1102230246251565e-16 * sqrt(fabs(app * aqq))) {
-                        const double tau = (aqq - app) / (2.0 * apq);
-                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                        c = 1.0 / sqrt(1.0 + t * t);
-                        s = t * c;
-                    }
-                } else {
-                    q = -1;     // bye
+                if (q >= K) continue;                                       // bye
+                double* gp = G + (long long)p * K;
+                double* gq = G + (long long)q * K;
+                double a = 0.0, b = 0.0, c = 0.0;
+                for (int k = hl; k < K; k += 16) {
+                    const double x = gp[k], y = gq[k];
+                    a = fma(x, x, a); b = fma(y, y, b); c = fma(x, y, c);
                 }
-                pp[i] = (short)p; qq[i] = (short)q; cs[i] = c; sn[i] = s;
-            }
-            __syncthreads();
-            // A <- J' A J, one 2x2 block per (pair_k, pair_l): no cross-block hazards.  Threads are laid out
-            // (jx = pair_k fastest, jy = pair_l): consecutive pairs own consecutive rows p (and q), so a warp's
-            // accesses to a column are contiguous in shared memory.
-            for (int il = jy; il < np; il += jrows) {
-                const int u = pp[il], v = qq[il];
-                const double cl = cs[il], sl = sn[il];
-                double* Au = A + u * ld;
-                double* Av = A + (v < 0 ? u : v) * ld;
-                for (int ik = jx; ik < np; ik += JAC_W) {
-                    const int p = pp[ik], q = qq[ik];
-                    const double ck = cs[ik], sk = sn[ik];
-                    if (q < 0 && v < 0) continue;
-                    if (sk == 0.0 && sl == 0.0) continue;
-                    if (q < 0) {            // single row p, columns (u,v): only the column rotation
-                        const double a = Au[p], b = Av[p];
-                        Au[p] = cl * a - sl * b;
-                        Av[p] = sl * a + cl * b;
-                    } else if (v < 0) {     // rows (p,q), single column u: only the row rotation
-                        const double a = Au[p], b = Au[q];
-                        Au[p] = ck * a - sk * b;
-                        Au[q] = sk * a + ck * b;
-                    } else {
-                        const double a_pu = Au[p], a_pv = Av[p], a_qu = Au[q], a_qv = Av[q];
-                        // columns (A J_l)
-                        const double t_pu = cl * a_pu - sl * a_pv, t_pv = sl * a_pu + cl * a_pv;
-                        const double t_qu = cl * a_qu - sl * a_qv, t_qv = sl * a_qu + cl * a_qv;
-                        // rows (J_k' .)
-                        Au[p] = ck * t_pu - sk * t_qu;
-                        Au[q] = sk * t_pu + ck * t_qu;
-                        Av[p] = ck * t_pv - sk * t_qv;
-                        Av[q] = sk * t_pv + ck * t_qv;
-                    }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(hmask, a, o);
+                    b += __shfl_xor_sync(hmask, b, o);
+                    c += __shfl_xor_sync(hmask, c, o);
                 }
-            }
-            // V <- V J   (jx = row k fastest: contiguous column accesses)
-            for (int il = jy; il < np; il += jrows) {
-                const int u = pp[il], v = qq[il];
-                if (v < 0) continue;
-                const double cl = cs[il], sl = sn[il];
-                if (sl == 0.0) continue;
-                double* Vu = V + u * ld;
-                double* Vv = V + v * ld;
-                for (int k = jx; k < K; k += JAC_W) {
-                    const double a = Vu[k], b = Vv[k];
-                    Vu[k] = cl * a - sl * b;
-                    Vv[k] = sl * a + cl * b;
+                if (c * c <= tol2 * a * b || (a < nul && b < nul)) continue;
+                // tan(theta) of the rotation that makes the two columns orthogonal; c^2 + s^2 = 1 to working precision
+                const double d = b - a, h = 2.0 * c;
+                const double rr = sqrt(fma(d, d, h * h));
+                const double t = h / (d + (d >= 0.0 ? rr : -rr));
+                const double cs = rsqrt(fma(t, t, 1.0)), sn = t * cs;
+                for (int k = hl; k < K; k += 16) {
+                    const double x = gp[k], y = gq[k];
+                    gp[k] = cs * x - sn * y;
+                    gq[k] = sn * x + cs * y;
                 }
+                if (hl == 0) atomicAdd(cnt, 1u);
             }
-            __syncthreads();
+            osj_grid_barrier(sync_counter, target, nb);
         }
+        // every rotation of this sweep has been counted before the last barrier of the sweep
+        if (*reinterpret_cast<volatile unsigned*>(cnt) == 0u) { ++sweep; converged = true; break; }
     }
-    __syncthreads();
-    // rank sort of the diagonal, descending (ties by index)
-    for (int i = tid; i < K; i += nt) {
-        const double li = A[i + (long long)i * ld];
-        int rank = 0;
-        for (int j = 0; j < K; ++j) {
-            const double lj = A[j + (long long)j * ld];
-            rank += (lj > li) || (lj == li && j < i);
-        }
-        lambda[rank] = li;
-        order[rank] = i;
-    }
-    if (tid == 0) *sweeps_out = sweep;
     if (use_smem)
-        for (long long e = tid; e < (long long)K * K; e += nt) Vg[e] = V[(e % K) + (e / K) * ld];
+        for (long long e = tid; e < (long long)K * K; e += nt) Gg[e] = G[e];
+    // sweeps executed (the last one without a rotation), or max_sweeps + 1 when the last sweep still rotated
+    if (blockIdx.x == 0 && tid == 0) *sweeps_out = converged ? sweep : max_sweeps + 1;
+}
+
+// eigenvalues = norms of the orthogonalised columns, rank-sorted descending (ties by index); eigenvectors = the
+// normalised columns, written to V (K x K).  One warp per column, then one thread per eigenvalue.
+__global__ void __launch_bounds__(256)
+k_osj_norms(const double* __restrict__ G, int K, double* __restrict__ norms) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= K) return;
+    double a = 0.0;
+    for (int k = lane; k < K; k += 32) { const double x = G[k + (long long)c * K]; a = fma(x, x, a); }
+    a = ssi_warp_sum(a);
+    if (lane == 0) norms[c] = sqrt(a);
+}
+__global__ void __launch_bounds__(256)
+k_osj_sort_normalise(double* __restrict__ G, int K, const double* __restrict__ norms, double* __restrict__ lambda, int* __restrict__ order,
+                     double* __restrict__ V) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= K) return;
+    const double li = norms[c];
+    int rank = 0;
+    for (int j = lane; j < K; j += 32) { const double lj = norms[j]; rank += (lj > li) || (lj == li && j < c); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    if (lane == 0) { lambda[rank] = li; order[rank] = c; }
+    // the eigenvector keeps the sign of its largest component positive?  No: signs are arbitrary, as psvd's are
+    const double inv = li > 0.0 ? 1.0 / li : 0.0;
+    for (int k = lane; k < K; k += 32) V[k + (long long)c * K] = G[k + (long long)c * K] * inv;
 }
 
 // ======================================================================================
@@ -484,17 +477,18 @@ __global__ void k_singular_values(const double* __restrict__ lambda, int K, doub
 // GPUs: every rank runs the gram stage on its row shard, the host all-reduces the K x K Gram, every rank
 // runs the (replicated) eigen stage and forms the P rows of its shard.
 struct swa_eig_t {
-    double *dG, *dV, *dLam, *dRisk;
+    double *dG, *dV, *dLam, *dRisk, *dNorms;
     int *dOrder, *dSweeps;
 };
 static int swa_eig_layout(ssi_ctx* ctx, int K, swa_eig_t& e) {
-    // layout of bEig: G (K*K) | V (K*K) | lambda (K) | risk | order (K ints) | sweeps (int)
+    // layout of bEig: G (K*K) | V (K*K) | lambda (K) | norms (K) | risk | order (K ints) | sweeps (int) | 4 counters
     const size_t KK = (size_t)K * K;
-    SSI_TRY(ssi_reserve(ctx, ctx->bEig, sizeof(double) * (2 * KK + K + 1) + sizeof(int) * (K + 2)));
+    SSI_TRY(ssi_reserve(ctx, ctx->bEig, sizeof(double) * (2 * KK + 2 * K + 1) + sizeof(int) * (K + 8)));
     e.dG = (double*)ctx->bEig.p;
     e.dV = e.dG + KK;
     e.dLam = e.dV + KK;
-    e.dRisk = e.dLam + K;
+    e.dNorms = e.dLam + K;
+    e.dRisk = e.dNorms + K;
     e.dOrder = (int*)(e.dRisk + 1);
     e.dSweeps = e.dOrder + K;
     return SSI_OK;
@@ -504,7 +498,7 @@ static int swa_check_shape(ssi_ctx* ctx, int M) {
     if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
     if (K < M) return ssi_fail(ctx, SSI_ERR_RANK, "deviation matrix has %d columns, cannot take M=%d", K, M);
     if (M > SSI_MAX_M) return ssi_fail(ctx, SSI_ERR_ARG, "M=%d exceeds the supported maximum %d", M, SSI_MAX_M);
-    if (K > 2 * JAC_MAXPAIRS) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "K=%d exceeds the eigen-solver limit %d", K, 2 * JAC_MAXPAIRS);
+    if (K > OSJ_KMAX) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "K=%d exceeds the eigen-solver limit %d", K, OSJ_KMAX);
     return SSI_OK;
 }
 
@@ -521,14 +515,37 @@ int ssi_swa_gram_stage(ssi_ctx* ctx, bool exact, double* dG_dst, bool* used_tens
 // of a tensor-core Gram and reports through *need_exact whether the Gram has to be recomputed exactly (synchronises).
 int ssi_swa_eigen_stage(ssi_ctx* ctx, int M, const double* dG_src, bool check, bool* need_exact) {
     const int K = (int)ctx->swa_K;
+    // every caller comes through here (single-GPU finish and the row-sharded ssi_swa_finish_gram)
+    if (K > OSJ_KMAX) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "K=%d exceeds the eigen-solver limit %d", K, OSJ_KMAX);
     swa_eig_t e;
     SSI_TRY(swa_eig_layout(ctx, K, e));
     if (dG_src != e.dG)
         SSI_CUDA(ctx, cudaMemcpyAsync(e.dG, dG_src, sizeof(double) * (size_t)K * K, cudaMemcpyDeviceToDevice, ctx->stream));
-    const size_t jsm = 2 * sizeof(double) * (size_t)(K | 1) * K;
-    const int use_smem = jsm + 24 * 1024 <= ctx->smem_optin;
-    if (use_smem) SSI_CUDA(ctx, cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm));
-    k_jacobi<<<1, 1024, use_smem ? jsm : 0, ctx->stream>>>(e.dG, e.dV, K, 60, e.dLam, e.dOrder, e.dSweeps, use_smem);
+    // one-sided Jacobi: in shared memory on one CTA for small K, else a cooperative grid on the matrix in global memory
+    unsigned* d_sync = reinterpret_cast<unsigned*>(e.dSweeps + 1);       // [sync counter | 3 rotation counters]
+    SSI_CUDA(ctx, cudaMemsetAsync(d_sync, 0, 4 * sizeof(unsigned), ctx->stream));
+    const int use_smem = K <= OSJ_SMEM_KMAX;
+    const size_t jsm = use_smem ? sizeof(double) * (size_t)K * K : 0;
+    if (jsm > 48 * 1024) SSI_CUDA(ctx, cudaFuncSetAttribute(k_osj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm));
+    int grid = 1;
+    if (!use_smem) {
+        const int np = (K + 1) / 2;
+        grid = std::max(1, std::min(ctx->sm_count, (np * 16 + OSJ_THREADS - 1) / OSJ_THREADS));
+    }
+    {
+        double* Gp = e.dG;
+        int Kv = K, ms = 60, us = use_smem;
+        unsigned* sc = d_sync;
+        unsigned* rc = d_sync + 1;
+        int* so = e.dSweeps;
+        void* args[] = {&Gp, &Kv, &ms, &sc, &rc, &so, &us};
+        if (grid > 1) SSI_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_osj, dim3(grid), dim3(OSJ_THREADS), args, jsm, ctx->stream));
+        else SSI_CUDA(ctx, cudaLaunchKernel((const void*)k_osj, dim3(1), dim3(OSJ_THREADS), args, jsm, ctx->stream));
+    }
+    SSI_LAUNCH_CHECK(ctx);
+    k_osj_norms<<<(K * 32 + 255) / 256, 256, 0, ctx->stream>>>(e.dG, K, e.dNorms);
+    SSI_LAUNCH_CHECK(ctx);
+    k_osj_sort_normalise<<<(K * 32 + 255) / 256, 256, 0, ctx->stream>>>(e.dG, K, e.dNorms, e.dLam, e.dOrder, e.dV);
     SSI_LAUNCH_CHECK(ctx);
     if (need_exact) *need_exact = false;
     if (!check) return SSI_OK;
@@ -579,14 +596,24 @@ int ssi_swa_factor_device(ssi_ctx* ctx, int M, float* dP_out, double* d_s, int* 
     swa_eig_t e;
     SSI_TRY(swa_eig_layout(ctx, (int)ctx->swa_K, e));
     ctx->stats.gram_risk = 0.0;
+    for (cudaEvent_t& ev : ctx->ev_stage)
+        if (!ev) SSI_CUDA(ctx, cudaEventCreate(&ev));
     bool tensor = false, need_exact = false;
+    cudaEventRecord(ctx->ev_stage[0], ctx->stream);
     SSI_TRY(ssi_swa_gram_stage(ctx, ctx->opt_gram_fp64 > 0, e.dG, &tensor));
+    cudaEventRecord(ctx->ev_stage[1], ctx->stream);
     SSI_TRY(ssi_swa_eigen_stage(ctx, M, e.dG, tensor, &need_exact));
     ctx->stats.gram_path = tensor ? 2 : 1;
-    if (need_exact) {
+    if (need_exact) {        // the stage times then describe the exact pass
+        cudaEventRecord(ctx->ev_stage[0], ctx->stream);
         SSI_TRY(ssi_swa_gram_stage(ctx, true, e.dG, nullptr));
+        cudaEventRecord(ctx->ev_stage[1], ctx->stream);
         SSI_TRY(ssi_swa_eigen_stage(ctx, M, e.dG, false, nullptr));
         ctx->stats.gram_path = 3;
     }
-    return ssi_swa_p_stage(ctx, M, dP_out, d_s, sweeps_host);
+    cudaEventRecord(ctx->ev_stage[2], ctx->stream);
+    const int rc = ssi_swa_p_stage(ctx, M, dP_out, d_s, sweeps_host);
+    cudaEventRecord(ctx->ev_stage[3], ctx->stream);
+    ctx->stage_pending = true;
+    return rc;
 }

@@ -72,12 +72,12 @@ k_mh_accept(float* __restrict__ z, const float* __restrict__ zp, double* __restr
             for (int m = 0; m < M; ++m) z[m + c * M] = zp[m + c * M];
             if (g) for (int m = 0; m < M; ++m) g[m + c * M] = gp[m + c * M];
         }
-        if (z_trace) {
-            float* dst = z_trace + ((long long)step * n_chains + c) * M;
+        if (z_trace) {            // the trace pointers address this step's row
+            float* dst = z_trace + c * M;
             for (int m = 0; m < M; ++m) dst[m] = z[m + c * M];
         }
-        if (lp_trace) lp_trace[(long long)step * n_chains + c] = lp[c];
-        if (acc_trace) acc_trace[(long long)step * n_chains + c] = acc ? 1 : 0;
+        if (lp_trace) lp_trace[c] = lp[c];
+        if (acc_trace) acc_trace[c] = acc ? 1 : 0;
         accepted = (acc && !force) ? 1u : 0u;
     }
     const unsigned warp_cnt = __popc(__ballot_sync(0xffffffffu, accepted));
@@ -88,13 +88,18 @@ k_mh_accept(float* __restrict__ z, const float* __restrict__ zp, double* __restr
 //   `MALA(x -> MvNormal((sigma_z^2 / 2) .* x, sigma_z))`, init_params = rand(MvNormal(zeros(M), sigma_z))): the proposal is
 //   z' = z + (sigma_z^2/2) grad lp(z) + sigma_z eps, accepted iff -e < lp' - lp + log q(z|z') - log q(z'|z); value and
 //   gradient of every chain's proposal come from one batched reverse pass (ssi_logpost_grad_device) per step.
-int ssi_mh_device(ssi_ctx* ctx, int kind, int64_t C, int64_t S, uint64_t seed, int64_t chain_off,
+// step0 > 0 continues chains (checkpoint / resume): d_z0 is then the state after step step0 - 1, its
+// log-density (and gradient) is re-evaluated -- the evaluation is deterministic and batch-invariant, so the continued run
+// is bit-identical to an uninterrupted one -- and steps step0 .. step0 + S - 1 draw from the Philox counters of those
+// steps; trace row t - step0 receives step t.
+int ssi_mh_device(ssi_ctx* ctx, int kind, int64_t C, int64_t S, uint64_t seed, int64_t chain_off, int64_t step0,
                   double sigma_z, double sigma_m, double sigma_p, uint32_t mask,
                   const float* d_z0, float* d_ztr, double* d_lptr, uint8_t* d_acctr) {
     if (!ctx->has_model || !ctx->has_data || !ctx->has_sub)
         return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before sampling");
     if (C <= 0 || S <= 0) return ssi_fail(ctx, SSI_ERR_ARG, "n_chains and n_steps must be positive");
-    if (chain_off < 0 || chain_off + C > 0xffffffffll || S > 0xffffffffll)
+    if (step0 < 0 || (step0 > 0 && !d_z0)) return ssi_fail(ctx, SSI_ERR_ARG, "a continued run (step_offset > 0) needs the chain state z");
+    if (chain_off < 0 || chain_off + C > 0xffffffffll || step0 + S > 0xffffffffll)
         return ssi_fail(ctx, SSI_ERR_ARG, "chain ids and steps must fit 32 bits");
     const int M = ctx->M;
     SSI_TRY(ssi_reserve(ctx, ctx->bMhZ, sizeof(float) * (size_t)M * C));
@@ -121,7 +126,19 @@ int ssi_mh_device(ssi_ctx* ctx, int kind, int64_t C, int64_t S, uint64_t seed, i
     const unsigned g_acc = (unsigned)((C + 255) / 256);
     double units = 0, flops = 0;
 
-    for (int64_t t = 0; t < S; ++t) {
+    if (step0 > 0) {
+        // re-establish (z, lp[, grad]) of the saved state: evaluate it as a proposal and force-accept it without a trace row
+        SSI_CUDA(ctx, cudaMemcpyAsync(zp, d_z0, sizeof(float) * (size_t)M * C, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (kind == 1) SSI_TRY(ssi_logpost_grad_device(ctx, zp, C, sigma_m, sigma_p, sigma_z, mask, lpp, gp));
+        else SSI_TRY(ssi_logpost_device(ctx, zp, C, sigma_m, sigma_p, sigma_z, mask, lpp, nullptr));
+        units += ctx->stats.last_units;
+        flops += ctx->stats.last_flops;
+        k_mh_accept<<<g_acc, 256, 0, ctx->stream>>>(z, zp, lp, lpp, C, M, seed, chain_off, 0u, 1, nullptr, nullptr, nullptr, cnt, g, gp,
+                                                  half_s2, inv2s2);
+        SSI_LAUNCH_CHECK(ctx);
+    }
+    for (int64_t i = 0; i < S; ++i) {
+        const int64_t t = step0 + i;
         if (t == 0 && d_z0) {
             SSI_CUDA(ctx, cudaMemcpyAsync(zp, d_z0, sizeof(float) * (size_t)M * C, cudaMemcpyDeviceToDevice, ctx->stream));
         } else {
@@ -132,13 +149,16 @@ int ssi_mh_device(ssi_ctx* ctx, int kind, int64_t C, int64_t S, uint64_t seed, i
         else SSI_TRY(ssi_logpost_device(ctx, zp, C, sigma_m, sigma_p, sigma_z, mask, lpp, nullptr));
         units += ctx->stats.last_units;
         flops += ctx->stats.last_flops;
+        // trace row i of this call = step t of the chain
         k_mh_accept<<<g_acc, 256, 0, ctx->stream>>>(z, zp, lp, lpp, C, M, seed, chain_off, (unsigned)t, t == 0,
-                                                  d_ztr, d_lptr, d_acctr, cnt, g, gp, half_s2, inv2s2);
+                                                  d_ztr ? d_ztr + (size_t)i * C * M : nullptr, d_lptr ? d_lptr + (size_t)i * C : nullptr,
+                                                  d_acctr ? d_acctr + (size_t)i * C : nullptr, cnt, g, gp, half_s2, inv2s2);
         SSI_LAUNCH_CHECK(ctx);
     }
     ctx->stats.last_units = units;
     ctx->stats.last_flops = flops;
-    ctx->stats.mh_proposals = C * (S - 1);
+    ctx->stats.mh_proposals = C * (S - (step0 == 0 ? 1 : 0));
+    ctx->mh_chains = C;
     return SSI_OK;
 }
 

@@ -61,15 +61,6 @@ __device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const CUtensorMap
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
         : "memory");
 }
-// the same load delivered to the same shared-memory offset (and mbarrier) of every CTA of the cluster named in cta_mask
-__device__ __forceinline__ void tma_load_3d_multicast_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                                           uint16_t cta_mask, uint64_t pol) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint "
-        "[%0], [%1, {%3, %4, %5}], [%2], %6, %7;"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask), "l"(pol)
-        : "memory");
-}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -103,11 +94,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         : "memory");
 }
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
-// arrive on the mbarrier at this offset in every CTA of cta_mask once the MMAs issued so far have retired
-__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(cta_mask) : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -205,8 +191,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
     return d;
 }
 // instruction descriptor, kind::f16: D=F32, A=B=BF16, both K-major, M=128, N=n
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
+__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// the same with the two operand formats chosen independently (bits [7,10) = A, [10,13) = B: 0 = F16, 1 = BF16)
+#define UMMA_FMT_F16 0u
+#define UMMA_FMT_BF16 1u
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16(int n, uint32_t a_fmt, uint32_t b_fmt) {
+    return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 

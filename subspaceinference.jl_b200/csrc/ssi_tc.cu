@@ -12,10 +12,24 @@
 // Every Dense layer is one launch of the same warp-specialised GEMM; hidden widths and the
 // input width are zero-padded to multiples of 64, so any Dense chain is supported.
 //
-// Precision: tcgen05 has no FP32-input mode.  Every FP32 operand x is split into
-// hi = bf16(x), lo = bf16(x - hi) and each product is issued as hi*hi + hi*lo + lo*hi with FP32
-// accumulation in TMEM ("BF16x3").  Measured against the Float64 oracle this keeps lp within
-// ~2e-7 relative (tolerance 1e-5); the roofline denominator is therefore 1/3 of the BF16 peak.
+// Precision: tcgen05 has no FP32-input mode.  Every FP32 operand x is split into two 16-bit planes
+// hi + lo and each product is issued as hi*hi + hi*lo + lo*hi with FP32 accumulation in TMEM: three
+// kind::f16 MMAs per product, so the roofline denominator is 1/3 of the BF16 peak.  Two plane formats
+// (option "tc_precision"):
+//   1 (default) "FP16x3": both planes FP16 (11 + 11 mantissa bits, representation error 2^-24 and a dropped lo*lo term
+//      of 2^-24 against 2^-18 for BF16 planes: FP32-grade products from the same three MMAs), every operand scaled by a
+//      power of two so that it sits high in FP16's range; the scales are undone exactly in the epilogue.
+//        weights      per (layer, sample) 2^jw from a rigorous bound |W_swa| + sum_m |z_m| |P_m| <= 2^14: cannot overflow;
+//        bases, X     one scale from their exact maximum (known when they are built);
+//        z            per sample, from its own largest component;
+//        activations  range unknown until they are computed: one scale per layer from a calibration pass at z = 0
+//                     (run once per (data, subspace) with BF16 planes) that maps the largest activation to [2^9, 2^10),
+//                     i.e. 64x..128x of headroom; conversions saturate; every plane-writing kernel tracks the largest
+//                     activation it wrote, and a call that exceeded FP16's range is REPEATED with BF16 planes
+//                     (ssi_tc_range_exceeded, checked where the host entry points synchronise anyway).
+//      (kind::f16 encodes the formats of A and B separately, but mixing them -- BF16 activations against FP16 weights,
+//      which would need no calibration -- raises an illegal-instruction fault on sm_100a: measured.)
+//   0 "BF16x3": hi = bf16(x), lo = bf16(x - hi) for both operands (round 1; the fallback, and kept for A-B runs).
 //
 // Orientation: D[m, n] = sum_k A[m, k] B[n, k] with m = datapoint (128 per tile, TMEM lane),
 // n = output feature (BN per tile, TMEM column), k = input feature.  A = activations
@@ -46,9 +60,11 @@ struct tc_params {
     int a_il;               // A operand planes interleaved per k-block: row = [kb][hi 64 | lo 64] (the basis layer's output)
     int stages, stage_bytes;
     int mt_block;           // > 0: work order (mt block, sample, mt in block) so that concurrently running CTAs share A tiles
-    int mt_pad;             // > 0 (cluster mode): work w = (sample w / mt_pad, row block w % mt_pad), mt_pad = m_tiles rounded up to
-                            // even so that the two CTAs of a cluster always hold the same sample; row block m_tiles is a dummy
     int n_work;
+    uint32_t idesc;         // instruction descriptor (operand format: FP16 or BF16 planes)
+    float a_scale;          // 2^ja of the NEXT layer's A planes, applied to this layer's output before it is split (1 for BF16x3)
+    float* amax;            // HIDDEN: running max |activation| this layer has written (range check of the FP16 planes)
+    const float* winv;      // [G] 2^-(jw_g + ja_in): accumulator -> true pre-activation (nullptr: 1)
     const float* bias;      // [G][width]  (width = padded out width of this layer)
     const float* Y;         // FINAL / FUSED: O x N column-major
     int O;                  // FINAL / FUSED: true output width
@@ -58,10 +74,14 @@ struct tc_params {
     double* partials;       // FINAL / FUSED: [G][m_tiles*4]
 };
 
-#define TC_MODE_HIDDEN 0    // store split-BF16 activations with TMA
+#define TC_MODE_HIDDEN 0    // store the split activations with TMA
 #define TC_MODE_FINAL  1    // this GEMM is the output layer: squared error in the epilogue
 #define TC_MODE_FUSED  2    // last hidden layer; the (narrow) output layer and the squared error are folded into the epilogue
 #define TC_OP 12            // FUSED: padded output width
+#define TC_PREC_BF16X3 0
+#define TC_PREC_FP16X3 1
+#define TC_F16_MAX 65504.0f
+#define TC_CAL_TOP 9        // calibration maps the largest activation seen at z = 0 to [2^TC_CAL_TOP, 2^(TC_CAL_TOP + 1))
 static int tc_smem_total(int mode) {
     return TC_SMEM_PIPE + 3072 + (mode == TC_MODE_HIDDEN ? TC_SMEM_STORE : (mode == TC_MODE_FUSED ? 2 * 256 * TC_OP * 4 : 0));
 }
@@ -71,18 +91,11 @@ static int tc_smem_total(int mode) {
 //   bias[2][256] floats, 12 mbarriers, TMEM base address
 //   staging area (last, size depends on the mode): HIDDEN per-warp TMA-store staging (32 KB);
 //   FUSED output-layer weight slices [2][256][TC_OP] (24 KB); FINAL nothing.
-// FUSED/FINAL leave >= 7 KB of the SM's 228 KB unused on purpose: the memory-bound basis-layer kernel of the NEXT
-// group (no shared memory, 1 KB reserved per CTA) is co-scheduled on the same SMs from a second stream.
 #define TC_OFF_BIAS TC_SMEM_PIPE
 #define TC_OFF_BAR (TC_OFF_BIAS + 2 * 256 * 4)
 #define TC_OFF_STORE (TC_OFF_BIAS + 3072)
 
 __device__ __forceinline__ bool tc_decode_work(const tc_params& p, int w, int& g, int& mt) {
-    if (p.mt_pad > 0) {
-        g = w / p.mt_pad;
-        mt = w - g * p.mt_pad;
-        return true;            // the dummy row block runs the whole protocol on out-of-range rows (TMA zero fill, masked epilogue)
-    }
     if (p.mt_block > 0) {
         const int per = p.G * p.mt_block;
         const int blk = w / per, rem = w - blk * per;
@@ -107,12 +120,46 @@ __device__ __forceinline__ float tc_act(float v) {
 
 __device__ __noinline__ float tc_act_rt(float v, int act) { return ssi_act(v, act); }
 
-// CL (option "tc_cluster", off by default): CTAs run as clusters of two that walk the same (sample, feature tile, k-block)
-// sequence on adjacent row blocks; each CTA fetches HALF of every weight tile and TMA multicasts it into both CTAs' shared
-// memory (weights are 2/3 of the bytes that cross L2 -> SM), and a stage is released to the producers when the MMAs of BOTH
-// CTAs have retired.  Measured on the wide config, same box, power-capped: 39.8 ms per launch against 38.0 ms without --
-// a third less L2 -> SM traffic buys no clock, and the lock step of the pair costs 4.7 %.
-template <int MODE, int ACT, bool CL>
+// ---- the two 16-bit planes of an operand ------------------------------------------------
+// Two values at a time.  FP16X3: the caller has applied the power-of-two scale; hi = FP16 (saturating: a value beyond the
+// calibrated range must not become Inf), lo = FP16 of the exact remainder.  BF16X3: both planes BF16.
+template <int PREC>
+__device__ __forceinline__ void tc_split_a2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    if (PREC == TC_PREC_FP16X3) {
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+    } else {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+        const float2 hf = __bfloat1622float2(h2);
+        hi = *reinterpret_cast<const uint32_t*>(&h2);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+        lo = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+}
+// one value, run-time format (the small preparation kernels): kind 0 = BF16 | BF16, 1 = FP16 | FP16 (saturating; the
+// caller's scale keeps |x| below 2^15 whenever the range is known)
+__device__ __forceinline__ void tc_split1(float x, int kind, unsigned short& hi, unsigned short& lo) {
+    if (kind == 1) {
+        const __half h = __float2half_rn(fminf(fmaxf(x, -TC_F16_MAX), TC_F16_MAX));
+        const __half l = __float2half_rn(x - __half2float(h));
+        hi = __half_as_ushort(h);
+        lo = __half_as_ushort(l);
+    } else {
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        hi = __bfloat16_as_ushort(h);
+        lo = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(h)));
+    }
+}
+// largest |activation| a plane-writing kernel has produced (true value, before the scale): non-negative floats order like
+// their bit patterns
+__device__ __forceinline__ void tc_amax_commit(float* amax, float mx) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && amax && mx > 0.0f) atomicMax(reinterpret_cast<unsigned*>(amax), __float_as_uint(mx));
+}
+
+template <int MODE, int ACT, int PREC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
            const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -133,7 +180,7 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
 
     if (threadIdx.x == 0) {
         if (smem_base & 1023u) { printf("ssi_tc: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
-        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL ? 2 : 1); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 128); }
         fence_barrier_init();
         tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
@@ -142,10 +189,8 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
     if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
     tc_fence_before();
     __syncthreads();
-    if (CL) cluster_sync_all();          // the peer's barriers are initialised before anything is multicast into this CTA
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
-    const uint32_t crank = CL ? cluster_ctarank() : 0;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -172,15 +217,8 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                         const uint64_t pa = (p.a_last_first && !p.a_shared && nt == p.n_tiles - 1) ? TC_EVICT_FIRST : pol_a;
                         tma_load_3d_hint(sA, &tmAh, full, ka, mt * TC_BM, p.a_shared ? 0 : g, pa);
                         tma_load_3d_hint(sA + a_bytes, &tmAl, full, p.a_il ? ka + TC_BK : ka, mt * TC_BM, p.a_shared ? 0 : g, pa);
-                        if (CL) {
-                            // this CTA's half of the rows of each weight plane, delivered to both CTAs (the maps' box is BN/2 rows)
-                            const uint32_t ho = crank * (b_bytes / 2);
-                            tma_load_3d_multicast_hint(sA + 2 * a_bytes + ho, &tmBh, full, kbe * TC_BK, nt * BN + (int)crank * (BN / 2), g, 3, TC_EVICT_LAST);
-                            tma_load_3d_multicast_hint(sA + 2 * a_bytes + b_bytes + ho, &tmBl, full, kbe * TC_BK, nt * BN + (int)crank * (BN / 2), g, 3, TC_EVICT_LAST);
-                        } else {
-                            tma_load_3d_hint(sA + 2 * a_bytes, &tmBh, full, kbe * TC_BK, nt * BN, g, TC_EVICT_LAST);
-                            tma_load_3d_hint(sA + 2 * a_bytes + b_bytes, &tmBl, full, kbe * TC_BK, nt * BN, g, TC_EVICT_LAST);
-                        }
+                        tma_load_3d_hint(sA + 2 * a_bytes, &tmBh, full, kbe * TC_BK, nt * BN, g, TC_EVICT_LAST);
+                        tma_load_3d_hint(sA + 2 * a_bytes + b_bytes, &tmBl, full, kbe * TC_BK, nt * BN, g, TC_EVICT_LAST);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -189,7 +227,7 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(BN);
+            const uint32_t idesc = p.idesc;
             int stage = 0;
             uint32_t phase = 0;
             uint32_t tile = 0;
@@ -214,8 +252,7 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                             umma_bf16(d_tmem, ah + ko, bl + ko, idesc, 1);
                             umma_bf16(d_tmem, al + ko, bh + ko, idesc, 1);
                         }
-                        if (CL) umma_commit_multicast(bar_empty + 8 * stage, 3);   // both CTAs' producers write this slot of both CTAs
-                        else umma_commit(bar_empty + 8 * stage);        // frees the smem slot when the MMAs retire
+                        umma_commit(bar_empty + 8 * stage);             // frees the smem slot when the MMAs retire
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(bar_tfull + 8 * ab);                   // accumulator complete -> epilogue
@@ -229,11 +266,14 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
         // HIDDEN: this warp's TMA-store staging: [2 buffers][hi | lo][32 rows x 64 B], SWIZZLE_64B
         const uint32_t stage_w = smem_base + TC_OFF_STORE + (uint32_t)(warp - 2) * 8192;
         const uint32_t swz = (uint32_t)((lane >> 1) & 3);
+        const float asc = p.a_scale;
+        float amx = 0.0f;                            // HIDDEN: largest |activation| this thread has written
         uint32_t chunk_ctr = 0;
         uint32_t tile = 0;
         for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
             int g, mt;
             if (!tc_decode_work(p, w, g, mt)) continue;
+            const float inv = p.winv ? p.winv[g] : 1.0f;     // exact power of two: undoes the operand scales
             double sse = 0.0;
             // FUSED: 4 rows per thread (see tmem_ld_16x256b_x8), partial sums over this thread's columns
             float pred[4][TC_OP];
@@ -272,7 +312,7 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                             for (int j = 0; j < 16; ++j) {
                                 const int o = nt * BN + c0 + j;
                                 if (o < p.O) {
-                                    const float df = tc_act<ACT>(__uint_as_float(v[j]) + sb[c0 + j]) - p.Y[o + m * p.O];
+                                    const float df = tc_act<ACT>(fmaf(__uint_as_float(v[j]), inv, sb[c0 + j])) - p.Y[o + m * p.O];
                                     sse += (double)df * (double)df;
                                 }
                             }
@@ -299,10 +339,10 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                                     const float4 ww = w4[o4];
                                     wv[4 * o4] = ww.x; wv[4 * o4 + 1] = ww.y; wv[4 * o4 + 2] = ww.z; wv[4 * o4 + 3] = ww.w;
                                 }
-                                const float h0 = tc_act<ACT>(__uint_as_float(v0[4 * i + e]) + b);
-                                const float h1 = tc_act<ACT>(__uint_as_float(v0[4 * i + 2 + e]) + b);
-                                const float h2 = tc_act<ACT>(__uint_as_float(v1[4 * i + e]) + b);
-                                const float h3 = tc_act<ACT>(__uint_as_float(v1[4 * i + 2 + e]) + b);
+                                const float h0 = tc_act<ACT>(fmaf(__uint_as_float(v0[4 * i + e]), inv, b));
+                                const float h1 = tc_act<ACT>(fmaf(__uint_as_float(v0[4 * i + 2 + e]), inv, b));
+                                const float h2 = tc_act<ACT>(fmaf(__uint_as_float(v1[4 * i + e]), inv, b));
+                                const float h3 = tc_act<ACT>(fmaf(__uint_as_float(v1[4 * i + 2 + e]), inv, b));
 #pragma unroll
                                 for (int o = 0; o < TC_OP; ++o) {
                                     pred[0][o] = fmaf(h0, wv[o], pred[0][o]);
@@ -322,13 +362,10 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
-                            const float x0 = tc_act<ACT>(__uint_as_float(v[j]) + sb[c0 + j]);
-                            const float x1 = tc_act<ACT>(__uint_as_float(v[j + 1]) + sb[c0 + j + 1]);
-                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-                            const float2 hf = __bfloat1622float2(h2);
-                            const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
-                            hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-                            lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+                            const float x0 = tc_act<ACT>(fmaf(__uint_as_float(v[j]), inv, sb[c0 + j]));
+                            const float x1 = tc_act<ACT>(fmaf(__uint_as_float(v[j + 1]), inv, sb[c0 + j + 1]));
+                            amx = fmaxf(amx, fmaxf(fabsf(x0), fabsf(x1)));
+                            tc_split_a2<PREC>(x0 * asc, x1 * asc, hi[j >> 1], lo[j >> 1]);
                         }
                         // the TMA store that last read this staging buffer (two chunks ago) must have finished reading
                         if (chunk_ctr >= 2) {
@@ -388,12 +425,14 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                 if (lane == 0 && mt < p.m_tiles) p.partials[(long long)g * (p.m_tiles * 4) + mt * 4 + q] = sse;
             }
         }
-        if (MODE == TC_MODE_HIDDEN && lane == 0) tma_store_wait_all();
+        if (MODE == TC_MODE_HIDDEN) {
+            tc_amax_commit(p.amax, amx);
+            if (lane == 0) tma_store_wait_all();
+        }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (CL) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -403,22 +442,63 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------
 // operand preparation
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
-    hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
-
-// X (in0 x N column-major == [N][in0]) -> Xh, Xl [N][Kp] (zero padded)
+// X (in0 x N column-major == [N][in0]) -> Xh, Xl [N][Kp] (zero padded); kind 0 (BF16 planes) or 1 (FP16 planes, scaled by 2^ja from max |X|)
 __global__ void __launch_bounds__(256)
-k_tc_split_x(const float* __restrict__ X, long long N, int in0, int Kp, bf16* __restrict__ Xh, bf16* __restrict__ Xl) {
+k_tc_split_x(const float* __restrict__ X, long long N, int in0, int Kp, int kind, float scale, bf16* __restrict__ Xh, bf16* __restrict__ Xl) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= N * Kp) return;
     const long long j = e / Kp;
     const int i = (int)(e % Kp);
-    bf16 hi, lo;
-    split_bf16(i < in0 ? X[j * in0 + i] : 0.0f, hi, lo);
-    Xh[e] = hi;
-    Xl[e] = lo;
+    unsigned short hi, lo;
+    tc_split1((i < in0 ? X[j * in0 + i] : 0.0f) * scale, kind, hi, lo);
+    reinterpret_cast<unsigned short*>(Xh)[e] = hi;
+    reinterpret_cast<unsigned short*>(Xl)[e] = lo;
+}
+
+// ---- FP16 planes: power-of-two scales of the weight operands ------------------------------------------------------
+// cmax[l][m] = max |column m of [P | W_swa]| over the flat range of layer l's weight matrix (once per subspace)
+__global__ void __launch_bounds__(256)
+k_tc_colmax(const float* __restrict__ PW /* n x (M+1) */, long long n, long long w_off, long long count, float* __restrict__ out) {
+    __shared__ float red[8];
+    const float* col = PW + (long long)blockIdx.x * n + w_off;
+    float mx = 0.0f;
+    for (long long e = threadIdx.x; e < count; e += blockDim.x) mx = fmaxf(mx, fabsf(col[e]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+        out[blockIdx.x] = mx;
+    }
+}
+// Per (layer, sample): bound = cmax[M] + sum_m |z_m| cmax[m] >= max |W_swa + P z| over the layer; the scale 2^jw puts the
+// bound in [2^13, 2^14), so the FP16 hi plane cannot overflow and a sample's scale depends on nothing but its own z
+// (bitwise batch invariance).  wscale[l][g] = 2^jw, winv[l][g] = 2^-(jw + ja).
+struct tc_ja_t { int v[SSI_MAX_LAYERS + 1]; };      // exponent of the scale of the A planes layer l consumes
+__global__ void k_tc_wscale(const float* __restrict__ Z, int M, int G, const float* __restrict__ cmax /* [nl][M+1] */, int nl, int gstride,
+                            const tc_ja_t ja_in, float* __restrict__ wscale, float* __restrict__ winv) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nl * G) return;
+    const int l = t / G, g = t % G;
+    const int ja = ja_in.v[l];
+    const float* cm = cmax + l * (M + 1);
+    float bound = cm[M];
+    for (int m = 0; m < M; ++m) bound = fmaf(fabsf(Z[m + (long long)g * M]), cm[m], bound);
+    int jw = 0;
+    if (bound > 0.0f && bound < 3.0e38f) jw = 13 - ilogbf(bound);
+    jw = max(-100, min(100, jw));
+    wscale[l * gstride + g] = scalbnf(1.0f, jw);
+    winv[l * gstride + g] = scalbnf(1.0f, -(jw + ja));
+}
+// max |x| of a float array into *out (one atomicMax on the bit pattern; *out zeroed by the caller)
+__global__ void __launch_bounds__(256)
+k_tc_absmax(const float* __restrict__ x, long long count, unsigned* __restrict__ out) {
+    float mx = 0.0f;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) mx = fmaxf(mx, fabsf(x[e]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.0f) atomicMax(out, __float_as_uint(mx));
 }
 
 // One Dense weight matrix of the group: flat (out x in, column-major: o + i*out) -> split BF16 [g][o][Kp],
@@ -430,14 +510,18 @@ k_tc_split_x(const float* __restrict__ X, long long N, int in0, int Kp, bf16* __
 __global__ void __launch_bounds__(256)
 k_tc_project_w(const float* __restrict__ Wswa, const float* __restrict__ P, const float* __restrict__ Z,
                long long n, int M, int G, long long w_off, int in, int out, int out_pad, int Kp,
+               const float* __restrict__ wscale /* [G] power-of-two scales (mixed planes) or nullptr */,
                bf16* __restrict__ Wh, bf16* __restrict__ Wl) {
     __shared__ __align__(16) float zs[SSI_MAX_M][TC_GMAX];                 // [m][g], zero for g >= G
-    __shared__ __align__(16) bf16 sh[TC_GMAX][PW_T][PW_T], sl[TC_GMAX][PW_T][PW_T];   // [g][o][i]
+    __shared__ __align__(16) unsigned short sh[TC_GMAX][PW_T][PW_T], sl[TC_GMAX][PW_T][PW_T];   // [g][o][i]
+    __shared__ float sc[TC_GMAX];
     const int tx = threadIdx.x & (PW_T - 1), ty = threadIdx.x >> 4;
     for (int e = threadIdx.x; e < M * TC_GMAX; e += 256) {
         const int m = e / TC_GMAX, g = e % TC_GMAX;
         zs[m][g] = g < G ? Z[m + g * M] : 0.0f;
     }
+    if (threadIdx.x < TC_GMAX) sc[threadIdx.x] = (wscale && threadIdx.x < G) ? wscale[threadIdx.x] : 1.0f;
+    const int kind = wscale ? 1 : 0;
     __syncthreads();
     const int i0 = blockIdx.x * PW_T, o0 = blockIdx.y * PW_T;
     const int i = i0 + ty, o = o0 + tx;
@@ -468,8 +552,8 @@ k_tc_project_w(const float* __restrict__ Wswa, const float* __restrict__ P, cons
     }
 #pragma unroll
     for (int g = 0; g < TC_GMAX; ++g) {
-        bf16 hi, lo;
-        split_bf16(acc[g], hi, lo);
+        unsigned short hi, lo;
+        tc_split1(acc[g] * sc[g], kind, hi, lo);
         sh[g][tx][ty] = hi;
         sl[g][tx][ty] = lo;
     }
@@ -563,15 +647,16 @@ template <int ACT, int MP>
 __global__ void __launch_bounds__(TC_BASIS_THREADS)
 k_tc_basis_layer(const float* __restrict__ bases /* [M+1][NW] */, long long NW, int M, int G,
                  const float* __restrict__ zpack /* [TC_GMAX][SSI_MAX_M], zero padded */,
-                 bf16* __restrict__ Hh, bf16* __restrict__ Hl /* [g][NW] */) {
+                 bf16* __restrict__ Hh, bf16* __restrict__ Hl /* [g][NW] */, int fp16, float a_scale, float* __restrict__ amax) {
     __shared__ __align__(16) float zs[TC_GMAX][MP];
     for (int e = threadIdx.x; e < TC_GMAX * MP; e += TC_BASIS_THREADS) zs[e / MP][e % MP] = zpack[(e / MP) * SSI_MAX_M + (e % MP)];
     __syncthreads();
     const long long base = (long long)blockIdx.x * (TC_BASIS_THREADS * TC_BASIS_ITERS * 2);
+    float amx = 0.0f;
 #pragma unroll 1
     for (int it = 0; it < TC_BASIS_ITERS; ++it) {
         const long long e = base + ((long long)it * TC_BASIS_THREADS + threadIdx.x) * 2;
-        if (e >= NW) break;
+        if (e >= NW) break;          // leaves the loop only: the whole warp meets again at tc_amax_commit
         float2 b[MP];
 #pragma unroll
         for (int m = 0; m < MP; ++m)
@@ -590,15 +675,17 @@ k_tc_basis_layer(const float* __restrict__ bases /* [M+1][NW] */, long long NW, 
             }
             const float x0 = tc_act<ACT>(x.x);
             const float x1 = tc_act<ACT>(x.y);
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-            const float2 hf = __bfloat1622float2(h2);
-            const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+            amx = fmaxf(amx, fmaxf(fabsf(x0), fabsf(x1)));
+            uint32_t h2, l2;
+            if (fp16) tc_split_a2<TC_PREC_FP16X3>(x0 * a_scale, x1 * a_scale, h2, l2);
+            else tc_split_a2<TC_PREC_BF16X3>(x0, x1, h2, l2);
             // interleaved output: 64 hi then 64 lo halves per block of 64 activations (see k_tc_basis_mma)
             bf16* o = Hh + 2 * ((long long)g * NW + (e & ~63ll)) + (e & 63);
-            __stcs(reinterpret_cast<unsigned int*>(o), *reinterpret_cast<const unsigned int*>(&h2));
-            __stcs(reinterpret_cast<unsigned int*>(o + 64), *reinterpret_cast<const unsigned int*>(&l2));
+            __stcs(reinterpret_cast<unsigned int*>(o), h2);
+            __stcs(reinterpret_cast<unsigned int*>(o + 64), l2);
         }
     }
+    tc_amax_commit(amax, amx);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -621,11 +708,15 @@ k_tc_basis_layer(const float* __restrict__ bases /* [M+1][NW] */, long long NW, 
 #define TB_OFF_BAR (TB_OFF_STORE + 4 * TB_SBUF * 8192)
 #define TB_SMEM_TOTAL (TB_OFF_BAR + 16 * 8 + 16)
 
-template <int ACT>
+// FP16 planes (PREC 1): row s of z carries its own scale 2^jz_s (from the sample's largest component), the bases one
+// scale 2^jb (from max |bases|): zinv[s] = 2^-(jz_s + jb) turns lane s of an accumulator into the true pre-activation;
+// a_scale is the calibrated scale of the activations that are split and stored; amax tracks the largest one written.
+template <int ACT, int PREC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__ CUtensorMap tmZl,
                const __grid_constant__ CUtensorMap tmTh, const __grid_constant__ CUtensorMap tmTl,
-               const __grid_constant__ CUtensorMap tmO, const int n_tiles) {
+               const __grid_constant__ CUtensorMap tmO, const int n_tiles, const float* __restrict__ zinv, const float a_scale,
+               float* __restrict__ amax) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + TB_OFF_BAR);     // full[4] empty[4] tfull[2] tempty[2] zfull
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
@@ -668,7 +759,7 @@ k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(TB_N);
+            const uint32_t idesc = PREC == TC_PREC_FP16X3 ? umma_idesc_f16(TB_N, UMMA_FMT_F16, UMMA_FMT_F16) : umma_idesc_bf16(TB_N);
             mbar_wait(bar_z, 0);
             tc_fence_after();
             const uint64_t zh = umma_desc_sw64(smem_base + TB_OFF_Z), zl = umma_desc_sw64(smem_base + TB_OFF_Z + 128 * 64);
@@ -709,6 +800,8 @@ k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__
         // and slows from 32.0 to 34.3 / 34.5 ms per 128 samples (DRAM reads 57 -> 75 GB), a net loss.
         const uint32_t stage_w = smem_base + TB_OFF_STORE + (uint32_t)(warp - 2) * (TB_SBUF * 8192);
         const uint32_t swz_h = (uint32_t)((2 * lane) & 7), swz_l = (uint32_t)((2 * lane + 1) & 7);     // SWIZZLE_128B: chunk ^ (row & 7)
+        const float pre_inv = zinv ? zinv[q * 32 + lane] : 1.0f;      // this thread's sample (TMEM lane)
+        float amx = 0.0f;
         uint32_t chunk_ctr = 0, tile = 0, sbuf = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile) {
             const uint32_t ab = tile & 1, aphase = (tile >> 1) & 1;
@@ -732,13 +825,10 @@ k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
-                        const float x0 = tc_act<ACT>(__uint_as_float(v[j]));
-                        const float x1 = tc_act<ACT>(__uint_as_float(v[j + 1]));
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-                        const float2 hf = __bfloat1622float2(h2);
-                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
-                        hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-                        lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+                        const float x0 = tc_act<ACT>(__uint_as_float(v[j]) * pre_inv);       // powers of two: exact
+                        const float x1 = tc_act<ACT>(__uint_as_float(v[j + 1]) * pre_inv);
+                        amx = fmaxf(amx, fmaxf(fabsf(x0), fabsf(x1)));
+                        tc_split_a2<PREC>(x0 * a_scale, x1 * a_scale, hi[j >> 1], lo[j >> 1]);
                     }
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -759,6 +849,7 @@ k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * ab);
         }
+        tc_amax_commit(amax, amx);
         if (lane == 0) tma_store_wait_all();
     }
     tc_fence_before();
@@ -769,30 +860,43 @@ k_tc_basis_mma(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__
     }
 }
 
-// zaug[s][m] = z[m, s] (m < M), 1 (m == M: the W_swa basis), 0 (padding and s >= G), split BF16, [128][32]
-__global__ void k_tc_pack_zaug(const float* __restrict__ Z, int M, int G, bf16* __restrict__ zh, bf16* __restrict__ zl) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 128 * 32) return;
-    const int s = t >> 5, m = t & 31;
-    const float v = s < G ? (m < M ? Z[m + s * M] : (m == M ? 1.0f : 0.0f)) : 0.0f;
-    bf16 hi, lo;
-    split_bf16(v, hi, lo);
-    zh[t] = hi;
-    zl[t] = lo;
+// zaug[s][m] = z[m, s] (m < M), 1 (m == M: the W_swa basis), 0 (padding and s >= G), split into two planes, [128][32].
+// kind 0: BF16 planes.  kind 1: FP16 planes, row s scaled by 2^jz_s with max(1, max_m |z_ms|) * 2^jz_s in [2^13, 2^14) -- a
+// function of the sample alone (bitwise batch invariance); zinv[s] = 2^-jz_s * bases_inv.  One warp per sample.
+__global__ void k_tc_pack_zaug(const float* __restrict__ Z, int M, int G, int kind, float bases_inv, bf16* __restrict__ zh, bf16* __restrict__ zl,
+                               float* __restrict__ zinv) {
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), m = threadIdx.x & 31;
+    if (s >= 128) return;
+    const float v = s < G ? (m < M ? Z[m + (long long)s * M] : (m == M ? 1.0f : 0.0f)) : 0.0f;
+    float scale = 1.0f;
+    if (kind == 1) {
+        float mx = fabsf(v);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        int jz = 0;
+        if (mx > 0.0f && mx < 3.0e38f) jz = max(-100, min(100, 13 - ilogbf(mx)));
+        scale = scalbnf(1.0f, jz);
+        if (m == 0) zinv[s] = scalbnf(1.0f, -jz) * bases_inv;
+    }
+    unsigned short hi, lo;
+    tc_split1(v * scale, kind, hi, lo);
+    reinterpret_cast<unsigned short*>(zh)[s * 32 + m] = hi;
+    reinterpret_cast<unsigned short*>(zl)[s * 32 + m] = lo;
 }
 
-// basesT[e][m] (K-major, KT BF16 per activation e, split hi / lo)  <-  bases[m][e] FP32, m <= M.  KT = 24 when M + 1 <= 24 (48-byte
+// basesT[e][m] (K-major, KT 16-bit values per activation e, two planes)  <-  bases[m][e] FP32, m <= M.  KT = 24 when M + 1 <= 24 (48-byte
 // rows; the TMA box stays 32 wide and the 8 columns past the tensor's edge arrive as zeros), else 32: the kernel that reads
-// this stream is HBM-bound and a quarter of a 32-wide row would be padding for M = 20.
+// this stream is HBM-bound and a quarter of a 32-wide row would be padding for M = 20.  kind 0: BF16 planes; 1: FP16 planes
+// scaled by 2^jb so that max |bases| < 2^14.
 __global__ void __launch_bounds__(256)
-k_tc_bases_kmajor(const float* __restrict__ bases, long long NW, int M1, int KT, bf16* __restrict__ th, bf16* __restrict__ tl) {
+k_tc_bases_kmajor(const float* __restrict__ bases, long long NW, int M1, int KT, int kind, float scale, bf16* __restrict__ th, bf16* __restrict__ tl) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= NW) return;
-    __align__(16) bf16 hi[32], lo[32];
+    __align__(16) unsigned short hi[32], lo[32];
 #pragma unroll
     for (int m = 0; m < 32; ++m) {
         const float v = m < M1 ? bases[(long long)m * NW + e] : 0.0f;
-        split_bf16(v, hi[m], lo[m]);
+        tc_split1(v * scale, kind, hi[m], lo[m]);
     }
     uint4* dh = reinterpret_cast<uint4*>(th + e * KT);
     uint4* dl = reinterpret_cast<uint4*>(tl + e * KT);
@@ -811,12 +915,12 @@ __global__ void k_tc_pack_z(const float* __restrict__ Z, int M, int G, float* __
 
 template <int MP>
 static void tc_launch_basis(int act, unsigned blocks, cudaStream_t st, const float* bases, long long NW, int M, int G, const float* zpack,
-                            bf16* Hh, bf16* Hl) {
+                            bf16* Hh, bf16* Hl, int fp16, float a_scale, float* amax) {
     switch (act) {
-        case SSI_ACT_RELU:    k_tc_basis_layer<SSI_ACT_RELU, MP><<<blocks, TC_BASIS_THREADS, 0, st>>>(bases, NW, M, G, zpack, Hh, Hl); break;
-        case SSI_ACT_TANH:    k_tc_basis_layer<SSI_ACT_TANH, MP><<<blocks, TC_BASIS_THREADS, 0, st>>>(bases, NW, M, G, zpack, Hh, Hl); break;
-        case SSI_ACT_SIGMOID: k_tc_basis_layer<SSI_ACT_SIGMOID, MP><<<blocks, TC_BASIS_THREADS, 0, st>>>(bases, NW, M, G, zpack, Hh, Hl); break;
-        default:              k_tc_basis_layer<SSI_ACT_IDENTITY, MP><<<blocks, TC_BASIS_THREADS, 0, st>>>(bases, NW, M, G, zpack, Hh, Hl); break;
+        case SSI_ACT_RELU:    k_tc_basis_layer<SSI_ACT_RELU, MP><<<blocks, TC_BASIS_THREADS, 0, st>>>(bases, NW, M, G, zpack, Hh, Hl, fp16, a_scale, amax); break;
+        case SSI_ACT_TANH:    k_tc_basis_layer<SSI_ACT_TANH, MP><<<blocks, TC_BASIS_THREADS, 0, st>>>(bases, NW, M, G, zpack, Hh, Hl, fp16, a_scale, amax); break;
+        case SSI_ACT_SIGMOID: k_tc_basis_layer<SSI_ACT_SIGMOID, MP><<<blocks, TC_BASIS_THREADS, 0, st>>>(bases, NW, M, G, zpack, Hh, Hl, fp16, a_scale, amax); break;
+        default:              k_tc_basis_layer<SSI_ACT_IDENTITY, MP><<<blocks, TC_BASIS_THREADS, 0, st>>>(bases, NW, M, G, zpack, Hh, Hl, fp16, a_scale, amax); break;
     }
 }
 
@@ -829,6 +933,10 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 struct ssi_tc_state {
     bool ready = false;
+    int prec = TC_PREC_FP16X3;           // plane formats in use (option "tc_precision"; BF16X3 after a range fallback)
+    bool fallback = false;               // an evaluation exceeded FP16's range: this (data, subspace) stays on BF16 planes
+    tc_ja_t ja_in{};                     // FP16 planes: exponent of the scale of the A planes GEMM layer l consumes
+    float* amax = nullptr;               // [SSI_MAX_LAYERS + 1] largest |activation| written into the A planes of layer l
     int nl = 0;                          // GEMM launches per group: L, or L-1 when the output layer is fused
     bool fused_out = false;              // output layer folded into the last hidden layer's epilogue (O <= TC_OP)
     bool basis = false;                  // first layer = affine-in-z combination of precomputed bases (k_tc_basis_layer)
@@ -844,29 +952,34 @@ struct ssi_tc_state {
     bf16 *Wh[SSI_MAX_LAYERS] = {nullptr}, *Wl[SSI_MAX_LAYERS] = {nullptr};
     float* bias[SSI_MAX_LAYERS] = {nullptr};
     bf16 *Hh[2] = {nullptr, nullptr}, *Hl[2] = {nullptr, nullptr};
+    // FP16 planes: column maxima of [P | W_swa] per GEMM layer, per-sample weight scales and their inverses [nl][G],
+    // per-sample inverse scales of the first-layer GEMM [128]
+    float *cmax = nullptr, *wscale = nullptr, *winv = nullptr, *zinv = nullptr;
+    float bases_scale = 1.0f;            // 2^jb of the K-major bases (FP16 planes)
     // basis-layer output [G][N][width0] (hi, lo) and its tensor maps as the A operand of the first GEMM layer
     bf16* Bh = nullptr;                      // basis layer output [G][N][width/64][hi 64 | lo 64] (planes interleaved per k-block)
     CUtensorMap tmBasisH, tmBasisL;
-    // basis layer on the tensor cores (k_tc_basis_mma): K-major split-BF16 bases [N*width0][32], z of the group [128][32]
+    // basis layer on the tensor cores (k_tc_basis_mma): K-major two-plane bases [N*width0][KT], z of the group [128][32]
     bool basis_mma = false;
     bf16 *Th = nullptr, *Tl = nullptr, *Zh = nullptr, *Zl = nullptr;
     CUtensorMap tmZh, tmZl, tmTh, tmTl, tmO;
     int KT = 32;                             // columns per row of Th / Tl (24 or 32)
     double* partials = nullptr;
     CUtensorMap tmAh[SSI_MAX_LAYERS], tmAl[SSI_MAX_LAYERS], tmBh[SSI_MAX_LAYERS], tmBl[SSI_MAX_LAYERS];
-    CUtensorMap tmBh2[SSI_MAX_LAYERS], tmBl2[SSI_MAX_LAYERS];     // boxes of BN/2 rows (cluster mode)
     CUtensorMap tmSh[SSI_MAX_LAYERS], tmSl[SSI_MAX_LAYERS];
     PFN_encodeTiled encode = nullptr;
 };
 
 static void tc_free(ssi_tc_state* s) {
     cudaFree(s->Xh); cudaFree(s->Xl); cudaFree(s->partials); cudaFree(s->Wout); cudaFree(s->bout); cudaFree(s->bases); cudaFree(s->zpack);
+    cudaFree(s->cmax); cudaFree(s->wscale); cudaFree(s->winv); cudaFree(s->zinv); cudaFree(s->amax);
     for (int i = 0; i < 2; ++i) { cudaFree(s->Hh[i]); cudaFree(s->Hl[i]); }
     cudaFree(s->Bh); cudaFree(s->Th); cudaFree(s->Tl); cudaFree(s->Zh); cudaFree(s->Zl);
     for (int l = 0; l < SSI_MAX_LAYERS; ++l) { cudaFree(s->Wh[l]); cudaFree(s->Wl[l]); cudaFree(s->bias[l]); }
     PFN_encodeTiled enc = s->encode;
     *s = ssi_tc_state();
     s->encode = enc;
+    (void)cudaGetLastError();
 }
 
 void ssi_tc_invalidate(ssi_ctx* ctx) {
@@ -904,19 +1017,35 @@ bool ssi_tc_preferred(const ssi_ctx* ctx) {
 
 typedef void (*tc_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                             const CUtensorMap, const tc_params);
-template <int MODE>
-static tc_kernel_t tc_kernel_for_act(int act, bool cl) {
+// only the HIDDEN epilogue writes operand planes: the other modes have one instantiation per activation
+template <int MODE, int PREC>
+static tc_kernel_t tc_kernel_for_act(int act) {
     switch (act) {
-        case SSI_ACT_RELU:    return cl ? k_tc_layer<MODE, SSI_ACT_RELU, true> : k_tc_layer<MODE, SSI_ACT_RELU, false>;
-        case SSI_ACT_TANH:    return cl ? k_tc_layer<MODE, SSI_ACT_TANH, true> : k_tc_layer<MODE, SSI_ACT_TANH, false>;
-        case SSI_ACT_SIGMOID: return cl ? k_tc_layer<MODE, SSI_ACT_SIGMOID, true> : k_tc_layer<MODE, SSI_ACT_SIGMOID, false>;
-        default:              return cl ? k_tc_layer<MODE, SSI_ACT_IDENTITY, true> : k_tc_layer<MODE, SSI_ACT_IDENTITY, false>;
+        case SSI_ACT_RELU:    return k_tc_layer<MODE, SSI_ACT_RELU, PREC>;
+        case SSI_ACT_TANH:    return k_tc_layer<MODE, SSI_ACT_TANH, PREC>;
+        case SSI_ACT_SIGMOID: return k_tc_layer<MODE, SSI_ACT_SIGMOID, PREC>;
+        default:              return k_tc_layer<MODE, SSI_ACT_IDENTITY, PREC>;
     }
 }
-static tc_kernel_t tc_kernel(int mode, int act, bool cl = false) {
-    if (mode == TC_MODE_FUSED) return tc_kernel_for_act<TC_MODE_FUSED>(act, cl);
-    if (mode == TC_MODE_FINAL) return tc_kernel_for_act<TC_MODE_FINAL>(act, cl);
-    return tc_kernel_for_act<TC_MODE_HIDDEN>(act, cl);
+static tc_kernel_t tc_kernel(int mode, int act, int prec) {
+    if (mode == TC_MODE_FUSED) return tc_kernel_for_act<TC_MODE_FUSED, 0>(act);
+    if (mode == TC_MODE_FINAL) return tc_kernel_for_act<TC_MODE_FINAL, 0>(act);
+    return prec == TC_PREC_FP16X3 ? tc_kernel_for_act<TC_MODE_HIDDEN, TC_PREC_FP16X3>(act) : tc_kernel_for_act<TC_MODE_HIDDEN, TC_PREC_BF16X3>(act);
+}
+
+typedef void (*tb_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const int,
+                            const float*, const float, float*);
+template <int PREC>
+static tb_kernel_t tb_kernel_for_act(int act) {
+    switch (act) {
+        case SSI_ACT_RELU:    return k_tc_basis_mma<SSI_ACT_RELU, PREC>;
+        case SSI_ACT_TANH:    return k_tc_basis_mma<SSI_ACT_TANH, PREC>;
+        case SSI_ACT_SIGMOID: return k_tc_basis_mma<SSI_ACT_SIGMOID, PREC>;
+        default:              return k_tc_basis_mma<SSI_ACT_IDENTITY, PREC>;
+    }
+}
+static tb_kernel_t tb_kernel(int act, int prec) {
+    return prec == TC_PREC_FP16X3 ? tb_kernel_for_act<TC_PREC_FP16X3>(act) : tb_kernel_for_act<TC_PREC_BF16X3>(act);
 }
 
 static int tc_make_map(ssi_ctx* ctx, CUtensorMap* map, void* base, uint64_t inner, uint64_t rows, uint64_t batch,
@@ -925,10 +1054,134 @@ static int tc_make_map(ssi_ctx* ctx, CUtensorMap* map, void* base, uint64_t inne
     cuuint64_t strides[2] = {inner * sizeof(bf16), inner * rows * sizeof(bf16)};
     cuuint32_t box[3] = {box_inner, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
+    // the planes hold BF16 or FP16 bit patterns; TMA only moves 16-bit elements (out-of-bounds elements are zero filled)
     const CUresult r = ctx->tc->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr,
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return ssi_fail(ctx, SSI_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SSI_OK;
+}
+
+// device memory of the tensor path for a group of G samples (bytes), given whether the first layer runs on the bases
+static double tc_group_bytes(const ssi_ctx* ctx, bool basis, int G) {
+    const ssi_model_t& m = ctx->model;
+    const double N = (double)ctx->N;
+    const int l0 = basis ? 1 : 0;
+    const bool fused = (m.L - l0 >= 2 && m.dims[m.L] <= TC_OP && !ctx->opt_tc_nofuse);
+    const int nl = fused ? m.L - 1 : m.L;
+    double bytes = 0, maxw = 0;
+    for (int l = l0; l < nl; ++l) {
+        const double kp = (m.dims[l] + 63) / 64 * 64;
+        const double w = (l == m.L - 1) ? (m.dims[l + 1] + 15) / 16 * 16 : (m.dims[l + 1] + 63) / 64 * 64;
+        bytes += 4.0 * G * w * kp + 4.0 * G * w;                      // two weight planes + bias
+        if (l < nl - 1) maxw = std::max(maxw, w);
+    }
+    const int stored = std::max(0, nl - 1 - l0);                      // GEMM layers whose activations are stored
+    bytes += 4.0 * G * N * maxw * std::min(stored, 2);                // ping-pong buffers, two planes each
+    if (basis) bytes += 4.0 * G * N * ((m.dims[1] + 63) / 64 * 64);   // the basis layer's output
+    return bytes;
+}
+
+int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse);
+
+static int tc_exp_for(float mx, int top) {       // 2^j with mx * 2^j in [2^top, 2^(top + 1))
+    if (!(mx > 0.0f) || !(mx < 3.0e38f)) return 0;
+    return std::max(-100, std::min(100, top - ilogbf(mx)));
+}
+
+// max |x| of a device array (synchronises)
+static int tc_absmax_host(ssi_ctx* ctx, const float* d, long long count, float* out) {
+    unsigned* d_mx = reinterpret_cast<unsigned*>(ctx->tc->amax + SSI_MAX_LAYERS);      // last slot: scratch outside calibrated layers
+    SSI_CUDA(ctx, cudaMemsetAsync(d_mx, 0, sizeof(unsigned), ctx->stream));
+    k_tc_absmax<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d, count, d_mx);
+    SSI_LAUNCH_CHECK(ctx);
+    SSI_CUDA(ctx, cudaMemcpyAsync(out, d_mx, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SSI_CUDA(ctx, cudaMemsetAsync(d_mx, 0, sizeof(unsigned), ctx->stream));
+    return SSI_OK;
+}
+
+// operands that depend on (data, subspace) only, in the plane format of s->prec: the K-major bases of the first-layer GEMM,
+// or the planes of the dataset when the first layer is a GEMM on X
+static int tc_build_static_operands(ssi_ctx* ctx) {
+    ssi_tc_state* s = ctx->tc;
+    const ssi_model_t& m = ctx->model;
+    const int64_t N = ctx->N;
+    const bool fp16 = s->prec == TC_PREC_FP16X3;
+    if (s->basis_mma) {
+        const long long NW = (long long)N * s->width[0];
+        s->bases_scale = 1.0f;
+        if (fp16) {
+            float mx = 0.0f;
+            SSI_TRY(tc_absmax_host(ctx, s->bases, (long long)(ctx->M + 1) * NW, &mx));
+            s->bases_scale = scalbnf(1.0f, tc_exp_for(mx, 13));
+        }
+        k_tc_bases_kmajor<<<(unsigned)((NW + 255) / 256), 256, 0, ctx->stream>>>(s->bases, NW, ctx->M + 1, s->KT, fp16 ? 1 : 0, s->bases_scale, s->Th, s->Tl);
+        SSI_LAUNCH_CHECK(ctx);
+    }
+    if (!s->basis) {
+        float xs = 1.0f;
+        s->ja_in.v[0] = 0;
+        if (fp16) {
+            float mx = 0.0f;
+            SSI_TRY(tc_absmax_host(ctx, ctx->dX, (long long)N * m.dims[0], &mx));
+            s->ja_in.v[0] = tc_exp_for(mx, 13);
+            xs = scalbnf(1.0f, s->ja_in.v[0]);
+        }
+        const long long tot = (long long)N * s->Kp[0];
+        k_tc_split_x<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->dX, N, m.dims[0], s->Kp[0], fp16 ? 1 : 0, xs, s->Xh, s->Xl);
+        SSI_LAUNCH_CHECK(ctx);
+    }
+    return SSI_OK;
+}
+
+// One evaluation at z = 0 on BF16 planes records the largest activation every layer writes; the FP16 scale of layer l's A
+// planes maps it to [2^TC_CAL_TOP, 2^(TC_CAL_TOP+1)): 64x..128x of headroom below FP16's maximum for the other samples.
+static int tc_calibrate(ssi_ctx* ctx) {
+    ssi_tc_state* s = ctx->tc;
+    float* dz = nullptr;
+    double* dsse = nullptr;
+    SSI_CUDA(ctx, cudaMalloc(&dz, sizeof(float) * SSI_MAX_M));
+    SSI_CUDA(ctx, cudaMalloc(&dsse, sizeof(double)));
+    cudaMemsetAsync(dz, 0, sizeof(float) * SSI_MAX_M, ctx->stream);
+    const int64_t launches = ctx->stats.kernel_launches;
+    const int rc = ssi_tc_sse(ctx, dz, 1, dsse);
+    float h[SSI_MAX_LAYERS + 1] = {0};
+    cudaMemcpyAsync(h, s->amax, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dz); cudaFree(dsse);
+    ctx->stats.kernel_launches = launches;               // preparation, not part of any call's count
+    if (rc != SSI_OK) return rc;
+    SSI_CUDA(ctx, e);
+    for (int l = s->l0; l < s->nl; ++l)
+        if (l > 0) s->ja_in.v[l] = tc_exp_for(h[l], TC_CAL_TOP);     // layer 0 reads the dataset: exact scale, set with its planes
+    SSI_CUDA(ctx, cudaMemsetAsync(s->amax, 0, sizeof(float) * (SSI_MAX_LAYERS + 1), ctx->stream));
+    s->prec = TC_PREC_FP16X3;
+    SSI_TRY(tc_build_static_operands(ctx));
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SSI_OK;
+}
+
+// Did an evaluation since the last check write an activation beyond the range of its FP16 planes?  (Called where the host
+// entry points have synchronised anyway.)  If so this (data, subspace) moves to BF16 planes for good and the caller repeats
+// its evaluation.
+int ssi_tc_range_exceeded(ssi_ctx* ctx, bool* exceeded) {
+    *exceeded = false;
+    ssi_tc_state* s = ctx->tc;
+    if (!s || !s->ready || s->prec != TC_PREC_FP16X3) return SSI_OK;
+    float h[SSI_MAX_LAYERS + 1];
+    SSI_CUDA(ctx, cudaMemcpyAsync(h, s->amax, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int l = std::max(1, s->l0); l < s->nl; ++l)
+        if (h[l] * scalbnf(1.0f, s->ja_in.v[l]) > 0.999f * TC_F16_MAX) *exceeded = true;
+    if (*exceeded) {
+        s->fallback = true;
+        s->prec = TC_PREC_BF16X3;
+        for (int l = 0; l <= SSI_MAX_LAYERS; ++l) s->ja_in.v[l] = 0;
+        SSI_CUDA(ctx, cudaMemsetAsync(s->amax, 0, sizeof(float) * (SSI_MAX_LAYERS + 1), ctx->stream));
+        SSI_TRY(tc_build_static_operands(ctx));
+        ctx->stats.tc_range_fallbacks++;
+    }
     return SSI_OK;
 }
 
@@ -946,12 +1199,20 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
     }
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     tc_free(s);
+    const int rc = [&]() -> int {
     const ssi_model_t& m = ctx->model;
     const int64_t N = ctx->N;
-    // first layer as a basis combination when a GEMM layer follows it and the bases fit comfortably in HBM
+    const bool want_fp16 = ctx->opt_tc_prec != 0;
+    s->prec = TC_PREC_BF16X3;            // the calibration pass below runs on BF16 planes, which cannot overflow
+    // Sizing against the memory that is actually free (the caller -- e.g. a torch process -- may hold part of the device):
+    // the first layer runs on precomputed bases when they (FP32 + K-major planes) take at most a third of what is free, and
+    // a group of samples gets at most 60 % of what is left after them.
+    size_t mem_free = 0, mem_total = 0;
+    SSI_CUDA(ctx, cudaMemGetInfo(&mem_free, &mem_total));
     const int w0pad = (m.dims[1] + 63) / 64 * 64;
     const double bases_bytes = (double)(ctx->M + 1) * (double)N * w0pad * sizeof(float);
-    s->basis = (m.L >= 2 && !ctx->opt_tc_nobasis && bases_bytes <= 16e9);
+    const double bases_all = bases_bytes + 4.0 * (double)N * w0pad * 32;
+    s->basis = (m.L >= 2 && !ctx->opt_tc_nobasis && bases_all <= (double)mem_free / 3.0);
     s->l0 = s->basis ? 1 : 0;
     s->fused_out = (m.L - s->l0 >= 2 && m.dims[m.L] <= TC_OP && !ctx->opt_tc_nofuse);
     s->nl = s->fused_out ? m.L - 1 : m.L;
@@ -960,17 +1221,12 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
     s->basis_mma = s->basis && ctx->M + 1 <= 32 && !ctx->opt_tc_simt_basis;
     int gmax = s->basis_mma ? 128 : TC_GMAX;
     {
-        // per-sample device memory of a group: split-BF16 activations of every stored layer + GEMM weights; keep a group
-        // under ~96 GB of the 180 GB (the bases, the dataset and the caller's buffers need room too)
-        double per_sample = 0;
-        int stored = 0;
-        for (int l = 0; l < m.L - 1; ++l) {
-            const double wpad = (m.dims[l + 1] + 63) / 64 * 64;
-            if (stored < 3) per_sample += 4.0 * (double)N * wpad;      // at most the basis buffer + two ping-pong buffers
-            ++stored;
-            per_sample += 4.0 * wpad * ((m.dims[l] + 63) / 64 * 64);
-        }
-        while (gmax > TC_GMAX && per_sample * gmax > 96e9) gmax -= TC_GMAX;
+        const double budget = 0.6 * ((double)mem_free - (s->basis ? bases_all : 4.0 * (double)N * ((m.dims[0] + 63) / 64 * 64)));
+        while (gmax > TC_GMAX && tc_group_bytes(ctx, s->basis, gmax) > budget) gmax -= TC_GMAX;
+        while (gmax > 1 && tc_group_bytes(ctx, s->basis, gmax) > budget) gmax /= 2;
+        if (tc_group_bytes(ctx, s->basis, gmax) > budget)
+            return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "tensor path: one sample needs %.1f GB of activations but only %.1f GB of device memory is free",
+                            tc_group_bytes(ctx, s->basis, 1) / 1e9, (double)mem_free / 1e9);
     }
     s->G = ctx->opt_group > 0 ? std::min(ctx->opt_group, gmax) : gmax;
     const int G = s->G;
@@ -987,6 +1243,20 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
         SSI_CUDA(ctx, cudaMalloc(&s->Wh[l], sizeof(bf16) * wn));
         SSI_CUDA(ctx, cudaMalloc(&s->Wl[l], sizeof(bf16) * wn));
         SSI_CUDA(ctx, cudaMalloc(&s->bias[l], sizeof(float) * (size_t)G * s->width[l]));
+    }
+    SSI_CUDA(ctx, cudaMalloc(&s->amax, sizeof(float) * (SSI_MAX_LAYERS + 1)));
+    SSI_CUDA(ctx, cudaMemsetAsync(s->amax, 0, sizeof(float) * (SSI_MAX_LAYERS + 1), ctx->stream));
+    if (want_fp16) {
+        SSI_CUDA(ctx, cudaMalloc(&s->zinv, sizeof(float) * 128));
+        SSI_CUDA(ctx, cudaMalloc(&s->cmax, sizeof(float) * (size_t)s->nl * (ctx->M + 1)));
+        SSI_CUDA(ctx, cudaMalloc(&s->wscale, sizeof(float) * (size_t)s->nl * G));
+        SSI_CUDA(ctx, cudaMalloc(&s->winv, sizeof(float) * (size_t)s->nl * G));
+        SSI_CUDA(ctx, cudaMemsetAsync(s->cmax, 0, sizeof(float) * (size_t)s->nl * (ctx->M + 1), ctx->stream));
+        for (int l = s->l0; l < s->nl; ++l) {
+            k_tc_colmax<<<ctx->M + 1, 256, 0, ctx->stream>>>(ctx->dP, m.n, m.w_off[l], (long long)m.dims[l] * m.dims[l + 1],
+                                                            s->cmax + (size_t)l * (ctx->M + 1));
+            SSI_LAUNCH_CHECK(ctx);
+        }
     }
     if (s->fused_out) {
         const int wl = s->width[s->nl - 1];
@@ -1020,17 +1290,10 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
             SSI_CUDA(ctx, cudaMalloc(&s->Tl, sizeof(bf16) * NW * s->KT));
             SSI_CUDA(ctx, cudaMalloc(&s->Zh, sizeof(bf16) * 128 * 32));
             SSI_CUDA(ctx, cudaMalloc(&s->Zl, sizeof(bf16) * 128 * 32));
-            k_tc_bases_kmajor<<<(unsigned)((NW + 255) / 256), 256, 0, ctx->stream>>>(s->bases, (long long)NW, ctx->M + 1, s->KT, s->Th, s->Tl);
-            SSI_LAUNCH_CHECK(ctx);
         }
     }
     const int m_tiles = (int)((N + TC_BM - 1) / TC_BM);
     SSI_CUDA(ctx, cudaMalloc(&s->partials, sizeof(double) * (size_t)G * m_tiles * 4));
-    if (!s->basis) {
-        const long long tot = (long long)N * s->Kp[0];
-        k_tc_split_x<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->dX, N, m.dims[0], s->Kp[0], s->Xh, s->Xl);
-        SSI_LAUNCH_CHECK(ctx);
-    }
     for (int l = s->l0; l < s->nl; ++l) {
         const CUtensorMapSwizzle S128 = CU_TENSOR_MAP_SWIZZLE_128B, S64 = CU_TENSOR_MAP_SWIZZLE_64B;
         if (l == 0) {
@@ -1050,9 +1313,6 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
         }
         SSI_TRY(tc_make_map(ctx, &s->tmBh[l], s->Wh[l], s->Kp[l], s->width[l], G, TC_BK, s->BN[l], S128));
         SSI_TRY(tc_make_map(ctx, &s->tmBl[l], s->Wl[l], s->Kp[l], s->width[l], G, TC_BK, s->BN[l], S128));
-        // cluster mode: each CTA of a pair fetches half of the rows of a weight tile and multicasts it
-        SSI_TRY(tc_make_map(ctx, &s->tmBh2[l], s->Wh[l], s->Kp[l], s->width[l], G, TC_BK, s->BN[l] / 2, S128));
-        SSI_TRY(tc_make_map(ctx, &s->tmBl2[l], s->Wl[l], s->Kp[l], s->width[l], G, TC_BK, s->BN[l] / 2, S128));
         if (l < s->nl - 1) {
             // epilogue stores of this layer's activations: 32 rows x 32 columns (64 B) per warp and chunk
             SSI_TRY(tc_make_map(ctx, &s->tmSh[l], s->Hh[l & 1], s->width[l], N, G, 32, 32, S64));
@@ -1064,8 +1324,8 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
     }
     for (int mode = 0; mode < 3; ++mode)
         for (int act = 0; act < 4; ++act)
-            for (int cl = 0; cl < 2; ++cl)
-                SSI_CUDA(ctx, cudaFuncSetAttribute(tc_kernel(mode, act, cl != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_total(mode)));
+            for (int prec = 0; prec < 2; ++prec)
+                SSI_CUDA(ctx, cudaFuncSetAttribute(tc_kernel(mode, act, prec), cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_total(mode)));
     if (s->basis_mma) {
         const CUtensorMapSwizzle S64 = CU_TENSOR_MAP_SWIZZLE_64B;
         const uint64_t NW = (uint64_t)N * s->width[0];
@@ -1086,13 +1346,21 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return ssi_fail(ctx, SSI_ERR_CUDA, "cuTensorMapEncodeTiled (basis store) failed with CUresult %d", (int)r);
         }
-        SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_basis_mma<SSI_ACT_IDENTITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_TOTAL));
-        SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_basis_mma<SSI_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_TOTAL));
-        SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_basis_mma<SSI_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_TOTAL));
-        SSI_CUDA(ctx, cudaFuncSetAttribute(k_tc_basis_mma<SSI_ACT_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_TOTAL));
+        for (int act = 0; act < 4; ++act)
+            for (int prec = 0; prec < 2; ++prec)
+                SSI_CUDA(ctx, cudaFuncSetAttribute(tb_kernel(act, prec), cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_TOTAL));
     }
+    SSI_TRY(tc_build_static_operands(ctx));           // BF16 planes of the bases / the dataset
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     s->ready = true;
+    if (want_fp16) SSI_TRY(tc_calibrate(ctx));       // one evaluation at z = 0 -> activation scales -> FP16 planes
+    return SSI_OK;
+    }();
+    if (rc != SSI_OK) {          // do not keep a half-built state (and its allocations) around
+        (void)cudaGetLastError();
+        tc_free(s);
+        return rc;
+    }
     return SSI_OK;
 }
 
@@ -1107,21 +1375,23 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
     const int m_tiles = (int)((N + TC_BM - 1) / TC_BM);
     const int parts = m_tiles * 4;
     const long long NW = s->basis ? (long long)N * s->width[0] : 0;
+    const bool fp16 = s->prec == TC_PREC_FP16X3;
 
     for (int64_t b0 = 0; b0 < B; b0 += s->G) {
         const int G = (int)std::min<int64_t>(s->G, B - b0);
         // ---- first layer as a combination of the precomputed bases ----
         if (s->basis_mma) {
-            k_tc_pack_zaug<<<(128 * 32 + 255) / 256, 256, 0, ctx->stream>>>(dZ + b0 * M, M, G, s->Zh, s->Zl);
+            k_tc_pack_zaug<<<128 / 8, 256, 0, ctx->stream>>>(dZ + b0 * M, M, G, fp16 ? 1 : 0, 1.0f / s->bases_scale, s->Zh, s->Zl, s->zinv);
             SSI_LAUNCH_CHECK(ctx);
             const int n_tiles = (int)((NW + TB_N - 1) / TB_N);
             const int grid = std::min(ctx->sm_count, n_tiles);
-            switch (m.act[0]) {
-                case SSI_ACT_RELU:    k_tc_basis_mma<SSI_ACT_RELU><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmO, n_tiles); break;
-                case SSI_ACT_TANH:    k_tc_basis_mma<SSI_ACT_TANH><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmO, n_tiles); break;
-                case SSI_ACT_SIGMOID: k_tc_basis_mma<SSI_ACT_SIGMOID><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmO, n_tiles); break;
-                default:              k_tc_basis_mma<SSI_ACT_IDENTITY><<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmO, n_tiles); break;
-            }
+            tb_kernel(m.act[0], s->prec)<<<grid, TC_THREADS, TB_SMEM_TOTAL, ctx->stream>>>(s->tmZh, s->tmZl, s->tmTh, s->tmTl, s->tmO, n_tiles,
+                                                                                          fp16 ? s->zinv : nullptr,
+                                                                                          scalbnf(1.0f, s->ja_in.v[1]), s->amax + 1);
+            SSI_LAUNCH_CHECK(ctx);
+        }
+        if (fp16) {
+            k_tc_wscale<<<(s->nl * G + 127) / 128, 128, 0, ctx->stream>>>(dZ + b0 * M, M, G, s->cmax, s->nl, s->G, s->ja_in, s->wscale, s->winv);
             SSI_LAUNCH_CHECK(ctx);
         }
         // ---- the SIMT kernels take TC_GMAX samples at a time ----
@@ -1135,11 +1405,14 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
                 const unsigned blocks = (unsigned)((NW + per_cta - 1) / per_cta);
                 bf16* oh = s->Bh + 2 * (long long)g0 * NW;
                 bf16* ol = nullptr;                                 // lo halves are interleaved behind the hi halves
-                if (M <= 8) tc_launch_basis<8>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol);
-                else if (M <= 12) tc_launch_basis<12>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol);
-                else if (M <= 20) tc_launch_basis<20>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol);
-                else if (M <= 32) tc_launch_basis<32>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol);
-                else tc_launch_basis<SSI_MAX_M>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol);
+                const int mx = fp16 ? 1 : 0;
+                const float a1 = scalbnf(1.0f, s->ja_in.v[1]);
+                float* am = s->amax + 1;
+                if (M <= 8) tc_launch_basis<8>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol, mx, a1, am);
+                else if (M <= 12) tc_launch_basis<12>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol, mx, a1, am);
+                else if (M <= 20) tc_launch_basis<20>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol, mx, a1, am);
+                else if (M <= 32) tc_launch_basis<32>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol, mx, a1, am);
+                else tc_launch_basis<SSI_MAX_M>(m.act[0], blocks, ctx->stream, s->bases, NW, M, gs, s->zpack, oh, ol, mx, a1, am);
                 SSI_LAUNCH_CHECK(ctx);
             }
             // K1: project the samples' weights straight into the GEMM operand layouts
@@ -1147,7 +1420,8 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
                 const size_t wo = (size_t)g0 * s->width[l] * s->Kp[l];
                 dim3 grid(s->Kp[l] / PW_T, (s->width[l] + PW_T - 1) / PW_T);
                 k_tc_project_w<<<grid, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, gs, m.w_off[l], m.dims[l], m.dims[l + 1],
-                                                             s->width[l], s->Kp[l], s->Wh[l] + wo, s->Wl[l] + wo);
+                                                             s->width[l], s->Kp[l], fp16 ? s->wscale + (size_t)l * s->G + g0 : nullptr,
+                                                             s->Wh[l] + wo, s->Wl[l] + wo);
                 SSI_LAUNCH_CHECK(ctx);
                 k_tc_project_b<<<(s->width[l] + 255) / 256, 256, 0, ctx->stream>>>(ctx->dWswa, ctx->dP, Zg, n, M, gs, m.b_off[l],
                                                                                m.dims[l + 1], s->width[l],
@@ -1182,17 +1456,14 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
             p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
             p.stages = std::min(4, TC_SMEM_PIPE / p.stage_bytes);
             p.bias = s->bias[l];
-            int grid = std::min(ctx->sm_count, G * m_tiles);
+            p.idesc = fp16 ? umma_idesc_f16(p.BN, UMMA_FMT_F16, UMMA_FMT_F16) : umma_idesc_bf16(p.BN);
+            p.winv = fp16 ? s->winv + (size_t)l * s->G : nullptr;
+            p.a_scale = scalbnf(1.0f, s->ja_in.v[l + 1]);         // of the planes this layer writes (HIDDEN)
+            p.amax = s->amax + (l + 1);
+            const int grid = std::min(ctx->sm_count, G * m_tiles);
             // a shared A operand (the dataset): run the group's samples side by side on the same m-tiles
             p.mt_block = (p.a_shared && G > 1 && !ctx->opt_tc_noorder) ? std::max(1, (grid + G - 1) / G) : 0;
             p.n_work = p.mt_block > 0 ? (m_tiles + p.mt_block - 1) / p.mt_block * p.mt_block * G : G * m_tiles;
-            // per-sample A (every layer behind the first): CTA pairs share the weight tiles by TMA multicast
-            const bool cl = !p.a_shared && ctx->opt_tc_cluster && p.BN >= 32 && m_tiles >= 2 && ctx->sm_count >= 2;
-            if (cl) {
-                p.mt_pad = (m_tiles + 1) & ~1;
-                p.n_work = G * p.mt_pad;
-                grid = std::min(ctx->sm_count & ~1, p.n_work);
-            }
             p.Y = ctx->dY; p.O = m.dims[m.L]; p.partials = s->partials;
             const bool last = (l == s->nl - 1);
             int mode = TC_MODE_HIDDEN;
@@ -1203,20 +1474,8 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
                 mode = TC_MODE_FINAL;
             }
             if (last) ssi_kt_begin(ctx);
-            if (cl) {
-                cudaLaunchConfig_t cfg{};
-                cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS);
-                cfg.dynamicSmemBytes = tc_smem_total(mode); cfg.stream = ctx->stream;
-                cudaLaunchAttribute attr{};
-                attr.id = cudaLaunchAttributeClusterDimension;
-                attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-                cfg.attrs = &attr; cfg.numAttrs = 1;
-                void* args[] = {&s->tmAh[l], &s->tmAl[l], &s->tmBh2[l], &s->tmBl2[l], &s->tmSh[l], &s->tmSl[l], &p};
-                SSI_CUDA(ctx, cudaLaunchKernelExC(&cfg, (const void*)tc_kernel(mode, p.act, true), args));
-            } else {
-                tc_kernel(mode, p.act)<<<grid, TC_THREADS, tc_smem_total(mode), ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l],
-                                                                                              s->tmSh[l], s->tmSl[l], p);
-            }
+            tc_kernel(mode, p.act, s->prec)<<<grid, TC_THREADS, tc_smem_total(mode), ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l],
+                                                                                                   s->tmSh[l], s->tmSl[l], p);
             SSI_LAUNCH_CHECK(ctx);
             if (last) ssi_kt_end(ctx);
         }

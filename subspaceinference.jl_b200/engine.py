@@ -22,14 +22,22 @@ class Engine:
     """Owns a device context.  Matrices are passed in the reference's (Julia) orientation:
     X (in0, N), Y (O, N), P (n, M), Z (M, B); they are handed to the library column-major."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """device: one CUDA device index, or a sequence of indices for a multi-device context (ssi_ctx_create_multi: one
+        process drives all of them; batched host calls are sharded by sample / chain, everything else is replicated)."""
         self._lib = _lib.load()
         h = C.c_void_p()
-        rc = self._lib.ssi_ctx_create(int(device), C.byref(h))
+        if isinstance(device, (list, tuple)):
+            devs = np.asarray(device, dtype=np.int32)
+            rc = self._lib.ssi_ctx_create_multi(_ptr(devs), len(devs), C.byref(h))
+            self.devices = tuple(int(d) for d in devs)
+        else:
+            rc = self._lib.ssi_ctx_create(int(device), C.byref(h))
+            self.devices = (int(device),)
         if rc != 0:
             raise SsiError(rc, self._lib.ssi_last_error(None).decode())
         self._h = h
-        self.device = int(device)
+        self.device = self.devices[0]
         self.dims: tuple[int, ...] | None = None
         self.M = 0
         self.N = 0
@@ -174,6 +182,28 @@ class Engine:
         fn = {"rwmh": self._lib.ssi_mh_run, "mala": self._lib.ssi_mala_run}[kind]
         self._check(fn(self._h, n_chains, n_steps, seed, chain_offset, sigma_z, sigma_m, sigma_p, mask,
                        _ptr(z0a), _ptr(zt), _ptr(lt), _ptr(at)))
+        self._last_chains = n_chains
+        return zt, lt, at
+
+    def mh_state(self):
+        """Final (z (M, n_chains) f32, lp (n_chains,) f64) of the last run's chains: what to save for mh_run_from."""
+        n = self._last_chains
+        z = np.empty((self.M, n), np.float32, order="F")
+        lp = np.empty(n, np.float64)
+        self._check(self._lib.ssi_mh_get_state(self._h, _ptr(z), _ptr(lp)))
+        return z, lp
+
+    def mh_run_from(self, z_state, step_offset: int, n_steps: int, seed: int, sigma_z=1.0, sigma_m=1.0, sigma_p=1.0, mask=TERM_LL,
+                    chain_offset: int = 0, want_z=True, want_lp=True, want_accept=True, kind: str = "rwmh"):
+        """Continue chains saved with mh_state(): steps step_offset .. step_offset + n_steps - 1 of the same Philox streams."""
+        z_state = _f32(z_state)
+        n_chains = z_state.shape[1]
+        zt = np.empty((self.M, n_chains, n_steps), np.float32, order="F") if want_z else None
+        lt = np.empty((n_chains, n_steps), np.float64, order="F") if want_lp else None
+        at = np.empty((n_chains, n_steps), np.uint8, order="F") if want_accept else None
+        self._check(self._lib.ssi_mh_run_from(self._h, {"rwmh": 0, "mala": 1}[kind], n_chains, n_steps, seed, chain_offset, step_offset,
+                                              sigma_z, sigma_m, sigma_p, mask, _ptr(z_state), _ptr(zt), _ptr(lt), _ptr(at)))
+        self._last_chains = n_chains
         return zt, lt, at
 
     def mala_run(self, *a, **kw):

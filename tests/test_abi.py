@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(ssi):
     assert sorted(_lib.SIGNATURES) == declared, "ctypes table and include/ssi.h disagree"
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported by libssi.so"
-    assert lib.ssi_version() == 100
+    assert lib.ssi_version() == 200
 
 
 def test_rng_replay_matches_oracle_on_host(ssi):

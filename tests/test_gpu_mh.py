@@ -154,3 +154,70 @@ def test_mala_chain_sharding_is_bitwise_invariant(ssi, engine):
     b = engine.mala_run(6, 10, 5, sigma_z=0.02, sigma_m=0.1, chain_offset=6)
     np.testing.assert_array_equal(full[0], np.concatenate([a[0], b[0]], axis=1))
     np.testing.assert_array_equal(full[1], np.concatenate([a[1], b[1]], axis=0))
+
+
+@pytest.mark.parametrize("kind,name", [("rwmh", "readme"), ("mala", "uci"), ("rwmh", "uci")])
+def test_resume_is_bitwise_identical(ssi, engine, kind, name):
+    """SURVEY 5 (checkpoint / resume): run(0..S) == run(0..S/2) then run_from(S/2..S) from the saved (z) state, bit for bit
+    (counter-based RNG, deterministic batch-invariant density)."""
+    prob = orc.make_problem(name, N=600 if name == "uci" else None)
+    _setup(engine, prob)
+    C, S, seed, sz, sm = 37, 12, 909, 0.05, 0.3
+    zt, lt, at = engine.mh_run(C, S, seed, sigma_z=sz, sigma_m=sm, chain_offset=11, kind=kind)
+    z_end, lp_end = engine.mh_state()
+    np.testing.assert_array_equal(z_end, zt[:, :, -1])
+    np.testing.assert_array_equal(lp_end, lt[:, -1])
+    h = 5
+    za, la, aa = engine.mh_run(C, h, seed, sigma_z=sz, sigma_m=sm, chain_offset=11, kind=kind)
+    z_mid, lp_mid = engine.mh_state()
+    np.testing.assert_array_equal(za, zt[:, :, :h])
+    # ... the process may exit here: (seed, step, z) is the whole checkpoint ...
+    zb, lb, ab = engine.mh_run_from(z_mid, h, S - h, seed, sigma_z=sz, sigma_m=sm, chain_offset=11, kind=kind)
+    np.testing.assert_array_equal(zb, zt[:, :, h:])
+    np.testing.assert_array_equal(lb, lt[:, h:])
+    np.testing.assert_array_equal(ab, at[:, h:])
+    assert engine.stats().mh_proposals == C * (S - h)
+    with pytest.raises(ssi.SsiError):
+        engine._check(engine._lib.ssi_mh_run_from(engine._h, 0, C, 3, seed, 0, 4, sz, sm, 1.0, 1, None, None, None, None))
+
+
+def test_multi_device_context_matches_single(ssi, engine):
+    """ssi_ctx_create_multi: one process, one context, every visible device.  With one GPU this is the degenerate
+    1-device case of the same code path; with several the chains / samples are sharded and the results must still be
+    bit-identical to the single-device context (global chain ids in the Philox counters, batch-invariant density)."""
+    import torch
+    ndev = torch.cuda.device_count()
+    prob = orc.make_problem("uci", N=900)
+    _setup(engine, prob)
+    rng = np.random.default_rng(3)
+    Z = (0.1 * rng.standard_normal((prob.M, 333))).astype(np.float32)
+    lp1, terms1 = engine.logpost(Z, 0.2, mask=7, return_terms=True)
+    lpg1, g1 = engine.logpost_grad(Z[:, :70], 0.2)
+    zt1, lt1, at1 = engine.mh_run(301, 6, 5, sigma_z=0.05, sigma_m=0.2, chain_offset=7)
+    W1 = engine.project(Z[:, :5])
+    for devs in ([0], list(range(ndev))):
+        with ssi.Engine(devs) as multi:
+            assert multi._lib.ssi_ctx_devices(multi._h) == len(devs)
+            _setup(multi, prob)
+            lp2, terms2 = multi.logpost(Z, 0.2, mask=7, return_terms=True)
+            np.testing.assert_array_equal(lp2, lp1)
+            np.testing.assert_array_equal(terms2, terms1)
+            lpg2, g2 = multi.logpost_grad(Z[:, :70], 0.2)
+            np.testing.assert_array_equal(lpg2, lpg1)
+            np.testing.assert_array_equal(g2, g1)
+            zt2, lt2, at2 = multi.mh_run(301, 6, 5, sigma_z=0.05, sigma_m=0.2, chain_offset=7)
+            np.testing.assert_array_equal(zt2, zt1)
+            np.testing.assert_array_equal(lt2, lt1)
+            np.testing.assert_array_equal(at2, at1)
+            st = multi.stats()
+            assert st.mh_proposals == 301 * 5 and st.mh_accepts == int(at1[:, 1:].sum())
+            z_end, lp_end = multi.mh_state()
+            np.testing.assert_array_equal(z_end, zt1[:, :, -1])
+            zb, lb, _ = multi.mh_run_from(z_end, 6, 2, 5, sigma_z=0.05, sigma_m=0.2, chain_offset=7)
+            zc, lc, _ = engine.mh_run_from(z_end, 6, 2, 5, sigma_z=0.05, sigma_m=0.2, chain_offset=7)
+            np.testing.assert_array_equal(zb, zc)
+            np.testing.assert_array_equal(lb, lc)
+            np.testing.assert_array_equal(multi.project(Z[:, :5]), W1)
+            with pytest.raises(ssi.SsiError) as ei:          # device pointers belong to one device
+                multi.logpost_dev(0, 1, 0)
+            assert ei.value.code == -1 or ei.value.code == -5
