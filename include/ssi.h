@@ -132,6 +132,18 @@ int  ssi_set_data(ssi_ctx* ctx, const float* X, const float* Y, int64_t N);
 /* W_swa (n) and P (n x M column-major), host pointers, copied; n must match the model    */
 int  ssi_set_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, int64_t n, int32_t M);
 
+/* ---- non-linear subspace operator: the density of auto_inference, src/space_inference.jl:246-251 -----------
+ *     new_W = W_swa + decoder(z)
+ * with `decoder` the Flux Chain of Dense layers trained by auto_encoder_subspace (src/subspace_construction.jl:125-141):
+ * Chain(Dense(dims[0], dims[1], act[0]), ..., Dense(dims[L-1], dims[L], act[L-1])), dims[0] = the subspace dimension of z,
+ * dims[L] = n (the model's parameter count), theta in Flux.destructure order (host, copied), W_swa n floats.  Replaces
+ * ssi_set_subspace: afterwards every entry point takes z of dims[0] rows (ssi_logpost_*, ssi_mh_*, ssi_mala_*, ssi_project,
+ * ssi_predict_batch).  The widths before the last layer are limited to 64.  The last layer is affine up to its activation, so
+ * with act[L-1] = identity the whole fast path applies at z' = h(z); another activation materialises the
+ * weights per sample (LAYERED path; no weight prior, no gradient).  As in the reference's Chain branch, the weight-prior
+ * line of that density is dead code (src/space_inference.jl:250-251): the default prior_mask stays SSI_TERM_LL.        */
+int  ssi_set_decoder(ssi_ctx* ctx, const float* W_swa, int32_t n_layers, const int32_t* dims, const int32_t* act, const float* theta);
+
 /* ---- density(z), batched over B subspace points (src/space_inference.jl:90-95) ----- */
 /* Z: M x B (host).  lp_out: B doubles.  terms_out: 3 x B doubles (ll, prior_w, prior_z) or NULL. */
 int  ssi_logpost_batch(ssi_ctx* ctx, const float* Z, int64_t B,
@@ -222,6 +234,12 @@ int  ssi_swa_push_dev(ssi_ctx* ctx, const float* dW, double n_scalar);
 int  ssi_swa_finish(ssi_ctx* ctx, int32_t M, float* W_swa_out, float* P_out, double* s_out, int32_t install);
 /* number of columns collected so far */
 int64_t ssi_swa_columns(const ssi_ctx* ctx);
+/* the deviation matrix collected so far, n x K column-major (host): `reshape(A, all_len, :)` of
+ * src/subspace_construction.jl:61,119,201 -- what auto_encoder_subspace trains its auto-encoder on (:134-139) and
+ * diffusion_subspace hands to its diffusion map (:203)                                                             */
+int  ssi_swa_deviations(ssi_ctx* ctx, float* A_out);
+/* the running W_swa (n floats, host) without factorising anything */
+int  ssi_swa_mean(ssi_ctx* ctx, float* W_swa_out);
 
 /* ---- the step before the path: mini-batch training on the device ----------------------------------
  * Replaces, for a Dense chain with cost = Flux.Losses.mse(m(x), y), the reference's training step

@@ -518,3 +518,29 @@ def make_problem(name: str, seed: int | None = None, N: int | None = None) -> Pr
         scales = 0.5 ** np.arange(1, M + 1)
     P = synthetic_subspace(rng, n, M, scales)
     return Problem(dims, acts, X, Y, W_swa, P)
+
+
+# --------------------------------------------------------------------------------------
+# Non-linear subspace operator (auto-encoder decoder)   (src/space_inference.jl:238-251)
+# --------------------------------------------------------------------------------------
+def decoder_forward(theta: np.ndarray, dims, acts, z: np.ndarray) -> np.ndarray:
+    """``decoder(z)`` for a Flux Chain of Dense layers dims[0] -> ... -> dims[-1] with parameters ``theta`` in
+    Flux.destructure order (the decoder auto_encoder_subspace trains, src/subspace_construction.jl:125-141)."""
+    return forward(np.asarray(theta, np.float64), dims, acts, np.asarray(z, np.float64).reshape(-1, 1)).reshape(-1)
+
+
+def density_decoder(prob: Problem, dec_theta, dec_dims, dec_acts, z, sigma_m=1.0, sigma_p=1.0, sigma_z=1.0, mask=TERM_LL) -> float:
+    """``density(z)`` of auto_inference, Chain branch (src/space_inference.jl:246-251): ``new_W = W_swa + decoder(z)``, then
+    the same likelihood as sub_inference; the weight-prior line is dead code there too (a line-leading ``+``, :250-251),
+    so the default mask is the likelihood alone.  prob.P is not used."""
+    z = np.asarray(z, np.float64)
+    w = np.asarray(prob.W_swa, np.float64) + decoder_forward(dec_theta, dec_dims, dec_acts, z)
+    pred = forward(w, prob.dims, prob.acts, np.asarray(prob.X, np.float64))
+    v = 0.0
+    if mask & TERM_LL:
+        v += gaussian_loglik(pred, np.asarray(prob.Y, np.float64), sigma_m)
+    if mask & TERM_PRIOR_W:
+        v += log_prior_w(w, sigma_p)
+    if mask & TERM_PRIOR_Z:
+        v += log_prior_z(z, sigma_z)
+    return v

@@ -131,6 +131,9 @@ def main():
     out["finish_frac"] = out["finish_gbs"] / (peaks["hbm_gbs"] * world)
     st = eng.stats()
     out["gram_path"], out["gram_risk"], out["jacobi_sweeps"] = st.gram_path, st.gram_risk, st.jacobi_sweeps
+    out["stage_ms"] = {"gram": st.finish_gram_ms, "eigen": st.finish_eigen_ms, "form_p": st.finish_p_ms}
+    out["gram_frac"] = 4.0 * a.n * a.K / max(st.finish_gram_ms, 1e-9) / 1e6 / peaks["hbm_gbs"] if world == 1 else None
+    out["form_p_frac"] = (4.0 * a.n * a.K + 4.0 * a.n * a.M) / max(st.finish_p_ms, 1e-9) / 1e6 / peaks["hbm_gbs"] if world == 1 else None
     if a.train and world == 1:
         out["train"] = train_section(eng, stream)
     if rank == 0:

@@ -58,6 +58,7 @@ SIGNATURES = {
     "ssi_set_model": (C.c_int, [_p, C.c_int, _p, _p]),
     "ssi_set_data": (C.c_int, [_p, _p, _p, _i64]),
     "ssi_set_subspace": (C.c_int, [_p, _p, _p, _i64, _i32]),
+    "ssi_set_decoder": (C.c_int, [_p, _p, _i32, _p, _p, _p]),
     "ssi_logpost_batch": (C.c_int, [_p, _p, _i64, _dbl, _dbl, _dbl, _u32, _p, _p]),
     "ssi_logpost_batch_dev": (C.c_int, [_p, _p, _i64, _dbl, _dbl, _dbl, _u32, _p, _p]),
     "ssi_logpost_grad_batch": (C.c_int, [_p, _p, _i64, _dbl, _dbl, _dbl, _u32, _p, _p]),
@@ -77,6 +78,8 @@ SIGNATURES = {
     "ssi_swa_push_dev": (C.c_int, [_p, _p, _dbl]),
     "ssi_swa_finish": (C.c_int, [_p, _i32, _p, _p, _p, _i32]),
     "ssi_swa_columns": (_i64, [_p]),
+    "ssi_swa_deviations": (C.c_int, [_p, _p]),
+    "ssi_swa_mean": (C.c_int, [_p, _p]),
     "ssi_train_begin": (C.c_int, [_p, _p, C.c_int32, _dbl, _dbl, _dbl]),
     "ssi_train_step": (C.c_int, [_p, _p, _i64, _i64, _p]),
     "ssi_train_snapshot": (C.c_int, [_p, _dbl]),

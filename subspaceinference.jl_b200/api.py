@@ -15,7 +15,7 @@ import numpy as np
 
 from ._lib import TERM_LL
 from .engine import Engine
-from .flux import ADAM, Chain, DataLoader, Descent, extract_params, load_params, split_data, train_step
+from .flux import ADAM, Chain, DataLoader, Descent, extract_params, load_params, mse, split_data, train_step
 
 _RWMH_ALIASES = ("rwmh", "mh")
 
@@ -163,6 +163,87 @@ def sub_inference(in_model, data, W_swa, P, *, σ_z: float = 1.0, σ_m: float = 
 
 
 inference = sub_inference
+
+
+def auto_encoder_subspace(model, cost, data, opt, encoder, decoder, *, T: int = 10, c: int = 1, M: int = 3, print_freq: int = 1,
+                          engine: Engine | None = None, device: int = 0, rng: np.random.Generator | None = None):
+    """(W_swa, decoder): the SWA moments and deviation matrix as in subspace_construction (on the device), then an
+    auto-encoder Chain(encoder, decoder) trained on the deviation columns (src/subspace_construction.jl:93-143).  Like the
+    SGD step, the auto-encoder training is host plumbing outside the accelerated path (`Flux.train!`, one epoch, ADAM(),
+    DataLoader(re_weight, batchsize = 5, shuffle = true), :134-141) and is delegated to torch autograd; its loss is
+    `Flux.mse(sae(X), X)` -- the `+ sum(sqnorm, autops)` line is a separate statement that never contributes (:130-131).
+    M is accepted and unused, as in the reference (the decoder's input width is the subspace dimension)."""
+    if not isinstance(model, Chain) or not isinstance(encoder, Chain) or not isinstance(decoder, Chain):
+        raise TypeError("Error: model_re function is not available for this model")
+    own = engine is None
+    eng = engine or Engine(device)
+    try:
+        n = int(extract_params(model).shape[0])
+        if encoder.dims[0] != n or decoder.dims[-1] != n or encoder.dims[-1] != decoder.dims[0]:
+            raise ValueError("DimensionMismatch: encoder must map n -> M and decoder M -> n")
+        eng.swa_begin(n, max(1, (T // c) * len(data)))
+        training_loss = 0.0
+        for i in range(1, T + 1):
+            for x, y in data:
+                training_loss = train_step(model, cost, opt, x, y)
+                if i % c == 0:
+                    eng.swa_push(extract_params(model), i / c)
+            if i % print_freq == 0 or i == T:
+                print("Traing loss: ", training_loss, " Epoch: ", i)
+        W_swa = eng.swa_mean()
+        re_weight = eng.swa_deviations()                                   # reshape(A, all_len, :)   (:119)
+        sae = Chain(*encoder.layers, *decoder.layers)
+        autoloss = lambda mm, X: mse(mm(X), X)
+        aopt = ADAM()                                                       # opt = ADAM()  (:134)
+        wdata = DataLoader(re_weight, re_weight, batchsize=5, shuffle=True, rng=rng)
+        for X, _ in wdata:
+            train_step(sae, lambda mm, a, b: autoloss(mm, a), aopt, X, X)
+        return W_swa, decoder
+    finally:
+        if own:
+            eng.close()
+
+
+def auto_inference(m, data, decoder, W_swa, *, σ_z: float = 1.0, σ_m: float = 1.0, σ_p: float = 1.0, itr: int = 100, M: int = 3,
+                   alg="hmc", backend="forwarddiff", n_chains: int = 1, seed: int = 0, chain_offset: int = 0,
+                   prior_mask: int = TERM_LL, engine: Engine | None = None, device: int = 0, return_z: bool = False):
+    """Sampling with a decoder in place of P: density(z) evaluates the model at W_swa + decoder(z)
+    (src/space_inference.jl:238-318).  :rwmh and :mala run on the device as in sub_inference; the reference's default
+    here is :hmc, whose host-side sampler is not part of the device path (Engine.logpost_grad is its l_pi_grad)."""
+    a = _sym(alg)
+    if a not in _RWMH_ALIASES and a != "mala":
+        if a in ("advi", "hmc", "nuts"):
+            raise NotImplementedError(f"{a} is not available on the device path (Engine.logpost_grad is its l_pi_grad)")
+        raise ValueError(f"{a} is not available")                         # src/space_inference.jl:316
+    if not isinstance(m, Chain) or not isinstance(decoder, Chain):
+        raise TypeError("Error: density function is not avaliable for this model")
+    if decoder.dims[0] != M:
+        raise ValueError(f"DimensionMismatch: the decoder takes {decoder.dims[0]} inputs but M = {M}")
+    X, Y = split_data(data)
+    own = engine is None
+    eng = engine or Engine(device)
+    try:
+        eng.set_model(m.dims, m.acts)
+        eng.set_data(X, Y)
+        eng.set_decoder(W_swa, decoder.dims, decoder.acts, extract_params(decoder))
+        zt, lt, _ = eng.mh_run(n_chains, itr, seed, sigma_z=σ_z, sigma_m=σ_m, sigma_p=σ_p, mask=prior_mask,
+                               chain_offset=chain_offset, want_accept=False, kind="mala" if a == "mala" else "rwmh")
+        if n_chains == 1 and not return_z:
+            W = eng.project(zt[:, 0, :])                                  # map(z -> W_swa + decoder(z.params), chm)  (:277)
+            return [W[:, t].copy() for t in range(itr)], lt[0].copy()
+        return zt, lt
+    finally:
+        if own:
+            eng.close()
+
+
+def autoencoder_inference(model, cost, data, opt, encoder, decoder, *, σ_z: float = 1.0, σ_m: float = 1.0, σ_p: float = 1.0,
+                          itr: int = 1000, T: int = 25, c: int = 1, M: int = 20, print_freq: int = 1, alg="hmc",
+                          backend="forwarddiff", **kw):
+    """construct the decoder subspace -> sample -> (chn, lp)   (src/space_inference.jl:198-210)."""
+    W_swa, decoder = auto_encoder_subspace(model, cost, data, opt, encoder, decoder, T=T, c=c, M=M, print_freq=print_freq,
+                                           device=kw.get("device", 0))
+    return auto_inference(model, data, decoder, W_swa, σ_z=σ_z, σ_m=σ_m, σ_p=σ_p, itr=itr, M=M, alg=alg, backend=backend, **kw)
 
 
 def predictive(in_model, W_swa, P, z_samples, inp, *, return_trajectories: bool = True,

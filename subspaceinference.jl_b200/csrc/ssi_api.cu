@@ -53,6 +53,21 @@ int ssi_reserve(ssi_ctx* ctx, ssi_buf_t& b, size_t bytes) {
     return SSI_OK;
 }
 
+int ssi_tensormap_encoder(ssi_ctx* ctx, PFN_ssi_encodeTiled* out) {
+    static std::once_flag once;
+    static PFN_ssi_encodeTiled fn = nullptr;
+    std::call_once(once, []() {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_ssi_encodeTiled)f;
+        (void)cudaGetLastError();
+    });
+    if (!fn) return ssi_fail(ctx, SSI_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    *out = fn;
+    return SSI_OK;
+}
+
 static void free_buf(ssi_buf_t& b) {
     if (b.p) cudaFree(b.p);
     b.p = nullptr;
@@ -152,14 +167,15 @@ int ssi_ctx_destroy(ssi_ctx* ctx) {
     if (ctx->is_multi()) return ssi_multi_destroy(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    ssi_dec_destroy(ctx);
     ssi_tc_destroy(ctx);
     ssi_b1_destroy(ctx);
     ssi_bm_destroy(ctx);
     ssi_train_destroy(ctx);
     cudaFree(ctx->dX); cudaFree(ctx->dY); cudaFree(ctx->dP); cudaFree(ctx->dSubGram);
-    cudaFree(ctx->dSwaMean); cudaFree(ctx->dDev);
+    cudaFree(ctx->dSwaMean); cudaFree(ctx->dDev); cudaFree(ctx->dSwaAmax);
     ssi_buf_t* bufs[] = {&ctx->bZ, &ctx->bLp, &ctx->bTerms, &ctx->bPartials, &ctx->bW, &ctx->bH0, &ctx->bH1, &ctx->bGram,
-                         &ctx->bEig, &ctx->bMisc, &ctx->bGradW, &ctx->bGradP, &ctx->bMhZ, &ctx->bMhZp, &ctx->bMhLp, &ctx->bMhLpP, &ctx->bMhCnt, &ctx->bMhG, &ctx->bSnap};
+                         &ctx->bEig, &ctx->bMisc, &ctx->bDecZ, &ctx->bDecT, &ctx->bGradW, &ctx->bGradP, &ctx->bMhZ, &ctx->bMhZp, &ctx->bMhLp, &ctx->bMhLpP, &ctx->bMhCnt, &ctx->bMhG, &ctx->bSnap};
     for (ssi_buf_t* b : bufs) free_buf(*b);
     for (cudaEvent_t e : ctx->kt_events) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev0);
@@ -235,6 +251,8 @@ int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
     // -1 = tensor-core Gram without the check (measurement only)
     if (!strcmp(key, "gram_fp64")) { ctx->opt_gram_fp64 = (int)value; return SSI_OK; }
     if (!strcmp(key, "gram_chunk")) { ctx->opt_gram_chunk = (int)value; return SSI_OK; }
+    if (!strcmp(key, "eig_single")) { ctx->opt_eig_single = value != 0; return SSI_OK; }
+    if (!strcmp(key, "formp_simt")) { ctx->opt_formp_simt = value != 0; return SSI_OK; }
     if (!strcmp(key, "tc_nobasis")) { ctx->opt_tc_nobasis = value != 0; ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx); ssi_bm_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "time_dominant")) {
         ctx->opt_time_dominant = value != 0;
@@ -244,6 +262,7 @@ int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
     if (!strcmp(key, "tc_k32")) { ctx->opt_tc_k32 = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "tc_alast")) { ctx->opt_tc_alast = value != 0; return SSI_OK; }
     if (!strcmp(key, "tc_nokrev")) { ctx->opt_tc_nokrev = value != 0; return SSI_OK; }
+    if (!strcmp(key, "tc_pair")) { ctx->opt_tc_pair = value != 0; return SSI_OK; }
     if (!strcmp(key, "tc_precision")) { ctx->opt_tc_prec = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "b1_simt")) { ctx->opt_b1_simt = value != 0; return SSI_OK; }
     if (!strcmp(key, "bm_nopack")) { ctx->opt_bm_nopack = value != 0; ssi_bm_invalidate(ctx); return SSI_OK; }
@@ -318,8 +337,9 @@ int ssi_set_data(ssi_ctx* ctx, const float* X, const float* Y, int64_t N) {
     return SSI_OK;
 }
 
-static int install_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, int64_t n, int M, cudaMemcpyKind kind) {
+static int install_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, int64_t n, int M, cudaMemcpyKind kind, bool keep_decoder = false) {
     if (!ctx->has_model) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_set_model must be called before the subspace is set");
+    if (!keep_decoder) ssi_dec_destroy(ctx);            // a linear subspace replaces a decoder
     if (n != ctx->model.n) return ssi_fail(ctx, SSI_ERR_ARG, "n=%lld does not match the model's %lld parameters", (long long)n, (long long)ctx->model.n);
     if (M < 1 || M > SSI_MAX_M) return ssi_fail(ctx, SSI_ERR_ARG, "M=%d must be in [1,%d]", M, SSI_MAX_M);
     SSI_TRY(ssi_use_device(ctx));
@@ -334,11 +354,24 @@ static int install_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, in
     SSI_CUDA(ctx, cudaMemcpyAsync(ctx->dP, P, sizeof(float) * (size_t)n * M, kind, ctx->stream));
     SSI_CUDA(ctx, cudaMemcpyAsync(ctx->dWswa, W_swa, sizeof(float) * (size_t)n, kind, ctx->stream));
     ctx->M = M;
+    ctx->Mz = M;
     SSI_TRY(ssi_subspace_gram(ctx));
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->has_sub = true;
     ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx); ssi_bm_invalidate(ctx);
     return SSI_OK;
+}
+
+}  // extern "C"
+int ssi_install_subspace_host(ssi_ctx* ctx, const float* W_swa, const float* P, int64_t n, int M) {
+    return install_subspace(ctx, W_swa, P, n, M, cudaMemcpyHostToDevice, true);
+}
+extern "C" {
+
+int ssi_set_decoder(ssi_ctx* ctx, const float* W_swa, int32_t n_layers, const int32_t* dims, const int32_t* act, const float* theta) {
+    if (!ctx) return SSI_ERR_ARG;
+    if (ctx->is_multi()) return ssi_multi_set_decoder(ctx, W_swa, n_layers, dims, act, theta);
+    return ssi_set_decoder_impl(ctx, W_swa, n_layers, dims, act, theta);
 }
 
 int ssi_set_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, int64_t n, int32_t M) {
@@ -383,10 +416,10 @@ int ssi_logpost_grad_batch(ssi_ctx* ctx, const float* Z, int64_t B, double sigma
         return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before evaluating the gradient");
     if (B == 0) return SSI_OK;
     SSI_TRY(ssi_use_device(ctx));
-    const size_t bz = sizeof(float) * (size_t)ctx->M * B;
+    const size_t bz = sizeof(float) * (size_t)ctx->Mz * B;
     SSI_TRY(ssi_reserve(ctx, ctx->bZ, bz));
     SSI_TRY(ssi_reserve(ctx, ctx->bLp, sizeof(double) * (size_t)B));
-    SSI_TRY(ssi_reserve(ctx, ctx->bTerms, sizeof(double) * (size_t)ctx->M * B));
+    SSI_TRY(ssi_reserve(ctx, ctx->bTerms, sizeof(double) * (size_t)ctx->Mz * B));
     SSI_CUDA(ctx, cudaMemcpyAsync(ctx->bZ.p, Z, bz, cudaMemcpyHostToDevice, ctx->stream));
     call_timer t(ctx);
     const int rc = ssi_logpost_grad_device(ctx, (const float*)ctx->bZ.p, B, sigma_m, sigma_p, sigma_z, prior_mask,
@@ -394,7 +427,7 @@ int ssi_logpost_grad_batch(ssi_ctx* ctx, const float* Z, int64_t B, double sigma
     t.stop(false);
     if (rc != SSI_OK) return rc;
     SSI_CUDA(ctx, cudaMemcpyAsync(lp_out, ctx->bLp.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
-    SSI_CUDA(ctx, cudaMemcpyAsync(grad_out, ctx->bTerms.p, sizeof(double) * (size_t)ctx->M * B, cudaMemcpyDeviceToHost, ctx->stream));
+    SSI_CUDA(ctx, cudaMemcpyAsync(grad_out, ctx->bTerms.p, sizeof(double) * (size_t)ctx->Mz * B, cudaMemcpyDeviceToHost, ctx->stream));
     return ssi_sync_internal(ctx);
 }
 
@@ -407,7 +440,7 @@ int ssi_logpost_batch(ssi_ctx* ctx, const float* Z, int64_t B, double sigma_m, d
         return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before evaluating the log-posterior");
     if (B == 0) return SSI_OK;
     SSI_TRY(ssi_use_device(ctx));
-    const size_t bz = sizeof(float) * (size_t)ctx->M * B;
+    const size_t bz = sizeof(float) * (size_t)ctx->Mz * B;
     SSI_TRY(ssi_reserve(ctx, ctx->bZ, bz));
     SSI_TRY(ssi_reserve(ctx, ctx->bLp, sizeof(double) * (size_t)B));
     if (terms_out) SSI_TRY(ssi_reserve(ctx, ctx->bTerms, sizeof(double) * 3 * (size_t)B));
@@ -474,12 +507,12 @@ int ssi_mh_run_host_slice(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_st
     if (n_chains <= 0 || n_steps <= 0) return ssi_fail(ctx, SSI_ERR_ARG, "n_chains and n_steps must be positive");
     SSI_TRY(ssi_use_device(ctx));
     const size_t cs = (size_t)n_chains * (size_t)n_steps;
-    const size_t bz = sizeof(float) * ctx->M * cs, bl = sizeof(double) * cs, ba = cs;
+    const size_t bz = sizeof(float) * ctx->Mz * cs, bl = sizeof(double) * cs, ba = cs;
     // one scratch allocation: [z_trace | lp_trace | acc | z0]
     const size_t off_l = z_trace ? (bz + 255) / 256 * 256 : 0;
     const size_t off_a = off_l + (lp_trace ? (bl + 255) / 256 * 256 : 0);
     const size_t off_z0 = off_a + (accept_trace ? (ba + 255) / 256 * 256 : 0);
-    const size_t bz0 = z0 ? sizeof(float) * (size_t)ctx->M * n_chains : 0;
+    const size_t bz0 = z0 ? sizeof(float) * (size_t)ctx->Mz * n_chains : 0;
     SSI_TRY(ssi_reserve(ctx, ctx->bSnap, off_z0 + bz0 + 256));
     char* base = (char*)ctx->bSnap.p;
     float* dzt = z_trace ? (float*)base : nullptr;
@@ -488,7 +521,7 @@ int ssi_mh_run_host_slice(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_st
     float* dz0 = nullptr;
     if (z0) {
         dz0 = (float*)(base + off_z0);
-        SSI_CUDA(ctx, cudaMemcpyAsync(dz0, z0 + (size_t)c0 * ctx->M, bz0, cudaMemcpyHostToDevice, ctx->stream));
+        SSI_CUDA(ctx, cudaMemcpyAsync(dz0, z0 + (size_t)c0 * ctx->Mz, bz0, cudaMemcpyHostToDevice, ctx->stream));
     }
     for (int attempt = 0; attempt < 2; ++attempt) {      // repeated only if the tensor path's FP16 planes overflowed
         call_timer t(ctx);
@@ -502,8 +535,8 @@ int ssi_mh_run_host_slice(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_st
         if (!exceeded) break;
     }
     // a step's row of the device trace is this device's n_chains chains; in the host trace rows are ld_chains chains apart
-    const size_t rz = sizeof(float) * (size_t)ctx->M * n_chains, rl = sizeof(double) * (size_t)n_chains, ra = (size_t)n_chains;
-    if (z_trace) SSI_CUDA(ctx, cudaMemcpy2DAsync(z_trace + (size_t)c0 * ctx->M, sizeof(float) * (size_t)ctx->M * ld_chains, dzt, rz, rz, (size_t)n_steps,
+    const size_t rz = sizeof(float) * (size_t)ctx->Mz * n_chains, rl = sizeof(double) * (size_t)n_chains, ra = (size_t)n_chains;
+    if (z_trace) SSI_CUDA(ctx, cudaMemcpy2DAsync(z_trace + (size_t)c0 * ctx->Mz, sizeof(float) * (size_t)ctx->Mz * ld_chains, dzt, rz, rz, (size_t)n_steps,
                                                  cudaMemcpyDeviceToHost, ctx->stream));
     if (lp_trace) SSI_CUDA(ctx, cudaMemcpy2DAsync(lp_trace + c0, sizeof(double) * (size_t)ld_chains, dlt, rl, rl, (size_t)n_steps,
                                                   cudaMemcpyDeviceToHost, ctx->stream));
@@ -551,7 +584,7 @@ int ssi_mh_run_from(ssi_ctx* ctx, int32_t kind, int64_t n_chains, int64_t n_step
 int ssi_mh_get_state_slice(ssi_ctx* ctx, float* z_out, double* lp_out) {
     if (ctx->mh_chains <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "no chains have been run on this context");
     SSI_TRY(ssi_use_device(ctx));
-    if (z_out) SSI_CUDA(ctx, cudaMemcpyAsync(z_out, ctx->bMhZ.p, sizeof(float) * (size_t)ctx->M * ctx->mh_chains, cudaMemcpyDeviceToHost, ctx->stream));
+    if (z_out) SSI_CUDA(ctx, cudaMemcpyAsync(z_out, ctx->bMhZ.p, sizeof(float) * (size_t)ctx->Mz * ctx->mh_chains, cudaMemcpyDeviceToHost, ctx->stream));
     if (lp_out) SSI_CUDA(ctx, cudaMemcpyAsync(lp_out, ctx->bMhLp.p, sizeof(double) * (size_t)ctx->mh_chains, cudaMemcpyDeviceToHost, ctx->stream));
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SSI_OK;
@@ -587,13 +620,15 @@ int ssi_project(ssi_ctx* ctx, const float* Z, int64_t B, float* W_out) {
     const int64_t n = ctx->model.n;
     // stream the samples through a bounded scratch
     const int64_t gmax = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)(1ull << 30) / (sizeof(float) * n)));
-    SSI_TRY(ssi_reserve(ctx, ctx->bZ, sizeof(float) * (size_t)ctx->M * gmax));
+    SSI_TRY(ssi_reserve(ctx, ctx->bZ, sizeof(float) * (size_t)ctx->Mz * gmax));
     SSI_TRY(ssi_reserve(ctx, ctx->bW, sizeof(float) * (size_t)n * gmax));
     call_timer t(ctx);
     for (int64_t b0 = 0; b0 < B; b0 += gmax) {
         const int64_t g = std::min(gmax, B - b0);
-        SSI_CUDA(ctx, cudaMemcpyAsync(ctx->bZ.p, Z + b0 * ctx->M, sizeof(float) * (size_t)ctx->M * g, cudaMemcpyHostToDevice, ctx->stream));
-        SSI_TRY(ssi_project_device(ctx, (const float*)ctx->bZ.p, g, (float*)ctx->bW.p));
+        SSI_CUDA(ctx, cudaMemcpyAsync(ctx->bZ.p, Z + b0 * ctx->Mz, sizeof(float) * (size_t)ctx->Mz * g, cudaMemcpyHostToDevice, ctx->stream));
+        const float* zin = (const float*)ctx->bZ.p;
+        if (ctx->dec_active) SSI_TRY(ssi_dec_project(ctx, zin, g, &zin));       // W = W_swa + decoder(z)
+        SSI_TRY(ssi_project_device(ctx, zin, g, (float*)ctx->bW.p));
         SSI_CUDA(ctx, cudaMemcpyAsync(W_out + b0 * n, ctx->bW.p, sizeof(float) * (size_t)n * g, cudaMemcpyDeviceToHost, ctx->stream));
         SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -627,7 +662,7 @@ int ssi_predict_batch(ssi_ctx* ctx, const float* Z, int64_t B, const float* Xg, 
     const int O = m.dims[m.L], in0 = m.dims[0];
     const size_t ON = (size_t)O * Ng;
     // staging: Z | Xg | mean, m2, std (doubles) | preds (optional)
-    SSI_TRY(ssi_reserve(ctx, ctx->bZ, sizeof(float) * (size_t)ctx->M * B));
+    SSI_TRY(ssi_reserve(ctx, ctx->bZ, sizeof(float) * (size_t)ctx->Mz * B));
     SSI_TRY(ssi_reserve(ctx, ctx->bLp, sizeof(float) * (size_t)in0 * Ng));
     SSI_TRY(ssi_reserve(ctx, ctx->bTerms, sizeof(double) * 3 * ON));
     if (preds_out) SSI_TRY(ssi_reserve(ctx, ctx->bMisc, sizeof(float) * ON * (size_t)B));
@@ -637,7 +672,7 @@ int ssi_predict_batch(ssi_ctx* ctx, const float* Z, int64_t B, const float* Xg, 
     double* d_m2 = d_mean + ON;
     double* d_std = d_m2 + ON;
     float* d_preds = preds_out ? (float*)ctx->bMisc.p : nullptr;
-    SSI_CUDA(ctx, cudaMemcpyAsync(dZ, Z, sizeof(float) * (size_t)ctx->M * B, cudaMemcpyHostToDevice, ctx->stream));
+    SSI_CUDA(ctx, cudaMemcpyAsync(dZ, Z, sizeof(float) * (size_t)ctx->Mz * B, cudaMemcpyHostToDevice, ctx->stream));
     SSI_CUDA(ctx, cudaMemcpyAsync(dXg, Xg, sizeof(float) * (size_t)in0 * Ng, cudaMemcpyHostToDevice, ctx->stream));
     call_timer t(ctx);
     const int rc = ssi_predict_device(ctx, dZ, B, dXg, Ng, d_preds, d_mean, d_std, d_m2);
@@ -655,13 +690,15 @@ int ssi_swa_begin(ssi_ctx* ctx, int64_t n, int64_t K_max) {
     if (n < 1 || K_max < 1) return ssi_fail(ctx, SSI_ERR_ARG, "n and K_max must be positive");
     SSI_TRY(ssi_use_device(ctx));
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->dSwaMean); cudaFree(ctx->dDev);
-    ctx->dSwaMean = ctx->dDev = nullptr;
+    cudaFree(ctx->dSwaMean); cudaFree(ctx->dDev); cudaFree(ctx->dSwaAmax);
+    ctx->dSwaMean = ctx->dDev = ctx->dSwaAmax = nullptr;
     ctx->swa_n = 0; ctx->swa_K = 0; ctx->swa_Kmax = 0; ctx->swa_ld = 0;
     SSI_CUDA(ctx, cudaMalloc(&ctx->dSwaMean, sizeof(float) * (size_t)n));
     const int64_t ld = (n + 31) / 32 * 32;
     SSI_CUDA(ctx, cudaMalloc(&ctx->dDev, sizeof(float) * (size_t)ld * K_max));
     SSI_CUDA(ctx, cudaMemsetAsync(ctx->dSwaMean, 0, sizeof(float) * (size_t)n, ctx->stream));   // W_swa = zeros (:31)
+    SSI_CUDA(ctx, cudaMalloc(&ctx->dSwaAmax, sizeof(float)));
+    SSI_CUDA(ctx, cudaMemsetAsync(ctx->dSwaAmax, 0, sizeof(float), ctx->stream));
     ctx->swa_n = n;
     ctx->swa_ld = ld;
     ctx->swa_Kmax = K_max;
@@ -692,6 +729,28 @@ int ssi_swa_push(ssi_ctx* ctx, const float* W, double n_scalar) {
     t.stop(false);
     if (rc != SSI_OK) return rc;
     return ssi_sync_internal(ctx);   // the caller may reuse W immediately
+}
+
+int ssi_swa_deviations(ssi_ctx* ctx, float* A_out) {
+    if (!ctx) return SSI_ERR_ARG;
+    SSI_FIRST_DEVICE(ctx, ssi_swa_deviations(ctx, A_out));
+    if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
+    if (!A_out) return ssi_fail(ctx, SSI_ERR_ARG, "A_out must be non-NULL");
+    SSI_TRY(ssi_use_device(ctx));
+    if (ctx->swa_K > 0)       // device columns are swa_ld apart (padded to 128 bytes), the caller's n apart
+        SSI_CUDA(ctx, cudaMemcpy2DAsync(A_out, sizeof(float) * (size_t)ctx->swa_n, ctx->dDev, sizeof(float) * (size_t)ctx->swa_ld,
+                                        sizeof(float) * (size_t)ctx->swa_n, (size_t)ctx->swa_K, cudaMemcpyDeviceToHost, ctx->stream));
+    return ssi_sync_internal(ctx);
+}
+
+int ssi_swa_mean(ssi_ctx* ctx, float* W_swa_out) {
+    if (!ctx) return SSI_ERR_ARG;
+    SSI_FIRST_DEVICE(ctx, ssi_swa_mean(ctx, W_swa_out));
+    if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
+    if (!W_swa_out) return ssi_fail(ctx, SSI_ERR_ARG, "W_swa_out must be non-NULL");
+    SSI_TRY(ssi_use_device(ctx));
+    SSI_CUDA(ctx, cudaMemcpyAsync(W_swa_out, ctx->dSwaMean, sizeof(float) * (size_t)ctx->swa_n, cudaMemcpyDeviceToHost, ctx->stream));
+    return ssi_sync_internal(ctx);
 }
 
 int64_t ssi_swa_columns(const ssi_ctx* ctx) { return ctx ? (ctx->is_multi() ? ctx->children[0]->swa_K : ctx->swa_K) : -1; }

@@ -2,6 +2,7 @@
 // translation units of libssi.so.  Internal; the public surface is include/ssi.h.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -35,6 +36,7 @@ struct ssi_tc_state;   // tensor-core path private state (ssi_tc.cu)
 struct ssi_b1_state;   // basis path private state (ssi_basis.cu)
 struct ssi_bm_state;   // basis path on the tensor cores (ssi_basis_mma.cu)
 struct ssi_train_state; // on-device training step (ssi_train.cu)
+struct ssi_decoder_t;   // non-linear subspace operator (ssi_decoder.cu)
 
 struct ssi_ctx {
     // A multi-device context (ssi_ctx_create_multi) owns one ordinary context per device and no device state of its own:
@@ -60,11 +62,14 @@ struct ssi_ctx {
     int opt_tc_k32 = 0;       // A-B: K-major bases always 32 columns wide
     int opt_tc_alast = 1;     // evict-first hint on the last read of a row block's activations (A-B: 0)
     int opt_tc_nokrev = 0;    // A-B: every feature tile reads the k-blocks in ascending order
+    int opt_tc_pair = 0;      // GEMM layers with per-sample activations as CTA pairs (cta_group::2)
     int opt_tc_prec = 1;      // operand planes of the tensor path: 1 mixed BF16/FP16 (default), 0 BF16x3 (round 1)
     int opt_bm_nopack = 0, opt_bm_variant = 1;     // A-B inside k_b1_mma: unpacked operands; ReLU epilogue variant
     int opt_b1_simt = 0;       // A-B: BASIS path on CUDA cores (k_logpost_basis1h) instead of the tensor-core kernel (k_b1_mma)
     int opt_tc_simt_basis = 0; // A-B: first layer as the FP32 SIMT basis combination instead of the tensor-core one
     int opt_gram_fp64 = 0;    // force the FP64 SIMT Gram (default: tensor-core TF32x2 Gram for large n, K <= 128)
+    int opt_formp_simt = 0;   // A-B: P = A V_M with loads from global memory (k_form_p) instead of the TMA-staged stream
+    int opt_eig_single = 0;   // A-B: eigen-solve on one CTA instead of a cluster of eight
     int opt_gram_chunk = 0;   // tiles (32 rows) per FP32 accumulation chunk of the tensor-core Gram (default 32)
     int opt_tc_nobasis = 0;   // debugging / A-B: run the first layer as a GEMM instead of the affine-in-z basis combination   // debugging / A-B: sample-major work order on the first layer
 
@@ -76,7 +81,14 @@ struct ssi_ctx {
     int64_t N = 0;
     float* dWswa = nullptr;   // n
     float* dP = nullptr;      // n x M
-    int M = 0;
+    int M = 0;                // columns of P (the dimension the kernels work in)
+    int Mz = 0;               // dimension of the caller's z: M, or the input width of a decoder (ssi_set_decoder)
+    // non-linear subspace operator: W = W_swa + decoder(z); P / dWswa then hold the decoder's affine head
+    ssi_decoder_t* dec = nullptr;
+    bool dec_active = false;
+    int dec_out_act = SSI_ACT_IDENTITY;   // activation of the decoder's last layer
+    float* dWbase = nullptr;              // W_swa proper when that activation is not the identity (W = dWbase + act(dWswa + P z'))
+    ssi_buf_t bDecZ, bDecT;
     // M-space quantities for the weight prior: G = [P | W_swa]^T [P | W_swa]  ((M+1)x(M+1), double)
     double* dSubGram = nullptr;
 
@@ -92,6 +104,7 @@ struct ssi_ctx {
     int64_t swa_ld = 0;          // leading dimension of dDev: n rounded up to 32 (columns 128-byte aligned for float4 / TMA)
     float* dSwaMean = nullptr;   // n
     float* dDev = nullptr;       // n x K_max, column-major
+    float* dSwaAmax = nullptr;   // running max |deviation| over all pushes (scale of the Gram's FP16 planes)
     ssi_buf_t bSnap;
 
     // tensor-core path
@@ -148,6 +161,11 @@ int ssi_fail(ssi_ctx* ctx, int code, const char* fmt, ...);
     } while (0)
 
 int ssi_reserve(ssi_ctx* ctx, ssi_buf_t& b, size_t bytes);
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (thread-safe, looked up once per process)
+typedef CUresult (*PFN_ssi_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int ssi_tensormap_encoder(ssi_ctx* ctx, PFN_ssi_encodeTiled* out);
 int ssi_use_device(ssi_ctx* ctx);
 int ssi_sync_internal(ssi_ctx* ctx);     // stream sync + timers, without the public ssi_sync's range report
 
@@ -174,6 +192,16 @@ int ssi_mh_run_host_slice(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_st
                           float* z_trace, double* lp_trace, uint8_t* accept_trace, int64_t ld_chains, int64_t c0);
 int ssi_mh_get_state_slice(ssi_ctx* ctx, float* z_out, double* lp_out);
 
+// ---- decoder (ssi_decoder.cu) -------------------------------------------------------------
+void ssi_dec_destroy(ssi_ctx* ctx);
+int ssi_set_decoder_impl(ssi_ctx* ctx, const float* W_swa, int n_layers, const int32_t* dims, const int32_t* act, const float* theta);
+int ssi_dec_project(ssi_ctx* ctx, const float* dZ, int64_t B, const float** dZin);      // z -> z' = h(z) (device, scratch)
+int ssi_dec_logpost(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m, double sigma_p, double sigma_z, uint32_t mask,
+                    double* d_lp, double* d_terms);
+int ssi_dec_logpost_grad(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m, double sigma_p, double sigma_z, uint32_t mask,
+                         double* d_lp, double* d_grad);
+int ssi_multi_set_decoder(ssi_ctx* ctx, const float* W_swa, int n_layers, const int32_t* dims, const int32_t* act, const float* theta);
+
 // ---- entry points between translation units --------------------------------------------
 // log-posterior of B device-resident subspace points; d_lp (B) and optional d_terms (3 x B)
 int ssi_logpost_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m, double sigma_p,
@@ -190,9 +218,9 @@ int ssi_build_first_layer_bases(ssi_ctx* ctx, float* bases, int ld);
 int ssi_subspace_gram(ssi_ctx* ctx);   // fills dSubGram after set_subspace
 // Gram of an n x K column-major FP32 matrix (ld = n) into a K x K double matrix on device
 // Gram of an n x K column-major FP32 matrix with leading dimension ld
-int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int K, double* dG, bool allow_tensor = true);
+int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int K, double* dG, bool allow_tensor, const float* d_amax);
 bool ssi_gram_tc_usable(const ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int K);
-int ssi_gram_tc_device(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int K, double* dG);
+int ssi_gram_tc_device(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int K, double* dG, const float* d_amax);
 
 // tensor-core path (ssi_tc.cu)
 bool ssi_tc_supported(const ssi_ctx* ctx);

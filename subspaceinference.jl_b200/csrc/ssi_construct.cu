@@ -9,6 +9,7 @@
 // The reference SVDs A directly with LowRankApprox.psvd; U_M S_M = A V_M is an identity,
 // so the result is the same up to column sign.
 #include "ssi_common.cuh"
+#include "ssi_ptx.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -20,7 +21,8 @@
 // FP32 throughout, no cancellation beyond (w - mean) itself.  Two float4 per thread in flight.
 __global__ void __launch_bounds__(256)
 k_swa_push(const float* __restrict__ W, float* __restrict__ mean, float* __restrict__ dev,
-           long long n, float inv, float c, int vec) {
+           long long n, float inv, float c, int vec, float* __restrict__ amax /* running max |deviation| (scale of the Gram's FP16 planes) */) {
+    float mx = 0.0f;
     const long long n4 = vec ? (n >> 2) : 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -37,6 +39,8 @@ k_swa_push(const float* __restrict__ W, float* __restrict__ mean, float* __restr
         m4[i + stride] = make_float4(fmaf(e1.x, inv, a1.x), fmaf(e1.y, inv, a1.y), fmaf(e1.z, inv, a1.z), fmaf(e1.w, inv, a1.w));
         __stcs(d4 + i, make_float4(e0.x * c, e0.y * c, e0.z * c, e0.w * c));
         __stcs(d4 + i + stride, make_float4(e1.x * c, e1.y * c, e1.z * c, e1.w * c));
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(fabsf(e0.x), fabsf(e0.y)), fmaxf(fabsf(e0.z), fabsf(e0.w))),
+                             fmaxf(fmaxf(fabsf(e1.x), fabsf(e1.y)), fmaxf(fabsf(e1.z), fabsf(e1.w)))));
     }
     for (; i < n4; i += stride) {
         const float4 w0 = __ldcs(W4 + i);
@@ -44,12 +48,18 @@ k_swa_push(const float* __restrict__ W, float* __restrict__ mean, float* __restr
         const float4 e0 = make_float4(w0.x - a0.x, w0.y - a0.y, w0.z - a0.z, w0.w - a0.w);
         m4[i] = make_float4(fmaf(e0.x, inv, a0.x), fmaf(e0.y, inv, a0.y), fmaf(e0.z, inv, a0.z), fmaf(e0.w, inv, a0.w));
         __stcs(d4 + i, make_float4(e0.x * c, e0.y * c, e0.z * c, e0.w * c));
+        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(e0.x), fabsf(e0.y)), fmaxf(fabsf(e0.z), fabsf(e0.w))));
     }
     for (long long j = (n4 << 2) + t0; j < n; j += stride) {   // tail (n % 4), or everything when !vec
         const float e = W[j] - mean[j];
         mean[j] = fmaf(e, inv, mean[j]);
         dev[j] = e * c;
+        mx = fmaxf(mx, fabsf(e));
     }
+    // |deviation| = |e| c with c <= 1: max |e| is a valid (and tight enough) bound
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.0f) atomicMax(reinterpret_cast<unsigned*>(amax), __float_as_uint(mx));
 }
 
 int ssi_swa_push_device(ssi_ctx* ctx, const float* dW, double n_scalar) {
@@ -63,7 +73,7 @@ int ssi_swa_push_device(ssi_ctx* ctx, const float* dW, double n_scalar) {
     const int blocks = ctx->sm_count * 8;
     // vec = 0: everything goes through the scalar tail loop
     k_swa_push<<<blocks, 256, 0, ctx->stream>>>(dW, ctx->dSwaMean, col, n, (float)(1.0 / (n_scalar + 1.0)),
-                                                (float)(n_scalar / (n_scalar + 1.0)), aligned ? 1 : 0);
+                                                (float)(n_scalar / (n_scalar + 1.0)), aligned ? 1 : 0, ctx->dSwaAmax);
     SSI_LAUNCH_CHECK(ctx);
     ctx->swa_K++;
     ctx->stats.last_bytes = 16.0 * (double)n;
@@ -147,8 +157,8 @@ __global__ void k_gram_reduce(const double* __restrict__ partial, int slabs, lon
     G[e] = s;
 }
 
-int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int K, double* dG, bool allow_tensor) {
-    if (allow_tensor && ssi_gram_tc_usable(ctx, dA, n, ld, K)) return ssi_gram_tc_device(ctx, dA, n, ld, K, dG);
+int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int K, double* dG, bool allow_tensor, const float* d_amax) {
+    if (allow_tensor && d_amax && ssi_gram_tc_usable(ctx, dA, n, ld, K)) return ssi_gram_tc_device(ctx, dA, n, ld, K, dG, d_amax);
     const int GT = K <= 32 ? 32 : 64;
     const int tiles = (K + GT - 1) / GT;
     const int pairs = tiles * (tiles + 1) / 2;
@@ -172,20 +182,24 @@ int ssi_gram_device(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int K,
 int ssi_subspace_gram(ssi_ctx* ctx) {
     // dP holds [P | W_swa] as an n x (M+1) column-major matrix
     // the prior's Gram stays on the exact FP64 path (K = M+1 is tiny)
-    return ssi_gram_device(ctx, ctx->dP, ctx->model.n, ctx->model.n, ctx->M + 1, ctx->dSubGram, false);
+    return ssi_gram_device(ctx, ctx->dP, ctx->model.n, ctx->model.n, ctx->M + 1, ctx->dSubGram, false, nullptr);
 }
 
 // ======================================================================================
-// K7: symmetric eigen-solve of the K x K Gram, FP64.
+// K7: symmetric eigen-solve of the K x K Gram, FP64 (Veselic-Hari / Drmac: Cholesky, then one-sided Jacobi).
 //
-// One-sided (Hestenes) Jacobi on the COLUMNS of G: a rotation of columns (p, q) needs their three inner products
-// (|g_p|^2, |g_q|^2, g_p.g_q) and touches those two columns only, so a half warp owns a pair, the inner products are
-// shuffle reductions and ONE barrier per round-robin round is all the synchronisation there is (the two-sided solver of
-// round 1 rotated rows and columns: two block-wide barriers per round around a serial rotation-parameter phase, 3.9 us
-// per round, 4.6 ms at K = 100).  When the columns are mutually orthogonal, G V = U S with U = V for a symmetric
-// positive semi-definite G: column i has norm lambda_i and direction v_i.  Accuracy: the rotations are orthogonal to
-// working precision by construction (c = rsqrt(1 + t^2), s = t c), small columns are never mixed into large ones beyond
-// eps, and the wanted (largest) eigenpairs come out with relative accuracy eps * lambda_0 / lambda_i.
+//   1. Pivoted Cholesky  Pi G Pi' = L L'  (in place, one CTA; a pivot below K eps * trace ends it: the remaining
+//      columns are the numerical null space).  The columns of L come out with decreasing norms, the order in which a
+//      one-sided Jacobi method converges fastest, and their singular values are sqrt(lambda): half the dynamic range
+//      (in digits) of the Gram's own columns -- 7 sweeps where Jacobi on G itself took 17 for BASELINE's construction.
+//   2. One-sided (Hestenes) Jacobi on the COLUMNS of L: a rotation of columns (p, q) needs their three inner products
+//      and touches those two columns only, so a half warp owns a pair, the inner products are shuffle reductions and
+//      ONE barrier per round-robin round is all the synchronisation there is (the two-sided solver of round 1 rotated
+//      rows and columns: two block-wide barriers per round around a serial rotation-parameter phase, 3.9 us per
+//      round, 4.6 ms at K = 100).  tan(theta) is computed in FP32 from exponent-aligned inputs and polished by one
+//      Newton step in FP64; c = rsqrt(1 + t^2), s = t c are orthogonal to working precision by construction, so
+//      accuracy does not depend on t -- only the convergence rate does.
+//   3. With the columns mutually orthogonal,  L V = U S:  lambda_i = |column i|^2 and Pi' u_i is the eigenvector.
 //   K <= 160: one CTA, the matrix lives in shared memory.  Larger K (README's batchsize-1 loader gives K = 1000, SURVEY
 //   Q3): a cooperative grid with the matrix in global memory (L2-resident) and a grid barrier per round; no pair tables,
 //   so K is limited by memory only (ssi_swa_* accept K <= 16384).
@@ -207,27 +221,88 @@ __device__ __forceinline__ void osj_grid_barrier(unsigned* counter, unsigned& ta
     }
 }
 
+// Pi G Pi' = L L' in place (full symmetric storage in, lower triangle out, strict upper triangle and the columns past the
+// numerical rank zeroed); perm[r] = original index of row r.  One CTA.
+__device__ void osj_pivoted_cholesky(double* __restrict__ G, int K, int* __restrict__ perm, double thresh, double* red, int* redi) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    for (int i = tid; i < K; i += nt) perm[i] = i;
+    __syncthreads();
+    int rank = K;
+    for (int j = 0; j < K; ++j) {
+        // pivot = largest remaining diagonal entry (ties: smallest index)
+        double best = -1.0;
+        int bi = j;
+        for (int i = j + tid; i < K; i += nt) {
+            const double v = G[i + (long long)i * K];
+            if (v > best) { best = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { red[warp] = best; redi[warp] = bi; }
+        __syncthreads();
+        best = red[0]; bi = redi[0];
+        for (int w = 1; w < nw; ++w)
+            if (red[w] > best || (red[w] == best && redi[w] < bi)) { best = red[w]; bi = redi[w]; }
+        __syncthreads();
+        if (!(best > thresh)) { rank = j; break; }
+        if (bi != j) {       // symmetric swap j <-> bi: the two rows, then the two columns
+            for (int k = tid; k < K; k += nt) { const double t = G[j + (long long)k * K]; G[j + (long long)k * K] = G[bi + (long long)k * K]; G[bi + (long long)k * K] = t; }
+            __syncthreads();
+            for (int k = tid; k < K; k += nt) { const double t = G[k + (long long)j * K]; G[k + (long long)j * K] = G[k + (long long)bi * K]; G[k + (long long)bi * K] = t; }
+            if (tid == 0) { const int t = perm[j]; perm[j] = perm[bi]; perm[bi] = t; }
+            __syncthreads();
+        }
+        const double ljj = sqrt(best), inv = 1.0 / ljj;
+        for (int i = j + tid; i < K; i += nt) G[i + (long long)j * K] = (i == j) ? ljj : G[i + (long long)j * K] * inv;
+        __syncthreads();
+        // trailing update, lower triangle: G[i, k] -= L[i, j] L[k, j] for j < k <= i
+        const int r = K - 1 - j;
+        for (long long e = tid; e < (long long)r * r; e += nt) {
+            const int k = j + 1 + (int)(e / r), i = j + 1 + (int)(e % r);
+            if (i >= k) G[i + (long long)k * K] = fma(-G[i + (long long)j * K], G[k + (long long)j * K], G[i + (long long)k * K]);
+        }
+        __syncthreads();
+        // the pivot search reads the diagonal only, the swaps read full rows: keep the matrix symmetric
+        for (long long e = tid; e < (long long)r * r; e += nt) {
+            const int k = j + 1 + (int)(e / r), i = j + 1 + (int)(e % r);
+            if (i > k) G[k + (long long)i * K] = G[i + (long long)k * K];
+        }
+        __syncthreads();
+    }
+    for (long long e = tid; e < (long long)K * K; e += nt) {
+        const int i = (int)(e % K), k = (int)(e / K);
+        if (i < k || k >= rank) G[e] = 0.0;
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(OSJ_THREADS)
-k_osj(double* __restrict__ Gg /* K x K column-major; on exit the rotated columns G V */, int K, int max_sweeps,
+k_osj(double* __restrict__ Gg /* K x K column-major Gram; on exit the orthogonalised columns of its Cholesky factor */, int K, int max_sweeps,
       unsigned* __restrict__ sync_counter /* zeroed */, unsigned* __restrict__ rot_count /* [3], zeroed */,
-      int* __restrict__ sweeps_out, int use_smem) {
+      int* __restrict__ perm /* K: row r of the result is original index perm[r] */, int* __restrict__ sweeps_out, int use_smem) {
     extern __shared__ double osj_smem[];
     double* G = use_smem ? osj_smem : Gg;
     __shared__ double red[32];
-    __shared__ double s_null;
+    __shared__ int redi[32];
+    __shared__ double s_tr;
     const int tid = threadIdx.x, nt = blockDim.x;
     const unsigned nb = gridDim.x;
     unsigned target = 0;
-    // columns whose squared norm is below (K eps trace)^2 are numerically in the null space: pairs of two such columns
-    // are left alone (they are never among the wanted directions)
-    double tr = 0.0;
-    for (int i = tid; i < K; i += nt) tr += fabs(Gg[i + (long long)i * K]);
-    tr = ssi_block_sum(tr, red);
-    if (tid == 0) { const double e = (double)K * 2.220446049250313e-16 * tr; s_null = e * e; }
-    if (use_smem)
-        for (long long e = tid; e < (long long)K * K; e += nt) G[e] = Gg[e];
-    __syncthreads();
-    const double nul = s_null;
+    if (blockIdx.x == 0) {
+        double tr = 0.0;
+        for (int i = tid; i < K; i += nt) tr += fabs(Gg[i + (long long)i * K]);
+        tr = ssi_block_sum(tr, red);
+        if (tid == 0) s_tr = tr;
+        if (use_smem)
+            for (long long e = tid; e < (long long)K * K; e += nt) G[e] = Gg[e];
+        __syncthreads();
+        osj_pivoted_cholesky(G, K, perm, (double)K * 2.220446049250313e-16 * s_tr, red, redi);
+    }
+    osj_grid_barrier(sync_counter, target, nb);          // the other CTAs of a cooperative grid wait for the factor
     const double tol = (double)K * 2.220446049250313e-16, tol2 = tol * tol;
 
     const int m = (K + 1) & ~1;                  // even number of players; index K (if any) is a bye
@@ -260,11 +335,18 @@ k_osj(double* __restrict__ Gg /* K x K column-major; on exit the rotated columns
                     b += __shfl_xor_sync(hmask, b, o);
                     c += __shfl_xor_sync(hmask, c, o);
                 }
-                if (c * c <= tol2 * a * b || (a < nul && b < nul)) continue;
-                // tan(theta) of the rotation that makes the two columns orthogonal; c^2 + s^2 = 1 to working precision
+                if (c * c <= tol2 * a * b) continue;              // already orthogonal (also: a null column)
+                // tan(theta) of the rotation that makes the two columns orthogonal solves  h t^2 + 2 d t - h = 0,
+                // d = |g_q|^2 - |g_p|^2, h = 2 g_p.g_q: the root of smaller magnitude, t = h / (d + sign(d) sqrt(d^2 + h^2)).
+                // FP32 on exponent-aligned copies, then one Newton step in FP64 (the divisor again in FP32).
                 const double d = b - a, h = 2.0 * c;
-                const double rr = sqrt(fma(d, d, h * h));
-                const double t = h / (d + (d >= 0.0 ? rr : -rr));
+                const int ex = max(__double2hiint(fabs(d)), __double2hiint(fabs(h))) >> 20;      // biased exponent of the larger
+                const double sc = __hiloint2double((2046 - ex) << 20, 0);                          // 2^-(exponent): both fit FP32 after scaling
+                const float df = (float)(d * sc), hf = (float)(h * sc);
+                const float rf = sqrtf(fmaf(df, df, hf * hf));
+                double t = (double)(hf / (df + copysignf(rf, df)));
+                const double f = fma(h * t, t, fma(2.0 * d, t, -h));
+                t -= f * (double)(1.0f / (float)((2.0 * (h * t + d)) * sc)) * sc;
                 const double cs = rsqrt(fma(t, t, 1.0)), sn = t * cs;
                 for (int k = hl; k < K; k += 16) {
                     const double x = gp[k], y = gq[k];
@@ -284,100 +366,292 @@ k_osj(double* __restrict__ Gg /* K x K column-major; on exit the rotated columns
     if (blockIdx.x == 0 && tid == 0) *sweeps_out = converged ? sweep : max_sweeps + 1;
 }
 
-// eigenvalues = norms of the orthogonalised columns, rank-sorted descending (ties by index); eigenvectors = the
-// normalised columns, written to V (K x K).  One warp per column, then one thread per eigenvalue.
+// The same solver for K <= 160 on a CLUSTER of 8 CTAs (distributed shared memory): on one SM the ~K^2 / 2 column updates of a
+// round are issue-bound (2.7 us per round at K = 100, measured); spread over eight SMs a round costs one pair's
+// latency chain plus a hardware cluster barrier.  Every CTA starts from its own copy of the Cholesky factor (computed
+// redundantly, bit-identically).  In every round a CTA orthogonalises the pairs that fall to its half warps, reading
+// its LOCAL shared memory, and writes each of the two columns -- rotated or not -- into the shared memory of the ONE CTA
+// that will own it in the next round (st.shared::cluster; the round-robin schedule is a closed formula, so the next
+// owner is computed, not communicated).  A column is thus valid exactly where it is needed: 2 column transfers per pair
+// and round (80 KB per round over the whole cluster at K = 100) instead of a broadcast.
+#define OSJC_CTAS 8
+#define OSJC_THREADS 256
+#define OSJC_HW (OSJC_THREADS / 16)        // half warps (pairs) per CTA and pass
+__device__ __forceinline__ uint32_t osjc_mapa(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void osjc_st_f64(uint32_t cluster_addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(cluster_addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void osjc_st_u32(uint32_t cluster_addr, unsigned v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+// pairs of round r: slot 0 = (m - 1, r), slot i = ((r + i) mod (m - 1), (r - i) mod (m - 1)); slot i belongs to half warp
+// i mod (8 * 16), i.e. to CTA (i mod 128) / 16
+__device__ __forceinline__ int osjc_owner(int x, int r, int m) {
+    int i;
+    if (x == m - 1 || x == r) i = 0;
+    else {
+        i = x - r; if (i < 0) i += m - 1;                  // x = (r + i) mod (m - 1)
+        if (i >= m / 2) i = (m - 1) - i;                   // else x = (r - i) mod (m - 1)
+    }
+    return (i % (OSJC_CTAS * OSJC_HW)) / OSJC_HW;
+}
+__global__ void __cluster_dims__(OSJC_CTAS, 1, 1) __launch_bounds__(OSJC_THREADS)
+k_osj_cluster(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__ perm_out, int* __restrict__ sweeps_out) {
+    extern __shared__ double osj_smem[];
+    double* G = osj_smem;                                     // K x K
+    int* s_perm = reinterpret_cast<int*>(G + (size_t)K * K);  // K
+    __shared__ double red[32];
+    __shared__ int redi[32];
+    __shared__ double s_tr;
+    __shared__ unsigned s_cnt, s_slot[OSJC_CTAS], s_mx, s_mxslot[OSJC_CTAS];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t rank = cluster_ctarank();
+    {
+        double tr = 0.0;
+        for (int i = tid; i < K; i += nt) tr += fabs(Gg[i + (long long)i * K]);
+        tr = ssi_block_sum(tr, red);
+        if (tid == 0) { s_tr = tr; s_cnt = 0; s_mx = 0; }
+        for (long long e = tid; e < (long long)K * K; e += nt) G[e] = Gg[e];
+        __syncthreads();
+        osj_pivoted_cholesky(G, K, s_perm, (double)K * 2.220446049250313e-16 * s_tr, red, redi);
+    }
+    cluster_sync_all();
+    const double tol = (double)K * 2.220446049250313e-16, tol2 = tol * tol;
+    const int m = (K + 1) & ~1, np = m / 2;
+    const int hw = (int)rank * OSJC_HW + (tid >> 4), n_hw = OSJC_CTAS * OSJC_HW;
+    const int hl = tid & 15;
+    const unsigned hmask = 0xffffu << (tid & 16);
+    const uint32_t g_local = smem_u32(G);
+    int sweep = 0;
+    bool converged = false;
+    for (; sweep < max_sweeps; ++sweep) {
+        for (int r = 0; r < m - 1; ++r) {
+            const int rn = (r + 1 == m - 1) ? 0 : r + 1;                  // the schedule is cyclic across sweeps
+            for (int i = hw; i < np; i += n_hw) {
+                int p, q;
+                if (i == 0) { p = m - 1; q = r; }
+                else { p = r + i; if (p >= m - 1) p -= m - 1; q = r - i; if (q < 0) q += m - 1; }
+                if (p > q) { const int t = p; p = q; q = t; }
+                const double* gp = G + (long long)p * K;
+                const uint32_t dst_p = osjc_mapa(g_local, (uint32_t)osjc_owner(p, rn, m)) + (uint32_t)(p * K) * 8u;
+                if (q >= K) {                                               // bye: the column only moves on
+                    for (int k = hl; k < K; k += 16) osjc_st_f64(dst_p + (uint32_t)k * 8u, gp[k]);
+                    continue;
+                }
+                const double* gq = G + (long long)q * K;
+                const uint32_t dst_q = osjc_mapa(g_local, (uint32_t)osjc_owner(q, rn, m)) + (uint32_t)(q * K) * 8u;
+                double a = 0.0, b = 0.0, c = 0.0;
+                for (int k = hl; k < K; k += 16) {
+                    const double x = gp[k], y = gq[k];
+                    a = fma(x, x, a); b = fma(y, y, b); c = fma(x, y, c);
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(hmask, a, o);
+                    b += __shfl_xor_sync(hmask, b, o);
+                    c += __shfl_xor_sync(hmask, c, o);
+                }
+                const double c2 = c * c, ab = a * b;
+                double cs = 1.0, sn = 0.0;
+                if (c2 > tol2 * ab) {
+                    const double d = b - a, h = 2.0 * c;
+                    const int ex = max(__double2hiint(fabs(d)), __double2hiint(fabs(h))) >> 20;
+                    const double sc = __hiloint2double((2046 - ex) << 20, 0);
+                    const float df = (float)(d * sc), hf = (float)(h * sc);
+                    const float rf = sqrtf(fmaf(df, df, hf * hf));
+                    double t = (double)(hf / (df + copysignf(rf, df)));
+                    const double f = fma(h * t, t, fma(2.0 * d, t, -h));
+                    t -= f * (double)(1.0f / (float)((2.0 * (h * t + d)) * sc)) * sc;
+                    cs = rsqrt(fma(t, t, 1.0));
+                    sn = t * cs;
+                    if (hl == 0) {
+                        atomicAdd(&s_cnt, 1u);
+                        atomicMax(&s_mx, __float_as_uint((float)(c2 / ab)));     // largest cos^2 rotated away in this sweep
+                    }
+                }
+                for (int k = hl; k < K; k += 16) {
+                    const double x = gp[k], y = gq[k];
+                    osjc_st_f64(dst_p + (uint32_t)k * 8u, cs * x - sn * y);
+                    osjc_st_f64(dst_q + (uint32_t)k * 8u, sn * x + cs * y);
+                }
+            }
+            if (r == m - 2) {       // last round of the sweep: publish this CTA's rotation count before the barrier
+                __syncthreads();
+                if (tid < OSJC_CTAS) {
+                    osjc_st_u32(osjc_mapa(smem_u32(&s_slot[rank]), (uint32_t)tid), s_cnt);
+                    osjc_st_u32(osjc_mapa(smem_u32(&s_mxslot[rank]), (uint32_t)tid), s_mx);
+                }
+            }
+            cluster_sync_all();
+        }
+        unsigned total = 0, mx = 0;
+#pragma unroll
+        for (int c = 0; c < OSJC_CTAS; ++c) { total += s_slot[c]; mx = max(mx, s_mxslot[c]); }
+        __syncthreads();
+        if (tid == 0) { s_cnt = 0; s_mx = 0; }
+        __syncthreads();
+        // converged when nothing was rotated, or when every rotation of the sweep was so small (cos < 3e-8) that what it
+        // leaves behind is of second order, cos^2 < 1e-15 (quadratic convergence of the Jacobi method)
+        if (total == 0u || __uint_as_float(mx) < 1e-15f) { ++sweep; converged = true; break; }
+    }
+    // every column is valid in the CTA that owns it in round 0 (the round after the last one): that CTA writes it out
+    for (int i = hw; i < np; i += n_hw) {
+        int p = (i == 0) ? m - 1 : i, q = (i == 0) ? 0 : m - 1 - i;        // round 0: (r + i, r - i) mod (m - 1) with r = 0
+        for (int k = hl; k < K; k += 16) {
+            if (p < K) Gg[k + (long long)p * K] = G[k + (long long)p * K];
+            if (q < K) Gg[k + (long long)q * K] = G[k + (long long)q * K];
+        }
+    }
+    cluster_sync_all();           // no CTA leaves while a peer may still write into its shared memory
+    if (rank == 0) {
+        for (int i = tid; i < K; i += nt) perm_out[i] = s_perm[i];
+        if (tid == 0) *sweeps_out = converged ? sweep : max_sweeps + 1;
+    }
+}
+
+// eigenvalues = squared norms of the orthogonalised columns, rank-sorted descending (ties by index); eigenvectors = the
+// normalised columns with their rows sent back through the pivoting permutation, written to V (K x K).  One warp per column.
 __global__ void __launch_bounds__(256)
-k_osj_norms(const double* __restrict__ G, int K, double* __restrict__ norms) {
+k_osj_norms(const double* __restrict__ G, int K, double* __restrict__ norms2) {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= K) return;
     double a = 0.0;
     for (int k = lane; k < K; k += 32) { const double x = G[k + (long long)c * K]; a = fma(x, x, a); }
     a = ssi_warp_sum(a);
-    if (lane == 0) norms[c] = sqrt(a);
+    if (lane == 0) norms2[c] = a;
 }
 __global__ void __launch_bounds__(256)
-k_osj_sort_normalise(double* __restrict__ G, int K, const double* __restrict__ norms, double* __restrict__ lambda, int* __restrict__ order,
-                     double* __restrict__ V) {
+k_osj_sort_normalise(const double* __restrict__ G, int K, const double* __restrict__ norms2, const int* __restrict__ perm,
+                     double* __restrict__ lambda, int* __restrict__ order, double* __restrict__ V) {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= K) return;
-    const double li = norms[c];
+    const double li = norms2[c];
     int rank = 0;
-    for (int j = lane; j < K; j += 32) { const double lj = norms[j]; rank += (lj > li) || (lj == li && j < c); }
+    for (int j = lane; j < K; j += 32) { const double lj = norms2[j]; rank += (lj > li) || (lj == li && j < c); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
     if (lane == 0) { lambda[rank] = li; order[rank] = c; }
-    // the eigenvector keeps the sign of its largest component positive?  No: signs are arbitrary, as psvd's are
-    const double inv = li > 0.0 ? 1.0 / li : 0.0;
-    for (int k = lane; k < K; k += 32) V[k + (long long)c * K] = G[k + (long long)c * K] * inv;
+    const double inv = li > 0.0 ? rsqrt(li) : 0.0;         // signs are arbitrary, as psvd's are
+    for (int k = lane; k < K; k += 32) V[perm[k] + (long long)c * K] = G[k + (long long)c * K] * inv;
 }
 
 // ======================================================================================
 // K8: P = A V_M  (second pass over A; V_M staged in shared memory, zero-padded to MP columns)
 // ======================================================================================
-#define FORMP_CONST_MAX 16384
-__constant__ float c_formp_v[FORMP_CONST_MAX];     // V_M as [K][MP] floats, zero padded
-
-__global__ void k_pack_v(const double* __restrict__ V, const int* __restrict__ order, int K, int M, int MP, float* __restrict__ out) {
+// V_M as [Kpad][MP] floats, zero padded in both directions (Kpad = K rounded up to the stage width of k_form_p_tma)
+__global__ void k_pack_v(const double* __restrict__ V, const int* __restrict__ order, int K, int Kpad, int M, int MP, float* __restrict__ out) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= K * MP) return;
+    if (e >= Kpad * MP) return;
     const int k = e / MP, j = e % MP;
-    out[e] = j < M ? (float)V[k + (long long)order[j] * K] : 0.0f;
+    out[e] = (j < M && k < K) ? (float)V[k + (long long)order[j] * K] : 0.0f;
 }
 
-// P = A V_M with V_M in the constant bank: the FMAs take V as a uniform operand, no shared-memory traffic.
-// R consecutive rows per thread (one 4R-byte load per column: a warp reads 128 R contiguous bytes of each column); R = 4 while
-// the R x MP accumulators fit the register file (MP <= 20), 2 up to MP = 32, 1 beyond (4 x 64 accumulators spilled 15 KB).
-template <int MP, int R>
-__global__ void __launch_bounds__(128)
-k_form_p_const(const float* __restrict__ A, long long n, long long ld, int K, int M, float* __restrict__ P) {
-    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * R;
-    if (i >= n) return;
-    float acc[R][MP];
+// P = A V_M as a stream through shared memory.  Per row of P the kernel spends K * M multiply-adds on 4 K bytes of A
+// (50 flop/B at K = 100, M = 20): on CUDA cores the FMA pipe and HBM are busy to the same degree, so the loads must not
+// cost the compute warps a single stall.  A TMA producer warp therefore keeps a ring of 5 stages (8 columns x 1024 rows
+// of A each) in flight, and the 8 compute warps -- 4 consecutive rows x MP outputs per thread, 80 accumulators for
+// MP = 20 -- read their operands from shared memory only: one 16-byte load of A and MP / 4 broadcast loads of V per 4 MP
+// FMAs.  (Round 1 loaded A straight from global memory into registers with V in the constant bank: 124 registers per
+// thread left 16 warps per SM to cover DRAM latency, 71 % of the HBM peak with the FMA pipe half idle; and the
+// module-global constant bank was shared by every context of a device.)  V lives in this CTA's shared memory now.
+#define FP_ROWS 1024
+#define FP_KC 8
+#define FP_STAGES 5
+#define FP_STAGE_BYTES (FP_KC * FP_ROWS * 4)
+#define FP_COMPUTE 256
+#define FP_THREADS (FP_COMPUTE + 32)
+template <int MP>
+__global__ void __launch_bounds__(FP_THREADS, 1)
+k_form_p_tma(const __grid_constant__ CUtensorMap tmA /* {n, K} FP32, box {256 rows, FP_KC columns} */, const float* __restrict__ Vp /* [Kpad][MP] */,
+             long long n, int Kpad, int M, float* __restrict__ P, int n_tiles) {
+    extern __shared__ __align__(1024) uint8_t fp_smem[];
+    float* Vs = reinterpret_cast<float*>(fp_smem + FP_STAGES * FP_STAGE_BYTES);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(fp_smem + FP_STAGES * FP_STAGE_BYTES + (size_t)Kpad * MP * 4);
+    const uint32_t smem_base = smem_u32(fp_smem);
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + 8 * FP_STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < FP_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, FP_COMPUTE / 32); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+    }
+    for (int e = threadIdx.x; e < Kpad * MP; e += FP_THREADS) Vs[e] = Vp[e];
+    __syncthreads();
+    const int k_stages = Kpad / FP_KC;
+
+    if (warp == FP_COMPUTE / 32) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int ks = 0; ks < k_stages; ++ks) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t full = bar_full + 8 * stage;
+                    mbar_expect_tx(full, FP_STAGE_BYTES);                   // rows / columns past the edge arrive as zeros
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int j = 0; j < MP; ++j) acc[r][j] = 0.0f;
-    if (i + R - 1 < n) {
-        // 10 independent loads in flight per thread (latency-bound otherwise: ncu showed 48 % DRAM, 24 % occupancy)
-#pragma unroll 10
-        for (int k = 0; k < K; ++k) {
-            float d[R];
-            if (R == 4) {
-                const float4 d4 = __ldcs(reinterpret_cast<const float4*>(A + i + (long long)k * ld));
-                d[0] = d4.x; d[1 % R] = d4.y; d[2 % R] = d4.z; d[3 % R] = d4.w;
-            } else if (R == 2) {
-                const float2 d2 = __ldcs(reinterpret_cast<const float2*>(A + i + (long long)k * ld));
-                d[0] = d2.x; d[1 % R] = d2.y;
-            } else {
-                d[0] = __ldcs(A + i + (long long)k * ld);
-            }
-#pragma unroll
-            for (int j = 0; j < MP; ++j) {
-                const float v = c_formp_v[k * MP + j];
-#pragma unroll
-                for (int r = 0; r < R; ++r) acc[r][j] = fmaf(d[r], v, acc[r][j]);
+                    for (int b = 0; b < FP_ROWS / 256; ++b)
+                        tma_load_2d_hint(smem_base + stage * FP_STAGE_BYTES + b * (FP_KC * 256 * 4), &tmA, full,
+                                         (int)((long long)tile * FP_ROWS + b * 256), ks * FP_KC, TC_EVICT_FIRST);     // A is read once
+                    if (++stage == FP_STAGES) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else {
-        for (int k = 0; k < K; ++k)
+        // ================= compute: 4 consecutive rows x MP columns of P per thread =================
+        const int t = threadIdx.x;
+        const uint32_t my = (uint32_t)(t >> 6) * (FP_KC * 256 * 4) + (uint32_t)(t & 63) * 16;       // box t / 64, rows 4 (t % 64) ..
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            float acc[4][MP];
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-                if (i + r < n) {
-                    const float d = A[i + r + (long long)k * ld];
+            for (int r = 0; r < 4; ++r)
 #pragma unroll
-                    for (int j = 0; j < MP; ++j) acc[r][j] = fmaf(d, c_formp_v[k * MP + j], acc[r][j]);
+                for (int j = 0; j < MP; ++j) acc[r][j] = 0.0f;
+            for (int ks = 0; ks < k_stages; ++ks) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                const float* sA = reinterpret_cast<const float*>(fp_smem + stage * FP_STAGE_BYTES + my);
+                const float* sV = Vs + ks * FP_KC * MP;
+#pragma unroll
+                for (int c = 0; c < FP_KC; ++c) {
+                    const float4 d = *reinterpret_cast<const float4*>(sA + c * 256);
+                    float v[MP];
+#pragma unroll
+                    for (int j = 0; j < MP; j += 4) {
+                        const float4 v4 = *reinterpret_cast<const float4*>(sV + c * MP + j);
+                        v[j] = v4.x; v[j + 1] = v4.y; v[j + 2] = v4.z; v[j + 3] = v4.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < MP; ++j) {
+                        acc[0][j] = fmaf(d.x, v[j], acc[0][j]);
+                        acc[1][j] = fmaf(d.y, v[j], acc[1][j]);
+                        acc[2][j] = fmaf(d.z, v[j], acc[2][j]);
+                        acc[3][j] = fmaf(d.w, v[j], acc[3][j]);
+                    }
                 }
-    }
-    const bool vec = (R == 4) && (i + 3 < n) && ((n & 3) == 0);      // columns of P are n apart: 16-byte stores need n % 4 == 0
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8 * stage);          // this warp is done reading the stage
+                if (++stage == FP_STAGES) { stage = 0; phase ^= 1; }
+            }
+            const long long i = (long long)tile * FP_ROWS + 4 * t;
+            if (i + 3 < n && (n & 3) == 0) {          // columns of P are n apart: 16-byte stores need n % 4 == 0
 #pragma unroll
-    for (int j = 0; j < MP; ++j) {
-        if (j >= M) break;
-        if (vec) {
-            __stcs(reinterpret_cast<float4*>(P + i + (long long)j * n), make_float4(acc[0][j], acc[1 % R][j], acc[2 % R][j], acc[3 % R][j]));
-        } else {
+                for (int j = 0; j < MP; ++j)
+                    if (j < M) __stcs(reinterpret_cast<float4*>(P + i + (long long)j * n), make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]));
+            } else {
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-                if (i + r < n) P[i + r + (long long)j * n] = acc[r][j];
+                for (int j = 0; j < MP; ++j)
+                    if (j < M) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            if (i + r < n) P[i + r + (long long)j * n] = acc[r][j];
+                    }
+            }
         }
     }
 }
@@ -423,14 +697,29 @@ k_form_p(const float* __restrict__ A, long long n, long long ld, int K, const do
 
 template <int MP>
 static int launch_form_p(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int K, const double* dV, const int* dOrder, int M, float* dP) {
-    if ((size_t)K * MP <= FORMP_CONST_MAX) {
-        SSI_TRY(ssi_reserve(ctx, ctx->bSnap, sizeof(float) * FORMP_CONST_MAX));
+    const int Kpad = (K + FP_KC - 1) / FP_KC * FP_KC;
+    const size_t v_bytes = sizeof(float) * (size_t)Kpad * MP;
+    const size_t smem_tma = (size_t)FP_STAGES * FP_STAGE_BYTES + v_bytes + 2 * FP_STAGES * 8;
+    if (MP <= 32 && smem_tma <= ctx->smem_optin && (ld % 4) == 0 && ((reinterpret_cast<uintptr_t>(dA) & 15) == 0) && n < (1ll << 31) &&
+        !ctx->opt_formp_simt) {
+        PFN_ssi_encodeTiled encode = nullptr;
+        SSI_TRY(ssi_tensormap_encoder(ctx, &encode));
+        CUtensorMap map;
+        cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)K};
+        cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+        cuuint32_t box[2] = {256, FP_KC};
+        cuuint32_t estr[2] = {1, 1};
+        const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(dA), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return ssi_fail(ctx, SSI_ERR_CUDA, "cuTensorMapEncodeTiled (form P) failed with CUresult %d", (int)r);
+        SSI_TRY(ssi_reserve(ctx, ctx->bSnap, v_bytes));
         float* stage = (float*)ctx->bSnap.p;
-        k_pack_v<<<(K * MP + 255) / 256, 256, 0, ctx->stream>>>(dV, dOrder, K, M, MP, stage);
+        k_pack_v<<<(Kpad * MP + 255) / 256, 256, 0, ctx->stream>>>(dV, dOrder, K, Kpad, M, MP, stage);
         SSI_LAUNCH_CHECK(ctx);
-        SSI_CUDA(ctx, cudaMemcpyToSymbolAsync(c_formp_v, stage, sizeof(float) * (size_t)K * MP, 0, cudaMemcpyDeviceToDevice, ctx->stream));
-        constexpr int R = MP <= 20 ? 4 : (MP <= 32 ? 2 : 1);
-        k_form_p_const<MP, R><<<(unsigned)((n + 128 * R - 1) / (128 * R)), 128, 0, ctx->stream>>>(dA, n, ld, K, M, dP);
+        const int n_tiles = (int)((n + FP_ROWS - 1) / FP_ROWS);
+        SSI_CUDA(ctx, cudaFuncSetAttribute(k_form_p_tma<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
+        k_form_p_tma<MP><<<std::min(ctx->sm_count, n_tiles), FP_THREADS, smem_tma, ctx->stream>>>(map, stage, n, Kpad, M, dP, n_tiles);
         SSI_LAUNCH_CHECK(ctx);
         return SSI_OK;
     }
@@ -478,12 +767,12 @@ __global__ void k_singular_values(const double* __restrict__ lambda, int K, doub
 // runs the (replicated) eigen stage and forms the P rows of its shard.
 struct swa_eig_t {
     double *dG, *dV, *dLam, *dRisk, *dNorms;
-    int *dOrder, *dSweeps;
+    int *dOrder, *dSweeps, *dPerm;
 };
 static int swa_eig_layout(ssi_ctx* ctx, int K, swa_eig_t& e) {
-    // layout of bEig: G (K*K) | V (K*K) | lambda (K) | norms (K) | risk | order (K ints) | sweeps (int) | 4 counters
+    // layout of bEig: G (K*K) | V (K*K) | lambda (K) | norms (K) | risk | order (K ints) | sweeps (int) | 4 counters | 3 pad | perm (K ints)
     const size_t KK = (size_t)K * K;
-    SSI_TRY(ssi_reserve(ctx, ctx->bEig, sizeof(double) * (2 * KK + 2 * K + 1) + sizeof(int) * (K + 8)));
+    SSI_TRY(ssi_reserve(ctx, ctx->bEig, sizeof(double) * (2 * KK + 2 * K + 1) + sizeof(int) * (2 * K + 8)));
     e.dG = (double*)ctx->bEig.p;
     e.dV = e.dG + KK;
     e.dLam = e.dV + KK;
@@ -491,6 +780,7 @@ static int swa_eig_layout(ssi_ctx* ctx, int K, swa_eig_t& e) {
     e.dRisk = e.dNorms + K;
     e.dOrder = (int*)(e.dRisk + 1);
     e.dSweeps = e.dOrder + K;
+    e.dPerm = e.dSweeps + 8;
     return SSI_OK;
 }
 static int swa_check_shape(ssi_ctx* ctx, int M) {
@@ -508,7 +798,7 @@ int ssi_swa_gram_stage(ssi_ctx* ctx, bool exact, double* dG_dst, bool* used_tens
     const int K = (int)ctx->swa_K;
     const bool tensor = !exact && ssi_gram_tc_usable(ctx, ctx->dDev, n, ctx->swa_ld, K);
     if (used_tensor) *used_tensor = tensor;
-    return ssi_gram_device(ctx, ctx->dDev, n, ctx->swa_ld, K, dG_dst, tensor);
+    return ssi_gram_device(ctx, ctx->dDev, n, ctx->swa_ld, K, dG_dst, tensor, ctx->dSwaAmax);
 }
 
 // Eigen-solve of the Gram in dG_src (device; copied, not destroyed).  With `check`, evaluates the conditioning estimate
@@ -532,20 +822,26 @@ int ssi_swa_eigen_stage(ssi_ctx* ctx, int M, const double* dG_src, bool check, b
         const int np = (K + 1) / 2;
         grid = std::max(1, std::min(ctx->sm_count, (np * 16 + OSJ_THREADS - 1) / OSJ_THREADS));
     }
-    {
+    if (use_smem && !ctx->opt_eig_single) {
+        // a cluster of 8 CTAs, every one with a copy of the matrix in its shared memory
+        const size_t csm = jsm + sizeof(int) * (size_t)K;
+        SSI_CUDA(ctx, cudaFuncSetAttribute(k_osj_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+        k_osj_cluster<<<OSJC_CTAS, OSJC_THREADS, csm, ctx->stream>>>(e.dG, K, 60, e.dPerm, e.dSweeps);
+    } else {
         double* Gp = e.dG;
         int Kv = K, ms = 60, us = use_smem;
         unsigned* sc = d_sync;
         unsigned* rc = d_sync + 1;
         int* so = e.dSweeps;
-        void* args[] = {&Gp, &Kv, &ms, &sc, &rc, &so, &us};
+        int* pm = e.dPerm;
+        void* args[] = {&Gp, &Kv, &ms, &sc, &rc, &pm, &so, &us};
         if (grid > 1) SSI_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_osj, dim3(grid), dim3(OSJ_THREADS), args, jsm, ctx->stream));
         else SSI_CUDA(ctx, cudaLaunchKernel((const void*)k_osj, dim3(1), dim3(OSJ_THREADS), args, jsm, ctx->stream));
     }
     SSI_LAUNCH_CHECK(ctx);
     k_osj_norms<<<(K * 32 + 255) / 256, 256, 0, ctx->stream>>>(e.dG, K, e.dNorms);
     SSI_LAUNCH_CHECK(ctx);
-    k_osj_sort_normalise<<<(K * 32 + 255) / 256, 256, 0, ctx->stream>>>(e.dG, K, e.dNorms, e.dLam, e.dOrder, e.dV);
+    k_osj_sort_normalise<<<(K * 32 + 255) / 256, 256, 0, ctx->stream>>>(e.dG, K, e.dNorms, e.dPerm, e.dLam, e.dOrder, e.dV);
     SSI_LAUNCH_CHECK(ctx);
     if (need_exact) *need_exact = false;
     if (!check) return SSI_OK;

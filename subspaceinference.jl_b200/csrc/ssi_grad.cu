@@ -179,6 +179,7 @@ int ssi_logpost_grad_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sig
     if (!ctx->has_model || !ctx->has_data || !ctx->has_sub)
         return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before evaluating the gradient");
     if (B <= 0) return SSI_OK;
+    if (ctx->dec_active) return ssi_dec_logpost_grad(ctx, dZ, B, sigma_m, sigma_p, sigma_z, mask, d_lp, d_grad);
     if (!(sigma_m > 0) || !(sigma_p > 0) || !(sigma_z > 0))
         return ssi_fail(ctx, SSI_ERR_ARG, "sigma_m, sigma_p, sigma_z must be positive");
     if ((mask & ~(SSI_TERM_LL | SSI_TERM_PRIOR_W | SSI_TERM_PRIOR_Z)) || mask == 0)

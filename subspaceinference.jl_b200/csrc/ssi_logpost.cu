@@ -282,9 +282,11 @@ __global__ void k_finalize(const finalize_args_t a, const double* __restrict__ s
 // LAYERED path
 // ======================================================================================
 // W[g][i] = W_swa[i] + sum_m P[i,m] z[m,g]      (src/space_inference.jl:91; K1)
+// With a decoder whose head is not affine (ssi_decoder.cu): W = Wbase + act(W_swa' + P z), W_swa' being the head's bias.
 __global__ void __launch_bounds__(256)
 k_project(const float* __restrict__ Wswa, const float* __restrict__ P, const float* __restrict__ Z,
-          long long n, int M, int G, float* __restrict__ W /* G x n (sample-major) or n x G col-major: same */) {
+          long long n, int M, int G, float* __restrict__ W /* G x n (sample-major) or n x G col-major: same */,
+          const float* __restrict__ Wbase, int act) {
     extern __shared__ float zs[];   // M x G
     for (int e = threadIdx.x; e < M * G; e += blockDim.x) zs[e] = Z[e];
     __syncthreads();
@@ -294,10 +296,11 @@ k_project(const float* __restrict__ Wswa, const float* __restrict__ P, const flo
 #pragma unroll 4
     for (int m = 0; m < M; ++m) p[m] = P[i + (long long)m * n];
     const float w0 = Wswa[i];
+    const float wb = Wbase ? Wbase[i] : 0.0f;
     for (int g = 0; g < G; ++g) {
         float v = w0;
         for (int m = 0; m < M; ++m) v = fmaf(p[m], zs[m + g * M], v);
-        W[i + (long long)g * n] = v;
+        W[i + (long long)g * n] = Wbase ? wb + ssi_act(v, act) : v;
     }
 }
 
@@ -308,7 +311,7 @@ int ssi_project_device(ssi_ctx* ctx, const float* dZ, int64_t B, float* dW) {
     for (int64_t b0 = 0; b0 < B; b0 += gmax) {
         const int G = (int)std::min<int64_t>(gmax, B - b0);
         k_project<<<(unsigned)((n + 255) / 256), 256, sizeof(float) * M * G, ctx->stream>>>(
-            ctx->dWswa, ctx->dP, dZ + b0 * M, n, M, G, dW + b0 * n);
+            ctx->dWswa, ctx->dP, dZ + b0 * M, n, M, G, dW + b0 * n, ctx->dWbase, ctx->dec_out_act);
         SSI_LAUNCH_CHECK(ctx);
     }
     return SSI_OK;
@@ -487,6 +490,7 @@ __global__ void k_pred_std(const double* __restrict__ m2, long long ON, long lon
 // dZ (M x B), dXg (in0 x Ng) device; d_preds (O x Ng x B) optional; d_mean, d_std (O x Ng doubles); d_m2 scratch (O x Ng)
 int ssi_predict_device(ssi_ctx* ctx, const float* dZ, int64_t B, const float* dXg, int64_t Ng,
                        float* d_preds, double* d_mean, double* d_std, double* d_m2) {
+    if (ctx->dec_active) SSI_TRY(ssi_dec_project(ctx, dZ, B, &dZ));       // W = W_swa + decoder(z): continue with z' = h(z)
     const ssi_model_t& m = ctx->model;
     const int64_t n = m.n;
     const int O = m.dims[m.L];
@@ -573,6 +577,7 @@ int ssi_logpost_finalize(ssi_ctx* ctx, const double* d_sse, const float* dZ, int
 // dispatch
 // ======================================================================================
 static int choose_path(ssi_ctx* ctx) {
+    if (ctx->dWbase) return SSI_PATH_LAYERED;       // non-affine decoder head: the weights are materialised per sample
     if (ctx->opt_path != SSI_PATH_AUTO) return ctx->opt_path;
     if (ssi_tc_preferred(ctx)) return SSI_PATH_TENSOR;
     if (ssi_bm_supported(ctx) || ssi_b1_supported(ctx)) return SSI_PATH_BASIS;
@@ -587,6 +592,7 @@ int ssi_logpost_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m,
     if (!ctx->has_model || !ctx->has_data || !ctx->has_sub)
         return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before evaluating the log-posterior");
     if (B <= 0) return SSI_OK;
+    if (ctx->dec_active) return ssi_dec_logpost(ctx, dZ, B, sigma_m, sigma_p, sigma_z, mask, d_lp, d_terms);
     if (!(sigma_m > 0) || !(sigma_p > 0) || !(sigma_z > 0))
         return ssi_fail(ctx, SSI_ERR_ARG, "sigma_m, sigma_p, sigma_z must be positive");
     if ((mask & ~(SSI_TERM_LL | SSI_TERM_PRIOR_W | SSI_TERM_PRIOR_Z)) || mask == 0)

@@ -101,7 +101,7 @@ int ssi_mh_device(ssi_ctx* ctx, int kind, int64_t C, int64_t S, uint64_t seed, i
     if (step0 < 0 || (step0 > 0 && !d_z0)) return ssi_fail(ctx, SSI_ERR_ARG, "a continued run (step_offset > 0) needs the chain state z");
     if (chain_off < 0 || chain_off + C > 0xffffffffll || step0 + S > 0xffffffffll)
         return ssi_fail(ctx, SSI_ERR_ARG, "chain ids and steps must fit 32 bits");
-    const int M = ctx->M;
+    const int M = ctx->Mz;         // the sampler works in the caller's z (a decoder maps it inside the density)
     SSI_TRY(ssi_reserve(ctx, ctx->bMhZ, sizeof(float) * (size_t)M * C));
     SSI_TRY(ssi_reserve(ctx, ctx->bMhZp, sizeof(float) * (size_t)M * C));
     SSI_TRY(ssi_reserve(ctx, ctx->bMhLp, sizeof(double) * (size_t)C));

@@ -142,7 +142,13 @@ int ssi_multi_set_data(ssi_ctx* ctx, const float* X, const float* Y, int64_t N) 
 
 int ssi_multi_set_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, int64_t n, int32_t M) {
     const int rc = for_each_device(ctx, [&](ssi_ctx* c, int) { return ssi_set_subspace(c, W_swa, P, n, M); });
-    if (rc == SSI_OK) { ctx->M = M; ctx->has_sub = true; }
+    if (rc == SSI_OK) { ctx->M = M; ctx->Mz = M; ctx->has_sub = true; }
+    return rc;
+}
+
+int ssi_multi_set_decoder(ssi_ctx* ctx, const float* W_swa, int n_layers, const int32_t* dims, const int32_t* act, const float* theta) {
+    const int rc = for_each_device(ctx, [&](ssi_ctx* c, int) { return ssi_set_decoder_impl(c, W_swa, n_layers, dims, act, theta); });
+    if (rc == SSI_OK) { ctx->M = ctx->children[0]->M; ctx->Mz = ctx->children[0]->Mz; ctx->has_sub = true; }
     return rc;
 }
 
@@ -154,7 +160,7 @@ int ssi_multi_logpost(ssi_ctx* ctx, int grad, const float* Z, int64_t B, double 
         return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before evaluating the log-posterior");
     if (B == 0) return SSI_OK;
     const int n_dev = (int)ctx->children.size();
-    const int M = ctx->M;
+    const int M = ctx->Mz;
     return for_each_device(ctx, [&](ssi_ctx* c, int d) {
         int64_t b0, b1;
         shard_range(B, n_dev, d, b0, b1);
@@ -187,7 +193,7 @@ int ssi_multi_mh_get_state(ssi_ctx* ctx, float* z_out, double* lp_out) {
     if (ctx->mh_chains <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "no chains have been run on this context");
     const int n_dev = (int)ctx->children.size();
     const int64_t C = ctx->mh_chains;
-    const int M = ctx->M;
+    const int M = ctx->Mz;
     return for_each_device(ctx, [&](ssi_ctx* c, int d) {
         int64_t c0, c1;
         shard_range(C, n_dev, d, c0, c1);
@@ -200,7 +206,7 @@ int ssi_multi_project(ssi_ctx* ctx, const float* Z, int64_t B, float* W_out) {
     if (!ctx->has_model || !ctx->has_sub) return ssi_fail(ctx, SSI_ERR_STATE, "model and subspace must be set");
     if (B == 0) return SSI_OK;
     const int n_dev = (int)ctx->children.size();
-    const int M = ctx->M;
+    const int M = ctx->Mz;
     const int64_t n = ctx->model.n;
     return for_each_device(ctx, [&](ssi_ctx* c, int d) {
         int64_t b0, b1;
@@ -216,7 +222,7 @@ int ssi_multi_swa_finish(ssi_ctx* ctx, int32_t M, float* W_swa_out, float* P_out
     if (!install || ctx->children.size() == 1) {
         const int rc = ssi_swa_finish(c0, M, W_swa_out, P_out, s_out, install);
         if (rc < 0) ctx->err = c0->err;
-        else if (install) { ctx->M = M; ctx->has_sub = true; }
+        else if (install) { ctx->M = M; ctx->Mz = M; ctx->has_sub = true; }
         return rc;
     }
     const int64_t n = c0->swa_n;

@@ -60,6 +60,7 @@ struct tc_params {
     int a_il;               // A operand planes interleaved per k-block: row = [kb][hi 64 | lo 64] (the basis layer's output)
     int stages, stage_bytes;
     int mt_block;           // > 0: work order (mt block, sample, mt in block) so that concurrently running CTAs share A tiles
+    int mt_pairs;           // PAIR: row-block pairs per sample, ceil(m_tiles / 2); the odd one out gets a dummy partner
     int n_work;
     uint32_t idesc;         // instruction descriptor (operand format: FP16 or BF16 planes)
     float a_scale;          // 2^ja of the NEXT layer's A planes, applied to this layer's output before it is split (1 for BF16x3)
@@ -95,7 +96,12 @@ static int tc_smem_total(int mode) {
 #define TC_OFF_BAR (TC_OFF_BIAS + 2 * 256 * 4)
 #define TC_OFF_STORE (TC_OFF_BIAS + 3072)
 
-__device__ __forceinline__ bool tc_decode_work(const tc_params& p, int w, int& g, int& mt) {
+__device__ __forceinline__ bool tc_decode_work(const tc_params& p, int w, int& g, int& mt, uint32_t crank = 0) {
+    if (p.mt_pairs > 0) {       // CTA pairs: both CTAs always take part; row block m_tiles (odd count) is a dummy (TMA zero fill, masked epilogue)
+        g = w / p.mt_pairs;
+        mt = 2 * (w - g * p.mt_pairs) + (int)crank;
+        return true;
+    }
     if (p.mt_block > 0) {
         const int per = p.G * p.mt_block;
         const int blk = w / per, rem = w - blk * per;
@@ -159,7 +165,12 @@ __device__ __forceinline__ void tc_amax_commit(float* amax, float mx) {
     if ((threadIdx.x & 31) == 0 && amax && mx > 0.0f) atomicMax(reinterpret_cast<unsigned*>(amax), __float_as_uint(mx));
 }
 
-template <int MODE, int ACT, int PREC>
+// PAIR (option "tc_pair"): the CTAs run as pairs on the two SMs of a TPC (cta_group::2).  A pair owns two adjacent 128-row
+// blocks of one sample; every CTA loads its own A tiles and HALF of each weight tile (128 of the 256 feature rows), the
+// even CTA's single thread issues 256 x 256 MMAs that read both CTAs' shared memory and write both CTAs' TMEM, and both
+// epilogues drain their own accumulator.  A stage is 64 KB instead of 96 KB (three stages instead of two) and every byte
+// of the weights crosses the L2 -> SM crossbar once per pair instead of once per CTA.
+template <int MODE, int ACT, int PREC, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
            const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -176,19 +187,25 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
     const uint32_t bar_tfull = smem_u32(s_bar + 8), bar_tempty = smem_u32(s_bar + 10);
     const uint32_t smem_base = smem_u32(smem);
     const int BN = p.BN;
-    const uint32_t a_bytes = TC_BM * TC_BK * 2, b_bytes = (uint32_t)BN * TC_BK * 2;
+    // PAIR: this CTA holds half of the rows of every weight tile
+    const uint32_t a_bytes = TC_BM * TC_BK * 2, b_bytes = (uint32_t)(PAIR ? BN / 2 : BN) * TC_BK * 2;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0;
+    // work items of this CTA (PAIR: of this pair)
+    const int w_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, w_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (threadIdx.x == 0) {
         if (smem_base & 1023u) { printf("ssi_tc: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 128); }
+        // PAIR: the leader's accumulator is free when the epilogues of BOTH CTAs have drained theirs
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, PAIR ? 256 : 128); }
         fence_barrier_init();
         tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
         if (MODE == TC_MODE_HIDDEN) { tma_prefetch_desc(&tmSh); tma_prefetch_desc(&tmSl); }
     }
-    if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
+    if (warp == 1) { if (PAIR) tmem_alloc_pair(smem_u32(s_tmem), 512); else tmem_alloc(smem_u32(s_tmem), 512); }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();        // the peer's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
@@ -200,25 +217,35 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
             // weights are re-read by every CTA working on the sample: keep them in L2; a shared A (the dataset)
             // likewise; per-sample activations are read by one CTA only
             const uint64_t pol_a = p.a_shared ? TC_EVICT_LAST : TC_EVICT_NORMAL;
-            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            for (int w = w_first; w < p.n_work; w += w_step) {
                 int g, mt;
-                if (!tc_decode_work(p, w, g, mt)) continue;
+                if (!tc_decode_work(p, w, g, mt, crank)) continue;
                 for (int nt = 0; nt < p.n_tiles; ++nt) {
                     for (int kb = 0; kb < p.k_blocks; ++kb) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                        const uint32_t full = bar_full + 8 * stage;
+                        // PAIR: the bytes of both CTAs are counted on the leader's barrier, which its MMA thread waits on
+                        const uint32_t full = PAIR ? mapa_u32(bar_full + 8 * stage, 0) : bar_full + 8 * stage;
                         const uint32_t sA = smem_base + stage * p.stage_bytes;
-                        mbar_expect_tx(full, 2 * a_bytes + 2 * b_bytes);
+                        if (!PAIR) mbar_expect_tx(full, 2 * a_bytes + 2 * b_bytes);
+                        else if (crank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * (2 * a_bytes + 2 * b_bytes));
                         // odd feature tiles walk the k-blocks backwards: the A k-blocks read last for tile nt are the first ones tile
                         // nt + 1 wants, which is what an LRU-like L2 still holds when a round of A tiles slightly exceeds it
                         const int kbe = (p.k_rev && (nt & 1)) ? p.k_blocks - 1 - kb : kb;
                         const int ka = p.a_il ? 2 * kbe * TC_BK : kbe * TC_BK;
                         // the last feature tile is the last reader of this row block's activations: let them go first
                         const uint64_t pa = (p.a_last_first && !p.a_shared && nt == p.n_tiles - 1) ? TC_EVICT_FIRST : pol_a;
-                        tma_load_3d_hint(sA, &tmAh, full, ka, mt * TC_BM, p.a_shared ? 0 : g, pa);
-                        tma_load_3d_hint(sA + a_bytes, &tmAl, full, p.a_il ? ka + TC_BK : ka, mt * TC_BM, p.a_shared ? 0 : g, pa);
-                        tma_load_3d_hint(sA + 2 * a_bytes, &tmBh, full, kbe * TC_BK, nt * BN, g, TC_EVICT_LAST);
-                        tma_load_3d_hint(sA + 2 * a_bytes + b_bytes, &tmBl, full, kbe * TC_BK, nt * BN, g, TC_EVICT_LAST);
+                        if (PAIR) {
+                            const int brow = nt * BN + (int)crank * (BN / 2);          // this CTA's half of the weight tile (the maps' box is BN/2 rows)
+                            tma_load_3d_pair_hint(sA, &tmAh, full, ka, mt * TC_BM, g, pa);
+                            tma_load_3d_pair_hint(sA + a_bytes, &tmAl, full, p.a_il ? ka + TC_BK : ka, mt * TC_BM, g, pa);
+                            tma_load_3d_pair_hint(sA + 2 * a_bytes, &tmBh, full, kbe * TC_BK, brow, g, TC_EVICT_LAST);
+                            tma_load_3d_pair_hint(sA + 2 * a_bytes + b_bytes, &tmBl, full, kbe * TC_BK, brow, g, TC_EVICT_LAST);
+                        } else {
+                            tma_load_3d_hint(sA, &tmAh, full, ka, mt * TC_BM, p.a_shared ? 0 : g, pa);
+                            tma_load_3d_hint(sA + a_bytes, &tmAl, full, p.a_il ? ka + TC_BK : ka, mt * TC_BM, p.a_shared ? 0 : g, pa);
+                            tma_load_3d_hint(sA + 2 * a_bytes, &tmBh, full, kbe * TC_BK, nt * BN, g, TC_EVICT_LAST);
+                            tma_load_3d_hint(sA + 2 * a_bytes + b_bytes, &tmBl, full, kbe * TC_BK, nt * BN, g, TC_EVICT_LAST);
+                        }
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -226,14 +253,14 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (lane == 0 && crank == 0) {           // PAIR: the even CTA issues for both
             const uint32_t idesc = p.idesc;
             int stage = 0;
             uint32_t phase = 0;
             uint32_t tile = 0;
-            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            for (int w = w_first; w < p.n_work; w += w_step) {
                 int g, mt;
-                if (!tc_decode_work(p, w, g, mt)) continue;
+                if (!tc_decode_work(p, w, g, mt, crank)) continue;
                 for (int nt = 0; nt < p.n_tiles; ++nt, ++tile) {
                     const uint32_t ab = tile & 1, aphase = (tile >> 1) & 1;
                     mbar_wait(bar_tempty + 8 * ab, aphase ^ 1);        // epilogue has drained this accumulator
@@ -248,14 +275,22 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; ++k) {
                             const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 bytes per K=16 step inside the swizzle row
-                            umma_bf16(d_tmem, ah + ko, bh + ko, idesc, (kb | k) != 0);
-                            umma_bf16(d_tmem, ah + ko, bl + ko, idesc, 1);
-                            umma_bf16(d_tmem, al + ko, bh + ko, idesc, 1);
+                            if (PAIR) {
+                                umma_f16_pair(d_tmem, ah + ko, bh + ko, idesc, (kb | k) != 0);
+                                umma_f16_pair(d_tmem, ah + ko, bl + ko, idesc, 1);
+                                umma_f16_pair(d_tmem, al + ko, bh + ko, idesc, 1);
+                            } else {
+                                umma_bf16(d_tmem, ah + ko, bh + ko, idesc, (kb | k) != 0);
+                                umma_bf16(d_tmem, ah + ko, bl + ko, idesc, 1);
+                                umma_bf16(d_tmem, al + ko, bh + ko, idesc, 1);
+                            }
                         }
-                        umma_commit(bar_empty + 8 * stage);             // frees the smem slot when the MMAs retire
+                        // frees the smem slot (PAIR: of both CTAs) when the MMAs retire
+                        if (PAIR) umma_commit_pair(bar_empty + 8 * stage); else umma_commit(bar_empty + 8 * stage);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(bar_tfull + 8 * ab);                   // accumulator complete -> epilogue
+                    // accumulator complete -> epilogue (PAIR: of both CTAs)
+                    if (PAIR) umma_commit_pair(bar_tfull + 8 * ab); else umma_commit(bar_tfull + 8 * ab);
                 }
             }
         }
@@ -270,9 +305,11 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
         float amx = 0.0f;                            // HIDDEN: largest |activation| this thread has written
         uint32_t chunk_ctr = 0;
         uint32_t tile = 0;
-        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+        // PAIR: "accumulator drained" is reported to the leader's barrier
+        const uint32_t tempty_remote = PAIR ? mapa_u32(bar_tempty, 0) : 0;
+        for (int w = w_first; w < p.n_work; w += w_step) {
             int g, mt;
-            if (!tc_decode_work(p, w, g, mt)) continue;
+            if (!tc_decode_work(p, w, g, mt, crank)) continue;
             const float inv = p.winv ? p.winv[g] : 1.0f;     // exact power of two: undoes the operand scales
             double sse = 0.0;
             // FUSED: 4 rows per thread (see tmem_ld_16x256b_x8), partial sums over this thread's columns
@@ -391,7 +428,7 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(bar_tempty + 8 * ab);
+                if (PAIR) mbar_arrive_cluster(tempty_remote + 8 * ab); else mbar_arrive(bar_tempty + 8 * ab);
             }
             if (MODE == TC_MODE_FUSED) {
                 // the 4 threads of a quad hold the same 4 rows for interleaved columns: reduce across the quad,
@@ -433,9 +470,10 @@ k_tc_layer(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUt
 
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();        // no CTA leaves (or frees TMEM) while its peer's MMAs or arrivals may still touch it
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -966,6 +1004,7 @@ struct ssi_tc_state {
     int KT = 32;                             // columns per row of Th / Tl (24 or 32)
     double* partials = nullptr;
     CUtensorMap tmAh[SSI_MAX_LAYERS], tmAl[SSI_MAX_LAYERS], tmBh[SSI_MAX_LAYERS], tmBl[SSI_MAX_LAYERS];
+    CUtensorMap tmBh2[SSI_MAX_LAYERS], tmBl2[SSI_MAX_LAYERS];     // boxes of BN/2 rows (CTA pairs)
     CUtensorMap tmSh[SSI_MAX_LAYERS], tmSl[SSI_MAX_LAYERS];
     PFN_encodeTiled encode = nullptr;
 };
@@ -1018,19 +1057,23 @@ bool ssi_tc_preferred(const ssi_ctx* ctx) {
 typedef void (*tc_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                             const CUtensorMap, const tc_params);
 // only the HIDDEN epilogue writes operand planes: the other modes have one instantiation per activation
-template <int MODE, int PREC>
+template <int MODE, int PREC, bool PAIR>
 static tc_kernel_t tc_kernel_for_act(int act) {
     switch (act) {
-        case SSI_ACT_RELU:    return k_tc_layer<MODE, SSI_ACT_RELU, PREC>;
-        case SSI_ACT_TANH:    return k_tc_layer<MODE, SSI_ACT_TANH, PREC>;
-        case SSI_ACT_SIGMOID: return k_tc_layer<MODE, SSI_ACT_SIGMOID, PREC>;
-        default:              return k_tc_layer<MODE, SSI_ACT_IDENTITY, PREC>;
+        case SSI_ACT_RELU:    return k_tc_layer<MODE, SSI_ACT_RELU, PREC, PAIR>;
+        case SSI_ACT_TANH:    return k_tc_layer<MODE, SSI_ACT_TANH, PREC, PAIR>;
+        case SSI_ACT_SIGMOID: return k_tc_layer<MODE, SSI_ACT_SIGMOID, PREC, PAIR>;
+        default:              return k_tc_layer<MODE, SSI_ACT_IDENTITY, PREC, PAIR>;
     }
 }
-static tc_kernel_t tc_kernel(int mode, int act, int prec) {
-    if (mode == TC_MODE_FUSED) return tc_kernel_for_act<TC_MODE_FUSED, 0>(act);
-    if (mode == TC_MODE_FINAL) return tc_kernel_for_act<TC_MODE_FINAL, 0>(act);
-    return prec == TC_PREC_FP16X3 ? tc_kernel_for_act<TC_MODE_HIDDEN, TC_PREC_FP16X3>(act) : tc_kernel_for_act<TC_MODE_HIDDEN, TC_PREC_BF16X3>(act);
+template <bool PAIR>
+static tc_kernel_t tc_kernel_p(int mode, int act, int prec) {
+    if (mode == TC_MODE_FUSED) return tc_kernel_for_act<TC_MODE_FUSED, 0, PAIR>(act);
+    if (mode == TC_MODE_FINAL) return tc_kernel_for_act<TC_MODE_FINAL, 0, PAIR>(act);
+    return prec == TC_PREC_FP16X3 ? tc_kernel_for_act<TC_MODE_HIDDEN, TC_PREC_FP16X3, PAIR>(act) : tc_kernel_for_act<TC_MODE_HIDDEN, TC_PREC_BF16X3, PAIR>(act);
+}
+static tc_kernel_t tc_kernel(int mode, int act, int prec, bool pair = false) {
+    return pair ? tc_kernel_p<true>(mode, act, prec) : tc_kernel_p<false>(mode, act, prec);
 }
 
 typedef void (*tb_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const int,
@@ -1191,10 +1234,8 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
     ssi_tc_state* s = ctx->tc;
     if (s->ready) return SSI_OK;
     if (!s->encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        SSI_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (qres != cudaDriverEntryPointSuccess || !fn) return ssi_fail(ctx, SSI_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        PFN_ssi_encodeTiled fn = nullptr;
+        SSI_TRY(ssi_tensormap_encoder(ctx, &fn));
         s->encode = (PFN_encodeTiled)fn;
     }
     SSI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1313,6 +1354,8 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
         }
         SSI_TRY(tc_make_map(ctx, &s->tmBh[l], s->Wh[l], s->Kp[l], s->width[l], G, TC_BK, s->BN[l], S128));
         SSI_TRY(tc_make_map(ctx, &s->tmBl[l], s->Wl[l], s->Kp[l], s->width[l], G, TC_BK, s->BN[l], S128));
+        SSI_TRY(tc_make_map(ctx, &s->tmBh2[l], s->Wh[l], s->Kp[l], s->width[l], G, TC_BK, s->BN[l] / 2, S128));
+        SSI_TRY(tc_make_map(ctx, &s->tmBl2[l], s->Wl[l], s->Kp[l], s->width[l], G, TC_BK, s->BN[l] / 2, S128));
         if (l < s->nl - 1) {
             // epilogue stores of this layer's activations: 32 rows x 32 columns (64 B) per warp and chunk
             SSI_TRY(tc_make_map(ctx, &s->tmSh[l], s->Hh[l & 1], s->width[l], N, G, 32, 32, S64));
@@ -1325,7 +1368,8 @@ int ssi_tc_prepare(ssi_ctx* ctx) {
     for (int mode = 0; mode < 3; ++mode)
         for (int act = 0; act < 4; ++act)
             for (int prec = 0; prec < 2; ++prec)
-                SSI_CUDA(ctx, cudaFuncSetAttribute(tc_kernel(mode, act, prec), cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_total(mode)));
+                for (int pair = 0; pair < 2; ++pair)
+                    SSI_CUDA(ctx, cudaFuncSetAttribute(tc_kernel(mode, act, prec, pair != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_total(mode)));
     if (s->basis_mma) {
         const CUtensorMapSwizzle S64 = CU_TENSOR_MAP_SWIZZLE_64B;
         const uint64_t NW = (uint64_t)N * s->width[0];
@@ -1452,18 +1496,27 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
             p.k_rev = (!p.a_shared && !ctx->opt_tc_nokrev) ? 1 : 0;
             p.a_last_first = ctx->opt_tc_alast;
             p.act = m.act[l];
-            p.stage_bytes = 2 * TC_BM * TC_BK * 2 + 2 * p.BN * TC_BK * 2;
+            // CTA pairs for the layers with per-sample activations (weight rows split across the pair: BN / 2 must be a whole
+            // number of 8-row swizzle atoms and a legal MMA N half)
+            const bool pair = !p.a_shared && ctx->opt_tc_pair && p.BN >= 32 && (p.BN % 32) == 0 && ctx->sm_count >= 2;
+            p.stage_bytes = 2 * TC_BM * TC_BK * 2 + 2 * (pair ? p.BN / 2 : p.BN) * TC_BK * 2;
             p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
             p.stages = std::min(4, TC_SMEM_PIPE / p.stage_bytes);
             p.bias = s->bias[l];
-            p.idesc = fp16 ? umma_idesc_f16(p.BN, UMMA_FMT_F16, UMMA_FMT_F16) : umma_idesc_bf16(p.BN);
+            const uint32_t fmt = fp16 ? UMMA_FMT_F16 : UMMA_FMT_BF16;
+            p.idesc = pair ? umma_idesc_f16_pair(p.BN, fmt, fmt) : umma_idesc_f16(p.BN, fmt, fmt);
             p.winv = fp16 ? s->winv + (size_t)l * s->G : nullptr;
             p.a_scale = scalbnf(1.0f, s->ja_in.v[l + 1]);         // of the planes this layer writes (HIDDEN)
             p.amax = s->amax + (l + 1);
-            const int grid = std::min(ctx->sm_count, G * m_tiles);
+            int grid = std::min(ctx->sm_count, G * m_tiles);
             // a shared A operand (the dataset): run the group's samples side by side on the same m-tiles
             p.mt_block = (p.a_shared && G > 1 && !ctx->opt_tc_noorder) ? std::max(1, (grid + G - 1) / G) : 0;
             p.n_work = p.mt_block > 0 ? (m_tiles + p.mt_block - 1) / p.mt_block * p.mt_block * G : G * m_tiles;
+            if (pair) {
+                p.mt_pairs = (m_tiles + 1) / 2;
+                p.n_work = G * p.mt_pairs;
+                grid = std::min(ctx->sm_count & ~1, 2 * p.n_work);
+            }
             p.Y = ctx->dY; p.O = m.dims[m.L]; p.partials = s->partials;
             const bool last = (l == s->nl - 1);
             int mode = TC_MODE_HIDDEN;
@@ -1474,8 +1527,20 @@ int ssi_tc_sse(ssi_ctx* ctx, const float* dZ, int64_t B, double* d_sse) {
                 mode = TC_MODE_FINAL;
             }
             if (last) ssi_kt_begin(ctx);
-            tc_kernel(mode, p.act, s->prec)<<<grid, TC_THREADS, tc_smem_total(mode), ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l],
-                                                                                                   s->tmSh[l], s->tmSl[l], p);
+            if (pair) {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS);
+                cfg.dynamicSmemBytes = tc_smem_total(mode); cfg.stream = ctx->stream;
+                cudaLaunchAttribute attr{};
+                attr.id = cudaLaunchAttributeClusterDimension;
+                attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+                cfg.attrs = &attr; cfg.numAttrs = 1;
+                void* args[] = {&s->tmAh[l], &s->tmAl[l], &s->tmBh2[l], &s->tmBl2[l], &s->tmSh[l], &s->tmSl[l], &p};
+                SSI_CUDA(ctx, cudaLaunchKernelExC(&cfg, (const void*)tc_kernel(mode, p.act, s->prec, true), args));
+            } else {
+                tc_kernel(mode, p.act, s->prec)<<<grid, TC_THREADS, tc_smem_total(mode), ctx->stream>>>(s->tmAh[l], s->tmAl[l], s->tmBh[l], s->tmBl[l],
+                                                                                                       s->tmSh[l], s->tmSl[l], p);
+            }
             SSI_LAUNCH_CHECK(ctx);
             if (last) ssi_kt_end(ctx);
         }

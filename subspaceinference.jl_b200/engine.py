@@ -105,6 +105,18 @@ class Engine:
         self._check(self._lib.ssi_set_subspace(self._h, _ptr(W_swa), _ptr(P), P.shape[0], P.shape[1]))
         self.M = int(P.shape[1])
 
+    def set_decoder(self, W_swa, dims: Sequence[int], acts: Sequence[int], theta):
+        """Non-linear subspace operator: W = W_swa + decoder(z), decoder = Chain of Dense layers dims[0] (= dimension of z)
+        -> ... -> dims[-1] (= n), parameters `theta` in Flux.destructure order (src/space_inference.jl:246-251)."""
+        W_swa, theta = _f32(W_swa).reshape(-1), _f32(theta).reshape(-1)
+        dims_a, acts_a = np.asarray(dims, dtype=np.int32), np.asarray(acts, dtype=np.int32)
+        if len(acts_a) != len(dims_a) - 1:
+            raise ValueError("need one activation per decoder layer")
+        if theta.shape[0] != int(sum(dims_a[l] * dims_a[l + 1] + dims_a[l + 1] for l in range(len(acts_a)))):
+            raise ValueError("theta does not have the decoder's number of parameters")
+        self._check(self._lib.ssi_set_decoder(self._h, _ptr(W_swa), len(acts_a), _ptr(dims_a), _ptr(acts_a), _ptr(theta)))
+        self.M = int(dims_a[0])
+
     # ---- density(z), batched -----------------------------------------------------------
     def logpost(self, Z, sigma_m=1.0, sigma_p=1.0, sigma_z=1.0, mask=TERM_LL, return_terms=False):
         Z = _f32(Z)
@@ -277,6 +289,17 @@ class Engine:
 
     def train_end(self):
         self._check(self._lib.ssi_train_end(self._h))
+
+    def swa_deviations(self) -> np.ndarray:
+        """The deviation matrix collected so far, (n, K) float32 (`reshape(A, all_len, :)`, src/subspace_construction.jl:61)."""
+        A = np.empty((self._swa_n, self.swa_columns()), np.float32, order="F")
+        self._check(self._lib.ssi_swa_deviations(self._h, _ptr(A)))
+        return A
+
+    def swa_mean(self) -> np.ndarray:
+        W = np.empty(self._swa_n, np.float32)
+        self._check(self._lib.ssi_swa_mean(self._h, _ptr(W)))
+        return W
 
     def swa_columns(self) -> int:
         return int(self._lib.ssi_swa_columns(self._h))

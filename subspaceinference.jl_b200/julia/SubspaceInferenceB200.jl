@@ -13,18 +13,24 @@ module SubspaceInferenceB200
 using Flux
 using Flux: Data.DataLoader
 
-export subspace_construction, subspace_inference, sub_inference, inference, predictive
+export subspace_construction, subspace_inference, sub_inference, inference, predictive,
+       auto_encoder_subspace, auto_inference, autoencoder_inference
 
 const libssi = get(ENV, "LIBSSI", joinpath(@__DIR__, "..", "lib", "libssi.so"))
 
 const TERM_LL, TERM_PRIOR_W, TERM_PRIOR_Z = UInt32(1), UInt32(2), UInt32(4)
 
 # ---- plumbing ------------------------------------------------------------------------------
+# Ctx(0): one device.  Ctx([0, 1, ..., 7]): ONE context over several devices (ssi_ctx_create_multi) -- this single Julia
+# process then drives all of them: W_swa, P, X, Y are replicated, the batched calls shard their samples / chains, every
+# device lands its slice in the host arrays.  No MPI.jl / NCCL.jl is needed on the Julia side.
 mutable struct Ctx
     h::Ptr{Cvoid}
-    function Ctx(device::Integer = 0)
+    function Ctx(device::Union{Integer, AbstractVector{<:Integer}} = 0)
         out = Ref{Ptr{Cvoid}}(C_NULL)
-        rc = ccall((:ssi_ctx_create, libssi), Cint, (Cint, Ref{Ptr{Cvoid}}), device, out)
+        rc = device isa Integer ?
+            ccall((:ssi_ctx_create, libssi), Cint, (Cint, Ref{Ptr{Cvoid}}), device, out) :
+            ccall((:ssi_ctx_create_multi, libssi), Cint, (Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}), Int32.(device), length(device), out)
         rc == 0 || throw(unsafe_string(ccall((:ssi_last_error, libssi), Cstring, (Ptr{Cvoid},), C_NULL)))
         c = new(out[])
         finalizer(x -> ccall((:ssi_ctx_destroy, libssi), Cint, (Ptr{Cvoid},), x.h), c)
@@ -90,8 +96,10 @@ function subspace_construction(model, cost, data, opt; T = 10, c = 1, M = 3, pri
     training_loss = 0.0
     ps = Flux.params(model)
     n = length(flat_params(model))
-    check(ctx, ccall((:ssi_swa_begin, libssi), Cint, (Ptr{Cvoid}, Int64, Int64), ctx.h, n, div(T, c) * length(data)))
+    check(ctx, ccall((:ssi_swa_begin, libssi), Cint, (Ptr{Cvoid}, Int64, Int64), ctx.h, n, max(1, div(T, c) * length(data))))
     if device_train
+        # the device step walks contiguous windows of the data set: a shuffled loader would silently train on other batches
+        data.shuffle && throw("Error: device_train needs a DataLoader without shuffle (pass index vectors to ssi_train_step otherwise)")
         dims, acts = describe(model)
         check(ctx, ccall((:ssi_set_model, libssi), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}), ctx.h, length(acts), dims, acts))
         X = Matrix{Float32}(data.data[1]); Y = Matrix{Float32}(data.data[2]); N = size(X, 2)
@@ -160,6 +168,84 @@ function sub_inference(in_model, data, W_swa, P; σ_z = 1.0, σ_m = 1.0, σ_p = 
 end
 
 const inference = sub_inference
+
+# Checkpoint / resume (SURVEY 5; the docs save and reload around sampling, docs/src/nn_example.md:158,168): the chains of the
+# last run are resumable from (seed, step, z).  `chain_state` returns their final (z, lp); `continue_chains` draws steps
+# step_offset .. step_offset + itr - 1 of the same Philox streams -- bit-identical to an uninterrupted run.
+function chain_state(ctx::Ctx, M::Integer, n_chains::Integer)
+    z = Matrix{Float32}(undef, M, n_chains); lp = Vector{Float64}(undef, n_chains)
+    check(ctx, ccall((:ssi_mh_get_state, libssi), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float64}), ctx.h, z, lp))
+    return z, lp
+end
+function continue_chains(ctx::Ctx, z_state::AbstractMatrix, step_offset::Integer, itr::Integer; σ_z = 1.0, σ_m = 1.0, σ_p = 1.0,
+                         alg = :rwmh, seed, chain_offset = 0, prior_mask = TERM_LL)
+    M, C = size(z_state)
+    zt = Array{Float32}(undef, M, C, itr); lp = Matrix{Float64}(undef, C, itr)
+    check(ctx, ccall((:ssi_mh_run_from, libssi), Cint,
+                     (Ptr{Cvoid}, Int32, Int64, Int64, UInt64, Int64, Int64, Float64, Float64, Float64, UInt32,
+                      Ptr{Float32}, Ptr{Float32}, Ptr{Float64}, Ptr{UInt8}),
+                     ctx.h, alg == :mala ? 1 : 0, C, itr, seed, chain_offset, step_offset, σ_z, σ_m, σ_p, prior_mask,
+                     Matrix{Float32}(z_state), zt, lp, C_NULL))
+    return zt, lp
+end
+
+# ---- non-linear subspace operator: new_W = W_swa + decoder(z)  (src/space_inference.jl:238-318) ---------------------------------
+# auto_encoder_subspace keeps the reference's code (src/subspace_construction.jl:93-143) except that the moment recurrence
+# runs on the device; the auto-encoder itself is trained by Flux as in the reference.
+function auto_encoder_subspace(model, cost, data, opt, encoder, decoder; T = 10, c = 1, M = 3, print_freq = 1, ctx::Ctx = Ctx())
+    training_loss = 0.0
+    ps = Flux.params(model)
+    n = length(flat_params(model))
+    check(ctx, ccall((:ssi_swa_begin, libssi), Cint, (Ptr{Cvoid}, Int64, Int64), ctx.h, n, max(1, div(T, c) * length(data))))
+    for i in 1:T
+        for d in data
+            gs = gradient(ps) do
+                training_loss = cost(model, d...)
+                return training_loss
+            end
+            Flux.update!(opt, ps, gs)
+            mod(i, c) == 0 && check(ctx, ccall((:ssi_swa_push, libssi), Cint, (Ptr{Cvoid}, Ptr{Float32}, Float64), ctx.h, flat_params(model), i / c))
+        end
+        ((mod(i, print_freq) == 0) || (i == T)) && println("Traing loss: ", training_loss, " Epoch: ", i)
+    end
+    K = ccall((:ssi_swa_columns, libssi), Int64, (Ptr{Cvoid},), ctx.h)
+    W_swa = Vector{Float32}(undef, n); re_weight = Matrix{Float32}(undef, n, K)
+    check(ctx, ccall((:ssi_swa_mean, libssi), Cint, (Ptr{Cvoid}, Ptr{Float32}), ctx.h, W_swa))
+    check(ctx, ccall((:ssi_swa_deviations, libssi), Cint, (Ptr{Cvoid}, Ptr{Float32}), ctx.h, re_weight))
+    sae = Chain(encoder, decoder)
+    autoloss(X) = Flux.mse(sae(X), X)                     # the reference's `+ sum(sqnorm, autops)` line never contributes (:130-131)
+    Flux.train!(autoloss, Flux.params(sae), DataLoader(re_weight, batchsize = 5, shuffle = true), ADAM())
+    return W_swa, decoder
+end
+
+function auto_inference(m, data, decoder, W_swa; σ_z = 1.0, σ_m = 1.0, σ_p = 1.0, itr = 100, M = 3, alg = :hmc,
+                        backend = :forwarddiff, n_chains = 1, seed = rand(UInt64), prior_mask = TERM_LL, ctx::Ctx = Ctx())
+    (alg == :rwmh || alg == :mh || alg == :mala) || throw("$alg is not available")            # :316; :hmc/:nuts/:advi stay host-side
+    dims, acts = describe(m)
+    check(ctx, ccall((:ssi_set_model, libssi), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}), ctx.h, length(acts), dims, acts))
+    X = Matrix{Float32}(data.data[1]); Y = Matrix{Float32}(data.data[2])
+    check(ctx, ccall((:ssi_set_data, libssi), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int64), ctx.h, X, Y, size(X, 2)))
+    ddims, dacts = describe(decoder)
+    check(ctx, ccall((:ssi_set_decoder, libssi), Cint, (Ptr{Cvoid}, Ptr{Float32}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Float32}),
+                     ctx.h, Float32.(W_swa), length(dacts), ddims, dacts, flat_params(decoder)))
+    zt = Array{Float32}(undef, M, n_chains, itr); lp = Matrix{Float64}(undef, n_chains, itr)
+    check(ctx, ccall((alg == :mala ? :ssi_mala_run : :ssi_mh_run, libssi), Cint,
+                     (Ptr{Cvoid}, Int64, Int64, UInt64, Int64, Float64, Float64, Float64, UInt32,
+                      Ptr{Float32}, Ptr{Float32}, Ptr{Float64}, Ptr{UInt8}),
+                     ctx.h, n_chains, itr, seed, 0, σ_z, σ_m, σ_p, prior_mask, C_NULL, zt, lp, C_NULL))
+    n_chains == 1 || return zt, lp
+    Wout = Matrix{Float32}(undef, length(W_swa), itr)          # map(z -> W_swa + decoder(z.params), chm)  (:277)
+    check(ctx, ccall((:ssi_project, libssi), Cint, (Ptr{Cvoid}, Ptr{Float32}, Int64, Ptr{Float32}), ctx.h, Matrix{Float32}(zt[:, 1, :]), itr, Wout))
+    return [Wout[:, t] for t in 1:itr], vec(lp[1, :])
+end
+
+function autoencoder_inference(model, cost, data, opt, encoder, decoder; σ_z = 1.0, σ_m = 1.0, σ_p = 1.0, itr = 1000, T = 25, c = 1,
+                               M = 20, print_freq = 1, alg = :hmc, backend = :forwarddiff, kw...)
+    ctx = Ctx()
+    W_swa, decoder = auto_encoder_subspace(model, cost, data, opt, encoder, decoder; T = T, c = c, M = M, print_freq = print_freq, ctx = ctx)
+    return auto_inference(model, data, decoder, W_swa; σ_z = σ_z, σ_m = σ_m, σ_p = σ_p, itr = itr, M = M, alg = alg,
+                          backend = backend, ctx = ctx, kw...)
+end
 
 # The sweep of docs/src/nn_example.md:207-216 + src/plotting.jl:8-9 on the device: trajectories[:, :, i] = re(W_swa + P z_i)(inp),
 # their mean and (corrected) std over the samples.  Z is M x B (subspace samples), inp is in0 x Ng.
