@@ -118,8 +118,8 @@ int  ssi_set_stream(ssi_ctx* ctx, void* cuda_stream);
 int  ssi_sync(ssi_ctx* ctx);
 /* keys: "path" (SSI_PATH_*), "group" (samples per wave on the tensor path), "tc_precision" (operand planes of the tensor
  * path: 1 = mixed BF16/FP16 planes, the default; 0 = BF16x3), and A/B switches used by the tests: "tc_nobasis", "tc_nofuse",
- * "tc_noorder", "tc_simt_basis", "tc_nokrev", "tc_alast", "tc_k32", "b1_simt", "bm_nopack", "bm_variant", "gram_fp64",
- * "gram_chunk" (see DESIGN.md); "time_dominant" (0/1) brackets every launch of the path's dominant kernel with CUDA events
+ * "tc_noorder", "tc_simt_basis", "tc_nokrev", "tc_alast", "tc_k32", "tc_pair" (1 = CTA pairs with cta_group::2, the default),
+ * "b1_simt", "bm_nopack", "bm_variant", "gram_fp64", "gram_chunk", "eig_cluster", "formp_simt" (see DESIGN.md); "time_dominant" (0/1) brackets every launch of the path's dominant kernel with CUDA events
  * (ssi_stats_t.dominant_ms) */
 int  ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value);
 int  ssi_stats(const ssi_ctx* ctx, ssi_stats_t* out);

@@ -62,14 +62,14 @@ struct ssi_ctx {
     int opt_tc_k32 = 0;       // A-B: K-major bases always 32 columns wide
     int opt_tc_alast = 1;     // evict-first hint on the last read of a row block's activations (A-B: 0)
     int opt_tc_nokrev = 0;    // A-B: every feature tile reads the k-blocks in ascending order
-    int opt_tc_pair = 0;      // GEMM layers with per-sample activations as CTA pairs (cta_group::2)
+    int opt_tc_pair = 1;      // GEMM layers with per-sample activations as CTA pairs (cta_group::2); 0: one CTA per tile (A-B)
     int opt_tc_prec = 1;      // operand planes of the tensor path: 1 mixed BF16/FP16 (default), 0 BF16x3 (round 1)
     int opt_bm_nopack = 0, opt_bm_variant = 1;     // A-B inside k_b1_mma: unpacked operands; ReLU epilogue variant
     int opt_b1_simt = 0;       // A-B: BASIS path on CUDA cores (k_logpost_basis1h) instead of the tensor-core kernel (k_b1_mma)
     int opt_tc_simt_basis = 0; // A-B: first layer as the FP32 SIMT basis combination instead of the tensor-core one
     int opt_gram_fp64 = 0;    // force the FP64 SIMT Gram (default: tensor-core TF32x2 Gram for large n, K <= 128)
     int opt_formp_simt = 0;   // A-B: P = A V_M with loads from global memory (k_form_p) instead of the TMA-staged stream
-    int opt_eig_single = 0;   // A-B: eigen-solve on one CTA instead of a cluster of eight
+    int opt_eig_cluster = 1;  // eigen-solve (K <= 160) on a cluster of eight CTAs; 0: one CTA (A-B)
     int opt_gram_chunk = 0;   // tiles (32 rows) per FP32 accumulation chunk of the tensor-core Gram (default 32)
     int opt_tc_nobasis = 0;   // debugging / A-B: run the first layer as a GEMM instead of the affine-in-z basis combination   // debugging / A-B: sample-major work order on the first layer
 

@@ -375,8 +375,9 @@ k_osj(double* __restrict__ Gg /* K x K column-major Gram; on exit the orthogonal
 // owner is computed, not communicated).  A column is thus valid exactly where it is needed: 2 column transfers per pair
 // and round (80 KB per round over the whole cluster at K = 100) instead of a broadcast.
 #define OSJC_CTAS 8
-#define OSJC_THREADS 256
-#define OSJC_HW (OSJC_THREADS / 16)        // half warps (pairs) per CTA and pass
+#define OSJC_THREADS 512
+#define OSJC_HW (OSJC_THREADS / 32)        // warps (pairs) per CTA and pass: one warp per pair
+#define OSJC_IT ((OSJ_SMEM_KMAX + 31) / 32)   // elements of a column per lane
 __device__ __forceinline__ uint32_t osjc_mapa(uint32_t local_addr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
@@ -422,9 +423,8 @@ k_osj_cluster(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__ 
     cluster_sync_all();
     const double tol = (double)K * 2.220446049250313e-16, tol2 = tol * tol;
     const int m = (K + 1) & ~1, np = m / 2;
-    const int hw = (int)rank * OSJC_HW + (tid >> 4), n_hw = OSJC_CTAS * OSJC_HW;
-    const int hl = tid & 15;
-    const unsigned hmask = 0xffffu << (tid & 16);
+    const int hw = (int)rank * OSJC_HW + (tid >> 5), n_hw = OSJC_CTAS * OSJC_HW;
+    const int hl = tid & 31;
     const uint32_t g_local = smem_u32(G);
     int sweep = 0;
     bool converged = false;
@@ -439,21 +439,27 @@ k_osj_cluster(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__ 
                 const double* gp = G + (long long)p * K;
                 const uint32_t dst_p = osjc_mapa(g_local, (uint32_t)osjc_owner(p, rn, m)) + (uint32_t)(p * K) * 8u;
                 if (q >= K) {                                               // bye: the column only moves on
-                    for (int k = hl; k < K; k += 16) osjc_st_f64(dst_p + (uint32_t)k * 8u, gp[k]);
+                    for (int k = hl; k < K; k += 32) osjc_st_f64(dst_p + (uint32_t)k * 8u, gp[k]);
                     continue;
                 }
                 const double* gq = G + (long long)q * K;
                 const uint32_t dst_q = osjc_mapa(g_local, (uint32_t)osjc_owner(q, rn, m)) + (uint32_t)(q * K) * 8u;
-                double a = 0.0, b = 0.0, c = 0.0;
-                for (int k = hl; k < K; k += 16) {
-                    const double x = gp[k], y = gq[k];
-                    a = fma(x, x, a); b = fma(y, y, b); c = fma(x, y, c);
-                }
+                // the lane's elements of both columns stay in registers: all loads leave before the first use
+                double x[OSJC_IT], y[OSJC_IT];
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) {
-                    a += __shfl_xor_sync(hmask, a, o);
-                    b += __shfl_xor_sync(hmask, b, o);
-                    c += __shfl_xor_sync(hmask, c, o);
+                for (int it = 0; it < OSJC_IT; ++it) {
+                    const int k = hl + 32 * it;
+                    x[it] = k < K ? gp[k] : 0.0;
+                    y[it] = k < K ? gq[k] : 0.0;
+                }
+                double a = 0.0, b = 0.0, c = 0.0;
+#pragma unroll
+                for (int it = 0; it < OSJC_IT; ++it) { a = fma(x[it], x[it], a); b = fma(y[it], y[it], b); c = fma(x[it], y[it], c); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
+                    c += __shfl_xor_sync(0xffffffffu, c, o);
                 }
                 const double c2 = c * c, ab = a * b;
                 double cs = 1.0, sn = 0.0;
@@ -469,14 +475,20 @@ k_osj_cluster(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__ 
                     cs = rsqrt(fma(t, t, 1.0));
                     sn = t * cs;
                     if (hl == 0) {
+                        // largest cos^2 rotated away in this sweep (single precision is plenty: it is compared with 1e-15)
+                        const int e2 = __double2hiint(ab) >> 20;
+                        const double s2 = __hiloint2double((2046 - e2) << 20, 0);
                         atomicAdd(&s_cnt, 1u);
-                        atomicMax(&s_mx, __float_as_uint((float)(c2 / ab)));     // largest cos^2 rotated away in this sweep
+                        atomicMax(&s_mx, __float_as_uint(fminf((float)(c2 * s2) / (float)(ab * s2), 1.0f)));
                     }
                 }
-                for (int k = hl; k < K; k += 16) {
-                    const double x = gp[k], y = gq[k];
-                    osjc_st_f64(dst_p + (uint32_t)k * 8u, cs * x - sn * y);
-                    osjc_st_f64(dst_q + (uint32_t)k * 8u, sn * x + cs * y);
+#pragma unroll
+                for (int it = 0; it < OSJC_IT; ++it) {
+                    const int k = hl + 32 * it;
+                    if (k < K) {
+                        osjc_st_f64(dst_p + (uint32_t)k * 8u, cs * x[it] - sn * y[it]);
+                        osjc_st_f64(dst_q + (uint32_t)k * 8u, sn * x[it] + cs * y[it]);
+                    }
                 }
             }
             if (r == m - 2) {       // last round of the sweep: publish this CTA's rotation count before the barrier
@@ -501,7 +513,7 @@ k_osj_cluster(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__ 
     // every column is valid in the CTA that owns it in round 0 (the round after the last one): that CTA writes it out
     for (int i = hw; i < np; i += n_hw) {
         int p = (i == 0) ? m - 1 : i, q = (i == 0) ? 0 : m - 1 - i;        // round 0: (r + i, r - i) mod (m - 1) with r = 0
-        for (int k = hl; k < K; k += 16) {
+        for (int k = hl; k < K; k += 32) {
             if (p < K) Gg[k + (long long)p * K] = G[k + (long long)p * K];
             if (q < K) Gg[k + (long long)q * K] = G[k + (long long)q * K];
         }
@@ -511,6 +523,100 @@ k_osj_cluster(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__ 
         for (int i = tid; i < K; i += nt) perm_out[i] = s_perm[i];
         if (tid == 0) *sweeps_out = converged ? sweep : max_sweeps + 1;
     }
+}
+
+// One CTA, one warp per pair, the matrix in shared memory, one __syncthreads per round (option eig_cluster = 0, A-B).  The
+// cluster kernel above pays ~1 us per round for its cluster barrier (release of the remote stores + arrive + wait; ncu: 46 %
+// of its samples), but this one is bound by the FP64 pipe of its single SM -- ~70 FP64 warp instructions per pair, 3.5 us per
+// round at K = 100: 3.2 ms against 2.05 ms on the cluster.
+#define OSJS_THREADS 1024
+__global__ void __launch_bounds__(OSJS_THREADS)
+k_osj_smem(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__ perm_out, int* __restrict__ sweeps_out) {
+    extern __shared__ double osj_smem[];
+    double* G = osj_smem;                                     // K x K
+    int* s_perm = reinterpret_cast<int*>(G + (size_t)K * K);  // K
+    __shared__ double red[32];
+    __shared__ int redi[32];
+    __shared__ double s_tr;
+    __shared__ unsigned s_cnt, s_mx;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    {
+        double tr = 0.0;
+        for (int i = tid; i < K; i += nt) tr += fabs(Gg[i + (long long)i * K]);
+        tr = ssi_block_sum(tr, red);
+        if (tid == 0) { s_tr = tr; s_cnt = 0; s_mx = 0; }
+        for (long long e = tid; e < (long long)K * K; e += nt) G[e] = Gg[e];
+        __syncthreads();
+        osj_pivoted_cholesky(G, K, s_perm, (double)K * 2.220446049250313e-16 * s_tr, red, redi);
+    }
+    const double tol = (double)K * 2.220446049250313e-16, tol2 = tol * tol;
+    const int m = (K + 1) & ~1, np = m / 2;
+    const int wid = tid >> 5, n_w = nt >> 5, hl = tid & 31;
+    int sweep = 0;
+    bool converged = false;
+    for (; sweep < max_sweeps; ++sweep) {
+        for (int r = 0; r < m - 1; ++r) {
+            for (int i = wid; i < np; i += n_w) {
+                int p, q;
+                if (i == 0) { p = m - 1; q = r; }
+                else { p = r + i; if (p >= m - 1) p -= m - 1; q = r - i; if (q < 0) q += m - 1; }
+                if (p > q) { const int t = p; p = q; q = t; }
+                if (q >= K) continue;                                       // bye
+                double* gp = G + (long long)p * K;
+                double* gq = G + (long long)q * K;
+                double x[OSJC_IT], y[OSJC_IT];
+#pragma unroll
+                for (int it = 0; it < OSJC_IT; ++it) {
+                    const int k = hl + 32 * it;
+                    x[it] = k < K ? gp[k] : 0.0;
+                    y[it] = k < K ? gq[k] : 0.0;
+                }
+                double a = 0.0, b = 0.0, c = 0.0;
+#pragma unroll
+                for (int it = 0; it < OSJC_IT; ++it) { a = fma(x[it], x[it], a); b = fma(y[it], y[it], b); c = fma(x[it], y[it], c); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
+                    c += __shfl_xor_sync(0xffffffffu, c, o);
+                }
+                const double c2 = c * c, ab = a * b;
+                if (c2 <= tol2 * ab) continue;
+                const double d = b - a, h = 2.0 * c;
+                const int ex = max(__double2hiint(fabs(d)), __double2hiint(fabs(h))) >> 20;
+                const double sc = __hiloint2double((2046 - ex) << 20, 0);
+                const float df = (float)(d * sc), hf = (float)(h * sc);
+                const float rf = sqrtf(fmaf(df, df, hf * hf));
+                double t = (double)(hf / (df + copysignf(rf, df)));
+                const double f = fma(h * t, t, fma(2.0 * d, t, -h));
+                t -= f * (double)(1.0f / (float)((2.0 * (h * t + d)) * sc)) * sc;
+                const double cs = rsqrt(fma(t, t, 1.0)), sn = t * cs;
+                if (hl == 0) {
+                    const int e2 = __double2hiint(ab) >> 20;
+                    const double s2 = __hiloint2double((2046 - e2) << 20, 0);
+                    atomicAdd(&s_cnt, 1u);
+                    atomicMax(&s_mx, __float_as_uint(fminf((float)(c2 * s2) / (float)(ab * s2), 1.0f)));
+                }
+#pragma unroll
+                for (int it = 0; it < OSJC_IT; ++it) {
+                    const int k = hl + 32 * it;
+                    if (k < K) {
+                        gp[k] = cs * x[it] - sn * y[it];
+                        gq[k] = sn * x[it] + cs * y[it];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const unsigned total = s_cnt, mx = s_mx;
+        __syncthreads();
+        if (tid == 0) { s_cnt = 0; s_mx = 0; }
+        __syncthreads();
+        if (total == 0u || __uint_as_float(mx) < 1e-15f) { ++sweep; converged = true; break; }
+    }
+    for (long long e = tid; e < (long long)K * K; e += nt) Gg[e] = G[e];
+    for (int i = tid; i < K; i += nt) perm_out[i] = s_perm[i];
+    if (tid == 0) *sweeps_out = converged ? sweep : max_sweeps + 1;
 }
 
 // eigenvalues = squared norms of the orthogonalised columns, rank-sorted descending (ties by index); eigenvectors = the
@@ -555,7 +661,8 @@ __global__ void k_pack_v(const double* __restrict__ V, const int* __restrict__ o
 // cost the compute warps a single stall.  A TMA producer warp therefore keeps a ring of 5 stages (8 columns x 1024 rows
 // of A each) in flight, and the 8 compute warps -- 4 consecutive rows x MP outputs per thread, 80 accumulators for
 // MP = 20 -- read their operands from shared memory only: one 16-byte load of A and MP / 4 broadcast loads of V per 4 MP
-// FMAs.  (Round 1 loaded A straight from global memory into registers with V in the constant bank: 124 registers per
+// FMAs.  What bounds it now is instruction issue (ncu: 70 % of the issue slots, FMA pipe 59 %, DRAM 60 %); packed FFMA2 with V
+// duplicated in shared memory was measured and is slower (twice the V loads for the same FMA-pipe time).  (Round 1 loaded A straight from global memory into registers with V in the constant bank: 124 registers per
 // thread left 16 warps per SM to cover DRAM latency, 71 % of the HBM peak with the FMA pipe half idle; and the
 // module-global constant bank was shared by every context of a device.)  V lives in this CTA's shared memory now.
 #define FP_ROWS 1024
@@ -822,11 +929,16 @@ int ssi_swa_eigen_stage(ssi_ctx* ctx, int M, const double* dG_src, bool check, b
         const int np = (K + 1) / 2;
         grid = std::max(1, std::min(ctx->sm_count, (np * 16 + OSJ_THREADS - 1) / OSJ_THREADS));
     }
-    if (use_smem && !ctx->opt_eig_single) {
-        // a cluster of 8 CTAs, every one with a copy of the matrix in its shared memory
+    if (use_smem && ctx->opt_eig_cluster) {
+        // a cluster of 8 CTAs, every one with a copy of the matrix in its shared memory (A-B: the cluster barrier costs more
+        // than it buys at these sizes)
         const size_t csm = jsm + sizeof(int) * (size_t)K;
         SSI_CUDA(ctx, cudaFuncSetAttribute(k_osj_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
         k_osj_cluster<<<OSJC_CTAS, OSJC_THREADS, csm, ctx->stream>>>(e.dG, K, 60, e.dPerm, e.dSweeps);
+    } else if (use_smem) {
+        const size_t csm = jsm + sizeof(int) * (size_t)K;
+        SSI_CUDA(ctx, cudaFuncSetAttribute(k_osj_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+        k_osj_smem<<<1, OSJS_THREADS, csm, ctx->stream>>>(e.dG, K, 60, e.dPerm, e.dSweeps);
     } else {
         double* Gp = e.dG;
         int Kv = K, ms = 60, us = use_smem;

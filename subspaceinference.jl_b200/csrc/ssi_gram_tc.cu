@@ -4,11 +4,11 @@
 // construction path produces (K = number of deviation columns, n ~ 1e7): one pass over A at HBM speed.
 //
 //   * A is column-major n x K == K rows of length n.  A TMA box {32 rows-of-A, 128 columns-of-A} lands in a RAW ring of
-//     eight 16 KB slots as a [128][32] FP32 tile with 128-byte swizzle (columns >= K are zero-filled by TMA).  The ring
+//     six 16 KB slots as a [128][32] FP32 tile with 128-byte swizzle (columns >= K are zero-filled by TMA).  The ring
 //     is deep because a tile gathers one 128-byte segment from each of the K columns (K different DRAM pages).
-//   * four converter warps turn a raw tile into the operand of tcgen05.mma kind::f16: two FP16 planes H = fp16(s x) and
+//   * six converter warps turn a raw tile into the operand of tcgen05.mma kind::f16: two FP16 planes H = fp16(s x) and
 //     L = fp16(s x - H), [128][32] halves each = 64-byte rows, K-major SWIZZLE_64B, H and L back to back (16 KB per
-//     operand slot, three slots).  s = 2^j puts the largest |A| (tracked by k_swa_push, one atomicMax per block) at 2^14,
+//     operand slot, six slots).  s = 2^j puts the largest |A| (tracked by k_swa_push, one atomicMax per block) at 2^14,
 //     so H cannot overflow and H + L carries 22 bits of every value that matters.  Round 1 split into TF32 planes in
 //     place (FP32 containers): 109 KB of shared-memory traffic per 16 KB of A, 80 % of the crossbar, 52 % of the HBM
 //     peak; 16-bit planes make it 71 KB and halve the tensor-core time.
@@ -22,8 +22,8 @@
 //     per-CTA FP64 partials (each thread owns its elements: plain load-add-store, no atomics) and reset; a final
 //     kernel sums the per-CTA partials in fixed order, symmetrises and undoes the scale.
 //
-// Roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-5 converters (one tile each),
-// warps 6-9 drain.  TMEM: 2 x (HH | HL) x 128 columns = 512.
+// Roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-7 converters (one tile each),
+// warps 8-11 drain.  TMEM: 2 x (HH | HL) x 128 columns = 512.
 #include "ssi_common.cuh"
 #include "ssi_ptx.cuh"
 
@@ -33,10 +33,12 @@
 #define GT_ROWS 32                   // rows of A per tile (= 128 bytes of FP32 = one swizzle row)
 #define GT_RAW_BYTES (128 * 128)     // [128 columns of A][32 rows] FP32
 #define GT_OP_BYTES (2 * 128 * 64)   // H | L: [128 columns of A][32 rows] FP16 each
-#define GT_RAW 8                     // raw slots
-#define GT_OPS 3                     // operand slots
-#define GT_CONV 4                    // converter warps
-#define GT_THREADS 320
+#define GT_CONV 6                    // converter warps: the split costs ~2000 cycles of latency per tile and warp, four warps were
+                                     // the bottleneck (970 cycles per tile at 56 % of the HBM peak)
+#define GT_RAW GT_CONV               // raw and operand slots: one of each per converter warp (tile t -> slot t % 6 = its converter),
+#define GT_OPS GT_CONV               // so that a warp only ever waits on barriers it cycles itself and can never run two phases
+                                     // ahead (an mbarrier parity wait cannot tell phase p from phase p + 2)
+#define GT_THREADS (64 + 32 * GT_CONV + 128)
 #define GT_OFF_OP (GT_RAW * GT_RAW_BYTES)
 #define GT_OFF_BAR (GT_OFF_OP + GT_OPS * GT_OP_BYTES)
 #define GT_NBAR (2 * GT_RAW + 2 * GT_OPS + 4)

@@ -68,11 +68,11 @@ def test_random_shapes_tensor_vs_oracle(ssi, engine, dims, acts, N, M, B):
     # that is smooth in z and cancels in MH margins (tests/test_gpu_scale.py)
     np.testing.assert_allclose(lp, ref, rtol=RTOL / 3)
     assert engine.stats().tc_range_fallbacks == 0
-    # A-B variant: CTA pairs (cta_group::2, 256-row MMAs over the two SMs of a TPC; odd tile counts exercise the dummy
-    # row block): the same products in the same order, so the same bits
-    engine.set_option("tc_pair", 1)
-    np.testing.assert_array_equal(engine.logpost(Z, 0.8), lp)
+    # A-B variant: one CTA per 128-row tile instead of CTA pairs (cta_group::2, 256-row MMAs over the two SMs of a TPC; odd
+    # tile counts exercise the pair's dummy row block): the same products in the same order, so the same bits
     engine.set_option("tc_pair", 0)
+    np.testing.assert_array_equal(engine.logpost(Z, 0.8), lp)
+    engine.set_option("tc_pair", 1)
     # the FP32 SIMT path of the same library must agree with the oracle at least as well
     engine.set_option("path", ssi.PATH_LAYERED)
     lp_simt = engine.logpost(Z, 0.8)
