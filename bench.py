@@ -218,7 +218,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample", "numpy_openblas", "torch_f64")},
             "e2e": {"value": res["value"], "unit": "sample*datapoint/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -369,7 +369,27 @@ def multi_ctx_section(ssi, torch, prob, world, B, sigma_m, zs, steps):
         eng.close()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line, on the process's real stdout."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def guard_stdout():
+    """Libraries write banners to file descriptor 1 ("NCCL version ..." at the first collective): keep stdout for the JSON
+    line alone by pointing fd 1 at stderr for the rest of the run."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -405,6 +425,9 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    # a host-side group for the waits that must not occupy a GPU: a rank parked in an NCCL barrier keeps a spinning kernel
+    # on its device, and a persistent grid launched beside it (the multi-device section below) runs in two waves
+    host_group = dist.new_group(backend="gloo") if world > 1 else None
 
     name, _, sigma_m, zs = WORKLOADS[args.workload]
     prob = workloads.make(name)
@@ -627,18 +650,19 @@ def main():
         line["streams"] = streams_section(ssi, torch, dev, local_rank, load_peaks())
         torch.cuda.empty_cache()
     if world > 1:
-        dist.barrier()                     # every rank has released its device memory
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)     # every rank has released its device memory (host-side wait: the GPUs stay idle)
         if rank == 0 and extras:
             try:
                 line["multi_device_ctx"] = multi_ctx_section(ssi, torch, prob, world, B if not mh else B, sigma_m, zs, 1)
             except Exception as ex:        # reported, never fatal for the headline line
                 line["multi_device_ctx"] = {"error": str(ex)[:300]}
-        dist.barrier()
+        dist.barrier(group=host_group)
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_reference(args.workload, budget_s=15.0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample", "numpy_openblas", "torch_f64")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

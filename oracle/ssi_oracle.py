@@ -348,17 +348,20 @@ def mala_propose_f32(z: np.ndarray, grad: np.ndarray, sigma_z: float, eps: np.nd
     return propose_f32(base, sigma_z, eps)
 
 
-def mala_log_alpha(z, zp, lp, lpp, g, gp, sigma_z: float) -> float:
-    """lp' - lp + log q(z | z') - log q(z' | z),  q(a | b) = N(a; b + (sigma_z^2/2) grad lp(b), sigma_z^2 I)."""
+def mala_log_alpha(z, zp, lp, lpp, g, gp, sigma_z: float, rule: int = 0) -> float:
+    """lp' - lp + log q(z | z') - log q(z' | z),  q(a | b) = N(a; b + (sigma_z^2/2) grad lp(b), sigma_z^2 I)  (rule 0).
+    rule 1 evaluates both densities with the NEGATED gradient, q(a | b) = N(a - b; -(sigma_z^2/2) grad lp(b), sigma_z^2 I):
+    AdvancedMH's MALA step is remembered to build its densities from ``proposal(-gradient)``; the pinned 0.6.2 source is
+    not in /root/reference to decide, so the library offers both (option ``mala_rule``) and this oracle restates both."""
     z, zp = np.asarray(z, np.float64), np.asarray(zp, np.float64)
-    h = 0.5 * sigma_z * sigma_z
+    h = 0.5 * sigma_z * sigma_z * (-1.0 if rule else 1.0)
     fwd = float(np.sum((zp - z - h * np.asarray(g, np.float64)) ** 2))
     rev = float(np.sum((z - zp - h * np.asarray(gp, np.float64)) ** 2))
     return lpp - lp + (fwd - rev) / (2.0 * sigma_z * sigma_z)
 
 
 def mala_chain(prob: Problem, n_steps: int, seed: int, chain: int, sigma_z=1.0, sigma_m=1.0, sigma_p=1.0,
-               mask=TERM_LL, z0=None):
+               mask=TERM_LL, z0=None, rule: int = 0):
     """One chain of ``sample(DensityModel(density), MALA(x -> MvNormal((sigma_z^2 / 2) .* x, sigma_z)), itr;
     init_params=rand(MvNormal(zeros(M), sigma_z)))`` (src/space_inference.jl:117-120): sample 1 is the initial point
     z0 = sigma_z*eps_0, step t draws the increment from N((sigma_z^2/2) grad lp(z), sigma_z^2 I) and accepts iff
@@ -380,7 +383,7 @@ def mala_chain(prob: Problem, n_steps: int, seed: int, chain: int, sigma_z=1.0, 
         zp = mala_propose_f32(z, g, sigma_z, rng_normals(seed, chain, t, M))
         lpp, gp = f(zp)
         e = rng_exponential(seed, chain, t)
-        la = mala_log_alpha(z, zp, lp, lpp, g, gp, sigma_z)
+        la = mala_log_alpha(z, zp, lp, lpp, g, gp, sigma_z, rule)
         margin[t] = la + e
         if -e < la:
             z, lp, g, acc[t] = zp, lpp, gp, 1

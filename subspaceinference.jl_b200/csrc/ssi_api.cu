@@ -7,6 +7,13 @@
 #include <cmath>
 #include <mutex>
 
+#include <nvtx3/nvToolsExt.h>        // header-only: NVTX ranges cost nothing unless a profiler is attached (tracing)
+struct nvtx_range {
+    explicit nvtx_range(const char* name) { nvtxRangePushA(name); }
+    ~nvtx_range() { nvtxRangePop(); }
+};
+#define SSI_NVTX(name) nvtx_range nvtx_range__(name)
+
 int ssi_mh_device(ssi_ctx*, int, int64_t, int64_t, uint64_t, int64_t, int64_t, double, double, double, uint32_t,
                   const float*, float*, double*, uint8_t*);
 int ssi_mh_fetch_accepts(ssi_ctx*);
@@ -262,6 +269,10 @@ int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
     if (!strcmp(key, "tc_k32")) { ctx->opt_tc_k32 = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "tc_alast")) { ctx->opt_tc_alast = value != 0; return SSI_OK; }
     if (!strcmp(key, "tc_nokrev")) { ctx->opt_tc_nokrev = value != 0; return SSI_OK; }
+    // MALA acceptance rule: 0 (default) = the Metropolis-adjusted Langevin ratio as documented; 1 = both proposal densities
+    // evaluated with the NEGATED gradient, q(a | b) = N(a - b; -(sigma^2/2) grad(a), sigma^2) -- how AdvancedMH's MALA step is
+    // remembered to be written (`spl.proposal(-t_cond.gradient)`); the pinned 0.6.2 source is not available to decide
+    if (!strcmp(key, "mala_rule")) { if (value != 0 && value != 1) return ssi_fail(ctx, SSI_ERR_ARG, "mala_rule must be 0 or 1"); ctx->opt_mala_rule = (int)value; return SSI_OK; }
     if (!strcmp(key, "tc_pair")) { ctx->opt_tc_pair = value != 0; return SSI_OK; }
     if (!strcmp(key, "tc_precision")) { ctx->opt_tc_prec = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "b1_simt")) { ctx->opt_b1_simt = value != 0; return SSI_OK; }
@@ -316,6 +327,7 @@ int ssi_set_model(ssi_ctx* ctx, int n_layers, const int32_t* dims, const int32_t
 
 int ssi_set_data(ssi_ctx* ctx, const float* X, const float* Y, int64_t N) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX("ssi_set_data");
     if (ctx->is_multi()) return ssi_multi_set_data(ctx, X, Y, N);
     if (!ctx->has_model) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_set_model must be called before ssi_set_data");
     if (!X || !Y || N < 1) return ssi_fail(ctx, SSI_ERR_ARG, "X, Y must be non-NULL and N >= 1");
@@ -370,12 +382,14 @@ extern "C" {
 
 int ssi_set_decoder(ssi_ctx* ctx, const float* W_swa, int32_t n_layers, const int32_t* dims, const int32_t* act, const float* theta) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX("ssi_set_decoder");
     if (ctx->is_multi()) return ssi_multi_set_decoder(ctx, W_swa, n_layers, dims, act, theta);
     return ssi_set_decoder_impl(ctx, W_swa, n_layers, dims, act, theta);
 }
 
 int ssi_set_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, int64_t n, int32_t M) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX("ssi_set_subspace");
     if (!W_swa || !P) return ssi_fail(ctx, SSI_ERR_ARG, "W_swa and P must be non-NULL");
     if (ctx->is_multi()) return ssi_multi_set_subspace(ctx, W_swa, P, n, M);
     return install_subspace(ctx, W_swa, P, n, M, cudaMemcpyHostToDevice);
@@ -384,6 +398,7 @@ int ssi_set_subspace(ssi_ctx* ctx, const float* W_swa, const float* P, int64_t n
 int ssi_logpost_batch_dev(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m, double sigma_p, double sigma_z,
                           uint32_t prior_mask, double* d_lp_out, double* d_terms_out) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX("ssi_logpost_batch_dev");
     if (B < 0 || (B > 0 && (!dZ || !d_lp_out))) return ssi_fail(ctx, SSI_ERR_ARG, "Z and lp_out must be non-NULL, B >= 0");
     SSI_NO_MULTI(ctx, "device-pointer entry points");
     SSI_TRY(ssi_use_device(ctx));
@@ -396,6 +411,7 @@ int ssi_logpost_batch_dev(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma
 int ssi_logpost_grad_batch_dev(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m, double sigma_p, double sigma_z,
                                uint32_t prior_mask, double* d_lp_out, double* d_grad_out) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX("ssi_logpost_grad_batch_dev");
     if (B < 0 || (B > 0 && (!dZ || !d_lp_out || !d_grad_out)))
         return ssi_fail(ctx, SSI_ERR_ARG, "Z, lp_out and grad_out must be non-NULL, B >= 0");
     SSI_NO_MULTI(ctx, "device-pointer entry points");
@@ -409,6 +425,7 @@ int ssi_logpost_grad_batch_dev(ssi_ctx* ctx, const float* dZ, int64_t B, double 
 int ssi_logpost_grad_batch(ssi_ctx* ctx, const float* Z, int64_t B, double sigma_m, double sigma_p, double sigma_z,
                            uint32_t prior_mask, double* lp_out, double* grad_out) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX("ssi_logpost_grad_batch");
     if (B < 0 || (B > 0 && (!Z || !lp_out || !grad_out)))
         return ssi_fail(ctx, SSI_ERR_ARG, "Z, lp_out and grad_out must be non-NULL, B >= 0");
     if (ctx->is_multi()) return ssi_multi_logpost(ctx, 1, Z, B, sigma_m, sigma_p, sigma_z, prior_mask, lp_out, grad_out);
@@ -434,6 +451,7 @@ int ssi_logpost_grad_batch(ssi_ctx* ctx, const float* Z, int64_t B, double sigma
 int ssi_logpost_batch(ssi_ctx* ctx, const float* Z, int64_t B, double sigma_m, double sigma_p, double sigma_z,
                       uint32_t prior_mask, double* lp_out, double* terms_out) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX("ssi_logpost_batch");
     if (B < 0 || (B > 0 && (!Z || !lp_out))) return ssi_fail(ctx, SSI_ERR_ARG, "Z and lp_out must be non-NULL, B >= 0");
     if (ctx->is_multi()) return ssi_multi_logpost(ctx, 0, Z, B, sigma_m, sigma_p, sigma_z, prior_mask, lp_out, terms_out);
     if (!ctx->has_model || !ctx->has_data || !ctx->has_sub)
@@ -467,6 +485,7 @@ static int mh_run_dev(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_steps,
                       double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* d_z0,
                       float* d_z_trace, double* d_lp_trace, uint8_t* d_accept_trace) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX(kind == 1 ? "ssi_mala_run_dev" : "ssi_mh_run_dev");
     SSI_NO_MULTI(ctx, "device-pointer entry points");
     SSI_TRY(ssi_use_device(ctx));
     call_timer t(ctx);
@@ -502,6 +521,7 @@ int ssi_mh_run_from_dev(ssi_ctx* ctx, int32_t kind, int64_t n_chains, int64_t n_
 int ssi_mh_run_host_slice(ssi_ctx* ctx, int kind, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset, int64_t step_offset,
                           double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask, const float* z0,
                           float* z_trace, double* lp_trace, uint8_t* accept_trace, int64_t ld_chains, int64_t c0) {
+    SSI_NVTX(kind == 1 ? "ssi_mala_run" : "ssi_mh_run");
     if (!ctx->has_model || !ctx->has_data || !ctx->has_sub)
         return ssi_fail(ctx, SSI_ERR_STATE, "model, data and subspace must be set before sampling");
     if (n_chains <= 0 || n_steps <= 0) return ssi_fail(ctx, SSI_ERR_ARG, "n_chains and n_steps must be positive");
@@ -612,6 +632,7 @@ int ssi_rng_replay(uint64_t seed, int64_t chain, int64_t step, int32_t M, float*
 
 int ssi_project(ssi_ctx* ctx, const float* Z, int64_t B, float* W_out) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX("ssi_project");
     if (ctx->is_multi()) return ssi_multi_project(ctx, Z, B, W_out);
     if (!ctx->has_model || !ctx->has_sub) return ssi_fail(ctx, SSI_ERR_STATE, "model and subspace must be set");
     if (B < 0 || (B > 0 && (!Z || !W_out))) return ssi_fail(ctx, SSI_ERR_ARG, "Z and W_out must be non-NULL");
@@ -652,6 +673,7 @@ int ssi_project(ssi_ctx* ctx, const float* Z, int64_t B, float* W_out) {
 int ssi_predict_batch(ssi_ctx* ctx, const float* Z, int64_t B, const float* Xg, int64_t Ng,
                       float* preds_out, double* mean_out, double* std_out) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX("ssi_predict_batch");
     SSI_FIRST_DEVICE(ctx, ssi_predict_batch(ctx, Z, B, Xg, Ng, preds_out, mean_out, std_out));
     if (!ctx->has_model || !ctx->has_sub) return ssi_fail(ctx, SSI_ERR_STATE, "model and subspace must be set before predicting");
     if (B < 0 || Ng < 0) return ssi_fail(ctx, SSI_ERR_ARG, "B and Ng must be non-negative");
@@ -707,6 +729,7 @@ int ssi_swa_begin(ssi_ctx* ctx, int64_t n, int64_t K_max) {
 
 int ssi_swa_push_dev(ssi_ctx* ctx, const float* dW, double n_scalar) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX("ssi_swa_push_dev");
     SSI_NO_MULTI(ctx, "device-pointer entry points");
     if (!dW) return ssi_fail(ctx, SSI_ERR_ARG, "W must be non-NULL");
     SSI_TRY(ssi_use_device(ctx));
@@ -718,6 +741,7 @@ int ssi_swa_push_dev(ssi_ctx* ctx, const float* dW, double n_scalar) {
 
 int ssi_swa_push(ssi_ctx* ctx, const float* W, double n_scalar) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX("ssi_swa_push");
     SSI_FIRST_DEVICE(ctx, ssi_swa_push(ctx, W, n_scalar));
     if (!W) return ssi_fail(ctx, SSI_ERR_ARG, "W must be non-NULL");
     if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
@@ -766,6 +790,7 @@ int ssi_train_begin(ssi_ctx* ctx, const float* W0, int32_t optimiser, double eta
 
 int ssi_train_step(ssi_ctx* ctx, const int64_t* idx, int64_t j0, int64_t nb, double* loss_out) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX("ssi_train_step");
     SSI_FIRST_DEVICE(ctx, ssi_train_step(ctx, idx, j0, nb, loss_out));
     SSI_TRY(ssi_use_device(ctx));
     call_timer t(ctx);
@@ -841,6 +866,7 @@ static int swa_scratch(ssi_ctx* ctx, int M, float** dPout, double** ds) {
 
 int ssi_swa_finish(ssi_ctx* ctx, int32_t M, float* W_swa_out, float* P_out, double* s_out, int32_t install) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX("ssi_swa_finish");
     if (ctx->is_multi()) return ssi_multi_swa_finish(ctx, M, W_swa_out, P_out, s_out, install);
     if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
     if (M < 1) return ssi_fail(ctx, SSI_ERR_ARG, "M must be positive");
@@ -858,6 +884,7 @@ int ssi_swa_finish(ssi_ctx* ctx, int32_t M, float* W_swa_out, float* P_out, doub
 
 int ssi_swa_gram_dev(ssi_ctx* ctx, double* dG_out, int32_t exact) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX("ssi_swa_gram_dev");
     SSI_NO_MULTI(ctx, "device-pointer entry points");
     if (ctx->swa_n <= 0 || ctx->swa_K <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "no snapshots have been pushed");
     if (!dG_out) return ssi_fail(ctx, SSI_ERR_ARG, "G_out must be a device pointer to K x K doubles");
@@ -873,6 +900,7 @@ int ssi_swa_gram_dev(ssi_ctx* ctx, double* dG_out, int32_t exact) {
 int ssi_swa_finish_gram(ssi_ctx* ctx, int32_t M, const double* dG, int32_t gram_exact, float* W_swa_out, float* P_out,
                         double* s_out, int32_t install) {
     if (!ctx) return SSI_ERR_ARG;
+    SSI_NVTX("ssi_swa_finish_gram");
     SSI_NO_MULTI(ctx, "device-pointer entry points");
     if (ctx->swa_n <= 0) return ssi_fail(ctx, SSI_ERR_STATE, "ssi_swa_begin has not been called");
     if (M < 1) return ssi_fail(ctx, SSI_ERR_ARG, "M must be positive");

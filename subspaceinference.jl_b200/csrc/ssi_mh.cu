@@ -43,7 +43,7 @@ k_mh_accept(float* __restrict__ z, const float* __restrict__ zp, double* __restr
             long long n_chains, int M, unsigned long long seed, long long chain_off, unsigned step, int force,
             float* __restrict__ z_trace, double* __restrict__ lp_trace, unsigned char* __restrict__ acc_trace,
             unsigned long long* __restrict__ n_acc,
-            double* __restrict__ g, const double* __restrict__ gp, double half_s2, double inv2s2) {
+            double* __restrict__ g, const double* __restrict__ gp, double half_s2, double inv2s2, int mala_rule) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned accepted = 0;
     if (c < n_chains) {
@@ -58,8 +58,11 @@ k_mh_accept(float* __restrict__ z, const float* __restrict__ zp, double* __restr
                 double fwd = 0.0, rev = 0.0;
                 for (int m = 0; m < M; ++m) {
                     const double a = (double)z[m + c * M], b = (double)zp[m + c * M];
-                    const double df = b - a - half_s2 * g[m + c * M];
-                    const double dr = a - b - half_s2 * gp[m + c * M];
+                    // rule 0: q(z'|z) = N(z'; z + (s^2/2) grad(z), s^2), q(z|z') likewise.  rule 1: the densities as AdvancedMH's
+                    // step is remembered to evaluate them, logpdf(proposal(-grad(x)), x - x') -- the drift enters negated and the
+                    // roles of the two gradients are swapped
+                    const double df = mala_rule ? (b - a + half_s2 * g[m + c * M]) : (b - a - half_s2 * g[m + c * M]);
+                    const double dr = mala_rule ? (a - b + half_s2 * gp[m + c * M]) : (a - b - half_s2 * gp[m + c * M]);
                     fwd += df * df;
                     rev += dr * dr;
                 }
@@ -134,7 +137,7 @@ int ssi_mh_device(ssi_ctx* ctx, int kind, int64_t C, int64_t S, uint64_t seed, i
         units += ctx->stats.last_units;
         flops += ctx->stats.last_flops;
         k_mh_accept<<<g_acc, 256, 0, ctx->stream>>>(z, zp, lp, lpp, C, M, seed, chain_off, 0u, 1, nullptr, nullptr, nullptr, cnt, g, gp,
-                                                  half_s2, inv2s2);
+                                                  half_s2, inv2s2, ctx->opt_mala_rule);
         SSI_LAUNCH_CHECK(ctx);
     }
     for (int64_t i = 0; i < S; ++i) {
@@ -152,7 +155,7 @@ int ssi_mh_device(ssi_ctx* ctx, int kind, int64_t C, int64_t S, uint64_t seed, i
         // trace row i of this call = step t of the chain
         k_mh_accept<<<g_acc, 256, 0, ctx->stream>>>(z, zp, lp, lpp, C, M, seed, chain_off, (unsigned)t, t == 0,
                                                   d_ztr ? d_ztr + (size_t)i * C * M : nullptr, d_lptr ? d_lptr + (size_t)i * C : nullptr,
-                                                  d_acctr ? d_acctr + (size_t)i * C : nullptr, cnt, g, gp, half_s2, inv2s2);
+                                                  d_acctr ? d_acctr + (size_t)i * C : nullptr, cnt, g, gp, half_s2, inv2s2, ctx->opt_mala_rule);
         SSI_LAUNCH_CHECK(ctx);
     }
     ctx->stats.last_units = units;

@@ -115,13 +115,17 @@ def test_many_chains_full_c2(ssi, engine):
     assert np.isfinite(lt).all()
 
 
+@pytest.mark.parametrize("rule", [0, 1])
 @pytest.mark.parametrize("name,N,sigma_z,sigma_m", [("uci", 1500, 0.02, 0.1), ("readme", None, 0.45, 1.0)])
-def test_mala_decisions_teacher_forced(ssi, engine, name, N, sigma_z, sigma_m):
+def test_mala_decisions_teacher_forced(ssi, engine, name, N, sigma_z, sigma_m, rule):
     """MALA (src/space_inference.jl:117-120) on the device vs the oracle, teacher-forced: from the device's own state at
     t-1 the Float64 oracle, on the replayed stream, must propose the same point (up to the FP32 gradient in the drift)
-    and take the same decision unless the margin is a near tie."""
+    and take the same decision unless the margin is a near tie.  Both acceptance rules the library offers (option
+    ``mala_rule``: 0 the documented Metropolis-adjusted Langevin ratio, 1 the negated-gradient proposal densities) are
+    held to their oracle restatement; which one AdvancedMH 0.6.2 evaluates is PARITY UNPINNED."""
     prob = orc.make_problem(name, N=N) if N else orc.make_problem(name)
     _setup(engine, prob)
+    engine.set_option("mala_rule", rule)
     C, S, seed = 5, 25, 77
     zt, lt, at = engine.mala_run(C, S, seed, sigma_z=sigma_z, sigma_m=sigma_m)
     near_ties = 0
@@ -133,7 +137,7 @@ def test_mala_decisions_teacher_forced(ssi, engine, name, N, sigma_z, sigma_m):
             lp_prev, g_prev = orc.density_and_grad(prob, z[t - 1], sigma_m)
             zp = orc.mala_propose_f32(z[t - 1], g_prev, sigma_z, orc.rng_normals(seed, c, t, prob.M))
             lp_prop, g_prop = orc.density_and_grad(prob, zp, sigma_m)
-            margin = orc.mala_log_alpha(z[t - 1], zp, lp_prev, lp_prop, g_prev, g_prop, sigma_z) + orc.rng_exponential(seed, c, t)
+            margin = orc.mala_log_alpha(z[t - 1], zp, lp_prev, lp_prop, g_prev, g_prop, sigma_z, rule) + orc.rng_exponential(seed, c, t)
             np.testing.assert_allclose(lt[c, t - 1], lp_prev, rtol=1e-5)
             if abs(margin) <= 1e-5 * max(1.0, abs(lp_prev)):       # the drift carries an FP32 gradient: wider tie band than RWMH
                 near_ties += 1
@@ -143,7 +147,8 @@ def test_mala_decisions_teacher_forced(ssi, engine, name, N, sigma_z, sigma_m):
             drift = 0.5 * sigma_z ** 2 * np.abs(g_prev).max()
             np.testing.assert_allclose(z[t], expect, rtol=0, atol=2e-4 * drift + np.abs(expect).max() * 2.4e-7 + 1e-12)
     assert near_ties <= 3
-    assert 0 < at[:, 1:].mean() < 1          # both outcomes are exercised
+    if rule == 0:
+        assert 0 < at[:, 1:].mean() < 1      # both outcomes are exercised (rule 1 is not a valid MH ratio: it may accept everything)
 
 
 def test_mala_chain_sharding_is_bitwise_invariant(ssi, engine):
