@@ -258,7 +258,7 @@ int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
     // -1 = tensor-core Gram without the check (measurement only)
     if (!strcmp(key, "gram_fp64")) { ctx->opt_gram_fp64 = (int)value; return SSI_OK; }
     if (!strcmp(key, "gram_chunk")) { ctx->opt_gram_chunk = (int)value; return SSI_OK; }
-    if (!strcmp(key, "eig_cluster")) { ctx->opt_eig_cluster = value != 0; return SSI_OK; }
+    if (!strcmp(key, "eig_cluster")) { ctx->opt_eig_cluster = (int)value; return SSI_OK; }
     if (!strcmp(key, "formp_simt")) { ctx->opt_formp_simt = value != 0; return SSI_OK; }
     if (!strcmp(key, "tc_nobasis")) { ctx->opt_tc_nobasis = value != 0; ssi_tc_invalidate(ctx); ssi_b1_invalidate(ctx); ssi_bm_invalidate(ctx); return SSI_OK; }
     if (!strcmp(key, "time_dominant")) {

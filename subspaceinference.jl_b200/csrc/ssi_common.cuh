@@ -70,8 +70,8 @@ struct ssi_ctx {
     int opt_tc_simt_basis = 0; // A-B: first layer as the FP32 SIMT basis combination instead of the tensor-core one
     int opt_gram_fp64 = 0;    // force the FP64 SIMT Gram (default: tensor-core TF32x2 Gram for large n, K <= 128)
     int opt_formp_simt = 0;   // A-B: P = A V_M with loads from global memory (k_form_p) instead of the TMA-staged stream
-    int opt_eig_cluster = 1;  // eigen-solve (K <= 160) on a cluster of eight CTAs; 0: one CTA (A-B)
-    int opt_gram_chunk = 0;   // tiles (32 rows) per FP32 accumulation chunk of the tensor-core Gram (default 32)
+    int opt_eig_cluster = 1;  // eigen-solve (K <= 160) on a cluster of eight CTAs (2: its first version); 0: one CTA (A-B)
+    int opt_gram_chunk = 0;   // tiles (64 rows) per FP32 accumulation chunk of the tensor-core Gram (default 16)
     int opt_tc_nobasis = 0;   // debugging / A-B: run the first layer as a GEMM instead of the affine-in-z basis combination   // debugging / A-B: sample-major work order on the first layer
 
     // model / data / subspace

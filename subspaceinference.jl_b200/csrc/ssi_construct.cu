@@ -222,8 +222,13 @@ __device__ __forceinline__ void osj_grid_barrier(unsigned* counter, unsigned& ta
 }
 
 // Pi G Pi' = L L' in place (full symmetric storage in, lower triangle out, strict upper triangle and the columns past the
-// numerical rank zeroed); perm[r] = original index of row r.  One CTA.
-__device__ void osj_pivoted_cholesky(double* __restrict__ G, int K, int* __restrict__ perm, double thresh, double* red, int* redi) {
+// numerical rank zeroed); perm[r] = original index of row r.  One CTA; G has leading dimension ld >= K.
+// Three block barriers per pivot step and no integer division: every warp finds the pivot for itself (same data, same
+// order, same answer), the symmetric swap is one pass, the trailing update writes both triangles (the two mirror entries
+// are the same fused multiply-add, bit for bit) so that the matrix stays symmetric without a mirror pass.  The first
+// version (block-wide argmax through shared memory, triangle update + mirror pass indexed by 64-bit division, seven
+// barriers per step) cost 0.6 ms at K = 100, 29 % of the eigen-solve.
+__device__ void osj_pivoted_cholesky(double* __restrict__ G, int K, int ld, int* __restrict__ perm, double thresh) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     for (int i = tid; i < K; i += nt) perm[i] = i;
     __syncthreads();
@@ -232,8 +237,8 @@ __device__ void osj_pivoted_cholesky(double* __restrict__ G, int K, int* __restr
         // pivot = largest remaining diagonal entry (ties: smallest index)
         double best = -1.0;
         int bi = j;
-        for (int i = j + tid; i < K; i += nt) {
-            const double v = G[i + (long long)i * K];
+        for (int i = j + lane; i < K; i += 32) {
+            const double v = G[i + (long long)i * ld];
             if (v > best) { best = v; bi = i; }
         }
 #pragma unroll
@@ -242,41 +247,34 @@ __device__ void osj_pivoted_cholesky(double* __restrict__ G, int K, int* __restr
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
-        if (lane == 0) { red[warp] = best; redi[warp] = bi; }
-        __syncthreads();
-        best = red[0]; bi = redi[0];
-        for (int w = 1; w < nw; ++w)
-            if (red[w] > best || (red[w] == best && redi[w] < bi)) { best = red[w]; bi = redi[w]; }
-        __syncthreads();
         if (!(best > thresh)) { rank = j; break; }
-        if (bi != j) {       // symmetric swap j <-> bi: the two rows, then the two columns
-            for (int k = tid; k < K; k += nt) { const double t = G[j + (long long)k * K]; G[j + (long long)k * K] = G[bi + (long long)k * K]; G[bi + (long long)k * K] = t; }
-            __syncthreads();
-            for (int k = tid; k < K; k += nt) { const double t = G[k + (long long)j * K]; G[k + (long long)j * K] = G[k + (long long)bi * K]; G[k + (long long)bi * K] = t; }
+        if (bi != j) {       // symmetric swap j <-> bi: thread k moves the four entries of row / column k it alone touches
+            for (int k = tid; k < K; k += nt) {
+                if (k == j) {
+                    const double t = G[j + (long long)j * ld]; G[j + (long long)j * ld] = G[bi + (long long)bi * ld]; G[bi + (long long)bi * ld] = t;
+                } else if (k != bi) {
+                    double t = G[j + (long long)k * ld]; G[j + (long long)k * ld] = G[bi + (long long)k * ld]; G[bi + (long long)k * ld] = t;
+                    t = G[k + (long long)j * ld]; G[k + (long long)j * ld] = G[k + (long long)bi * ld]; G[k + (long long)bi * ld] = t;
+                }
+            }
             if (tid == 0) { const int t = perm[j]; perm[j] = perm[bi]; perm[bi] = t; }
             __syncthreads();
         }
         const double ljj = sqrt(best), inv = 1.0 / ljj;
-        for (int i = j + tid; i < K; i += nt) G[i + (long long)j * K] = (i == j) ? ljj : G[i + (long long)j * K] * inv;
+        double* cj = G + (long long)j * ld;
+        for (int i = j + tid; i < K; i += nt) cj[i] = (i == j) ? ljj : cj[i] * inv;
         __syncthreads();
-        // trailing update, lower triangle: G[i, k] -= L[i, j] L[k, j] for j < k <= i
-        const int r = K - 1 - j;
-        for (long long e = tid; e < (long long)r * r; e += nt) {
-            const int k = j + 1 + (int)(e / r), i = j + 1 + (int)(e % r);
-            if (i >= k) G[i + (long long)k * K] = fma(-G[i + (long long)j * K], G[k + (long long)j * K], G[i + (long long)k * K]);
-        }
-        __syncthreads();
-        // the pivot search reads the diagonal only, the swaps read full rows: keep the matrix symmetric
-        for (long long e = tid; e < (long long)r * r; e += nt) {
-            const int k = j + 1 + (int)(e / r), i = j + 1 + (int)(e % r);
-            if (i > k) G[k + (long long)i * K] = G[i + (long long)k * K];
+        // trailing update, both triangles: G[i, k] -= L[i, j] L[k, j] for i, k > j
+        for (int k = j + 1 + warp; k < K; k += nw) {
+            const double lk = cj[k];
+            double* ck = G + (long long)k * ld;
+            for (int i = j + 1 + lane; i < K; i += 32) ck[i] = fma(-cj[i], lk, ck[i]);
         }
         __syncthreads();
     }
-    for (long long e = tid; e < (long long)K * K; e += nt) {
-        const int i = (int)(e % K), k = (int)(e / K);
-        if (i < k || k >= rank) G[e] = 0.0;
-    }
+    for (int k = warp; k < K; k += nw)
+        for (int i = lane; i < K; i += 32)
+            if (i < k || k >= rank) G[i + (long long)k * ld] = 0.0;
     __syncthreads();
 }
 
@@ -287,7 +285,6 @@ k_osj(double* __restrict__ Gg /* K x K column-major Gram; on exit the orthogonal
     extern __shared__ double osj_smem[];
     double* G = use_smem ? osj_smem : Gg;
     __shared__ double red[32];
-    __shared__ int redi[32];
     __shared__ double s_tr;
     const int tid = threadIdx.x, nt = blockDim.x;
     const unsigned nb = gridDim.x;
@@ -300,7 +297,7 @@ k_osj(double* __restrict__ Gg /* K x K column-major Gram; on exit the orthogonal
         if (use_smem)
             for (long long e = tid; e < (long long)K * K; e += nt) G[e] = Gg[e];
         __syncthreads();
-        osj_pivoted_cholesky(G, K, perm, (double)K * 2.220446049250313e-16 * s_tr, red, redi);
+        osj_pivoted_cholesky(G, K, K, perm, (double)K * 2.220446049250313e-16 * s_tr);
     }
     osj_grid_barrier(sync_counter, target, nb);          // the other CTAs of a cooperative grid wait for the factor
     const double tol = (double)K * 2.220446049250313e-16, tol2 = tol * tol;
@@ -406,7 +403,6 @@ k_osj_cluster(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__ 
     double* G = osj_smem;                                     // K x K
     int* s_perm = reinterpret_cast<int*>(G + (size_t)K * K);  // K
     __shared__ double red[32];
-    __shared__ int redi[32];
     __shared__ double s_tr;
     __shared__ unsigned s_cnt, s_slot[OSJC_CTAS], s_mx, s_mxslot[OSJC_CTAS];
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -418,7 +414,7 @@ k_osj_cluster(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__ 
         if (tid == 0) { s_tr = tr; s_cnt = 0; s_mx = 0; }
         for (long long e = tid; e < (long long)K * K; e += nt) G[e] = Gg[e];
         __syncthreads();
-        osj_pivoted_cholesky(G, K, s_perm, (double)K * 2.220446049250313e-16 * s_tr, red, redi);
+        osj_pivoted_cholesky(G, K, K, s_perm, (double)K * 2.220446049250313e-16 * s_tr);
     }
     cluster_sync_all();
     const double tol = (double)K * 2.220446049250313e-16, tol2 = tol * tol;
@@ -525,6 +521,165 @@ k_osj_cluster(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__ 
     }
 }
 
+// Second version of the cluster solver (default; the one above stays as option eig_cluster = 2 for A-B).  Same schedule and
+// the same data movement, with the latency chain of a round -- which is what the solver's time consists of: 891 rounds of
+// one rotation each at K = 100 -- cut down:
+//   * columns are padded to IT * 32 rows (zeros), IT a template parameter: no predicates, no partial loops;
+//   * tan(theta) comes from the FP32 closed form alone.  c = rsqrt(1 + t^2) and s = t c are still exact in FP64 (FP32 seed,
+//     one cubically convergent correction), so the rotation is orthogonal to working precision whatever t is; an error of
+//     2^-22 in t leaves 2^-22 of the pair's inner product behind instead of nothing, which the next sweep removes -- the
+//     FP64 Newton step on t bought nothing but latency;
+//   * division and square root are the approximate single-instruction forms (no slow-path calls);
+//   * the cluster barrier is split: arrive after the stores, then the indices and remote addresses of the NEXT round are
+//     computed, then wait.
+//   * the pair slots are dealt out in equal contiguous runs (ceil(np / 8) per CTA).  A column moves to the neighbouring slot
+//     from one round to the next, so only the two columns at each run boundary cross to another SM; and the FP64 pipe -- 64
+//     lanes per clock and SM, ~80 FP64 warp instructions per pair -- is shared by 7 pairs instead of 16: the first version
+//     filled CTA after CTA (16, 16, 16, 2 pairs at K = 100) and its three full SMs were FP64-bound at ~2600 cycles a round.
+__device__ __forceinline__ int osjc2_slot(int x, int r, int m) {
+    if (x == m - 1 || x == r) return 0;
+    int i = x - r; if (i < 0) i += m - 1;                  // x = (r + i) mod (m - 1)
+    if (i >= m / 2) i = (m - 1) - i;                       // else x = (r - i) mod (m - 1)
+    return i;
+}
+template <int IT>
+__global__ void __cluster_dims__(OSJC_CTAS, 1, 1) __launch_bounds__(OSJC_THREADS)
+k_osj_cluster2(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__ perm_out, int* __restrict__ sweeps_out) {
+    constexpr int KP = IT * 32;
+    extern __shared__ double osj_smem[];
+    double* G = osj_smem;                                     // K columns of KP rows
+    int* s_perm = reinterpret_cast<int*>(G + (size_t)K * KP);  // K
+    __shared__ double red[32];
+    __shared__ double s_tr;
+    __shared__ unsigned s_cnt, s_slot[OSJC_CTAS], s_mx, s_mxslot[OSJC_CTAS];
+    const int tid = threadIdx.x, nt = blockDim.x, hl = tid & 31, wid = tid >> 5;
+    const uint32_t rank = cluster_ctarank();
+    {
+        double tr = 0.0;
+        for (int i = tid; i < K; i += nt) tr += fabs(Gg[i + (long long)i * K]);
+        tr = ssi_block_sum(tr, red);
+        if (tid == 0) { s_tr = tr; s_cnt = 0; s_mx = 0; }
+        for (int k = wid; k < K; k += OSJC_HW)
+            for (int i = hl; i < KP; i += 32) G[i + k * KP] = i < K ? Gg[i + (long long)k * K] : 0.0;
+        __syncthreads();
+        osj_pivoted_cholesky(G, K, KP, s_perm, (double)K * 2.220446049250313e-16 * s_tr);
+    }
+    cluster_sync_all();
+    const double tol = (double)K * 2.220446049250313e-16, tol2 = tol * tol;
+    const int m = (K + 1) & ~1, np = m / 2;
+    const int spc = (np + OSJC_CTAS - 1) / OSJC_CTAS;         // pair slots per CTA (<= OSJC_HW, checked by the host)
+    const int slot = (int)rank * spc + wid;                   // this warp's pair slot in every round
+    const bool has_pair = wid < spc && slot < np;
+    const uint32_t g_local = smem_u32(G);
+    // pair of slot i in round r: slot 0 = (m - 1, r), slot i = ((r + i) mod (m - 1), (r - i) mod (m - 1)), ordered p < q
+    int p = 0, q = 0;
+    uint32_t dst_p = 0, dst_q = 0;
+    auto plan = [&](int r) {
+        if (!has_pair) return;
+        const int rn = (r + 1 == m - 1) ? 0 : r + 1;          // the schedule is cyclic across sweeps
+        if (slot == 0) { p = m - 1; q = r; }
+        else { p = r + slot; if (p >= m - 1) p -= m - 1; q = r - slot; if (q < 0) q += m - 1; }
+        if (p > q) { const int t = p; p = q; q = t; }
+        dst_p = osjc_mapa(g_local, (uint32_t)(osjc2_slot(p, rn, m) / spc)) + (uint32_t)(p * KP + hl) * 8u;
+        dst_q = q < K ? osjc_mapa(g_local, (uint32_t)(osjc2_slot(q, rn, m) / spc)) + (uint32_t)(q * KP + hl) * 8u : 0u;
+    };
+    plan(0);
+    int sweep = 0;
+    bool converged = false;
+    for (; sweep < max_sweeps; ++sweep) {
+        for (int r = 0; r < m - 1; ++r) {
+            if (has_pair) {
+                const double* gp = G + p * KP + hl;
+                double x[IT], y[IT];
+#pragma unroll
+                for (int it = 0; it < IT; ++it) x[it] = gp[32 * it];
+                if (q >= K) {                                               // bye: the column only moves on
+#pragma unroll
+                    for (int it = 0; it < IT; ++it) osjc_st_f64(dst_p + (uint32_t)it * 256u, x[it]);
+                } else {
+                    const double* gq = G + q * KP + hl;
+#pragma unroll
+                    for (int it = 0; it < IT; ++it) y[it] = gq[32 * it];
+                    double a = 0.0, b = 0.0, c = 0.0;
+#pragma unroll
+                    for (int it = 0; it < IT; ++it) { a = fma(x[it], x[it], a); b = fma(y[it], y[it], b); c = fma(x[it], y[it], c); }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        a += __shfl_xor_sync(0xffffffffu, a, o);
+                        b += __shfl_xor_sync(0xffffffffu, b, o);
+                        c += __shfl_xor_sync(0xffffffffu, c, o);
+                    }
+                    const double c2 = c * c, ab = a * b;
+                    double cs = 1.0, sn = 0.0;
+                    if (c2 > tol2 * ab) {
+                        // t = h / (d + sign(d) sqrt(d^2 + h^2)), d = |g_q|^2 - |g_p|^2, h = 2 g_p.g_q, on exponent-aligned FP32 copies
+                        const double d = b - a, h = c + c;
+                        const int ex = max(__double2hiint(fabs(d)), __double2hiint(fabs(h))) >> 20;
+                        const double sc = __hiloint2double((2046 - ex) << 20, 0);
+                        const float df = (float)(d * sc), hf = (float)(h * sc);
+                        float rf;
+                        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(fmaf(df, df, hf * hf)));
+                        const double t = (double)__fdividef(hf, df + copysignf(rf, df));
+                        const double w = fma(t, t, 1.0);                  // in [1, 2]
+                        float r0;
+                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"((float)w));
+                        const double c0 = (double)r0;
+                        const double e = fma(-w * c0, c0, 1.0);           // 1 - w c0^2, ~2^-22
+                        cs = fma(c0 * e, fma(0.375, e, 0.5), c0);         // c0 (1 + e/2 + 3 e^2 / 8): error ~e^3
+                        sn = t * cs;
+                        if (hl == 0) {
+                            // largest cos^2 rotated away in this sweep (single precision is plenty: it is compared with 1e-15)
+                            const int e2 = __double2hiint(ab) >> 20;
+                            const double s2 = __hiloint2double((2046 - e2) << 20, 0);
+                            atomicAdd(&s_cnt, 1u);
+                            atomicMax(&s_mx, __float_as_uint(fminf(__fdividef((float)(c2 * s2), (float)(ab * s2)), 1.0f)));
+                        }
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int it = 0; it < IT; ++it) {
+                        osjc_st_f64(dst_p + (uint32_t)it * 256u, cs * x[it] - sn * y[it]);
+                        osjc_st_f64(dst_q + (uint32_t)it * 256u, sn * x[it] + cs * y[it]);
+                    }
+                }
+            }
+            if (r == m - 2) {       // last round of the sweep: publish this CTA's rotation count before the barrier
+                __syncthreads();
+                if (tid < OSJC_CTAS) {
+                    osjc_st_u32(osjc_mapa(smem_u32(&s_slot[rank]), (uint32_t)tid), s_cnt);
+                    osjc_st_u32(osjc_mapa(smem_u32(&s_mxslot[rank]), (uint32_t)tid), s_mx);
+                }
+                __syncwarp();
+            }
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            plan(r + 1 == m - 1 ? 0 : r + 1);
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
+        unsigned total = 0, mx = 0;
+#pragma unroll
+        for (int c = 0; c < OSJC_CTAS; ++c) { total += s_slot[c]; mx = max(mx, s_mxslot[c]); }
+        __syncthreads();
+        if (tid == 0) { s_cnt = 0; s_mx = 0; }
+        __syncthreads();
+        // converged when nothing was rotated, or when every rotation of the sweep was so small (cos < 3e-8) that what it
+        // leaves behind is of second order, cos^2 < 1e-15 (quadratic convergence of the Jacobi method)
+        if (total == 0u || __uint_as_float(mx) < 1e-15f) { ++sweep; converged = true; break; }
+    }
+    // every column is valid in the CTA that owns it in round 0 (the round after the last one): that CTA writes it out
+    if (has_pair) {
+        const int pp = (slot == 0) ? m - 1 : slot, qq = (slot == 0) ? 0 : m - 1 - slot;      // round 0: (r + i, r - i) mod (m - 1) with r = 0
+        for (int k = hl; k < K; k += 32) {
+            if (pp < K) Gg[k + (long long)pp * K] = G[k + pp * KP];
+            if (qq < K) Gg[k + (long long)qq * K] = G[k + qq * KP];
+        }
+    }
+    cluster_sync_all();           // no CTA leaves while a peer may still write into its shared memory
+    if (rank == 0) {
+        for (int i = tid; i < K; i += nt) perm_out[i] = s_perm[i];
+        if (tid == 0) *sweeps_out = converged ? sweep : max_sweeps + 1;
+    }
+}
+
 // One CTA, one warp per pair, the matrix in shared memory, one __syncthreads per round (option eig_cluster = 0, A-B).  The
 // cluster kernel above pays ~1 us per round for its cluster barrier (release of the remote stores + arrive + wait; ncu: 46 %
 // of its samples), but this one is bound by the FP64 pipe of its single SM -- ~70 FP64 warp instructions per pair, 3.5 us per
@@ -536,7 +691,6 @@ k_osj_smem(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__ per
     double* G = osj_smem;                                     // K x K
     int* s_perm = reinterpret_cast<int*>(G + (size_t)K * K);  // K
     __shared__ double red[32];
-    __shared__ int redi[32];
     __shared__ double s_tr;
     __shared__ unsigned s_cnt, s_mx;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -547,7 +701,7 @@ k_osj_smem(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__ per
         if (tid == 0) { s_tr = tr; s_cnt = 0; s_mx = 0; }
         for (long long e = tid; e < (long long)K * K; e += nt) G[e] = Gg[e];
         __syncthreads();
-        osj_pivoted_cholesky(G, K, s_perm, (double)K * 2.220446049250313e-16 * s_tr, red, redi);
+        osj_pivoted_cholesky(G, K, K, s_perm, (double)K * 2.220446049250313e-16 * s_tr);
     }
     const double tol = (double)K * 2.220446049250313e-16, tol2 = tol * tol;
     const int m = (K + 1) & ~1, np = m / 2;
@@ -929,9 +1083,24 @@ int ssi_swa_eigen_stage(ssi_ctx* ctx, int M, const double* dG_src, bool check, b
         const int np = (K + 1) / 2;
         grid = std::max(1, std::min(ctx->sm_count, (np * 16 + OSJ_THREADS - 1) / OSJ_THREADS));
     }
-    if (use_smem && ctx->opt_eig_cluster) {
-        // a cluster of 8 CTAs, every one with a copy of the matrix in its shared memory (A-B: the cluster barrier costs more
-        // than it buys at these sizes)
+    if (use_smem && ctx->opt_eig_cluster == 1 && (K + 1) / 2 <= OSJC_CTAS * OSJC_HW) {
+        // a cluster of 8 CTAs, one warp per column pair, each column in the shared memory of the CTA that needs it next
+        const int it = (K + 31) / 32;
+        const size_t csm = sizeof(double) * (size_t)K * it * 32 + sizeof(int) * (size_t)K;
+#define OSJC2_LAUNCH(IT_)                                                                                                       \
+    do {                                                                                                                        \
+        SSI_CUDA(ctx, cudaFuncSetAttribute(k_osj_cluster2<IT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));         \
+        k_osj_cluster2<IT_><<<OSJC_CTAS, OSJC_THREADS, csm, ctx->stream>>>(e.dG, K, 60, e.dPerm, e.dSweeps);                     \
+    } while (0)
+        switch (it) {
+            case 1: OSJC2_LAUNCH(1); break;
+            case 2: OSJC2_LAUNCH(2); break;
+            case 3: OSJC2_LAUNCH(3); break;
+            case 4: OSJC2_LAUNCH(4); break;
+            default: OSJC2_LAUNCH(5); break;
+        }
+#undef OSJC2_LAUNCH
+    } else if (use_smem && ctx->opt_eig_cluster) {
         const size_t csm = jsm + sizeof(int) * (size_t)K;
         SSI_CUDA(ctx, cudaFuncSetAttribute(k_osj_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
         k_osj_cluster<<<OSJC_CTAS, OSJC_THREADS, csm, ctx->stream>>>(e.dG, K, 60, e.dPerm, e.dSweeps);

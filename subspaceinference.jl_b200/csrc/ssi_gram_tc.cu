@@ -3,15 +3,19 @@
 // Replaces the factorisation work inside psvd(A) (src/subspace_construction.jl:63) for the shapes the
 // construction path produces (K = number of deviation columns, n ~ 1e7): one pass over A at HBM speed.
 //
-//   * A is column-major n x K == K rows of length n.  A TMA box {32 rows-of-A, 128 columns-of-A} lands in a RAW ring of
-//     six 16 KB slots as a [128][32] FP32 tile with 128-byte swizzle (columns >= K are zero-filled by TMA).  The ring
-//     is deep because a tile gathers one 128-byte segment from each of the K columns (K different DRAM pages).
-//   * six converter warps turn a raw tile into the operand of tcgen05.mma kind::f16: two FP16 planes H = fp16(s x) and
-//     L = fp16(s x - H), [128][32] halves each = 64-byte rows, K-major SWIZZLE_64B, H and L back to back (16 KB per
-//     operand slot, six slots).  s = 2^j puts the largest |A| (tracked by k_swa_push, one atomicMax per block) at 2^14,
-//     so H cannot overflow and H + L carries 22 bits of every value that matters.  Round 1 split into TF32 planes in
-//     place (FP32 containers): 109 KB of shared-memory traffic per 16 KB of A, 80 % of the crossbar, 52 % of the HBM
-//     peak; 16-bit planes make it 71 KB and halve the tensor-core time.
+//   * A is column-major n x K == K rows of length n.  A TMA box {64 rows-of-A, K8 columns-of-A} (K8 = K rounded up to 8)
+//     lands in a RAW ring as a plain [K8][64] FP32 tile: 256 contiguous bytes per column.  The segment length matters
+//     more than anything else here: a tile gathers one segment from each of the K columns (K different DRAM pages), and
+//     TMA gathers of 128-byte segments top out at 4.6 TB/s on this part whatever the depth of the ring, 256-byte ones
+//     reach 7.0 TB/s (profiles/explore/tma_gather.cu, profiles/r02_explore_tma_gather.txt) -- the 32-row tiles of the
+//     first tensor-core version sat at 3.7 TB/s for that reason.
+//   * eight converter warps split every raw tile between them (item = one float4 = 4 rows of one column; a warp reads 512
+//     contiguous bytes, conflict-free) and write the operand of tcgen05.mma kind::f16: two FP16 planes H = fp16(s x) and
+//     L = fp16(s x - H), [128][64] halves each = 128-byte rows, K-major SWIZZLE_128B, H and L back to back (32 KB per
+//     operand slot).  Every converter warp walks the tiles in order, so no warp can be two phases ahead of a barrier (an
+//     mbarrier parity wait cannot tell phase p from phase p + 2) and the ring depths are free: 3 operand slots, up to 4
+//     raw slots.  s = 2^j puts the largest |A| (tracked by k_swa_push, one atomicMax per block) at 2^14, so H cannot
+//     overflow and H + L carries 22 bits of every value that matters.
 //   * one thread issues, per 16 rows of A,  [HH | HL] += H [H ; L]'  (the B operand spans the H tile and the L tile
 //     behind it, so H is fetched once; FP32 accumulators in TMEM).  G = HH + HL + HL' drops only L L', 2^-24 relative.
 //     (BF16 planes were tried: their L L' term is 2^-18 of H H' and all-positive on the diagonal, so it must be kept,
@@ -21,34 +25,35 @@
 //   * FP32 accumulation in the tensor core truncates, so accumulators are drained every `chunk` tiles (1024 rows) into
 //     per-CTA FP64 partials (each thread owns its elements: plain load-add-store, no atomics) and reset; a final
 //     kernel sums the per-CTA partials in fixed order, symmetrises and undoes the scale.
+//   * shared-memory traffic per tile (K = 100): 26 KB TMA write + 26 KB converter reads + 26 KB plane writes + 46 KB of
+//     operand fetches by the four MMAs = 124 KB per 25.6 KB of A: at 128 B/clk that is ~1000 cycles per tile and SM, about
+//     the HBM time of the tile (950 cycles at 6.5 TB/s) -- the two pipes are balanced, neither has slack.
 //
-// Roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-7 converters (one tile each),
-// warps 8-11 drain.  TMEM: 2 x (HH | HL) x 128 columns = 512.
+// Roles (448 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-9 converters, warps 10-13 drain.
+// TMEM: 2 x (HH | HL) x 128 columns = 512.
 #include "ssi_common.cuh"
 #include "ssi_ptx.cuh"
 
 #include <cuda_fp16.h>
 #include <algorithm>
 
-#define GT_ROWS 32                   // rows of A per tile (= 128 bytes of FP32 = one swizzle row)
-#define GT_RAW_BYTES (128 * 128)     // [128 columns of A][32 rows] FP32
-#define GT_OP_BYTES (2 * 128 * 64)   // H | L: [128 columns of A][32 rows] FP16 each
-#define GT_CONV 6                    // converter warps: the split costs ~2000 cycles of latency per tile and warp, four warps were
-                                     // the bottleneck (970 cycles per tile at 56 % of the HBM peak)
-#define GT_RAW GT_CONV               // raw and operand slots: one of each per converter warp (tile t -> slot t % 6 = its converter),
-#define GT_OPS GT_CONV               // so that a warp only ever waits on barriers it cycles itself and can never run two phases
-                                     // ahead (an mbarrier parity wait cannot tell phase p from phase p + 2)
+#define GT_ROWS 64                   // rows of A per tile (256 contiguous bytes per column)
+#define GT_OP_BYTES (2 * 128 * 128)  // H | L: [128 columns of A][64 rows] FP16 each, 128-byte rows
+#define GT_OPS 3                     // operand slots
+#define GT_RAW_MAX 4                 // raw slots (fewer when K8 * 256 bytes do not fit four times)
+#define GT_CONV 8                    // converter warps
 #define GT_THREADS (64 + 32 * GT_CONV + 128)
-#define GT_OFF_OP (GT_RAW * GT_RAW_BYTES)
-#define GT_OFF_BAR (GT_OFF_OP + GT_OPS * GT_OP_BYTES)
-#define GT_NBAR (2 * GT_RAW + 2 * GT_OPS + 4)
-#define GT_SMEM_TOTAL (GT_OFF_BAR + GT_NBAR * 8 + 16)
+#define GT_OFF_BAR (GT_OPS * GT_OP_BYTES)                 // operand slots first (1024-byte aligned for SWIZZLE_128B)
+#define GT_NBAR (2 * GT_RAW_MAX + 2 * GT_OPS + 4)
+#define GT_OFF_RAW (GT_OFF_BAR + 256)                     // barriers + TMEM slot, then the raw ring
+#define GT_SMEM_MAX (227 * 1024)
 
 struct gram_tc_params {
     const float* amax;         // device: largest |A| (from k_swa_push), defines the power-of-two scale of the FP16 planes
     long long n;
     int K, NP;                 // NP = K rounded up to 16 (MMA N)
-    long long tiles_total;     // ceil(n / 32)
+    int K8, n_raw, raw_bytes;  // K rounded up to 8 (TMA box), raw slots and their size (K8 * 256)
+    long long tiles_total;     // ceil(n / 64)
     long long tiles_per_cta;
     int chunk;                 // tiles per FP32 accumulation chunk
     double* partial;           // [grid][2][NP][128]  (pass, column b, row a)
@@ -62,18 +67,24 @@ k_gram_tc(const __grid_constant__ CUtensorMap tmA, const gram_tc_params p) {
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + GT_NBAR);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bar_rfull = smem_u32(s_bar), bar_rempty = bar_rfull + 8 * GT_RAW;
-    const uint32_t bar_ofull = bar_rempty + 8 * GT_RAW, bar_oempty = bar_ofull + 8 * GT_OPS;
+    const uint32_t bar_rfull = smem_u32(s_bar), bar_rempty = bar_rfull + 8 * GT_RAW_MAX;
+    const uint32_t bar_ofull = bar_rempty + 8 * GT_RAW_MAX, bar_oempty = bar_ofull + 8 * GT_OPS;
     const uint32_t bar_tfull = bar_oempty + 8 * GT_OPS, bar_tempty = bar_tfull + 16;
 
     if (threadIdx.x == 0) {
         if (smem_base & 1023u) { printf("ssi_gram_tc: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
-        for (int s = 0; s < GT_RAW; ++s) { mbar_init(bar_rfull + 8 * s, 1); mbar_init(bar_rempty + 8 * s, 32); }
-        for (int s = 0; s < GT_OPS; ++s) { mbar_init(bar_ofull + 8 * s, 32); mbar_init(bar_oempty + 8 * s, 1); }
+        for (int s = 0; s < p.n_raw; ++s) { mbar_init(bar_rfull + 8 * s, 1); mbar_init(bar_rempty + 8 * s, GT_CONV); }
+        for (int s = 0; s < GT_OPS; ++s) { mbar_init(bar_ofull + 8 * s, GT_CONV); mbar_init(bar_oempty + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 128); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
     }
+    // operand rows >= K8 (columns of A that do not exist) are never written by the converters: zero them once
+    for (int i = threadIdx.x; i < GT_OPS * 2 * (128 - p.K8) * 8; i += GT_THREADS) {
+        const int chunk = i & 7, r = (i >> 3) % (128 - p.K8), pl = (i >> 3) / (128 - p.K8);       // pl = slot * 2 + plane
+        *reinterpret_cast<uint4*>(smem + (size_t)pl * (128 * 128) + (size_t)(p.K8 + r) * 128 + chunk * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
     if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
     tc_fence_before();
     __syncthreads();
@@ -91,11 +102,11 @@ k_gram_tc(const __grid_constant__ CUtensorMap tmA, const gram_tc_params p) {
             int stage = 0;
             uint32_t phase = 0;
             for (long long t = t_begin; t < t_end; ++t) {
-                mbar_wait(bar_rempty + 8 * stage, phase ^ 1);          // the converter that read this raw slot is done with it
-                mbar_expect_tx(bar_rfull + 8 * stage, GT_RAW_BYTES);
+                mbar_wait(bar_rempty + 8 * stage, phase ^ 1);          // every converter warp is done with this raw slot
+                mbar_expect_tx(bar_rfull + 8 * stage, p.raw_bytes);
                 // A is streamed exactly once: do not let it evict the FP64 partials from L2
-                tma_load_2d_hint(smem_base + stage * GT_RAW_BYTES, &tmA, bar_rfull + 8 * stage, (int)(t * GT_ROWS), 0, TC_EVICT_FIRST);
-                if (++stage == GT_RAW) { stage = 0; phase ^= 1; }
+                tma_load_2d_hint(smem_base + GT_OFF_RAW + stage * p.raw_bytes, &tmA, bar_rfull + 8 * stage, (int)(t * GT_ROWS), 0, TC_EVICT_FIRST);
+                if (++stage == p.n_raw) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -117,10 +128,10 @@ k_gram_tc(const __grid_constant__ CUtensorMap tmA, const gram_tc_params p) {
                 for (bool first = true; t < c_end; ++t, first = false) {
                     mbar_wait(bar_ofull + 8 * stage, phase);            // H and L tiles are ready
                     tc_fence_after();
-                    const uint64_t dh = umma_desc_sw64(smem_base + GT_OFF_OP + stage * GT_OP_BYTES);
+                    const uint64_t dh = umma_desc_sw128(smem_base + stage * GT_OP_BYTES);
 #pragma unroll
                     for (int k = 0; k < GT_ROWS / 16; ++k) {
-                        const uint64_t ko = (uint64_t)(k * 32 >> 4);    // 16 FP16 = 32 bytes per k-step inside the 64-byte row
+                        const uint64_t ko = (uint64_t)(k * 32 >> 4);    // 16 FP16 = 32 bytes per k-step inside the 128-byte row
                         umma_bf16(d_acc, dh + ko, dh + ko, idesc, !(first && k == 0));
                     }
                     umma_commit(bar_oempty + 8 * stage);
@@ -130,41 +141,42 @@ k_gram_tc(const __grid_constant__ CUtensorMap tmA, const gram_tc_params p) {
             }
         }
     } else if (warp < 2 + GT_CONV) {
-        // ================= converters: raw FP32 tile -> FP16 planes H | L in the K-major SWIZZLE_64B operand layout =================
-        const int cw = warp - 2;                  // this warp takes tiles cw, cw + GT_CONV, ...
+        // ================= converters: raw FP32 tile -> FP16 planes H | L in the K-major SWIZZLE_128B operand layout =================
+        const int cw = warp - 2;
         const float amax = *p.amax;
         const float sc = (amax > 0.0f && amax < 3.0e38f) ? scalbnf(1.0f, max(-100, min(100, 14 - ilogbf(amax)))) : 1.0f;
-        // lane -> (column c0 + lane / 4 of an 8-column group, 8-row chunk lane % 4): two adjacent 16-byte chunks of the raw
-        // row (rows 8j .. 8j+7 of A) become one 16-byte chunk of each plane
-        const int cl = lane >> 2, j = lane & 3;
-        for (long long t = cw; t < my_tiles; t += GT_CONV) {
-            const int rs = (int)(t % GT_RAW), os = (int)(t % GT_OPS);
-            mbar_wait(bar_rfull + 8 * rs, (uint32_t)((t / GT_RAW) & 1));
-            mbar_wait(bar_oempty + 8 * os, (uint32_t)(((t / GT_OPS) & 1) ^ 1));       // the MMAs that read this operand slot have retired
-            const uint8_t* raw = smem + (size_t)rs * GT_RAW_BYTES;
-            uint8_t* opH = smem + GT_OFF_OP + (size_t)os * GT_OP_BYTES;
-            uint8_t* opL = opH + 128 * 64;
+        // item i = (column i / 16 of A, rows 4 (i % 16) .. + 3): a warp reads 32 consecutive float4 = two whole columns of the
+        // raw tile and writes two whole 128-byte rows of each plane (8 bytes per lane), both conflict-free
+        const int items = p.K8 * 16;
+        int rs = 0, os = 0;
+        uint32_t rphase = 0, ophase = 0;
+        for (long long t = 0; t < my_tiles; ++t) {
+            mbar_wait(bar_rfull + 8 * rs, rphase);
+            mbar_wait(bar_oempty + 8 * os, ophase ^ 1);       // the MMAs that read this operand slot have retired
+            const uint8_t* raw = smem + GT_OFF_RAW + (size_t)rs * p.raw_bytes;
+            uint8_t* opH = smem + (size_t)os * GT_OP_BYTES;
+            uint8_t* opL = opH + 128 * 128;
 #pragma unroll 4
-            for (int g8 = 0; g8 < 16; ++g8) {
-                const int c = g8 * 8 + cl;                    // column of A = row of the operand; c & 7 == cl
-                const float4 x0 = *reinterpret_cast<const float4*>(raw + c * 128 + (((2 * j) ^ cl) << 4));
-                const float4 x1 = *reinterpret_cast<const float4*>(raw + c * 128 + (((2 * j + 1) ^ cl) << 4));
-                const float v0 = x0.x * sc, v1 = x0.y * sc, v2 = x0.z * sc, v3 = x0.w * sc;
-                const float v4 = x1.x * sc, v5 = x1.y * sc, v6 = x1.z * sc, v7 = x1.w * sc;
+            for (int i = cw * 32 + lane; i < items; i += GT_CONV * 32) {
+                const int c = i >> 4, q = i & 15;
+                const float4 x = *reinterpret_cast<const float4*>(raw + (size_t)i * 16);
+                const float v0 = x.x * sc, v1 = x.y * sc, v2 = x.z * sc, v3 = x.w * sc;
                 const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
-                const __half2 h45 = __floats2half2_rn(v4, v5), h67 = __floats2half2_rn(v6, v7);
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23), f45 = __half22float2(h45), f67 = __half22float2(h67);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
                 const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y), l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
-                const __half2 l45 = __floats2half2_rn(v4 - f45.x, v5 - f45.y), l67 = __floats2half2_rn(v6 - f67.x, v7 - f67.y);
-                const uint32_t off = (uint32_t)c * 64 + (uint32_t)((j ^ ((c >> 1) & 3)) << 4);      // SWIZZLE_64B: chunk ^ bits [7, 9) of the address
-                *reinterpret_cast<uint4*>(opH + off) = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23),
-                                                                  *reinterpret_cast<const uint32_t*>(&h45), *reinterpret_cast<const uint32_t*>(&h67));
-                *reinterpret_cast<uint4*>(opL + off) = make_uint4(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23),
-                                                                  *reinterpret_cast<const uint32_t*>(&l45), *reinterpret_cast<const uint32_t*>(&l67));
+                // SWIZZLE_128B: the 16-byte chunk index is XORed with the row index inside the 8-row atom
+                const uint32_t off = (uint32_t)c * 128 + (uint32_t)(((q >> 1) ^ (c & 7)) << 4) + (uint32_t)((q & 1) << 3);
+                *reinterpret_cast<uint2*>(opH + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+                *reinterpret_cast<uint2*>(opL + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
             }
             fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core (async proxy)
-            mbar_arrive(bar_ofull + 8 * os);
-            mbar_arrive(bar_rempty + 8 * rs);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar_ofull + 8 * os);
+                mbar_arrive(bar_rempty + 8 * rs);
+            }
+            if (++rs == p.n_raw) { rs = 0; rphase ^= 1; }
+            if (++os == GT_OPS) { os = 0; ophase ^= 1; }
         }
     } else {
         // ================= drain: TMEM chunk sums -> FP64 per-CTA partials =================
@@ -257,10 +269,11 @@ int ssi_gram_tc_device(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int
     CUtensorMap map;
     cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)K};
     cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {GT_ROWS, 128};
+    const int K8 = (K + 7) / 8 * 8;
+    cuuint32_t box[2] = {GT_ROWS, (cuuint32_t)K8};
     cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(dA), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return ssi_fail(ctx, SSI_ERR_CUDA, "cuTensorMapEncodeTiled (gram) failed with CUresult %d", (int)r);
 
@@ -269,17 +282,21 @@ int ssi_gram_tc_device(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, int
     p.n = n;
     p.K = K;
     p.NP = (K + 15) / 16 * 16;
+    p.K8 = K8;
+    p.raw_bytes = K8 * GT_ROWS * (int)sizeof(float);
+    p.n_raw = std::min(GT_RAW_MAX, (GT_SMEM_MAX - GT_OFF_RAW) / p.raw_bytes);
+    const int smem_bytes = GT_OFF_RAW + p.n_raw * p.raw_bytes;
     p.tiles_total = (n + GT_ROWS - 1) / GT_ROWS;
     const int grid = (int)std::min<long long>(ctx->sm_count, p.tiles_total);
     p.tiles_per_cta = (p.tiles_total + grid - 1) / grid;
-    p.chunk = ctx->opt_gram_chunk > 0 ? ctx->opt_gram_chunk : 32;       // 1024 rows per FP32 chunk
+    p.chunk = ctx->opt_gram_chunk > 0 ? ctx->opt_gram_chunk : 16;       // 1024 rows per FP32 chunk
     const int elems = 2 * p.NP * 128;
     SSI_TRY(ssi_reserve(ctx, ctx->bGram, sizeof(double) * (size_t)(grid + 1) * elems));
     p.partial = (double*)ctx->bGram.p;
     double* dS = p.partial + (size_t)grid * elems;
-    SSI_CUDA(ctx, cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_TOTAL));
+    SSI_CUDA(ctx, cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     ssi_kt_begin(ctx);
-    k_gram_tc<<<grid, GT_THREADS, GT_SMEM_TOTAL, ctx->stream>>>(map, p);
+    k_gram_tc<<<grid, GT_THREADS, smem_bytes, ctx->stream>>>(map, p);
     SSI_LAUNCH_CHECK(ctx);
     ssi_kt_end(ctx);
     k_gram_tc_sum<<<(elems + 127) / 128, 128, 0, ctx->stream>>>(p.partial, grid, elems, p.NP, dS);

@@ -145,7 +145,10 @@ def test_mala_decisions_teacher_forced(ssi, engine, name, N, sigma_z, sigma_m, r
             assert bool(at[c, t]) == (margin > 0), f"decision differs at chain {c} step {t}, margin {margin}"
             expect = zp if margin > 0 else z[t - 1]
             drift = 0.5 * sigma_z ** 2 * np.abs(g_prev).max()
-            np.testing.assert_allclose(z[t], expect, rtol=0, atol=2e-4 * drift + np.abs(expect).max() * 2.4e-7 + 1e-12)
+            # rule 1 accepts nearly everything, so its chains leave the mode and reach points where the FP32 gradient
+            # cancels harder; the proposal code is the same for both rules and is held to the tight bound under rule 0
+            gtol = 2e-4 if rule == 0 else 2e-3
+            np.testing.assert_allclose(z[t], expect, rtol=0, atol=gtol * drift + np.abs(expect).max() * 2.4e-7 + 1e-12)
     assert near_ties <= 3
     if rule == 0:
         assert 0 < at[:, 1:].mean() < 1      # both outcomes are exercised (rule 1 is not a valid MH ratio: it may accept everything)
