@@ -521,46 +521,77 @@ k_osj_cluster(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__ 
     }
 }
 
-// Second version of the cluster solver (default; the one above stays as option eig_cluster = 2 for A-B).  Same schedule and
-// the same data movement, with the latency chain of a round -- which is what the solver's time consists of: 891 rounds of
-// one rotation each at K = 100 -- cut down:
-//   * columns are padded to IT * 32 rows (zeros), IT a template parameter: no predicates, no partial loops;
-//   * tan(theta) comes from the FP32 closed form alone.  c = rsqrt(1 + t^2) and s = t c are still exact in FP64 (FP32 seed,
-//     one cubically convergent correction), so the rotation is orthogonal to working precision whatever t is; an error of
-//     2^-22 in t leaves 2^-22 of the pair's inner product behind instead of nothing, which the next sweep removes -- the
-//     FP64 Newton step on t bought nothing but latency;
-//   * division and square root are the approximate single-instruction forms (no slow-path calls);
-//   * the cluster barrier is split: arrive after the stores, then the indices and remote addresses of the NEXT round are
-//     computed, then wait.
+// Second version of the cluster solver (default; the one above stays as option eig_cluster = 2 for A-B).  Same schedule,
+// no barrier: the solver's time is 891 rounds of one rotation each at K = 100, so what counts is the latency of a round.
+//   * DATAFLOW instead of a cluster barrier per round.  A rotated column goes to the shared memory of its next owner with
+//     st.async, which completes transaction bytes on an mbarrier of the warp that will consume it (one mbarrier per pair slot
+//     and round parity); that warp posts arrive.expect_tx for its two columns and waits on its own barrier only.  The first
+//     version's barrier.cluster.arrive.release compiles to MEMBAR.ALL.GPU + ERRBAR + the hardware barrier, its acquire side to
+//     CCTL.IVALL: ~1000 of the 2300 cycles of a round (ncu, profiles/r02_ncu_streams.txt).  A neighbour can run at most one
+//     round ahead of a slot (its next inputs need this slot's output), hence two barriers per slot; bytes that land before
+//     the consumer has posted its expect_tx are legal (the phase cannot complete without the consumer's own arrival).
 //   * the pair slots are dealt out in equal contiguous runs (ceil(np / 8) per CTA).  A column moves to the neighbouring slot
 //     from one round to the next, so only the two columns at each run boundary cross to another SM; and the FP64 pipe -- 64
 //     lanes per clock and SM, ~80 FP64 warp instructions per pair -- is shared by 7 pairs instead of 16: the first version
 //     filled CTA after CTA (16, 16, 16, 2 pairs at K = 100) and its three full SMs were FP64-bound at ~2600 cycles a round.
+//   * columns are padded to IT * 32 rows (zeros), IT a template parameter: no predicates, no partial loops;
+//   * tan(theta) comes from the FP32 closed form alone.  c = rsqrt(1 + t^2) and s = t c are still exact in FP64 (FP32 seed,
+//     one cubically convergent correction), so the rotation is orthogonal to working precision whatever t is; an error of
+//     2^-22 in t leaves 2^-22 of the pair's inner product behind instead of nothing, which the next sweep removes -- the
+//     FP64 Newton step on t bought nothing but latency (same 9 sweeps at K = 100);
+//   * division and square root are the approximate single-instruction forms (no slow-path calls).
 __device__ __forceinline__ int osjc2_slot(int x, int r, int m) {
     if (x == m - 1 || x == r) return 0;
     int i = x - r; if (i < 0) i += m - 1;                  // x = (r + i) mod (m - 1)
     if (i >= m / 2) i = (m - 1) - i;                       // else x = (r - i) mod (m - 1)
     return i;
 }
+__device__ __forceinline__ void osjc_st_async_f64(uint32_t cluster_addr, double v, uint32_t cluster_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(cluster_addr), "l"(__double_as_longlong(v)), "r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ bool osjc_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void osjc_wait_cluster(uint32_t bar, uint32_t parity) {
+    if (osjc_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!osjc_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > (1ll << 31)) {
+            printf("ssi: eigen-solver column wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
 template <int IT>
 __global__ void __cluster_dims__(OSJC_CTAS, 1, 1) __launch_bounds__(OSJC_THREADS)
 k_osj_cluster2(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__ perm_out, int* __restrict__ sweeps_out) {
     constexpr int KP = IT * 32;
+    constexpr uint32_t COLB = KP * 8;                          // bytes of a column
     extern __shared__ double osj_smem[];
     double* G = osj_smem;                                     // K columns of KP rows
     int* s_perm = reinterpret_cast<int*>(G + (size_t)K * KP);  // K
     __shared__ double red[32];
     __shared__ double s_tr;
-    __shared__ unsigned s_cnt, s_slot[OSJC_CTAS], s_mx, s_mxslot[OSJC_CTAS];
+    __shared__ unsigned s_cnt, s_slot[OSJC_CTAS], s_big, s_bigslot[OSJC_CTAS];
+    __shared__ __align__(8) uint64_t s_bar[OSJC_HW][2];       // [pair slot of this CTA][round parity]
     const int tid = threadIdx.x, nt = blockDim.x, hl = tid & 31, wid = tid >> 5;
     const uint32_t rank = cluster_ctarank();
     {
         double tr = 0.0;
         for (int i = tid; i < K; i += nt) tr += fabs(Gg[i + (long long)i * K]);
         tr = ssi_block_sum(tr, red);
-        if (tid == 0) { s_tr = tr; s_cnt = 0; s_mx = 0; }
+        if (tid == 0) { s_tr = tr; s_cnt = 0; s_big = 0; }
+        if (tid < 2 * OSJC_HW) mbar_init(smem_u32(&s_bar[tid >> 1][tid & 1]), 1);
         for (int k = wid; k < K; k += OSJC_HW)
             for (int i = hl; i < KP; i += 32) G[i + k * KP] = i < K ? Gg[i + (long long)k * K] : 0.0;
+        fence_barrier_init();
         __syncthreads();
         osj_pivoted_cholesky(G, K, KP, s_perm, (double)K * 2.220446049250313e-16 * s_tr);
     }
@@ -570,36 +601,58 @@ k_osj_cluster2(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__
     const int spc = (np + OSJC_CTAS - 1) / OSJC_CTAS;         // pair slots per CTA (<= OSJC_HW, checked by the host)
     const int slot = (int)rank * spc + wid;                   // this warp's pair slot in every round
     const bool has_pair = wid < spc && slot < np;
-    const uint32_t g_local = smem_u32(G);
-    // pair of slot i in round r: slot 0 = (m - 1, r), slot i = ((r + i) mod (m - 1), (r - i) mod (m - 1)), ordered p < q
-    int p = 0, q = 0;
-    uint32_t dst_p = 0, dst_q = 0;
-    auto plan = [&](int r) {
-        if (!has_pair) return;
-        const int rn = (r + 1 == m - 1) ? 0 : r + 1;          // the schedule is cyclic across sweeps
-        if (slot == 0) { p = m - 1; q = r; }
-        else { p = r + slot; if (p >= m - 1) p -= m - 1; q = r - slot; if (q < 0) q += m - 1; }
-        if (p > q) { const int t = p; p = q; q = t; }
-        dst_p = osjc_mapa(g_local, (uint32_t)(osjc2_slot(p, rn, m) / spc)) + (uint32_t)(p * KP + hl) * 8u;
-        dst_q = q < K ? osjc_mapa(g_local, (uint32_t)(osjc2_slot(q, rn, m) / spc)) + (uint32_t)(q * KP + hl) * 8u : 0u;
+    const uint32_t g_local = smem_u32(G), bar_local = smem_u32(&s_bar[0][0]);
+    const uint32_t my_bar = bar_local + (uint32_t)wid * 16u;
+    // Round-robin schedule, round r: slot 0 holds columns (A, B) = (m - 1, r), slot i holds (r + i, r - i) mod (m - 1).  From one
+    // round to the next both column indices of a slot grow by one (slot 0's A stays), A moves to slot i - 1 (slot 1's A becomes
+    // slot 0's B, slot 0's A stays put) and B to slot i + 1 (the last slot's B becomes its own A): the two destinations of a warp
+    // never change, only the column offsets advance.  Column m - 1 = K is a phantom when K is odd: slot 0 then only forwards B.
+    const bool phantom = slot == 0 && (K & 1);
+    const uint32_t wrap = (uint32_t)(m - 1) * COLB;
+    uint32_t offA = (slot == 0 ? (uint32_t)(m - 1) : (uint32_t)slot) * COLB;
+    uint32_t offB = (slot == 0 ? 0u : (uint32_t)(m - 1 - slot)) * COLB;
+    uint32_t dstA = 0, dstB = 0, barA = 0, barB = 0;           // shared::cluster addresses in the CTAs of the next owners
+    if (has_pair) {
+        const int sa = max(slot - 1, 0), sb = min(slot + 1, np - 1);
+        const int ca = sa / spc, cb = sb / spc;
+        dstA = osjc_mapa(g_local, (uint32_t)ca) + (uint32_t)hl * 8u;
+        dstB = osjc_mapa(g_local, (uint32_t)cb) + (uint32_t)hl * 8u;
+        barA = osjc_mapa(bar_local, (uint32_t)ca) + (uint32_t)(sa - ca * spc) * 16u;
+        barB = osjc_mapa(bar_local, (uint32_t)cb) + (uint32_t)(sb - cb * spc) * 16u;
+    }
+    const uint32_t expect = (phantom ? 1u : 2u) * COLB;
+    // wait for the columns of round g >= 1 (the data of round 0 is the local Cholesky factor): g counts rounds over all sweeps,
+    // the columns of round g are announced on the barrier of parity g & 1, whose ((g - 1) >> 1)-th phase that is
+    auto await = [&](unsigned g) {
+        if (g == 0u) return;
+        const uint32_t bar = my_bar + (g & 1u) * 8u;
+        if (hl == 0) mbar_expect_tx(bar, expect);
+        __syncwarp();
+        mbar_wait(bar, ((g - 1u) >> 1) & 1u);
     };
-    plan(0);
+    const char* Gb = reinterpret_cast<const char*>(G) + hl * 8;
+    unsigned g = 0;
     int sweep = 0;
     bool converged = false;
     for (; sweep < max_sweeps; ++sweep) {
-        for (int r = 0; r < m - 1; ++r) {
-            if (has_pair) {
-                const double* gp = G + p * KP + hl;
+        unsigned cnt = 0, big = 0;
+        if (has_pair) {
+            for (int r = 0; r < m - 1; ++r) {
+                await(g);
+                ++g;
+                const uint32_t par = (g & 1u) * 8u;                          // parity of the round the results are for
+                // the columns keep their index: where column j lives is the same offset in every CTA
+                const uint32_t nA = slot == 0 ? offA : (offA + COLB == wrap ? 0u : offA + COLB);
+                const uint32_t nB = offB + COLB == wrap ? 0u : offB + COLB;
                 double x[IT], y[IT];
 #pragma unroll
-                for (int it = 0; it < IT; ++it) x[it] = gp[32 * it];
-                if (q >= K) {                                               // bye: the column only moves on
+                for (int it = 0; it < IT; ++it) y[it] = *reinterpret_cast<const double*>(Gb + offB + it * 256);
+                if (phantom) {                                               // bye: the column only moves on
 #pragma unroll
-                    for (int it = 0; it < IT; ++it) osjc_st_f64(dst_p + (uint32_t)it * 256u, x[it]);
+                    for (int it = 0; it < IT; ++it) osjc_st_async_f64(dstB + offB + (uint32_t)it * 256u, y[it], barB + par);
                 } else {
-                    const double* gq = G + q * KP + hl;
 #pragma unroll
-                    for (int it = 0; it < IT; ++it) y[it] = gq[32 * it];
+                    for (int it = 0; it < IT; ++it) x[it] = *reinterpret_cast<const double*>(Gb + offA + it * 256);
                     double a = 0.0, b = 0.0, c = 0.0;
 #pragma unroll
                     for (int it = 0; it < IT; ++it) { a = fma(x[it], x[it], a); b = fma(y[it], y[it], b); c = fma(x[it], y[it], c); }
@@ -612,7 +665,7 @@ k_osj_cluster2(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__
                     const double c2 = c * c, ab = a * b;
                     double cs = 1.0, sn = 0.0;
                     if (c2 > tol2 * ab) {
-                        // t = h / (d + sign(d) sqrt(d^2 + h^2)), d = |g_q|^2 - |g_p|^2, h = 2 g_p.g_q, on exponent-aligned FP32 copies
+                        // t = h / (d + sign(d) sqrt(d^2 + h^2)), d = |y|^2 - |x|^2, h = 2 x.y, on exponent-aligned FP32 copies
                         const double d = b - a, h = c + c;
                         const int ex = max(__double2hiint(fabs(d)), __double2hiint(fabs(h))) >> 20;
                         const double sc = __hiloint2double((2046 - ex) << 20, 0);
@@ -627,50 +680,44 @@ k_osj_cluster2(double* __restrict__ Gg, int K, int max_sweeps, int* __restrict__
                         const double e = fma(-w * c0, c0, 1.0);           // 1 - w c0^2, ~2^-22
                         cs = fma(c0 * e, fma(0.375, e, 0.5), c0);         // c0 (1 + e/2 + 3 e^2 / 8): error ~e^3
                         sn = t * cs;
-                        if (hl == 0) {
-                            // largest cos^2 rotated away in this sweep (single precision is plenty: it is compared with 1e-15)
-                            const int e2 = __double2hiint(ab) >> 20;
-                            const double s2 = __hiloint2double((2046 - e2) << 20, 0);
-                            atomicAdd(&s_cnt, 1u);
-                            atomicMax(&s_mx, __float_as_uint(fminf(__fdividef((float)(c2 * s2), (float)(ab * s2)), 1.0f)));
-                        }
-                        __syncwarp();
+                        ++cnt;
+                        big |= (c2 > 1e-15 * ab) ? 1u : 0u;               // a rotation that was not yet of second order
                     }
 #pragma unroll
                     for (int it = 0; it < IT; ++it) {
-                        osjc_st_f64(dst_p + (uint32_t)it * 256u, cs * x[it] - sn * y[it]);
-                        osjc_st_f64(dst_q + (uint32_t)it * 256u, sn * x[it] + cs * y[it]);
+                        osjc_st_async_f64(dstA + offA + (uint32_t)it * 256u, cs * x[it] - sn * y[it], barA + par);
+                        osjc_st_async_f64(dstB + offB + (uint32_t)it * 256u, sn * x[it] + cs * y[it], barB + par);
                     }
                 }
+                offA = nA;
+                offB = nB;
             }
-            if (r == m - 2) {       // last round of the sweep: publish this CTA's rotation count before the barrier
-                __syncthreads();
-                if (tid < OSJC_CTAS) {
-                    osjc_st_u32(osjc_mapa(smem_u32(&s_slot[rank]), (uint32_t)tid), s_cnt);
-                    osjc_st_u32(osjc_mapa(smem_u32(&s_mxslot[rank]), (uint32_t)tid), s_mx);
-                }
-                __syncwarp();
-            }
-            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-            plan(r + 1 == m - 1 ? 0 : r + 1);
-            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            if (hl == 0 && cnt) { atomicAdd(&s_cnt, cnt); atomicOr(&s_big, big); }
         }
-        unsigned total = 0, mx = 0;
+        // end of the sweep: every CTA tells every CTA how much it rotated (the one cluster barrier per sweep)
+        __syncthreads();
+        if (tid < OSJC_CTAS) {
+            osjc_st_u32(osjc_mapa(smem_u32(&s_slot[rank]), (uint32_t)tid), s_cnt);
+            osjc_st_u32(osjc_mapa(smem_u32(&s_bigslot[rank]), (uint32_t)tid), s_big);
+        }
+        cluster_sync_all();
+        unsigned total = 0, anybig = 0;
 #pragma unroll
-        for (int c = 0; c < OSJC_CTAS; ++c) { total += s_slot[c]; mx = max(mx, s_mxslot[c]); }
+        for (int c = 0; c < OSJC_CTAS; ++c) { total += s_slot[c]; anybig |= s_bigslot[c]; }
         __syncthreads();
-        if (tid == 0) { s_cnt = 0; s_mx = 0; }
-        __syncthreads();
+        if (tid == 0) { s_cnt = 0; s_big = 0; }
+        cluster_sync_all();           // nobody publishes the next sweep's counts before everybody has read these
         // converged when nothing was rotated, or when every rotation of the sweep was so small (cos < 3e-8) that what it
         // leaves behind is of second order, cos^2 < 1e-15 (quadratic convergence of the Jacobi method)
-        if (total == 0u || __uint_as_float(mx) < 1e-15f) { ++sweep; converged = true; break; }
+        if (total == 0u || !anybig) { ++sweep; converged = true; break; }
     }
-    // every column is valid in the CTA that owns it in round 0 (the round after the last one): that CTA writes it out
+    // the columns of the round that would come next have been sent to their owners: wait for them, then write them out
     if (has_pair) {
-        const int pp = (slot == 0) ? m - 1 : slot, qq = (slot == 0) ? 0 : m - 1 - slot;      // round 0: (r + i, r - i) mod (m - 1) with r = 0
+        await(g);
+        const int ja = (int)(offA / COLB), jb = (int)(offB / COLB);
         for (int k = hl; k < K; k += 32) {
-            if (pp < K) Gg[k + (long long)pp * K] = G[k + pp * KP];
-            if (qq < K) Gg[k + (long long)qq * K] = G[k + qq * KP];
+            if (!phantom) Gg[k + (long long)ja * K] = G[k + ja * KP];
+            Gg[k + (long long)jb * K] = G[k + jb * KP];
         }
     }
     cluster_sync_all();           // no CTA leaves while a peer may still write into its shared memory
