@@ -264,11 +264,22 @@ __device__ void osj_pivoted_cholesky(double* __restrict__ G, int K, int ld, int*
         double* cj = G + (long long)j * ld;
         for (int i = j + tid; i < K; i += nt) cj[i] = (i == j) ? ljj : cj[i] * inv;
         __syncthreads();
-        // trailing update, both triangles: G[i, k] -= L[i, j] L[k, j] for i, k > j
-        for (int k = j + 1 + warp; k < K; k += nw) {
-            const double lk = cj[k];
-            double* ck = G + (long long)k * ld;
-            for (int i = j + 1 + lane; i < K; i += 32) ck[i] = fma(-cj[i], lk, ck[i]);
+        // trailing update, both triangles: G[i, k] -= L[i, j] L[k, j] for i, k > j.  A lane keeps its four entries of column j
+        // in registers while the warp walks its columns k: four independent load / fma / store chains per step
+        for (int i0 = j + 1 + lane; i0 < K; i0 += 128) {
+            double ci[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ci[u] = (i0 + 32 * u < K) ? cj[i0 + 32 * u] : 0.0;
+            for (int k = j + 1 + warp; k < K; k += nw) {
+                const double lk = -cj[k];
+                double* ck = G + (long long)k * ld + i0;
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = (i0 + 32 * u < K) ? ck[32 * u] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + 32 * u < K) ck[32 * u] = fma(ci[u], lk, v[u]);
+            }
         }
         __syncthreads();
     }
