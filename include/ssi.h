@@ -96,6 +96,7 @@ typedef struct ssi_stats_t {
     double finish_p_ms;        /* P = A V_M (K8)                                                            */
     int64_t tc_range_fallbacks;/* tensor path: evaluations repeated on BF16 planes because an activation left the   */
                                /* calibrated range of the FP16 planes; 0 in normal operation   */
+    int64_t gemm_tc_launches;  /* gradient / training GEMMs this context ran on the tensor cores (ssi_gemm_tc.cu)     */
 } ssi_stats_t;
 
 int  ssi_version(void);

@@ -182,7 +182,7 @@ int ssi_ctx_destroy(ssi_ctx* ctx) {
     cudaFree(ctx->dX); cudaFree(ctx->dY); cudaFree(ctx->dP); cudaFree(ctx->dSubGram);
     cudaFree(ctx->dSwaMean); cudaFree(ctx->dDev); cudaFree(ctx->dSwaAmax);
     ssi_buf_t* bufs[] = {&ctx->bZ, &ctx->bLp, &ctx->bTerms, &ctx->bPartials, &ctx->bW, &ctx->bH0, &ctx->bH1, &ctx->bGram,
-                         &ctx->bEig, &ctx->bMisc, &ctx->bDecZ, &ctx->bDecT, &ctx->bGradW, &ctx->bGradP, &ctx->bMhZ, &ctx->bMhZp, &ctx->bMhLp, &ctx->bMhLpP, &ctx->bMhCnt, &ctx->bMhG, &ctx->bSnap};
+                         &ctx->bEig, &ctx->bMisc, &ctx->bDecZ, &ctx->bDecT, &ctx->bGradW, &ctx->bGradP, &ctx->bRowsum, &ctx->bGemmAmax, &ctx->bMhZ, &ctx->bMhZp, &ctx->bMhLp, &ctx->bMhLpP, &ctx->bMhCnt, &ctx->bMhG, &ctx->bSnap};
     for (ssi_buf_t* b : bufs) free_buf(*b);
     for (cudaEvent_t e : ctx->kt_events) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev0);
@@ -272,6 +272,11 @@ int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
     // MALA acceptance rule: 0 (default) = the Metropolis-adjusted Langevin ratio as documented; 1 = both proposal densities
     // evaluated with the NEGATED gradient, q(a | b) = N(a - b; -(sigma^2/2) grad(a), sigma^2) -- how AdvancedMH's MALA step is
     // remembered to be written (`spl.proposal(-t_cond.gradient)`); the pinned 0.6.2 source is not available to decide
+    if (!strcmp(key, "grad_group_gb")) { ctx->opt_grad_group_gb = (int)value; return SSI_OK; }
+    if (!strcmp(key, "gemm_tc_mask")) { ctx->opt_gemm_tc_mask = (int)value; return SSI_OK; }
+    if (!strcmp(key, "gemm_prec")) { ctx->opt_gemm_prec = (int)value; return SSI_OK; }
+    if (!strcmp(key, "gemm_simt")) { ctx->opt_gemm_simt = value != 0; return SSI_OK; }
+    if (!strcmp(key, "gemm_chunk")) { ctx->opt_gemm_chunk = (int)value; return SSI_OK; }
     if (!strcmp(key, "mala_rule")) { if (value != 0 && value != 1) return ssi_fail(ctx, SSI_ERR_ARG, "mala_rule must be 0 or 1"); ctx->opt_mala_rule = (int)value; return SSI_OK; }
     if (!strcmp(key, "tc_pair")) { ctx->opt_tc_pair = value != 0; return SSI_OK; }
     if (!strcmp(key, "tc_precision")) { ctx->opt_tc_prec = value != 0; ssi_tc_invalidate(ctx); return SSI_OK; }

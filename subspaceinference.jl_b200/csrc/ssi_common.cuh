@@ -62,6 +62,11 @@ struct ssi_ctx {
     int opt_tc_k32 = 0;       // A-B: K-major bases always 32 columns wide
     int opt_tc_alast = 1;     // evict-first hint on the last read of a row block's activations (A-B: 0)
     int opt_tc_nokrev = 0;    // A-B: every feature tile reads the k-blocks in ascending order
+    int opt_grad_group_gb = 0; // scratch budget (GB) of the generic gradient path per group of samples (default 6)
+    int opt_gemm_tc_mask = 0; // 0 all; else which GEMM orientations may use the tensor cores (see ssi_gemm_tc.cu)
+    int opt_gemm_prec = 1;    // tensor-core GEMM planes: 1 FP16 with a per-operand scale (FP32-grade), 0 BF16 (no pre-pass)
+    int opt_gemm_simt = 0;    // 1: keep the gradient / training GEMMs on the SIMT kernel (A-B against ssi_gemm_tc.cu)
+    int opt_gemm_chunk = 0;   // k-blocks (32 k) per FP32 accumulation chunk of the tensor-core GEMM (default 32)
     int opt_mala_rule = 0;    // 0 textbook MALA ratio, 1 negated-gradient proposal densities (see ssi_api.cu)
     int opt_tc_pair = 1;      // GEMM layers with per-sample activations as CTA pairs (cta_group::2); 0: one CTA per tile (A-B)
     int opt_tc_prec = 1;      // operand planes of the tensor path: 1 mixed BF16/FP16 (default), 0 BF16x3 (round 1)
@@ -95,6 +100,8 @@ struct ssi_ctx {
 
     // scratch
     ssi_buf_t bZ, bLp, bTerms, bPartials, bW, bH0, bH1, bGram, bEig, bMisc, bGradW, bGradP;
+    ssi_buf_t bGemmAmax;      // per-batch operand magnitudes of the tensor-core GEMM in flight (ssi_gemm_tc.cu)
+    ssi_buf_t bRowsum;        // per-slice partials of the bias gradients (ssi_grad.cu)
 
     // MH state
     ssi_buf_t bMhZ, bMhZp, bMhLp, bMhLpP, bMhCnt, bMhG;
@@ -207,7 +214,7 @@ int ssi_multi_set_decoder(ssi_ctx* ctx, const float* W_swa, int n_layers, const 
 // log-posterior of B device-resident subspace points; d_lp (B) and optional d_terms (3 x B)
 int ssi_logpost_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sigma_m, double sigma_p,
                        double sigma_z, uint32_t mask, double* d_lp, double* d_terms);
-int ssi_project_device(ssi_ctx* ctx, const float* dZ, int64_t B, float* dW /* n x B */);
+int ssi_project_device(ssi_ctx* ctx, const float* dZ, int64_t B, float* dW /* ldw x B */, int64_t ldw = 0 /* 0: n */);
 int ssi_logpost_finalize(ssi_ctx* ctx, const double* d_sse, const float* dZ, int64_t B, double sigma_m, double sigma_p,
                          double sigma_z, uint32_t mask, double* d_lp, double* d_terms);
 // value and gradient (M x B doubles) of the log-posterior of B device-resident subspace points (ssi_grad.cu)

@@ -89,7 +89,12 @@ k_gemm_simt(const gemm_t p) {
     }
 }
 
+int ssi_gemm_tc_try(ssi_ctx* ctx, const gemm_t& g, int batches, bool a_kfast, bool b_jfast, bool* used);
+
 int ssi_launch_gemm(ssi_ctx* ctx, const gemm_t& g, int batches, bool a_kfast, bool b_jfast) {
+    bool on_tensor_cores = false;
+    SSI_TRY(ssi_gemm_tc_try(ctx, g, batches, a_kfast, b_jfast, &on_tensor_cores));
+    if (on_tensor_cores) return SSI_OK;
     dim3 grid((g.J + GT_T - 1) / GT_T, (g.O + GT_T - 1) / GT_T, batches);
     if (grid.y > 65535 || grid.z > 65535) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "gradient path: shape too large for one launch");
     if (a_kfast && b_jfast) k_gemm_simt<true, true><<<grid, 256, 0, ctx->stream>>>(g);
@@ -123,17 +128,56 @@ k_grad_delta_out(const float* __restrict__ pred, long long pred_sb, const float*
     if (threadIdx.x == 0) partials[g * n_chunks + blockIdx.x] = tot;
 }
 
-// gb(o) = sum_j delta(o, j): one warp per (sample, o), fixed order
+// gb(o) = sum_j delta(o, j), fixed order.  delta is (O x N) with o fast: a warp takes 32 consecutive o (one coalesced
+// 128-byte row per datapoint), the 8 warps of a block take every 8th datapoint of the block's slice of N; the per-block
+// partials are summed in order by the second kernel.  (The first version gave a warp one o and let it stride through N:
+// 32 sectors per load, 1.2 ms per 1024 x 60000 layer and sample.)
+#define RS_SLICES 64
 __global__ void __launch_bounds__(256)
-k_grad_rowsum(const float* __restrict__ delta, long long d_sb, int O, long long N, float* __restrict__ out, long long out_sb) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int o = blockIdx.x * 8 + warp;
+k_grad_rowsum_part(const float* __restrict__ delta, long long d_sb, int O, long long N, float* __restrict__ part /* [g][RS_SLICES][O] */) {
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int o = blockIdx.x * 32 + lane;
+    const int slice = blockIdx.y;
+    const long long g = blockIdx.z;
+    const long long per = (N + RS_SLICES - 1) / RS_SLICES;
+    const long long j0 = slice * per, j1 = min(N, j0 + per);
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    if (o < O) {
+        const float* d = delta + g * d_sb + o;
+        long long j = j0 + warp;
+        for (; j + 24 < j1; j += 32) {
+            s0 += d[j * O]; s1 += d[(j + 8) * O]; s2 += d[(j + 16) * O]; s3 += d[(j + 24) * O];
+        }
+        for (; j < j1; j += 8) s0 += d[j * O];
+    }
+    red[warp][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (warp == 0 && o < O) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][lane];
+        part[(g * RS_SLICES + slice) * O + o] = t;
+    }
+}
+__global__ void k_grad_rowsum_fin(const float* __restrict__ part, int O, float* __restrict__ out, long long out_sb) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
     const long long g = blockIdx.y;
     if (o >= O) return;
-    float s = 0.0f;
-    for (long long j = lane; j < N; j += 32) s += delta[g * d_sb + o + j * O];
-    s = ssi_warp_sum(s);
-    if (lane == 0) out[g * out_sb + o] = s;
+    float t = 0.0f;
+    for (int s = 0; s < RS_SLICES; ++s) t += part[(g * RS_SLICES + s) * O + o];
+    out[g * out_sb + o] = t;
+}
+static int launch_rowsum(ssi_ctx* ctx, const float* delta, long long d_sb, int O, long long N, int g, float* out, long long out_sb) {
+    SSI_TRY(ssi_reserve(ctx, ctx->bRowsum, sizeof(float) * (size_t)g * RS_SLICES * O));
+    float* part = (float*)ctx->bRowsum.p;
+    dim3 grid((O + 31) / 32, RS_SLICES, g);
+    k_grad_rowsum_part<<<grid, 256, 0, ctx->stream>>>(delta, d_sb, O, N, part);
+    SSI_LAUNCH_CHECK(ctx);
+    dim3 g2((O + 127) / 128, g);
+    k_grad_rowsum_fin<<<g2, 128, 0, ctx->stream>>>(part, O, out, out_sb);
+    SSI_LAUNCH_CHECK(ctx);
+    return SSI_OK;
 }
 
 int ssi_launch_delta_out(ssi_ctx* ctx, const float* pred, long long pred_sb, const float* Y, float* delta, long long delta_sb,
@@ -144,10 +188,7 @@ int ssi_launch_delta_out(ssi_ctx* ctx, const float* pred, long long pred_sb, con
     return SSI_OK;
 }
 int ssi_launch_rowsum(ssi_ctx* ctx, const float* delta, long long d_sb, int O, long long N, int g, float* out, long long out_sb) {
-    dim3 rg((O + 7) / 8, g);
-    k_grad_rowsum<<<rg, 256, 0, ctx->stream>>>(delta, d_sb, O, N, out, out_sb);
-    SSI_LAUNCH_CHECK(ctx);
-    return SSI_OK;
+    return launch_rowsum(ctx, delta, d_sb, O, N, g, out, out_sb);
 }
 
 // grad_z(m, g) = sum_s part[s][m + g*M]  (+ prior terms), fixed order
@@ -218,41 +259,55 @@ int ssi_logpost_grad_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sig
     long long h_off[SSI_MAX_LAYERS + 1];
     h_off[0] = 0;
     for (int l = 1; l <= L; ++l) { h_off[l] = act_elems; act_elems += (long long)m.dims[l] * N; maxw = std::max(maxw, m.dims[l]); }
-    const double per_sample = 4.0 * (2.0 * n + (double)act_elems + 2.0 * maxw * (double)N);
-    int G = (int)std::max(1.0, std::min(64.0, 6e9 / per_sample));
+    // sample strides are padded to 16 bytes so that the tensor-core GEMM (TMA) can address every sample's slice
+    const long long np = (n + 3) & ~3ll;
+    act_elems = (act_elems + 3) & ~3ll;
+    const double per_sample = 4.0 * (2.0 * np + (double)act_elems + 2.0 * maxw * (double)N);
+    // samples per group: the tensor-core GEMMs want many tiles per launch (the weight gradient of a 1024 x 1024 layer is only
+    // 32 tiles per sample against 148 SMs), so take what a third of the free memory holds, 64 samples at most
+    double budget = 6e9;
+    if (ctx->opt_grad_group_gb > 0) budget = ctx->opt_grad_group_gb * 1e9;
+    else {
+        size_t mem_free = 0, mem_total = 0;
+        if (cudaMemGetInfo(&mem_free, &mem_total) == cudaSuccess) {
+            const double held = (double)ctx->bW.cap + (double)ctx->bGradW.cap + (double)ctx->bH0.cap + (double)ctx->bH1.cap;
+            budget = std::max(budget, ((double)mem_free + held) / 3.0);
+        }
+    }
+    int G = (int)std::max(1.0, std::min(64.0, budget / per_sample));
     G = (int)std::min<int64_t>(G, B);
     const long long split = 4096;                       // rows of P per partial of the final projection
     const int S = (int)((n + split - 1) / split);
     const int n_chunks = (int)((N + 255) / 256);
-    SSI_TRY(ssi_reserve(ctx, ctx->bW, sizeof(float) * (size_t)n * G));
-    SSI_TRY(ssi_reserve(ctx, ctx->bGradW, sizeof(float) * (size_t)n * G));
+    SSI_TRY(ssi_reserve(ctx, ctx->bW, sizeof(float) * (size_t)np * G));
+    SSI_TRY(ssi_reserve(ctx, ctx->bGradW, sizeof(float) * (size_t)np * G));
     SSI_TRY(ssi_reserve(ctx, ctx->bH0, sizeof(float) * (size_t)act_elems * G));
-    SSI_TRY(ssi_reserve(ctx, ctx->bH1, sizeof(float) * (size_t)2 * maxw * N * G));
+    SSI_TRY(ssi_reserve(ctx, ctx->bH1, sizeof(float) * (size_t)2 * (((long long)maxw * N + 3) & ~3ll) * G));
     SSI_TRY(ssi_reserve(ctx, ctx->bPartials, sizeof(double) * (size_t)B * n_chunks));
     SSI_TRY(ssi_reserve(ctx, ctx->bGradP, sizeof(float) * (size_t)S * M * G));
     SSI_TRY(ssi_reserve(ctx, ctx->bMisc, sizeof(double) * (size_t)B));
     float* dW = (float*)ctx->bW.p;
     float* gW = (float*)ctx->bGradW.p;
     float* H = (float*)ctx->bH0.p;                      // [g][act_elems]
-    float* D[2] = {(float*)ctx->bH1.p, (float*)ctx->bH1.p + (size_t)maxw * N * G};   // [g][maxw x N] each
+    float* D[2] = {(float*)ctx->bH1.p, (float*)ctx->bH1.p + (size_t)(((long long)maxw * N + 3) & ~3ll) * G};   // [g][maxw x N] each
     double* partials = (double*)ctx->bPartials.p;
     float* gpart = (float*)ctx->bGradP.p;
     double* d_sse = (double*)ctx->bMisc.p;
-    const long long d_sb = (long long)maxw * N;
+    const long long d_sb = ((long long)maxw * N + 3) & ~3ll;
     const float coef = (mask & SSI_TERM_LL) ? (float)(1.0 / (sigma_m * sigma_m)) : 0.0f;
 
     for (int64_t b0 = 0; b0 < B; b0 += G) {
         const int g = (int)std::min<int64_t>(G, B - b0);
-        SSI_TRY(ssi_project_device(ctx, dZ + b0 * M, g, dW));
+        SSI_TRY(ssi_project_device(ctx, dZ + b0 * M, g, dW, np));
         // ---- forward, every activation kept ----
         for (int l = 0; l < L; ++l) {
             const int in = m.dims[l], out = m.dims[l + 1];
             gemm_t q{};
-            q.A = dW + m.w_off[l]; q.a_so = 1; q.a_sk = out; q.a_sb = n;
+            q.A = dW + m.w_off[l]; q.a_so = 1; q.a_sk = out; q.a_sb = np;
             q.B = l == 0 ? ctx->dX : H + h_off[l]; q.b_sk = 1; q.b_sj = in; q.b_sb = l == 0 ? 0 : act_elems;
             q.C = H + h_off[l + 1]; q.c_so = 1; q.c_sj = out; q.c_sb = act_elems;
             q.O = out; q.J = (int)N; q.K = in; q.split = 0;
-            q.epi = 1; q.act = m.act[l]; q.bias = dW + m.b_off[l]; q.bias_sb = n;
+            q.epi = 1; q.act = m.act[l]; q.bias = dW + m.b_off[l]; q.bias_sb = np;
             SSI_TRY(ssi_launch_gemm(ctx, q, g, false, false));
         }
         // ---- output delta + squared error ----
@@ -270,16 +325,14 @@ int ssi_logpost_grad_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sig
             gemm_t q{};
             q.A = delta; q.a_so = 1; q.a_sk = out; q.a_sb = d_sb;
             q.B = l == 0 ? ctx->dX : H + h_off[l]; q.b_sk = in; q.b_sj = 1; q.b_sb = l == 0 ? 0 : act_elems;
-            q.C = gW + m.w_off[l]; q.c_so = 1; q.c_sj = out; q.c_sb = n;
+            q.C = gW + m.w_off[l]; q.c_so = 1; q.c_sj = out; q.c_sb = np;
             q.O = out; q.J = in; q.K = N; q.split = 0; q.epi = 0;
             SSI_TRY(ssi_launch_gemm(ctx, q, g, false, true));
-            dim3 rg((out + 7) / 8, g);
-            k_grad_rowsum<<<rg, 256, 0, ctx->stream>>>(delta, d_sb, out, N, gW + m.b_off[l], n);
-            SSI_LAUNCH_CHECK(ctx);
+            SSI_TRY(launch_rowsum(ctx, delta, d_sb, out, N, g, gW + m.b_off[l], np));
             if (l > 0) {
                 // delta_{l-1}(i, j) = sum_o W_l(o, i) delta_l(o, j) * act_{l-1}'(H_{l-1}(i, j))
                 gemm_t r{};
-                r.A = dW + m.w_off[l]; r.a_so = out; r.a_sk = 1; r.a_sb = n;
+                r.A = dW + m.w_off[l]; r.a_so = out; r.a_sk = 1; r.a_sb = np;
                 r.B = delta; r.b_sk = 1; r.b_sj = out; r.b_sb = d_sb;
                 r.C = D[l & 1]; r.c_so = 1; r.c_sj = in; r.c_sb = d_sb;
                 r.O = in; r.J = (int)N; r.K = out; r.split = 0;
@@ -291,7 +344,7 @@ int ssi_logpost_grad_device(ssi_ctx* ctx, const float* dZ, int64_t B, double sig
         {
             gemm_t q{};
             q.A = ctx->dP; q.a_so = n; q.a_sk = 1; q.a_sb = 0;
-            q.B = gW; q.b_sk = 1; q.b_sj = n; q.b_sb = 0;
+            q.B = gW; q.b_sk = 1; q.b_sj = np; q.b_sb = 0;
             q.C = gpart; q.c_so = 1; q.c_sj = M; q.c_sb = (long long)M * g;
             q.O = M; q.J = g; q.K = n; q.split = split; q.epi = 0;
             SSI_TRY(ssi_launch_gemm(ctx, q, S, true, false));

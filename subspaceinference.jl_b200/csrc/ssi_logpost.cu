@@ -285,8 +285,8 @@ __global__ void k_finalize(const finalize_args_t a, const double* __restrict__ s
 // With a decoder whose head is not affine (ssi_decoder.cu): W = Wbase + act(W_swa' + P z), W_swa' being the head's bias.
 __global__ void __launch_bounds__(256)
 k_project(const float* __restrict__ Wswa, const float* __restrict__ P, const float* __restrict__ Z,
-          long long n, int M, int G, float* __restrict__ W /* G x n (sample-major) or n x G col-major: same */,
-          const float* __restrict__ Wbase, int act) {
+          long long n, int M, int G, float* __restrict__ W /* G x ldw (sample-major) or ldw x G col-major: same */,
+          const float* __restrict__ Wbase, int act, long long ldw) {
     extern __shared__ float zs[];   // M x G
     for (int e = threadIdx.x; e < M * G; e += blockDim.x) zs[e] = Z[e];
     __syncthreads();
@@ -300,18 +300,19 @@ k_project(const float* __restrict__ Wswa, const float* __restrict__ P, const flo
     for (int g = 0; g < G; ++g) {
         float v = w0;
         for (int m = 0; m < M; ++m) v = fmaf(p[m], zs[m + g * M], v);
-        W[i + (long long)g * n] = Wbase ? wb + ssi_act(v, act) : v;
+        W[i + (long long)g * ldw] = Wbase ? wb + ssi_act(v, act) : v;
     }
 }
 
-int ssi_project_device(ssi_ctx* ctx, const float* dZ, int64_t B, float* dW) {
+int ssi_project_device(ssi_ctx* ctx, const float* dZ, int64_t B, float* dW, int64_t ldw) {
     const int64_t n = ctx->model.n;
+    if (ldw <= 0) ldw = n;
     const int M = ctx->M;
     const int gmax = std::max(1, (int)(32768 / (sizeof(float) * M)));
     for (int64_t b0 = 0; b0 < B; b0 += gmax) {
         const int G = (int)std::min<int64_t>(gmax, B - b0);
         k_project<<<(unsigned)((n + 255) / 256), 256, sizeof(float) * M * G, ctx->stream>>>(
-            ctx->dWswa, ctx->dP, dZ + b0 * M, n, M, G, dW + b0 * n, ctx->dWbase, ctx->dec_out_act);
+            ctx->dWswa, ctx->dP, dZ + b0 * M, n, M, G, dW + b0 * ldw, ctx->dWbase, ctx->dec_out_act, ldw);
         SSI_LAUNCH_CHECK(ctx);
     }
     return SSI_OK;

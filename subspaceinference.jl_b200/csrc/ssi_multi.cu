@@ -122,6 +122,7 @@ int ssi_multi_stats(const ssi_ctx* ctx, ssi_stats_t* out) {
             acc.mh_proposals += s.mh_proposals;
             acc.dominant_ms = std::max(acc.dominant_ms, s.dominant_ms);
             acc.dominant_launches += s.dominant_launches;
+            acc.gemm_tc_launches += s.gemm_tc_launches;
         }
     }
     *out = acc;

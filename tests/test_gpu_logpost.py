@@ -163,6 +163,7 @@ def test_error_behaviour(ssi):
     ((3, 1), (0,), 1, 1, 3),                          # single layer, single datapoint
     ((33, 65, 17, 9, 4), (1, 2, 1, 0), 257, 6, 4),    # deeper chain
     ((96, 128, 128, 10), (1, 1, 0), 300, 20, 3),      # wide-ish chain: several tiles per GEMM, split projection
+    ((96, 256, 192, 8), (1, 2, 0), 3000, 12, 3),      # big enough for the tensor-core GEMM: ragged tiles, 3 accumulation chunks
 ])
 def test_gradient_vs_oracle(ssi, engine, dims, acts, N, M, B):
     """l_pi_grad (src/space_inference.jl:107) batched: value within 1e-5 relative, gradient within 1e-4 of its norm
@@ -190,6 +191,17 @@ def test_gradient_vs_oracle(ssi, engine, dims, acts, N, M, B):
         engine.set_option("path", ssi.PATH_AUTO)
         np.testing.assert_allclose(lp_f, lp_g, rtol=2e-6)
         np.testing.assert_allclose(g_f, g_g, rtol=0, atol=2e-4 * np.abs(g_g).max())
+    if dims == (96, 256, 192, 8):
+        # the large contractions ran on the tensor cores (ssi_gemm_tc.cu) and agree with the SIMT kernel
+        assert engine.stats().gemm_tc_launches > 0
+        lp_t, g_t = engine.logpost_grad(Z, 0.7, 1.3, 0.9, mask=1)
+        before = engine.stats().gemm_tc_launches
+        engine.set_option("gemm_simt", 1)
+        lp_s, g_s = engine.logpost_grad(Z, 0.7, 1.3, 0.9, mask=1)
+        assert engine.stats().gemm_tc_launches == before
+        engine.set_option("gemm_simt", 0)
+        np.testing.assert_allclose(lp_t, lp_s, rtol=2e-6)
+        np.testing.assert_allclose(g_t, g_s, rtol=0, atol=5e-5 * np.linalg.norm(g_s, axis=0).max())
     # a sample's gradient does not depend on the rest of the batch
     lp_a, g_a = engine.logpost_grad(Z[:, :2], 0.7, 1.3, 0.9, mask=7)
     lp_b, g_b = engine.logpost_grad(Z, 0.7, 1.3, 0.9, mask=7)
