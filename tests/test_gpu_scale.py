@@ -108,6 +108,41 @@ def test_tensor_path_mh_decisions_full_c3(ssi, engine):
     assert dec >= 16 and flips_fp32 == 0 and rel < 1e-6
 
 
+def test_gradient_wide_on_tensor_cores(ssi, engine):
+    """l_pi_grad (src/space_inference.jl:107) on the wide network at N = 6000: the reverse pass runs its large
+    contractions on the tensor cores (ssi_gemm_tc.cu, FP16 planes with per-sample scales) and must match the Float64
+    oracle to the bar of the generic gradient test (1e-4 of the gradient norm; the FP32 CUDA-core pass is at 1.8e-5 here, the
+    tensor-core pass at 3.7e-5: its FP32 accumulation truncates where an FMA chain rounds); the value it returns is the
+    density's value."""
+    prob = orc.make_problem("wide", N=6000)
+    _setup(engine, prob)
+    rng = np.random.default_rng(11)
+    B, sigma_m = 3, 0.5
+    Z = (2e-2 * rng.standard_normal((prob.M, B))).astype(np.float32)
+    before = engine.stats().gemm_tc_launches
+    lp, g = engine.logpost_grad(Z, sigma_m)
+    assert engine.stats().gemm_tc_launches - before >= 5          # 2 forward layers, 2 weight gradients, 1 back-propagated delta
+    engine.set_option("gemm_simt", 1)
+    lp_s, g_s = engine.logpost_grad(Z, sigma_m)
+    engine.set_option("gemm_simt", 0)
+    lp_d = engine.logpost(Z, sigma_m)
+    worst = worst_s = 0.0
+    for b in range(B):
+        lp_ref, g_ref = orc.density_and_grad(prob, Z[:, b].astype(np.float64), sigma_m)
+        nrm = np.linalg.norm(g_ref)
+        worst = max(worst, np.linalg.norm(g[:, b] - g_ref) / nrm)
+        worst_s = max(worst_s, np.linalg.norm(g_s[:, b] - g_ref) / nrm)
+        assert abs(lp[b] - lp_ref) <= 1e-6 * abs(lp_ref)
+    print(f"wide N=6000 gradient: tensor cores {worst:.2e}, CUDA cores {worst_s:.2e} of the gradient norm; "
+          f"lp vs density call {np.max(np.abs(lp - lp_d) / np.abs(lp_d)):.1e}")
+    assert worst < 1e-4 and worst < 4 * worst_s
+    np.testing.assert_allclose(lp, lp_d, rtol=1e-6)
+    # a sample's gradient does not depend on what else is in the batch (per-sample scales)
+    lp1, g1 = engine.logpost_grad(Z[:, 1:2], sigma_m)
+    np.testing.assert_array_equal(g1[:, 0], g[:, 1])
+    assert lp1[0] == lp[1]
+
+
 def test_readme_literal_batchsize1_K1000(ssi):
     """BASELINE configs[0] as literally configured (README.md:59,74-79): DataLoader(X, Y, shuffle=true) is batchsize 1,
     so T = 10, c = 1 collect K = 1000 deviation columns for n = 682 parameters; opt = ADAM(0.1), M = 3."""
