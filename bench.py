@@ -52,8 +52,10 @@ WORKLOADS = {
     "uci-mala": ("uci", 4096, 0.1, 0.01),
     # configs[4] per GPU: 8192 of the 65536 chains in the M=20 subspace of the wide MLP, samples and log-probs gathered with NCCL
     "wide-mh": ("wide", 8192, 1.0, 0.02),
+    # MALA on the wide MLP: value + gradient per step, the reverse pass on the tensor-core GEMM (ssi_gemm_tc.cu)
+    "wide-mala": ("wide", 512, 1.0, 0.02),
 }
-MH_STEPS_BY_WORKLOAD = {"wide-mh": 2}      # a wide MH step is 8192 x 60000 units (~3 s): two per bench step
+MH_STEPS_BY_WORKLOAD = {"wide-mh": 2, "wide-mala": 2}      # a wide MH step is 8192 x 60000 units (~3 s): two per bench step
 MH_STEPS = 100
 
 

@@ -118,10 +118,15 @@ const char* ssi_last_error(const ssi_ctx* ctx);
 int  ssi_set_stream(ssi_ctx* ctx, void* cuda_stream);
 int  ssi_sync(ssi_ctx* ctx);
 /* keys: "path" (SSI_PATH_*), "group" (samples per wave on the tensor path), "tc_precision" (operand planes of the tensor
- * path: 1 = mixed BF16/FP16 planes, the default; 0 = BF16x3), and A/B switches used by the tests: "tc_nobasis", "tc_nofuse",
- * "tc_noorder", "tc_simt_basis", "tc_nokrev", "tc_alast", "tc_k32", "tc_pair" (1 = CTA pairs with cta_group::2, the default),
- * "b1_simt", "bm_nopack", "bm_variant", "gram_fp64", "gram_chunk", "eig_cluster", "formp_simt" (see DESIGN.md); "time_dominant" (0/1) brackets every launch of the path's dominant kernel with CUDA events
- * (ssi_stats_t.dominant_ms) */
+ * path: 1 = FP16 planes with power-of-two scales, the default; 0 = BF16x3), "mala_rule" (0 = the documented Metropolis-adjusted
+ * Langevin ratio, the default; 1 = both proposal densities evaluated with the negated gradient, see ssi_mala_run),
+ * "grad_group_gb" (scratch budget of the generic gradient path per group of samples; default a third of the free memory),
+ * and A/B switches used by the tests: "tc_nobasis", "tc_nofuse", "tc_noorder", "tc_simt_basis", "tc_nokrev", "tc_alast",
+ * "tc_k32", "tc_pair" (1 = CTA pairs with cta_group::2, the default), "b1_simt", "bm_nopack", "bm_variant", "gram_fp64",
+ * "gram_chunk", "eig_cluster" (1 = dataflow cluster solver, default; 2 = cluster solver with a barrier per round; 0 = one
+ * CTA), "formp_simt", "gemm_simt" (1 = gradient / training GEMMs on the SIMT kernel), "gemm_prec" (tensor-core GEMM planes:
+ * 1 = FP16 with per-sample scales, default; 0 = BF16), "gemm_chunk", "gemm_tc_mask" (see DESIGN.md); "time_dominant" (0/1)
+ * brackets every launch of the path's dominant kernel with CUDA events (ssi_stats_t.dominant_ms) */
 int  ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value);
 int  ssi_stats(const ssi_ctx* ctx, ssi_stats_t* out);
 
@@ -186,7 +191,10 @@ int  ssi_mh_run_dev(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t se
  * sigma_z*eps(chain,0), the reference's init_params); step t proposes z' = z + (sigma_z^2/2) grad lp(z) + sigma_z*eps(chain,t)
  * and accepts iff -e(chain,t) < lp' - lp + log q(z|z') - log q(z'|z) with q(a|b) = N(a; b + (sigma_z^2/2) grad lp(b),
  * sigma_z^2 I) (the Metropolis-adjusted Langevin step as AdvancedMH documents it; the pinned 0.6.2 source is not
- * vendored).  Values and gradients come from ssi_logpost_grad_batch_dev.                              */
+ * vendored).  Option "mala_rule" = 1 evaluates both densities with the NEGATED gradient,
+ * q(a|b) = N(a - b; -(sigma_z^2/2) grad lp(b), sigma_z^2 I) -- how that release's step is remembered to be written
+ * (`proposal(-gradient)`); neither can be pinned without the source, both are held to the oracle's restatement.
+ * Values and gradients come from ssi_logpost_grad_batch_dev.                                                         */
 int  ssi_mala_run(ssi_ctx* ctx, int64_t n_chains, int64_t n_steps, uint64_t seed, int64_t chain_offset,
                   double sigma_z, double sigma_m, double sigma_p, uint32_t prior_mask,
                   const float* z0_or_null,
