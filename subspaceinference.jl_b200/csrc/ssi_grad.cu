@@ -89,12 +89,234 @@ k_gemm_simt(const gemm_t p) {
     }
 }
 
+// ---- skinny shapes: the output layer of a regression / classification head has O <= 16 rows, which neither the 64x64 SIMT
+// tile nor the 128-row tensor-core tile fits (and a leading dimension of 10 floats is not TMA-addressable).  Three
+// memory-bound kernels, one per orientation the reverse pass produces; all sums in a fixed order.
+#define SK_MAXO 16
+// (1) forward, O <= 16: C(o, j) = epi(sum_k A(o, k) B(k, j)), A o-fast (W_L), B k-fast (H_{L-1}).  A warp takes four datapoints j
+// at a time, lanes over k (coalesced), A transposed into shared memory as [o][K]: one shared-memory read of A serves four
+// datapoints (with one it was the shared-memory pipe, not HBM, that set the pace).
+template <int OO>
+__global__ void __launch_bounds__(256)
+k_gemm_skinny_fwd(const gemm_t p, int J_per_block) {
+    extern __shared__ float sk_As[];          // [OO][K]
+    const long long b = blockIdx.y;
+    const int K = (int)p.K;
+    const float* A = p.A + b * p.a_sb;
+    for (int e = threadIdx.x; e < p.O * K; e += blockDim.x) {
+        const int o = e % p.O, k = e / p.O;
+        sk_As[o * K + k] = A[o + (long long)k * p.a_sk];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* Bm = p.B + b * p.b_sb;
+    const int j_begin = blockIdx.x * J_per_block, j_end = min(p.J, j_begin + J_per_block);
+    for (int j0 = j_begin + 4 * warp; j0 < j_end; j0 += 32) {
+        const float* col[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) col[c] = Bm + (long long)min(j0 + c, j_end - 1) * p.b_sj;
+        float acc[4][OO];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int o = 0; o < OO; ++o) acc[c][o] = 0.0f;
+        // four k-steps (sixteen independent loads) in flight per lane: the loop is bound by DRAM latency otherwise
+        for (int k = lane; k < K; k += 128) {
+            float h[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) h[u][c] = (k + 32 * u < K) ? col[c][k + 32 * u] : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (k + 32 * u < K) {
+#pragma unroll
+                    for (int o = 0; o < OO; ++o)
+                        if (o < p.O) {
+                            const float w = sk_As[o * K + k + 32 * u];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) acc[c][o] = fmaf(w, h[u][c], acc[c][o]);
+                        }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int o = 0; o < OO; ++o) {
+                if (o < p.O) {                       // warp-uniform
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) acc[c][o] += __shfl_xor_sync(0xffffffffu, acc[c][o], d);
+                }
+            }
+        if (lane < 4 && j0 + lane < j_end) {
+            const int j = j0 + lane;
+#pragma unroll
+            for (int o = 0; o < OO; ++o)
+                if (o < p.O) {
+                    float v = lane == 0 ? acc[0][o] : lane == 1 ? acc[1][o] : lane == 2 ? acc[2][o] : acc[3][o];
+                    const long long ci = o + (long long)j * p.c_sj;
+                    if (p.epi == 1) v = ssi_act(v + p.bias[b * p.bias_sb + o], p.act);
+                    else if (p.epi == 2) v *= act_deriv_from_output(p.Hprev[b * p.h_sb + ci], p.act);
+                    p.C[b * p.c_sb + ci] = v;
+                }
+        }
+    }
+}
+// (2) back-propagated delta through the head, K <= 16: C(o, j) = epi(sum_k A(o, k) B(k, j)), A k-fast (W_L read as (i, o)),
+// B k-fast (delta_L).  A thread per o (coalesced along o), its row of A in registers; the block's slice of B sits in shared
+// memory, padded to KK per datapoint, and is read with broadcast 16-byte loads.
+template <int KK>
+__global__ void __launch_bounds__(256)
+k_gemm_skinny_k(const gemm_t p, int J_per_block) {
+    extern __shared__ __align__(16) float sk_Bs[];     // [J_per_block][KK]
+    const long long b = blockIdx.z;
+    const int o = blockIdx.x * 256 + threadIdx.x;
+    const int K = (int)p.K;
+    const float* Bm = p.B + b * p.b_sb;
+    const int j_begin = blockIdx.y * J_per_block, j_end = min(p.J, j_begin + J_per_block);
+    for (int e = threadIdx.x; e < (j_end - j_begin) * KK; e += 256) {
+        const int k = e % KK, jj = e / KK;
+        sk_Bs[e] = k < K ? Bm[(long long)(j_begin + jj) * p.b_sj + k] : 0.0f;
+    }
+    float a[KK];
+#pragma unroll
+    for (int k = 0; k < KK; ++k) a[k] = (o < p.O && k < K) ? p.A[b * p.a_sb + (long long)o * p.a_so + k] : 0.0f;
+    __syncthreads();
+    if (o >= p.O) return;
+    // eight datapoints per pass, the layer outputs they need requested before the first use
+    for (int j0 = j_begin; j0 < j_end; j0 += 8) {
+        float hp[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            hp[u] = (p.epi == 2 && j0 + u < j_end) ? p.Hprev[b * p.h_sb + o + (long long)(j0 + u) * p.c_sj] : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u;
+            if (j < j_end) {
+                const float4* col = reinterpret_cast<const float4*>(sk_Bs + (j - j_begin) * KK);
+                float v = 0.0f;
+#pragma unroll
+                for (int k4 = 0; k4 < KK / 4; ++k4) {
+                    const float4 d = col[k4];
+                    v = fmaf(a[4 * k4], d.x, v); v = fmaf(a[4 * k4 + 1], d.y, v); v = fmaf(a[4 * k4 + 2], d.z, v); v = fmaf(a[4 * k4 + 3], d.w, v);
+                }
+                if (p.epi == 1) v = ssi_act(v + p.bias[b * p.bias_sb + o], p.act);
+                else if (p.epi == 2) v *= act_deriv_from_output(hp[u], p.act);
+                p.C[b * p.c_sb + o + (long long)j * p.c_sj] = v;
+            }
+        }
+    }
+}
+// (3) weight gradient of the head, O <= 16 and a long contraction: C(o, j) = sum_k A(o, k) B(k, j), A o-fast (delta_L), B j-fast
+// (H_{L-1}).  A thread per j (coalesced along j), O accumulators; A is staged through shared memory 64 k at a time (padded
+// to OO per k, broadcast 16-byte loads); the contraction is cut into SK_SLICES slices whose partials the second kernel adds
+// in order.
+#define SK_SLICES 32
+#define SK_KC 64
+template <int OO>
+__global__ void __launch_bounds__(256)
+k_gemm_skinny_gw(const gemm_t p, float* __restrict__ part /* [batch][slice][O][J] */) {
+    __shared__ __align__(16) float As[SK_KC * OO];
+    const long long b = blockIdx.z;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    const int slice = blockIdx.y;
+    const long long per = (p.K + SK_SLICES - 1) / SK_SLICES;
+    const long long k0 = slice * per, k1 = min(p.K, k0 + per);
+    const float* A = p.A + b * p.a_sb;
+    const float* Bm = p.B + b * p.b_sb + min(j, p.J - 1);
+    float acc[OO];
+#pragma unroll
+    for (int o = 0; o < OO; ++o) acc[o] = 0.0f;
+    for (long long kc = k0; kc < k1; kc += SK_KC) {
+        const int nk = (int)min((long long)SK_KC, k1 - kc);
+        __syncthreads();
+        for (int e = threadIdx.x; e < SK_KC * OO; e += 256) {
+            const int o = e % OO, kk = e / OO;
+            As[e] = (o < p.O && kk < nk) ? A[(kc + kk) * p.a_sk + o] : 0.0f;
+        }
+        __syncthreads();
+        for (int kk = 0; kk < nk; kk += 8) {
+            float h[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) h[u] = (kk + u < nk) ? Bm[(kc + kk + u) * p.b_sk] : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float4* d4 = reinterpret_cast<const float4*>(As + (kk + u) * OO);      // rows past nk are zero
+#pragma unroll
+                for (int o4 = 0; o4 < OO / 4; ++o4) {
+                    const float4 d = d4[o4];
+                    acc[4 * o4] = fmaf(d.x, h[u], acc[4 * o4]); acc[4 * o4 + 1] = fmaf(d.y, h[u], acc[4 * o4 + 1]);
+                    acc[4 * o4 + 2] = fmaf(d.z, h[u], acc[4 * o4 + 2]); acc[4 * o4 + 3] = fmaf(d.w, h[u], acc[4 * o4 + 3]);
+                }
+            }
+        }
+    }
+    if (j >= p.J) return;
+    float* dst = part + ((b * SK_SLICES + slice) * p.O) * (long long)p.J + j;
+#pragma unroll
+    for (int o = 0; o < OO; ++o)
+        if (o < p.O) dst[(long long)o * p.J] = acc[o];
+}
+__global__ void k_gemm_skinny_gw_fin(const gemm_t p, const float* __restrict__ part) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = blockIdx.y;
+    const long long b = blockIdx.z;
+    if (j >= p.J) return;
+    float t = 0.0f;
+    for (int s = 0; s < SK_SLICES; ++s) t += part[((b * SK_SLICES + s) * p.O + o) * (long long)p.J + j];
+    p.C[b * p.c_sb + o + (long long)j * p.c_sj] = t;
+}
+
+// Takes g when it is one of the three skinny shapes (*used = true).
+static int gemm_skinny_try(ssi_ctx* ctx, const gemm_t& g, int batches, bool a_kfast, bool b_jfast, bool* used) {
+    *used = false;
+    if (ctx->opt_gemm_simt || g.split > 0 || g.c_so != 1 || batches < 1 || batches > 65535) return SSI_OK;
+    if (g.K >= (1ll << 31) || (double)g.O * g.J * (double)g.K * batches < 4e6) return SSI_OK;
+    if (!a_kfast && !b_jfast && g.a_so == 1 && g.b_sk == 1 && g.O <= SK_MAXO && g.J >= 1024 && (size_t)g.O * g.K * 4 <= 160 * 1024) {
+        const int jpb = 256;
+        dim3 grid((g.J + jpb - 1) / jpb, batches);
+        const size_t sm = sizeof(float) * (size_t)g.O * g.K;
+        if (g.O <= 4) {
+            if (sm > 48 * 1024) SSI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_skinny_fwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_gemm_skinny_fwd<4><<<grid, 256, sm, ctx->stream>>>(g, jpb);
+        } else {
+            if (sm > 48 * 1024) SSI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_skinny_fwd<SK_MAXO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_gemm_skinny_fwd<SK_MAXO><<<grid, 256, sm, ctx->stream>>>(g, jpb);
+        }
+        SSI_LAUNCH_CHECK(ctx);
+        *used = true;
+    } else if (a_kfast && !b_jfast && g.a_sk == 1 && g.b_sk == 1 && g.K <= SK_MAXO && g.O >= 64 && g.J >= 64) {
+        const int jpb = 64;
+        dim3 grid((g.O + 255) / 256, (g.J + jpb - 1) / jpb, batches);
+        if (grid.y > 65535) return SSI_OK;
+        if (g.K <= 4) k_gemm_skinny_k<4><<<grid, 256, sizeof(float) * jpb * 4, ctx->stream>>>(g, jpb);
+        else k_gemm_skinny_k<SK_MAXO><<<grid, 256, sizeof(float) * jpb * SK_MAXO, ctx->stream>>>(g, jpb);
+        SSI_LAUNCH_CHECK(ctx);
+        *used = true;
+    } else if (!a_kfast && b_jfast && g.a_so == 1 && g.b_sj == 1 && g.O <= SK_MAXO && g.J >= 64 && g.K >= 1024) {
+        SSI_TRY(ssi_reserve(ctx, ctx->bSkinny, sizeof(float) * (size_t)batches * SK_SLICES * g.O * g.J));
+        float* part = (float*)ctx->bSkinny.p;
+        dim3 grid((g.J + 255) / 256, SK_SLICES, batches);
+        if (g.O <= 4) k_gemm_skinny_gw<4><<<grid, 256, 0, ctx->stream>>>(g, part);
+        else k_gemm_skinny_gw<SK_MAXO><<<grid, 256, 0, ctx->stream>>>(g, part);
+        SSI_LAUNCH_CHECK(ctx);
+        dim3 g2((g.J + 255) / 256, g.O, batches);
+        k_gemm_skinny_gw_fin<<<g2, 256, 0, ctx->stream>>>(g, part);
+        SSI_LAUNCH_CHECK(ctx);
+        *used = true;
+    }
+    return SSI_OK;
+}
+
 int ssi_gemm_tc_try(ssi_ctx* ctx, const gemm_t& g, int batches, bool a_kfast, bool b_jfast, bool* used);
 
 int ssi_launch_gemm(ssi_ctx* ctx, const gemm_t& g, int batches, bool a_kfast, bool b_jfast) {
-    bool on_tensor_cores = false;
-    SSI_TRY(ssi_gemm_tc_try(ctx, g, batches, a_kfast, b_jfast, &on_tensor_cores));
-    if (on_tensor_cores) return SSI_OK;
+    bool taken = false;
+    SSI_TRY(gemm_skinny_try(ctx, g, batches, a_kfast, b_jfast, &taken));
+    if (taken) return SSI_OK;
+    SSI_TRY(ssi_gemm_tc_try(ctx, g, batches, a_kfast, b_jfast, &taken));
+    if (taken) return SSI_OK;
     dim3 grid((g.J + GT_T - 1) / GT_T, (g.O + GT_T - 1) / GT_T, batches);
     if (grid.y > 65535 || grid.z > 65535) return ssi_fail(ctx, SSI_ERR_UNSUPPORTED, "gradient path: shape too large for one launch");
     if (a_kfast && b_jfast) k_gemm_simt<true, true><<<grid, 256, 0, ctx->stream>>>(g);
