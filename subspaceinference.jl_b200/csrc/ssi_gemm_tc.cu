@@ -67,14 +67,23 @@ struct gemm_tc_params {
     const float* Hprev; long long h_sb;
 };
 
+// tanh / sigmoid out of line: the epilogue is unrolled 32 wide, and their inline expansions alone were several thousand
+// instructions of a kernel whose other warps stall on instruction fetch
+__device__ __noinline__ float gx_act_slow(float v, int act) { return ssi_act(v, act); }
+__device__ __forceinline__ float gx_act(float v, int act) {
+    if (act == SSI_ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == SSI_ACT_TANH || act == SSI_ACT_SIGMOID) return gx_act_slow(v, act);
+    return v;
+}
 // power-of-two scale that puts mx in [2^14, 2^15)
 __device__ __forceinline__ int gx_scale_exp(float mx) {
     return (mx > 0.0f && mx < 3.0e38f) ? max(-100, min(100, 14 - ilogbf(mx))) : 0;
 }
 // eight consecutive k of one row -> one 16-byte chunk of each plane
-__device__ __forceinline__ void gx_split8(const float v[8], uint4& hi, uint4& lo, bool fp16, float sc) {
+template <bool F16>
+__device__ __forceinline__ void gx_split8(const float v[8], uint4& hi, uint4& lo, float sc) {
     uint32_t h[4], l[4];
-    if (fp16) {
+    if (F16) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float a = v[2 * i] * sc, b = v[2 * i + 1] * sc;
@@ -101,14 +110,13 @@ __device__ __forceinline__ void gx_split8(const float v[8], uint4& hi, uint4& lo
 }
 
 // raw FP32 tile (ROWS x 32 k) -> planes H, L ([ROWS][32] BF16, 64-byte rows, SWIZZLE_64B); ct = converter thread 0..255
-template <int ROWS>
-__device__ __forceinline__ void gx_convert(const uint8_t* __restrict__ raw, uint8_t* __restrict__ H, uint8_t* __restrict__ L, int kfast, int ct,
-                                           bool fp16, float sc) {
+template <int ROWS, bool KFAST, bool F16>
+__device__ __forceinline__ void gx_convert(const uint8_t* __restrict__ raw, uint8_t* __restrict__ H, uint8_t* __restrict__ L, int ct, float sc) {
 #pragma unroll 2
     for (int i = ct; i < ROWS * 4; i += GX_CONV * 32) {
         int r, q;
         float v[8];
-        if (kfast) {
+        if (KFAST) {
             // [ROWS][32 k], 128-byte rows, TMA SWIZZLE_128B (16-byte chunk ^ row % 8): a quarter warp reads two whole rows
             r = i >> 2; q = i & 3;
             const float4 x0 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * q) ^ (r & 7)) << 4));
@@ -122,13 +130,15 @@ __device__ __forceinline__ void gx_convert(const uint8_t* __restrict__ raw, uint
             for (int e = 0; e < 8; ++e) v[e] = src[e * ROWS];
         }
         uint4 hi, lo;
-        gx_split8(v, hi, lo, fp16, sc);
+        gx_split8<F16>(v, hi, lo, sc);
         const uint32_t off = (uint32_t)r * 64u + (uint32_t)((q ^ ((r >> 1) & 3)) << 4);      // SWIZZLE_64B: chunk ^ bits [7, 9) of the address
         *reinterpret_cast<uint4*>(H + off) = hi;
         *reinterpret_cast<uint4*>(L + off) = lo;
     }
 }
 
+// AK / BK: the raw tiles of A / B are k-fast; F16: FP16 planes with per-batch scales (else BF16 planes)
+template <bool AK, bool BK, bool F16>
 __global__ void __launch_bounds__(GX_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const gemm_tc_params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -174,9 +184,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint32_t full = bar_rfull + 8 * stage;
                     mbar_expect_tx(full, GX_RAW_STAGE);
                     const uint32_t dA = smem_base + stage * GX_RAW_STAGE, dB = dA + GX_RAW_A;
-                    if (p.a_kfast) tma_load_3d(dA, &tmA, full, kb * GX_BK, to * GX_BM, ab);
+                    if (AK) tma_load_3d(dA, &tmA, full, kb * GX_BK, to * GX_BM, ab);
                     else tma_load_3d(dA, &tmA, full, to * GX_BM, kb * GX_BK, ab);
-                    if (p.b_kfast) tma_load_3d(dB, &tmB, full, kb * GX_BK, tj * GX_BN, bb);
+                    if (BK) tma_load_3d(dB, &tmB, full, kb * GX_BK, tj * GX_BN, bb);
                     else tma_load_3d(dB, &tmB, full, tj * GX_BN, kb * GX_BK, bb);
                     if (++stage == GX_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -185,7 +195,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t fmt = p.amaxA ? UMMA_FMT_F16 : UMMA_FMT_BF16;
+            const uint32_t fmt = F16 ? UMMA_FMT_F16 : UMMA_FMT_BF16;
             const uint32_t idesc = umma_idesc_f16(GX_BN, fmt, fmt);
             int stage = 0;
             uint32_t phase = 0;
@@ -222,20 +232,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     } else if (warp < 2 + GX_CONV) {
         // ================= converters =================
         const int ct = threadIdx.x - 64;
-        const bool fp16 = p.amaxA != nullptr;
         int stage = 0;
         uint32_t phase = 0;
         for (long long w = blockIdx.x; w < p.n_work; w += gridDim.x) {
             const int b = (int)(w / tiles_per_batch);
-            const float scA = fp16 ? scalbnf(1.0f, gx_scale_exp(p.amaxA[p.a_batched ? b : 0])) : 1.0f;
-            const float scB = fp16 ? scalbnf(1.0f, gx_scale_exp(p.amaxB[p.b_batched ? b : 0])) : 1.0f;
+            const float scA = F16 ? scalbnf(1.0f, gx_scale_exp(p.amaxA[p.a_batched ? b : 0])) : 1.0f;
+            const float scB = F16 ? scalbnf(1.0f, gx_scale_exp(p.amaxB[p.b_batched ? b : 0])) : 1.0f;
             for (int kb = 0; kb < p.n_kb; ++kb) {
                 mbar_wait(bar_rfull + 8 * stage, phase);
                 mbar_wait(bar_oempty + 8 * stage, phase ^ 1);          // the MMAs that read this operand slot have retired
                 const uint8_t* raw = smem + stage * GX_RAW_STAGE;
                 uint8_t* op = smem + GX_OFF_OP + stage * GX_OP_STAGE;
-                gx_convert<GX_BM>(raw, op, op + GX_OP_A, p.a_kfast, ct, fp16, scA);
-                gx_convert<GX_BN>(raw + GX_RAW_A, op + 2 * GX_OP_A, op + 2 * GX_OP_A + GX_OP_B, p.b_kfast, ct, fp16, scB);
+                gx_convert<GX_BM, AK, F16>(raw, op, op + GX_OP_A, ct, scA);
+                gx_convert<GX_BN, BK, F16>(raw + GX_RAW_A, op + 2 * GX_OP_A, op + 2 * GX_OP_A + GX_OP_B, ct, scB);
                 fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) {
@@ -256,7 +265,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int o = to * GX_BM + q * 32 + lane;
             float* crow = p.C + (long long)b * p.c_sb + o;
             const float bias = (p.epi == 1 && o < p.O) ? p.bias[(long long)b * p.bias_sb + o] : 0.0f;
-            const float unscale = p.amaxA ? scalbnf(1.0f, -(gx_scale_exp(p.amaxA[p.a_batched ? b : 0]) + gx_scale_exp(p.amaxB[p.b_batched ? b : 0]))) : 1.0f;
+            const float unscale = F16 ? scalbnf(1.0f, -(gx_scale_exp(p.amaxA[p.a_batched ? b : 0]) + gx_scale_exp(p.amaxB[p.b_batched ? b : 0]))) : 1.0f;
             for (int c = 0; c < n_chunks; ++c, ++cidx) {
                 const uint32_t ab = cidx & 1u, aphase = (cidx >> 1) & 1u;
                 mbar_wait(bar_tfull + 8 * ab, aphase);
@@ -291,7 +300,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                 float val = __uint_as_float(v[jj]) * unscale;
                                 if (rmw) val += pre[jj];
                                 if (last) {
-                                    if (p.epi == 1) val = ssi_act(val + bias, p.act);
+                                    if (p.epi == 1) val = gx_act(val + bias, p.act);
                                     else if (p.epi == 2)
                                         val *= act_deriv_from_output(rmw ? hrow[(long long)(jb + jj) * p.c_sj] : pre[jj], p.act);
                                 }
@@ -421,9 +430,14 @@ int ssi_gemm_tc_try(ssi_ctx* ctx, const gemm_t& g, int batches, bool a_kfast, bo
     p.a_kfast = a_kfast ? 1 : 0; p.b_kfast = b_jfast ? 0 : 1;
     p.a_batched = a_b ? 1 : 0; p.b_batched = b_b ? 1 : 0;
     p.epi = g.epi; p.act = g.act; p.bias = g.bias; p.bias_sb = g.bias_sb; p.Hprev = g.Hprev; p.h_sb = g.h_sb;
-    SSI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, GX_SMEM));
+    typedef void (*gx_kernel_t)(const CUtensorMap, const CUtensorMap, const gemm_tc_params);
+    static const gx_kernel_t kernels[8] = {k_gemm_tc<false, false, false>, k_gemm_tc<false, false, true>, k_gemm_tc<false, true, false>,
+                                           k_gemm_tc<false, true, true>,   k_gemm_tc<true, false, false>, k_gemm_tc<true, false, true>,
+                                           k_gemm_tc<true, true, false>,   k_gemm_tc<true, true, true>};
+    const gx_kernel_t kern = kernels[(p.a_kfast ? 4 : 0) + (p.b_kfast ? 2 : 0) + (p.amaxA ? 1 : 0)];
+    SSI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GX_SMEM));
     const int grid = (int)std::min<long long>(ctx->sm_count, p.n_work);
-    k_gemm_tc<<<grid, GX_THREADS, GX_SMEM, ctx->stream>>>(mapA, mapB, p);
+    kern<<<grid, GX_THREADS, GX_SMEM, ctx->stream>>>(mapA, mapB, p);
     SSI_LAUNCH_CHECK(ctx);
     ++ctx->stats.gemm_tc_launches;
     *used = true;
