@@ -20,8 +20,10 @@
 //     behind it, so H is fetched once; FP32 accumulators in TMEM).  G = HH + HL + HL' drops only L L', 2^-24 relative.
 //     (BF16 planes were tried: their L L' term is 2^-18 of H H' and all-positive on the diagonal, so it must be kept,
 //     and accumulated next to H H' in FP32 a third of it was truncated away -- 3e-7 of lambda_0, measured.  Loading A
-//     with plain 16-byte loads straight into the operand layout -- no raw ring -- was tried too: 1.5 ms, bound by the
-//     latency of its own loads.)
+//     with plain 16-byte loads straight into registers -- no raw ring, 72 KB instead of 124 KB of shared-memory traffic per
+//     tile -- was tried twice: 1.5 ms with one tile in flight per warp, 1.31 ms with sixteen converter warps keeping two
+//     tiles ahead in three register buffers (53 KB per SM in flight): both bound by the latency of their own loads, where
+//     the TMA ring runs at 0.94 ms.)
 //   * FP32 accumulation in the tensor core truncates, so accumulators are drained every `chunk` tiles (1024 rows) into
 //     per-CTA FP64 partials (each thread owns its elements: plain load-add-store, no atomics) and reset; a final
 //     kernel sums the per-CTA partials in fixed order, symmetrises and undoes the scale.
