@@ -143,6 +143,43 @@ def test_gradient_wide_on_tensor_cores(ssi, engine):
     assert lp1[0] == lp[1]
 
 
+def test_mala_decisions_wide_reduced(ssi, engine):
+    """The :mala branch (src/space_inference.jl:117-120) on the wide network at N = 6000, value on the tensor path and
+    gradient through the tensor-core GEMM: teacher-forced from the device's own states, the Float64 oracle on the replayed
+    stream must propose the same point (up to the FP32-grade gradient in the drift) and take the same decision outside the
+    tie bands of the RWMH test above."""
+    prob = orc.make_problem("wide", N=6000)
+    _setup(engine, prob)
+    C, S, seed, sigma_z, sigma_m = 4, 4, 99, 4e-3, 0.5
+    before = engine.stats().gemm_tc_launches
+    zt, lt, at = engine.mala_run(C, S, seed, sigma_z=sigma_z, sigma_m=sigma_m, chain_offset=7)
+    assert engine.stats().gemm_tc_launches > before
+    t0 = time.time()
+    dec = flips = flips_fp32 = near = 0
+    for ci in range(C):
+        c = 7 + ci
+        z = zt[:, ci, :].T
+        for t in range(1, S):
+            lp_prev, g_prev = orc.density_and_grad(prob, z[t - 1].astype(np.float64), sigma_m)
+            zp = orc.mala_propose_f32(z[t - 1], g_prev, sigma_z, orc.rng_normals(seed, c, t, prob.M))
+            lp_prop, g_prop = orc.density_and_grad(prob, zp.astype(np.float64), sigma_m)
+            margin = orc.mala_log_alpha(z[t - 1], zp, lp_prev, lp_prop, g_prev, g_prop, sigma_z) + orc.rng_exponential(seed, c, t)
+            assert abs(lt[ci, t - 1] - lp_prev) <= 1e-6 * abs(lp_prev)
+            dec += 1
+            if abs(margin) <= TIE_BAND:
+                near += 1
+            if bool(at[ci, t]) != (margin > 0):
+                flips += abs(margin) > TIE_BAND
+                flips_fp32 += abs(margin) > FP32_BAND * abs(lp_prev)
+                continue
+            expect = zp if margin > 0 else z[t - 1]
+            drift = 0.5 * sigma_z ** 2 * np.abs(g_prev).max()
+            np.testing.assert_allclose(z[t], expect, rtol=0, atol=2e-4 * drift + np.abs(expect).max() * 2.4e-7 + 1e-12)
+    print(f"wide N=6000 MALA: {dec} decisions, {int(at[:, 1:].sum())} accepted, {flips} flips outside the absolute band, "
+          f"{flips_fp32} outside the FP32 band, {near} near ties ({time.time() - t0:.0f} s of oracle)")
+    assert dec >= 12 and flips_fp32 == 0
+
+
 def test_readme_literal_batchsize1_K1000(ssi):
     """BASELINE configs[0] as literally configured (README.md:59,74-79): DataLoader(X, Y, shuffle=true) is batchsize 1,
     so T = 10, c = 1 collect K = 1000 deviation columns for n = 682 parameters; opt = ADAM(0.1), M = 3."""
