@@ -54,7 +54,8 @@ def test_wide_subspaces(ssi, engine, n, K, M):
     assert _rel(orc.align_signs(Pd, P_ref), P_ref) < 2e-3
 
 
-@pytest.mark.parametrize("n,K,M", [(682, 15, 3), (1001, 40, 5), (4096, 100, 20), (37, 64, 4), (50000, 33, 20)])
+@pytest.mark.parametrize("n,K,M", [(682, 15, 3), (1001, 40, 5), (4096, 100, 20), (37, 64, 4), (50000, 33, 20),
+                                   (300, 1, 1), (300, 2, 2), (300, 3, 2), (2000, 129, 10), (2000, 160, 16)])   # eigen-solver edges: one pair, a bye, five rows per lane
 def test_random_snapshots_vs_oracle(ssi, engine, n, K, M):
     rng = np.random.default_rng(n * 1000 + K)
     w = rng.standard_normal(n) * 0.1
