@@ -370,7 +370,9 @@ int ssi_gemm_tc_try(ssi_ctx* ctx, const gemm_t& g, int batches, bool a_kfast, bo
     const int kind = (!a_kfast && !b_jfast) ? 1 : (!a_kfast && b_jfast) ? 2 : (a_kfast && !b_jfast) ? 4 : 8;
     if (ctx->opt_gemm_tc_mask && !(ctx->opt_gemm_tc_mask & kind)) return SSI_OK;
     if (g.O < 1 || g.J < 64 || g.K < 8 || g.K >= (1ll << 31)) return SSI_OK;
-    if ((double)g.O * g.J * (double)g.K * batches < 6.7e7) return SSI_OK;                 // launch + pipeline fill would dominate
+    // small problems: launch + pipeline fill would dominate.  Per batch, NOT per launch: which kernel evaluates a sample must
+    // not depend on how many other samples share the call (results are compared bitwise across batch compositions)
+    if ((double)g.O * g.J * (double)g.K < 1.6e7) return SSI_OK;
     // TMA: 16-byte aligned bases and strides
     if (a_kfast ? !(g.a_sk == 1 && gx_aligned(g.A, g.a_so)) : !(g.a_so == 1 && gx_aligned(g.A, g.a_sk))) return SSI_OK;
     if (b_jfast ? !(g.b_sj == 1 && gx_aligned(g.B, g.b_sk)) : !(g.b_sk == 1 && gx_aligned(g.B, g.b_sj))) return SSI_OK;

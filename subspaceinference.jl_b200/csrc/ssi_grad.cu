@@ -272,7 +272,7 @@ __global__ void k_gemm_skinny_gw_fin(const gemm_t p, const float* __restrict__ p
 static int gemm_skinny_try(ssi_ctx* ctx, const gemm_t& g, int batches, bool a_kfast, bool b_jfast, bool* used) {
     *used = false;
     if (ctx->opt_gemm_simt || g.split > 0 || g.c_so != 1 || batches < 1 || batches > 65535) return SSI_OK;
-    if (g.K >= (1ll << 31) || (double)g.O * g.J * (double)g.K * batches < 4e6) return SSI_OK;
+    if (g.K >= (1ll << 31) || (double)g.O * g.J * (double)g.K < 1e6) return SSI_OK;      // per batch: the choice must not depend on the batch size
     if (!a_kfast && !b_jfast && g.a_so == 1 && g.b_sk == 1 && g.O <= SK_MAXO && g.J >= 1024 && (size_t)g.O * g.K * 4 <= 160 * 1024) {
         const int jpb = 256;
         dim3 grid((g.J + jpb - 1) / jpb, batches);

@@ -164,6 +164,7 @@ def test_error_behaviour(ssi):
     ((33, 65, 17, 9, 4), (1, 2, 1, 0), 257, 6, 4),    # deeper chain
     ((96, 128, 128, 10), (1, 1, 0), 300, 20, 3),      # wide-ish chain: several tiles per GEMM, split projection
     ((96, 256, 192, 8), (1, 2, 0), 3000, 12, 3),      # big enough for the tensor-core GEMM: ragged tiles, 3 accumulation chunks
+    ((100, 132, 68, 8), (2, 1, 0), 1500, 6, 4),       # tensor-core GEMM with ragged rows (132 = 128 + 4), columns and k tails
 ])
 def test_gradient_vs_oracle(ssi, engine, dims, acts, N, M, B):
     """l_pi_grad (src/space_inference.jl:107) batched: value within 1e-5 relative, gradient within 1e-4 of its norm
@@ -191,7 +192,7 @@ def test_gradient_vs_oracle(ssi, engine, dims, acts, N, M, B):
         engine.set_option("path", ssi.PATH_AUTO)
         np.testing.assert_allclose(lp_f, lp_g, rtol=2e-6)
         np.testing.assert_allclose(g_f, g_g, rtol=0, atol=2e-4 * np.abs(g_g).max())
-    if dims == (96, 256, 192, 8):
+    if dims in ((96, 256, 192, 8), (100, 132, 68, 8)):
         # the large contractions ran on the tensor cores (ssi_gemm_tc.cu) and agree with the SIMT kernel
         assert engine.stats().gemm_tc_launches > 0
         lp_t, g_t = engine.logpost_grad(Z, 0.7, 1.3, 0.9, mask=1)
