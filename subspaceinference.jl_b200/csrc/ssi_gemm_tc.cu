@@ -51,6 +51,7 @@
 #define GX_OFF_BAR (GX_OFF_OP + GX_STAGES * GX_OP_STAGE)
 #define GX_NBAR (4 * GX_STAGES + 4)
 #define GX_SMEM (GX_OFF_BAR + GX_NBAR * 8 + 16)
+#define GX_EPW 16                                    // output columns per epilogue pass (loads of a pass are issued before their use)
 
 struct gemm_tc_params {
     const float* amaxA;          // device: largest |A| per batch (one entry when A is shared), NULL with BF16 planes.  Per batch, not per
@@ -275,27 +276,27 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const bool rmw = !first, deriv = last && p.epi == 2;
                 const float* hrow = deriv ? p.Hprev + (long long)b * p.h_sb + o : nullptr;
 #pragma unroll 1
-                for (int j0 = 0; j0 < GX_BN; j0 += 32) {
+                for (int j0 = 0; j0 < GX_BN; j0 += GX_EPW) {
                     const int jb = tj * GX_BN + j0;
                     if (jb >= p.J) break;                                    // warp-uniform
                     // everything this pass reads from global memory is requested before the first use: 32 (64) independent
                     // loads per thread instead of a load -> add -> store chain per element
                     // (one array: a pass that needs both the running sum and the layer output -- an activation derivative
                     // after a contraction longer than one chunk -- takes the output late)
-                    float pre[32];
+                    float pre[GX_EPW];
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
+                    for (int jj = 0; jj < GX_EPW; ++jj) {
                         const bool ok = o < p.O && jb + jj < p.J;
                         const float* src = rmw ? crow : hrow;
                         pre[jj] = ((rmw || deriv) && ok) ? src[(long long)(jb + jj) * p.c_sj] : 0.0f;
                     }
-                    uint32_t v[32];
+                    uint32_t v[GX_EPW];
                     tmem_ld16(taddr + j0, v);
-                    tmem_ld16(taddr + j0 + 16, v + 16);
+                    if (GX_EPW > 16) tmem_ld16(taddr + j0 + 16, v + (GX_EPW > 16 ? 16 : 0));
                     tmem_ld_wait();
                     if (o < p.O) {
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) {
+                        for (int jj = 0; jj < GX_EPW; ++jj) {
                             if (jb + jj < p.J) {
                                 float val = __uint_as_float(v[jj]) * unscale;
                                 if (rmw) val += pre[jj];
