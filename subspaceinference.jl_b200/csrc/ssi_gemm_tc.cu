@@ -11,10 +11,11 @@
 //     arrive as [rows][32 k] with 128-byte swizzle, o- / j-fast tiles as [32 k][rows]); edges are zero-filled by TMA;
 //   * eight converter warps split every raw tile into two 16-bit planes in the K-major SWIZZLE_64B operand layout
 //     (transposing the o- / j-fast tiles on the way; both access patterns are conflict-free).  Default: FP16 planes
-//     hi = fp16(s x), lo = fp16(s x - hi) with ONE power-of-two scale s per operand and launch that puts the operand's
-//     largest magnitude at 2^14 (a strided absmax pre-pass, k_gemm_absmax): 11 + 11 bits, operands exact to 2^-22 of
-//     their largest element -- FP32-grade.  Option gemm_prec = 0: BF16 planes without scale or pre-pass (8 + 8 bits: the
-//     forward pass then carries 2^-17 per operand, 5e-5 of the gradient norm on the test shapes);
+//     hi = fp16(s x), lo = fp16(s x - hi) with one power-of-two scale s per operand AND BATCH that puts that batch's
+//     largest magnitude at 2^14 (a strided absmax pre-pass, k_gemm_absmax; per batch so that a sample's result cannot
+//     depend on what else is in the launch): 11 + 11 bits for everything within 2^-17 of the largest element.  Option
+//     gemm_prec = 0: BF16 planes without scale or pre-pass (8 + 8 bits: the forward pass then carries 2^-17 per operand,
+//     5e-5 of the gradient norm on the test shapes).  Orientation and plane format are template parameters;
 //   * one thread issues  D += Al Bh' + Ah Bl' + Ah Bh'  (tcgen05.mma kind::f16, M = 128, N = 256, FP32 accumulators in
 //     TMEM, two accumulator buffers);
 //   * four epilogue warps drain an accumulator every `chunk` k-blocks (1024 k): the tensor core's FP32 accumulation
@@ -26,7 +27,8 @@
 //
 // Shared memory per k-block: 48 KB raw + 48 KB of plane writes + 48 KB converter reads + 72 KB operand fetches: the
 // kernel is bound by the shared-memory pipe, not by the tensor pipe.  Requirements (else the caller
-// falls back to the SIMT kernel): 16-byte aligned bases and strides, c_so == 1, no split-K.
+// falls back to the SIMT kernel): 16-byte aligned bases and strides, c_so == 1, no split-K, at least 1.6e7 multiply-adds per
+// batch (the choice never depends on the number of batches).
 #include "ssi_common.cuh"
 #include "ssi_ptx.cuh"
 #include "ssi_gemm.cuh"
