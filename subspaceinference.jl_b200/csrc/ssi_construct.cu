@@ -871,21 +871,24 @@ __global__ void k_pack_v(const double* __restrict__ V, const int* __restrict__ o
 
 // P = A V_M as a stream through shared memory.  Per row of P the kernel spends K * M multiply-adds on 4 K bytes of A
 // (50 flop/B at K = 100, M = 20): on CUDA cores the FMA pipe and HBM are busy to the same degree, so the loads must not
-// cost the compute warps a single stall.  A TMA producer warp therefore keeps a ring of 5 stages (8 columns x 1024 rows
-// of A each) in flight, and the 8 compute warps -- 4 consecutive rows x MP outputs per thread, 80 accumulators for
+// cost the compute warps a single stall.  A TMA producer warp therefore keeps a ring of 5 stages (8 columns x 256 rows
+// of A each) in flight, and the 2 compute warps of a CTA -- 4 consecutive rows x MP outputs per thread, 80 accumulators for
 // MP = 20 -- read their operands from shared memory only: one 16-byte load of A and MP / 4 broadcast loads of V per 4 MP
-// FMAs.  What bounds it now is instruction issue (ncu: 70 % of the issue slots, FMA pipe 59 %, DRAM 60 %); packed FFMA2 with V
-// duplicated in shared memory was measured and is slower (twice the V loads for the same FMA-pipe time).  (Round 1 loaded A straight from global memory into registers with V in the constant bank: 124 registers per
-// thread left 16 warps per SM to cover DRAM latency, 71 % of the HBM peak with the FMA pipe half idle; and the
+// FMAs.  FOUR small CTAs per SM rather than one large one: a CTA's tile-boundary epilogue and barrier waits overlap with
+// the main loops of the other three (one CTA with 8 / 10 / 12 compute warps: 0.977 / 1.056 / 0.987 ms; two CTAs of 4:
+// 0.958 ms; four of 2: 0.944 ms).  What bounds it is instruction issue (ncu: 70 % of the issue slots, FMA pipe 59 %, DRAM
+// 60 %); packed FFMA2 with V duplicated in shared memory was measured and is slower (twice the V loads for the same
+// FMA-pipe time).  (Round 1 loaded A straight from global memory into registers with V in the constant bank: 124
+// registers per thread left 16 warps per SM to cover DRAM latency, 71 % of the HBM peak with the FMA pipe half idle; and the
 // module-global constant bank was shared by every context of a device.)  V lives in this CTA's shared memory now.
-#define FP_ROWS 1024
+#define FP_ROWS 256
 #define FP_KC 8
 #define FP_STAGES 5
 #define FP_STAGE_BYTES (FP_KC * FP_ROWS * 4)
-#define FP_COMPUTE 256
+#define FP_COMPUTE 64
 #define FP_THREADS (FP_COMPUTE + 32)
 template <int MP>
-__global__ void __launch_bounds__(FP_THREADS, 1)
+__global__ void __launch_bounds__(FP_THREADS, 4)
 k_form_p_tma(const __grid_constant__ CUtensorMap tmA /* {n, K} FP32, box {256 rows, FP_KC columns} */, const float* __restrict__ Vp /* [Kpad][MP] */,
              long long n, int Kpad, int M, float* __restrict__ P, int n_tiles) {
     extern __shared__ __align__(1024) uint8_t fp_smem[];
@@ -1039,7 +1042,7 @@ static int launch_form_p(ssi_ctx* ctx, const float* dA, int64_t n, int64_t ld, i
         SSI_LAUNCH_CHECK(ctx);
         const int n_tiles = (int)((n + FP_ROWS - 1) / FP_ROWS);
         SSI_CUDA(ctx, cudaFuncSetAttribute(k_form_p_tma<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
-        k_form_p_tma<MP><<<std::min(ctx->sm_count, n_tiles), FP_THREADS, smem_tma, ctx->stream>>>(map, stage, n, Kpad, M, dP, n_tiles);
+        k_form_p_tma<MP><<<std::min(4 * ctx->sm_count, n_tiles), FP_THREADS, smem_tma, ctx->stream>>>(map, stage, n, Kpad, M, dP, n_tiles);
         SSI_LAUNCH_CHECK(ctx);
         return SSI_OK;
     }
