@@ -50,7 +50,7 @@ def train_section(eng, stream, dims=(784, 2048, 2048, 2048, 10), N=8192, nb=512,
     flops = 3.0 * nb * 2.0 * sum(dims[l] * dims[l + 1] for l in range(len(dims) - 1))
     return {"model": "-".join(map(str, dims)), "n": n, "batch": nb, "optimiser": "ADAM", "step_plus_snapshot_ms": ms,
             "tflops_fp32": flops / (ms * 1e-3) / 1e12, "host_step_ms": host_ms, "host_threads": torch.get_num_threads(),
-            "note": "device: SIMT FP32 GEMMs (correctness-first 'next' row); host: torch CPU autograd + snapshot copy not included"}
+            "note": "device: forward/backward GEMMs on the tensor cores where the shape qualifies (ssi_gemm_tc.cu), else SIMT FP32; host: torch CPU autograd + snapshot copy not included"}
 
 
 def main():
