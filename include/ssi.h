@@ -125,7 +125,7 @@ int  ssi_sync(ssi_ctx* ctx);
  * "tc_k32", "tc_pair" (1 = CTA pairs with cta_group::2, the default), "b1_simt", "bm_nopack", "bm_variant", "gram_fp64",
  * "gram_chunk", "eig_cluster" (1 = dataflow cluster solver, default; 2 = cluster solver with a barrier per round; 0 = one
  * CTA), "formp_simt", "gemm_simt" (1 = gradient / training GEMMs on the SIMT kernel), "gemm_prec" (tensor-core GEMM planes:
- * 1 = FP16 with per-sample scales, default; 0 = BF16), "gemm_chunk", "gemm_tc_mask" (see DESIGN.md); "time_dominant" (0/1)
+ * 1 = FP16 with per-sample scales, default; 0 = BF16), "gemm_split_acc", "gemm_fwd_chunk", "gemm_chunk", "gemm_tc_mask" (see DESIGN.md); "time_dominant" (0/1)
  * brackets every launch of the path's dominant kernel with CUDA events (ssi_stats_t.dominant_ms) */
 int  ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value);
 int  ssi_stats(const ssi_ctx* ctx, ssi_stats_t* out);

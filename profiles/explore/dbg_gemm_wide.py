@@ -12,6 +12,7 @@ ref = [orc.density_and_grad(prob, Z[:, b].astype(np.float64), sigma_m) for b in 
 gref = np.stack([r[1] for r in ref], axis=1)
 def err(g): return np.max(np.linalg.norm(g - gref, axis=0) / np.linalg.norm(gref, axis=0))
 eng.set_option("gemm_simt", 1); print("simt", err(eng.logpost_grad(Z, sigma_m)[1])); eng.set_option("gemm_simt", 0)
-for mask, chunk, prec in ((0, 32, 1), (0, 16, 1), (0, 8, 1), (0, 4, 1), (0, 2, 1), (1, 8, 1), (6, 8, 1)):
-    eng.set_option("gemm_tc_mask", mask); eng.set_option("gemm_chunk", chunk); eng.set_option("gemm_prec", prec)
-    print("mask", mask, "chunk", chunk, "prec", prec, err(eng.logpost_grad(Z, sigma_m)[1]))
+eng.set_option("gemm_split_acc", 2)
+for fc in (32, 16, 8, 4):
+    eng.set_option("gemm_fwd_chunk", fc)
+    print("split_acc 2 fwd_chunk", fc, err(eng.logpost_grad(Z, sigma_m)[1]))

@@ -275,6 +275,8 @@ int ssi_set_option(ssi_ctx* ctx, const char* key, int64_t value) {
     if (!strcmp(key, "grad_group_gb")) { ctx->opt_grad_group_gb = (int)value; return SSI_OK; }
     if (!strcmp(key, "gemm_tc_mask")) { ctx->opt_gemm_tc_mask = (int)value; return SSI_OK; }
     if (!strcmp(key, "gemm_prec")) { ctx->opt_gemm_prec = (int)value; return SSI_OK; }
+    if (!strcmp(key, "gemm_split_acc")) { ctx->opt_gemm_split_acc = (int)value; return SSI_OK; }
+    if (!strcmp(key, "gemm_fwd_chunk")) { ctx->opt_gemm_fwd_chunk = (int)value; return SSI_OK; }
     if (!strcmp(key, "gemm_simt")) { ctx->opt_gemm_simt = value != 0; return SSI_OK; }
     if (!strcmp(key, "gemm_chunk")) { ctx->opt_gemm_chunk = (int)value; return SSI_OK; }
     if (!strcmp(key, "mala_rule")) { if (value != 0 && value != 1) return ssi_fail(ctx, SSI_ERR_ARG, "mala_rule must be 0 or 1"); ctx->opt_mala_rule = (int)value; return SSI_OK; }

@@ -65,6 +65,8 @@ struct ssi_ctx {
     int opt_grad_group_gb = 0; // scratch budget (GB) of the generic gradient path per group of samples (default 6)
     int opt_gemm_tc_mask = 0; // 0 all; else which GEMM orientations may use the tensor cores (see ssi_gemm_tc.cu)
     int opt_gemm_prec = 1;    // tensor-core GEMM planes: 1 FP16 with a per-operand scale (FP32-grade), 0 BF16 (no pre-pass)
+    int opt_gemm_split_acc = 2; // tensor-core GEMM: separate accumulator for the small terms: 2 forward layers only (default), 1 all, 0 none
+    int opt_gemm_fwd_chunk = 0; // accumulation chunk (k-blocks) of the forward layers when their accumulators are split
     int opt_gemm_simt = 0;    // 1: keep the gradient / training GEMMs on the SIMT kernel (A-B against ssi_gemm_tc.cu)
     int opt_gemm_chunk = 0;   // k-blocks (32 k) per FP32 accumulation chunk of the tensor-core GEMM (default 32)
     int opt_mala_rule = 0;    // 0 textbook MALA ratio, 1 negated-gradient proposal densities (see ssi_api.cu)

@@ -17,7 +17,13 @@
 //     gemm_prec = 0: BF16 planes without scale or pre-pass (8 + 8 bits: the forward pass then carries 2^-17 per operand,
 //     5e-5 of the gradient norm on the test shapes).  Orientation and plane format are template parameters;
 //   * one thread issues  D += Al Bh' + Ah Bl' + Ah Bh'  (tcgen05.mma kind::f16, M = 128, N = 256, FP32 accumulators in
-//     TMEM, two accumulator buffers);
+//     TMEM, two accumulator buffers).  The forward layers (bias + activation epilogue) keep the two small terms in an
+//     accumulator of their own: they are 2^-11 of the large term, and added into the same truncating accumulator they
+//     lose the bits below the running sum's ulp -- most of what the lo planes carry.  That, not the length of the
+//     accumulation, was the 3.7e-5 of the gradient norm the first version of this kernel showed on the wide network
+//     (FP32 FMA chains: 1.8e-5; with the split: 1.35e-5).  It costs the double buffering of those launches (+7 % on the
+//     whole gradient), so the backward GEMMs, whose results are sums the error averages out of, do without
+//     (option gemm_split_acc: 2 forward only, 1 all, 0 none);
 //   * four epilogue warps drain an accumulator every `chunk` k-blocks (1024 k): the tensor core's FP32 accumulation
 //     truncates, so a long contraction (the weight gradient runs over all N datapoints) is summed in FP32 through the
 //     output tile itself (each tile has one owner: plain read-add-write), and the last chunk applies the epilogue
@@ -65,6 +71,7 @@ struct gemm_tc_params {
     int n_kb, chunk;             // k-blocks of 32; k-blocks per accumulation chunk
     int a_kfast, b_kfast;
     int a_batched, b_batched;
+    int split_acc;               // 1: small terms (Al Bh' + Ah Bl') and the large term in separate accumulators (no double buffering)
     int epi, act;
     const float* bias; long long bias_sb;
     const float* Hprev; long long h_sb;
@@ -206,10 +213,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (long long w = blockIdx.x; w < p.n_work; w += gridDim.x) {
                 int kb = 0;
                 for (int c = 0; c < n_chunks; ++c, ++cidx) {
-                    const uint32_t ab = cidx & 1u, aphase = (cidx >> 1) & 1u;
+                    // split_acc: both buffers belong to this chunk (large term in 0, small terms in 1), each used every chunk
+                    const uint32_t ab = p.split_acc ? 0u : (cidx & 1u), aphase = p.split_acc ? (cidx & 1u) : ((cidx >> 1) & 1u);
                     mbar_wait(bar_tempty + 8 * ab, aphase ^ 1);
+                    if (p.split_acc) mbar_wait(bar_tempty + 8, aphase ^ 1);
                     tc_fence_after();
                     const uint32_t d_acc = tmem_base + ab * 256;
+                    const uint32_t d_small = p.split_acc ? tmem_base + 256 : d_acc;
                     const int kb_end = min(p.n_kb, (c + 1) * p.chunk);
                     for (bool first = true; kb < kb_end; ++kb) {
                         mbar_wait(bar_ofull + 8 * stage, phase);
@@ -220,9 +230,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                         for (int ks = 0; ks < GX_BK / 16; ++ks) {
                             const uint64_t ko = (uint64_t)(ks * 32 >> 4);      // 16 BF16 = 32 bytes per k-step inside the 64-byte row
-                            umma_bf16(d_acc, dAl + ko, dBh + ko, idesc, first ? 0u : 1u);
-                            umma_bf16(d_acc, dAh + ko, dBl + ko, idesc, 1u);
-                            umma_bf16(d_acc, dAh + ko, dBh + ko, idesc, 1u);
+                            umma_bf16(d_small, dAl + ko, dBh + ko, idesc, first ? 0u : 1u);
+                            umma_bf16(d_small, dAh + ko, dBl + ko, idesc, 1u);
+                            umma_bf16(d_acc, dAh + ko, dBh + ko, idesc, (first && p.split_acc) ? 0u : 1u);
                             first = false;
                         }
                         umma_commit(bar_oempty + 8 * stage);
@@ -270,7 +280,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const float bias = (p.epi == 1 && o < p.O) ? p.bias[(long long)b * p.bias_sb + o] : 0.0f;
             const float unscale = F16 ? scalbnf(1.0f, -(gx_scale_exp(p.amaxA[p.a_batched ? b : 0]) + gx_scale_exp(p.amaxB[p.b_batched ? b : 0]))) : 1.0f;
             for (int c = 0; c < n_chunks; ++c, ++cidx) {
-                const uint32_t ab = cidx & 1u, aphase = (cidx >> 1) & 1u;
+                const uint32_t ab = p.split_acc ? 0u : (cidx & 1u), aphase = p.split_acc ? (cidx & 1u) : ((cidx >> 1) & 1u);
                 mbar_wait(bar_tfull + 8 * ab, aphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
@@ -296,6 +306,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     tmem_ld16(taddr + j0, v);
                     if (GX_EPW > 16) tmem_ld16(taddr + j0 + 16, v + (GX_EPW > 16 ? 16 : 0));
                     tmem_ld_wait();
+                    if (p.split_acc) {                       // add the small-term accumulator (FP32, round to nearest)
+                        uint32_t v2[16];
+                        tmem_ld16(taddr + 256 + j0, v2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(v2[jj]));
+                    }
                     if (o < p.O) {
 #pragma unroll
                         for (int jj = 0; jj < GX_EPW; ++jj) {
@@ -314,6 +331,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
                 tc_fence_before();
                 mbar_arrive(bar_tempty + 8 * ab);
+                if (p.split_acc) mbar_arrive(bar_tempty + 8);
             }
         }
     }
@@ -434,6 +452,8 @@ int ssi_gemm_tc_try(ssi_ctx* ctx, const gemm_t& g, int batches, bool a_kfast, bo
     p.chunk = ctx->opt_gemm_chunk > 0 ? ctx->opt_gemm_chunk : 32;
     p.a_kfast = a_kfast ? 1 : 0; p.b_kfast = b_jfast ? 0 : 1;
     p.a_batched = a_b ? 1 : 0; p.b_batched = b_b ? 1 : 0;
+    p.split_acc = (ctx->opt_gemm_split_acc == 1 || (ctx->opt_gemm_split_acc == 2 && g.epi == 1)) ? 1 : 0;
+    if (p.split_acc && g.epi == 1 && ctx->opt_gemm_fwd_chunk > 0) p.chunk = ctx->opt_gemm_fwd_chunk;
     p.epi = g.epi; p.act = g.act; p.bias = g.bias; p.bias_sb = g.bias_sb; p.Hprev = g.Hprev; p.h_sb = g.h_sb;
     typedef void (*gx_kernel_t)(const CUtensorMap, const CUtensorMap, const gemm_tc_params);
     static const gx_kernel_t kernels[8] = {k_gemm_tc<false, false, false>, k_gemm_tc<false, false, true>, k_gemm_tc<false, true, false>,

@@ -111,9 +111,8 @@ def test_tensor_path_mh_decisions_full_c3(ssi, engine):
 def test_gradient_wide_on_tensor_cores(ssi, engine):
     """l_pi_grad (src/space_inference.jl:107) on the wide network at N = 6000: the reverse pass runs its large
     contractions on the tensor cores (ssi_gemm_tc.cu, FP16 planes with per-sample scales) and must match the Float64
-    oracle to the bar of the generic gradient test (1e-4 of the gradient norm; the FP32 CUDA-core pass is at 1.8e-5 here, the
-    tensor-core pass at 3.7e-5: its FP32 accumulation truncates where an FMA chain rounds); the value it returns is the
-    density's value."""
+    oracle as well as the FP32 CUDA-core pass does (1.7e-5 of the gradient norm here; 8.4e-5 before the forward layers got a
+    separate accumulator for their small terms); the value it returns is the density's value."""
     prob = orc.make_problem("wide", N=6000)
     _setup(engine, prob)
     rng = np.random.default_rng(11)
@@ -135,7 +134,7 @@ def test_gradient_wide_on_tensor_cores(ssi, engine):
         assert abs(lp[b] - lp_ref) <= 1e-6 * abs(lp_ref)
     print(f"wide N=6000 gradient: tensor cores {worst:.2e}, CUDA cores {worst_s:.2e} of the gradient norm; "
           f"lp vs density call {np.max(np.abs(lp - lp_d) / np.abs(lp_d)):.1e}")
-    assert worst < 1e-4
+    assert worst < 5e-5 and worst < 2.5 * worst_s
     np.testing.assert_allclose(lp, lp_d, rtol=1e-6)
     # a sample's gradient does not depend on what else is in the batch (per-sample scales)
     lp1, g1 = engine.logpost_grad(Z[:, 1:2], sigma_m)
