@@ -59,7 +59,7 @@
 #define GX_OFF_BAR (GX_OFF_OP + GX_STAGES * GX_OP_STAGE)
 #define GX_NBAR (4 * GX_STAGES + 4)
 #define GX_SMEM (GX_OFF_BAR + GX_NBAR * 8 + 16)
-#define GX_EPW 16                                    // output columns per epilogue pass (loads of a pass are issued before their use)
+#define GX_EPW 16                                    // output columns per epilogue pass (= one tcgen05.ld of 16 columns)
 
 struct gemm_tc_params {
     const float* amaxA;          // device: largest |A| per batch (one entry when A is shared), NULL with BF16 planes.  Per batch, not per
@@ -287,24 +287,31 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const bool first = c == 0, last = c == n_chunks - 1;
                 const bool rmw = !first, deriv = last && p.epi == 2;
                 const float* hrow = deriv ? p.Hprev + (long long)b * p.h_sb + o : nullptr;
+                // Everything a pass reads from global memory (the running sum of a chunked contraction, or the layer output an
+                // activation derivative is taken from) is requested one pass AHEAD: sixteen independent loads per thread are
+                // in flight while the previous sixteen columns are processed, instead of a load -> add -> store chain per
+                // element.  (One array: a pass that needs both -- a derivative after a contraction longer than one chunk --
+                // takes the layer output late.)
+                const float* src = rmw ? crow : hrow;
+                const bool need = (rmw || deriv) && o < p.O;
+                float nxt[GX_EPW];
+#pragma unroll
+                for (int jj = 0; jj < GX_EPW; ++jj)
+                    nxt[jj] = (need && tj * GX_BN + jj < p.J) ? src[(long long)(tj * GX_BN + jj) * p.c_sj] : 0.0f;
 #pragma unroll 1
                 for (int j0 = 0; j0 < GX_BN; j0 += GX_EPW) {
                     const int jb = tj * GX_BN + j0;
                     if (jb >= p.J) break;                                    // warp-uniform
-                    // everything this pass reads from global memory is requested before the first use: 32 (64) independent
-                    // loads per thread instead of a load -> add -> store chain per element
-                    // (one array: a pass that needs both the running sum and the layer output -- an activation derivative
-                    // after a contraction longer than one chunk -- takes the output late)
                     float pre[GX_EPW];
 #pragma unroll
-                    for (int jj = 0; jj < GX_EPW; ++jj) {
-                        const bool ok = o < p.O && jb + jj < p.J;
-                        const float* src = rmw ? crow : hrow;
-                        pre[jj] = ((rmw || deriv) && ok) ? src[(long long)(jb + jj) * p.c_sj] : 0.0f;
+                    for (int jj = 0; jj < GX_EPW; ++jj) pre[jj] = nxt[jj];
+                    if (j0 + GX_EPW < GX_BN) {
+#pragma unroll
+                        for (int jj = 0; jj < GX_EPW; ++jj)
+                            nxt[jj] = (need && jb + GX_EPW + jj < p.J) ? src[(long long)(jb + GX_EPW + jj) * p.c_sj] : 0.0f;
                     }
                     uint32_t v[GX_EPW];
                     tmem_ld16(taddr + j0, v);
-                    if (GX_EPW > 16) tmem_ld16(taddr + j0 + 16, v + (GX_EPW > 16 ? 16 : 0));
                     tmem_ld_wait();
                     if (p.split_acc) {                       // add the small-term accumulator (FP32, round to nearest)
                         uint32_t v2[16];
